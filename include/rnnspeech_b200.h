@@ -1,0 +1,181 @@
+/*
+ * rnnspeech_b200 -- C ABI of the B200-native acoustic-model hot path
+ * (features -> LSTM stack fwd/bwd -> CTC loss/grad/decode -> clip + Adam).
+ *
+ * The reference (domerin0/rnn-speech) is pure Python on TensorFlow-1 + librosa
+ * and has NO FFI of its own for this path: the "interface each entry point
+ * replaces" is therefore the Python method / TF op the reference calls, cited
+ * as file:line relative to the reference root.  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative rs_status on error;
+ *     rs_last_error() returns a thread-local message for the last failure;
+ *   - all `*_d` / data pointers are DEVICE pointers owned by the caller
+ *     (e.g. torch tensors' data_ptr()); the library never allocates device
+ *     memory: scratch is passed in, sized by the matching *_workspace_bytes;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it
+ *     and nothing synchronises the host unless stated;
+ *   - thread-compatible: no internal threads, no global mutable state beyond
+ *     the thread-local error string;  one process per GPU rank;
+ *   - no CPU fallback: every entry point needs an sm_100 device.
+ */
+#ifndef RNNSPEECH_B200_H_
+#define RNNSPEECH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RS_OK = 0,
+  RS_ERR_INVALID = -1,      /* bad argument (reference: ValueError / InvalidArgumentError) */
+  RS_ERR_CUDA = -2,         /* CUDA runtime error, message holds cudaGetErrorString */
+  RS_ERR_UNSUPPORTED = -3,  /* shape outside what the kernels support */
+  RS_ERR_WORKSPACE = -4     /* workspace / reserve buffer too small */
+} rs_status;
+
+int rs_version(void);
+const char* rs_last_error(void);
+/* Number of SMs of the current device (grid sizing is a multiple of this). */
+int rs_sm_count(void);
+/* Number of kernels this library has launched in this process so far. */
+uint64_t rs_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * (a) Feature extraction.  Replaces AudioProcessor.process_signal(sig, sr)
+ *     -> _extract_fbank / _extract_mfcc, util/audioprocessor.py:52-161, for a
+ *     whole batch of utterances in one call, and the padded-batch contract of
+ *     AcousticModel.build_dataset (models/AcousticModel.py:809-827) plus the
+ *     time-major transpose of create_training_rnn (:147-152).
+ *
+ *   pcm_d      float32 PCM, utterances concatenated
+ *   offsets_d  int64[B+1] sample offsets into pcm_d (utterance b = [off[b], off[b+1]))
+ *   max_samples  host copy of the longest utterance length (grid sizing)
+ *   sr         sample rate; frame = round(.025 sr), hop = round(.01 sr)
+ *   Tmax       max_input_seq_length: frames >= Tmax are dropped, rows
+ *              [nframes, Tmax) are zero-filled
+ *   delta_mode RS_DELTA_INTERP (librosa >= 0.6.1, savgol 'interp') or
+ *              RS_DELTA_EDGE (librosa <= 0.6.0, edge replicate, /20)
+ *   time_major 0: out is [B, Tmax, F]   1: out is [Tmax, B, F]
+ *   out_d      float32 features, F = 120 (fbank) / n_mfcc (mfcc)
+ *   nframes_d  int32[B]: PRE-truncation frame count (the reference's
+ *              `length` return value, util/audioprocessor.py:156-161)
+ * ------------------------------------------------------------------------ */
+#define RS_DELTA_INTERP 0
+#define RS_DELTA_EDGE 1
+#define RS_FBANK_DIM 120
+
+size_t rs_fbank_workspace_bytes(int B, int64_t max_samples, int sr);
+/* ceil(|n - round(.025 sr)| / round(.01 sr)): util/audioprocessor.py:92 */
+int64_t rs_fbank_num_frames(int64_t n_samples, int sr);
+/* host-only: the mel weights [40*257] / Hamming window [512] the kernels use (CPU tests) */
+int rs_fbank_tables_host(int sr, float* melw_out, float* window_out, int* frame_length, int* frame_step);
+int rs_fbank_forward(const float* pcm_d, const int64_t* offsets_d, int B, int64_t max_samples,
+                     int sr, int Tmax, int delta_mode, int time_major,
+                     float* out_d, int32_t* nframes_d, void* ws_d, size_t ws_bytes, void* stream);
+
+size_t rs_mfcc_workspace_bytes(int B, int64_t max_samples, int sr);
+/* 1 + n / round(.01 sr)  (librosa stft, center=True) */
+int64_t rs_mfcc_num_frames(int64_t n_samples, int sr);
+int rs_mfcc_forward(const float* pcm_d, const int64_t* offsets_d, int B, int64_t max_samples,
+                    int sr, int Tmax, int n_mfcc, int time_major,
+                    float* out_d, int32_t* nframes_d, void* ws_d, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * (b) Acoustic model: input dense -> L x LSTM (TF BasicLSTMCell semantics,
+ *     gate order i,j,f,o, forget_bias 1.0, per-step in/out dropout,
+ *     dynamic_rnn sequence-length masking, persistent state in/out) ->
+ *     output dense.  Replaces AcousticModel._build_base_rnn
+ *     (models/AcousticModel.py:189-317) and the BPTT half of
+ *     _add_training_on_rnn (:386-401).
+ *
+ *   params_d   float32 flat parameter buffer, TF variable layouts in the
+ *              reference's checkpoint order (models/AcousticModel.py:515-527):
+ *              input_w[F,H] input_b[H] {kernel_l[2H,4H] bias_l[4H]}xL
+ *              output_w[H,C] output_b[C]
+ *   x_d        float32 [T, B, F] time-major features
+ *   len_d      int32 [B] valid frames per item (0 allowed)
+ *   state_in_d / state_out_d   float32 [L, 2, B, H] (c then h per layer);
+ *              state_in_d may be NULL (zeros); state_out_d may be NULL or
+ *              alias state_in_d
+ *   keep_in / keep_out  dropout keep probabilities (1.0 = identity)
+ *   seed       dropout seed for this call (masks = f(seed, layer, t, b, h))
+ *   logits_d   float32 [T, B, C]
+ *   reserve_d  activations kept for backward (NULL => inference, nothing saved)
+ *   grads_d    float32 flat buffer, same layout as params_d; backward
+ *              ACCUMULATES (+=) into it (the reference's accumulate_gradients_op,
+ *              models/AcousticModel.py:392-401)
+ * ------------------------------------------------------------------------ */
+typedef struct rs_am rs_am;
+
+int rs_am_create(rs_am** out, int num_layers, int hidden_size, int input_dim, int num_labels,
+                 int batch_size, int max_T);
+void rs_am_destroy(rs_am* am);
+int64_t rs_am_param_count(const rs_am* am);
+/* offset (in floats) of a named variable inside the flat buffer: which = 0 input_w,
+ * 1 input_b, 2 kernel (layer), 3 bias (layer), 4 output_w, 5 output_b */
+int64_t rs_am_param_offset(const rs_am* am, int which, int layer);
+size_t rs_am_reserve_bytes(const rs_am* am);
+size_t rs_am_workspace_bytes(const rs_am* am);
+int rs_am_forward(rs_am* am, const float* params_d, const float* x_d, const int32_t* len_d, int T,
+                  const float* state_in_d, float* state_out_d,
+                  float keep_in, float keep_out, uint64_t seed,
+                  float* logits_d, void* reserve_d, void* ws_d, size_t ws_bytes, void* stream);
+/* Measurement hooks: when enabled, CUDA events are recorded on the launch stream around
+ * each recurrent kernel; rs_am_recurrent_ms returns the last duration (synchronises on
+ * that event only).  backward = 0 | 1. */
+int rs_am_enable_timing(rs_am* am, int enable);
+int rs_am_recurrent_ms(rs_am* am, int backward, int layer, float* ms);
+/* keep_in / keep_out / seed must repeat the values given to the matching forward
+ * (the dropout masks are recomputed, not stored).  The reserve is consumed:
+ * one backward per forward. */
+int rs_am_backward(rs_am* am, const float* params_d, const float* x_d, const int32_t* len_d, int T,
+                   float keep_in, float keep_out, uint64_t seed,
+                   const float* dlogits_d, void* reserve_d, float* grads_d,
+                   void* ws_d, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * (c) CTC.  Replaces tf.nn.ctc_loss(sparse_labels, logits, seq_len,
+ *     ignore_longer_outputs_than_inputs=True) (models/AcousticModel.py:357)
+ *     including its gradient, and provides the greedy decode the north star
+ *     names as the prediction parity surface (:312-314).
+ *
+ *   logits_d   float32 [T, B, C] time-major, softmax applied inside
+ *   labels_d   int32, label sequences concatenated; label_offsets_d int32[B+1]
+ *   len_d      int32[B]
+ *   blank      blank index (reference: C-1 = 79)
+ *   beta_skip  RS_CTC_BETA_SOURCE (TF rule, default) / RS_CTC_BETA_DEST
+ *   loss_d     float32[B];  grad_d float32 [T,B,C] or NULL (loss only)
+ * ------------------------------------------------------------------------ */
+#define RS_CTC_BETA_SOURCE 0
+#define RS_CTC_BETA_DEST 1
+
+size_t rs_ctc_workspace_bytes(int T, int B, int C, int max_label_len);
+int rs_ctc_loss_grad(const float* logits_d, const int32_t* labels_d, const int32_t* label_offsets_d,
+                     const int32_t* len_d, int T, int B, int C, int max_label_len, int blank,
+                     int beta_skip, float* loss_d, float* grad_d,
+                     void* ws_d, size_t ws_bytes, void* stream);
+/* out_d int32 [B, T] (decoded ids, row-padded with -1), out_len_d int32 [B] */
+int rs_ctc_greedy_decode(const float* logits_d, const int32_t* len_d, int T, int B, int C, int blank,
+                         int32_t* out_d, int32_t* out_len_d, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Update rule.  Replaces tf.clip_by_global_norm + AdamOptimizer.apply_gradients
+ * (models/AcousticModel.py:388,404-406).
+ *   rs_sumsq: sumsq_d[0] = sum(g^2)  (float64 accumulator, device)
+ *   rs_clip_adam_step: reads sumsq_d[0] on device (no host sync):
+ *       g' = g * clip / max(sqrt(sumsq), clip);  TF ApplyAdam with step `step` (1-based)
+ * ------------------------------------------------------------------------ */
+int rs_sumsq(const float* g_d, int64_t n, double* sumsq_d, void* stream);
+int rs_clip_adam_step(float* params_d, const float* grads_d, float* m_d, float* v_d, int64_t n,
+                      const double* sumsq_d, float clip, float lr, float beta1, float beta2,
+                      float eps, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNNSPEECH_B200_H_ */

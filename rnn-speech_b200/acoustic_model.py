@@ -1,0 +1,579 @@
+# coding=utf-8
+"""B200 replacement for the reference's ``models/AcousticModel.py``.
+
+Acoustic RNN trained with CTC loss: input dense -> L x LSTM -> output dense ->
+CTC.  Same class name, constructor and method names / return values as
+``models.AcousticModel.AcousticModel`` (/root/reference/models/AcousticModel.py:28-939)
+so that ``stt.py`` keeps its structure; every method that took a ``tf.Session``
+still accepts (and ignores) a ``sess`` argument.  All arithmetic runs in the CUDA
+kernels behind the C ABI (include/rnnspeech_b200.h); torch tensors are used only
+as device-memory holders and for NCCL plumbing.  There is no CPU fallback.
+
+Data-parallel training (not in the reference): one process
+per GPU, each rank runs its own mini-batches, one NCCL all-reduce(SUM) over the
+flat gradient buffer per step (the reference differentiates the SUM of the
+per-item losses, models/AcousticModel.py:386-388, so SUM -- not mean -- keeps the
+update identical to the reference run with mini_batch_size = world size).
+"""
+import logging
+import os
+import pickle
+import time
+from random import randint
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import labels as labelcodec
+from .audioprocessor import AudioProcessor
+
+
+def _stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class OutOfRangeError(Exception):
+    """End of dataset (stands in for tf.errors.OutOfRangeError)."""
+
+
+def levenshtein(a, b):
+    """Edit distance between two integer sequences (numpy row DP)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if len(a) == 0:
+        return len(b)
+    if len(b) == 0:
+        return len(a)
+    idx = np.arange(len(b) + 1)
+    prev = idx.copy()
+    for i in range(1, len(a) + 1):
+        cost = (b != a[i - 1]).astype(np.int64)
+        cur = np.empty_like(prev)
+        cur[0] = i
+        cur[1:] = np.minimum(prev[1:] + 1, prev[:-1] + cost)
+        cur = np.minimum.accumulate(cur - idx) + idx
+        prev = cur
+    return int(prev[-1])
+
+
+class AcousticModel(object):
+    def __init__(self, num_layers, hidden_size, batch_size, max_input_seq_length,
+                 max_target_seq_length, input_dim, normalization, num_labels, device=None, seed=0):
+        """
+        Initialize the acoustic rnn model parameters (models/AcousticModel.py:29-94)
+
+        :param num_layers: number of lstm layers
+        :param hidden_size: size of hidden layers
+        :param batch_size: number of training examples fed at once
+        :param max_input_seq_length: maximum length of input vector sequence
+        :param max_target_seq_length: maximum length of ouput vector sequence
+        :param input_dim: dimension of input vector
+        :param normalization: boolean indicating whether or not to normalize data in a input batch
+        :param num_labels: the numbers of output labels
+        """
+        self.num_layers = num_layers
+        self.hidden_size = hidden_size
+        self.batch_size = batch_size
+        self.max_input_seq_length = max_input_seq_length
+        self.max_target_seq_length = max_target_seq_length
+        self.input_dim = input_dim
+        self.normalization = normalization
+        self.num_labels = num_labels
+        if normalization:
+            # models/AcousticModel.py:253-259 -- off by default (config.ini:88); not on the B200 path yet
+            raise NotImplementedError("batch_normalization=True is not supported by the B200 kernels")
+        if not torch.cuda.is_available():
+            raise RuntimeError("rnnspeech_b200.AcousticModel needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.seed = seed
+        self.beta_skip = _lib.CTC_BETA_SOURCE
+
+        self.input_keep_prob = self.output_keep_prob = 1.0
+        self.grad_clip = None
+        self.lr_decay_factor = None
+        self.learning_rate_var = None
+        self.global_step = 0
+        self.is_training = False
+        self.rnn_created = False
+        self.training_created = False
+        self.tensorboard_dir = None
+        self.timeline_enabled = False
+        self._train_iter = self._valid_iter = None
+        self._train_dataset = self._valid_dataset = None
+
+        self._handle = None
+        self.params = self.grads = self.adam_m = self.adam_v = None
+        self.rnn_state = None
+        self._dropout_calls = 0
+
+    # ------------------------------------------------------------ construction
+    def _create_common(self):
+        if self.rnn_created:
+            logging.fatal("Trying to create the acoustic RNN but it is already.")
+            return
+        h = _lib.c_void_p()
+        _lib.call("rs_am_create", _lib.ctypes.byref(h), self.num_layers, self.hidden_size, self.input_dim,
+                  self.num_labels, self.batch_size, self.max_input_seq_length)
+        self._handle = h
+        n = _lib.raw("rs_am_param_count")(h)
+        self.n_params = int(n)
+        self.params = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
+        self._ws = torch.empty(int(_lib.raw("rs_am_workspace_bytes")(h)), dtype=torch.uint8, device=self.device)
+        self.rnn_state = torch.zeros((self.num_layers, 2, self.batch_size, self.hidden_size), dtype=torch.float32,
+                                     device=self.device)
+        self._ctc_ws = None
+        self.rnn_created = True
+
+    def create_forward_rnn(self):
+        """Create the forward-only RNN (models/AcousticModel.py:96-120)."""
+        self._create_common()
+
+    def create_training_rnn(self, input_keep_prob, output_keep_prob, grad_clip, learning_rate, lr_decay_factor,
+                            use_iterator=False):
+        """Create the training RNN (models/AcousticModel.py:122-187)."""
+        self._create_common()
+        self.input_keep_prob = float(input_keep_prob)
+        self.output_keep_prob = float(output_keep_prob)
+        self.grad_clip = float(grad_clip)
+        self.learning_rate_var = float(learning_rate)
+        self.lr_decay_factor = float(lr_decay_factor)
+        self.use_iterator = use_iterator
+        h = self._handle
+        self._reserve = torch.empty(int(_lib.raw("rs_am_reserve_bytes")(h)), dtype=torch.uint8, device=self.device)
+        self.grads = torch.zeros_like(self.params)
+        self.adam_m = torch.zeros_like(self.params)
+        self.adam_v = torch.zeros_like(self.params)
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
+        # accumulators (models/AcousticModel.py:364-383): [mean_loss, error_rate, mini_batch]
+        self._acc = torch.zeros(3, dtype=torch.float32, device=self.device)
+        self.training_created = True
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib.raw("rs_am_destroy")(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------- parameters
+    def param_views(self):
+        """name -> view into the flat parameter buffer, with the reference's
+        checkpoint variable names (models/AcousticModel.py:515-527)."""
+        h, H, F, C = self._handle, self.hidden_size, self.input_dim, self.num_labels
+        off = lambda which, layer=0: int(_lib.raw("rs_am_param_offset")(h, which, layer))
+        views = {}
+
+        def view(buf, o, shape):
+            n = int(np.prod(shape))
+            return buf[o:o + n].view(*shape)
+        def build(buf):
+            out = {"Input_Layer/input_w": view(buf, off(0), (F, H)), "Input_Layer/input_b": view(buf, off(1), (H,))}
+            for l in range(self.num_layers):
+                out["rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % l] = view(buf, off(2, l), (2 * H, 4 * H))
+                out["rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/bias" % l] = view(buf, off(3, l), (4 * H,))
+            out["Output_layer/output_w"] = view(buf, off(4), (H, C))
+            out["Output_layer/output_b"] = view(buf, off(5), (C,))
+            return out
+        views = build(self.params)
+        return views
+
+    def grad_views(self):
+        saved = self.params
+        try:
+            self.params = self.grads
+            return self.param_views()
+        finally:
+            self.params = saved
+
+    def initialize(self, sess=None):
+        """Xavier / glorot-uniform weights, zero biases (models/AcousticModel.py:242-245,
+        :303-306, BasicLSTMCell defaults); deterministic in self.seed."""
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(int(self.seed))
+        for name, v in self.param_views().items():
+            if v.dim() == 2:
+                lim = float(np.sqrt(6.0 / (v.shape[0] + v.shape[1])))
+                w = (torch.rand(v.shape, generator=gen, dtype=torch.float32) * 2.0 - 1.0) * lim
+                v.copy_(w.to(self.device))
+            else:
+                v.zero_()
+        self.global_step = 0
+        self.rnn_state.zero_()
+
+    def load_flat_params(self, flat):
+        flat = torch.as_tensor(np.asarray(flat, dtype=np.float32))
+        assert flat.numel() == self.n_params
+        self.params.copy_(flat.to(self.device))
+
+    def get_learning_rate(self):
+        return self.learning_rate_var
+
+    def set_learning_rate(self, sess, learning_rate):
+        self.learning_rate_var = float(learning_rate)
+
+    def learning_rate_decay_op(self, sess=None):
+        """models/AcousticModel.py:354 -- learning_rate *= lr_decay_factor"""
+        self.learning_rate_var = self.learning_rate_var * self.lr_decay_factor
+        return self.learning_rate_var
+
+    def set_is_training(self, sess, is_training):
+        self.is_training = bool(is_training)
+
+    # ----------------------------------------------------------- checkpointing
+    def save(self, session, checkpoint_dir):
+        """models/AcousticModel.py:483-487.  Writes the same variable set (weights,
+        global_step, learning_rate; no Adam slots, no RNN state) as a numpy archive
+        named like the TF checkpoint prefix."""
+        path = os.path.join(checkpoint_dir, "acousticmodel.ckpt-%d.npz" % self.global_step)
+        arrays = {k: v.detach().cpu().numpy() for k, v in self.param_views().items()}
+        arrays["global_step"] = np.int64(self.global_step)
+        arrays["learning_rate"] = np.float32(self.learning_rate_var if self.learning_rate_var is not None else 0.0)
+        np.savez(path, **arrays)
+        with open(os.path.join(checkpoint_dir, "checkpoint"), "w") as fh:
+            fh.write('model_checkpoint_path: "%s"\n' % os.path.basename(path))
+        logging.info("Checkpoint saved")
+        return path
+
+    def restore(self, session, checkpoint_dir):
+        """models/AcousticModel.py:489-499"""
+        state = os.path.join(checkpoint_dir, "checkpoint")
+        if os.path.exists(state):
+            line = open(state).readline()
+            name = line.split('"')[1]
+            data = np.load(os.path.join(checkpoint_dir, name))
+            for k, v in self.param_views().items():
+                v.copy_(torch.from_numpy(data[k]).to(self.device))
+            self.global_step = int(data["global_step"])
+            if self.learning_rate_var is not None:
+                self.learning_rate_var = float(data["learning_rate"])
+            logging.info("Restored model parameters from %s (global_step id %d)", name, self.global_step)
+        else:
+            logging.info("Created model with fresh parameters.")
+
+    # -------------------------------------------------------------- hot path
+    def _labels_to_device(self, label_rows):
+        lens = np.array([len(r) for r in label_rows], dtype=np.int32)
+        offs = np.zeros(len(label_rows) + 1, dtype=np.int32)
+        np.cumsum(lens, out=offs[1:])
+        flat = np.concatenate([np.asarray(r, dtype=np.int32) for r in label_rows]) if offs[-1] > 0 \
+            else np.zeros((1,), np.int32)
+        if flat.size and (flat.min() < 0 or flat.max() >= self.num_labels):
+            raise ValueError("labels must be in [0, num_labels)")
+        return (torch.from_numpy(flat).to(self.device, non_blocking=True),
+                torch.from_numpy(offs).to(self.device, non_blocking=True), int(lens.max()) if len(lens) else 0)
+
+    def sparse_labels_from_dense(self, dense_labels, fill_empty):
+        """models/AcousticModel.py:151-156 / :174-178: drop every 0 of the dense
+        zero-padded label batch; (iterator path) fill empty rows with [num_labels-1]."""
+        dense = np.asarray(dense_labels)
+        rows = [row[row != 0].astype(np.int32) for row in dense]
+        while fill_empty and len(rows) < self.batch_size:
+            rows.append(np.zeros((0,), np.int32))
+        if fill_empty:
+            rows = [r if len(r) else np.array([self.num_labels - 1], np.int32) for r in rows]
+        return rows
+
+    def forward(self, x_d, len_d, training=False, keep_state=True, T=None, logits=None):
+        """x_d float32 [T,B,F] (device), len_d int32 [B].  Returns logits [T,B,C].
+        training=True keeps the activations for one backward call and applies the
+        configured dropout."""
+        assert x_d.dtype == torch.float32 and x_d.is_contiguous() and x_d.dim() == 3
+        T = int(x_d.shape[0]) if T is None else int(T)
+        assert x_d.shape[1] == self.batch_size and x_d.shape[2] == self.input_dim
+        if logits is None:
+            logits = torch.empty((T, self.batch_size, self.num_labels), dtype=torch.float32, device=self.device)
+        keep_in = self.input_keep_prob if training else 1.0
+        keep_out = self.output_keep_prob if training else 1.0
+        self._dropout_calls += 1
+        seed = (int(self.seed) * 1000003 + self._dropout_calls) & 0xFFFFFFFFFFFFFFFF
+        self._last_fwd = (keep_in, keep_out, seed, T)
+        _lib.call("rs_am_forward", self._handle, self.params.data_ptr(), x_d.data_ptr(), len_d.data_ptr(), T,
+                  self.rnn_state.data_ptr(), self.rnn_state.data_ptr() if keep_state else None,
+                  keep_in, keep_out, seed, logits.data_ptr(),
+                  self._reserve.data_ptr() if training else None, self._ws.data_ptr(), self._ws.numel(),
+                  _stream_ptr())
+        return logits
+
+    def backward(self, x_d, len_d, dlogits):
+        keep_in, keep_out, seed, T = self._last_fwd
+        _lib.call("rs_am_backward", self._handle, self.params.data_ptr(), x_d.data_ptr(), len_d.data_ptr(), T,
+                  keep_in, keep_out, seed, dlogits.data_ptr(), self._reserve.data_ptr(), self.grads.data_ptr(),
+                  self._ws.data_ptr(), self._ws.numel(), _stream_ptr())
+
+    def ctc_loss(self, logits, label_rows, len_d, want_grad=True):
+        """tf.nn.ctc_loss(..., ignore_longer_outputs_than_inputs=True) + gradient.
+        Returns (loss [B] device, grad [T,B,C] device or None)."""
+        T, B, C = logits.shape
+        flat, offs, maxlen = self._labels_to_device(label_rows)
+        need = int(_lib.raw("rs_ctc_workspace_bytes")(T, B, C, maxlen))
+        if self._ctc_ws is None or self._ctc_ws.numel() < need:
+            self._ctc_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        loss = torch.empty((B,), dtype=torch.float32, device=self.device)
+        grad = torch.empty_like(logits) if want_grad else None
+        _lib.call("rs_ctc_loss_grad", logits.data_ptr(), flat.data_ptr(), offs.data_ptr(), len_d.data_ptr(), T, B, C,
+                  maxlen, self.num_labels - 1, self.beta_skip, loss.data_ptr(),
+                  grad.data_ptr() if want_grad else None, self._ctc_ws.data_ptr(), self._ctc_ws.numel(),
+                  _stream_ptr())
+        return loss, grad
+
+    def greedy_decode(self, logits, len_d):
+        """Per-frame argmax, collapse repeats, drop blank.  Returns (ids [B,T] int32
+        padded with -1, lengths [B]) on the device."""
+        T, B, C = logits.shape
+        out = torch.empty((B, T), dtype=torch.int32, device=self.device)
+        out_len = torch.empty((B,), dtype=torch.int32, device=self.device)
+        _lib.call("rs_ctc_greedy_decode", logits.data_ptr(), len_d.data_ptr(), T, B, C, self.num_labels - 1,
+                  out.data_ptr(), out_len.data_ptr(), _stream_ptr())
+        return out, out_len
+
+    def _error_rate(self, logits, len_d, label_rows):
+        """mean over the batch of edit_distance(prediction, truth) / len(truth)
+        (tf.edit_distance(normalize=True), models/AcousticModel.py:370); the
+        prediction here is the greedy path (the reference uses beam search)."""
+        ids, lens = self.greedy_decode(logits, len_d)
+        ids = ids.cpu().numpy()
+        lens = lens.cpu().numpy()
+        rates = []
+        for b, truth in enumerate(label_rows):
+            hyp = ids[b, :lens[b]]
+            d = levenshtein(hyp, truth)
+            rates.append(d / float(len(truth)) if len(truth) else (float("inf") if d else 0.0))
+        return float(np.mean(rates))
+
+    def step_on_batch(self, x_d, len_d, label_rows, compute_gradients=True, compute_error_rate=True):
+        """One mini-batch of run_step (models/AcousticModel.py:634-660) on explicit
+        device tensors: forward, CTC, (backward + gradient accumulation),
+        accumulate mean loss / error rate / mini-batch count, keep the RNN state."""
+        logits = self.forward(x_d, len_d, training=compute_gradients, keep_state=True)
+        loss, grad = self.ctc_loss(logits, label_rows, len_d, want_grad=compute_gradients)
+        if compute_gradients:
+            self.backward(x_d, len_d, grad)
+        # display loss: mean(loss[b] / len[b])            (models/AcousticModel.py:361-362)
+        self._acc[0] += (loss / len_d.to(torch.float32)).mean()
+        if compute_error_rate:
+            self._acc[1] += self._error_rate(logits, len_d, label_rows)
+        self._acc[2] += 1.0
+        return loss
+
+    def apply_gradients(self):
+        """train_step_op (models/AcousticModel.py:404-406): all-reduce (data parallel),
+        clip the ACCUMULATED gradient by its global norm, Adam, global_step += 1."""
+        if torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM)
+        self.global_step += 1
+        _lib.call("rs_sumsq", self.grads.data_ptr(), self.n_params, self._sumsq.data_ptr(), _stream_ptr())
+        _lib.call("rs_clip_adam_step", self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
+                  self.adam_v.data_ptr(), self.n_params, self._sumsq.data_ptr(), self.grad_clip,
+                  self.learning_rate_var, 0.9, 0.999, 1e-8, self.global_step, _stream_ptr())
+
+    # ---------------------------------------------------------- measurement
+    def enable_timing(self):
+        """CUDA events on the launch stream around every recurrent kernel."""
+        _lib.call("rs_am_enable_timing", self._handle, 1)
+
+    def recurrent_ms(self):
+        """(forward_ms, backward_ms): per-layer durations of the last step's recurrent kernels."""
+        out = ([], [])
+        for d in (0, 1):
+            for l in range(self.num_layers):
+                ms = _lib.ctypes.c_float()
+                _lib.call("rs_am_recurrent_ms", self._handle, d, l, _lib.ctypes.byref(ms))
+                out[d].append(ms.value)
+        return out
+
+    # ------------------------------------------------------- step protocol
+    def start_batch(self, session=None, is_training=True, run_options=None, run_metadata=None):
+        """models/AcousticModel.py:662-670"""
+        self._acc.zero_()
+        self.set_is_training(session, is_training)
+        if is_training:
+            self.grads.zero_()
+
+    def _next_batch(self):
+        it = self._train_iter if self.is_training else self._valid_iter
+        if it is None:
+            raise RuntimeError("no dataset attached: call add_datasets_input / add_dataset_input first")
+        try:
+            return next(it)
+        except StopIteration:
+            raise OutOfRangeError()
+
+    def run_step(self, session=None, compute_gradients=True, run_options=None, run_metadata=None,
+                 compute_error_rate=True):
+        """models/AcousticModel.py:634-660: one mini-batch pulled from the attached dataset."""
+        start_time = time.time()
+        x_d, len_d, dense_labels = self._next_batch()
+        rows = self.sparse_labels_from_dense(dense_labels, fill_empty=True)
+        self.step_on_batch(x_d, len_d, rows, compute_gradients, compute_error_rate)
+        mini_batch_num = float(self._acc[2].item())
+        logging.debug("Step duration : %.2f", time.time() - start_time)
+        return mini_batch_num
+
+    def end_batch(self, session=None, is_training=True, run_options=None, run_metadata=None,
+                  rnn_state_reset_ratio=1.0):
+        """models/AcousticModel.py:672-703"""
+        if is_training:
+            self.apply_gradients()
+            # Reset the hidden state at the given random ratio (default to always)   (:681-682)
+            if randint(1, int(1 // rnn_state_reset_ratio)) == 1:
+                self.rnn_state.zero_()
+        acc = self._acc.cpu().numpy()
+        if torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            t = self._acc.clone()
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+            acc = t.cpu().numpy()
+        batchs_count = acc[2]
+        mean_loss = acc[0] / batchs_count
+        mean_error_rate = acc[1] / batchs_count
+        return mean_loss, mean_error_rate, self.global_step
+
+    def run_train_step(self, sess=None, mini_batch_size=1, rnn_state_reset_ratio=1.0, run_options=None,
+                       run_metadata=None, compute_error_rate=True):
+        """models/AcousticModel.py:887-939.  Returns (mean_loss, mean_error_rate,
+        current_step, dataset_empty)."""
+        start_time = time.time()
+        dataset_empty = False
+        self.start_batch(sess, True)
+        mini_batch_num = 0
+        try:
+            for _ in range(mini_batch_size):
+                mini_batch_num = self.run_step(sess, True, compute_error_rate=compute_error_rate)
+        except OutOfRangeError:
+            logging.debug("Dataset empty, exiting train step")
+            dataset_empty = True
+        if mini_batch_num > 0:
+            mean_loss, mean_error_rate, current_step = self.end_batch(sess, True,
+                                                                      rnn_state_reset_ratio=rnn_state_reset_ratio)
+            logging.info("Batch %d : loss %.5f - error_rate %.5f - duration %.2f",
+                         current_step, mean_loss, mean_error_rate, time.time() - start_time)
+            return mean_loss, mean_error_rate, current_step, dataset_empty
+        return 0.0, 0.0, self.global_step, dataset_empty
+
+    def run_evaluation(self, sess=None, run_options=None, run_metadata=None):
+        """models/AcousticModel.py:779-799"""
+        start_time = time.time()
+        logging.info("Start evaluating...")
+        self.start_batch(sess, False)
+        if self._valid_dataset is not None:
+            self._valid_iter = iter(self._valid_dataset)
+        try:
+            while True:
+                self.run_step(sess, False)
+        except OutOfRangeError:
+            logging.debug("Dataset empty, exiting evaluation step")
+        mean_loss, mean_error_rate, current_step = self.end_batch(sess, False, rnn_state_reset_ratio=1.0)
+        self.rnn_state.zero_()     # always reset the RNN state after evaluation (:793-795)
+        logging.info("Evaluation at step %d : loss %.5f - error_rate %.5f - duration %.2f",
+                     current_step, mean_loss, mean_error_rate, time.time() - start_time)
+        return mean_loss, mean_error_rate, current_step
+
+    def process_input(self, session, inputs, input_seq_lengths, run_options=None, run_metadata=None):
+        """models/AcousticModel.py:705-721: forward only; returns int32 [B, maxdecoded]
+        padded with num_labels (which get_labels_str drops).  The RNN state is NOT
+        carried over (the reference does not run rnn_keep_state_op here)."""
+        x = torch.as_tensor(np.ascontiguousarray(np.asarray(inputs, dtype=np.float32))).to(self.device)
+        lens = torch.as_tensor(np.asarray(input_seq_lengths, dtype=np.int32)).to(self.device)
+        logits = self.forward(x, lens, training=False, keep_state=False)
+        ids, out_len = self.greedy_decode(logits, lens)
+        ids = ids.cpu().numpy()
+        out_len = out_len.cpu().numpy()
+        width = int(out_len.max()) if len(out_len) else 0
+        pred = np.full((len(out_len), width), self.num_labels, dtype=np.int32)
+        for b, n in enumerate(out_len):
+            pred[b, :n] = ids[b, :n]
+        return pred
+
+    # ------------------------------------------------------------- datasets
+    @staticmethod
+    def build_dataset(input_set, batch_size, max_input_seq_length, max_target_seq_length,
+                      signal_processing, char_map, sr=None, device=None, delta_mode="interp"):
+        """models/AcousticModel.py:801-840.  Items are [audio, label, ...] where
+        audio is a file name or an in-memory (signal, sample_rate) pair."""
+        from .dataset import AudioBatchDataset
+        return AudioBatchDataset(input_set, batch_size, max_input_seq_length, max_target_seq_length,
+                                 signal_processing, char_map, device=device, delta_mode=delta_mode)
+
+    def add_dataset_input(self, dataset):
+        """models/AcousticModel.py:842-853"""
+        self._train_dataset = self._valid_dataset = dataset
+        self._train_iter = self._valid_iter = iter(dataset)
+        return dataset
+
+    def add_datasets_input(self, train_dataset, valid_dataset):
+        """models/AcousticModel.py:855-871"""
+        self._train_dataset, self._valid_dataset = train_dataset, valid_dataset
+        self._train_iter, self._valid_iter = iter(train_dataset), iter(valid_dataset)
+        return train_dataset, valid_dataset
+
+    def reset_train_iterator(self):
+        """stands in for sess.run(t_iterator.initializer) (stt.py:193-195)"""
+        self._train_iter = iter(self._train_dataset)
+
+    def add_tensorboard(self, session, tensorboard_dir, tb_run_name=None, timeline_enabled=False):
+        """models/AcousticModel.py:409-465: kept as a no-op hook (scalar logging goes
+        through `logging`; per-phase timing through --timeline JSON)."""
+        self.tensorboard_dir = tensorboard_dir
+        self.timeline_enabled = timeline_enabled
+
+    # --------------------------------------------------------------- metrics
+    @staticmethod
+    def calculate_wer(first_string, second_string):
+        """Word-level Levenshtein distance (models/AcousticModel.py:529-580).
+        > calculate_wer("who is there", "is there") == 1"""
+        r, h = first_string.split(), second_string.split()
+        vocab = {w: i for i, w in enumerate(set(r) | set(h))}
+        return levenshtein([vocab[w] for w in r], [vocab[w] for w in h])
+
+    @staticmethod
+    def calculate_cer(first_string, second_string):
+        """Character-level Levenshtein distance ignoring spaces (models/AcousticModel.py:582-632).
+        > calculate_cer("who is there", "who i thre") == 2"""
+        r = [ord(c) for c in first_string.replace(" ", "")]
+        h = [ord(c) for c in second_string.replace(" ", "")]
+        return levenshtein(r, h)
+
+    def evaluate_full(self, sess, eval_dataset, input_seq_length, signal_processing, char_map,
+                      run_options=None, run_metadata=None):
+        """models/AcousticModel.py:723-777: WER / CER (percent) over a list of
+        [audio, label, ...] items; audio = file name or (signal, sr)."""
+        audio_processor = AudioProcessor(input_seq_length, signal_processing, device=self.device)
+        wer_list, cer_list = [], []
+        feats, lens, labs = [], [], []
+        file_number = 0
+        for item in eval_dataset:
+            audio, label = item[0], item[1]
+            if isinstance(audio, (tuple, list)):
+                feat_vec, feat_len = audio_processor.process_signal(audio[0], audio[1])
+            else:
+                feat_vec, feat_len = audio_processor.process_audio_file(audio)
+            file_number += 1
+            if len(label) > self.max_target_seq_length or feat_len > self.max_input_seq_length:
+                logging.warning("Warning - sample too long : %s (input : %d / text : %s)", audio, feat_len, len(label))
+            else:
+                padded = np.zeros((self.max_input_seq_length, audio_processor.feature_size), np.float32)
+                padded[:len(feat_vec)] = feat_vec
+                feats.append(padded)
+                lens.append(feat_len)
+                labs.append(label)
+            if file_number == len(eval_dataset):
+                while len(feats) < self.batch_size and len(feats) > 0:
+                    feats.append(np.zeros((self.max_input_seq_length, audio_processor.feature_size), np.float32))
+                    lens.append(0)
+                    labs.append("")
+            if len(feats) == self.batch_size:
+                batch = np.swapaxes(np.stack(feats), 0, 1)
+                predictions = self.process_input(sess, batch, lens)
+                for index, prediction in enumerate(predictions):
+                    text = labelcodec.get_labels_str(char_map, prediction)
+                    truth = labs[index]
+                    if len(truth) > 0:
+                        wer_list.append(self.calculate_wer(text, truth) / float(len(truth.split())))
+                        cer_list.append(self.calculate_cer(text, truth) / float(len(truth.replace(" ", ""))))
+                feats, lens, labs = [], [], []
+        wer = (sum(wer_list) * 100) / float(len(wer_list))
+        cer = (sum(cer_list) * 100) / float(len(cer_list))
+        return wer, cer

@@ -1,0 +1,148 @@
+# coding=utf-8
+"""B200 replacement for the reference's ``util/audioprocessor.py``.
+
+Same class name, constructor, attributes and return values as
+``util.audioprocessor.AudioProcessor`` (/root/reference/util/audioprocessor.py:10-61)
+so callers (stt.py:24-27, :240, :335-354; models/AcousticModel.py:726, :812-813)
+need no change.  The arithmetic runs in the CUDA feature kernels
+(csrc/features.cu) through the C ABI; there is no CPU fallback.
+
+Added (not in the reference): ``process_batch`` -- a whole batch of utterances in
+one launch, result left on the device, optionally time-major, which is what the
+training path consumes.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+# GLOBALS (util/audioprocessor.py:6-7)
+FRAME_STRIDE = 0.01
+FRAME_SIZE = 0.025
+
+_DELTA_MODES = {"interp": _lib.DELTA_INTERP, "edge": _lib.DELTA_EDGE}
+
+
+def _stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class AudioProcessor(object):
+    def __init__(self, max_input_seq_length, feature_type="mfcc", delta_mode="interp", device=None):
+        """
+        feature_type - string options are: mfcc, fbank
+        mfcc is a 20-dim input
+        fbank is 120-dim input (mel filterbank with delta and double delta)
+
+        delta_mode - which librosa.feature.delta the fbank path reproduces:
+            "interp" (librosa >= 0.6.1, scipy savgol_filter mode='interp') or
+            "edge"   (librosa <= 0.6.0, edge-replicated FIR, window / sum|w|).
+        """
+        self.max_input_seq_length = max_input_seq_length
+        self.feature_type = feature_type
+        if self.feature_type == "mfcc":
+            self.feature_size = 20
+        elif self.feature_type == "fbank":
+            self.feature_size = 120
+        else:
+            raise ValueError("{0} is not a valid extraction function, \
+            only fbank and mfcc are accepted.".format(self.feature_type))
+        if delta_mode not in _DELTA_MODES:
+            raise ValueError("delta_mode must be 'interp' or 'edge', got %r" % (delta_mode,))
+        self.delta_mode = delta_mode
+        self._device = device
+        self._ws = None
+
+    @staticmethod
+    def get_mfcc_length_from_duration(duration):
+        """util/audioprocessor.py:29-39"""
+        length = int(duration // FRAME_STRIDE) - 1
+        return length
+
+    # ------------------------------------------------------------------ helpers
+    def _dev(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError("rnnspeech_b200.AudioProcessor needs a CUDA device (no CPU fallback)")
+        return torch.device(self._device if self._device is not None else "cuda")
+
+    def num_frames(self, n_samples, sr):
+        if self.feature_type == "fbank":
+            return int(_lib.raw("rs_fbank_num_frames")(int(n_samples), int(sr)))
+        return int(_lib.raw("rs_mfcc_num_frames")(int(n_samples), int(sr)))
+
+    def _workspace(self, nbytes, dev):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
+            self._ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+        return self._ws
+
+    def features_device(self, pcm_d, offsets_d, batch, max_samples, sr, time_major=True, out=None, nframes=None):
+        """Device-resident entry: pcm_d float32 [sum n], offsets_d int64 [B+1].
+        Returns (features [Tmax,B,F] or [B,Tmax,F] float32, nframes int32 [B]),
+        both on the device; nframes is the PRE-truncation frame count."""
+        dev = pcm_d.device
+        Tmax, F = int(self.max_input_seq_length), self.feature_size
+        shape = (Tmax, batch, F) if time_major else (batch, Tmax, F)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=dev)
+        if nframes is None:
+            nframes = torch.empty((batch,), dtype=torch.int32, device=dev)
+        assert out.is_contiguous() and tuple(out.shape) == shape and out.dtype == torch.float32
+        if self.feature_type == "fbank":
+            ws_bytes = _lib.raw("rs_fbank_workspace_bytes")(batch, int(max_samples), int(sr))
+            ws = self._workspace(ws_bytes, dev)
+            _lib.call("rs_fbank_forward", pcm_d.data_ptr(), offsets_d.data_ptr(), batch, int(max_samples), int(sr),
+                      Tmax, _DELTA_MODES[self.delta_mode], 1 if time_major else 0, out.data_ptr(),
+                      nframes.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr())
+        else:
+            ws_bytes = _lib.raw("rs_mfcc_workspace_bytes")(batch, int(max_samples), int(sr))
+            ws = self._workspace(ws_bytes, dev)
+            _lib.call("rs_mfcc_forward", pcm_d.data_ptr(), offsets_d.data_ptr(), batch, int(max_samples), int(sr),
+                      Tmax, F, 1 if time_major else 0, out.data_ptr(), nframes.data_ptr(), ws.data_ptr(),
+                      ws.numel(), _stream_ptr())
+        return out, nframes
+
+    def process_batch(self, signals, sr, time_major=True):
+        """signals: list of 1-D float arrays (host).  One H2D copy, one launch
+        sequence; returns device tensors (features, nframes)."""
+        dev = self._dev()
+        lens = [int(len(s)) for s in signals]
+        if min(lens) < 1:
+            raise ValueError("empty signal")
+        if self.feature_type == "fbank" and self.delta_mode == "interp":
+            for n in lens:
+                if self.num_frames(n, sr) < 9:
+                    # librosa.feature.delta(mode='interp') raises when width 9 > number of frames
+                    raise ValueError("delta(mode='interp') needs at least 9 frames, got %d" % self.num_frames(n, sr))
+        offsets = np.zeros(len(signals) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        host = torch.empty((int(offsets[-1]),), dtype=torch.float32, pin_memory=True)
+        hview = host.numpy()
+        for s, o in zip(signals, offsets[:-1]):
+            hview[o:o + len(s)] = np.asarray(s, dtype=np.float32)
+        pcm_d = host.to(dev, non_blocking=True)
+        off_d = torch.from_numpy(offsets).to(dev, non_blocking=True)
+        return self.features_device(pcm_d, off_d, len(signals), max(lens), sr, time_major=time_major)
+
+    # ---------------------------------------------------------- reference API
+    def process_signal(self, sig, sr):
+        """
+        :param sig: audio signal to process
+        :param sr: audio signal rate
+        :returns: mfcc: feature array [T', F] (truncated to max_input_seq_length)
+        :returns: mfcc_length: original length of the features before truncation
+        (util/audioprocessor.py:52-61)
+        """
+        feat, nframes = self.process_batch([np.asarray(sig)], sr, time_major=False)
+        length = int(nframes.cpu()[0])
+        keep = min(length, int(self.max_input_seq_length))
+        return feat[0, :keep].cpu().numpy(), length
+
+    def process_audio_file(self, file_name):
+        """util/audioprocessor.py:41-50.  The reference decodes with
+        librosa.load(file, mono=True), i.e. resampled to 22 050 Hz; decode and
+        resampling are a SURVEY section-8(f) 'next' row.  WAV files are read with
+        the standard library and resampled with a polyphase filter (NOT
+        bit-identical to librosa's kaiser_best)."""
+        from .audiofile import load_audio
+        sig, sr = load_audio(file_name)
+        return self.process_signal(sig, sr)

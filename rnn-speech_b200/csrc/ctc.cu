@@ -1,0 +1,345 @@
+// CTC loss + gradient and greedy decode for sm_100a.
+//
+// Replaces tf.nn.ctc_loss(...) / prediction at
+// /root/reference/models/AcousticModel.py:357 and :312-314.  The lattice rules
+// are TF's (tensorflow/core/util/ctc/ctc_loss_calculator.{h,cc}), including the
+// asymmetric alpha/beta skip test that is live because the reference's EOS label
+// id equals the blank id; see oracle/ctc.py for the restated rules.
+//
+// Kernels
+//   ctc_lse_kernel        one warp per (t,b) row: log-sum-exp over the C logits
+//   ctc_lattice_kernel    2 CTAs per item (blockIdx.y = 0: alpha forward in time,
+//                         1: beta backward in time), lattice row double-buffered
+//                         in shared memory, rows streamed to the workspace
+//   ctc_grad_kernel       one warp per (t,b) row: y - sum_u exp(alpha+beta-logp)
+//   ctc_greedy_kernel     one CTA per item: per-frame argmax, collapse, compact
+#include "common.cuh"
+
+namespace rs {
+
+static constexpr float kNegInf = -INFINITY;
+
+__device__ __forceinline__ float lse2(float a, float b) {
+  float m = fmaxf(a, b);
+  if (m == kNegInf) return kNegInf;
+  return m + logf(expf(a - m) + expf(b - m));
+}
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  float m = fmaxf(a, fmaxf(b, c));
+  if (m == kNegInf) return kNegInf;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+// lse[t*B+b] = logsumexp_k logits[t,b,k]   (rows with t >= len[b] are skipped)
+__global__ void ctc_lse_kernel(const float* __restrict__ logits, const int* __restrict__ len,
+                               int T, int B, int C, float* __restrict__ lse) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= T * B) return;
+  int t = row / B, b = row - t * B;
+  if (t >= len[b]) return;
+  const float* p = logits + (size_t)row * C;
+  float m = kNegInf;
+  for (int k = lane; k < C; k += 32) m = fmaxf(m, p[k]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int k = lane; k < C; k += 32) s += expf(p[k] - m);
+  s = warp_sum(s);
+  if (lane == 0) lse[row] = m + logf(s);
+}
+
+// status per item: 0 = normal, 1 = skipped (len == 0 or labels longer than input)
+struct CtcItem {
+  int L;       // frames
+  int N;       // labels
+  int U;       // 2N+1
+  int skip;
+};
+
+__device__ __forceinline__ CtcItem ctc_item(const int* len, const int* label_offsets, int b) {
+  CtcItem it;
+  it.L = len[b];
+  it.N = label_offsets[b + 1] - label_offsets[b];
+  it.U = 2 * it.N + 1;
+  it.skip = (it.L == 0 || it.N > it.L) ? 1 : 0;
+  return it;
+}
+
+// dynamic smem: int lp[Upad]; float row[2][Upad + 2]
+__global__ void __launch_bounds__(1024)
+ctc_lattice_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
+                   const int* __restrict__ labels, const int* __restrict__ label_offsets,
+                   const int* __restrict__ len, int T, int B, int C, int Upad, int blank,
+                   int beta_skip_dest, float* __restrict__ alpha, float* __restrict__ beta,
+                   float* __restrict__ loss) {
+  extern __shared__ unsigned char smem_raw[];
+  int* lp = reinterpret_cast<int*>(smem_raw);
+  float* rowbuf = reinterpret_cast<float*>(lp + Upad);
+  const int b = blockIdx.x;
+  const bool is_beta = blockIdx.y == 1;
+  const CtcItem it = ctc_item(len, label_offsets, b);
+  if (it.skip) {
+    if (is_beta && threadIdx.x == 0) loss[b] = 0.f;
+    return;
+  }
+  const int U = it.U, L = it.L;
+  const int* lab = labels + label_offsets[b];
+  for (int u = threadIdx.x; u < U; u += blockDim.x) lp[u] = (u & 1) ? lab[u >> 1] : blank;
+  const int stride = Upad + 2;
+  // row r lives at rowbuf[r*stride + 2 + u] (alpha: two -inf guards in front)
+  //                 rowbuf[r*stride + u]     (beta: two -inf guards behind)
+  for (int i = threadIdx.x; i < 2 * stride; i += blockDim.x) rowbuf[i] = kNegInf;
+  __syncthreads();
+  float* out = (is_beta ? beta : alpha) + (size_t)b * T * Upad;
+
+  if (!is_beta) {
+    float* prev = rowbuf + 2;
+    float* cur = rowbuf + stride + 2;
+    const float* lg = logits + (size_t)b * C;
+    const float l0 = lse[b];
+    for (int u = threadIdx.x; u < U; u += blockDim.x) {
+      float v = kNegInf;
+      if (u == 0) v = lg[blank] - l0;
+      else if (u == 1) v = lg[lp[1]] - l0;
+      prev[u] = v;
+      out[u] = v;
+    }
+    __syncthreads();
+    for (int t = 1; t < L; ++t) {
+      const float* lgt = logits + ((size_t)t * B + b) * C;
+      const float lt = lse[t * B + b];
+      const int lo = max(0, U - 2 * (L - t)), hi = min(U, 2 * (t + 1));
+      for (int u = threadIdx.x; u < U; u += blockDim.x) {
+        float v = kNegInf;
+        if (u >= lo && u < hi) {
+          const int l = lp[u];
+          const bool skip = (u > 1) && (l != blank) && (l != lp[u - 2]);
+          const float a0 = prev[u], a1 = prev[u - 1], a2 = skip ? prev[u - 2] : kNegInf;
+          v = lse3(a0, a1, a2) + (lgt[l] - lt);
+        }
+        cur[u] = v;
+        out[(size_t)t * Upad + u] = v;
+      }
+      __syncthreads();
+      float* tmp = prev; prev = cur; cur = tmp;
+    }
+  } else {
+    float* prev = rowbuf;            // beta[t+1] + logp[t+1]  ("nxt" in the oracle)
+    float* cur = rowbuf + stride;
+    // row L-1
+    {
+      const float* lgt = logits + ((size_t)(L - 1) * B + b) * C;
+      const float lt = lse[(L - 1) * B + b];
+      for (int u = threadIdx.x; u < U; u += blockDim.x) {
+        float v = (u >= U - 2) ? 0.f : kNegInf;
+        out[(size_t)(L - 1) * Upad + u] = v;
+        prev[u] = v + (lgt[lp[u]] - lt);
+      }
+    }
+    __syncthreads();
+    for (int t = L - 2; t >= 0; --t) {
+      const float* lgt = logits + ((size_t)t * B + b) * C;
+      const float lt = lse[t * B + b];
+      const int lo = max(0, U - 2 * (L - t)), hi = min(U, 2 * (t + 1));
+      for (int u = threadIdx.x; u < U; u += blockDim.x) {
+        float v = kNegInf;
+        const int l = lp[u];
+        if (u >= lo && u < hi) {
+          bool skip = false;
+          if (u + 2 < U) {
+            const int l2 = lp[u + 2];
+            skip = beta_skip_dest ? (l2 != blank && l2 != l) : (l != blank && l != l2);
+          }
+          const float b0 = prev[u], b1 = prev[u + 1], b2 = skip ? prev[u + 2] : kNegInf;
+          v = lse3(b0, b1, b2);
+        }
+        out[(size_t)t * Upad + u] = v;
+        cur[u] = v + (lgt[l] - lt);   // becomes "nxt" for row t-1; at t == 0 it is alpha0-weighted
+      }
+      __syncthreads();
+      float* tmp = prev; prev = cur; cur = tmp;
+    }
+    // log p(z|x) = LSE_u(alpha[0,u] + beta[0,u]); alpha[0,u] = logp[0,l'u] for u in {0,1}
+    // and prev[u] now holds beta[0,u] + logp[0,l'u].
+    if (threadIdx.x == 0) {
+      float lpz = (U > 1) ? lse2(prev[0], prev[1]) : prev[0];
+      loss[b] = -lpz;   // +inf when no valid path
+    }
+  }
+}
+
+// one warp per (t,b) row.  dynamic smem: float acc[warps][C]
+__global__ void ctc_grad_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
+                                const int* __restrict__ labels, const int* __restrict__ label_offsets,
+                                const int* __restrict__ len, int T, int B, int C, int Upad, int blank,
+                                const float* __restrict__ alpha, const float* __restrict__ beta,
+                                const float* __restrict__ loss, float* __restrict__ grad) {
+  extern __shared__ float acc_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= T * B) return;
+  const int t = row / B, b = row - t * B;
+  float* g = grad + (size_t)row * C;
+  const CtcItem it = ctc_item(len, label_offsets, b);
+  if (it.skip || t >= it.L) {
+    for (int k = lane; k < C; k += 32) g[k] = 0.f;
+    return;
+  }
+  const float* p = logits + (size_t)row * C;
+  const float lt = lse[row];
+  const float nll = loss[b];
+  if (nll == INFINITY) {               // "No valid path found": dy = y
+    for (int k = lane; k < C; k += 32) g[k] = expf(p[k] - lt);
+    return;
+  }
+  float* acc = acc_all + warp * C;
+  for (int k = lane; k < C; k += 32) acc[k] = 0.f;
+  __syncwarp();
+  const float* a = alpha + ((size_t)b * T + t) * Upad;
+  const float* be = beta + ((size_t)b * T + t) * Upad;
+  const int* lab = labels + label_offsets[b];
+  const int U = it.U;
+  float blank_sum = 0.f;
+  for (int u = lane; u < U; u += 32) {
+    const float ab = a[u] + be[u];
+    const float w = (ab == kNegInf) ? 0.f : expf(ab + nll);
+    if (u & 1) {
+      const int l = lab[u >> 1];
+      atomicAdd(&acc[l], w);
+    } else {
+      blank_sum += w;
+    }
+  }
+  blank_sum = warp_sum(blank_sum);
+  __syncwarp();
+  if (lane == 0) acc[blank] += blank_sum;
+  __syncwarp();
+  for (int k = lane; k < C; k += 32) g[k] = expf(p[k] - lt) - acc[k];
+}
+
+// one CTA per item.  dynamic smem: int path[T]; int counts[blockDim]
+__global__ void ctc_greedy_kernel(const float* __restrict__ logits, const int* __restrict__ len,
+                                  int T, int B, int C, int blank, int* __restrict__ out,
+                                  int* __restrict__ out_len) {
+  extern __shared__ int gsm[];
+  int* path = gsm;
+  int* counts = gsm + T;
+  const int b = blockIdx.x;
+  const int L = min(len[b], T);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int t = warp; t < L; t += nw) {
+    const float* p = logits + ((size_t)t * B + b) * C;
+    float best = kNegInf;
+    int bi = 0x7fffffff;
+    for (int k = lane; k < C; k += 32) {
+      float v = p[k];
+      if (v > best || (v == best && k < bi)) { best = v; bi = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) path[t] = bi;
+  }
+  __syncthreads();
+  const int seg = (L + blockDim.x - 1) / blockDim.x;
+  const int t0 = min(L, (int)threadIdx.x * seg), t1 = min(L, t0 + seg);
+  int cnt = 0;
+  for (int t = t0; t < t1; ++t) {
+    const int c = path[t];
+    if (c != blank && (t == 0 || c != path[t - 1])) ++cnt;
+  }
+  counts[threadIdx.x] = cnt;
+  __syncthreads();
+  // exclusive scan (blockDim <= 1024): simple Hillis-Steele in shared memory
+  for (int o = 1; o < blockDim.x; o <<= 1) {
+    int v = (threadIdx.x >= o) ? counts[threadIdx.x - o] : 0;
+    __syncthreads();
+    counts[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int pos = counts[threadIdx.x] - cnt;
+  int* o = out + (size_t)b * T;
+  for (int t = t0; t < t1; ++t) {
+    const int c = path[t];
+    if (c != blank && (t == 0 || c != path[t - 1])) o[pos++] = c;
+  }
+  const int total = counts[blockDim.x - 1];
+  if (threadIdx.x == 0) out_len[b] = total;
+  __syncthreads();
+  for (int t = total + threadIdx.x; t < T; t += blockDim.x) o[t] = -1;
+}
+
+}  // namespace rs
+
+using namespace rs;
+
+static inline int ctc_upad(int max_label_len) { return (int)align_up((size_t)(2 * max_label_len + 1), 32); }
+
+extern "C" size_t rs_ctc_workspace_bytes(int T, int B, int C, int max_label_len) {
+  (void)C;
+  size_t upad = ctc_upad(max_label_len);
+  size_t lse = align_up((size_t)T * B * sizeof(float), 256);
+  size_t lat = align_up((size_t)T * B * upad * sizeof(float), 256);
+  return lse + 2 * lat;
+}
+
+extern "C" int rs_ctc_loss_grad(const float* logits_d, const int32_t* labels_d,
+                                const int32_t* label_offsets_d, const int32_t* len_d, int T, int B,
+                                int C, int max_label_len, int blank, int beta_skip, float* loss_d,
+                                float* grad_d, void* ws_d, size_t ws_bytes, void* stream) {
+  RS_REQUIRE(T > 0 && B > 0 && C > 1, RS_ERR_INVALID, "rs_ctc_loss_grad: bad shape T=%d B=%d C=%d", T, B, C);
+  RS_REQUIRE(blank >= 0 && blank < C, RS_ERR_INVALID, "rs_ctc_loss_grad: blank %d outside [0,%d)", blank, C);
+  RS_REQUIRE(max_label_len >= 0, RS_ERR_INVALID, "rs_ctc_loss_grad: max_label_len < 0");
+  RS_REQUIRE(beta_skip == RS_CTC_BETA_SOURCE || beta_skip == RS_CTC_BETA_DEST, RS_ERR_INVALID,
+             "rs_ctc_loss_grad: unknown beta_skip %d", beta_skip);
+  RS_REQUIRE(ws_bytes >= rs_ctc_workspace_bytes(T, B, C, max_label_len), RS_ERR_WORKSPACE,
+             "rs_ctc_loss_grad: workspace %zu < %zu", ws_bytes, rs_ctc_workspace_bytes(T, B, C, max_label_len));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int upad = ctc_upad(max_label_len);
+  char* ws = (char*)ws_d;
+  float* lse = (float*)ws;
+  size_t lse_b = align_up((size_t)T * B * sizeof(float), 256);
+  size_t lat_b = align_up((size_t)T * B * upad * sizeof(float), 256);
+  float* alpha = (float*)(ws + lse_b);
+  float* beta = (float*)(ws + lse_b + lat_b);
+
+  const int rows = T * B;
+  ctc_lse_kernel<<<cdiv(rows, 8), 256, 0, st>>>(logits_d, len_d, T, B, C, lse);
+  RS_CHECK_LAUNCH();
+  const int U = 2 * max_label_len + 1;
+  int threads = (int)align_up((size_t)U, 32);
+  if (threads > 1024) threads = 1024;
+  size_t smem = (size_t)upad * sizeof(int) + 2 * (size_t)(upad + 2) * sizeof(float);
+  RS_REQUIRE(smem <= 200 * 1024, RS_ERR_UNSUPPORTED, "rs_ctc_loss_grad: label length %d too large", max_label_len);
+  if (smem > 48 * 1024)
+    RS_CHECK_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctc_lattice_kernel<<<dim3(B, 2), threads, smem, st>>>(logits_d, lse, labels_d, label_offsets_d, len_d, T, B, C,
+                                                        upad, blank, beta_skip == RS_CTC_BETA_DEST ? 1 : 0,
+                                                        alpha, beta, loss_d);
+  RS_CHECK_LAUNCH();
+  if (grad_d) {
+    const int warps = 8;
+    size_t gsmem = (size_t)warps * C * sizeof(float);
+    RS_REQUIRE(gsmem <= 48 * 1024, RS_ERR_UNSUPPORTED, "rs_ctc_loss_grad: C=%d too large", C);
+    ctc_grad_kernel<<<cdiv(rows, warps), warps * 32, gsmem, st>>>(logits_d, lse, labels_d, label_offsets_d, len_d,
+                                                                  T, B, C, upad, blank, alpha, beta, loss_d, grad_d);
+    RS_CHECK_LAUNCH();
+  }
+  return RS_OK;
+}
+
+extern "C" int rs_ctc_greedy_decode(const float* logits_d, const int32_t* len_d, int T, int B, int C,
+                                    int blank, int32_t* out_d, int32_t* out_len_d, void* stream) {
+  RS_REQUIRE(T > 0 && B > 0 && C > 0, RS_ERR_INVALID, "rs_ctc_greedy_decode: bad shape T=%d B=%d C=%d", T, B, C);
+  const int threads = 256;
+  size_t smem = ((size_t)T + threads) * sizeof(int);
+  RS_REQUIRE(smem <= 200 * 1024, RS_ERR_UNSUPPORTED, "rs_ctc_greedy_decode: T=%d too large", T);
+  if (smem > 48 * 1024)
+    RS_CHECK_CUDA(cudaFuncSetAttribute(ctc_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctc_greedy_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(logits_d, len_d, T, B, C, blank, out_d, out_len_d);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}

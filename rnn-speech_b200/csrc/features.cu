@@ -1,0 +1,391 @@
+// Fused feature extraction for sm_100a.
+//
+// Replaces AudioProcessor._extract_fbank / _extract_mfcc
+// (/root/reference/util/audioprocessor.py:63-161) for a whole batch per call.
+//
+// fbank (120-dim):
+//   fbank_logmel_kernel  PCM tile -> shared memory (coalesced, read once) ->
+//                        pre-emphasis + Hamming -> two real frames packed into one
+//                        512-point complex FFT per warp (shared-memory radix-2
+//                        butterflies) -> |X|^2/512 -> 40 HTK-mel triangles -> 10 log10
+//                        -> log-mel [B,T,40] in the workspace + per-CTA column sums
+//   fbank_delta_kernel   per-utterance mean (from the partial sums) -> mean-norm ->
+//                        delta -> delta-delta -> [.,.,120] (batch- or time-major),
+//                        zero fill up to Tmax
+// The reference computes in float64; these kernels compute in fp32 with tables
+// built in double on the host (tolerances are stated in tests/test_features_gpu.py).
+#include "common.cuh"
+#include <mutex>
+#include <vector>
+#include <map>
+
+namespace rs {
+
+static constexpr int kNfft = 512;
+static constexpr int kBins = kNfft / 2 + 1;  // 257
+static constexpr int kNfilt = 40;
+static constexpr int kFramesPerCta = 32;
+static constexpr int kFbankWarps = 8;
+static constexpr double kPi = 3.14159265358979323846;
+
+// python3 round(): round half to even
+static inline int py_round(double x) {
+  double r = nearbyint(x);  // default rounding mode = to nearest even
+  return (int)r;
+}
+
+struct FrameParams { int frame_length, frame_step; };
+static inline FrameParams frame_params(int sr) {
+  FrameParams p;
+  p.frame_length = py_round(0.025 * sr);
+  p.frame_step = py_round(0.01 * sr);
+  return p;
+}
+static inline int64_t fbank_num_frames(int64_t n, const FrameParams& p) {
+  int64_t d = n - p.frame_length;
+  if (d < 0) d = -d;
+  return (d + p.frame_step - 1) / p.frame_step;   // ceil(|n - fl| / step)
+}
+
+// ---- host-built tables (double math, then rounded to fp32) ------------------
+struct FbankTables {
+  float window[kNfft];          // Hamming(frame_length) cropped / zero-padded to 512
+  float tw_re[kNfft / 2];       // exp(-2 pi i k / 512)
+  float tw_im[kNfft / 2];
+  float melw[kNfilt * kBins];   // dense [40][257]
+  int mstart[kNfilt];
+  int mend[kNfilt];
+};
+
+static void build_fbank_tables(int sr, FbankTables* t) {
+  FrameParams fp = frame_params(sr);
+  for (int i = 0; i < kNfft; ++i) {
+    double w = 0.0;
+    if (i < fp.frame_length) {
+      w = (fp.frame_length == 1) ? 1.0 : 0.54 - 0.46 * cos(2.0 * kPi * i / (fp.frame_length - 1));
+    }
+    t->window[i] = (float)w;
+  }
+  for (int k = 0; k < kNfft / 2; ++k) {
+    t->tw_re[k] = (float)cos(-2.0 * kPi * k / kNfft);
+    t->tw_im[k] = (float)sin(-2.0 * kPi * k / kNfft);
+  }
+  // util/audioprocessor.py:107-133
+  double high_mel = 2595.0 * log10(1.0 + ((double)sr / 2.0) / 700.0);
+  double bins[kNfilt + 2];
+  for (int i = 0; i < kNfilt + 2; ++i) {
+    // np.linspace(0, high_mel, 42): start + i*step with step = (stop-start)/41, last point exact
+    double mel = (i == kNfilt + 1) ? high_mel : i * (high_mel / (kNfilt + 1));
+    double hz = 700.0 * (pow(10.0, mel / 2595.0) - 1.0);
+    bins[i] = floor((kNfft + 1) * hz / sr);
+  }
+  for (int i = 0; i < kNfilt * kBins; ++i) t->melw[i] = 0.f;
+  for (int m = 1; m <= kNfilt; ++m) {
+    int lo = (int)bins[m - 1], ce = (int)bins[m], hi = (int)bins[m + 1];
+    for (int k = lo; k < ce && k < kBins; ++k)
+      t->melw[(m - 1) * kBins + k] = (float)((k - bins[m - 1]) / (bins[m] - bins[m - 1]));
+    for (int k = ce; k < hi && k < kBins; ++k)
+      t->melw[(m - 1) * kBins + k] = (float)((bins[m + 1] - k) / (bins[m + 1] - bins[m]));
+    t->mstart[m - 1] = lo < kBins ? lo : kBins;
+    t->mend[m - 1] = hi < kBins ? hi : kBins;
+  }
+}
+
+static const FbankTables* get_fbank_tables(int sr) {
+  static std::mutex mu;
+  static std::map<int, FbankTables*> cache;
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(sr);
+  if (it != cache.end()) return it->second;
+  FbankTables* t = new FbankTables();
+  build_fbank_tables(sr, t);
+  cache[sr] = t;
+  return t;
+}
+
+// ---- kernels ------------------------------------------------------------------
+
+__device__ __forceinline__ int bitrev9(int x) { return (int)(__brev((unsigned)x) >> 23); }
+
+// grid (ceil(Tfull_max / 32), B), 256 threads.
+// dynamic smem: float pcm[span + 1]; float fft[8 warps][2][512]; float pw[8][2][257(+pad)]
+__global__ void __launch_bounds__(kFbankWarps * 32)
+fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ offsets,
+                    const FbankTables* __restrict__ tab, int frame_length, int frame_step,
+                    int Tstride, int nblk, float* __restrict__ logmel, float* __restrict__ partial,
+                    int* __restrict__ nframes_out) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.y;
+  const int64_t off = offsets[b];
+  const int64_t n = offsets[b + 1] - off;
+  int64_t d = n - frame_length; if (d < 0) d = -d;
+  const int T = (int)((d + frame_step - 1) / frame_step);
+  if (blockIdx.x == 0 && threadIdx.x == 0) nframes_out[b] = T;
+  const int t0 = blockIdx.x * kFramesPerCta;
+  float* part = partial + ((size_t)b * nblk + blockIdx.x) * kNfilt;
+  if (t0 >= T) {
+    if (threadIdx.x < kNfilt) part[threadIdx.x] = 0.f;
+    return;
+  }
+  const int nfr = min(kFramesPerCta, T - t0);
+  const int nuse = min(frame_length, kNfft);       // rfft(frames, 512) crops or zero-pads
+  const int span = (kFramesPerCta - 1) * frame_step + nuse;
+  float* spcm = sm;                                 // [span + 1], spcm[i] = x[s0 - 1 + i]
+  float* sfft = spcm + ((span + 1 + 3) & ~3);       // [8][2][512]
+  float* spw = sfft + kFbankWarps * 2 * kNfft;      // [8][2][260]
+  float* scol = spw + kFbankWarps * 2 * 260;        // [8][40] per-warp column sums
+  const int64_t s0 = (int64_t)t0 * frame_step;
+  const float* x = pcm + off;
+  for (int i = threadIdx.x; i < span + 1; i += blockDim.x) {
+    int64_t s = s0 - 1 + i;
+    spcm[i] = (s >= 0 && s < n) ? x[s] : 0.f;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = lane; i < kNfilt; i += 32) scol[warp * kNfilt + i] = 0.f;
+  __syncthreads();
+
+  float* re = sfft + warp * 2 * kNfft;
+  float* im = re + kNfft;
+  float* pw = spw + warp * 2 * 260;
+  const float* __restrict__ win = tab->window;
+  const float* __restrict__ twr = tab->tw_re;
+  const float* __restrict__ twi = tab->tw_im;
+
+  for (int pair = warp; pair * 2 < nfr; pair += kFbankWarps) {
+    const int fa = pair * 2, fb = fa + 1;
+    const bool has_b = fb < nfr;
+    // load (pre-emphasis, window) in bit-reversed order: frame A -> re, frame B -> im
+    for (int i = lane; i < kNfft; i += 32) {
+      float va = 0.f, vb = 0.f;
+      if (i < nuse) {
+        const float w = win[i];
+        {
+          const int p = fa * frame_step + i + 1;         // index into spcm (shifted by one)
+          const int64_t s = s0 + fa * frame_step + i;    // absolute sample
+          // y[0] = x[0]; y[s] = x[s] - 0.97 x[s-1]; zero beyond the signal
+          float cur = spcm[p], prev = (s > 0) ? spcm[p - 1] : 0.f;
+          va = (s < n) ? (cur - 0.97f * prev) * w : 0.f;
+        }
+        if (has_b) {
+          const int p = fb * frame_step + i + 1;
+          const int64_t s = s0 + fb * frame_step + i;
+          float cur = spcm[p], prev = (s > 0) ? spcm[p - 1] : 0.f;
+          vb = (s < n) ? (cur - 0.97f * prev) * w : 0.f;
+        }
+      }
+      const int r = bitrev9(i);
+      re[r] = va;
+      im[r] = vb;
+    }
+    __syncwarp();
+    // 9 radix-2 DIT stages
+#pragma unroll 1
+    for (int s = 1; s <= 9; ++s) {
+      const int half = 1 << (s - 1);
+      const int tstep = kNfft >> s;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int i = lane + 32 * r;
+        const int pos = i & (half - 1);
+        const int a = ((i >> (s - 1)) << s) + pos;
+        const int bb = a + half;
+        const float wr = twr[pos * tstep], wi = twi[pos * tstep];
+        const float xr = re[bb], xi = im[bb];
+        const float tr = wr * xr - wi * xi, ti = wr * xi + wi * xr;
+        const float ar = re[a], ai = im[a];
+        re[a] = ar + tr; im[a] = ai + ti;
+        re[bb] = ar - tr; im[bb] = ai - ti;
+      }
+      __syncwarp();
+    }
+    // unpack the two real spectra, power = |X|^2 / 512
+    for (int k = lane; k < kBins; k += 32) {
+      const int nk = (kNfft - k) & (kNfft - 1);
+      const float zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
+      const float ar = 0.5f * (zr + yr), ai = 0.5f * (zi - yi);
+      const float br = 0.5f * (zi + yi), bi = -0.5f * (zr - yr);
+      pw[k] = (ar * ar + ai * ai) * (1.0f / kNfft);
+      pw[260 + k] = (br * br + bi * bi) * (1.0f / kNfft);
+    }
+    __syncwarp();
+    // 40 triangular filters; one lane owns filter m for BOTH frames of the pair so the
+    // per-warp column sums are accumulated in a fixed order (deterministic).
+    for (int m = lane; m < kNfilt; m += 32) {
+      const float* w = tab->melw + m * kBins;
+      float acc_a = 0.f, acc_b = 0.f;
+      const int k1 = tab->mend[m];
+      for (int k = tab->mstart[m]; k < k1; ++k) {
+        const float wk = w[k];
+        acc_a = fmaf(pw[k], wk, acc_a);
+        acc_b = fmaf(pw[260 + k], wk, acc_b);
+      }
+      if (acc_a == 0.f) acc_a = 2.220446049250313e-16f;   // util/audioprocessor.py:135
+      if (acc_b == 0.f) acc_b = 2.220446049250313e-16f;
+      const float va = 10.0f * log10f(acc_a);
+      float colsum = va;
+      logmel[((size_t)b * Tstride + (t0 + fa)) * kNfilt + m] = va;
+      if (has_b) {
+        const float vb = 10.0f * log10f(acc_b);
+        logmel[((size_t)b * Tstride + (t0 + fb)) * kNfilt + m] = vb;
+        colsum += vb;
+      }
+      scol[warp * kNfilt + m] += colsum;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < kNfilt) {
+    float s = 0.f;
+    for (int w = 0; w < kFbankWarps; ++w) s += scol[w * kNfilt + threadIdx.x];
+    part[threadIdx.x] = s;
+  }
+}
+
+// grid (ceil(Tmax / 32), B), 256 threads
+__global__ void __launch_bounds__(256)
+fbank_delta_kernel(const float* __restrict__ logmel, const float* __restrict__ partial,
+                   const int* __restrict__ nframes, int Tstride, int nblk, int Tmax, int B,
+                   int delta_mode, int time_major, float* __restrict__ out) {
+  constexpr int TT = 32;
+  __shared__ float xs[(TT + 32) * kNfilt];
+  __shared__ float d1[(TT + 16) * kNfilt];
+  __shared__ float mean[kNfilt];
+  const int b = blockIdx.y;
+  const int T = nframes[b];
+  const int t0 = blockIdx.x * TT;
+  const int Tout = min(T, Tmax);
+  auto out_row = [&](int t) -> float* {
+    return time_major ? out + ((size_t)t * B + b) * RS_FBANK_DIM : out + ((size_t)b * Tmax + t) * RS_FBANK_DIM;
+  };
+  if (t0 >= Tout) {   // pure zero fill
+    for (int i = threadIdx.x; i < TT * RS_FBANK_DIM; i += blockDim.x) {
+      int t = t0 + i / RS_FBANK_DIM;
+      if (t < Tmax) out_row(t)[i % RS_FBANK_DIM] = 0.f;
+    }
+    return;
+  }
+  if (threadIdx.x < kNfilt) {
+    // deterministic fixed-order sum of the per-CTA partials (double accumulate)
+    double s = 0.0;
+    for (int i = 0; i < nblk; ++i) s += (double)partial[((size_t)b * nblk + i) * kNfilt + threadIdx.x];
+    mean[threadIdx.x] = (float)(s / (double)T + 1e-8);
+  }
+  __syncthreads();
+  // halos: delta-delta at frame t reads d1 in [t-8, t+8] ('interp' edge frames use a
+  // centre up to 4 frames away), and d1 at frame i reads x in [i-8, i+8].
+  const int xlo = t0 - 16;    // xs row r <-> frame xlo + r
+  for (int i = threadIdx.x; i < (TT + 32) * kNfilt; i += blockDim.x) {
+    const int t = xlo + i / kNfilt, m = i % kNfilt;
+    xs[i] = (t >= 0 && t < T) ? logmel[((size_t)b * Tstride + t) * kNfilt + m] - mean[m] : 0.f;
+  }
+  __syncthreads();
+  const int half = 4;
+  const float inv = delta_mode == RS_DELTA_INTERP ? (1.0f / 60.0f) : (1.0f / 20.0f);
+  // centre index used for output frame t
+  auto centre = [&](int t) -> int {
+    if (delta_mode == RS_DELTA_INTERP) return min(max(t, half), T - 1 - half);
+    return t;
+  };
+  auto clampi = [&](int t) -> int { return min(max(t, 0), T - 1); };
+  const int dlo = t0 - 8;     // d1 row r <-> frame dlo + r
+  for (int i = threadIdx.x; i < (TT + 16) * kNfilt; i += blockDim.x) {
+    const int t = dlo + i / kNfilt, m = i % kNfilt;
+    float v = 0.f;
+    if (t >= 0 && t < T) {
+      const int c = centre(t);
+#pragma unroll
+      for (int j = -half; j <= half; ++j) v += (float)j * xs[(clampi(c + j) - xlo) * kNfilt + m];
+      v *= inv;
+    }
+    d1[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TT * kNfilt; i += blockDim.x) {
+    const int t = t0 + i / kNfilt, m = i % kNfilt;
+    if (t >= Tmax) continue;
+    float* o = out_row(t);
+    if (t < Tout) {
+      const int c = centre(t);
+      float v = 0.f;
+#pragma unroll
+      for (int j = -half; j <= half; ++j) v += (float)j * d1[(clampi(c + j) - dlo) * kNfilt + m];
+      o[m] = xs[(t - xlo) * kNfilt + m];
+      o[kNfilt + m] = d1[(t - dlo) * kNfilt + m];
+      o[2 * kNfilt + m] = v * inv;
+    } else {
+      o[m] = 0.f; o[kNfilt + m] = 0.f; o[2 * kNfilt + m] = 0.f;
+    }
+  }
+}
+
+}  // namespace rs
+
+using namespace rs;
+
+static size_t fbank_tables_bytes() { return align_up(sizeof(FbankTables), 256); }
+
+extern "C" size_t rs_fbank_workspace_bytes(int B, int64_t max_samples, int sr) {
+  FrameParams fp = frame_params(sr);
+  int64_t Tfull = fbank_num_frames(max_samples, fp);
+  int64_t nblk = (Tfull + kFramesPerCta - 1) / kFramesPerCta;
+  if (nblk < 1) nblk = 1;
+  return fbank_tables_bytes() + align_up((size_t)B * Tfull * kNfilt * sizeof(float), 256) +
+         align_up((size_t)B * nblk * kNfilt * sizeof(float), 256);
+}
+
+// Host-side table dump for the CPU tests (no device work): dense mel weights
+// [40*257] and the frame parameters the kernels will use.
+extern "C" int rs_fbank_tables_host(int sr, float* melw_out, float* window_out, int* frame_length,
+                                    int* frame_step) {
+  RS_REQUIRE(sr > 0, RS_ERR_INVALID, "rs_fbank_tables_host: sr must be positive");
+  const FbankTables* t = get_fbank_tables(sr);
+  if (melw_out) for (int i = 0; i < kNfilt * kBins; ++i) melw_out[i] = t->melw[i];
+  if (window_out) for (int i = 0; i < kNfft; ++i) window_out[i] = t->window[i];
+  FrameParams fp = frame_params(sr);
+  if (frame_length) *frame_length = fp.frame_length;
+  if (frame_step) *frame_step = fp.frame_step;
+  return RS_OK;
+}
+
+extern "C" int64_t rs_fbank_num_frames(int64_t n, int sr) {
+  return fbank_num_frames(n, frame_params(sr));
+}
+
+extern "C" int rs_fbank_forward(const float* pcm_d, const int64_t* offsets_d, int B, int64_t max_samples,
+                                int sr, int Tmax, int delta_mode, int time_major, float* out_d,
+                                int32_t* nframes_d, void* ws_d, size_t ws_bytes, void* stream) {
+  RS_REQUIRE(B > 0 && Tmax > 0 && sr > 0 && max_samples > 0, RS_ERR_INVALID,
+             "rs_fbank_forward: bad arguments B=%d Tmax=%d sr=%d max_samples=%lld", B, Tmax, sr, (long long)max_samples);
+  RS_REQUIRE(delta_mode == RS_DELTA_INTERP || delta_mode == RS_DELTA_EDGE, RS_ERR_INVALID,
+             "rs_fbank_forward: unknown delta_mode %d", delta_mode);
+  RS_REQUIRE(ws_bytes >= rs_fbank_workspace_bytes(B, max_samples, sr), RS_ERR_WORKSPACE,
+             "rs_fbank_forward: workspace %zu < %zu", ws_bytes, rs_fbank_workspace_bytes(B, max_samples, sr));
+  cudaStream_t st = (cudaStream_t)stream;
+  FrameParams fp = frame_params(sr);
+  RS_REQUIRE(fp.frame_step > 0 && fp.frame_length > 0, RS_ERR_INVALID, "rs_fbank_forward: sr %d too small", sr);
+  const int64_t Tfull64 = fbank_num_frames(max_samples, fp);
+  RS_REQUIRE(Tfull64 > 0 && Tfull64 < (1 << 30), RS_ERR_INVALID, "rs_fbank_forward: frame count %lld", (long long)Tfull64);
+  const int Tfull = (int)Tfull64;
+  const int nblk = cdiv(Tfull, kFramesPerCta);
+  char* ws = (char*)ws_d;
+  FbankTables* tab_d = (FbankTables*)ws;
+  float* logmel = (float*)(ws + fbank_tables_bytes());
+  float* partial = (float*)(ws + fbank_tables_bytes() + align_up((size_t)B * Tfull * kNfilt * sizeof(float), 256));
+  const FbankTables* tab_h = get_fbank_tables(sr);
+  RS_CHECK_CUDA(cudaMemcpyAsync(tab_d, tab_h, sizeof(FbankTables), cudaMemcpyHostToDevice, st));
+
+  const int nuse = fp.frame_length < kNfft ? fp.frame_length : kNfft;
+  const int span = (kFramesPerCta - 1) * fp.frame_step + nuse;
+  size_t smem = (size_t)(((span + 1 + 3) & ~3) + kFbankWarps * 2 * kNfft + kFbankWarps * 2 * 260 +
+                         kFbankWarps * kNfilt) * sizeof(float);
+  RS_REQUIRE(smem <= 220 * 1024, RS_ERR_UNSUPPORTED, "rs_fbank_forward: sr %d needs %zu B smem", sr, smem);
+  RS_CHECK_CUDA(cudaFuncSetAttribute(fbank_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fbank_logmel_kernel<<<dim3(nblk, B), kFbankWarps * 32, smem, st>>>(pcm_d, offsets_d, tab_d, fp.frame_length,
+                                                                     fp.frame_step, Tfull, nblk, logmel, partial,
+                                                                     nframes_d);
+  RS_CHECK_LAUNCH();
+  fbank_delta_kernel<<<dim3(cdiv(Tmax, 32), B), 256, 0, st>>>(logmel, partial, nframes_d, Tfull, nblk, Tmax, B,
+                                                              delta_mode, time_major, out_d);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}

@@ -1,0 +1,361 @@
+// Acoustic model (input dense -> L x LSTM -> output dense) forward / backward
+// orchestration behind the rs_am_* C ABI.
+//
+// Replaces AcousticModel._build_base_rnn (/root/reference/models/AcousticModel.py:189-317)
+// and the gradient half of _add_training_on_rnn (:386-401).  See oracle/model.py
+// for the restated TF semantics this follows.
+#include "common.cuh"
+#include "gemm.cuh"
+#include "lstm_rec.cuh"
+
+struct rs_am {
+  int L, H, F, C, B, Tmax;
+  int64_t n_params;
+  int64_t off_input_w, off_input_b, off_output_w, off_output_b;
+  int64_t off_kernel[64], off_bias[64];
+  // optional per-kernel timing of the recurrent kernels (CUDA events on the launch stream)
+  int timing;
+  cudaEvent_t ev[2][64][2];     // [fwd|bwd][layer][start|stop]
+  int ev_valid[2][64];
+};
+
+namespace rs {
+namespace {
+
+// out = in * keep_mask(stream a) / keep_a * keep_mask(stream b) / keep_b
+// (either factor may be disabled with thr == 0xffffffff)
+__global__ void dropout2_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n, uint64_t key,
+                                uint32_t sa, uint32_t thr_a, float inv_a, uint32_t sb, uint32_t thr_b,
+                                float inv_b) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = in[i];
+    if (thr_a != 0xffffffffu) v = dropout_keep(key, sa, (uint64_t)i, thr_a) ? v * inv_a : 0.f;
+    if (thr_b != 0xffffffffu) v = dropout_keep(key, sb, (uint64_t)i, thr_b) ? v * inv_b : 0.f;
+    out[i] = v;
+  }
+}
+
+inline uint32_t thr24(float keep) { return keep >= 1.0f ? 0xffffffffu : (uint32_t)((double)keep * 16777216.0); }
+
+int dropout2(const float* in, float* out, int64_t n, uint64_t seed, int sa, float keep_a, int sb, float keep_b,
+             cudaStream_t st) {
+  const uint32_t ta = sa >= 0 ? thr24(keep_a) : 0xffffffffu, tb = sb >= 0 ? thr24(keep_b) : 0xffffffffu;
+  int grid = (int)((n + 255) / 256);
+  const int cap = sm_count() * 16;
+  if (grid > cap) grid = cap;
+  dropout2_kernel<<<grid, 256, 0, st>>>(in, out, n, splitmix64(seed), (uint32_t)(sa < 0 ? 0 : sa), ta,
+                                        1.0f / keep_a, (uint32_t)(sb < 0 ? 0 : sb), tb, 1.0f / keep_b);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+// Buffer plan.  Everything is in floats; TBH = Tmax*B*H.
+struct Plan {
+  size_t TBH, TB4H, state;
+  // reserve (per layer): xin | out | gates | cs ; then top
+  size_t res_layer;      // floats per layer
+  size_t res_total;      // floats
+  // workspace: barrier (256 B) | gx (TB4H) | bufA, bufB, bufC (TBH each) | scratch reserve for inference
+  size_t ws_fixed;       // bytes before the inference reserve
+  size_t ws_total;       // bytes
+};
+
+Plan make_plan(const rs_am* am) {
+  Plan p;
+  p.TBH = (size_t)am->Tmax * am->B * am->H;
+  p.TB4H = 4 * p.TBH;
+  p.res_layer = p.TBH /*xin*/ + p.TBH /*out*/ + p.TB4H /*gates*/ + p.TBH /*cs*/;
+  p.state = (size_t)am->L * 2 * am->B * am->H;
+  p.res_total = p.res_layer * am->L + p.TBH /*top*/ + p.TBH /*rnn_in*/ + p.state /*initial state copy*/;
+  p.ws_fixed = 256 + (p.TB4H + 3 * p.TBH) * sizeof(float);
+  // inference (reserve == NULL): ping-pong activations + the state copy live in the workspace
+  p.ws_total = p.ws_fixed + (3 * p.TBH + p.state) * sizeof(float);
+  return p;
+}
+
+}  // namespace
+}  // namespace rs
+
+using namespace rs;
+
+extern "C" int rs_am_create(rs_am** out, int num_layers, int hidden_size, int input_dim, int num_labels,
+                            int batch_size, int max_T) {
+  RS_REQUIRE(out != nullptr, RS_ERR_INVALID, "rs_am_create: out is NULL");
+  RS_REQUIRE(num_layers > 0 && num_layers <= 64, RS_ERR_INVALID, "rs_am_create: num_layers %d outside [1,64]", num_layers);
+  RS_REQUIRE(hidden_size > 0 && input_dim > 0 && num_labels > 1 && batch_size > 0 && max_T > 0, RS_ERR_INVALID,
+             "rs_am_create: non-positive dimension");
+  RS_REQUIRE(hidden_size <= kRecMaxH, RS_ERR_UNSUPPORTED, "rs_am_create: hidden_size %d > %d", hidden_size, kRecMaxH);
+  RS_REQUIRE(batch_size <= kRecMaxB, RS_ERR_UNSUPPORTED, "rs_am_create: batch_size %d > %d", batch_size, kRecMaxB);
+  rs_am* am = new rs_am();
+  am->L = num_layers; am->H = hidden_size; am->F = input_dim; am->C = num_labels;
+  am->B = batch_size; am->Tmax = max_T;
+  int64_t off = 0;
+  const int64_t H = hidden_size;
+  am->off_input_w = off; off += (int64_t)input_dim * H;
+  am->off_input_b = off; off += H;
+  for (int l = 0; l < num_layers; ++l) {
+    am->off_kernel[l] = off; off += 2 * H * 4 * H;
+    am->off_bias[l] = off; off += 4 * H;
+  }
+  am->off_output_w = off; off += H * num_labels;
+  am->off_output_b = off; off += num_labels;
+  am->n_params = off;
+  am->timing = 0;
+  for (int d = 0; d < 2; ++d)
+    for (int l = 0; l < 64; ++l) am->ev_valid[d][l] = 0;
+  *out = am;
+  return RS_OK;
+}
+
+extern "C" void rs_am_destroy(rs_am* am) {
+  if (!am) return;
+  if (am->timing)
+    for (int d = 0; d < 2; ++d)
+      for (int l = 0; l < am->L; ++l) { cudaEventDestroy(am->ev[d][l][0]); cudaEventDestroy(am->ev[d][l][1]); }
+  delete am;
+}
+
+extern "C" int rs_am_enable_timing(rs_am* am, int enable) {
+  RS_REQUIRE(am != nullptr, RS_ERR_INVALID, "rs_am_enable_timing: NULL handle");
+  if (enable && !am->timing) {
+    for (int d = 0; d < 2; ++d)
+      for (int l = 0; l < am->L; ++l) {
+        RS_CHECK_CUDA(cudaEventCreate(&am->ev[d][l][0]));
+        RS_CHECK_CUDA(cudaEventCreate(&am->ev[d][l][1]));
+      }
+    am->timing = 1;
+  }
+  return RS_OK;
+}
+
+extern "C" int rs_am_recurrent_ms(rs_am* am, int backward, int layer, float* ms) {
+  RS_REQUIRE(am && ms && am->timing, RS_ERR_INVALID, "rs_am_recurrent_ms: timing not enabled");
+  RS_REQUIRE(layer >= 0 && layer < am->L && (backward == 0 || backward == 1), RS_ERR_INVALID,
+             "rs_am_recurrent_ms: bad index");
+  RS_REQUIRE(am->ev_valid[backward][layer], RS_ERR_INVALID, "rs_am_recurrent_ms: kernel has not run");
+  RS_CHECK_CUDA(cudaEventSynchronize(am->ev[backward][layer][1]));
+  RS_CHECK_CUDA(cudaEventElapsedTime(ms, am->ev[backward][layer][0], am->ev[backward][layer][1]));
+  return RS_OK;
+}
+
+extern "C" int64_t rs_am_param_count(const rs_am* am) { return am ? am->n_params : -1; }
+
+extern "C" int64_t rs_am_param_offset(const rs_am* am, int which, int layer) {
+  if (!am) return -1;
+  switch (which) {
+    case 0: return am->off_input_w;
+    case 1: return am->off_input_b;
+    case 2: return (layer >= 0 && layer < am->L) ? am->off_kernel[layer] : -1;
+    case 3: return (layer >= 0 && layer < am->L) ? am->off_bias[layer] : -1;
+    case 4: return am->off_output_w;
+    case 5: return am->off_output_b;
+  }
+  return -1;
+}
+
+extern "C" size_t rs_am_reserve_bytes(const rs_am* am) { return am ? make_plan(am).res_total * sizeof(float) : 0; }
+extern "C" size_t rs_am_workspace_bytes(const rs_am* am) { return am ? make_plan(am).ws_total : 0; }
+
+namespace {
+struct Bufs {
+  unsigned* barrier;
+  float *gx, *bufA, *bufB, *bufC;
+  float* rnn_in;
+  float* top;
+  float* state0;   // [L,2,B,H] copy of the initial state of this call
+  float *xin[64], *out[64], *gates[64], *cs[64];
+};
+
+// Carve the workspace and the reserve (or, for inference, the workspace tail).
+Bufs carve(const rs_am* am, const Plan& p, void* reserve, void* ws) {
+  Bufs b;
+  char* w = (char*)ws;
+  b.barrier = (unsigned*)w;
+  float* f = (float*)(w + 256);
+  b.gx = f; f += p.TB4H;
+  b.bufA = f; f += p.TBH;
+  b.bufB = f; f += p.TBH;
+  b.bufC = f; f += p.TBH;
+  if (reserve) {
+    float* r = (float*)reserve;
+    for (int l = 0; l < am->L; ++l) {
+      b.xin[l] = r; r += p.TBH;
+      b.out[l] = r; r += p.TBH;
+      b.gates[l] = r; r += p.TB4H;
+      b.cs[l] = r; r += p.TBH;
+    }
+    b.top = r; r += p.TBH;
+    b.rnn_in = r; r += p.TBH;
+    b.state0 = r;
+  } else {
+    // inference: layer l reads xin from one ping-pong buffer and writes out to the other
+    float* t0 = f; float* t1 = f + p.TBH; float* t2 = f + 2 * p.TBH;
+    for (int l = 0; l < am->L; ++l) {
+      b.xin[l] = (l & 1) ? t1 : t0;
+      b.out[l] = (l & 1) ? t0 : t1;
+      b.gates[l] = nullptr;
+      b.cs[l] = nullptr;
+    }
+    b.top = t2;
+    b.rnn_in = t2;
+    b.state0 = f + 3 * p.TBH;
+  }
+  return b;
+}
+
+// Without dropout the hop out[l] -> xin[l+1] (and out[L-1] -> top) is the identity:
+// alias the buffers instead of copying.  Forward and backward apply the same rule.
+void alias_identity_hops(Bufs& b, int L, bool drop_in, bool drop_out) {
+  if (drop_in || drop_out) {
+    if (!drop_out) b.top = b.out[L - 1];
+    return;
+  }
+  for (int l = 0; l + 1 < L; ++l) b.xin[l + 1] = b.out[l];
+  b.top = b.out[L - 1];
+}
+}  // namespace
+
+extern "C" int rs_am_forward(rs_am* am, const float* params_d, const float* x_d, const int32_t* len_d, int T,
+                             const float* state_in_d, float* state_out_d, float keep_in, float keep_out,
+                             uint64_t seed, float* logits_d, void* reserve_d, void* ws_d, size_t ws_bytes,
+                             void* stream) {
+  RS_REQUIRE(am && params_d && x_d && len_d && logits_d && ws_d, RS_ERR_INVALID, "rs_am_forward: NULL argument");
+  RS_REQUIRE(T > 0 && T <= am->Tmax, RS_ERR_INVALID, "rs_am_forward: T=%d outside [1,%d]", T, am->Tmax);
+  RS_REQUIRE(keep_in > 0.f && keep_in <= 1.f && keep_out > 0.f && keep_out <= 1.f, RS_ERR_INVALID,
+             "rs_am_forward: keep probabilities must be in (0,1]");
+  const Plan p = make_plan(am);
+  RS_REQUIRE(ws_bytes >= p.ws_total, RS_ERR_WORKSPACE, "rs_am_forward: workspace %zu < %zu", ws_bytes, p.ws_total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = am->L, H = am->H, F = am->F, C = am->C, B = am->B;
+  const int TB = T * B;
+  const int64_t nTBH = (int64_t)TB * H;
+  Bufs bf = carve(am, p, reserve_d, ws_d);
+  int rc;
+
+  // Private copy of the initial state: state_out_d may alias state_in_d, and backward
+  // must differentiate against the state this call STARTED from.
+  if (state_in_d)
+    RS_CHECK_CUDA(cudaMemcpyAsync(bf.state0, state_in_d, p.state * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  else
+    RS_CHECK_CUDA(cudaMemsetAsync(bf.state0, 0, p.state * sizeof(float), st));
+
+  // input dense: rnn_in = x @ w_i + b_i                         (models/AcousticModel.py:247-250)
+  const bool drop_in = keep_in < 1.f, drop_out = keep_out < 1.f;
+  alias_identity_hops(bf, L, drop_in, drop_out);
+  float* rnn_in = drop_in ? bf.rnn_in : bf.xin[0];
+  if ((rc = sgemm(0, 0, TB, H, F, x_d, F, params_d + am->off_input_w, H, rnn_in, H,
+                  params_d + am->off_input_b, 0, st)) != RS_OK) return rc;
+  if (drop_in)
+    if ((rc = dropout2(rnn_in, bf.xin[0], nTBH, seed, 0, keep_in, -1, 1.f, st)) != RS_OK) return rc;
+
+  for (int l = 0; l < L; ++l) {
+    const float* K = params_d + am->off_kernel[l];
+    const float* bias = params_d + am->off_bias[l];
+    // hoisted input half: gx = xin @ K[:H] + b                  (BasicLSTMCell: [x,h] @ kernel + bias)
+    if ((rc = sgemm(0, 0, TB, 4 * H, H, bf.xin[l], H, K, 4 * H, bf.gx, 4 * H, bias, 0, st)) != RS_OK) return rc;
+    RecFwdArgs a;
+    a.gx = bf.gx;
+    a.Wh = K + (size_t)H * 4 * H;
+    a.len = len_d;
+    a.c0 = bf.state0 + ((size_t)l * 2 + 0) * B * H;
+    a.h0 = bf.state0 + ((size_t)l * 2 + 1) * B * H;
+    a.cT = state_out_d ? state_out_d + ((size_t)l * 2 + 0) * B * H : nullptr;
+    a.hT = state_out_d ? state_out_d + ((size_t)l * 2 + 1) * B * H : nullptr;
+    a.out = bf.out[l];
+    a.gates = bf.gates[l];
+    a.cs = bf.cs[l];
+    a.barrier = bf.barrier;
+    a.T = T; a.B = B; a.H = H;
+    if (am->timing) RS_CHECK_CUDA(cudaEventRecord(am->ev[0][l][0], st));
+    if ((rc = lstm_rec_forward(a, st)) != RS_OK) return rc;
+    if (am->timing) { RS_CHECK_CUDA(cudaEventRecord(am->ev[0][l][1], st)); am->ev_valid[0][l] = 1; }
+    // cell-output dropout, then the next cell's input dropout   (DropoutWrapper, :232-233)
+    float* next = (l + 1 < L) ? bf.xin[l + 1] : bf.top;
+    if (next == bf.out[l]) continue;   // identity hop, aliased
+    if (l + 1 < L) {
+      if ((rc = dropout2(bf.out[l], next, nTBH, seed, drop_out ? 2 * l + 1 : -1, keep_out,
+                         drop_in ? 2 * (l + 1) : -1, keep_in, st)) != RS_OK) return rc;
+    } else {
+      if ((rc = dropout2(bf.out[l], next, nTBH, seed, drop_out ? 2 * l + 1 : -1, keep_out, -1, 1.f, st)) != RS_OK)
+        return rc;
+    }
+  }
+  // output dense                                               (models/AcousticModel.py:308-309)
+  return sgemm(0, 0, TB, C, H, bf.top, H, params_d + am->off_output_w, C, logits_d, C,
+               params_d + am->off_output_b, 0, st);
+}
+
+extern "C" int rs_am_backward(rs_am* am, const float* params_d, const float* x_d, const int32_t* len_d, int T,
+                              float keep_in, float keep_out, uint64_t seed, const float* dlogits_d,
+                              void* reserve_d, float* grads_d, void* ws_d, size_t ws_bytes, void* stream) {
+  RS_REQUIRE(am && params_d && x_d && len_d && dlogits_d && reserve_d && grads_d && ws_d, RS_ERR_INVALID,
+             "rs_am_backward: NULL argument");
+  RS_REQUIRE(T > 0 && T <= am->Tmax, RS_ERR_INVALID, "rs_am_backward: T=%d outside [1,%d]", T, am->Tmax);
+  RS_REQUIRE(keep_in > 0.f && keep_in <= 1.f && keep_out > 0.f && keep_out <= 1.f, RS_ERR_INVALID,
+             "rs_am_backward: keep probabilities must be in (0,1]");
+  const Plan p = make_plan(am);
+  RS_REQUIRE(ws_bytes >= p.ws_total, RS_ERR_WORKSPACE, "rs_am_backward: workspace %zu < %zu", ws_bytes, p.ws_total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = am->L, H = am->H, F = am->F, C = am->C, B = am->B;
+  const int TB = T * B;
+  const int64_t nTBH = (int64_t)TB * H;
+  Bufs bf = carve(am, p, reserve_d, ws_d);
+  int rc;
+  const bool drop_in = keep_in < 1.f, drop_out = keep_out < 1.f;
+  alias_identity_hops(bf, L, drop_in, drop_out);
+
+  // output dense
+  if ((rc = sgemm(1, 0, H, C, TB, bf.top, H, dlogits_d, C, grads_d + am->off_output_w, C, nullptr, 1, st)) != RS_OK) return rc;
+  if ((rc = colsum(dlogits_d, TB, C, C, grads_d + am->off_output_b, 1, st)) != RS_OK) return rc;
+  // d(top) = dlogits @ w_o^T
+  float* dcur = bf.bufA;
+  if ((rc = sgemm(0, 1, TB, H, C, dlogits_d, C, params_d + am->off_output_w, C, dcur, H, nullptr, 0, st)) != RS_OK) return rc;
+
+  for (int l = L - 1; l >= 0; --l) {
+    const float* K = params_d + am->off_kernel[l];
+    float* gK = grads_d + am->off_kernel[l];
+    // through the dropout(s) that sit between out[l] and what consumed it
+    float* dout = bf.bufB;
+    const bool identity_hop = (l == L - 1) ? !drop_out : (!drop_out && !drop_in);
+    if (identity_hop) {
+      dout = dcur;
+    } else if (l == L - 1) {
+      if ((rc = dropout2(dcur, dout, nTBH, seed, drop_out ? 2 * l + 1 : -1, keep_out, -1, 1.f, st)) != RS_OK) return rc;
+    } else {
+      if ((rc = dropout2(dcur, dout, nTBH, seed, drop_out ? 2 * l + 1 : -1, keep_out,
+                         drop_in ? 2 * (l + 1) : -1, keep_in, st)) != RS_OK) return rc;
+    }
+    RecBwdArgs a;
+    a.dout = dout;
+    a.gates = bf.gates[l];
+    a.cs = bf.cs[l];
+    a.c0 = bf.state0 + ((size_t)l * 2 + 0) * B * H;
+    a.Wh = K + (size_t)H * 4 * H;
+    a.len = len_d;
+    a.barrier = bf.barrier;
+    a.T = T; a.B = B; a.H = H;
+    if (am->timing) RS_CHECK_CUDA(cudaEventRecord(am->ev[1][l][0], st));
+    if ((rc = lstm_rec_backward(a, st)) != RS_OK) return rc;
+    if (am->timing) { RS_CHECK_CUDA(cudaEventRecord(am->ev[1][l][1], st)); am->ev_valid[1][l] = 1; }
+    const float* dg = bf.gates[l];
+    // dK[:H] += xin^T @ dgates ; dK[H:] += hprev^T @ dgates ; db += colsum(dgates)
+    if ((rc = sgemm(1, 0, H, 4 * H, TB, bf.xin[l], H, dg, 4 * H, gK, 4 * H, nullptr, 1, st)) != RS_OK) return rc;
+    if (T > 1)
+      if ((rc = sgemm(1, 0, H, 4 * H, (T - 1) * B, bf.out[l], H, dg + (size_t)B * 4 * H, 4 * H,
+                      gK + (size_t)H * 4 * H, 4 * H, nullptr, 1, st)) != RS_OK) return rc;
+    // t = 0 term of the recurrent half: h_{-1} is the carried-in state
+    if ((rc = sgemm(1, 0, H, 4 * H, B, bf.state0 + ((size_t)l * 2 + 1) * B * H, H, dg, 4 * H,
+                    gK + (size_t)H * 4 * H, 4 * H, nullptr, 1, st)) != RS_OK) return rc;
+    if ((rc = colsum(dg, TB, 4 * H, 4 * H, grads_d + am->off_bias[l], 1, st)) != RS_OK) return rc;
+    // dxin = dgates @ K[:H]^T
+    if ((rc = sgemm(0, 1, TB, H, 4 * H, dg, 4 * H, K, 4 * H, dcur, H, nullptr, 0, st)) != RS_OK) return rc;
+  }
+  // through layer 0's input dropout, then the input dense
+  float* drnn = dcur;
+  if (drop_in) {
+    drnn = bf.bufB;
+    if ((rc = dropout2(dcur, drnn, nTBH, seed, 0, keep_in, -1, 1.f, st)) != RS_OK) return rc;
+  }
+  if ((rc = sgemm(1, 0, F, H, TB, x_d, F, drnn, H, grads_d + am->off_input_w, H, nullptr, 1, st)) != RS_OK) return rc;
+  return colsum(drnn, TB, H, H, grads_d + am->off_input_b, 1, st);
+}

@@ -1,0 +1,73 @@
+# coding=utf-8
+"""Input pipeline contract of AcousticModel.build_dataset
+(/root/reference/models/AcousticModel.py:801-840) without tf.data: an iterable of
+mini-batches ``(features [Tmax,B,F] float32 device, lengths [B] int32 device,
+dense labels [B, Lmax_in_batch] int32 host, zero-padded)``.
+
+The last, incomplete batch is padded to ``batch_size`` with zero features /
+length 0 / empty labels, as create_training_rnn does (:147-159).  Feature
+extraction for the whole mini-batch is one GPU launch sequence
+(AudioProcessor.process_batch).
+"""
+import logging
+
+import numpy as np
+import torch
+
+from . import labels as labelcodec
+from .audioprocessor import AudioProcessor
+
+
+class AudioBatchDataset(object):
+    def __init__(self, input_set, batch_size, max_input_seq_length, max_target_seq_length, signal_processing,
+                 char_map, device=None, delta_mode="interp"):
+        self.items = [[item[0], item[1]] for item in input_set]
+        self.batch_size = batch_size
+        self.max_input_seq_length = max_input_seq_length
+        self.max_target_seq_length = max_target_seq_length
+        self.char_map = char_map
+        self.audio_processor = AudioProcessor(max_input_seq_length, signal_processing, delta_mode=delta_mode,
+                                              device=device)
+
+    def __len__(self):
+        return (len(self.items) + self.batch_size - 1) // self.batch_size
+
+    def _load(self, audio):
+        if isinstance(audio, (tuple, list)):
+            return np.asarray(audio[0], dtype=np.float32), int(audio[1])
+        from .audiofile import load_audio
+        return load_audio(audio)
+
+    def __iter__(self):
+        B = self.batch_size
+        for start in range(0, len(self.items), B):
+            chunk = self.items[start:start + B]
+            sigs, srs, labs = [], [], []
+            for audio, label in chunk:
+                sig, sr = self._load(audio)
+                sigs.append(sig)
+                srs.append(sr)
+                labs.append(labelcodec.get_str_labels(self.char_map, label) if isinstance(label, str)
+                            else list(label))
+            if len(set(srs)) != 1:
+                raise ValueError("all utterances of a mini-batch must share one sample rate, got %s" % sorted(set(srs)))
+            n_real = len(sigs)
+            feats, nframes = self.audio_processor.process_batch(sigs, srs[0], time_major=True)
+            if n_real < B:      # pad the batch (features 0, length 0)
+                full = torch.zeros((feats.shape[0], B, feats.shape[2]), dtype=feats.dtype, device=feats.device)
+                full[:, :n_real] = feats
+                lens = torch.zeros((B,), dtype=torch.int32, device=feats.device)
+                lens[:n_real] = nframes
+                feats, nframes = full, lens
+            over = nframes > self.max_input_seq_length
+            if bool(over.any()):
+                # the reference would hand tf.nn.ctc_loss a length > Tmax and fail (TODO at
+                # models/AcousticModel.py:837-838); clamp instead and say so
+                logging.warning("utterance longer than max_input_seq_length: truncated to %d frames",
+                                self.max_input_seq_length)
+                nframes = torch.clamp(nframes, max=self.max_input_seq_length)
+            width = max([len(l) for l in labs] + [1])
+            dense = np.zeros((n_real, width), dtype=np.int32)
+            for i, l in enumerate(labs):
+                dense[i, :len(l)] = l
+            yield feats, nframes, dense

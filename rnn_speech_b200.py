@@ -1,0 +1,12 @@
+"""Loader: makes the package directory ``rnn-speech_b200/`` importable as
+``rnn_speech_b200`` (a hyphen is not a valid identifier)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "rnn-speech_b200")
+_spec = importlib.util.spec_from_file_location("rnn_speech_b200", os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["rnn_speech_b200"] = _mod
+_spec.loader.exec_module(_mod)

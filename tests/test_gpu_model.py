@@ -1,0 +1,157 @@
+"""GPU parity: the LSTM stack forward / backward (through the C ABI) against
+oracle/model.py (float64) and the golden vectors of BASELINE config 1.
+
+Tolerances (kernels accumulate in fp32): logits 2e-4 absolute, final state 1e-4,
+CTC loss 1e-4 relative (north-star gate 1e-3), gradients 1e-3 of the largest
+gradient entry.  Greedy label ids must be identical wherever the oracle's top-2
+logit margin exceeds MARGIN (frames closer than that are ties at fp32 resolution
+and are counted and reported, not compared).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import ctc, model
+
+pytestmark = pytest.mark.gpu
+MARGIN = 1e-3
+
+
+def _build(pkg, cuda, L, H, F, C, B, T, flat, training, ki=1.0, ko=1.0):
+    m = pkg.AcousticModel(L, H, B, T, 600, F, False, C, device=cuda)
+    if training:
+        m.create_training_rnn(ki, ko, 1, 3e-4, 0.33)
+    else:
+        m.create_forward_rnn()
+    m.load_flat_params(flat)
+    return m
+
+
+def _dev(a, cuda, dtype):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(cuda)
+
+
+def _assert_labels_match(logits_gpu, logits_oracle, lens):
+    margin = ctc.top2_margin(logits_oracle, lens)
+    safe = margin > MARGIN
+    same = logits_gpu.argmax(-1) == logits_oracle.argmax(-1)
+    valid = np.arange(logits_oracle.shape[0])[:, None] < np.asarray(lens)[None, :]
+    assert np.all(same[safe & valid]), "argmax differs on a frame with margin > %g" % MARGIN
+    n_tie = int((~safe & valid).sum())
+    return n_tie
+
+
+def test_cfg1_golden_forward_backward(pkg, cuda):
+    g = golden("model_cfg1.npz")
+    L, H, F, C, T, B = [int(v) for v in g["dims"]]
+    m = _build(pkg, cuda, L, H, F, C, B, T, g["flat_params"], training=True)
+    x, lens = _dev(g["x"], cuda, np.float32), _dev(g["lens"], cuda, np.int32)
+    labs = [g["lab_%d" % i] for i in range(B)]
+    logits = m.forward(x, lens, training=True)
+    np.testing.assert_allclose(logits.cpu().numpy(), g["logits"], atol=2e-4)
+    np.testing.assert_allclose(m.rnn_state[0, 0].cpu().numpy(), g["state_c"], atol=1e-4)
+    np.testing.assert_allclose(m.rnn_state[0, 1].cpu().numpy(), g["state_h"], atol=1e-4)
+    loss, grad = m.ctc_loss(logits, labs, lens)
+    np.testing.assert_allclose(loss.cpu().numpy(), g["loss"], rtol=1e-4)
+    m.grads.zero_()
+    m.backward(x, lens, grad)
+    got = m.grads.cpu().numpy()
+    scale = np.abs(g["flat_grads"]).max()
+    assert np.abs(got - g["flat_grads"]).max() < 1e-3 * scale
+    # greedy labels identical to the oracle's (bit-exact ids)
+    ids, n = m.greedy_decode(logits, lens)
+    want = ctc.greedy_decode(g["logits"], g["lens"])
+    ties = _assert_labels_match(logits.cpu().numpy(), g["logits"], g["lens"])
+    if ties == 0:
+        for b in range(B):
+            np.testing.assert_array_equal(ids[b, :int(n[b])].cpu().numpy(), want[b])
+
+
+@pytest.mark.parametrize("L,H,F,C,B,T,ki,ko", [
+    (2, 50, 20, 50, 3, 17, 1.0, 1.0),       # odd sizes (reference's own test model: L2 H50 C50)
+    (2, 64, 120, 80, 5, 33, 0.8, 0.5),      # dropout on both sides of every cell
+    (3, 128, 120, 80, 40, 12, 1.0, 1.0),    # batch > 32 (two batch chunks)
+])
+def test_random_models_with_state_and_dropout(pkg, cuda, L, H, F, C, B, T, ki, ko):
+    rng = np.random.default_rng(L * 1000 + H)
+    p = model.init_params(L, H, F, C, seed=1, dtype=np.float64)
+    for k in p:
+        if p[k].ndim == 1:
+            p[k] = rng.standard_normal(p[k].shape) * 0.1
+    flat = model.flatten(p, L, H, F, C)
+    x = rng.standard_normal((T, B, F))
+    lens = rng.integers(0, T + 1, size=B).astype(np.int32)
+    lens[0] = T
+    state = [(rng.standard_normal((B, H)) * .3, rng.standard_normal((B, H)) * .3) for _ in range(L)]
+    m = _build(pkg, cuda, L, H, F, C, B, T, flat, training=True, ki=ki, ko=ko)
+    st = np.stack([np.stack([c, h]) for c, h in state])                # [L,2,B,H]
+    m.rnn_state.copy_(_dev(st, cuda, np.float32))
+    xd, ld = _dev(x, cuda, np.float32), _dev(lens, cuda, np.int32)
+    logits = m.forward(xd, ld, training=True)
+    keep_in, keep_out, seed, _ = m._last_fwd
+    want, new_state, cache = model.forward(p, x, lens, L, H, state=state, keep_in=keep_in, keep_out=keep_out,
+                                           seed=seed)
+    np.testing.assert_allclose(logits.cpu().numpy(), want, atol=3e-4)
+    for l in range(L):
+        np.testing.assert_allclose(m.rnn_state[l, 0].cpu().numpy(), new_state[l][0], atol=2e-4)
+        np.testing.assert_allclose(m.rnn_state[l, 1].cpu().numpy(), new_state[l][1], atol=2e-4)
+    dl = rng.standard_normal(want.shape) * (np.arange(T)[:, None, None] < lens[None, :, None])
+    m.grads.zero_()
+    m.backward(xd, ld, _dev(dl, cuda, np.float32))
+    gw = model.flatten(model.backward(p, cache, dl, L, H), L, H, F, C)
+    got = m.grads.cpu().numpy()
+    assert np.abs(got - gw).max() < 1e-3 * np.abs(gw).max()
+    # accumulate semantics: a second forward/backward doubles the buffer (same seed & state)
+    m.rnn_state.copy_(_dev(st, cuda, np.float32))
+    m._dropout_calls -= 1
+    m.forward(xd, ld, training=True)
+    m.backward(xd, ld, _dev(dl, cuda, np.float32))
+    assert np.abs(m.grads.cpu().numpy() - 2 * gw).max() < 2e-3 * np.abs(gw).max()
+
+
+def test_inference_path_equals_training_path_without_dropout(pkg, cuda):
+    L, H, F, C, B, T = 2, 64, 20, 30, 4, 21
+    rng = np.random.default_rng(2)
+    flat = model.flatten(model.init_params(L, H, F, C, seed=4), L, H, F, C)
+    x = _dev(rng.standard_normal((T, B, F)), cuda, np.float32)
+    lens = _dev(np.array([21, 3, 0, 17]), cuda, np.int32)
+    a = _build(pkg, cuda, L, H, F, C, B, T, flat, training=True)
+    b = _build(pkg, cuda, L, H, F, C, B, T, flat, training=False)
+    la = a.forward(x, lens, training=True)
+    lb = b.forward(x, lens, training=False)
+    assert torch.equal(la, lb)
+    # padded frames give the output bias; zero-length rows keep their state
+    bias = a.param_views()["Output_layer/output_b"]
+    assert torch.equal(la[5, 1], bias) and torch.equal(la[0, 2], bias)
+    assert float(b.rnn_state[:, :, 2].abs().max()) == 0.0
+    # process_input does not carry the state over (models/AcousticModel.py:716)
+    before = b.rnn_state.clone()
+    pred = b.process_input(None, x.cpu().numpy(), lens.cpu().numpy())
+    assert torch.equal(before, b.rnn_state) and pred.dtype == np.int32 and pred.shape[0] == B
+
+
+def test_cfg2_shape_forward_against_oracle(pkg, cuda):
+    """BASELINE config 2 (3x768, B=32, T=998, F=120): logits, CTC loss (1e-3 gate)
+    and greedy labels against the float64 oracle on the same synthetic input."""
+    L, H, F, C, B, T = 3, 768, 120, 80, 32, 998
+    rng = np.random.default_rng(0)
+    p = model.init_params(L, H, F, C, seed=0)
+    flat = model.flatten(p, L, H, F, C)
+    x = rng.standard_normal((T, B, F)).astype(np.float32)
+    lens = np.full(B, T, np.int32)
+    lens[1::4] = rng.integers(T // 2, T, size=len(lens[1::4]))
+    labs = [np.append(rng.integers(1, 79, size=rng.integers(60, 121)), 79).astype(np.int32) for _ in range(B)]
+    m = _build(pkg, cuda, L, H, F, C, B, 1000, flat, training=False)
+    logits = m.forward(_dev(x, cuda, np.float32), _dev(lens, cuda, np.int32), training=False)
+    want, _, _ = model.forward(p, x, lens, L, H, keep_cache=False)
+    got = logits.cpu().numpy()
+    err = np.abs(got - want).max()
+    loss, _ = m.ctc_loss(logits, labs, _dev(lens, cuda, np.int32), want_grad=False)
+    want_loss, _ = ctc.ctc_loss_and_grad(want, labs, lens, want_grad=False)
+    rel = np.abs(loss.cpu().numpy() - want_loss) / np.abs(want_loss)
+    ties = _assert_labels_match(got, want, lens)
+    print("cfg-2 forward: max |logit err| %.2e, max rel CTC loss err %.2e, %d near-tie frames of %d"
+          % (err, rel.max(), ties, int(lens.sum())))
+    assert err < 1e-3
+    assert rel.max() < 1e-3

@@ -1,0 +1,140 @@
+"""GPU parity of the update rule and of one complete training step (features ->
+forward -> CTC -> backward -> clip -> Adam) against the oracle pipeline, plus the
+step protocol of the reference (start_batch / run_step / end_batch)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctc, features, model, optim
+
+pytestmark = pytest.mark.gpu
+
+
+def test_clip_adam_matches_oracle(pkg, cuda):
+    rng = np.random.default_rng(0)
+    n = 100003
+    theta = rng.standard_normal(n).astype(np.float32)
+    m = pkg.AcousticModel(1, 8, 2, 4, 10, 8, False, 5, device=cuda)
+    m.create_training_rnn(1.0, 1.0, 1, 3e-4, 0.33)
+    lib = pkg._lib
+    th = torch.from_numpy(theta.copy()).to(cuda)
+    am, av = torch.zeros_like(th), torch.zeros_like(th)
+    ss = torch.zeros(1, dtype=torch.float64, device=cuda)
+    o_th, o_m, o_v = theta.astype(np.float64), np.zeros(n), np.zeros(n)
+    stream = torch.cuda.current_stream().cuda_stream
+    for step, scale in ((1, 5.0), (2, 1e-3), (3, 1.0)):                  # clipped, unclipped, clipped
+        g = (rng.standard_normal(n) * scale).astype(np.float32)
+        gd = torch.from_numpy(g).to(cuda)
+        lib.call("rs_sumsq", gd.data_ptr(), n, ss.data_ptr(), stream)
+        lib.call("rs_clip_adam_step", th.data_ptr(), gd.data_ptr(), am.data_ptr(), av.data_ptr(), n, ss.data_ptr(),
+                 1.0, 3e-4, 0.9, 0.999, 1e-8, step, stream)
+        o_th, o_m, o_v, norm = optim.clip_adam_step(o_th, g.astype(np.float64), o_m, o_v, step, 3e-4, 1.0)
+        assert abs(float(ss.cpu()[0]) ** 0.5 - norm) < 1e-6 * norm
+        np.testing.assert_allclose(th.cpu().numpy(), o_th, atol=2e-7)
+        np.testing.assert_allclose(am.cpu().numpy(), o_m, atol=1e-7)
+    with pytest.raises(ValueError):
+        lib.call("rs_clip_adam_step", th.data_ptr(), gd.data_ptr(), am.data_ptr(), av.data_ptr(), n, ss.data_ptr(),
+                 1.0, 3e-4, 0.9, 0.999, 1e-8, 0, stream)
+
+
+def _synthetic_set(rng, n_items, seconds=1.0, sr=16000, n_labels=8):
+    items = []
+    for _ in range(n_items):
+        sig = (0.1 * rng.standard_normal(int(seconds * sr))).astype(np.float32)
+        lab = np.append(rng.integers(1, 79, size=n_labels), 79).astype(np.int32)
+        items.append([(sig, sr), lab])
+    return items
+
+
+def test_full_training_step_matches_oracle_pipeline(pkg, cuda):
+    """BASELINE config 1: 1x128 LSTM, batch 2 of 1 s audio, 8 labels + EOS, through
+    the reference's step protocol; parameters after one step vs the oracle."""
+    L, H, F, C, B, Tmax = 1, 128, 120, 80, 2, 100
+    rng = np.random.default_rng(0)
+    items = _synthetic_set(rng, 2)
+    m = pkg.AcousticModel(L, H, B, Tmax, 600, F, False, C, device=cuda, seed=0)
+    m.create_training_rnn(1.0, 1.0, 1, 3e-4, 0.33, use_iterator=True)
+    m.initialize(None)
+    theta0 = m.params.cpu().numpy().astype(np.float64)
+    ds = pkg.AcousticModel.build_dataset(items, B, Tmax, 600, "fbank", pkg.ENGLISH_CHAR_MAP, device=cuda)
+    m.add_datasets_input(ds, ds)
+    mean_loss, err, step, empty = m.run_train_step(None, 1, 1.0)
+    assert step == 1 and not empty and np.isfinite(mean_loss) and 0.0 <= err
+    # oracle pipeline on the same inputs
+    feats = []
+    for (sig, sr), _ in items:
+        f, n = features.fbank(sig, sr, Tmax)
+        pad = np.zeros((Tmax, F))
+        pad[:n] = f
+        feats.append(pad)
+    x = np.stack(feats, axis=1)
+    lens = np.array([98, 98])
+    p = model.unflatten(theta0, L, H, F, C)
+    logits, _, cache = model.forward(p, x, lens, L, H)
+    labs = [it[1] for it in items]
+    loss, dlogits = ctc.ctc_loss_and_grad(logits, labs, lens)
+    g = model.flatten(model.backward(p, cache, dlogits, L, H), L, H, F, C)
+    assert abs(mean_loss - np.mean(loss / lens)) < 1e-3 * abs(np.mean(loss / lens))     # north-star gate
+    np.testing.assert_allclose(m.grads.cpu().numpy(), g, atol=2e-3 * np.abs(g).max())
+    th, _, _, _ = optim.clip_adam_step(theta0, g, np.zeros_like(g), np.zeros_like(g), 1, 3e-4, 1.0)
+    upd_want, upd_got = th - theta0, m.params.cpu().numpy() - theta0
+    # Adam's first step is lr * sign(g) wherever |g| >> eps: compare where the oracle gradient is not tiny
+    big = np.abs(g) / max(np.linalg.norm(g), 1.0) > 1e-6
+    np.testing.assert_allclose(upd_got[big], upd_want[big], atol=3e-6)
+    # state reset ratio 1.0 -> zero state after the step (models/AcousticModel.py:681-682)
+    assert float(m.rnn_state.abs().max()) == 0.0
+
+
+def test_step_protocol_accumulates_minibatches_and_epoch_end(pkg, cuda):
+    L, H, F, C, B, Tmax = 1, 32, 120, 80, 2, 100
+    rng = np.random.default_rng(1)
+    items = _synthetic_set(rng, 5)               # 3 mini-batches, the last one padded
+    m = pkg.AcousticModel(L, H, B, Tmax, 600, F, False, C, device=cuda, seed=1)
+    m.create_training_rnn(0.8, 0.5, 1, 1e-3, 0.33, use_iterator=True)
+    m.initialize(None)
+    ds = pkg.AcousticModel.build_dataset(items, B, Tmax, 600, "fbank", pkg.ENGLISH_CHAR_MAP, device=cuda)
+    m.add_datasets_input(ds, ds)
+    l1, e1, s1, empty1 = m.run_train_step(None, 2, 0.25)
+    assert s1 == 1 and not empty1
+    l2, e2, s2, empty2 = m.run_train_step(None, 2, 0.25)         # 1 mini-batch left, then OutOfRange
+    assert s2 == 2 and empty2
+    l3, e3, s3, empty3 = m.run_train_step(None, 2, 0.25)         # nothing left
+    assert (l3, e3, s3, empty3) == (0.0, 0.0, 2, True)
+    m.reset_train_iterator()
+    losses = [m.run_train_step(None, 3, 1.0)[0] for _ in range(1)]
+    ev_loss, ev_err, ev_step = m.run_evaluation(None)
+    assert np.isfinite(ev_loss) or np.isinf(ev_loss)             # padded rows have length 0 (reference: same)
+    assert ev_step == m.global_step
+    lr = m.get_learning_rate()
+    m.learning_rate_decay_op()
+    assert abs(m.get_learning_rate() - lr * 0.33) < 1e-12
+
+
+def test_loss_decreases_on_a_fixed_batch(pkg, cuda):
+    L, H, F, C, B, Tmax = 2, 64, 120, 80, 4, 100
+    rng = np.random.default_rng(3)
+    items = _synthetic_set(rng, 4)
+    m = pkg.AcousticModel(L, H, B, Tmax, 600, F, False, C, device=cuda, seed=3)
+    m.create_training_rnn(1.0, 1.0, 1, 3e-3, 0.33, use_iterator=True)
+    m.initialize(None)
+    ds = pkg.AcousticModel.build_dataset(items, B, Tmax, 600, "fbank", pkg.ENGLISH_CHAR_MAP, device=cuda)
+    losses = []
+    for _ in range(12):
+        m.add_datasets_input(ds, ds)
+        losses.append(m.run_train_step(None, 1, 1.0, compute_error_rate=False)[0])
+    assert losses[-1] < 0.8 * losses[0], losses
+
+
+def test_checkpoint_roundtrip(pkg, cuda, tmp_path):
+    m = pkg.AcousticModel(2, 32, 2, 50, 60, 20, False, 80, device=cuda, seed=7)
+    m.create_training_rnn(1.0, 1.0, 1, 3e-4, 0.33)
+    m.initialize(None)
+    m.global_step = 41
+    m.save(None, str(tmp_path))
+    n = pkg.AcousticModel(2, 32, 2, 50, 60, 20, False, 80, device=cuda, seed=8)
+    n.create_training_rnn(1.0, 1.0, 1, 1e-2, 0.33)
+    n.initialize(None)
+    n.restore(None, str(tmp_path))
+    assert torch.equal(m.params, n.params) and n.global_step == 41 and abs(n.get_learning_rate() - 3e-4) < 1e-9
+    names = set(m.param_views())
+    assert "rnn/multi_rnn_cell/cell_1/basic_lstm_cell/kernel" in names and "Input_Layer/input_w" in names
