@@ -175,6 +175,12 @@ int rs_clip_adam_step(float* params_d, const float* grads_d, float* m_d, float* 
                       const double* sumsq_d, float clip, float lr, float beta1, float beta2,
                       float eps, int64_t step, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Self-test of the tcgen05 / TMEM / descriptor plumbing (used by the GPU tests):
+ * D[128,N] = A[128,K] * B[N,K]^T on one CTA; split != 0 uses the bf16x3 split.
+ * ------------------------------------------------------------------------ */
+int rs_tc_selftest(const float* A_d, const float* B_d, float* D_d, int N, int K, int split, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,24 +65,34 @@ __device__ __forceinline__ CtcItem ctc_item(const int* len, const int* label_off
   return it;
 }
 
-// dynamic smem: int lp[Upad]; float row[2][Upad + 2]
+// Lattice rows are stored SHIFTED: alpha~[t,u] = alpha[t,u] - Oa[t], beta~[t,u] = beta[t,u] - Ob[t],
+// with the per-(item, t) offsets Oa / Ob accumulated in double.  The shift applied at step t is
+// the maximum of the previous row, so the fp32 lattice values stay O(|log y|) instead of growing
+// to |log p(z|x)| (thousands for 10 s utterances, where an fp32 ulp is 2.4e-4): the gradient then
+// agrees with a float64 evaluation to ~1e-5 instead of ~1e-2 (TF's own fp32 lattice has the
+// latter error).  The shift is exact bookkeeping, not an approximation.
+//
+// dynamic smem: int lp[Upad]; float row[2][Upad + 2]; float wmax[2][32]
 __global__ void __launch_bounds__(1024)
 ctc_lattice_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
                    const int* __restrict__ labels, const int* __restrict__ label_offsets,
                    const int* __restrict__ len, int T, int B, int C, int Upad, int blank,
                    int beta_skip_dest, float* __restrict__ alpha, float* __restrict__ beta,
+                   double* __restrict__ offs_a, double* __restrict__ offs_b, double* __restrict__ logp_out,
                    float* __restrict__ loss) {
   extern __shared__ unsigned char smem_raw[];
   int* lp = reinterpret_cast<int*>(smem_raw);
   float* rowbuf = reinterpret_cast<float*>(lp + Upad);
+  float* wmax = rowbuf + 2 * (Upad + 2);
   const int b = blockIdx.x;
   const bool is_beta = blockIdx.y == 1;
   const CtcItem it = ctc_item(len, label_offsets, b);
   if (it.skip) {
-    if (is_beta && threadIdx.x == 0) loss[b] = 0.f;
+    if (is_beta && threadIdx.x == 0) { loss[b] = 0.f; logp_out[b] = 0.0; }
     return;
   }
   const int U = it.U, L = it.L;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int* lab = labels + label_offsets[b];
   for (int u = threadIdx.x; u < U; u += blockDim.x) lp[u] = (u & 1) ? lab[u >> 1] : blank;
   const int stride = Upad + 2;
@@ -91,56 +101,84 @@ ctc_lattice_kernel(const float* __restrict__ logits, const float* __restrict__ l
   for (int i = threadIdx.x; i < 2 * stride; i += blockDim.x) rowbuf[i] = kNegInf;
   __syncthreads();
   float* out = (is_beta ? beta : alpha) + (size_t)b * T * Upad;
+  double* offs = (is_beta ? offs_b : offs_a) + (size_t)b * T;
+  double O = 0.0;
+  auto row_max = [&](int slot) -> float {   // max over the per-warp maxima written last step
+    float m = kNegInf;
+    for (int w = 0; w < nw; ++w) m = fmaxf(m, wmax[slot * 32 + w]);
+    return (m == kNegInf) ? 0.f : m;
+  };
 
   if (!is_beta) {
     float* prev = rowbuf + 2;
     float* cur = rowbuf + stride + 2;
     const float* lg = logits + (size_t)b * C;
     const float l0 = lse[b];
+    float mloc = kNegInf;
     for (int u = threadIdx.x; u < U; u += blockDim.x) {
       float v = kNegInf;
       if (u == 0) v = lg[blank] - l0;
       else if (u == 1) v = lg[lp[1]] - l0;
       prev[u] = v;
       out[u] = v;
+      mloc = fmaxf(mloc, v);
     }
+    mloc = warp_max(mloc);
+    if (lane == 0) wmax[warp] = mloc;
+    if (threadIdx.x == 0) offs[0] = 0.0;
     __syncthreads();
     for (int t = 1; t < L; ++t) {
+      const float M = row_max((t - 1) & 1);
+      O += (double)M;
+      if (threadIdx.x == 0) offs[t] = O;
       const float* lgt = logits + ((size_t)t * B + b) * C;
       const float lt = lse[t * B + b];
       const int lo = max(0, U - 2 * (L - t)), hi = min(U, 2 * (t + 1));
+      mloc = kNegInf;
       for (int u = threadIdx.x; u < U; u += blockDim.x) {
         float v = kNegInf;
         if (u >= lo && u < hi) {
           const int l = lp[u];
           const bool skip = (u > 1) && (l != blank) && (l != lp[u - 2]);
           const float a0 = prev[u], a1 = prev[u - 1], a2 = skip ? prev[u - 2] : kNegInf;
-          v = lse3(a0, a1, a2) + (lgt[l] - lt);
+          v = (lse3(a0, a1, a2) - M) + (lgt[l] - lt);
         }
         cur[u] = v;
         out[(size_t)t * Upad + u] = v;
+        mloc = fmaxf(mloc, v);
       }
+      mloc = warp_max(mloc);
+      if (lane == 0) wmax[(t & 1) * 32 + warp] = mloc;
       __syncthreads();
       float* tmp = prev; prev = cur; cur = tmp;
     }
   } else {
-    float* prev = rowbuf;            // beta[t+1] + logp[t+1]  ("nxt" in the oracle)
+    float* prev = rowbuf;            // beta~[t+1] + logp[t+1]  ("nxt" in the oracle), offset Ob[t+1]
     float* cur = rowbuf + stride;
-    // row L-1
+    float mloc = kNegInf;
     {
       const float* lgt = logits + ((size_t)(L - 1) * B + b) * C;
       const float lt = lse[(L - 1) * B + b];
       for (int u = threadIdx.x; u < U; u += blockDim.x) {
         float v = (u >= U - 2) ? 0.f : kNegInf;
         out[(size_t)(L - 1) * Upad + u] = v;
-        prev[u] = v + (lgt[lp[u]] - lt);
+        const float nx = v + (lgt[lp[u]] - lt);
+        prev[u] = nx;
+        mloc = fmaxf(mloc, nx);
       }
     }
+    mloc = warp_max(mloc);
+    if (lane == 0) wmax[((L - 1) & 1) * 32 + warp] = mloc;
+    if (threadIdx.x == 0) offs[L - 1] = 0.0;
     __syncthreads();
     for (int t = L - 2; t >= 0; --t) {
+      const float M = row_max((t + 1) & 1);
+      O += (double)M;
+      if (threadIdx.x == 0) offs[t] = O;
       const float* lgt = logits + ((size_t)t * B + b) * C;
       const float lt = lse[t * B + b];
       const int lo = max(0, U - 2 * (L - t)), hi = min(U, 2 * (t + 1));
+      mloc = kNegInf;
       for (int u = threadIdx.x; u < U; u += blockDim.x) {
         float v = kNegInf;
         const int l = lp[u];
@@ -151,19 +189,25 @@ ctc_lattice_kernel(const float* __restrict__ logits, const float* __restrict__ l
             skip = beta_skip_dest ? (l2 != blank && l2 != l) : (l != blank && l != l2);
           }
           const float b0 = prev[u], b1 = prev[u + 1], b2 = skip ? prev[u + 2] : kNegInf;
-          v = lse3(b0, b1, b2);
+          v = lse3(b0, b1, b2) - M;
         }
         out[(size_t)t * Upad + u] = v;
-        cur[u] = v + (lgt[l] - lt);   // becomes "nxt" for row t-1; at t == 0 it is alpha0-weighted
+        const float nx = v + (lgt[l] - lt);   // becomes "nxt" for row t-1
+        cur[u] = nx;
+        mloc = fmaxf(mloc, nx);
       }
+      mloc = warp_max(mloc);
+      if (lane == 0) wmax[(t & 1) * 32 + warp] = mloc;
       __syncthreads();
       float* tmp = prev; prev = cur; cur = tmp;
     }
     // log p(z|x) = LSE_u(alpha[0,u] + beta[0,u]); alpha[0,u] = logp[0,l'u] for u in {0,1}
-    // and prev[u] now holds beta[0,u] + logp[0,l'u].
+    // and prev[u] now holds beta~[0,u] + logp[0,l'u] (offset O = Ob[0]).
     if (threadIdx.x == 0) {
-      float lpz = (U > 1) ? lse2(prev[0], prev[1]) : prev[0];
-      loss[b] = -lpz;   // +inf when no valid path
+      const float lpz = (U > 1) ? lse2(prev[0], prev[1]) : prev[0];
+      const double logp = (lpz == kNegInf) ? -INFINITY : (double)lpz + O;
+      logp_out[b] = logp;
+      loss[b] = (float)(-logp);   // +inf when no valid path
     }
   }
 }
@@ -173,7 +217,8 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logits, const float* _
                                 const int* __restrict__ labels, const int* __restrict__ label_offsets,
                                 const int* __restrict__ len, int T, int B, int C, int Upad, int blank,
                                 const float* __restrict__ alpha, const float* __restrict__ beta,
-                                const float* __restrict__ loss, float* __restrict__ grad) {
+                                const double* __restrict__ offs_a, const double* __restrict__ offs_b,
+                                const double* __restrict__ logp_in, float* __restrict__ grad) {
   extern __shared__ float acc_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -187,11 +232,13 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logits, const float* _
   }
   const float* p = logits + (size_t)row * C;
   const float lt = lse[row];
-  const float nll = loss[b];
-  if (nll == INFINITY) {               // "No valid path found": dy = y
+  const double logp = logp_in[b];
+  if (logp == -INFINITY) {             // "No valid path found": dy = y
     for (int k = lane; k < C; k += 32) g[k] = expf(p[k] - lt);
     return;
   }
+  // alpha + beta - log p = alpha~ + beta~ + shift, the scalar part evaluated in double
+  const float shift = (float)(offs_a[(size_t)b * T + t] + offs_b[(size_t)b * T + t] - logp);
   float* acc = acc_all + warp * C;
   for (int k = lane; k < C; k += 32) acc[k] = 0.f;
   __syncwarp();
@@ -202,7 +249,7 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logits, const float* _
   float blank_sum = 0.f;
   for (int u = lane; u < U; u += 32) {
     const float ab = a[u] + be[u];
-    const float w = (ab == kNegInf) ? 0.f : expf(ab + nll);
+    const float w = (ab == kNegInf) ? 0.f : expf(ab + shift);
     if (u & 1) {
       const int l = lab[u >> 1];
       atomicAdd(&acc[l], w);
@@ -283,7 +330,8 @@ extern "C" size_t rs_ctc_workspace_bytes(int T, int B, int C, int max_label_len)
   size_t upad = ctc_upad(max_label_len);
   size_t lse = align_up((size_t)T * B * sizeof(float), 256);
   size_t lat = align_up((size_t)T * B * upad * sizeof(float), 256);
-  return lse + 2 * lat;
+  size_t offs = align_up((size_t)T * B * sizeof(double), 256);
+  return lse + 2 * lat + 2 * offs + align_up((size_t)B * sizeof(double), 256);
 }
 
 extern "C" int rs_ctc_loss_grad(const float* logits_d, const int32_t* labels_d,
@@ -305,6 +353,10 @@ extern "C" int rs_ctc_loss_grad(const float* logits_d, const int32_t* labels_d,
   size_t lat_b = align_up((size_t)T * B * upad * sizeof(float), 256);
   float* alpha = (float*)(ws + lse_b);
   float* beta = (float*)(ws + lse_b + lat_b);
+  size_t offs_b_ = align_up((size_t)T * B * sizeof(double), 256);
+  double* offs_a = (double*)(ws + lse_b + 2 * lat_b);
+  double* offs_b = (double*)(ws + lse_b + 2 * lat_b + offs_b_);
+  double* logp = (double*)(ws + lse_b + 2 * lat_b + 2 * offs_b_);
 
   const int rows = T * B;
   ctc_lse_kernel<<<cdiv(rows, 8), 256, 0, st>>>(logits_d, len_d, T, B, C, lse);
@@ -312,20 +364,20 @@ extern "C" int rs_ctc_loss_grad(const float* logits_d, const int32_t* labels_d,
   const int U = 2 * max_label_len + 1;
   int threads = (int)align_up((size_t)U, 32);
   if (threads > 1024) threads = 1024;
-  size_t smem = (size_t)upad * sizeof(int) + 2 * (size_t)(upad + 2) * sizeof(float);
+  size_t smem = (size_t)upad * sizeof(int) + 2 * (size_t)(upad + 2) * sizeof(float) + 64 * sizeof(float);
   RS_REQUIRE(smem <= 200 * 1024, RS_ERR_UNSUPPORTED, "rs_ctc_loss_grad: label length %d too large", max_label_len);
   if (smem > 48 * 1024)
     RS_CHECK_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ctc_lattice_kernel<<<dim3(B, 2), threads, smem, st>>>(logits_d, lse, labels_d, label_offsets_d, len_d, T, B, C,
                                                         upad, blank, beta_skip == RS_CTC_BETA_DEST ? 1 : 0,
-                                                        alpha, beta, loss_d);
+                                                        alpha, beta, offs_a, offs_b, logp, loss_d);
   RS_CHECK_LAUNCH();
   if (grad_d) {
     const int warps = 8;
     size_t gsmem = (size_t)warps * C * sizeof(float);
     RS_REQUIRE(gsmem <= 48 * 1024, RS_ERR_UNSUPPORTED, "rs_ctc_loss_grad: C=%d too large", C);
     ctc_grad_kernel<<<cdiv(rows, warps), warps * 32, gsmem, st>>>(logits_d, lse, labels_d, label_offsets_d, len_d,
-                                                                  T, B, C, upad, blank, alpha, beta, loss_d, grad_d);
+                                                                  T, B, C, upad, blank, alpha, beta, offs_a, offs_b, logp, grad_d);
     RS_CHECK_LAUNCH();
   }
   return RS_OK;

@@ -49,10 +49,10 @@ static inline int64_t fbank_num_frames(int64_t n, const FrameParams& p) {
 
 // ---- host-built tables (double math, then rounded to fp32) ------------------
 struct FbankTables {
-  float window[kNfft];          // Hamming(frame_length) cropped / zero-padded to 512
-  float tw_re[kNfft / 2];       // exp(-2 pi i k / 512)
-  float tw_im[kNfft / 2];
-  float melw[kNfilt * kBins];   // dense [40][257]
+  double window[kNfft];         // Hamming(frame_length) cropped / zero-padded to 512
+  double tw_re[kNfft / 2];      // exp(-2 pi i k / 512)
+  double tw_im[kNfft / 2];
+  double melw[kNfilt * kBins];  // dense [40][257]
   int mstart[kNfilt];
   int mend[kNfilt];
 };
@@ -64,11 +64,11 @@ static void build_fbank_tables(int sr, FbankTables* t) {
     if (i < fp.frame_length) {
       w = (fp.frame_length == 1) ? 1.0 : 0.54 - 0.46 * cos(2.0 * kPi * i / (fp.frame_length - 1));
     }
-    t->window[i] = (float)w;
+    t->window[i] = w;
   }
   for (int k = 0; k < kNfft / 2; ++k) {
-    t->tw_re[k] = (float)cos(-2.0 * kPi * k / kNfft);
-    t->tw_im[k] = (float)sin(-2.0 * kPi * k / kNfft);
+    t->tw_re[k] = cos(-2.0 * kPi * k / kNfft);
+    t->tw_im[k] = sin(-2.0 * kPi * k / kNfft);
   }
   // util/audioprocessor.py:107-133
   double high_mel = 2595.0 * log10(1.0 + ((double)sr / 2.0) / 700.0);
@@ -79,13 +79,13 @@ static void build_fbank_tables(int sr, FbankTables* t) {
     double hz = 700.0 * (pow(10.0, mel / 2595.0) - 1.0);
     bins[i] = floor((kNfft + 1) * hz / sr);
   }
-  for (int i = 0; i < kNfilt * kBins; ++i) t->melw[i] = 0.f;
+  for (int i = 0; i < kNfilt * kBins; ++i) t->melw[i] = 0.0;
   for (int m = 1; m <= kNfilt; ++m) {
     int lo = (int)bins[m - 1], ce = (int)bins[m], hi = (int)bins[m + 1];
     for (int k = lo; k < ce && k < kBins; ++k)
-      t->melw[(m - 1) * kBins + k] = (float)((k - bins[m - 1]) / (bins[m] - bins[m - 1]));
+      t->melw[(m - 1) * kBins + k] = (k - bins[m - 1]) / (bins[m] - bins[m - 1]);
     for (int k = ce; k < hi && k < kBins; ++k)
-      t->melw[(m - 1) * kBins + k] = (float)((bins[m + 1] - k) / (bins[m + 1] - bins[m]));
+      t->melw[(m - 1) * kBins + k] = (bins[m + 1] - k) / (bins[m + 1] - bins[m]);
     t->mstart[m - 1] = lo < kBins ? lo : kBins;
     t->mend[m - 1] = hi < kBins ? hi : kBins;
   }
@@ -108,13 +108,18 @@ static const FbankTables* get_fbank_tables(int sr) {
 __device__ __forceinline__ int bitrev9(int x) { return (int)(__brev((unsigned)x) >> 23); }
 
 // grid (ceil(Tfull_max / 32), B), 256 threads.
-// dynamic smem: float pcm[span + 1]; float fft[8 warps][2][512]; float pw[8][2][257(+pad)]
+// The reference computes this stage in float64 (its zero padding promotes the signal,
+// util/audioprocessor.py:96-97) after a float32 pre-emphasis; so does this kernel: the
+// FFT, power, mel sums and log10 run in fp64 (0.4 GFLOP per batch of 32 -- negligible
+// against B200's fp64 rate), which keeps log-mel of weak bins exact instead of carrying
+// fp32 FFT leakage error.
+// dynamic smem: float pcm[span + 1]; double fft[8 warps][2][512]; double pw[8][2][260]; double col[8][40]
 __global__ void __launch_bounds__(kFbankWarps * 32)
 fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ offsets,
                     const FbankTables* __restrict__ tab, int frame_length, int frame_step,
-                    int Tstride, int nblk, float* __restrict__ logmel, float* __restrict__ partial,
+                    int Tstride, int nblk, double* __restrict__ logmel, double* __restrict__ partial,
                     int* __restrict__ nframes_out) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) unsigned char sm_raw[];
   const int b = blockIdx.y;
   const int64_t off = offsets[b];
   const int64_t n = offsets[b + 1] - off;
@@ -122,18 +127,18 @@ fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ o
   const int T = (int)((d + frame_step - 1) / frame_step);
   if (blockIdx.x == 0 && threadIdx.x == 0) nframes_out[b] = T;
   const int t0 = blockIdx.x * kFramesPerCta;
-  float* part = partial + ((size_t)b * nblk + blockIdx.x) * kNfilt;
+  double* part = partial + ((size_t)b * nblk + blockIdx.x) * kNfilt;
   if (t0 >= T) {
-    if (threadIdx.x < kNfilt) part[threadIdx.x] = 0.f;
+    if (threadIdx.x < kNfilt) part[threadIdx.x] = 0.0;
     return;
   }
   const int nfr = min(kFramesPerCta, T - t0);
   const int nuse = min(frame_length, kNfft);       // rfft(frames, 512) crops or zero-pads
   const int span = (kFramesPerCta - 1) * frame_step + nuse;
-  float* spcm = sm;                                 // [span + 1], spcm[i] = x[s0 - 1 + i]
-  float* sfft = spcm + ((span + 1 + 3) & ~3);       // [8][2][512]
-  float* spw = sfft + kFbankWarps * 2 * kNfft;      // [8][2][260]
-  float* scol = spw + kFbankWarps * 2 * 260;        // [8][40] per-warp column sums
+  double* sfft = reinterpret_cast<double*>(sm_raw);              // [8][2][512]
+  double* spw = sfft + kFbankWarps * 2 * kNfft;                  // [8][2][260]
+  double* scol = spw + kFbankWarps * 2 * 260;                    // [8][40] per-warp column sums
+  float* spcm = reinterpret_cast<float*>(scol + kFbankWarps * kNfilt);   // [span + 1], spcm[i] = x[s0 - 1 + i]
   const int64_t s0 = (int64_t)t0 * frame_step;
   const float* x = pcm + off;
   for (int i = threadIdx.x; i < span + 1; i += blockDim.x) {
@@ -141,36 +146,39 @@ fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ o
     spcm[i] = (s >= 0 && s < n) ? x[s] : 0.f;
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = lane; i < kNfilt; i += 32) scol[warp * kNfilt + i] = 0.f;
+  for (int i = lane; i < kNfilt; i += 32) scol[warp * kNfilt + i] = 0.0;
   __syncthreads();
 
-  float* re = sfft + warp * 2 * kNfft;
-  float* im = re + kNfft;
-  float* pw = spw + warp * 2 * 260;
-  const float* __restrict__ win = tab->window;
-  const float* __restrict__ twr = tab->tw_re;
-  const float* __restrict__ twi = tab->tw_im;
+  double* re = sfft + warp * 2 * kNfft;
+  double* im = re + kNfft;
+  double* pw = spw + warp * 2 * 260;
+  const double* __restrict__ win = tab->window;
+  const double* __restrict__ twr = tab->tw_re;
+  const double* __restrict__ twi = tab->tw_im;
 
   for (int pair = warp; pair * 2 < nfr; pair += kFbankWarps) {
     const int fa = pair * 2, fb = fa + 1;
     const bool has_b = fb < nfr;
-    // load (pre-emphasis, window) in bit-reversed order: frame A -> re, frame B -> im
+    // load (float32 pre-emphasis, float64 window) in bit-reversed order: frame A -> re, frame B -> im
     for (int i = lane; i < kNfft; i += 32) {
-      float va = 0.f, vb = 0.f;
+      double va = 0.0, vb = 0.0;
       if (i < nuse) {
-        const float w = win[i];
+        const double w = win[i];
         {
           const int p = fa * frame_step + i + 1;         // index into spcm (shifted by one)
           const int64_t s = s0 + fa * frame_step + i;    // absolute sample
-          // y[0] = x[0]; y[s] = x[s] - 0.97 x[s-1]; zero beyond the signal
-          float cur = spcm[p], prev = (s > 0) ? spcm[p - 1] : 0.f;
-          va = (s < n) ? (cur - 0.97f * prev) * w : 0.f;
+          // y[0] = x[0]; y[s] = x[s] - 0.97 x[s-1] in float32 with separately rounded product
+          // (numpy: sig[1:] - 0.97 * sig[:-1] on a float32 array); zero beyond the signal
+          const float prev = (s > 0) ? spcm[p - 1] : 0.f;
+          const float y = (s < n) ? __fsub_rn(spcm[p], __fmul_rn(0.97f, prev)) : 0.f;
+          va = (double)y * w;
         }
         if (has_b) {
           const int p = fb * frame_step + i + 1;
           const int64_t s = s0 + fb * frame_step + i;
-          float cur = spcm[p], prev = (s > 0) ? spcm[p - 1] : 0.f;
-          vb = (s < n) ? (cur - 0.97f * prev) * w : 0.f;
+          const float prev = (s > 0) ? spcm[p - 1] : 0.f;
+          const float y = (s < n) ? __fsub_rn(spcm[p], __fmul_rn(0.97f, prev)) : 0.f;
+          vb = (double)y * w;
         }
       }
       const int r = bitrev9(i);
@@ -189,10 +197,10 @@ fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ o
         const int pos = i & (half - 1);
         const int a = ((i >> (s - 1)) << s) + pos;
         const int bb = a + half;
-        const float wr = twr[pos * tstep], wi = twi[pos * tstep];
-        const float xr = re[bb], xi = im[bb];
-        const float tr = wr * xr - wi * xi, ti = wr * xi + wi * xr;
-        const float ar = re[a], ai = im[a];
+        const double wr = twr[pos * tstep], wi = twi[pos * tstep];
+        const double xr = re[bb], xi = im[bb];
+        const double tr = wr * xr - wi * xi, ti = wr * xi + wi * xr;
+        const double ar = re[a], ai = im[a];
         re[a] = ar + tr; im[a] = ai + ti;
         re[bb] = ar - tr; im[bb] = ai - ti;
       }
@@ -201,31 +209,31 @@ fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ o
     // unpack the two real spectra, power = |X|^2 / 512
     for (int k = lane; k < kBins; k += 32) {
       const int nk = (kNfft - k) & (kNfft - 1);
-      const float zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
-      const float ar = 0.5f * (zr + yr), ai = 0.5f * (zi - yi);
-      const float br = 0.5f * (zi + yi), bi = -0.5f * (zr - yr);
-      pw[k] = (ar * ar + ai * ai) * (1.0f / kNfft);
-      pw[260 + k] = (br * br + bi * bi) * (1.0f / kNfft);
+      const double zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
+      const double ar = 0.5 * (zr + yr), ai = 0.5 * (zi - yi);
+      const double br = 0.5 * (zi + yi), bi = -0.5 * (zr - yr);
+      pw[k] = (ar * ar + ai * ai) * (1.0 / kNfft);
+      pw[260 + k] = (br * br + bi * bi) * (1.0 / kNfft);
     }
     __syncwarp();
     // 40 triangular filters; one lane owns filter m for BOTH frames of the pair so the
     // per-warp column sums are accumulated in a fixed order (deterministic).
     for (int m = lane; m < kNfilt; m += 32) {
-      const float* w = tab->melw + m * kBins;
-      float acc_a = 0.f, acc_b = 0.f;
+      const double* w = tab->melw + m * kBins;
+      double acc_a = 0.0, acc_b = 0.0;
       const int k1 = tab->mend[m];
       for (int k = tab->mstart[m]; k < k1; ++k) {
-        const float wk = w[k];
-        acc_a = fmaf(pw[k], wk, acc_a);
-        acc_b = fmaf(pw[260 + k], wk, acc_b);
+        const double wk = w[k];
+        acc_a = fma(pw[k], wk, acc_a);
+        acc_b = fma(pw[260 + k], wk, acc_b);
       }
-      if (acc_a == 0.f) acc_a = 2.220446049250313e-16f;   // util/audioprocessor.py:135
-      if (acc_b == 0.f) acc_b = 2.220446049250313e-16f;
-      const float va = 10.0f * log10f(acc_a);
-      float colsum = va;
+      if (acc_a == 0.0) acc_a = 2.220446049250313e-16;   // util/audioprocessor.py:135
+      if (acc_b == 0.0) acc_b = 2.220446049250313e-16;
+      const double va = 10.0 * log10(acc_a);
+      double colsum = va;
       logmel[((size_t)b * Tstride + (t0 + fa)) * kNfilt + m] = va;
       if (has_b) {
-        const float vb = 10.0f * log10f(acc_b);
+        const double vb = 10.0 * log10(acc_b);
         logmel[((size_t)b * Tstride + (t0 + fb)) * kNfilt + m] = vb;
         colsum += vb;
       }
@@ -235,7 +243,7 @@ fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ o
   }
   __syncthreads();
   if (threadIdx.x < kNfilt) {
-    float s = 0.f;
+    double s = 0.0;
     for (int w = 0; w < kFbankWarps; ++w) s += scol[w * kNfilt + threadIdx.x];
     part[threadIdx.x] = s;
   }
@@ -243,13 +251,13 @@ fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ o
 
 // grid (ceil(Tmax / 32), B), 256 threads
 __global__ void __launch_bounds__(256)
-fbank_delta_kernel(const float* __restrict__ logmel, const float* __restrict__ partial,
+fbank_delta_kernel(const double* __restrict__ logmel, const double* __restrict__ partial,
                    const int* __restrict__ nframes, int Tstride, int nblk, int Tmax, int B,
                    int delta_mode, int time_major, float* __restrict__ out) {
   constexpr int TT = 32;
-  __shared__ float xs[(TT + 32) * kNfilt];
-  __shared__ float d1[(TT + 16) * kNfilt];
-  __shared__ float mean[kNfilt];
+  __shared__ double xs[(TT + 32) * kNfilt];
+  __shared__ double d1[(TT + 16) * kNfilt];
+  __shared__ double mean[kNfilt];
   const int b = blockIdx.y;
   const int T = nframes[b];
   const int t0 = blockIdx.x * TT;
@@ -267,8 +275,8 @@ fbank_delta_kernel(const float* __restrict__ logmel, const float* __restrict__ p
   if (threadIdx.x < kNfilt) {
     // deterministic fixed-order sum of the per-CTA partials (double accumulate)
     double s = 0.0;
-    for (int i = 0; i < nblk; ++i) s += (double)partial[((size_t)b * nblk + i) * kNfilt + threadIdx.x];
-    mean[threadIdx.x] = (float)(s / (double)T + 1e-8);
+    for (int i = 0; i < nblk; ++i) s += partial[((size_t)b * nblk + i) * kNfilt + threadIdx.x];
+    mean[threadIdx.x] = s / (double)T + 1e-8;
   }
   __syncthreads();
   // halos: delta-delta at frame t reads d1 in [t-8, t+8] ('interp' edge frames use a
@@ -276,11 +284,11 @@ fbank_delta_kernel(const float* __restrict__ logmel, const float* __restrict__ p
   const int xlo = t0 - 16;    // xs row r <-> frame xlo + r
   for (int i = threadIdx.x; i < (TT + 32) * kNfilt; i += blockDim.x) {
     const int t = xlo + i / kNfilt, m = i % kNfilt;
-    xs[i] = (t >= 0 && t < T) ? logmel[((size_t)b * Tstride + t) * kNfilt + m] - mean[m] : 0.f;
+    xs[i] = (t >= 0 && t < T) ? logmel[((size_t)b * Tstride + t) * kNfilt + m] - mean[m] : 0.0;
   }
   __syncthreads();
   const int half = 4;
-  const float inv = delta_mode == RS_DELTA_INTERP ? (1.0f / 60.0f) : (1.0f / 20.0f);
+  const double inv = delta_mode == RS_DELTA_INTERP ? (1.0 / 60.0) : (1.0 / 20.0);
   // centre index used for output frame t
   auto centre = [&](int t) -> int {
     if (delta_mode == RS_DELTA_INTERP) return min(max(t, half), T - 1 - half);
@@ -290,11 +298,11 @@ fbank_delta_kernel(const float* __restrict__ logmel, const float* __restrict__ p
   const int dlo = t0 - 8;     // d1 row r <-> frame dlo + r
   for (int i = threadIdx.x; i < (TT + 16) * kNfilt; i += blockDim.x) {
     const int t = dlo + i / kNfilt, m = i % kNfilt;
-    float v = 0.f;
+    double v = 0.0;
     if (t >= 0 && t < T) {
       const int c = centre(t);
 #pragma unroll
-      for (int j = -half; j <= half; ++j) v += (float)j * xs[(clampi(c + j) - xlo) * kNfilt + m];
+      for (int j = -half; j <= half; ++j) v += (double)j * xs[(clampi(c + j) - xlo) * kNfilt + m];
       v *= inv;
     }
     d1[i] = v;
@@ -306,12 +314,12 @@ fbank_delta_kernel(const float* __restrict__ logmel, const float* __restrict__ p
     float* o = out_row(t);
     if (t < Tout) {
       const int c = centre(t);
-      float v = 0.f;
+      double v = 0.0;
 #pragma unroll
-      for (int j = -half; j <= half; ++j) v += (float)j * d1[(clampi(c + j) - dlo) * kNfilt + m];
-      o[m] = xs[(t - xlo) * kNfilt + m];
-      o[kNfilt + m] = d1[(t - dlo) * kNfilt + m];
-      o[2 * kNfilt + m] = v * inv;
+      for (int j = -half; j <= half; ++j) v += (double)j * d1[(clampi(c + j) - dlo) * kNfilt + m];
+      o[m] = (float)xs[(t - xlo) * kNfilt + m];
+      o[kNfilt + m] = (float)d1[(t - dlo) * kNfilt + m];
+      o[2 * kNfilt + m] = (float)(v * inv);
     } else {
       o[m] = 0.f; o[kNfilt + m] = 0.f; o[2 * kNfilt + m] = 0.f;
     }
@@ -329,8 +337,8 @@ extern "C" size_t rs_fbank_workspace_bytes(int B, int64_t max_samples, int sr) {
   int64_t Tfull = fbank_num_frames(max_samples, fp);
   int64_t nblk = (Tfull + kFramesPerCta - 1) / kFramesPerCta;
   if (nblk < 1) nblk = 1;
-  return fbank_tables_bytes() + align_up((size_t)B * Tfull * kNfilt * sizeof(float), 256) +
-         align_up((size_t)B * nblk * kNfilt * sizeof(float), 256);
+  return fbank_tables_bytes() + align_up((size_t)B * Tfull * kNfilt * sizeof(double), 256) +
+         align_up((size_t)B * nblk * kNfilt * sizeof(double), 256);
 }
 
 // Host-side table dump for the CPU tests (no device work): dense mel weights
@@ -339,8 +347,8 @@ extern "C" int rs_fbank_tables_host(int sr, float* melw_out, float* window_out, 
                                     int* frame_step) {
   RS_REQUIRE(sr > 0, RS_ERR_INVALID, "rs_fbank_tables_host: sr must be positive");
   const FbankTables* t = get_fbank_tables(sr);
-  if (melw_out) for (int i = 0; i < kNfilt * kBins; ++i) melw_out[i] = t->melw[i];
-  if (window_out) for (int i = 0; i < kNfft; ++i) window_out[i] = t->window[i];
+  if (melw_out) for (int i = 0; i < kNfilt * kBins; ++i) melw_out[i] = (float)t->melw[i];
+  if (window_out) for (int i = 0; i < kNfft; ++i) window_out[i] = (float)t->window[i];
   FrameParams fp = frame_params(sr);
   if (frame_length) *frame_length = fp.frame_length;
   if (frame_step) *frame_step = fp.frame_step;
@@ -369,15 +377,15 @@ extern "C" int rs_fbank_forward(const float* pcm_d, const int64_t* offsets_d, in
   const int nblk = cdiv(Tfull, kFramesPerCta);
   char* ws = (char*)ws_d;
   FbankTables* tab_d = (FbankTables*)ws;
-  float* logmel = (float*)(ws + fbank_tables_bytes());
-  float* partial = (float*)(ws + fbank_tables_bytes() + align_up((size_t)B * Tfull * kNfilt * sizeof(float), 256));
+  double* logmel = (double*)(ws + fbank_tables_bytes());
+  double* partial = (double*)(ws + fbank_tables_bytes() + align_up((size_t)B * Tfull * kNfilt * sizeof(double), 256));
   const FbankTables* tab_h = get_fbank_tables(sr);
   RS_CHECK_CUDA(cudaMemcpyAsync(tab_d, tab_h, sizeof(FbankTables), cudaMemcpyHostToDevice, st));
 
   const int nuse = fp.frame_length < kNfft ? fp.frame_length : kNfft;
   const int span = (kFramesPerCta - 1) * fp.frame_step + nuse;
-  size_t smem = (size_t)(((span + 1 + 3) & ~3) + kFbankWarps * 2 * kNfft + kFbankWarps * 2 * 260 +
-                         kFbankWarps * kNfilt) * sizeof(float);
+  size_t smem = (size_t)(kFbankWarps * 2 * kNfft + kFbankWarps * 2 * 260 + kFbankWarps * kNfilt) * sizeof(double) +
+                (size_t)(span + 1 + 3) * sizeof(float);
   RS_REQUIRE(smem <= 220 * 1024, RS_ERR_UNSUPPORTED, "rs_fbank_forward: sr %d needs %zu B smem", sr, smem);
   RS_CHECK_CUDA(cudaFuncSetAttribute(fbank_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fbank_logmel_kernel<<<dim3(nblk, B), kFbankWarps * 32, smem, st>>>(pcm_d, offsets_d, tab_d, fp.frame_length,

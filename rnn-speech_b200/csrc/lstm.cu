@@ -62,10 +62,11 @@ struct Plan {
 
 Plan make_plan(const rs_am* am) {
   Plan p;
-  p.TBH = (size_t)am->Tmax * am->B * am->H;
+  // every carved buffer starts on a 256-byte boundary (vector loads in the kernels)
+  p.TBH = align_up((size_t)am->Tmax * am->B * am->H, 64);
   p.TB4H = 4 * p.TBH;
   p.res_layer = p.TBH /*xin*/ + p.TBH /*out*/ + p.TB4H /*gates*/ + p.TBH /*cs*/;
-  p.state = (size_t)am->L * 2 * am->B * am->H;
+  p.state = align_up((size_t)am->L * 2 * am->B * am->H, 64);
   p.res_total = p.res_layer * am->L + p.TBH /*top*/ + p.TBH /*rnn_in*/ + p.state /*initial state copy*/;
   p.ws_fixed = 256 + (p.TB4H + 3 * p.TBH) * sizeof(float);
   // inference (reserve == NULL): ping-pong activations + the state copy live in the workspace
@@ -235,9 +236,10 @@ extern "C" int rs_am_forward(rs_am* am, const float* params_d, const float* x_d,
   // Private copy of the initial state: state_out_d may alias state_in_d, and backward
   // must differentiate against the state this call STARTED from.
   if (state_in_d)
-    RS_CHECK_CUDA(cudaMemcpyAsync(bf.state0, state_in_d, p.state * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    RS_CHECK_CUDA(cudaMemcpyAsync(bf.state0, state_in_d, (size_t)L * 2 * B * H * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, st));
   else
-    RS_CHECK_CUDA(cudaMemsetAsync(bf.state0, 0, p.state * sizeof(float), st));
+    RS_CHECK_CUDA(cudaMemsetAsync(bf.state0, 0, (size_t)L * 2 * B * H * sizeof(float), st));
 
   // input dense: rnn_in = x @ w_i + b_i                         (models/AcousticModel.py:247-250)
   const bool drop_in = keep_in < 1.f, drop_out = keep_out < 1.f;

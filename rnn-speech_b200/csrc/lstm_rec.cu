@@ -51,7 +51,7 @@ __device__ __forceinline__ void stage_T(float* __restrict__ stg, const float* __
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (b < B && src != nullptr) {
       const float* p = src + (size_t)b * ld + c;
-      if (c + 3 < ncols && ((ld & 3) == 0)) {
+      if (c + 3 < ncols && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
         v = coherent ? __ldcg(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
       } else {
         if (c < ncols) v.x = coherent ? __ldcg(p) : p[0];

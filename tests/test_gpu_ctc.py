@@ -1,9 +1,10 @@
 """GPU parity: CUDA CTC loss / gradient / greedy decode (through the C ABI)
 against oracle/ctc.py and the committed golden vectors.
 
-Tolerances (oracle is float64, kernels fp32): loss 1e-4 relative (the north-star
-gate is 1e-3), gradient 2e-5 absolute (entries are probabilities in [-1, 1]);
-greedy label ids bit-exact.
+Tolerances (oracle is float64, kernels keep the lattice in fp32 but shifted so its
+values stay O(|log y|), offsets in fp64): loss 1e-5 relative (the north-star gate is
+1e-3), gradient 1e-4 absolute (entries are probabilities in [-1, 1]); greedy label
+ids bit-exact.
 """
 import numpy as np
 import pytest
@@ -39,8 +40,8 @@ def test_ctc_matches_golden(pkg, cuda, tag, mode):
     T = g["logits"].shape[0]
     m = _model(pkg, cuda, B, T)
     loss, grad = _run(m, g["logits"], labs, g["lens"], mode)
-    np.testing.assert_allclose(loss, g["loss_" + mode], rtol=1e-4, atol=1e-5)
-    np.testing.assert_allclose(grad, g["grad_" + mode], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(loss, g["loss_" + mode], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(grad, g["grad_" + mode], rtol=0, atol=1e-4)
     loss_only, _ = _run(m, g["logits"], labs, g["lens"], mode, want_grad=False)
     np.testing.assert_array_equal(loss_only, loss)
     if tag == "noeos":
@@ -57,7 +58,7 @@ def test_ctc_edge_cases(pkg, cuda):
     want_loss, want_grad = ctc.ctc_loss_and_grad(logits, labs, lens)
     assert loss[0] == 0 and loss[1] == 0 and loss[3] == 0               # skipped items
     assert np.isinf(loss[2]) and np.isinf(want_loss[2])                 # no valid path
-    np.testing.assert_allclose(grad, want_grad, atol=2e-5)
+    np.testing.assert_allclose(grad, want_grad, atol=1e-4)
     with pytest.raises(ValueError):
         _run(m, logits, [np.array([7])] * 4, lens)                      # label >= num_classes
 
@@ -77,8 +78,8 @@ def test_ctc_random_against_oracle(pkg, cuda, T, B, lab_lo, lab_hi):
     want_loss, want_grad = ctc.ctc_loss_and_grad(logits, labs, lens)
     rel = np.abs(loss - want_loss) / np.abs(want_loss)
     print("ctc T=%d: max rel loss err %.2e, max |grad err| %.2e" % (T, rel.max(), np.abs(grad - want_grad).max()))
-    assert rel.max() < 1e-4
-    np.testing.assert_allclose(grad, want_grad, rtol=0, atol=5e-5)
+    assert rel.max() < 1e-5
+    np.testing.assert_allclose(grad, want_grad, rtol=0, atol=1e-4)
     for b in range(B):
         assert np.all(grad[lens[b]:, b] == 0)
 

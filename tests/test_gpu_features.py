@@ -1,9 +1,10 @@
 """GPU parity: CUDA fbank kernels (through the C ABI) against the golden vectors
 produced by the REFERENCE's own _extract_fbank and against the oracle.
 
-Tolerance: the reference computes in float64, the kernels in fp32 (512-point FFT,
-log10, mean over up to ~2000 frames): |diff| <= 2e-3 on features whose static part
-is in dB (range roughly -160..+40); observed error is reported by bench/profiles.
+Tolerance: the reference computes in float64 after a float32 pre-emphasis and so do
+the kernels (fp64 FFT / mel / log10 / deltas); the result is rounded to float32 once,
+as the reference does at models/AcousticModel.py:816.  |diff| <= 1e-4 on features
+whose static part is in dB (|value| up to ~160, float32 ulp there is 1.5e-5).
 """
 import numpy as np
 import pytest
@@ -13,7 +14,7 @@ from conftest import golden
 from oracle import features
 
 pytestmark = pytest.mark.gpu
-ATOL = 2e-3
+ATOL = 1e-4
 CASES = ["cfg1_1s_16k", "ragged_16k", "crop_22k", "trunc_16k", "silence_16k"]
 
 
@@ -80,4 +81,4 @@ def test_fbank_linearity_property(pkg, cuda):
     ap = pkg.AudioProcessor(3510, "fbank", device=cuda)
     a, _ = ap.process_batch([sig], 16000)
     b, _ = ap.process_batch([sig * 4.0], 16000)
-    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=1e-3)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=2e-4)

@@ -79,8 +79,10 @@ def test_full_training_step_matches_oracle_pipeline(pkg, cuda):
     th, _, _, _ = optim.clip_adam_step(theta0, g, np.zeros_like(g), np.zeros_like(g), 1, 3e-4, 1.0)
     upd_want, upd_got = th - theta0, m.params.cpu().numpy() - theta0
     # Adam's first step is lr * sign(g) wherever |g| >> eps: compare where the oracle gradient is not tiny
-    big = np.abs(g) / max(np.linalg.norm(g), 1.0) > 1e-6
+    # (entries with a near-zero gradient may legitimately take the other sign at fp32 resolution)
+    big = np.abs(g) / max(np.linalg.norm(g), 1.0) > 1e-4
     np.testing.assert_allclose(upd_got[big], upd_want[big], atol=3e-6)
+    assert np.mean(np.abs(upd_got - upd_want) > 3e-6) < 1e-3
     # state reset ratio 1.0 -> zero state after the step (models/AcousticModel.py:681-682)
     assert float(m.rnn_state.abs().max()) == 0.0
 
@@ -103,7 +105,8 @@ def test_step_protocol_accumulates_minibatches_and_epoch_end(pkg, cuda):
     m.reset_train_iterator()
     losses = [m.run_train_step(None, 3, 1.0)[0] for _ in range(1)]
     ev_loss, ev_err, ev_step = m.run_evaluation(None)
-    assert np.isfinite(ev_loss) or np.isinf(ev_loss)             # padded rows have length 0 (reference: same)
+    # the padded row has length 0: loss/len = 0/0 -> the reference's displayed mean is NaN too (:361-362)
+    assert np.isnan(ev_loss) or np.isfinite(ev_loss)
     assert ev_step == m.global_step
     lr = m.get_learning_rate()
     m.learning_rate_decay_op()
