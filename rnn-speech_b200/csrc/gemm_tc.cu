@@ -1,0 +1,340 @@
+// Persistent warp-specialised tcgen05 GEMM (TMA -> smem ring -> tcgen05.mma -> TMEM ->
+// epilogue warps), used for every batched projection of the acoustic model:
+//   gx = xin @ K[:H] (+b), logits = top @ w_o (+b), rnn_in = x @ w_i (+b), dxin = dgates @ K[:H]^T.
+// One CTA per SM, 128 x 128 output tiles, BK = 64, 3-stage ring, two TMEM accumulator
+// stages so that the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7: epilogue
+// fp32-grade accuracy from bf16 tensor cores: products = 3 issues A_hi*B_hi + A_hi*B_lo +
+// A_lo*B_hi into the same accumulator (see tc_common.cuh).
+#include "gemm_tc.cuh"
+#include "tc_common.cuh"
+#include <cuda.h>
+
+namespace rs {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int STAGES = 3;
+constexpr int TILE_A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int TILE_B_BYTES = BN * BK * 2;   // 16 KB
+constexpr int STAGE_BYTES = 2 * TILE_A_BYTES + 2 * TILE_B_BYTES;
+constexpr int NTHREADS = 256;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+struct KParams {
+  int M, N, K, products;
+  int tiles_m, tiles_n;
+  GemmTcOut out;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, KParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = p.tiles_m * p.tiles_n;
+  const int nkb = (p.K + BK - 1) / BK;
+  const bool x3 = p.products == 3;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA_hi); tc::tma_prefetch_desc(&tmB_hi);
+    if (x3) { tc::tma_prefetch_desc(&tmA_lo); tc::tma_prefetch_desc(&tmB_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull_bar[s], 1); tc::mbar_init(&tempty_bar[s], 4); }
+    tc::fence_mbar_init();
+  }
+  if (warp == 2) tc::tmem_alloc(&tmem_slot, 2 * BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      const uint32_t tx = (uint32_t)(x3 ? STAGE_BYTES : TILE_A_BYTES + TILE_B_BYTES);
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          unsigned char* st = smem + (size_t)s * STAGE_BYTES;
+          tc::mbar_arrive_expect_tx(&full_bar[s], tx);
+          tc::tma_load_2d(st, &tmA_hi, kb * BK, m0, &full_bar[s]);
+          tc::tma_load_2d(st + 2 * TILE_A_BYTES, &tmB_hi, kb * BK, n0, &full_bar[s]);
+          if (x3) {
+            tc::tma_load_2d(st + TILE_A_BYTES, &tmA_lo, kb * BK, m0, &full_bar[s]);
+            tc::tma_load_2d(st + 2 * TILE_A_BYTES + TILE_B_BYTES, &tmB_lo, kb * BK, n0, &full_bar[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::instr_desc_bf16(BM, BN);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+        const int as = tl & 1;
+        tc::mbar_wait(&tempty_bar[as], ((tl >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d = tmem + (uint32_t)(as * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          tc::mbar_wait(&full_bar[s], ph);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint64_t dah = tc::smem_desc_sw128(sa), dal = tc::smem_desc_sw128(sa + TILE_A_BYTES);
+          const uint64_t dbh = tc::smem_desc_sw128(sa + 2 * TILE_A_BYTES);
+          const uint64_t dbl = tc::smem_desc_sw128(sa + 2 * TILE_A_BYTES + TILE_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            tc::mma_bf16_ss(d, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
+            if (x3) {
+              tc::mma_bf16_ss(d, dah + 2 * k, dbl + 2 * k, idesc, true);
+              tc::mma_bf16_ss(d, dal + 2 * k, dbh + 2 * k, idesc, true);
+            }
+          }
+          tc::mma_commit(&empty_bar[s]);
+        }
+        tc::mma_commit(&tfull_bar[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;                       // TMEM lane quadrant of this warp
+    const GemmTcOut& o = p.out;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+      const int as = tl & 1;
+      const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+      tc::mbar_wait(&tfull_bar[as], (tl >> 1) & 1);
+      tc::tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      int rt = 0, rb = 0;
+      if (o.mode == GEMM_OUT_REC) { rt = m / o.recB; rb = m - rt * o.recB; }
+#pragma unroll 1
+      for (int c = 0; c < BN / 16; ++c) {
+        float v[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 16), v);
+        tc::tmem_ld_wait();
+        const int nb = n0 + c * 16;
+        if (row_ok && nb < p.N) {
+        if (o.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (nb + i < p.N) v[i] += __ldg(o.bias + nb + i);
+        }
+        if (o.mode == GEMM_OUT_F32) {
+          float* cp = o.C + (size_t)m * o.ldc + nb;
+          if (nb + 15 < p.N && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 x = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (o.accumulate) {
+                const float4 y = *reinterpret_cast<const float4*>(cp + i);
+                x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+              }
+              *reinterpret_cast<float4*>(cp + i) = x;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (nb + i < p.N) cp[i] = o.accumulate ? cp[i] + v[i] : v[i];
+          }
+        } else if (o.mode == GEMM_OUT_REC) {
+          const int nslice = o.recH / o.recU;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = nb + i;
+            if (n < p.N) {
+              const int g = n / o.recH, unit = n - g * o.recH;
+              const size_t idx = (((size_t)rt * nslice + unit / o.recU) * (4 * o.recU) + (unit % o.recU) * 4 + g) *
+                                     (size_t)o.recBpad + rb;
+              o.C[idx] = v[i];
+            }
+          }
+        } else {
+          __nv_bfloat16* hp = o.Chi + (size_t)m * o.ldc + nb;
+          __nv_bfloat16* lp = o.Clo + (size_t)m * o.ldc + nb;
+          if (nb + 15 < p.N && ((reinterpret_cast<uintptr_t>(hp) & 15) == 0)) {
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              tc::split_bf16(v[2 * i], h0, l0);
+              tc::split_bf16(v[2 * i + 1], h1, l1);
+              h[i] = tc::pack_bf16(h0, h1);
+              l[i] = tc::pack_bf16(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(hp) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(hp + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+            *reinterpret_cast<uint4*>(lp) = make_uint4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<uint4*>(lp + 8) = make_uint4(l[4], l[5], l[6], l[7]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (nb + i < p.N) {
+                __nv_bfloat16 h0, l0;
+                tc::split_bf16(v[i], h0, l0);
+                hp[i] = h0; lp[i] = l0;
+              }
+          }
+        }
+        }
+        __syncwarp();
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[as]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem, 2 * BN);
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    __nv_bfloat16 h, l;
+    tc::split_bf16(in[i], h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+// 32x32 smem tile transpose; in [R,C] -> out [C,R]
+__global__ void split_planes_T_kernel(const float* __restrict__ in, int R, int C, int ld_in,
+                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_out) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) {
+      __nv_bfloat16 h, l;
+      tc::split_bf16(tile[threadIdx.x][i], h, l);
+      hi[(size_t)c * ld_out + r] = h;
+      if (lo) lo[(size_t)c * ld_out + r] = l;
+    }
+  }
+}
+
+int make_tmap(CUtensorMap* map, const __nv_bfloat16* base, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  RS_REQUIRE(fn != nullptr, RS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  RS_REQUIRE((ld % 8) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, RS_ERR_INVALID,
+             "TMA operand needs ld %% 8 == 0 and a 16-byte aligned base (ld=%d)", ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RS_REQUIRE(r == CUDA_SUCCESS, RS_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows=%d cols=%d ld=%d)", (int)r,
+             rows, cols, ld);
+  return RS_OK;
+}
+
+}  // namespace
+
+int tmap_2d_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols, int ld, int box_rows) {
+  return make_tmap(reinterpret_cast<CUtensorMap*>(map64), base, rows, cols, ld, box_rows);
+}
+
+int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
+               cudaStream_t st) {
+  if (M <= 0 || N <= 0) return RS_OK;
+  RS_REQUIRE(K > 0 && (products == 1 || products == 3), RS_ERR_INVALID, "gemm_tc_nt: K=%d products=%d", K, products);
+  RS_REQUIRE(products == 1 || (A.lo && B.lo), RS_ERR_INVALID, "gemm_tc_nt: bf16x3 needs lo planes");
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = make_tmap(&ta_hi, A.hi, M, K, A.ld, BM)) != RS_OK) return rc;
+  if ((rc = make_tmap(&tb_hi, B.hi, N, K, B.ld, BN)) != RS_OK) return rc;
+  if (products == 3) {
+    if ((rc = make_tmap(&ta_lo, A.lo, M, K, A.ld, BM)) != RS_OK) return rc;
+    if ((rc = make_tmap(&tb_lo, B.lo, N, K, B.ld, BN)) != RS_OK) return rc;
+  } else {
+    ta_lo = ta_hi; tb_lo = tb_hi;
+  }
+  KParams p;
+  p.M = M; p.N = N; p.K = K; p.products = products;
+  p.tiles_m = cdiv(M, BM); p.tiles_n = cdiv(N, BN);
+  p.out = out;
+  const int ntiles = p.tiles_m * p.tiles_n;
+  int grid = sm_count();
+  if (grid > ntiles) grid = ntiles;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+  RS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gemm_tc_kernel<<<grid, NTHREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+int split_planes(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t st) {
+  if (n <= 0) return RS_OK;
+  int grid = (int)((n + 255) / 256);
+  const int cap = sm_count() * 16;
+  if (grid > cap) grid = cap;
+  split_planes_kernel<<<grid, 256, 0, st>>>(in, hi, lo, n);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+int split_planes_transposed(const float* in, int R, int C, int ld_in, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out,
+                            cudaStream_t st) {
+  if (R <= 0 || C <= 0) return RS_OK;
+  split_planes_T_kernel<<<dim3(cdiv(C, 32), cdiv(R, 32)), dim3(32, 8), 0, st>>>(in, R, C, ld_in, hi, lo, ld_out);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+}  // namespace rs
+
+using namespace rs;
+
+// Test hook: C[M,N] = A[M,K] * B[N,K]^T (+bias) from fp32 inputs; scratch_d must hold
+// 2*(M*Kp + N*Kp) bf16 with Kp = K rounded up to 8.
+extern "C" int rs_gemm_tc_test(const float* A_d, const float* B_d, const float* bias_d, float* C_d, int M, int N,
+                               int K, int products, void* scratch_d, size_t scratch_bytes, void* stream) {
+  RS_REQUIRE(A_d && B_d && C_d && scratch_d, RS_ERR_INVALID, "rs_gemm_tc_test: NULL argument");
+  RS_REQUIRE(K % 8 == 0, RS_ERR_INVALID, "rs_gemm_tc_test: K must be a multiple of 8");
+  const size_t need = 2 * ((size_t)M * K + (size_t)N * K) * sizeof(__nv_bfloat16) + 64;
+  RS_REQUIRE(scratch_bytes >= need, RS_ERR_WORKSPACE, "rs_gemm_tc_test: scratch %zu < %zu", scratch_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* ah = (__nv_bfloat16*)scratch_d;
+  __nv_bfloat16* al = ah + (size_t)M * K;
+  __nv_bfloat16* bh = al + (size_t)M * K;
+  __nv_bfloat16* bl = bh + (size_t)N * K;
+  int rc;
+  if ((rc = split_planes(A_d, ah, al, (int64_t)M * K, st)) != RS_OK) return rc;
+  if ((rc = split_planes(B_d, bh, bl, (int64_t)N * K, st)) != RS_OK) return rc;
+  SplitMat A{ah, al, M, K, K}, B{bh, bl, N, K, K};
+  GemmTcOut o{};
+  o.mode = GEMM_OUT_F32; o.C = C_d; o.ldc = N; o.bias = bias_d; o.accumulate = 0;
+  return gemm_tc_nt(A, B, M, N, K, products, o, st);
+}

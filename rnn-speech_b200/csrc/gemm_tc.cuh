@@ -1,0 +1,47 @@
+// tcgen05 GEMMs for the batched projections of the acoustic model.
+#pragma once
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace rs {
+
+// A "split" activation / weight matrix: x ~= hi + lo, two bf16 planes with one layout.
+struct SplitMat {
+  const __nv_bfloat16* hi;
+  const __nv_bfloat16* lo;   // may be nullptr (plain bf16)
+  int rows, cols, ld;        // row-major, ld in elements (multiple of 8)
+};
+
+enum GemmOut {
+  GEMM_OUT_F32 = 0,        // C[m*ldc + n] fp32 (+bias) (+= when accumulate)
+  GEMM_OUT_REC = 1,        // gate pre-activations in the recurrent kernel's layout (see lstm_rec_tc.cu)
+  GEMM_OUT_SPLIT = 2       // bf16 hi/lo planes, row-major ldc
+};
+
+struct GemmTcOut {
+  int mode;
+  float* C;
+  __nv_bfloat16* Chi;
+  __nv_bfloat16* Clo;
+  int ldc;
+  const float* bias;       // [N] or nullptr
+  int accumulate;          // GEMM_OUT_F32 only
+  // GEMM_OUT_REC: row m = t*B + b, col n = g*H + unit ->
+  //   ((t*nslice + unit/U)*(4U) + (unit%U)*4 + g) * Bpad + b
+  int recB, recBpad, recH, recU;
+};
+
+// C[M,N] = A[M,K] * B[N,K]^T, both operands K-major (row-major with K contiguous).
+// products = 3: bf16x3 (needs lo planes), 1: plain bf16.
+// Shape rules: lda/ldb multiples of 8 elements, 16-byte aligned bases; any M, N, K
+// (tails are zero-filled by TMA and masked in the epilogue).
+int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
+               cudaStream_t st);
+
+// out planes <- split(in * scale) elementwise; optional dropout masks as in lstm.cu
+int split_planes(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t st);
+// transpose + split: in [R,C] row-major (ld_in) -> planes [C,R] row-major (ld_out)
+int split_planes_transposed(const float* in, int R, int C, int ld_in, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out,
+                            cudaStream_t st);
+
+}  // namespace rs

@@ -24,3 +24,26 @@ def test_tcgen05_selftest_matches_fp64_matmul(pkg, cuda, N, K):
         err = np.abs(D.cpu().numpy() - want).max() / scale
         print("tcgen05 selftest N=%d K=%d split=%d: rel err %.2e" % (N, K, split, err))
         assert err < tol
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 200, 120), (1024, 3072, 768), (31936, 80, 768), (128, 128, 64), (4000, 768, 3072)])
+def test_tcgen05_gemm_against_fp64(pkg, cuda, M, N, K):
+    """The persistent TMA + tcgen05 GEMM used for every batched projection: tails in M, N
+    and K (TMA zero fill), bias, plain bf16 and bf16x3."""
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    want = A.astype(np.float64) @ B.astype(np.float64).T + bias
+    Ad, Bd, bd = (torch.from_numpy(a).to(cuda) for a in (A, B, bias))
+    scratch = torch.empty(2 * (M * K + N * K) * 2 + 64, dtype=torch.uint8, device=cuda)
+    for products, tol in ((1, 2e-2), (3, 2e-5)):
+        C = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
+        pkg._lib.call("rs_gemm_tc_test", Ad.data_ptr(), Bd.data_ptr(), bd.data_ptr(), C.data_ptr(), M, N, K, products,
+                      scratch.data_ptr(), scratch.numel(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = C.cpu().numpy()
+        err = np.abs(got - want).max() / np.abs(want).max()
+        print("tcgen05 gemm %dx%dx%d products=%d: rel err %.2e" % (M, N, K, products, err))
+        assert not np.isnan(got).any()
+        assert err < tol

@@ -77,6 +77,37 @@ def tc_diag():
                 print("   got[64,:8]", got[64, :8], "\n   want[64,:8]", want[64, :8])
 
 
+def gemm_diag():
+    import time
+    for (M, N, K) in ((300, 200, 120), (1024, 3072, 768), (31936, 3072, 768)):
+        rng = np.random.default_rng(M + N + K)
+        A = rng.standard_normal((M, K)).astype(np.float32)
+        B = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+        bias = rng.standard_normal(N).astype(np.float32)
+        Ad, Bd, bd = (torch.from_numpy(a).to(dev) for a in (A, B, bias))
+        want = (Ad.double() @ Bd.double().T + bd.double()).cpu().numpy()
+        scratch = torch.empty(2 * (M * K + N * K) * 2 + 64, dtype=torch.uint8, device=dev)
+        for products in (1, 3):
+            C = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev)
+            args = (Ad.data_ptr(), Bd.data_ptr(), bd.data_ptr(), C.data_ptr(), M, N, K, products, scratch.data_ptr(),
+                    scratch.numel(), torch.cuda.current_stream().cuda_stream)
+            rs._lib.call("rs_gemm_tc_test", *args)
+            torch.cuda.synchronize()
+            got = C.cpu().numpy()
+            e = np.abs(got - want)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                rs._lib.call("rs_gemm_tc_test", *args)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 5
+            print("gemm %dx%dx%d products=%d: rel err %.3e nan %d; %.3f ms incl. split (%.1f TFLOP/s useful)" % (
+                M, N, K, products, e.max() / np.abs(want).max(), int(np.isnan(got).sum()), dt * 1e3,
+                2.0 * M * N * K / dt / 1e12))
+            if not (e.max() / np.abs(want).max() < 0.05):
+                bad = np.argwhere(~(e < 0.05 * np.abs(want).max()))
+                print("   first bad entries", bad[:5].tolist(), "of", len(bad))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ctc", "fbank"]
     if "ctc" in which:
@@ -85,3 +116,5 @@ if __name__ == "__main__":
         fbank_diag()
     if "tc" in which:
         tc_diag()
+    if "gemm" in which:
+        gemm_diag()
