@@ -119,6 +119,9 @@ int64_t rs_am_param_count(const rs_am* am);
 /* offset (in floats) of a named variable inside the flat buffer: which = 0 input_w,
  * 1 input_b, 2 kernel (layer), 3 bias (layer), 4 output_w, 5 output_b */
 int64_t rs_am_param_offset(const rs_am* am, int which, int layer);
+/* 1 if this shape runs on the tcgen05 kernels (hidden_size % 64 == 0, batch <= 64, weights
+ * fit in shared memory), 0 if it runs on the fp32 FFMA kernels. */
+int rs_am_uses_tensor_cores(const rs_am* am);
 size_t rs_am_reserve_bytes(const rs_am* am);
 size_t rs_am_workspace_bytes(const rs_am* am);
 int rs_am_forward(rs_am* am, const float* params_d, const float* x_d, const int32_t* len_d, int T,

@@ -116,6 +116,7 @@ class AcousticModel(object):
         _lib.call("rs_am_create", _lib.ctypes.byref(h), self.num_layers, self.hidden_size, self.input_dim,
                   self.num_labels, self.batch_size, self.max_input_seq_length)
         self._handle = h
+        self.uses_tensor_cores = bool(_lib.raw("rs_am_uses_tensor_cores")(h))
         n = _lib.raw("rs_am_param_count")(h)
         self.n_params = int(n)
         self.params = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)

@@ -62,6 +62,14 @@ __host__ __device__ __forceinline__ bool dropout_keep(uint64_t key, uint32_t str
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float tanhf_(float x) { return tanhf(x); }
 
+// MUFU-based forms for the latency-critical tensor-core recurrent kernels: ex2.approx /
+// rcp.approx, absolute error ~1e-6 on (0,1) / (-1,1) outputs for |x| <= 16.
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  x = fminf(fmaxf(x, -15.0f), 15.0f);
+  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

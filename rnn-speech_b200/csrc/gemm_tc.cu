@@ -50,11 +50,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = p.tiles_m * p.tiles_n;
   const int nkb = (p.K + BK - 1) / BK;
-  const bool x3 = p.products == 3;
+  const bool use_blo = (p.products & 1) != 0, use_alo = (p.products & 2) != 0;   // extra terms A_hi*B_lo / A_lo*B_hi
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA_hi); tc::tma_prefetch_desc(&tmB_hi);
-    if (x3) { tc::tma_prefetch_desc(&tmA_lo); tc::tma_prefetch_desc(&tmB_lo); }
+    if (use_alo) tc::tma_prefetch_desc(&tmA_lo);
+    if (use_blo) tc::tma_prefetch_desc(&tmB_lo);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
@@ -70,7 +71,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      const uint32_t tx = (uint32_t)(x3 ? STAGE_BYTES : TILE_A_BYTES + TILE_B_BYTES);
+      const uint32_t tx = (uint32_t)(TILE_A_BYTES + TILE_B_BYTES + (use_alo ? TILE_A_BYTES : 0) + (use_blo ? TILE_B_BYTES : 0));
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -81,10 +82,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tc::mbar_arrive_expect_tx(&full_bar[s], tx);
           tc::tma_load_2d(st, &tmA_hi, kb * BK, m0, &full_bar[s]);
           tc::tma_load_2d(st + 2 * TILE_A_BYTES, &tmB_hi, kb * BK, n0, &full_bar[s]);
-          if (x3) {
-            tc::tma_load_2d(st + TILE_A_BYTES, &tmA_lo, kb * BK, m0, &full_bar[s]);
-            tc::tma_load_2d(st + 2 * TILE_A_BYTES + TILE_B_BYTES, &tmB_lo, kb * BK, n0, &full_bar[s]);
-          }
+          if (use_alo) tc::tma_load_2d(st + TILE_A_BYTES, &tmA_lo, kb * BK, m0, &full_bar[s]);
+          if (use_blo) tc::tma_load_2d(st + 2 * TILE_A_BYTES + TILE_B_BYTES, &tmB_lo, kb * BK, n0, &full_bar[s]);
         }
       }
     }
@@ -109,10 +108,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             tc::mma_bf16_ss(d, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
-            if (x3) {
-              tc::mma_bf16_ss(d, dah + 2 * k, dbl + 2 * k, idesc, true);
-              tc::mma_bf16_ss(d, dal + 2 * k, dbh + 2 * k, idesc, true);
-            }
+            if (use_blo) tc::mma_bf16_ss(d, dah + 2 * k, dbl + 2 * k, idesc, true);
+            if (use_alo) tc::mma_bf16_ss(d, dal + 2 * k, dbh + 2 * k, idesc, true);
           }
           tc::mma_commit(&empty_bar[s]);
         }
@@ -243,6 +240,38 @@ __global__ void split_planes_T_kernel(const float* __restrict__ in, int R, int C
   }
 }
 
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int R, int C, int ld_in,
+                                      __nv_bfloat16* __restrict__ out, int ld_out) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  for (int i = threadIdx.y; i < 64; i += blockDim.y)
+    for (int jj = threadIdx.x; jj < 64; jj += 32) {
+      const int r = r0 + i, c = c0 + jj;
+      tile[i][jj] = (r < R && c < C) ? in[(size_t)r * ld_in + c] : __float2bfloat16(0.f);
+    }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 64; i += blockDim.y)
+    for (int jj = threadIdx.x; jj < 64; jj += 32) {
+      const int c = c0 + i, r = r0 + jj;
+      if (c < C && r < R) out[(size_t)c * ld_out + r] = tile[jj][i];
+    }
+}
+
+// one warp per row
+__global__ void rowsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int R,
+                                     int C, int ld, float* __restrict__ out, int accumulate) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    s += __bfloat162float(hi[(size_t)row * ld + c]);
+    if (lo) s += __bfloat162float(lo[(size_t)row * ld + c]);
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[row] = accumulate ? out[row] + s : s;
+}
+
 int make_tmap(CUtensorMap* map, const __nv_bfloat16* base, int rows, int cols, int ld, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   RS_REQUIRE(fn != nullptr, RS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
@@ -269,18 +298,16 @@ int tmap_2d_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols, int
 int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
                cudaStream_t st) {
   if (M <= 0 || N <= 0) return RS_OK;
-  RS_REQUIRE(K > 0 && (products == 1 || products == 3), RS_ERR_INVALID, "gemm_tc_nt: K=%d products=%d", K, products);
-  RS_REQUIRE(products == 1 || (A.lo && B.lo), RS_ERR_INVALID, "gemm_tc_nt: bf16x3 needs lo planes");
+  RS_REQUIRE(K > 0, RS_ERR_INVALID, "gemm_tc_nt: K=%d", K);
+  // bf16x3 degrades gracefully to the planes that exist: hi*hi (+ hi*B_lo) (+ A_lo*hi)
+  products = (products == 3 ? ((B.lo ? 1 : 0) | (A.lo ? 2 : 0)) : 0);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   if ((rc = make_tmap(&ta_hi, A.hi, M, K, A.ld, BM)) != RS_OK) return rc;
   if ((rc = make_tmap(&tb_hi, B.hi, N, K, B.ld, BN)) != RS_OK) return rc;
-  if (products == 3) {
-    if ((rc = make_tmap(&ta_lo, A.lo, M, K, A.ld, BM)) != RS_OK) return rc;
-    if ((rc = make_tmap(&tb_lo, B.lo, N, K, B.ld, BN)) != RS_OK) return rc;
-  } else {
-    ta_lo = ta_hi; tb_lo = tb_hi;
-  }
+  ta_lo = ta_hi; tb_lo = tb_hi;
+  if (products & 2) if ((rc = make_tmap(&ta_lo, A.lo, M, K, A.ld, BM)) != RS_OK) return rc;
+  if (products & 1) if ((rc = make_tmap(&tb_lo, B.lo, N, K, B.ld, BN)) != RS_OK) return rc;
   KParams p;
   p.M = M; p.N = N; p.K = K; p.products = products;
   p.tiles_m = cdiv(M, BM); p.tiles_n = cdiv(N, BN);
@@ -309,6 +336,21 @@ int split_planes_transposed(const float* in, int R, int C, int ld_in, __nv_bfloa
                             cudaStream_t st) {
   if (R <= 0 || C <= 0) return RS_OK;
   split_planes_T_kernel<<<dim3(cdiv(C, 32), cdiv(R, 32)), dim3(32, 8), 0, st>>>(in, R, C, ld_in, hi, lo, ld_out);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+int transpose_bf16(const __nv_bfloat16* in, int R, int C, int ld_in, __nv_bfloat16* out, int ld_out, cudaStream_t st) {
+  if (R <= 0 || C <= 0) return RS_OK;
+  transpose_bf16_kernel<<<dim3(cdiv(C, 64), cdiv(R, 64)), dim3(32, 8), 0, st>>>(in, R, C, ld_in, out, ld_out);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+int rowsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int R, int C, int ld, float* out, int accumulate,
+                  cudaStream_t st) {
+  if (R <= 0) return RS_OK;
+  rowsum_planes_kernel<<<cdiv(R, 8), 256, 0, st>>>(hi, lo, R, C, ld, out, accumulate);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }

@@ -32,7 +32,8 @@ struct GemmTcOut {
 };
 
 // C[M,N] = A[M,K] * B[N,K]^T, both operands K-major (row-major with K contiguous).
-// products = 3: bf16x3 (needs lo planes), 1: plain bf16.
+// products = 3: bf16x3 over whichever lo planes are present (A_hi*B_hi + A_hi*B_lo + A_lo*B_hi),
+// 1: plain bf16 (hi planes only).
 // Shape rules: lda/ldb multiples of 8 elements, 16-byte aligned bases; any M, N, K
 // (tails are zero-filled by TMA and masked in the epilogue).
 int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
@@ -43,5 +44,10 @@ int split_planes(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t 
 // transpose + split: in [R,C] row-major (ld_in) -> planes [C,R] row-major (ld_out)
 int split_planes_transposed(const float* in, int R, int C, int ld_in, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out,
                             cudaStream_t st);
+// bf16 matrix transpose: in [R,C] (ld_in) -> out [C,R] (ld_out)
+int transpose_bf16(const __nv_bfloat16* in, int R, int C, int ld_in, __nv_bfloat16* out, int ld_out, cudaStream_t st);
+// out[r] (+)= sum_c (hi[r][c] + lo[r][c])  over a [R, C] plane pair (lo may be nullptr)
+int rowsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int R, int C, int ld, float* out, int accumulate,
+                  cudaStream_t st);
 
 }  // namespace rs

@@ -7,17 +7,9 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "lstm_rec.cuh"
+#include <stdlib.h>
 
-struct rs_am {
-  int L, H, F, C, B, Tmax;
-  int64_t n_params;
-  int64_t off_input_w, off_input_b, off_output_w, off_output_b;
-  int64_t off_kernel[64], off_bias[64];
-  // optional per-kernel timing of the recurrent kernels (CUDA events on the launch stream)
-  int timing;
-  cudaEvent_t ev[2][64][2];     // [fwd|bwd][layer][start|stop]
-  int ev_valid[2][64];
-};
+#include "lstm_internal.cuh"
 
 namespace rs {
 namespace {
@@ -102,6 +94,13 @@ extern "C" int rs_am_create(rs_am** out, int num_layers, int hidden_size, int in
   am->off_output_b = off; off += num_labels;
   am->n_params = off;
   am->timing = 0;
+  // tensor-core path when the shape fits it (RS_DISABLE_TC=1 forces the FFMA kernels)
+  {
+    RecTcBwdGeom bg;
+    const char* off = getenv("RS_DISABLE_TC");
+    am->use_tc = !(off && off[0] == '1') && rec_tc_geometry(hidden_size, batch_size, &am->tc) &&
+                 rec_tc_bwd_geometry(hidden_size, batch_size, &bg);
+  }
   for (int d = 0; d < 2; ++d)
     for (int l = 0; l < 64; ++l) am->ev_valid[d][l] = 0;
   *out = am;
@@ -154,8 +153,15 @@ extern "C" int64_t rs_am_param_offset(const rs_am* am, int which, int layer) {
   return -1;
 }
 
-extern "C" size_t rs_am_reserve_bytes(const rs_am* am) { return am ? make_plan(am).res_total * sizeof(float) : 0; }
-extern "C" size_t rs_am_workspace_bytes(const rs_am* am) { return am ? make_plan(am).ws_total : 0; }
+extern "C" size_t rs_am_reserve_bytes(const rs_am* am) {
+  if (!am) return 0;
+  return am->use_tc ? am_tc_reserve_bytes(am) : make_plan(am).res_total * sizeof(float);
+}
+extern "C" size_t rs_am_workspace_bytes(const rs_am* am) {
+  if (!am) return 0;
+  return am->use_tc ? am_tc_workspace_bytes(am) : make_plan(am).ws_total;
+}
+extern "C" int rs_am_uses_tensor_cores(const rs_am* am) { return am ? am->use_tc : 0; }
 
 namespace {
 struct Bufs {
@@ -224,6 +230,9 @@ extern "C" int rs_am_forward(rs_am* am, const float* params_d, const float* x_d,
   RS_REQUIRE(T > 0 && T <= am->Tmax, RS_ERR_INVALID, "rs_am_forward: T=%d outside [1,%d]", T, am->Tmax);
   RS_REQUIRE(keep_in > 0.f && keep_in <= 1.f && keep_out > 0.f && keep_out <= 1.f, RS_ERR_INVALID,
              "rs_am_forward: keep probabilities must be in (0,1]");
+  if (am->use_tc)
+    return am_tc_forward(am, params_d, x_d, len_d, T, state_in_d, state_out_d, keep_in, keep_out, seed, logits_d,
+                         reserve_d, ws_d, ws_bytes, (cudaStream_t)stream);
   const Plan p = make_plan(am);
   RS_REQUIRE(ws_bytes >= p.ws_total, RS_ERR_WORKSPACE, "rs_am_forward: workspace %zu < %zu", ws_bytes, p.ws_total);
   cudaStream_t st = (cudaStream_t)stream;
@@ -295,6 +304,9 @@ extern "C" int rs_am_backward(rs_am* am, const float* params_d, const float* x_d
   RS_REQUIRE(T > 0 && T <= am->Tmax, RS_ERR_INVALID, "rs_am_backward: T=%d outside [1,%d]", T, am->Tmax);
   RS_REQUIRE(keep_in > 0.f && keep_in <= 1.f && keep_out > 0.f && keep_out <= 1.f, RS_ERR_INVALID,
              "rs_am_backward: keep probabilities must be in (0,1]");
+  if (am->use_tc)
+    return am_tc_backward(am, params_d, x_d, len_d, T, keep_in, keep_out, seed, dlogits_d, reserve_d, grads_d, ws_d,
+                          ws_bytes, (cudaStream_t)stream);
   const Plan p = make_plan(am);
   RS_REQUIRE(ws_bytes >= p.ws_total, RS_ERR_WORKSPACE, "rs_am_backward: workspace %zu < %zu", ws_bytes, p.ws_total);
   cudaStream_t st = (cudaStream_t)stream;

@@ -108,6 +108,77 @@ def gemm_diag():
                 print("   first bad entries", bad[:5].tolist(), "of", len(bad))
 
 
+def model_diag(which):
+    from tests.conftest import golden
+    if "cfg1" in which:
+        g = golden("model_cfg1.npz")
+        L, H, F, C, T, B = [int(v) for v in g["dims"]]
+        m = rs.AcousticModel(L, H, B, T, 600, F, False, C, device=dev)
+        m.create_training_rnn(1.0, 1.0, 1, 3e-4, 0.33)
+        m.load_flat_params(g["flat_params"])
+        print("cfg1: tensor cores:", m.uses_tensor_cores)
+        x = torch.from_numpy(g["x"]).to(dev)
+        lens = torch.from_numpy(g["lens"]).to(dev)
+        logits = m.forward(x, lens, training=True)
+        torch.cuda.synchronize()
+        got = logits.cpu().numpy()
+        print("cfg1 fwd: max |logit err| %.3e (nan %d); state c err %.3e h err %.3e" % (
+            np.abs(got - g["logits"]).max(), int(np.isnan(got).sum()),
+            np.abs(m.rnn_state[0, 0].cpu().numpy() - g["state_c"]).max(),
+            np.abs(m.rnn_state[0, 1].cpu().numpy() - g["state_h"]).max()))
+        labs = [g["lab_%d" % i] for i in range(B)]
+        loss, grad = m.ctc_loss(logits, labs, lens)
+        print("cfg1 loss rel err", np.abs(loss.cpu().numpy() - g["loss"]) / g["loss"])
+        m.grads.zero_()
+        m.backward(x, lens, grad)
+        torch.cuda.synchronize()
+        gg = m.grads.cpu().numpy()
+        views = m.grad_views()
+        want = g["flat_grads"]
+        print("cfg1 bwd: max |grad err| / max|grad| = %.3e (nan %d)" % (np.abs(gg - want).max() / np.abs(want).max(), int(np.isnan(gg).sum())))
+        off = 0
+        for name, v in views.items():
+            n = v.numel()
+            e = np.abs(gg[off:off + n] - want[off:off + n]).max() / (np.abs(want[off:off + n]).max() + 1e-30)
+            print("    %-55s rel err %.3e" % (name, e))
+            off += n
+    if "cfg2" in which:
+        L, H, F, C, B, T = 3, 768, 120, 80, 32, 998
+        rng = np.random.default_rng(0)
+        p = model.init_params(L, H, F, C, seed=0)
+        flat = model.flatten(p, L, H, F, C)
+        x = rng.standard_normal((T, B, F)).astype(np.float32)
+        lens = np.full(B, T, np.int32)
+        lens[1::4] = rng.integers(T // 2, T, size=len(lens[1::4]))
+        m = rs.AcousticModel(L, H, B, 1000, 600, F, False, C, device=dev)
+        m.create_training_rnn(1.0, 1.0, 1, 3e-4, 0.33)
+        m.load_flat_params(flat)
+        m.enable_timing()
+        print("cfg2: tensor cores:", m.uses_tensor_cores)
+        xd, ld = torch.from_numpy(x).to(dev), torch.from_numpy(lens).to(dev)
+        for it in range(2):
+            m.rnn_state.zero_()
+            logits = m.forward(xd, ld, training=True, keep_state=False)
+            torch.cuda.synchronize()
+        want, _, _ = model.forward(p, x, lens, L, H, keep_cache=False)
+        got = logits.cpu().numpy()
+        margin = ctc.top2_margin(want, lens)
+        valid = np.arange(T)[:, None] < lens[None, :]
+        diff = (got.argmax(-1) != want.argmax(-1)) & valid
+        print("cfg2 fwd: max |logit err| %.3e (nan %d); argmax mismatches %d of %d frames; largest margin among mismatches %.2e" % (
+            np.abs(got - want).max(), int(np.isnan(got).sum()), int(diff.sum()), int(valid.sum()),
+            float(margin[diff].max()) if diff.any() else 0.0))
+        labs = [np.append(rng.integers(1, 79, size=rng.integers(60, 121)), 79).astype(np.int32) for _ in range(B)]
+        loss, grad = m.ctc_loss(logits, labs, ld)
+        wl, _ = ctc.ctc_loss_and_grad(want, labs, lens, want_grad=False)
+        print("cfg2 loss max rel err %.3e" % (np.abs(loss.cpu().numpy() - wl) / wl).max())
+        m.grads.zero_()
+        m.backward(xd, ld, grad)
+        torch.cuda.synchronize()
+        print("cfg2 grads finite:", bool(torch.isfinite(m.grads).all()), "norm %.4e" % float(m.grads.double().norm()))
+        print("cfg2 recurrent kernel ms fwd/bwd:", m.recurrent_ms())
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ctc", "fbank"]
     if "ctc" in which:
@@ -118,3 +189,5 @@ if __name__ == "__main__":
         tc_diag()
     if "gemm" in which:
         gemm_diag()
+    if "cfg1" in which or "cfg2" in which:
+        model_diag(which)
