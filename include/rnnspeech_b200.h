@@ -133,6 +133,8 @@ int rs_am_forward(rs_am* am, const float* params_d, const float* x_d, const int3
  * that event only).  backward = 0 | 1. */
 int rs_am_enable_timing(rs_am* am, int enable);
 int rs_am_recurrent_ms(rs_am* am, int backward, int layer, float* ms);
+/* Debug: %globaltimer stamps [T][8] (uint64) of CTA 0 of the layer-0 recurrent kernels. */
+int rs_am_set_debug_timeline(rs_am* am, void* fwd_d, void* bwd_d);
 /* keep_in / keep_out / seed must repeat the values given to the matching forward
  * (the dropout masks are recomputed, not stored).  The reserve is consumed:
  * one backward per forward. */

@@ -94,6 +94,7 @@ extern "C" int rs_am_create(rs_am** out, int num_layers, int hidden_size, int in
   am->off_output_b = off; off += num_labels;
   am->n_params = off;
   am->timing = 0;
+  am->dbg_fwd = am->dbg_bwd = nullptr;
   // tensor-core path when the shape fits it (RS_DISABLE_TC=1 forces the FFMA kernels)
   {
     RecTcBwdGeom bg;
@@ -125,6 +126,15 @@ extern "C" int rs_am_enable_timing(rs_am* am, int enable) {
       }
     am->timing = 1;
   }
+  return RS_OK;
+}
+
+// Debug: device buffers ([T][8] uint64 each) that receive %globaltimer stamps of CTA 0 of the
+// layer-0 tensor-core recurrent kernels (see tools/gpu_diag.py timeline); NULL disables.
+extern "C" int rs_am_set_debug_timeline(rs_am* am, void* fwd_d, void* bwd_d) {
+  RS_REQUIRE(am != nullptr, RS_ERR_INVALID, "rs_am_set_debug_timeline: NULL handle");
+  am->dbg_fwd = (unsigned long long*)fwd_d;
+  am->dbg_bwd = (unsigned long long*)bwd_d;
   return RS_OK;
 }
 

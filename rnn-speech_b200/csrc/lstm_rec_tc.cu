@@ -41,6 +41,12 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define RS_STAMP(dbgp, step, ev) do { if ((dbgp) && blockIdx.x == 0) (dbgp)[(size_t)(step) * 8 + (ev)] = gtime(); } while (0)
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __device__ __forceinline__ float pick4(int sel, float a0, float a1, float a2, float a3) {
@@ -95,6 +101,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
           while (ld_acquire_u32(a.barrier) < nctas * (unsigned)t) {}
           tc::fence_proxy_async_all();     // other CTAs' generic-proxy stores of h_{t-1} -> TMA reads
         }
+        RS_STAMP(a.dbg, t, 0);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
@@ -104,6 +111,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
           tc::tma_load_2d(st, &tmH_hi, kb * 64, t * B, &full_bar[s]);                  // slot t = h_{t-1}
           tc::tma_load_2d(st + plane_b_bytes, &tmH_lo, kb * 64, t * B, &full_bar[s]);
         }
+        RS_STAMP(a.dbg, t, 1);
       }
     }
   } else if (warp == 3) {
@@ -120,6 +128,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
           const uint32_t ph = (it / p.stages) & 1;
           tc::mbar_wait(&full_bar[s], ph);
           tc::tc_fence_after();
+          if (kb == 0) RS_STAMP(a.dbg, t, 2);
           const uint64_t dwh = tc::smem_desc_sw128(sa + (uint32_t)kb * p.a_kb_bytes);
           const uint64_t dwl = tc::smem_desc_sw128(sa + (uint32_t)(nkb + kb) * p.a_kb_bytes);
           const uint32_t sb = tc::smem_u32(sRing + (size_t)s * p.stage_bytes);
@@ -133,6 +142,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
           tc::mma_commit(&empty_bar[s]);
         }
         tc::mma_commit(&tfull_bar);
+        RS_STAMP(a.dbg, t, 3);
       }
     }
   } else {
@@ -178,6 +188,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
       }
       tc::mbar_wait(&tfull_bar, (uint32_t)(t & 1));
       tc::tc_fence_after();
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 4);
 #pragma unroll
       for (int gl = 0; gl < MAXG; ++gl) {
         const int gi = hf + 2 * gl;
@@ -238,10 +249,12 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
         }
       }
       // publish: every epilogue thread's stores -> gpu scope -> async proxy of other SMs
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 5);
       tc::tc_fence_before();
       __threadfence();
       tc::fence_proxy_async_all();
       epi_bar_sync();
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 6);
       if (threadIdx.x == 0 && t + 1 < T) red_release_add(a.barrier, 1u);
     }
     if (row_ok) {
@@ -316,6 +329,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         ++epoch;
         while (ld_acquire_u32(a.barrier) < nctas * epoch) {}
         tc::fence_proxy_async_all();
+        RS_STAMP(a.dbg, t, 0);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
@@ -323,6 +337,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           tc::mbar_arrive_expect_tx(&full_bar[s], p.stage_bytes);
           tc::tma_load_2d(sRing + (size_t)s * p.stage_bytes, &tmG, kb * 64, t * B, &full_bar[s]);
         }
+        RS_STAMP(a.dbg, t, 1);
       }
     }
   } else if (warp == 3) {
@@ -338,6 +353,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           const uint32_t ph = (it / p.stages) & 1;
           tc::mbar_wait(&full_bar[s], ph);
           tc::tc_fence_after();
+          if (kb == 0) RS_STAMP(a.dbg, t, 2);
           const uint64_t dg = tc::smem_desc_sw128(tc::smem_u32(sRing + (size_t)s * p.stage_bytes));
           const uint64_t dw = tc::smem_desc_sw128(sw + (uint32_t)kb * W_KB_BYTES);
 #pragma unroll
@@ -345,6 +361,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           tc::mma_commit(&empty_bar[s]);
         }
         tc::mma_commit(&tfull_bar);
+        RS_STAMP(a.dbg, t, 3);
       }
     }
   } else {
@@ -381,6 +398,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         tc::tc_fence_after();
         tc::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 8), dh);
         tc::tmem_ld_wait();
+        if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 4);
       } else {
 #pragma unroll
         for (int u = 0; u < 8; ++u) dh[u] = 0.f;
@@ -428,10 +446,12 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           *reinterpret_cast<uint4*>(a.dg_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
         }
       }
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 5);
       tc::tc_fence_before();
       __threadfence();
       tc::fence_proxy_async_all();
       epi_bar_sync();
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 6);
       if (threadIdx.x == 0 && t > 0) red_release_add(a.barrier, 1u);
     }
   }

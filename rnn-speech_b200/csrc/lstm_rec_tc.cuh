@@ -34,6 +34,7 @@ struct RecTcFwdArgs {
   float* cs;                       // [T,B,H] fp32 (training) or nullptr
   unsigned* barrier;
   int T;
+  unsigned long long* dbg;         // optional [T][8] globaltimer stamps of CTA 0 (nullptr = off)
 };
 
 int lstm_rec_tc_forward(const RecTcGeom& g, const RecTcFwdArgs& a, cudaStream_t st);
@@ -58,6 +59,7 @@ struct RecTcBwdArgs {
   const int* len;
   unsigned* barrier;
   int T;
+  unsigned long long* dbg;         // optional [T][8] globaltimer stamps of CTA 0
 };
 int lstm_rec_tc_backward(const RecTcBwdGeom& g, const RecTcBwdArgs& a, cudaStream_t st);
 

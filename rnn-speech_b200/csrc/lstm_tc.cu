@@ -231,6 +231,7 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     a.cT = state_out_d ? state_out_d + ((size_t)l * 2 + 0) * B * H : nullptr;
     a.hT = state_out_d ? state_out_d + ((size_t)l * 2 + 1) * B * H : nullptr;
     a.gates = bf.gates[l]; a.cs = bf.cs[l]; a.barrier = bf.barrier; a.T = T;
+    a.dbg = (l == 0) ? am->dbg_fwd : nullptr;
     if (am->timing) RS_CHECK_CUDA(cudaEventRecord(am->ev[0][l][0], st));
     RC(lstm_rec_tc_forward(am->tc, a, st));
     if (am->timing) { RS_CHECK_CUDA(cudaEventRecord(am->ev[0][l][1], st)); am->ev_valid[0][l] = 1; }
@@ -319,6 +320,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     a.dout = dout; a.gates = bf.gates[l]; a.cs = bf.cs[l];
     a.c0 = bf.state0 + ((size_t)l * 2 + 0) * B * H;
     a.wh_hi = bf.whs_hi[l]; a.dg_hi = bf.dg_hi; a.dg_lo = bf.dg_lo; a.len = len_d; a.barrier = bf.barrier; a.T = T;
+    a.dbg = (l == 0) ? am->dbg_bwd : nullptr;
     if (am->timing) RS_CHECK_CUDA(cudaEventRecord(am->ev[1][l][0], st));
     RC(lstm_rec_tc_backward(bg, a, st));
     if (am->timing) { RS_CHECK_CUDA(cudaEventRecord(am->ev[1][l][1], st)); am->ev_valid[1][l] = 1; }

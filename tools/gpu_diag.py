@@ -109,7 +109,8 @@ def gemm_diag():
 
 
 def model_diag(which):
-    from tests.conftest import golden
+    def golden(name):
+        return np.load(os.path.join(ROOT, "tests", "golden", name))
     if "cfg1" in which:
         g = golden("model_cfg1.npz")
         L, H, F, C, T, B = [int(v) for v in g["dims"]]
@@ -154,6 +155,9 @@ def model_diag(which):
         m.create_training_rnn(1.0, 1.0, 1, 3e-4, 0.33)
         m.load_flat_params(flat)
         m.enable_timing()
+        dbg_f = torch.zeros((T, 8), dtype=torch.int64, device=dev)
+        dbg_b = torch.zeros((T, 8), dtype=torch.int64, device=dev)
+        rs._lib.call("rs_am_set_debug_timeline", m._handle, dbg_f.data_ptr(), dbg_b.data_ptr())
         print("cfg2: tensor cores:", m.uses_tensor_cores)
         xd, ld = torch.from_numpy(x).to(dev), torch.from_numpy(lens).to(dev)
         for it in range(2):
@@ -177,6 +181,16 @@ def model_diag(which):
         torch.cuda.synchronize()
         print("cfg2 grads finite:", bool(torch.isfinite(m.grads).all()), "norm %.4e" % float(m.grads.double().norm()))
         print("cfg2 recurrent kernel ms fwd/bwd:", m.recurrent_ms())
+        names = ["P0 barrier seen", "P1 TMA issued", "M0 first stage landed", "M1 MMAs issued", "E0 accum ready",
+                 "E1 math+stores done", "E2 fences+cta bar done"]
+        for tag, d in (("fwd", dbg_f.cpu().numpy()), ("bwd", dbg_b.cpu().numpy())):
+            steps = list(range(400, 406)) if tag == "fwd" else list(range(405, 399, -1))
+            t0 = d[steps[0], 0]
+            print("timeline %s (ns relative to step %d's P0; columns: %s)" % (tag, steps[0], "; ".join(names)))
+            for sidx in steps:
+                print("   step %d:" % sidx, " ".join("%7d" % (int(d[sidx, e]) - int(t0)) for e in range(7)))
+            per = np.diff(d[100:900, 0].astype(np.int64))
+            print("   mean |P0(t+1)-P0(t)| = %.0f ns" % np.abs(per).mean())
 
 
 if __name__ == "__main__":
