@@ -185,6 +185,9 @@ int rs_clip_adam_step(float* params_d, const float* grads_d, float* m_d, float* 
  * D[128,N] = A[128,K] * B[N,K]^T on one CTA; split != 0 uses the bf16x3 split.
  * ------------------------------------------------------------------------ */
 int rs_tc_selftest(const float* A_d, const float* B_d, float* D_d, int N, int K, int split, void* stream);
+/* tcgen05.mma issue-rate microbenchmark (one CTA, SS operands): out_cycles_d int64[2] =
+ * {cycles to issue, cycles until the last MMA completed}. */
+int rs_tc_mma_bench(int M, int N, int count, int variant, int nacc, void* out_cycles_d, void* stream);
 /* Test hook for the production tcgen05 GEMM: C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) from fp32
  * inputs (split to bf16 planes inside); products = 1 (plain bf16) or 3 (bf16x3).
  * scratch_d: 2*(M*K + N*K)*2 + 64 bytes.  K multiple of 8. */

@@ -69,7 +69,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t tmem = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // converged warp; one elected lane issues each TMA / arrive
       uint32_t it = 0;
       const uint32_t tx = (uint32_t)(TILE_A_BYTES + TILE_B_BYTES + (use_alo ? TILE_A_BYTES : 0) + (use_blo ? TILE_B_BYTES : 0));
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -79,16 +79,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t ph = (it / STAGES) & 1;
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           unsigned char* st = smem + (size_t)s * STAGE_BYTES;
-          tc::mbar_arrive_expect_tx(&full_bar[s], tx);
-          tc::tma_load_2d(st, &tmA_hi, kb * BK, m0, &full_bar[s]);
-          tc::tma_load_2d(st + 2 * TILE_A_BYTES, &tmB_hi, kb * BK, n0, &full_bar[s]);
-          if (use_alo) tc::tma_load_2d(st + TILE_A_BYTES, &tmA_lo, kb * BK, m0, &full_bar[s]);
-          if (use_blo) tc::tma_load_2d(st + 2 * TILE_A_BYTES + TILE_B_BYTES, &tmB_lo, kb * BK, n0, &full_bar[s]);
+          tc::mbar_arrive_expect_tx_warp(&full_bar[s], tx);
+          tc::tma_load_2d_warp(st, &tmA_hi, kb * BK, m0, &full_bar[s]);
+          tc::tma_load_2d_warp(st + 2 * TILE_A_BYTES, &tmB_hi, kb * BK, n0, &full_bar[s]);
+          if (use_alo) tc::tma_load_2d_warp(st + TILE_A_BYTES, &tmA_lo, kb * BK, m0, &full_bar[s]);
+          if (use_blo) tc::tma_load_2d_warp(st + 2 * TILE_A_BYTES + TILE_B_BYTES, &tmB_lo, kb * BK, n0, &full_bar[s]);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // converged warp, elect.sync inside each issue
       const uint32_t idesc = tc::instr_desc_bf16(BM, BN);
       uint32_t it = 0, tl = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
@@ -107,13 +107,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint64_t dbl = tc::smem_desc_sw128(sa + 2 * TILE_A_BYTES + TILE_B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            tc::mma_bf16_ss(d, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
-            if (use_blo) tc::mma_bf16_ss(d, dah + 2 * k, dbl + 2 * k, idesc, true);
-            if (use_alo) tc::mma_bf16_ss(d, dal + 2 * k, dbh + 2 * k, idesc, true);
+            tc::mma_bf16_ss_warp(d, dah + 2 * k, dbh + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+            if (use_blo) tc::mma_bf16_ss_warp(d, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+            if (use_alo) tc::mma_bf16_ss_warp(d, dal + 2 * k, dbh + 2 * k, idesc, 1u);
           }
-          tc::mma_commit(&empty_bar[s]);
+          tc::mma_commit_warp(&empty_bar[s]);
         }
-        tc::mma_commit(&tfull_bar[as]);
+        tc::mma_commit_warp(&tfull_bar[as]);
       }
     }
   } else if (warp >= 4) {

@@ -1,36 +1,52 @@
-// Tensor-core persistent recurrent LSTM kernel (forward), sm_100a.
+// Tensor-core persistent recurrent LSTM kernels (forward and backward), sm_100a.
 //
 // Replaces the tf.nn.dynamic_rnn loop over BasicLSTMCell
-// (/root/reference/models/AcousticModel.py:227-237, :277-278) for one layer; same
-// semantics as lstm_rec.cu / oracle/model.py.
+// (/root/reference/models/AcousticModel.py:227-237, :277-278) and its BPTT for one layer;
+// same semantics as lstm_rec.cu / oracle/model.py.
 //
-// Ownership: CTA j owns hidden units [jU, jU+U) (U = 16 or 8).  Its 4U gate rows of
-// Wh^T (bf16 hi + lo planes, K-major, SWIZZLE_128B) are loaded ONCE by TMA and stay in
-// shared memory for all T steps; the cell state stays in registers.  Per step:
+// Forward.  CTA j owns hidden units [jU, jU+U) (U = 8 or 16).  Its 4U gate rows of Wh^T
+// (bf16 hi + lo planes, K-major, SWIZZLE_128B) are loaded ONCE by TMA and stay in shared
+// memory for all T steps; the cell state stays in registers.  Per step:
 //   producer thread : waits on the grid barrier (all CTAs published h_{t-1}), then streams
-//                     h_{t-1} (hi + lo planes, [Bpad x H]) through a TMA ring, 64 columns a stage
-//   MMA thread      : D[128 x Bpad] (TMEM, fp32) = W_hi h_hi + W_hi h_lo + W_lo h_hi, tcgen05.mma
-//                     M = 128 (rows >= 4U are don't-care), N = Bpad, K = 16 per instruction
+//                     h_{t-1} (hi + lo planes, [Bpad x H]) with TMA, 64 columns a box, four
+//                     boxes (one "group") per mbarrier -- the whole of h_{t-1} is in flight
+//   MMA thread      : D[64 x Bpad] (TMEM, fp32) = W_hi h_hi + W_hi h_lo + W_lo h_hi with
+//                     tcgen05.mma M = 64 (rows >= 4U are don't-care), N = Bpad, K = 16
 //   epilogue warps  : tcgen05.ld the accumulator, add the hoisted input projection gx, apply
-//                     the gate non-linearities (row r = 4*unit + gate, so a lane quad holds
+//                     the gate non-linearities (row m = 4*unit + gate, so a lane quad holds
 //                     i,j,f,o of one unit), exchange inside the quad by shuffles, update c,
 //                     publish h_t as bf16 hi/lo planes, arrive on the grid barrier.
+// Backward.  CTA j owns hidden units [16j, 16j+16): its 16 rows of Wh ([16][4H] bf16) are
+// the resident B operand (N = 16); dgates_t ([Bpad x 4H] bf16) streams through a TMA ring as
+// the A operand (M = 64), D[b][u] = dh_{t-1}.
+//
+// M = 64 accumulator layout (cta_group::1): row m lives in TMEM lane 32*(m/16) + m%16, i.e.
+// 16 lanes of each of the four 32-lane sub-partitions; epilogue warp w reads sub-partition
+// w%4 and only its lanes 0..15 carry rows.
+//
+// Measured on B200 (tools/gpu_diag.py timeline): one tcgen05.mma with a 128-row SS operand
+// costs ~44 cycles (shared-memory operand bandwidth), one mbarrier wait + commit round ~400
+// cycles: hence M = 64 and four K-blocks per barrier.
 #include "lstm_rec_tc.cuh"
 #include "tc_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace rs {
 namespace {
 
-constexpr int NTHREADS = 192;   // warps 0,1,4,5: epilogue; warp 2: TMA producer; warp 3: MMA issuer
+constexpr int NTHREADS = 320;   // warps 0-7: epilogue (sub-partition w%4, column half w/4); 8: TMA; 9: MMA
+constexpr int NEPI = 256;
 constexpr int MAXG = 2;         // 16-column groups per epilogue thread (Bpad <= 64, two column halves)
-constexpr int MAXSTAGES = 8;
+constexpr int MAXSLOTS = 16;    // ring slots (groups of GKB K-blocks)
+constexpr int GKB = 4;          // K-blocks (64 columns each) per mbarrier
 
 struct KArgs {
   RecTcFwdArgs a;
-  int H, B, Bpad, U, nslice, stages, nkb;
+  int H, B, Bpad, U, nslice, slots, nkb, ngroups;
+  int variant;                  // bit0: per-CTA flags (else one atomic counter); bit1: reserve stores before the signal
   uint32_t a_kb_bytes;          // one K-block of the resident operand: 4U rows x 128 B
-  uint32_t stage_bytes;         // one ring stage: 2 planes x Bpad rows x 128 B
+  uint32_t kb_bytes;            // one streamed K-block: 2 planes x Bpad rows x 128 B
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -46,8 +62,35 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define RS_STAMP(dbgp, step, ev) do { if ((dbgp) && blockIdx.x == 0) (dbgp)[(size_t)(step) * 8 + (ev)] = gtime(); } while (0)
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Grid barrier without atomics: CTA j publishes its step count in flags[j]; a whole warp polls
+// all flags with coalesced acquire loads (one L2 round trip per poll, no same-address traffic).
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_flags_warp(const unsigned* flags, unsigned nctas, unsigned target, int lane,
+                                                unsigned long long* dbg = nullptr, int step = 0) {
+  // relaxed polling (all flag loads of one poll in flight together), one acquire fence at the end
+  for (;;) {
+    unsigned v0 = target, v1 = target, v2 = target, v3 = target, v4 = target;
+    if ((unsigned)lane < nctas) v0 = ld_relaxed_u32(flags + lane);
+    if ((unsigned)lane + 32 < nctas) v1 = ld_relaxed_u32(flags + lane + 32);
+    if ((unsigned)lane + 64 < nctas) v2 = ld_relaxed_u32(flags + lane + 64);
+    if ((unsigned)lane + 96 < nctas) v3 = ld_relaxed_u32(flags + lane + 96);
+    if ((unsigned)lane + 128 < nctas) v4 = ld_relaxed_u32(flags + lane + 128);
+    const bool ok = v0 >= target && v1 >= target && v2 >= target && v3 >= target && v4 >= target;
+    if (__all_sync(0xffffffffu, ok)) break;
+  }
+  if (dbg && lane == 0 && blockIdx.x == 0) dbg[(size_t)step * 16 + 15] = gtime();
+  __syncwarp();
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+#define RS_STAMP(dbgp, step, ev) do { if ((dbgp) && blockIdx.x == 0) (dbgp)[(size_t)(step) * 16 + (ev)] = gtime(); } while (0)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ float pick4(int sel, float a0, float a1, float a2, float a3) {
   const float lo = (sel & 1) ? a1 : a0;
@@ -60,101 +103,127 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
                   const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo, KArgs p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t a_full, full_bar[MAXSTAGES], empty_bar[MAXSTAGES], tfull_bar;
+  __shared__ uint64_t a_full, full_bar[MAXSLOTS], empty_bar[MAXSLOTS], tfull_bar;
   __shared__ uint32_t tmem_slot;
   const RecTcFwdArgs& a = p.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x;
-  const int H = p.H, B = p.B, Bpad = p.Bpad, U = p.U, T = a.T, nkb = p.nkb;
+  const int H = p.H, B = p.B, Bpad = p.Bpad, U = p.U, T = a.T, nkb = p.nkb, ngroups = p.ngroups;
   unsigned char* sA = smem;                                         // [2 planes][nkb][a_kb_bytes]
-  unsigned char* sRing = smem + 2 * (size_t)nkb * p.a_kb_bytes;     // [stages][2 planes][Bpad*128]
+  unsigned char* sRing = smem + 2 * (size_t)nkb * p.a_kb_bytes;     // [slots][GKB][2 planes][Bpad*128]
   const uint32_t plane_b_bytes = (uint32_t)Bpad * 128;
+  const uint32_t slot_bytes = GKB * p.kb_bytes;
+  const bool full_flight = p.slots >= ngroups;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < Bpad) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     tc::mbar_init(&a_full, 1);
-    for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.slots; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     tc::mbar_init(&tfull_bar, 1);
     tc::fence_mbar_init();
   }
-  if (warp == 2) tc::tmem_alloc(&tmem_slot, tmem_cols);
+  if (warp == 8) tc::tmem_alloc(&tmem_slot, tmem_cols);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp == 2) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
+    // (the whole warp runs this converged; one elected lane issues each TMA / arrive)
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmW_hi); tc::tma_prefetch_desc(&tmW_lo);
       tc::tma_prefetch_desc(&tmH_hi); tc::tma_prefetch_desc(&tmH_lo);
-      tc::mbar_arrive_expect_tx(&a_full, 2u * (uint32_t)nkb * p.a_kb_bytes);
-      for (int kb = 0; kb < nkb; ++kb) {
-        tc::tma_load_2d(sA + (size_t)kb * p.a_kb_bytes, &tmW_hi, kb * 64, j * 4 * U, &a_full);
-        tc::tma_load_2d(sA + (size_t)(nkb + kb) * p.a_kb_bytes, &tmW_lo, kb * 64, j * 4 * U, &a_full);
-      }
-      const unsigned nctas = gridDim.x;
-      uint32_t it = 0;
-      for (int t = 0; t < T; ++t) {
-        if (t > 0) {
-          while (ld_acquire_u32(a.barrier) < nctas * (unsigned)t) {}
-          tc::fence_proxy_async_all();     // other CTAs' generic-proxy stores of h_{t-1} -> TMA reads
-        }
-        RS_STAMP(a.dbg, t, 0);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          tc::mbar_wait(&empty_bar[s], ph ^ 1);
-          unsigned char* st = sRing + (size_t)s * p.stage_bytes;
-          tc::mbar_arrive_expect_tx(&full_bar[s], 2 * plane_b_bytes);
-          tc::tma_load_2d(st, &tmH_hi, kb * 64, t * B, &full_bar[s]);                  // slot t = h_{t-1}
-          tc::tma_load_2d(st + plane_b_bytes, &tmH_lo, kb * 64, t * B, &full_bar[s]);
-        }
-        RS_STAMP(a.dbg, t, 1);
-      }
     }
-  } else if (warp == 3) {
+    __syncwarp();
+    tc::mbar_arrive_expect_tx_warp(&a_full, 2u * (uint32_t)nkb * p.a_kb_bytes);
+    for (int kb = 0; kb < nkb; ++kb) {
+      tc::tma_load_2d_warp(sA + (size_t)kb * p.a_kb_bytes, &tmW_hi, kb * 64, j * 4 * U, &a_full);
+      tc::tma_load_2d_warp(sA + (size_t)(nkb + kb) * p.a_kb_bytes, &tmW_lo, kb * 64, j * 4 * U, &a_full);
+    }
+    const unsigned nctas = gridDim.x;
+    uint32_t git = 0;
+    for (int t = 0; t < T; ++t) {
+      if (t > 0) {
+        if (p.variant & 1) wait_flags_warp(a.barrier, nctas, (unsigned)t, lane, a.dbg, t);
+        else { while (ld_acquire_u32(a.barrier) < nctas * (unsigned)t) {} __syncwarp(); }
+        tc::fence_proxy_async_all();     // other CTAs' generic-proxy stores of h_{t-1} -> TMA reads
+      }
+      if (lane == 0) RS_STAMP(a.dbg, t, 0);
+      __syncwarp();
+      for (int grp = 0; grp < ngroups; ++grp, ++git) {
+        const int s = git % p.slots;
+        const uint32_t ph = (git / p.slots) & 1;
+        // with the whole of h in flight a slot is reused one step later, after the grid barrier,
+        // i.e. after this CTA's epilogue consumed the accumulator: no empty barrier needed
+        if (!full_flight) tc::mbar_wait(&empty_bar[s], ph ^ 1);
+        const int kb0 = grp * GKB, kbn = min(GKB, nkb - kb0);
+        unsigned char* st = sRing + (size_t)s * slot_bytes;
+        tc::mbar_arrive_expect_tx_warp(&full_bar[s], (uint32_t)kbn * p.kb_bytes);
+        for (int i = 0; i < kbn; ++i) {
+          unsigned char* dst = st + (size_t)i * p.kb_bytes;
+          tc::tma_load_2d_warp(dst, &tmH_hi, (kb0 + i) * 64, t * B, &full_bar[s]);               // slot t = h_{t-1}
+          tc::tma_load_2d_warp(dst + plane_b_bytes, &tmH_lo, (kb0 + i) * 64, t * B, &full_bar[s]);
+        }
+      }
+      if (lane == 0) RS_STAMP(a.dbg, t, 1);
+      __syncwarp();
+    }
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = tc::instr_desc_bf16(128, Bpad);
+    // (converged warp, elect.sync inside each issue: see tc_common.cuh)
+    {
+      const uint32_t idesc = tc::instr_desc_bf16(64, Bpad);
       tc::mbar_wait(&a_full, 0);
       tc::tc_fence_after();
-      const uint32_t sa = tc::smem_u32(sA);
-      uint32_t it = 0;
+      const uint64_t dw_hi0 = tc::smem_desc_sw128(tc::smem_u32(sA));
+      const uint64_t dw_lo0 = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)nkb * p.a_kb_bytes));
+      const uint64_t dring0 = tc::smem_desc_sw128(tc::smem_u32(sRing));
+      const uint64_t a_kb_u = p.a_kb_bytes >> 4, kb_u = p.kb_bytes >> 4, pl_u = plane_b_bytes >> 4;
+      uint32_t git = 0;
       for (int t = 0; t < T; ++t) {
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        for (int grp = 0; grp < ngroups; ++grp, ++git) {
+          const int s = git % p.slots;
+          const uint32_t ph = (git / p.slots) & 1;
           tc::mbar_wait(&full_bar[s], ph);
           tc::tc_fence_after();
-          if (kb == 0) RS_STAMP(a.dbg, t, 2);
-          const uint64_t dwh = tc::smem_desc_sw128(sa + (uint32_t)kb * p.a_kb_bytes);
-          const uint64_t dwl = tc::smem_desc_sw128(sa + (uint32_t)(nkb + kb) * p.a_kb_bytes);
-          const uint32_t sb = tc::smem_u32(sRing + (size_t)s * p.stage_bytes);
-          const uint64_t dhh = tc::smem_desc_sw128(sb), dhl = tc::smem_desc_sw128(sb + plane_b_bytes);
+          if (lane == 0 && grp == 0) RS_STAMP(a.dbg, t, 2);
+          if (lane == 0 && grp < 4) RS_STAMP(a.dbg, t, 8 + grp);
+          __syncwarp();
+          const int kb0 = grp * GKB, kbn = min(GKB, nkb - kb0);
+          for (int i = 0; i < kbn; ++i) {
+            const uint64_t dwh = dw_hi0 + (uint64_t)(kb0 + i) * a_kb_u;
+            const uint64_t dwl = dw_lo0 + (uint64_t)(kb0 + i) * a_kb_u;
+            const uint64_t dhh = dring0 + (uint64_t)s * (slot_bytes >> 4) + (uint64_t)i * kb_u;
+            const uint64_t dhl = dhh + pl_u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            tc::mma_bf16_ss(tmem, dwh + 2 * k, dhh + 2 * k, idesc, (kb | k) != 0);
-            tc::mma_bf16_ss(tmem, dwh + 2 * k, dhl + 2 * k, idesc, true);
-            tc::mma_bf16_ss(tmem, dwl + 2 * k, dhh + 2 * k, idesc, true);
+            for (int k = 0; k < 4; ++k) {
+              tc::mma_bf16_ss_warp(tmem, dwh + 2 * k, dhh + 2 * k, idesc, (uint32_t)((kb0 | i | k) != 0));
+              tc::mma_bf16_ss_warp(tmem, dwh + 2 * k, dhl + 2 * k, idesc, 1u);
+              tc::mma_bf16_ss_warp(tmem, dwl + 2 * k, dhh + 2 * k, idesc, 1u);
+            }
           }
-          tc::mma_commit(&empty_bar[s]);
+          if (lane == 0 && grp < 4) RS_STAMP(a.dbg, t, 12 + grp);
+          __syncwarp();
+          if (!full_flight) tc::mma_commit_warp(&empty_bar[s]);
         }
-        tc::mma_commit(&tfull_bar);
-        RS_STAMP(a.dbg, t, 3);
+        tc::mma_commit_warp(&tfull_bar);
+        if (lane == 0) RS_STAMP(a.dbg, t, 3);
+        __syncwarp();
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;                     // TMEM lane quadrant (rows 32q .. 32q+31)
+    const int q = warp & 3;                     // TMEM sub-partition: accumulator rows 16q .. 16q+15 in lanes 0..15
     const int hf = warp >> 2;                   // which 16-column groups: hf, hf + 2
-    const int r = q * 32 + lane;                // accumulator row
-    const bool row_ok = r < 4 * U;
+    const int m = q * 16 + (lane & 15);         // accumulator row
+    const bool row_ok = lane < 16 && m < 4 * U;
     const int g = lane & 3;                     // gate of this row: 0 i, 1 j, 2 f, 3 o
-    const int unit = j * U + (r >> 2);
+    const int unit = j * U + (m >> 2);
     const int ng = Bpad / 16;
     float c[MAXG][4], hl[MAXG][4];
+    float act_keep[MAXG][16], cn_keep[MAXG][4];
     int lenr[MAXG][4];
 #pragma unroll
     for (int gl = 0; gl < MAXG; ++gl)
@@ -178,7 +247,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
         const int gi = hf + 2 * gl;
         if (row_ok && gi < ng) {
           const float4* gp = reinterpret_cast<const float4*>(
-              a.gx + (((size_t)t * p.nslice + j) * (4 * U) + r) * Bpad + gi * 16);
+              a.gx + (((size_t)t * p.nslice + j) * (4 * U) + m) * Bpad + gi * 16);
 #pragma unroll
           for (int i = 0; i < 4; ++i) gxv[gl][i] = __ldg(gp + i);
         } else {
@@ -207,14 +276,11 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
               act[4 * i + e] = fmaf(fast_sigmoid(z), post_m, post_a);
             }
           }
-          if (a.gates && row_ok) {
+          // (the activated gates are kept for backward; they are stored AFTER h_t is published,
+          //  below, so that they do not sit in front of the barrier's store drain)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int b = gi * 16 + i;
-              if (b < B) a.gates[((size_t)t * B + b) * 4 * H + (size_t)g * H + unit] = act[i];
-            }
-          }
-          // quad exchange: this lane owns cells b = gi*16 + 4g + k; gate tau comes from lane g^... = tau
+          for (int i = 0; i < 16; ++i) act_keep[gl][i] = act[i];
+          // quad exchange: this lane owns cells b = gi*16 + 4g + k; gate tau comes from lane g ^ (g^tau)
           float own[4], rcv[3][4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) own[k] = pick4(g, act[k], act[4 + k], act[8 + k], act[12 + k]);
@@ -243,19 +309,64 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
               const size_t o = ((size_t)(t + 1) * B + b) * H + unit;
               a.h_hi[o] = hh;
               a.h_lo[o] = hlo;
-              if (a.cs) a.cs[((size_t)t * B + b) * H + unit] = c_new;
+            }
+            cn_keep[gl][k] = c_new;
+          }
+        }
+      }
+      if (p.variant & 2) {
+      if (a.gates && row_ok) {
+#pragma unroll
+        for (int gl = 0; gl < MAXG; ++gl) {
+          const int gi = hf + 2 * gl;
+          if (gi < ng) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int b = gi * 16 + i;
+              if (b < B) a.gates[((size_t)t * B + b) * 4 * H + (size_t)g * H + unit] = act_keep[gl][i];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int b = gi * 16 + 4 * g + k;
+              if (b < B) a.cs[((size_t)t * B + b) * H + unit] = cn_keep[gl][k];
             }
           }
         }
       }
-      // publish: every epilogue thread's stores -> gpu scope -> async proxy of other SMs
+      }
+      // publish: generic stores -> async proxy (per-thread proxy fence); gpu-scope visibility:
+      // the CTA barrier followed by ONE release-add is cumulative over every thread's stores
       if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 5);
       tc::tc_fence_before();
-      __threadfence();
       tc::fence_proxy_async_all();
       epi_bar_sync();
       if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 6);
-      if (threadIdx.x == 0 && t + 1 < T) red_release_add(a.barrier, 1u);
+      if (threadIdx.x == 0 && t + 1 < T) {
+        if (p.variant & 1) st_release_u32(a.barrier + j, (unsigned)(t + 1));
+        else red_release_add(a.barrier, 1u);
+      }
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 7);
+      // reserve for backward (not on the critical path of the recurrence)
+      if (!(p.variant & 2)) {
+      if (a.gates && row_ok) {
+#pragma unroll
+        for (int gl = 0; gl < MAXG; ++gl) {
+          const int gi = hf + 2 * gl;
+          if (gi < ng) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int b = gi * 16 + i;
+              if (b < B) a.gates[((size_t)t * B + b) * 4 * H + (size_t)g * H + unit] = act_keep[gl][i];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int b = gi * 16 + 4 * g + k;
+              if (b < B) a.cs[((size_t)t * B + b) * H + unit] = cn_keep[gl][k];
+            }
+          }
+        }
+      }
+      }
     }
     if (row_ok) {
 #pragma unroll
@@ -272,103 +383,112 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_const
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tmem, tmem_cols);
+  if (warp == 8) tc::tmem_dealloc(tmem, tmem_cols);
 }
 
-
 // ------------------------------------------------------------------------------------
-// Backward recurrent kernel.  CTA j owns hidden units [16j, 16j+16): its 16 rows of Wh
-// ([16][4H] bf16, K-major) are resident in shared memory (the B operand, N = 16); per
-// step the freshly published dgates_t ([Bpad x 4H] bf16) stream through a TMA ring as
-// the A operand (M = 128, rows >= Bpad are don't-care) and D[b][u] = dh_{t-1} lands in
-// TMEM lanes 0..B-1.  Epilogue thread (b, 8 units) does the cell backward for its units.
+// Backward recurrent kernel (see the file header).
 // ------------------------------------------------------------------------------------
 constexpr int BW_U = 16;
+constexpr int BW_GKB = 8;        // K-blocks per mbarrier in the backward ring
 
 struct KBwdArgs {
   RecTcBwdArgs a;
-  int H, B, Bpad, stages, nkb;
-  uint32_t stage_bytes;          // Bpad rows x 128 B
+  int H, B, Bpad, slots, nkb, ngroups;
+  int variant;
+  uint32_t kb_bytes;             // Bpad rows x 128 B
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG, KBwdArgs p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t w_full, full_bar[MAXSTAGES], empty_bar[MAXSTAGES], tfull_bar;
+  __shared__ uint64_t w_full, full_bar[MAXSLOTS], empty_bar[MAXSLOTS], tfull_bar;
   __shared__ uint32_t tmem_slot;
   const RecTcBwdArgs& a = p.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x;
-  const int H = p.H, B = p.B, T = a.T, nkb = p.nkb, G = 4 * p.H;
+  const int H = p.H, B = p.B, T = a.T, nkb = p.nkb, ngroups = p.ngroups, G = 4 * p.H;
   constexpr uint32_t W_KB_BYTES = BW_U * 128;                       // 2 KB per K-block
   unsigned char* sW = smem;                                          // [nkb][16 rows x 128 B]
-  unsigned char* sRing = smem + (size_t)nkb * W_KB_BYTES;            // [stages][Bpad x 128 B] (+ overhang pad)
+  unsigned char* sRing = smem + (size_t)nkb * W_KB_BYTES;            // [slots][GKB][Bpad x 128 B] (+ overhang pad)
+  const uint32_t slot_bytes = BW_GKB * p.kb_bytes;
 
   if (threadIdx.x == 0) {
     tc::mbar_init(&w_full, 1);
-    for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.slots; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     tc::mbar_init(&tfull_bar, 1);
     tc::fence_mbar_init();
   }
-  if (warp == 2) tc::tmem_alloc(&tmem_slot, 32);
+  if (warp == 8) tc::tmem_alloc(&tmem_slot, 32);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp == 2) {
-    if (lane == 0) {
-      tc::tma_prefetch_desc(&tmW); tc::tma_prefetch_desc(&tmG);
-      tc::mbar_arrive_expect_tx(&w_full, (uint32_t)nkb * W_KB_BYTES);
-      for (int kb = 0; kb < nkb; ++kb) tc::tma_load_2d(sW + (size_t)kb * W_KB_BYTES, &tmW, kb * 64, j * BW_U, &w_full);
-      const unsigned nctas = gridDim.x;
-      uint32_t it = 0;
-      unsigned epoch = 0;
-      for (int t = T - 1; t >= 1; --t) {        // dh_{t-1} from dgates_t
-        ++epoch;
-        while (ld_acquire_u32(a.barrier) < nctas * epoch) {}
-        tc::fence_proxy_async_all();
-        RS_STAMP(a.dbg, t, 0);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          tc::mbar_wait(&empty_bar[s], ph ^ 1);
-          tc::mbar_arrive_expect_tx(&full_bar[s], p.stage_bytes);
-          tc::tma_load_2d(sRing + (size_t)s * p.stage_bytes, &tmG, kb * 64, t * B, &full_bar[s]);
-        }
-        RS_STAMP(a.dbg, t, 1);
+  if (warp == 8) {
+    if (lane == 0) { tc::tma_prefetch_desc(&tmW); tc::tma_prefetch_desc(&tmG); }
+    __syncwarp();
+    tc::mbar_arrive_expect_tx_warp(&w_full, (uint32_t)nkb * W_KB_BYTES);
+    for (int kb = 0; kb < nkb; ++kb) tc::tma_load_2d_warp(sW + (size_t)kb * W_KB_BYTES, &tmW, kb * 64, j * BW_U, &w_full);
+    const unsigned nctas = gridDim.x;
+    uint32_t git = 0;
+    unsigned epoch = 0;
+    for (int t = T - 1; t >= 1; --t) {        // dh_{t-1} from dgates_t
+      ++epoch;
+      if (p.variant & 1) wait_flags_warp(a.barrier, nctas, epoch, lane, a.dbg, t);
+      else { while (ld_acquire_u32(a.barrier) < nctas * epoch) {} __syncwarp(); }
+      tc::fence_proxy_async_all();
+      if (lane == 0) RS_STAMP(a.dbg, t, 0);
+      __syncwarp();
+      for (int grp = 0; grp < ngroups; ++grp, ++git) {
+        const int s = git % p.slots;
+        const uint32_t ph = (git / p.slots) & 1;
+        tc::mbar_wait(&empty_bar[s], ph ^ 1);
+        const int kb0 = grp * BW_GKB, kbn = min(BW_GKB, nkb - kb0);
+        tc::mbar_arrive_expect_tx_warp(&full_bar[s], (uint32_t)kbn * p.kb_bytes);
+        for (int i = 0; i < kbn; ++i)
+          tc::tma_load_2d_warp(sRing + (size_t)s * slot_bytes + (size_t)i * p.kb_bytes, &tmG, (kb0 + i) * 64, t * B, &full_bar[s]);
       }
+      if (lane == 0) RS_STAMP(a.dbg, t, 1);
+      __syncwarp();
     }
-  } else if (warp == 3) {
-    if (lane == 0) {
-      const uint32_t idesc = tc::instr_desc_bf16(128, BW_U);
+  } else if (warp == 9) {
+    {
+      const uint32_t idesc = tc::instr_desc_bf16(64, BW_U);
       tc::mbar_wait(&w_full, 0);
       tc::tc_fence_after();
-      const uint32_t sw = tc::smem_u32(sW);
-      uint32_t it = 0;
+      const uint64_t dw0 = tc::smem_desc_sw128(tc::smem_u32(sW));
+      const uint64_t dring0 = tc::smem_desc_sw128(tc::smem_u32(sRing));
+      const uint64_t kb_u = p.kb_bytes >> 4;
+      uint32_t git = 0;
       for (int t = T - 1; t >= 1; --t) {
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        for (int grp = 0; grp < ngroups; ++grp, ++git) {
+          const int s = git % p.slots;
+          const uint32_t ph = (git / p.slots) & 1;
           tc::mbar_wait(&full_bar[s], ph);
           tc::tc_fence_after();
-          if (kb == 0) RS_STAMP(a.dbg, t, 2);
-          const uint64_t dg = tc::smem_desc_sw128(tc::smem_u32(sRing + (size_t)s * p.stage_bytes));
-          const uint64_t dw = tc::smem_desc_sw128(sw + (uint32_t)kb * W_KB_BYTES);
+          if (lane == 0 && grp == 0) RS_STAMP(a.dbg, t, 2);
+          __syncwarp();
+          const int kb0 = grp * BW_GKB, kbn = min(BW_GKB, nkb - kb0);
+          for (int i = 0; i < kbn; ++i) {
+            const uint64_t dg = dring0 + (uint64_t)s * (slot_bytes >> 4) + (uint64_t)i * kb_u;
+            const uint64_t dw = dw0 + (uint64_t)(kb0 + i) * (W_KB_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::mma_bf16_ss(tmem, dg + 2 * k, dw + 2 * k, idesc, (kb | k) != 0);
-          tc::mma_commit(&empty_bar[s]);
+            for (int k = 0; k < 4; ++k) tc::mma_bf16_ss_warp(tmem, dg + 2 * k, dw + 2 * k, idesc, (uint32_t)((kb0 | i | k) != 0));
+          }
+          tc::mma_commit_warp(&empty_bar[s]);
         }
-        tc::mma_commit(&tfull_bar);
-        RS_STAMP(a.dbg, t, 3);
+        tc::mma_commit_warp(&tfull_bar);
+        if (lane == 0) RS_STAMP(a.dbg, t, 3);
+        __syncwarp();
       }
     }
   } else {
-    const int q = warp & 3;                     // TMEM lane quadrant: batch rows 32q .. 32q+31
+    const int q = warp & 3;                     // TMEM sub-partition: batch rows 16q .. 16q+15 in lanes 0..15
     const int hf = warp >> 2;                   // units 8hf .. 8hf+7 of the slice
-    const int b = q * 32 + lane;
-    const bool ok = b < B;
+    const int b = q * 16 + (lane & 15);
+    const bool ok = lane < 16 && b < B;
     const int unit0 = j * BW_U + hf * 8;
     const int len_b = ok ? a.len[b] : 0;
     float dc[8];
@@ -448,62 +568,20 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       }
       if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 5);
       tc::tc_fence_before();
-      __threadfence();
       tc::fence_proxy_async_all();
       epi_bar_sync();
       if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 6);
-      if (threadIdx.x == 0 && t > 0) red_release_add(a.barrier, 1u);
+      if (threadIdx.x == 0 && t > 0) {
+        if (p.variant & 1) st_release_u32(a.barrier + j, n + 1);
+        else red_release_add(a.barrier, 1u);
+      }
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 7);
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tmem, 32);
+  if (warp == 8) tc::tmem_dealloc(tmem, 32);
 }
-
-}  // namespace
-
-bool rec_tc_bwd_geometry(int H, int B, RecTcBwdGeom* g) {
-  if (H % 64 != 0 || H < 64 || B < 1 || B > 64) return false;
-  if (H / BW_U > sm_count()) return false;
-  const int Bpad = (B + 15) / 16 * 16;
-  const size_t budget = 227 * 1024 - 2048;
-  const int nkb = 4 * H / 64;
-  const size_t w_bytes = (size_t)nkb * BW_U * 128;
-  const size_t stage = (size_t)Bpad * 128;
-  const size_t overhang = 128 * 128 - stage;          // M = 128 reads 128 rows from each stage base
-  if (w_bytes + 2 * stage + overhang > budget) return false;
-  int stages = (int)((budget - w_bytes - overhang) / stage);
-  if (stages > MAXSTAGES) stages = MAXSTAGES;
-  g->H = H; g->B = B; g->Bpad = Bpad; g->nslice = H / BW_U; g->stages = stages;
-  g->smem_bytes = w_bytes + (size_t)stages * stage + overhang + 1024;
-  return true;
-}
-
-int lstm_rec_tc_backward(const RecTcBwdGeom& g, const RecTcBwdArgs& a, cudaStream_t st) {
-  RS_REQUIRE(a.T > 0, RS_ERR_INVALID, "lstm_rec_tc_backward: T=%d", a.T);
-  CUtensorMap tw, tg;
-  int rc;
-  if ((rc = tmap_2d_bf16(&tw, a.wh_hi, g.H, 4 * g.H, 4 * g.H, BW_U)) != RS_OK) return rc;
-  if ((rc = tmap_2d_bf16(&tg, a.dg_hi, a.T * g.B, 4 * g.H, 4 * g.H, g.Bpad)) != RS_OK) return rc;
-  KBwdArgs p;
-  p.a = a;
-  p.H = g.H; p.B = g.B; p.Bpad = g.Bpad; p.stages = g.stages; p.nkb = 4 * g.H / 64;
-  p.stage_bytes = (uint32_t)g.Bpad * 128;
-  int dev = 0, per_sm = 0, nsm = 0;
-  RS_CHECK_CUDA(cudaGetDevice(&dev));
-  RS_CHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  RS_CHECK_CUDA(cudaFuncSetAttribute(rec_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-  RS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rec_tc_bwd_kernel, NTHREADS, g.smem_bytes));
-  RS_REQUIRE(per_sm * nsm >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_tc_backward: %d CTAs cannot be co-resident", g.nslice);
-  RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned), st));
-  void* kargs[] = {(void*)&tw, (void*)&tg, (void*)&p};
-  RS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)rec_tc_bwd_kernel, dim3(g.nslice), dim3(NTHREADS), kargs,
-                                            g.smem_bytes, st));
-  count_launch();
-  return RS_OK;
-}
-
-namespace {
 
 // wrec[(unit/U)*4U + (unit%U)*4 + g][k] = Wh[k][g*H + unit]; Wh = kernel + H*4H (row-major [H,4H])
 __global__ void pack_wrec_kernel(const float* __restrict__ Wh, int H, int U, __nv_bfloat16* __restrict__ hi,
@@ -534,31 +612,52 @@ bool rec_tc_geometry(int H, int B, RecTcGeom* g) {
   if (H % 64 != 0 || H < 64 || B < 1 || B > 64) return false;
   const int Bpad = (B + 15) / 16 * 16;
   const size_t budget = 227 * 1024 - 2048;            // dynamic smem minus alignment slack / static barriers
-  const int nkb = H / 64;
+  const int nkb = H / 64, ngroups = (nkb + GKB - 1) / GKB;
   const int nsm = sm_count();
+  // The step time is bounded by how much of h_{t-1} can be in flight at once, so take the
+  // slice width U whose resident weights leave room for the deepest ring; ties go to the
+  // wider slice (fewer CTAs re-reading h from L2).
+  bool found = false;
+  double best = -1.0;
   for (int U = 16; U >= 8; U /= 2) {
     if (H % U != 0 || H / U > nsm) continue;
     const size_t a_bytes = 2 * (size_t)nkb * (4 * U) * 128;
-    const size_t stage = 2 * (size_t)Bpad * 128;
-    if (a_bytes + 2 * stage > budget) continue;
-    // the M = 128 instruction reads 128 rows from each K-block base: the ring behind the
-    // resident operand must cover that overhang
-    int stages = (int)((budget - a_bytes) / stage);
-    if (stages > MAXSTAGES) stages = MAXSTAGES;
-    if (stages > nkb) stages = nkb;
-    if (stages < 2) continue;
-    const size_t overhang = 128 * 128 - (size_t)(4 * U) * 128;
-    if ((size_t)stages * stage < overhang) continue;
-    g->H = H; g->B = B; g->Bpad = Bpad; g->U = U; g->nslice = H / U; g->stages = stages;
-    g->smem_bytes = a_bytes + (size_t)stages * stage + 1024;
-    return true;
+    const size_t slot = (size_t)GKB * 2 * Bpad * 128;
+    if (a_bytes + slot > budget) continue;
+    int slots = (int)((budget - a_bytes) / slot);
+    if (slots > MAXSLOTS) slots = MAXSLOTS;
+    if (slots > ngroups) slots = ngroups;
+    if (slots < 1) continue;
+    // the M = 64 instruction reads 64 rows from each K-block base: what lies behind the resident
+    // operand (the ring) must cover that overhang
+    const size_t overhang = 64 * 128 - (size_t)(4 * U) * 128;
+    if ((size_t)slots * slot < overhang) continue;
+    const double score = (double)slots / ngroups;
+    if (score > best + 1e-9) {
+      best = score; found = true;
+      g->H = H; g->B = B; g->Bpad = Bpad; g->U = U; g->nslice = H / U; g->stages = slots;
+      g->smem_bytes = a_bytes + (size_t)slots * slot + 1024;
+    }
   }
-  return false;
+  return found;
 }
 
 int pack_wrec(const float* kernel, int H, int U, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st) {
   pack_wrec_kernel<<<dim3(cdiv(4 * H, 32), cdiv(H, 32)), dim3(32, 8), 0, st>>>(kernel + (size_t)H * 4 * H, H, U, hi, lo);
   RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+template <typename K>
+static int coop_launch(K kernel, int grid, size_t smem, void** kargs, cudaStream_t st, const char* name) {
+  int dev = 0, per_sm = 0, nsm = 0;
+  RS_CHECK_CUDA(cudaGetDevice(&dev));
+  RS_CHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  RS_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NTHREADS, smem));
+  RS_REQUIRE(per_sm * nsm >= grid, RS_ERR_UNSUPPORTED, "%s: %d CTAs cannot be co-resident", name, grid);
+  RS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(NTHREADS), kargs, smem, st));
+  count_launch();
   return RS_OK;
 }
 
@@ -573,21 +672,49 @@ int lstm_rec_tc_forward(const RecTcGeom& g, const RecTcFwdArgs& a, cudaStream_t 
   if ((rc = tmap_2d_bf16(&th_lo, a.h_lo, hrows, g.H, g.H, g.Bpad)) != RS_OK) return rc;
   KArgs p;
   p.a = a;
-  p.H = g.H; p.B = g.B; p.Bpad = g.Bpad; p.U = g.U; p.nslice = g.nslice; p.stages = g.stages; p.nkb = g.H / 64;
+  p.H = g.H; p.B = g.B; p.Bpad = g.Bpad; p.U = g.U; p.nslice = g.nslice; p.slots = g.stages; p.nkb = g.H / 64;
+  p.ngroups = (p.nkb + GKB - 1) / GKB;
   p.a_kb_bytes = (uint32_t)(4 * g.U) * 128;
-  p.stage_bytes = 2u * (uint32_t)g.Bpad * 128;
-  int dev = 0, per_sm = 0, nsm = 0;
-  RS_CHECK_CUDA(cudaGetDevice(&dev));
-  RS_CHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  RS_CHECK_CUDA(cudaFuncSetAttribute(rec_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-  RS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rec_tc_fwd_kernel, NTHREADS, g.smem_bytes));
-  RS_REQUIRE(per_sm * nsm >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_tc_forward: %d CTAs cannot be co-resident", g.nslice);
-  RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned), st));
+  p.kb_bytes = 2u * (uint32_t)g.Bpad * 128;
+  { const char* v = getenv("RS_REC_VARIANT"); p.variant = v ? atoi(v) : 0; }
+  RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
   void* kargs[] = {(void*)&tw_hi, (void*)&tw_lo, (void*)&th_hi, (void*)&th_lo, (void*)&p};
-  RS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)rec_tc_fwd_kernel, dim3(g.nslice), dim3(NTHREADS), kargs,
-                                            g.smem_bytes, st));
-  count_launch();
-  return RS_OK;
+  return coop_launch(rec_tc_fwd_kernel, g.nslice, g.smem_bytes, kargs, st, "lstm_rec_tc_forward");
+}
+
+bool rec_tc_bwd_geometry(int H, int B, RecTcBwdGeom* g) {
+  if (H % 64 != 0 || H < 64 || B < 1 || B > 64) return false;
+  if (H / BW_U > sm_count()) return false;
+  const int Bpad = (B + 15) / 16 * 16;
+  const size_t budget = 227 * 1024 - 2048;
+  const int nkb = 4 * H / 64, ngroups = (nkb + BW_GKB - 1) / BW_GKB;
+  const size_t w_bytes = (size_t)nkb * BW_U * 128;
+  const size_t slot = (size_t)BW_GKB * Bpad * 128;
+  const size_t overhang = 64 * 128 - (size_t)Bpad * 128;      // M = 64 reads 64 rows from each K-block base
+  if (w_bytes + slot + overhang > budget) return false;
+  int slots = (int)((budget - w_bytes - overhang) / slot);
+  if (slots > MAXSLOTS) slots = MAXSLOTS;
+  if (slots > ngroups) slots = ngroups;
+  g->H = H; g->B = B; g->Bpad = Bpad; g->nslice = H / BW_U; g->stages = slots;
+  g->smem_bytes = w_bytes + (size_t)slots * slot + overhang + 1024;
+  return true;
+}
+
+int lstm_rec_tc_backward(const RecTcBwdGeom& g, const RecTcBwdArgs& a, cudaStream_t st) {
+  RS_REQUIRE(a.T > 0, RS_ERR_INVALID, "lstm_rec_tc_backward: T=%d", a.T);
+  CUtensorMap tw, tg;
+  int rc;
+  if ((rc = tmap_2d_bf16(&tw, a.wh_hi, g.H, 4 * g.H, 4 * g.H, BW_U)) != RS_OK) return rc;
+  if ((rc = tmap_2d_bf16(&tg, a.dg_hi, a.T * g.B, 4 * g.H, 4 * g.H, g.Bpad)) != RS_OK) return rc;
+  KBwdArgs p;
+  p.a = a;
+  p.H = g.H; p.B = g.B; p.Bpad = g.Bpad; p.slots = g.stages; p.nkb = 4 * g.H / 64;
+  p.ngroups = (p.nkb + BW_GKB - 1) / BW_GKB;
+  p.kb_bytes = (uint32_t)g.Bpad * 128;
+  { const char* v = getenv("RS_REC_VARIANT"); p.variant = v ? atoi(v) : 0; }
+  RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
+  void* kargs[] = {(void*)&tw, (void*)&tg, (void*)&p};
+  return coop_launch(rec_tc_bwd_kernel, g.nslice, g.smem_bytes, kargs, st, "lstm_rec_tc_backward");
 }
 
 }  // namespace rs

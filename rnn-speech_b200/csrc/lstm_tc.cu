@@ -65,7 +65,7 @@ void carve(const rs_am* am, void* reserve, void* ws, bool training, TcBufs* b, s
   const size_t TB = (size_t)T * B, TBp = (size_t)up8((int)TB);
   const int Fp = up8(F), Cp = up8(C);
   Bump w(ws);
-  b->barrier = w.take<unsigned>(64);
+  b->barrier = w.take<unsigned>(256);
   b->gx = w.take<float>((size_t)T * 4 * H * am->tc.Bpad);
   for (int l = 0; l < L; ++l) {
     b->wx_hi[l] = w.take<bf16>((size_t)4 * H * H); b->wx_lo[l] = w.take<bf16>((size_t)4 * H * H);

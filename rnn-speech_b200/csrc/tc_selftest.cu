@@ -102,3 +102,82 @@ extern "C" int rs_tc_selftest(const float* A_d, const float* B_d, float* D_d, in
   RS_CHECK_LAUNCH();
   return RS_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Issue-rate microbenchmark: one CTA issues `count` tcgen05.mma (kind::f16, SS) of shape
+// M x N x 16 over `ntiles` distinct resident A/B K-slices and `nacc` accumulators, and
+// reports the elapsed SM cycles from first issue to completion (mbarrier commit).
+// Used to size the recurrent kernels (DESIGN.md "Recurrent step budget").
+// ---------------------------------------------------------------------------------------
+namespace rs {
+namespace {
+template <int M, int N, int NACC, bool WARP>
+__device__ __forceinline__ void mma_bench_body(uint32_t tmem, uint32_t sa, uint32_t sb, int count, uint64_t* bar,
+                                               long long* out_cycles) {
+  // 8 resident K-slices (2 K-blocks x 4), descriptors precomputed; `count` multiple of 8
+  const uint32_t idesc = tc::instr_desc_bf16(M, N);
+  uint64_t da[8], db[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    da[i] = tc::smem_desc_sw128(sa + (i >> 2) * 128 * 128) + 2 * (i & 3);
+    db[i] = tc::smem_desc_sw128(sb + (i >> 2) * N * 128) + 2 * (i & 3);
+  }
+  const long long t0 = clock64();
+  for (int it = 0; it < count; it += 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t d = tmem + (uint32_t)((i % NACC) * N);
+      if (WARP) tc::mma_bf16_ss_warp(d, da[i], db[i], idesc, (uint32_t)(it > 0 || i >= NACC));
+      else tc::mma_bf16_ss(d, da[i], db[i], idesc, it > 0 || i >= NACC);
+    }
+  }
+  const long long t1 = clock64();
+  if (WARP) tc::mma_commit_warp(bar); else tc::mma_commit(bar);
+  tc::mbar_wait(bar, 0);
+  const long long t2 = clock64();
+  if ((threadIdx.x & 31) == 0) { out_cycles[0] = t1 - t0; out_cycles[1] = t2 - t0; }
+}
+
+__global__ void __launch_bounds__(128, 1)
+tc_mma_bench_kernel(int M, int N, int count, int variant, int nacc, long long* out_cycles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (2 * 128 * 128 + 2 * 256 * 128) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sa = tc::smem_u32(smem), sb = sa + 2 * 128 * 128;
+  const bool wmode = variant == 1;
+  if (warp == 1 && (wmode || (tid & 31) == 0)) {
+#define RS_CASE(MM, NN, AA) \
+    if (M == MM && N == NN && nacc == AA) { \
+      if (wmode) mma_bench_body<MM, NN, AA, true>(tmem, sa, sb, count, &bar, out_cycles); \
+      else mma_bench_body<MM, NN, AA, false>(tmem, sa, sb, count, &bar, out_cycles); }
+    RS_CASE(64, 32, 1) RS_CASE(64, 32, 4) RS_CASE(128, 32, 1) RS_CASE(128, 32, 4)
+    RS_CASE(64, 16, 1) RS_CASE(64, 16, 4) RS_CASE(128, 128, 1) RS_CASE(128, 256, 1) RS_CASE(64, 64, 1) RS_CASE(64, 64, 4)
+#undef RS_CASE
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+}  // namespace
+}  // namespace rs
+
+// out_cycles_d: int64[2] = {issue cycles, issue-to-completion cycles}
+// variant 0: issued by one thread inside a divergent region; 1: converged warp + elect.sync
+extern "C" int rs_tc_mma_bench(int M, int N, int count, int variant, int nacc, void* out_cycles_d, void* stream) {
+  RS_REQUIRE((M == 64 || M == 128) && N >= 16 && N <= 256 && N % 16 == 0 && count > 0 && count % 8 == 0 && nacc > 0 &&
+                 N * nacc <= 256, RS_ERR_INVALID, "rs_tc_mma_bench: bad arguments");
+  size_t smem = 2 * 128 * 128 + 2 * 256 * 128 + 1024;
+  RS_CHECK_CUDA(cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_mma_bench_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(M, N, count, variant, nacc, (long long*)out_cycles_d);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}

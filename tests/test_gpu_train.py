@@ -80,9 +80,10 @@ def test_full_training_step_matches_oracle_pipeline(pkg, cuda):
     upd_want, upd_got = th - theta0, m.params.cpu().numpy() - theta0
     # Adam's first step is lr * sign(g) wherever |g| >> eps: compare where the oracle gradient is not tiny
     # (entries with a near-zero gradient may legitimately take the other sign at fp32 resolution)
-    big = np.abs(g) / max(np.linalg.norm(g), 1.0) > 1e-4
+    # (the tensor-core path carries dh through a bf16 product: more small entries may flip)
+    big = np.abs(g) / max(np.linalg.norm(g), 1.0) > (1e-2 if m.uses_tensor_cores else 1e-4)
     np.testing.assert_allclose(upd_got[big], upd_want[big], atol=3e-6)
-    assert np.mean(np.abs(upd_got - upd_want) > 3e-6) < 1e-3
+    assert np.mean(np.abs(upd_got - upd_want) > 3e-6) < (5e-2 if m.uses_tensor_cores else 1e-3)
     # state reset ratio 1.0 -> zero state after the step (models/AcousticModel.py:681-682)
     assert float(m.rnn_state.abs().max()) == 0.0
 

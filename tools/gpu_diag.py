@@ -155,8 +155,8 @@ def model_diag(which):
         m.create_training_rnn(1.0, 1.0, 1, 3e-4, 0.33)
         m.load_flat_params(flat)
         m.enable_timing()
-        dbg_f = torch.zeros((T, 8), dtype=torch.int64, device=dev)
-        dbg_b = torch.zeros((T, 8), dtype=torch.int64, device=dev)
+        dbg_f = torch.zeros((T, 16), dtype=torch.int64, device=dev)
+        dbg_b = torch.zeros((T, 16), dtype=torch.int64, device=dev)
         rs._lib.call("rs_am_set_debug_timeline", m._handle, dbg_f.data_ptr(), dbg_b.data_ptr())
         print("cfg2: tensor cores:", m.uses_tensor_cores)
         xd, ld = torch.from_numpy(x).to(dev), torch.from_numpy(lens).to(dev)
@@ -188,9 +188,29 @@ def model_diag(which):
             t0 = d[steps[0], 0]
             print("timeline %s (ns relative to step %d's P0; columns: %s)" % (tag, steps[0], "; ".join(names)))
             for sidx in steps:
-                print("   step %d:" % sidx, " ".join("%7d" % (int(d[sidx, e]) - int(t0)) for e in range(7)))
+                print("   step %d:" % sidx, " ".join("%7d" % (int(d[sidx, e]) - int(t0)) for e in range(7)),
+                      " | signal done %7d, all flags seen %7d" % (int(d[sidx, 7]) - int(t0), int(d[sidx, 15]) - int(t0)))
+                if tag == "fwd":
+                    print("        group waits passed:", " ".join("%7d" % (int(d[sidx, e]) - int(t0)) for e in range(8, 11)),
+                          " group MMAs issued:", " ".join("%7d" % (int(d[sidx, e]) - int(t0)) for e in range(12, 15)))
             per = np.diff(d[100:900, 0].astype(np.int64))
             print("   mean |P0(t+1)-P0(t)| = %.0f ns" % np.abs(per).mean())
+
+
+def mma_bench():
+    out = torch.zeros(2, dtype=torch.int64, device=dev)
+    print("tcgen05.mma SS issue-rate (one CTA): cycles/MMA (issue), cycles/MMA (to completion)")
+    for variant in (0, 1):
+        for (M, N, nacc) in ((64, 32, 1), (64, 32, 4), (128, 32, 1), (128, 32, 4), (64, 16, 1), (64, 16, 4), (64, 64, 1),
+                             (64, 64, 4), (128, 128, 1), (128, 256, 1)):
+            count = 576
+            for rep in range(2):
+                out.zero_()
+                rs._lib.call("rs_tc_mma_bench", M, N, count, variant, nacc, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+            c = out.cpu().numpy()
+            print("   %s M=%3d N=%3d nacc=%d: issue %.1f, complete %.1f cycles/MMA" % (
+                "warp+elect " if variant else "one thread ", M, N, nacc, c[0] / count, c[1] / count))
 
 
 if __name__ == "__main__":
@@ -203,5 +223,7 @@ if __name__ == "__main__":
         tc_diag()
     if "gemm" in which:
         gemm_diag()
+    if "mma" in which:
+        mma_bench()
     if "cfg1" in which or "cfg2" in which:
         model_diag(which)
