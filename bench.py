@@ -275,17 +275,26 @@ def run_b200(args):
     rec_flops_fwd = 2.0 * c["B"] * c["H"] * 4 * c["H"] * T          # h_{t-1} @ Wh over T steps, per launch
     rec_ms = float(np.mean(rec_f + rec_b))
     achieved = rec_flops_fwd / (rec_ms / 1e3) / 1e12
-    roofline = {"kernel": "lstm_rec_fwd_kernel / lstm_rec_bwd_kernel (per-layer persistent recurrent kernels)",
+    tc = bool(m.uses_tensor_cores)
+    roofline = {"kernel": ("rec_tc_fwd_kernel / rec_tc_bwd_kernel (tcgen05 persistent recurrent kernels, one launch "
+                           "per layer per direction)") if tc else "lstm_rec_fwd_kernel / lstm_rec_bwd_kernel (fp32 FFMA)",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / tensor_peak,
+                # dram__bytes_read+write per launch from profiles/r01_ncu_recurrent_kernels.txt (fwd 946 MB, bwd 961 MB)
+                "traffic": 953.0e6 if tc else None, "peak_source": peak_src,
                 "launch_ms": {"fwd": rec_f, "bwd": rec_b}, "share_of_step": (sum(rec_f) + sum(rec_b)) / (ms / args.steps),
-                "note": "algorithmic flops = 2*B*H*4H*T per launch; the recurrence is latency-bound "
-                        "(T sequential steps, grid barrier per step), see DESIGN.md"}
+                "note": "algorithmic flops = 2*B*H*4H*T per launch (150.7 GFLOP at cfg-2; the bf16x3 forward issues 3x "
+                        "that on the tensor pipe); the recurrence is a chain of T dependent steps with a grid-wide "
+                        "exchange of h per step, so it is latency-bound, not tensor-bound: see DESIGN.md 'Recurrent "
+                        "step budget' for the measured per-step timeline"}
     line = {
         "metric": "utterances/sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16x3" if tc else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": c["B"] * world, "parallelism": "dp%d" % world,
+                   "arithmetic": ("bf16 tensor cores with a 3-term hi/lo split (fp32-grade products, fp32 accumulate) "
+                                  "forward and in all batched GEMMs; plain bf16 in the backward dh recurrence; fp64 "
+                                  "feature extraction; fp32 CTC / Adam") if tc else "fp32",
                    "l2": "per-step working set (activations 2.1 GB + 57 MB params x4) exceeds the 126 MB L2; no flush needed",
                    "train_tflop_per_step": train_flops_per_utt(c, T) * c["B"] * world / 1e12},
         "e2e": {"value": e2e, "unit": "utt/s", "ms_per_step": ms_e2e / args.steps,

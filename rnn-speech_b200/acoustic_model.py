@@ -27,6 +27,7 @@ import torch
 from . import _lib
 from . import labels as labelcodec
 from .audioprocessor import AudioProcessor
+from .dist import allreduce_sum_
 
 
 def _stream_ptr():
@@ -361,9 +362,7 @@ class AcousticModel(object):
     def apply_gradients(self):
         """train_step_op (models/AcousticModel.py:404-406): all-reduce (data parallel),
         clip the ACCUMULATED gradient by its global norm, Adam, global_step += 1."""
-        if torch.distributed.is_available() and torch.distributed.is_initialized() \
-                and torch.distributed.get_world_size() > 1:
-            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM)
+        allreduce_sum_(self.grads)
         self.global_step += 1
         _lib.call("rs_sumsq", self.grads.data_ptr(), self.n_params, self._sumsq.data_ptr(), _stream_ptr())
         _lib.call("rs_clip_adam_step", self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
@@ -421,12 +420,7 @@ class AcousticModel(object):
             # Reset the hidden state at the given random ratio (default to always)   (:681-682)
             if randint(1, int(1 // rnn_state_reset_ratio)) == 1:
                 self.rnn_state.zero_()
-        acc = self._acc.cpu().numpy()
-        if torch.distributed.is_available() and torch.distributed.is_initialized() \
-                and torch.distributed.get_world_size() > 1:
-            t = self._acc.clone()
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
-            acc = t.cpu().numpy()
+        acc = allreduce_sum_(self._acc.clone()).cpu().numpy()
         batchs_count = acc[2]
         mean_loss = acc[0] / batchs_count
         mean_error_rate = acc[1] / batchs_count
