@@ -314,6 +314,7 @@ int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int pr
   p.out = out;
   const int ntiles = p.tiles_m * p.tiles_n;
   int grid = sm_count();
+  if (out.max_ctas > 0 && grid > out.max_ctas) grid = out.max_ctas;
   if (grid > ntiles) grid = ntiles;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
   RS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

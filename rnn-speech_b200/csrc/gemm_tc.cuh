@@ -29,6 +29,7 @@ struct GemmTcOut {
   // GEMM_OUT_REC: row m = t*B + b, col n = g*H + unit ->
   //   ((t*nslice + unit/U)*(4U) + (unit%U)*4 + g) * Bpad + b
   int recB, recBpad, recH, recU;
+  int max_ctas;            // 0 = one CTA per SM; otherwise cap the persistent grid (side-stream GEMMs)
 };
 
 // C[M,N] = A[M,K] * B[N,K]^T, both operands K-major (row-major with K contiguous).

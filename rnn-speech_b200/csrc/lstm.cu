@@ -95,6 +95,7 @@ extern "C" int rs_am_create(rs_am** out, int num_layers, int hidden_size, int in
   am->n_params = off;
   am->timing = 0;
   am->dbg_fwd = am->dbg_bwd = nullptr;
+  am->side_ready = 0;
   // tensor-core path when the shape fits it (RS_DISABLE_TC=1 forces the FFMA kernels)
   {
     RecTcBwdGeom bg;
@@ -113,6 +114,11 @@ extern "C" void rs_am_destroy(rs_am* am) {
   if (am->timing)
     for (int d = 0; d < 2; ++d)
       for (int l = 0; l < am->L; ++l) { cudaEventDestroy(am->ev[d][l][0]); cudaEventDestroy(am->ev[d][l][1]); }
+  if (am->side_ready) {
+    for (int l = 0; l < am->L; ++l) { cudaEventDestroy(am->ev_rec[l]); cudaEventDestroy(am->ev_side[l]); }
+    cudaEventDestroy(am->ev_fork);
+    cudaStreamDestroy(am->side);
+  }
   delete am;
 }
 

@@ -14,6 +14,10 @@ struct rs_am {
   int ev_valid[2][64];
   // tensor-core path (H % 64 == 0, B <= 64, weights fit in shared memory); else FFMA kernels
   int use_tc;
+  // side stream for the weight-gradient work that overlaps the next layer's recurrence
+  cudaStream_t side;
+  cudaEvent_t ev_rec[64], ev_side[64], ev_fork;
+  int side_ready;
   unsigned long long* dbg_fwd;   // optional device buffers [T][8] for kernel timelines (layer 0)
   unsigned long long* dbg_bwd;
   rs::RecTcGeom tc;

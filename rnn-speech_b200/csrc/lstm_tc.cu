@@ -43,7 +43,7 @@ struct TcBufs {
   bf16 *wxs_hi[64], *wxs_lo[64];  // K[:H] as stored [H][4H]
   bf16 *whs_hi[64];               // K[H:] as stored [H][4H] (hi)
   bf16 *wos_hi, *wos_lo;          // w_o as stored [H][Cp]
-  bf16 *dg_hi, *dg_lo;            // [T*B][4H]
+  bf16 *dg_hi[2], *dg_lo[2];      // [T*B][4H], ping-pong over layers (the side stream still reads layer l's)
   bf16 *dgT_hi, *dgT_lo;          // [4H][TBp]
   bf16 *actT_hi, *actT_lo;        // [H][TBp] transposed activations
   bf16 *dl_hi, *dl_lo;            // dlogits planes [T*B][Cp]
@@ -76,7 +76,7 @@ void carve(const rs_am* am, void* reserve, void* ws, bool training, TcBufs* b, s
   b->wi_hi = w.take<bf16>((size_t)H * Fp); b->wi_lo = w.take<bf16>((size_t)H * Fp);
   b->wo_hi = w.take<bf16>((size_t)C * H); b->wo_lo = w.take<bf16>((size_t)C * H);
   b->wos_hi = w.take<bf16>((size_t)H * Cp); b->wos_lo = w.take<bf16>((size_t)H * Cp);
-  b->dg_hi = w.take<bf16>(TB * 4 * H); b->dg_lo = w.take<bf16>(TB * 4 * H);
+  for (int i = 0; i < 2; ++i) { b->dg_hi[i] = w.take<bf16>(TB * 4 * H); b->dg_lo[i] = w.take<bf16>(TB * 4 * H); }
   b->dgT_hi = w.take<bf16>((size_t)4 * H * TBp); b->dgT_lo = w.take<bf16>((size_t)4 * H * TBp);
   b->actT_hi = w.take<bf16>((size_t)H * TBp); b->actT_lo = w.take<bf16>((size_t)H * TBp);
   b->dl_hi = w.take<bf16>(TB * Cp); b->dl_lo = w.take<bf16>(TB * Cp);
@@ -307,6 +307,21 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     o.mode = GEMM_OUT_F32; o.C = bf.dcur; o.ldc = H;
     RC(gemm_tc_nt(A, Bm, TB, H, C, 3, o, st));
   }
+  // Weight-gradient work (transposes, dK GEMMs, bias sums) is off the critical path: it runs on
+  // a side stream, on the SMs the 48-CTA recurrent kernel of the next layer leaves idle.
+  if (!am->side_ready) {
+    RS_CHECK_CUDA(cudaStreamCreateWithFlags(&am->side, cudaStreamNonBlocking));
+    for (int l = 0; l < L; ++l) {
+      RS_CHECK_CUDA(cudaEventCreateWithFlags(&am->ev_rec[l], cudaEventDisableTiming));
+      RS_CHECK_CUDA(cudaEventCreateWithFlags(&am->ev_side[l], cudaEventDisableTiming));
+    }
+    RS_CHECK_CUDA(cudaEventCreateWithFlags(&am->ev_fork, cudaEventDisableTiming));
+    am->side_ready = 1;
+  }
+  cudaStream_t side = am->side;
+  const int side_ctas = sm_count() - bg.nslice > 16 ? sm_count() - bg.nslice : 16;
+  RS_CHECK_CUDA(cudaEventRecord(am->ev_fork, st));
+  RS_CHECK_CUDA(cudaStreamWaitEvent(side, am->ev_fork, 0));
   for (int l = L - 1; l >= 0; --l) {
     const bool last = l + 1 == L;
     const bool hop_drop = last ? drop_out : (drop_out || drop_in);
@@ -316,44 +331,52 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
                      (!last && drop_in) ? 2 * (l + 1) : -1, keep_in, st));
       dout = bf.dtmp;
     }
+    const int set = l & 1;
+    // this dg set was last read by the side work of layer l+2
+    if (l + 2 < L) RS_CHECK_CUDA(cudaStreamWaitEvent(st, am->ev_side[l + 2], 0));
     RecTcBwdArgs a;
     a.dout = dout; a.gates = bf.gates[l]; a.cs = bf.cs[l];
     a.c0 = bf.state0 + ((size_t)l * 2 + 0) * B * H;
-    a.wh_hi = bf.whs_hi[l]; a.dg_hi = bf.dg_hi; a.dg_lo = bf.dg_lo; a.len = len_d; a.barrier = bf.barrier; a.T = T;
+    a.wh_hi = bf.whs_hi[l]; a.dg_hi = bf.dg_hi[set]; a.dg_lo = bf.dg_lo[set]; a.len = len_d; a.barrier = bf.barrier; a.T = T;
     a.dbg = (l == 0) ? am->dbg_bwd : nullptr;
     if (am->timing) RS_CHECK_CUDA(cudaEventRecord(am->ev[1][l][0], st));
     RC(lstm_rec_tc_backward(bg, a, st));
     if (am->timing) { RS_CHECK_CUDA(cudaEventRecord(am->ev[1][l][1], st)); am->ev_valid[1][l] = 1; }
-    // dK[:H] += xin^T dg ; dK[H:] += hprev^T dg ; db += colsum(dg)
-    RC(transpose_bf16(bf.dg_hi, TB, 4 * H, 4 * H, bf.dgT_hi, TBp, st));
-    RC(transpose_bf16(bf.dg_lo, TB, 4 * H, 4 * H, bf.dgT_lo, TBp, st));
-    SplitMat G{bf.dgT_hi, bf.dgT_lo, 4 * H, TB, TBp};
-    float* gK = grads_d + am->off_kernel[l];
+    RS_CHECK_CUDA(cudaEventRecord(am->ev_rec[l], st));
+    // ---- critical path: dxin = dg @ K[:H]^T feeds the next layer's recurrence
     {
-      RC(transpose_bf16(xin_hi[l], TB, H, H, bf.actT_hi, TBp, st));
-      RC(transpose_bf16(xin_lo[l], TB, H, H, bf.actT_lo, TBp, st));
-      SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp};
-      GemmTcOut o{};
-      o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1;
-      RC(gemm_tc_nt(A, G, H, 4 * H, TB, 3, o, st));
-    }
-    {
-      RC(transpose_bf16(bf.hp_hi[l], TB, H, H, bf.actT_hi, TBp, st));       // slots 0..T-1 = h_{t-1}
-      RC(transpose_bf16(bf.hp_lo[l], TB, H, H, bf.actT_lo, TBp, st));
-      SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp};
-      GemmTcOut o{};
-      o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1;
-      RC(gemm_tc_nt(A, G, H, 4 * H, TB, 3, o, st));
-    }
-    RC(rowsum_planes(bf.dgT_hi, bf.dgT_lo, 4 * H, TB, TBp, grads_d + am->off_bias[l], 1, st));
-    // dxin = dg @ K[:H]^T
-    {
-      SplitMat A{bf.dg_hi, bf.dg_lo, TB, 4 * H, 4 * H}, Bm{bf.wxs_hi[l], bf.wxs_lo[l], H, 4 * H, 4 * H};
+      SplitMat A{bf.dg_hi[set], bf.dg_lo[set], TB, 4 * H, 4 * H}, Bm{bf.wxs_hi[l], bf.wxs_lo[l], H, 4 * H, 4 * H};
       GemmTcOut o{};
       o.mode = GEMM_OUT_F32; o.C = bf.dcur; o.ldc = H;
       RC(gemm_tc_nt(A, Bm, TB, H, 4 * H, 3, o, st));
     }
+    // ---- side stream: dK[:H] += xin^T dg ; dK[H:] += hprev^T dg ; db += colsum(dg)
+    RS_CHECK_CUDA(cudaStreamWaitEvent(side, am->ev_rec[l], 0));
+    RC(transpose_bf16(bf.dg_hi[set], TB, 4 * H, 4 * H, bf.dgT_hi, TBp, side));
+    RC(transpose_bf16(bf.dg_lo[set], TB, 4 * H, 4 * H, bf.dgT_lo, TBp, side));
+    SplitMat G{bf.dgT_hi, bf.dgT_lo, 4 * H, TB, TBp};
+    float* gK = grads_d + am->off_kernel[l];
+    {
+      RC(transpose_bf16(xin_hi[l], TB, H, H, bf.actT_hi, TBp, side));
+      RC(transpose_bf16(xin_lo[l], TB, H, H, bf.actT_lo, TBp, side));
+      SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp};
+      GemmTcOut o{};
+      o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = side_ctas;
+      RC(gemm_tc_nt(A, G, H, 4 * H, TB, 3, o, side));
+    }
+    {
+      RC(transpose_bf16(bf.hp_hi[l], TB, H, H, bf.actT_hi, TBp, side));       // slots 0..T-1 = h_{t-1}
+      RC(transpose_bf16(bf.hp_lo[l], TB, H, H, bf.actT_lo, TBp, side));
+      SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp};
+      GemmTcOut o{};
+      o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = side_ctas;
+      RC(gemm_tc_nt(A, G, H, 4 * H, TB, 3, o, side));
+    }
+    RC(rowsum_planes(bf.dgT_hi, bf.dgT_lo, 4 * H, TB, TBp, grads_d + am->off_bias[l], 1, side));
+    RS_CHECK_CUDA(cudaEventRecord(am->ev_side[l], side));
   }
+  // join: the input-dense gradient below reuses actT, and the caller's stream owns grads_d afterwards
+  for (int l = 0; l < L && l < 2; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(st, am->ev_side[l], 0));
   // through layer 0's input dropout, then the input dense: dw_i += x^T drnn, db_i += colsum
   const float* drnn = bf.dcur;
   if (drop_in) {

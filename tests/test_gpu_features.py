@@ -82,3 +82,29 @@ def test_fbank_linearity_property(pkg, cuda):
     a, _ = ap.process_batch([sig], 16000)
     b, _ = ap.process_batch([sig * 4.0], 16000)
     np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=2e-4)
+
+
+@pytest.mark.parametrize("sr,lens", [(16000, [16000, 9000]), (22050, [22050])])
+def test_mfcc_matches_oracle(pkg, cuda, sr, lens):
+    """MFCC-20 (librosa.feature.mfcc semantics restated in oracle/features.py; parity unpinned
+    upstream).  fp32 kernels vs the float64 oracle: |diff| <= 2e-3 on coefficients of magnitude
+    up to several hundred (dB-scaled log-mel through an orthonormal DCT)."""
+    rng = np.random.default_rng(sr)
+    sigs = [(0.1 * rng.standard_normal(n)).astype(np.float32) + 0.2 * np.sin(np.arange(n) * 0.05).astype(np.float32)
+            for n in lens]
+    ap = pkg.AudioProcessor(3510, "mfcc", device=cuda)
+    assert ap.feature_size == 20
+    feats, nframes = ap.process_batch(sigs, sr, time_major=False)
+    feats, nframes = feats.cpu().numpy(), nframes.cpu().numpy()
+    for i, s in enumerate(sigs):
+        want, T = features.mfcc(s, sr, 3510)
+        assert nframes[i] == T == 1 + len(s) // features.frame_params(sr)[1]
+        err = np.abs(feats[i, :T] - want).max()
+        print("mfcc sr=%d n=%d: max |diff| %.2e (max |coef| %.1f)" % (sr, len(s), err, np.abs(want).max()))
+        assert err < 2e-3
+        assert np.all(feats[i, T:] == 0)
+    one, length = ap.process_signal(sigs[0], sr)
+    assert one.shape == (length, 20) and length == nframes[0]
+    short = pkg.AudioProcessor(40, "mfcc", device=cuda)
+    f40, l40 = short.process_signal(sigs[0], sr)
+    assert f40.shape == (40, 20) and l40 == nframes[0]          # truncated features, untruncated length
