@@ -188,6 +188,12 @@ int rs_tc_selftest(const float* A_d, const float* B_d, float* D_d, int N, int K,
 /* tcgen05.mma issue-rate microbenchmark (one CTA, SS operands): out_cycles_d int64[2] =
  * {cycles to issue, cycles until the last MMA completed}. */
 int rs_tc_mma_bench(int M, int N, int count, int variant, int nacc, void* out_cycles_d, void* stream);
+/* Self-test of the TMEM-resident A operand ("TS" MMA) with the hi/lo stacking of the recurrent
+ * kernels: A_d [64,K], B_d [32,K] fp32 -> raw accumulator D_d [128 TMEM lanes][64 columns]
+ * (lane 32q+i = A_hi row 16q+i, lane 32q+16+i = A_lo row 16q+i; columns 0..31 = B_hi, 32..63 = B_lo).
+ * K multiple of 64, <= 768.  out_cycles_d int64[2] (or NULL) as in rs_tc_mma_bench, for `reps` passes. */
+int rs_tc_ts_selftest(const float* A_d, const float* B_d, float* D_d, int K, int variant, int reps,
+                      void* out_cycles_d, void* stream);
 /* Test hook for the production tcgen05 GEMM: C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) from fp32
  * inputs (split to bf16 planes inside); products = 1 (plain bf16) or 3 (bf16x3).
  * scratch_d: 2*(M*K + N*K)*2 + 64 bytes.  K multiple of 8. */

@@ -295,6 +295,58 @@ int tmap_2d_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols, int
   return make_tmap(reinterpret_cast<CUtensorMap*>(map64), base, rows, cols, ld, box_rows);
 }
 
+// Plain (unswizzled) 2-D map for TMA stores of a [box_rows x box_cols] shared-memory tile.
+int tmap_store_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols, int ld, int box_rows, int box_cols) {
+  EncodeTiledFn fn = encode_fn();
+  RS_REQUIRE(fn != nullptr, RS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  RS_REQUIRE((ld % 8) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (box_cols % 8) == 0, RS_ERR_INVALID,
+             "TMA store map needs ld %% 8 == 0, box_cols %% 8 == 0 and a 16-byte aligned base");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map64), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base),
+                  gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RS_REQUIRE(r == CUDA_SUCCESS, RS_ERR_CUDA, "cuTensorMapEncodeTiled (store) failed with %d", (int)r);
+  return RS_OK;
+}
+
+// Plain 3-D store map: dims {d0, d1, d2} elements with byte strides {2, s1, s2}; box {b0, b1, b2}.
+int tmap_store3_bf16(void* map64, const __nv_bfloat16* base, int d0, int d1, int d2, size_t s1_bytes, size_t s2_bytes,
+                     int b0, int b1, int b2) {
+  EncodeTiledFn fn = encode_fn();
+  RS_REQUIRE(fn != nullptr, RS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t gstr[2] = {(cuuint64_t)s1_bytes, (cuuint64_t)s2_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map64), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(base),
+                  gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RS_REQUIRE(r == CUDA_SUCCESS, RS_ERR_CUDA, "cuTensorMapEncodeTiled (store3) failed with %d", (int)r);
+  return RS_OK;
+}
+
+// 4-D map over a row-interleaved plane pair [rows][2][cols] bf16 (hi | lo per row): one box
+// {64 k, box_rows, 2 planes, box_kb K-blocks} lands as box_kb stacked SWIZZLE_128B operand tiles
+// [kb][plane][box_rows][64] -- the stacked (hi rows; lo rows) B operand of the TMEM-resident kernels.
+int tmap_stacked_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols, int box_rows, int box_kb) {
+  EncodeTiledFn fn = encode_fn();
+  RS_REQUIRE(fn != nullptr, RS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  RS_REQUIRE((cols % 64) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, RS_ERR_INVALID,
+             "stacked TMA map needs cols %% 64 == 0 and a 16-byte aligned base");
+  cuuint64_t gdim[4] = {64, (cuuint64_t)rows, 2, (cuuint64_t)(cols / 64)};
+  cuuint64_t gstr[3] = {(cuuint64_t)cols * 2 * 2, (cuuint64_t)cols * 2, 128};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 2, (cuuint32_t)box_kb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map64), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base),
+                  gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RS_REQUIRE(r == CUDA_SUCCESS, RS_ERR_CUDA, "cuTensorMapEncodeTiled (stacked) failed with %d (rows=%d cols=%d)", (int)r, rows, cols);
+  return RS_OK;
+}
+
 int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
                cudaStream_t st) {
   if (M <= 0 || N <= 0) return RS_OK;

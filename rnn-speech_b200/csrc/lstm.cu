@@ -100,8 +100,11 @@ extern "C" int rs_am_create(rs_am** out, int num_layers, int hidden_size, int in
   {
     RecTcBwdGeom bg;
     const char* off = getenv("RS_DISABLE_TC");
-    am->use_tc = !(off && off[0] == '1') && rec_tc_geometry(hidden_size, batch_size, &am->tc) &&
-                 rec_tc_bwd_geometry(hidden_size, batch_size, &bg);
+    const bool allow = !(off && off[0] == '1');
+    // first choice: weights resident in tensor memory (lstm_rec_ts.cu); else in shared memory
+    am->use_tc = allow && (rec_ts_geometry(hidden_size, batch_size, &am->tc) ||
+                           (rec_tc_geometry(hidden_size, batch_size, &am->tc) &&
+                            rec_tc_bwd_geometry(hidden_size, batch_size, &bg)));
   }
   for (int d = 0; d < 2; ++d)
     for (int l = 0; l < 64; ++l) am->ev_valid[d][l] = 0;

@@ -636,6 +636,7 @@ bool rec_tc_geometry(int H, int B, RecTcGeom* g) {
     if (score > best + 1e-9) {
       best = score; found = true;
       g->H = H; g->B = B; g->Bpad = Bpad; g->U = U; g->nslice = H / U; g->stages = slots;
+      g->ts = 0; g->nkb_t = 0; g->ngl = 0; g->gkb = 0;
       g->smem_bytes = a_bytes + (size_t)slots * slot + 1024;
     }
   }

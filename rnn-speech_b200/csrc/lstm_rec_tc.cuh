@@ -14,6 +14,11 @@ struct RecTcGeom {
   int H, B, Bpad, U, nslice;      // Bpad = B rounded up to 16 (<= 64); nslice = H / U CTAs
   int stages;                     // h ring depth
   size_t smem_bytes;
+  // TMEM-resident variant (lstm_rec_ts.cu): U = 16, weights in tensor memory
+  int ts;                         // 1: use lstm_rec_ts_forward / _backward (and the blob reserve layout)
+  int nkb_t;                      // forward K-blocks resident in TMEM (the rest in shared memory)
+  int gkb;                        // forward K-blocks per TMA box
+  int ngl;                        // 16-column groups per epilogue thread
 };
 
 // false if the shape is outside the tensor-core path (caller falls back to the FFMA kernels)
@@ -23,8 +28,9 @@ struct RecTcFwdArgs {
   const float* gx;                 // rec layout
   const __nv_bfloat16* wrec_hi;    // [4H][H]
   const __nv_bfloat16* wrec_lo;
-  __nv_bfloat16* h_hi;             // [(T+1)*B][H]
-  __nv_bfloat16* h_lo;
+  __nv_bfloat16* h_hi;             // [(T+1)*B] rows of h_ld elements (h_ld = H, or 2H for the row-interleaved
+  __nv_bfloat16* h_lo;             //  [rows][hi | lo] layout of the TMEM-resident kernels, h_lo = h_hi + H)
+  int h_ld;
   const int* len;                  // [B]
   const float* c0;                 // [B,H] fp32
   float* cT;                       // [B,H] or nullptr
@@ -63,10 +69,22 @@ struct RecTcBwdArgs {
 };
 int lstm_rec_tc_backward(const RecTcBwdGeom& g, const RecTcBwdArgs& a, cudaStream_t st);
 
+// TMEM-resident kernels (lstm_rec_ts.cu).  Same argument structs; `gates` is the private reserve
+// blob of rec_ts_blob_floats() floats (forward writes, backward reads), `cs` is unused.
+// Geometry: H % 128 == 0, B <= 64; false -> use the shared-memory-resident kernels above.
+bool rec_ts_geometry(int H, int B, RecTcGeom* g);
+size_t rec_ts_blob_floats(const RecTcGeom& g, int T);
+int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a, cudaStream_t st);
+int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a, cudaStream_t st);
+
 // Wh (rows H..2H-1 of the TF kernel [2H,4H]) -> wrec planes
 int pack_wrec(const float* kernel, int H, int U, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 
 // defined in gemm_tc.cu
 int tmap_2d_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols, int ld, int box_rows);
+int tmap_store_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols, int ld, int box_rows, int box_cols);
+int tmap_store3_bf16(void* map64, const __nv_bfloat16* base, int d0, int d1, int d2, size_t s1_bytes, size_t s2_bytes,
+                     int b0, int b1, int b2);
+int tmap_stacked_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols, int box_rows, int box_kb);
 
 }  // namespace rs

@@ -1,0 +1,781 @@
+// Recurrent LSTM kernels with the recurrent weights resident in TENSOR MEMORY (sm_100a).
+//
+// Same contract as lstm_rec_tc.cu (tf.nn.dynamic_rnn over BasicLSTMCell and its BPTT,
+// /root/reference/models/AcousticModel.py:227-237, :277-278; oracle/model.py), different
+// machine mapping.  In lstm_rec_tc.cu the weights are the shared-memory operand of every
+// tcgen05.mma, and re-reading them from shared memory each step is what bounds the step
+// (one M64 N32 K16 MMA costs ~25 cycles of operand traffic, 144 of them per step).  Here the
+// weights are the A operand in TMEM, written once per launch with tcgen05.st:
+//
+// Forward.  CTA j owns hidden units [16j, 16j+16) = 64 gate rows (row m = 4*unit + gate).  TMEM
+// lane 32q+i (i < 16) holds W_hi row 16q+i, lane 32q+16+i holds W_lo of the same row; K runs
+// along the columns (two bf16 per 32-bit column).  h_{t-1} arrives by TMA as ONE stacked B
+// tile per K-block: rows 0..Bpad-1 = h_hi, rows Bpad..2Bpad-1 = h_lo (N = 2 Bpad).  One M128
+// MMA per 16 K-elements then yields all four partial products; the epilogue adds
+// hi*hi + hi*lo (same lane, two column ranges) + lo*hi (lane + 16, one shuffle) -- the
+// bf16x3 product of tc_common.cuh -- in 48 MMAs of ~33 cycles instead of 144 of ~25.
+// K-blocks that do not fit in the 512 TMEM columns (H > 896) stay in shared memory as an
+// ordinary SS operand with the same row stacking.
+//
+// Backward.  dh_{t-1}^T[k, b] = sum_n Wh[k, n] dgates_t[b, n]: M = 128 hidden units k per
+// CLUSTER of 8 CTAs, K = 4H split 8 ways over the cluster (CTA s holds Wh[128 rows, its H/2
+// columns] in TMEM: 24 MMAs of M128 N=Bpad at H = 768 instead of 192).  The eight partial
+// accumulators are reduce-scattered through distributed shared memory with st.async
+// (complete_tx on the owner's mbarrier): CTA s of the cluster ends up with the 16 units
+// [128i+16s, +16) and does their cell backward.  Each CTA streams only its K-segment of
+// dgates_t (24 KB instead of 196 KB).
+//
+// Both kernels publish their per-step result (h_t planes / dgates_t planes) through a shared
+// memory staging tile and 16-byte coalesced global stores, then signal the grid barrier.
+// The values forward saves for backward live in a private "blob" whose layout is the thread
+// layout of the two epilogues (both own the same cells), so every access is a coalesced float4.
+#include "lstm_rec_tc.cuh"
+#include "tc_common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace rs {
+namespace {
+
+constexpr int NTHREADS = 320;   // warps 0-7: epilogue (sub-partition w%4, column half w/4); 8: TMA; 9: MMA
+constexpr int MAXG = 2;         // 16-column groups per epilogue thread (Bpad <= 64)
+constexpr int MAXSLOTS = 16;
+constexpr int GKB = 4;          // K-blocks per mbarrier (forward)
+constexpr int TSU = 16;         // hidden units per CTA
+constexpr int BLOB_ITEMS = 5;   // i, j, f, o, c_t
+constexpr int CL = 8;           // backward cluster size (K split)
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// timeline stamps of CTA 0 (rows [0,T)) and of the last CTA (rows [T,2T)); 16 events per step
+#define RS_STAMP(dbgp, step, ev) do { if ((dbgp) && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) \
+    (dbgp)[((size_t)(blockIdx.x ? a.T : 0) + (size_t)(step)) * 16 + (ev)] = gtime(); } while (0)
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// grid barrier wait.  variant bit1: relaxed polls + one acquire fence instead of acquire polls
+__device__ __forceinline__ void red_relaxed_add(unsigned* p, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// variant bit2: relaxed polls and NO acquire fence (the data is only read through TMA, which is
+// issued after -- control-dependent on -- the poll that saw the count)
+__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target, int variant) {
+  if (variant & 4) {
+    while (ld_relaxed_u32(ctr) < target) {}
+  } else if (variant & 2) {
+    while (ld_relaxed_u32(ctr) < target) {}
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  } else {
+    while (ld_acquire_u32(ctr) < target) {}
+  }
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ float pick4(int sel, float a0, float a1, float a2, float a3) {
+  const float lo = (sel & 1) ? a1 : a0;
+  const float hi = (sel & 1) ? a3 : a2;
+  return (sel & 2) ? hi : lo;
+}
+
+// ---- cluster / distributed shared memory ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 16-byte store into a peer CTA's shared memory; completes 16 tx bytes on the peer's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                 "r"(__float_as_uint(v.w)), "r"(remote_mbar)
+               : "memory");
+}
+
+struct KFwd {
+  RecTcFwdArgs a;
+  int H, B, Bpad, nslice, slots, nkb, nkb_t, ngroups, ngl, gkb;
+  int variant;                  // RS_TS_VARIANT switches, see ts_variant()
+  uint32_t kb_bytes;            // one streamed K-block: 2 planes x Bpad rows x 128 B
+};
+
+// blob float2 index of (step t, slice j, group gl, item, warp, lane)
+__device__ __forceinline__ size_t blob_idx(int t, int nslice, int j, int ngl, int gl, int item, int warp, int lane) {
+  return ((((((size_t)t * nslice + j) * ngl + gl) * BLOB_ITEMS + item) * 8 + warp) * 32 + lane);
+}
+
+// Epilogue thread layout shared by forward and backward (8 warps): q = warp & 3 is the TMEM
+// sub-partition, hf = warp >> 2 picks the 16-column (batch) groups gi = hf, hf + 2.  Lane:
+// l16 = lane & 15 -> gate row m = 16q + l16 (unit ul = m >> 2 of the slice, gate g = lane & 3);
+// up = lane >> 4 -> columns [8 up, 8 up + 8) of the group.  After the quad exchange the lane owns
+// the two cells (unit ul, batch b = 16 gi + 8 up + 2 g + k), k = 0, 1.
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmS, KFwd p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[MAXSLOTS], empty_bar[MAXSLOTS], tfull_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(128) __nv_bfloat16 sH[64][2][TSU];          // staged h_t [b][plane][unit]
+  const RecTcFwdArgs& a = p.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x;
+  const int H = p.H, B = p.B, Bpad = p.Bpad, T = a.T, nkb = p.nkb, nkb_t = p.nkb_t, ngroups = p.ngroups, gkb = p.gkb;
+  const int nkb_s = nkb - nkb_t;
+  unsigned char* sA = smem;                                         // [nkb_s][128 rows x 128 B] resident SS K-blocks
+  unsigned char* sRing = smem + (size_t)nkb_s * 16384;              // [slots][gkb][2 planes][Bpad*128]
+  const uint32_t slot_bytes = (uint32_t)gkb * p.kb_bytes;
+  const bool full_flight = p.slots >= ngroups;
+  const uint32_t colD = (uint32_t)nkb_t * 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.slots; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(&tfull_bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    // ---- resident weights: TMEM lane = threadIdx.x; gate row 16q + (lane & 15), hi plane for lane < 16
+    const int row = j * 64 + 16 * warp + (lane & 15);
+    const __nv_bfloat16* src = ((lane < 16) ? a.wrec_hi : a.wrec_lo) + (size_t)row * H;
+    for (int c0 = 0; c0 < nkb_t * 32; c0 += 8) {
+      const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0));
+      const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0 + 8));
+      const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      tc::tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+    }
+    for (int kb = nkb_t; kb < nkb; ++kb) {
+      unsigned char* tile = sA + (size_t)(kb - nkb_t) * 16384 + (size_t)threadIdx.x * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(tile + ((c ^ (threadIdx.x & 7)) << 4)) = __ldg(reinterpret_cast<const uint4*>(src + kb * 64 + c * 8));
+    }
+    tc::tmem_st_wait();
+    tc::fence_proxy_async_smem();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) tc::tma_prefetch_desc(&tmH);
+    __syncwarp();
+    const unsigned per_step = gridDim.x * (unsigned)(Bpad / 8);
+    uint32_t git = 0;
+    for (int t = 0; t < T; ++t) {
+      if (t > 0) {
+        wait_counter(a.barrier, per_step * (unsigned)t, p.variant);
+        __syncwarp();
+        if (!(p.variant & 8)) tc::fence_proxy_async_all();     // other CTAs' generic-proxy stores of h_{t-1} -> TMA reads
+      }
+      if (lane == 0) RS_STAMP(a.dbg, t, 0);
+      __syncwarp();
+      for (int grp = 0; grp < ngroups; ++grp, ++git) {
+        const int s = git % p.slots;
+        const uint32_t ph = (git / p.slots) & 1;
+        if (!full_flight) tc::mbar_wait(&empty_bar[s], ph ^ 1);
+        tc::mbar_arrive_expect_tx_warp(&full_bar[s], slot_bytes);
+        // one box = gkb stacked tiles [kb][plane][Bpad rows][64]; row t*B = slot t = h_{t-1}
+        tc::tma_load_4d_warp(sRing + (size_t)s * slot_bytes, &tmH, 0, t * B, 0, grp * gkb, &full_bar[s]);
+      }
+      if (lane == 0) RS_STAMP(a.dbg, t, 1);
+      __syncwarp();
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp)
+    const uint32_t idesc = tc::instr_desc_bf16(128, 2 * Bpad);
+    const uint64_t dA0 = tc::smem_desc_sw128(tc::smem_u32(sA));
+    const uint64_t dring0 = tc::smem_desc_sw128(tc::smem_u32(sRing));
+    const uint64_t kb_u = p.kb_bytes >> 4;
+    const uint32_t tmemD = tmem + colD;
+    uint32_t git = 0;
+    for (int t = 0; t < T; ++t) {
+      for (int grp = 0; grp < ngroups; ++grp, ++git) {
+        const int s = git % p.slots;
+        const uint32_t ph = (git / p.slots) & 1;
+        tc::mbar_wait(&full_bar[s], ph);
+        tc::tc_fence_after();
+        if (lane == 0 && grp == 0) RS_STAMP(a.dbg, t, 2);
+        if (lane == 0 && grp >= 1 && grp <= 3) RS_STAMP(a.dbg, t, 10 + grp);       // 11..13: later groups landed
+        __syncwarp();
+        for (int i = 0; i < gkb; ++i) {
+          const int kb = grp * gkb + i;
+          const uint64_t dh = dring0 + (uint64_t)s * (slot_bytes >> 4) + (uint64_t)i * kb_u;
+          if (kb < nkb_t) tc::mma4_bf16_ts_warp(tmemD, tmem + (uint32_t)(kb * 32), dh, idesc, (uint32_t)(kb != 0));
+          else tc::mma4_bf16_ss_warp(tmemD, dA0 + (uint64_t)(kb - nkb_t) * (16384 >> 4), dh, idesc, (uint32_t)(kb != 0));
+        }
+        if (lane == 0 && grp == 0) RS_STAMP(a.dbg, t, 14);                          // group 0 MMAs issued
+        __syncwarp();
+        if (!full_flight) tc::mma_commit_warp(&empty_bar[s]);
+      }
+      tc::mma_commit_warp(&tfull_bar);
+      if (lane == 0) RS_STAMP(a.dbg, t, 3);
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3, hf = warp >> 2, l16 = lane & 15, up = lane >> 4;
+    const int m = q * 16 + l16;                 // gate row (hi copy in lanes 0..15, lo copy in 16..31)
+    const int g = lane & 3;                     // gate of this row: 0 i, 1 j, 2 f, 3 o
+    const int ul = m >> 2;                      // unit inside the slice
+    const int unit = j * TSU + ul;
+    const int ng = Bpad / 16;
+    const uint32_t tmemD = tmem + colD + ((uint32_t)(q * 32) << 16);
+    float c[MAXG][2], hl[MAXG][2];
+    int lenr[MAXG][2];
+#pragma unroll
+    for (int gl = 0; gl < MAXG; ++gl)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int b = (hf + 2 * gl) * 16 + 8 * up + 2 * g + k;
+        const bool ok = (hf + 2 * gl) < ng && b < B;
+        c[gl][k] = ok ? a.c0[(size_t)b * H + unit] : 0.f;
+        hl[gl][k] = ok ? a.h0[(size_t)b * H + unit] : 0.f;
+        lenr[gl][k] = ok ? a.len[b] : 0;
+      }
+    const float fbias = (g == 2) ? 1.0f : 0.0f;          // forget_bias
+    const float pre = (g == 1) ? 2.0f : 1.0f;            // tanh(x) = 2*sigmoid(2x) - 1
+    const float post_m = (g == 1) ? 2.0f : 1.0f, post_a = (g == 1) ? -1.0f : 0.0f;
+    float2* blob = reinterpret_cast<float2*>(a.gates);
+    const unsigned nstore = (unsigned)(4 * Bpad);         // 16-byte chunks of the staged h tile
+
+    for (int t = 0; t < T; ++t) {
+      // hoisted input projection for this step (independent of the recurrence: issue early)
+      float4 gxv[MAXG][2];
+#pragma unroll
+      for (int gl = 0; gl < MAXG; ++gl) {
+        const int gi = hf + 2 * gl;
+        if (gi < ng) {
+          const float4* gp = reinterpret_cast<const float4*>(
+              a.gx + (((size_t)t * p.nslice + j) * 64 + m) * Bpad + gi * 16 + 8 * up);
+          gxv[gl][0] = __ldg(gp);
+          gxv[gl][1] = __ldg(gp + 1);
+        } else {
+          gxv[gl][0] = gxv[gl][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      float2 keep[MAXG][BLOB_ITEMS];
+      tc::mbar_wait(&tfull_bar, (uint32_t)(t & 1));
+      tc::tc_fence_after();
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 4);
+#pragma unroll
+      for (int gl = 0; gl < MAXG; ++gl) {
+        const int gi = hf + 2 * gl;
+        if (gi < ng) {                           // warp-uniform
+          float v[16], w[16];
+          tc::tmem_ld16(tmemD + (uint32_t)(gi * 16), v);             // hi rows: W_hi h_hi ; lo rows: W_lo h_hi
+          tc::tmem_ld16(tmemD + (uint32_t)(Bpad + gi * 16), w);      // hi rows: W_hi h_lo
+          tc::tmem_ld_wait();
+          // the hi-row lane finishes columns 0..7, its lo-row partner (lane ^ 16) columns 8..15
+          float act[8];
+          const float xs[8] = {gxv[gl][0].x, gxv[gl][0].y, gxv[gl][0].z, gxv[gl][0].w,
+                               gxv[gl][1].x, gxv[gl][1].y, gxv[gl][1].z, gxv[gl][1].w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float s_a = v[i] + w[i], s_b = v[8 + i] + w[8 + i];
+            const float got = __shfl_xor_sync(0xffffffffu, up ? v[i] : s_b, 16);
+            const float z = ((up ? (got + v[8 + i]) : (s_a + got)) + xs[i] + fbias) * pre;
+            act[i] = fmaf(fast_sigmoid(z), post_m, post_a);
+          }
+          // quad exchange: this lane owns columns 2g + k; gate tau comes from lane g ^ (g ^ tau)
+          float own[2], rcv[3][2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) own[k] = pick4(g, act[k], act[2 + k], act[4 + k], act[6 + k]);
+#pragma unroll
+          for (int d = 1; d < 4; ++d)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const float snd = pick4(g ^ d, act[k], act[2 + k], act[4 + k], act[6 + k]);
+              rcv[d - 1][k] = __shfl_xor_sync(0xffffffffu, snd, d);
+            }
+          float gv[4][2], cn[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const float ig = pick4(g ^ 0, own[k], rcv[0][k], rcv[1][k], rcv[2][k]);
+            const float jg = pick4(g ^ 1, own[k], rcv[0][k], rcv[1][k], rcv[2][k]);
+            const float fg = pick4(g ^ 2, own[k], rcv[0][k], rcv[1][k], rcv[2][k]);
+            const float og = pick4(g ^ 3, own[k], rcv[0][k], rcv[1][k], rcv[2][k]);
+            const int b = gi * 16 + 8 * up + 2 * g + k;
+            const float c_new = c[gl][k] * fg + ig * jg;
+            const float h_new = fast_tanh(c_new) * og;
+            const bool valid = t < lenr[gl][k];
+            if (valid) { c[gl][k] = c_new; hl[gl][k] = h_new; }
+            __nv_bfloat16 hh, hlo;
+            tc::split_bf16(valid ? h_new : 0.f, hh, hlo);
+            sH[b][0][ul] = hh;
+            sH[b][1][ul] = hlo;
+            gv[0][k] = ig; gv[1][k] = jg; gv[2][k] = fg; gv[3][k] = og; cn[k] = c_new;
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) keep[gl][it] = make_float2(gv[it][0], gv[it][1]);
+          keep[gl][4] = make_float2(cn[0], cn[1]);
+        }
+      }
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 5);
+      tc::tc_fence_before();
+      if (p.variant & 16) tc::fence_proxy_async_smem();
+      epi_bar_sync();
+      if (p.variant & 16) {
+        // publish h_t (both planes) with one TMA store; the bulk-group wait returns when the writes are performed
+        if (threadIdx.x == 0) {
+          tc::tma_store_3d(&tmS, &sH[0][0][0], j * TSU, 0, (t + 1) * B);
+          tc::bulk_commit();
+          RS_STAMP(a.dbg, t, 9);
+          tc::bulk_wait_all();
+          RS_STAMP(a.dbg, t, 10);
+          if (t + 1 < T) red_relaxed_add(a.barrier, (unsigned)(Bpad / 8));
+        }
+      } else if (threadIdx.x < nstore) {
+        // publish h_t: 16-byte coalesced stores of the staged tile, one release per storing warp
+        const int b = (int)threadIdx.x >> 2, pl = ((int)threadIdx.x >> 1) & 1, half = (int)threadIdx.x & 1;
+        if (b < B) {
+          const uint4 x = *reinterpret_cast<const uint4*>(&sH[b][pl][half * 8]);
+          __nv_bfloat16* dst = (pl ? a.h_lo : a.h_hi) + ((size_t)(t + 1) * B + b) * a.h_ld + j * TSU + half * 8;
+          *reinterpret_cast<uint4*>(dst) = x;
+        }
+        if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 9);
+        if (!(p.variant & 1)) tc::fence_proxy_async_all();
+        __syncwarp();
+        if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 10);
+        if (lane == 0 && t + 1 < T) red_release_add(a.barrier, 1u);
+      }
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 6);
+      // reserve for backward (not on the critical path of the recurrence)
+      if (blob) {
+#pragma unroll
+        for (int gl = 0; gl < MAXG; ++gl) {
+          if (hf + 2 * gl < ng) {
+#pragma unroll
+            for (int it = 0; it < BLOB_ITEMS; ++it) blob[blob_idx(t, p.nslice, j, p.ngl, gl, it, warp, lane)] = keep[gl][it];
+          }
+        }
+      }
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 7);
+      if (threadIdx.x == 0 && a.dbg && blockIdx.x == 0) a.dbg[(size_t)t * 16 + 15] = (unsigned long long)clock64();   // SM clock vs globaltimer
+    }
+#pragma unroll
+    for (int gl = 0; gl < MAXG; ++gl)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int b = (hf + 2 * gl) * 16 + 8 * up + 2 * g + k;
+        if ((hf + 2 * gl) < ng && b < B) {
+          if (a.cT) a.cT[(size_t)b * H + unit] = c[gl][k];
+          if (a.hT) a.hT[(size_t)b * H + unit] = hl[gl][k];
+        }
+      }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------
+// Backward
+// ------------------------------------------------------------------------------------
+struct KBwd {
+  RecTcBwdArgs a;
+  int H, B, Bpad, nslice, nkbs, ngl;       // nkbs = K-blocks of this CTA's K segment (H/2 / 64)
+  int variant;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmS_hi,
+                  const __grid_constant__ CUtensorMap tmS_lo, KBwd p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar, tfull_bar, recv_bar;
+  __shared__ uint32_t tmem_slot;
+  const RecTcBwdArgs& a = p.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = p.H, B = p.B, Bpad = p.Bpad, T = a.T, nkbs = p.nkbs, G = 4 * H;
+  const uint32_t rank = cluster_ctarank();            // K segment / owned unit slice inside the 128-unit block
+  const int blk = blockIdx.x / CL;
+  const int j = blk * CL + (int)rank;                   // 16-unit slice (same numbering as forward)
+  const int kseg0 = (int)rank * (H / 2);                // first dgates column of this CTA's K segment
+  const uint32_t kb_bytes = (uint32_t)Bpad * 128;
+  unsigned char* sG = smem;                                                  // [nkbs][Bpad x 128 B] dgates_t K segment
+  float* sR = reinterpret_cast<float*>(smem + (size_t)nkbs * kb_bytes);      // [CL src][16 units][Bpad] partial dh
+  __nv_bfloat16* sDG = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(sR) + (size_t)CL * TSU * Bpad * 4);
+                                                                             // [2 planes][Bpad][4 gates][16 units]
+  const uint32_t colD = (uint32_t)(H / 4);
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&full_bar, 1);
+    tc::mbar_init(&tfull_bar, 1);
+    tc::mbar_init(&recv_bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&tmem_slot, p.tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp < 4) {
+    // resident Wh[128 rows of the block][K segment]: TMEM lane = threadIdx.x = hidden unit k
+    const __nv_bfloat16* src = a.wh_hi + (size_t)(blk * 128 + (int)threadIdx.x) * G + kseg0;
+    for (int c0 = 0; c0 < H / 4; c0 += 8) {
+      const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0));
+      const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0 + 8));
+      const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      tc::tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+    }
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  cluster_sync_all();                                   // peers' mbarriers are initialised before any st.async
+
+  if (warp == 8) {
+    if (lane == 0) tc::tma_prefetch_desc(&tmG);
+    __syncwarp();
+    const unsigned per_step = gridDim.x * 8u;
+    unsigned epoch = 0;
+    for (int t = T - 1; t >= 1; --t) {        // dh_{t-1} from dgates_t
+      ++epoch;
+      wait_counter(a.barrier, per_step * epoch, p.variant);
+      __syncwarp();
+      if (!(p.variant & 8)) tc::fence_proxy_async_all();
+      if (lane == 0) RS_STAMP(a.dbg, t, 0);
+      __syncwarp();
+      tc::mbar_arrive_expect_tx_warp(&full_bar, (uint32_t)nkbs * kb_bytes);
+      for (int i = 0; i < nkbs; ++i) tc::tma_load_2d_warp(sG + (size_t)i * kb_bytes, &tmG, kseg0 + i * 64, t * B, &full_bar);
+      if (lane == 0) RS_STAMP(a.dbg, t, 1);
+      __syncwarp();
+    }
+  } else if (warp == 9) {
+    const uint32_t idesc = tc::instr_desc_bf16(128, Bpad);
+    const uint64_t dg0 = tc::smem_desc_sw128(tc::smem_u32(sG));
+    const uint32_t tmemD = tmem + colD;
+    uint32_t n = 0;
+    for (int t = T - 1; t >= 1; --t, ++n) {
+      tc::mbar_wait(&full_bar, n & 1);
+      tc::tc_fence_after();
+      if (lane == 0) RS_STAMP(a.dbg, t, 2);
+      __syncwarp();
+      for (int i = 0; i < nkbs; ++i)
+        tc::mma4_bf16_ts_warp(tmemD, tmem + (uint32_t)(i * 32), dg0 + (uint64_t)i * (kb_bytes >> 4), idesc, (uint32_t)(i != 0));
+      tc::mma_commit_warp(&tfull_bar);
+      if (lane == 0) RS_STAMP(a.dbg, t, 3);
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3, hf = warp >> 2, l16 = lane & 15, up = lane >> 4;
+    const int g = lane & 3;
+    const int ul = q * 4 + (l16 >> 2);                   // owned unit inside the slice (cell math)
+    const int unit = j * TSU + ul;
+    const int ng = Bpad / 16;
+    const uint32_t tmemD = tmem + colD + ((uint32_t)(q * 32) << 16);
+    // push side: TMEM lane 32q + lane = unit 32q + lane of the block -> owner rank, unit inside its slice
+    const uint32_t owner = (uint32_t)(2 * q + up);
+    const uint32_t sR_local = tc::smem_u32(sR);
+    const uint32_t push_base = mapa_u32(sR_local + (uint32_t)(((int)rank * TSU + l16) * Bpad) * 4u, owner);
+    const uint32_t push_bar = mapa_u32(tc::smem_u32(&recv_bar), owner);
+    const float2* blob = reinterpret_cast<const float2*>(a.gates);
+    int lenr[MAXG][2];
+    float dc[MAXG][2];
+#pragma unroll
+    for (int gl = 0; gl < MAXG; ++gl)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int b = (hf + 2 * gl) * 16 + 8 * up + 2 * g + k;
+        lenr[gl][k] = ((hf + 2 * gl) < ng && b < B) ? a.len[b] : 0;
+        dc[gl][k] = 0.f;
+      }
+    const unsigned nchunk = (unsigned)(2 * Bpad * 4 * 2);     // 16-byte chunks of the staged dgates tile
+    uint32_t n = 0;
+    for (int t = T - 1; t >= 0; --t, ++n) {
+      // operands of the cell backward (independent of the recurrence: issue before waiting)
+      float2 it2[MAXG][BLOB_ITEMS], cp2[MAXG];
+      float dy[MAXG][2];
+#pragma unroll
+      for (int gl = 0; gl < MAXG; ++gl) {
+        const int gi = hf + 2 * gl;
+        if (gi < ng) {
+#pragma unroll
+          for (int it = 0; it < BLOB_ITEMS; ++it) it2[gl][it] = __ldg(blob + blob_idx(t, p.nslice, j, p.ngl, gl, it, warp, lane));
+          if (t > 0) cp2[gl] = __ldg(blob + blob_idx(t - 1, p.nslice, j, p.ngl, gl, 4, warp, lane));
+          float cpv[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int b = gi * 16 + 8 * up + 2 * g + k;
+            dy[gl][k] = (b < B) ? __ldg(a.dout + ((size_t)t * B + b) * H + unit) : 0.f;
+            cpv[k] = (t == 0 && b < B) ? __ldg(a.c0 + (size_t)b * H + unit) : 0.f;
+          }
+          if (t == 0) cp2[gl] = make_float2(cpv[0], cpv[1]);
+        }
+      }
+      float dh[MAXG][2];
+#pragma unroll
+      for (int gl = 0; gl < MAXG; ++gl) dh[gl][0] = dh[gl][1] = 0.f;
+      if (n > 0) {
+        // partial dh_t^T of this CTA's K segment -> reduce-scatter over the cluster
+        if (threadIdx.x == 0) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                       ::"r"(tc::smem_u32(&recv_bar)), "r"((uint32_t)(CL * TSU * Bpad * 4)) : "memory");
+        }
+        tc::mbar_wait(&tfull_bar, (n - 1) & 1);
+        tc::tc_fence_after();
+        if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 4);
+#pragma unroll
+        for (int gl = 0; gl < MAXG; ++gl) {
+          const int gi = hf + 2 * gl;
+          if (gi < ng) {
+            float v[16];
+            tc::tmem_ld16(tmemD + (uint32_t)(gi * 16), v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              st_async_v4(push_base + (uint32_t)(gi * 16 + 4 * i) * 4u, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]),
+                          push_bar);
+          }
+        }
+        tc::tc_fence_before();
+        if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 9);
+        tc::mbar_wait(&recv_bar, (n - 1) & 1);
+        if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 8);
+#pragma unroll
+        for (int gl = 0; gl < MAXG; ++gl) {
+          const int gi = hf + 2 * gl;
+          if (gi < ng) {
+#pragma unroll
+            for (int s = 0; s < CL; ++s) {
+              const float2 x = *reinterpret_cast<const float2*>(sR + ((size_t)s * TSU + ul) * Bpad + gi * 16 + 8 * up + 2 * g);
+              dh[gl][0] += x.x; dh[gl][1] += x.y;
+            }
+          }
+        }
+      }
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 13);
+#pragma unroll
+      for (int gl = 0; gl < MAXG; ++gl) {
+        const int gi = hf + 2 * gl;
+        if (gi < ng) {
+          const float* pi = reinterpret_cast<const float*>(&it2[gl][0]);
+          const float* pj = reinterpret_cast<const float*>(&it2[gl][1]);
+          const float* pf = reinterpret_cast<const float*>(&it2[gl][2]);
+          const float* po = reinterpret_cast<const float*>(&it2[gl][3]);
+          const float* pct = reinterpret_cast<const float*>(&it2[gl][4]);
+          const float* pcp = reinterpret_cast<const float*>(&cp2[gl]);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int b = gi * 16 + 8 * up + 2 * g + k;
+            float di = 0.f, dj = 0.f, df = 0.f, dob = 0.f;
+            if (t < lenr[gl][k]) {
+              const float ig = pi[k], jg = pj[k], fg = pf[k], og = po[k];
+              const float dh_tot = dh[gl][k] + dy[gl][k];
+              const float tch = fast_tanh(pct[k]);
+              dob = dh_tot * tch * og * (1.f - og);
+              const float dc_tot = dc[gl][k] + dh_tot * og * (1.f - tch * tch);
+              di = dc_tot * jg * ig * (1.f - ig);
+              dj = dc_tot * ig * (1.f - jg * jg);
+              df = dc_tot * pcp[k] * fg * (1.f - fg);
+              dc[gl][k] = dc_tot * fg;
+            }
+            const float d4[4] = {di, dj, df, dob};
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) {
+              __nv_bfloat16 h0, l0;
+              tc::split_bf16(d4[gg], h0, l0);
+              sDG[(((size_t)0 * Bpad + b) * 4 + gg) * TSU + ul] = h0;
+              sDG[(((size_t)1 * Bpad + b) * 4 + gg) * TSU + ul] = l0;
+            }
+          }
+        }
+      }
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 5);
+      if (p.variant & 16) tc::fence_proxy_async_smem();
+      epi_bar_sync();
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 10);
+      if (p.variant & 16) {
+        if (threadIdx.x == 0) {
+          tc::tma_store_3d(&tmS_hi, sDG, j * TSU, 0, t * B);
+          tc::tma_store_3d(&tmS_lo, sDG + (size_t)Bpad * 4 * TSU, j * TSU, 0, t * B);
+          tc::bulk_commit();
+          RS_STAMP(a.dbg, t, 11);
+          tc::bulk_wait_all();
+          RS_STAMP(a.dbg, t, 12);
+          if (t > 0) red_relaxed_add(a.barrier, 8u);
+          RS_STAMP(a.dbg, t, 6);
+        }
+        continue;
+      }
+      // publish dgates_t: 16-byte coalesced stores of the staged tile, one release per warp
+      for (unsigned ch = threadIdx.x; ch < nchunk; ch += 256) {
+        const int half = ch & 1, gg = (ch >> 1) & 3, b = (ch >> 3) % Bpad, pl = (ch >> 3) / Bpad;
+        if (b < B) {
+          const uint4 x = *reinterpret_cast<const uint4*>(sDG + (((size_t)pl * Bpad + b) * 4 + gg) * TSU + half * 8);
+          __nv_bfloat16* dst = (pl ? a.dg_lo : a.dg_hi) + ((size_t)t * B + b) * G + (size_t)gg * H + j * TSU + half * 8;
+          *reinterpret_cast<uint4*>(dst) = x;
+        }
+      }
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 11);
+      if (!(p.variant & 1)) tc::fence_proxy_async_all();
+      __syncwarp();
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 12);
+      if (lane == 0 && t > 0) red_release_add(a.barrier, 1u);
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 6);
+      // (the staged tile is rewritten only after the next tfull wait, i.e. after the grid barrier
+      //  that needs all eight releases above, each of which follows its warp's reads of the tile)
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) tc::tmem_dealloc(tmem, p.tmem_cols);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+// RS_TS_VARIANT switches (default 29 = all of them; 0 = the conservative protocol with generic
+// stores, red.release / ld.acquire and proxy fences on both sides -- results are bit-identical,
+// tests/test_gpu_model.py compares the two):
+//   1  no writer-side fence.proxy.async     4  relaxed polling without an acquire fence
+//   8  no reader-side fence.proxy.async    16  publish with TMA stores + bulk-group wait + red.relaxed
+static int ts_variant() {
+  const char* v = getenv("RS_TS_VARIANT");
+  return v ? atoi(v) : 29;
+}
+static bool ts_enabled() {
+  const char* v = getenv("RS_REC_TS");
+  return !(v && v[0] == '0');
+}
+
+bool rec_ts_geometry(int H, int B, RecTcGeom* g) {
+  if (!ts_enabled()) return false;
+  if (H % 128 != 0 || H < 128 || B < 1 || B > 64) return false;
+  if (H / TSU > sm_count()) return false;
+  const int Bpad = (B + 15) / 16 * 16;
+  const int nkb = H / 64;
+  int nkb_t = (512 - 2 * Bpad) / 32;
+  if (nkb_t > nkb) nkb_t = nkb;
+  // K-blocks per TMA box / mbarrier.  Measured (cfg-2): ONE box carrying all of h_{t-1} lands sooner than the
+  // same bytes split over several TMA instructions (they are served one after the other), and the MMAs of an
+  // early group slow the arrival of the later ones; so take the whole of h when it fits.
+  const size_t budget = 227 * 1024 - 8192;
+  const size_t a_bytes = (size_t)(nkb - nkb_t) * 16384;
+  int gkb = nkb;
+  if (a_bytes + (size_t)gkb * 2 * Bpad * 128 > budget || gkb > 256) gkb = (nkb % 4 == 0) ? 4 : (nkb % 3 == 0) ? 3 : 2;
+  { const char* v = getenv("RS_TS_GKB"); if (v && atoi(v) > 0 && nkb % atoi(v) == 0) gkb = atoi(v); }
+  const int ngroups = nkb / gkb;
+  const size_t slot = (size_t)gkb * 2 * Bpad * 128;
+  if (a_bytes + slot > budget) return false;
+  int slots = (int)((budget - a_bytes) / slot);
+  if (slots > MAXSLOTS) slots = MAXSLOTS;
+  if (slots > ngroups) slots = ngroups;
+  g->H = H; g->B = B; g->Bpad = Bpad; g->U = TSU; g->nslice = H / TSU; g->stages = slots;
+  g->smem_bytes = a_bytes + (size_t)slots * slot + 1024;
+  if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;      // one CTA per SM (each allocates all of TMEM)
+  g->ts = 1;
+  g->gkb = gkb;
+  g->nkb_t = nkb_t;
+  g->ngl = (Bpad / 16 + 1) / 2;
+  // backward: TMEM columns = H/4 (Wh segment) + Bpad (accumulator) must fit
+  if (H / 4 + Bpad > 512) return false;
+  return true;
+}
+
+size_t rec_ts_blob_floats(const RecTcGeom& g, int T) {
+  return (size_t)T * g.nslice * g.ngl * BLOB_ITEMS * 8 * 32 * 2;
+}
+
+int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a, cudaStream_t st) {
+  RS_REQUIRE(a.T > 0, RS_ERR_INVALID, "lstm_rec_ts_forward: T=%d", a.T);
+  RS_REQUIRE(a.h_ld == 2 * g.H && a.h_lo == a.h_hi + g.H, RS_ERR_INVALID,
+             "lstm_rec_ts_forward: h planes must be row-interleaved ([rows][hi H | lo H])");
+  CUtensorMap th, ts;
+  int rc;
+  const int hrows = (a.T + 1) * g.B;
+  if ((rc = tmap_stacked_bf16(&th, a.h_hi, hrows, g.H, g.Bpad, g.gkb)) != RS_OK) return rc;
+  if ((rc = tmap_store3_bf16(&ts, a.h_hi, g.H, 2, hrows, (size_t)g.H * 2, (size_t)2 * g.H * 2, TSU, 2, g.B)) != RS_OK) return rc;
+  KFwd p;
+  p.a = a;
+  p.H = g.H; p.B = g.B; p.Bpad = g.Bpad; p.nslice = g.nslice; p.slots = g.stages; p.nkb = g.H / 64; p.nkb_t = g.nkb_t;
+  p.gkb = g.gkb;
+  p.ngroups = p.nkb / g.gkb;
+  p.ngl = g.ngl;
+  p.kb_bytes = 2u * (uint32_t)g.Bpad * 128;
+  p.variant = ts_variant();
+  RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
+  int dev = 0, per_sm = 0, nsm = 0;
+  RS_CHECK_CUDA(cudaGetDevice(&dev));
+  RS_CHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  RS_CHECK_CUDA(cudaFuncSetAttribute(rec_ts_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  RS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rec_ts_fwd_kernel, NTHREADS, g.smem_bytes));
+  RS_REQUIRE(per_sm * nsm >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_ts_forward: %d CTAs cannot be co-resident", g.nslice);
+  void* kargs[] = {(void*)&th, (void*)&ts, (void*)&p};
+  RS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)rec_ts_fwd_kernel, dim3(g.nslice), dim3(NTHREADS), kargs,
+                                            g.smem_bytes, st));
+  count_launch();
+  return RS_OK;
+}
+
+int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a, cudaStream_t st) {
+  RS_REQUIRE(a.T > 0, RS_ERR_INVALID, "lstm_rec_ts_backward: T=%d", a.T);
+  CUtensorMap tg;
+  int rc;
+  if ((rc = tmap_2d_bf16(&tg, a.dg_hi, a.T * g.B, 4 * g.H, 4 * g.H, g.Bpad)) != RS_OK) return rc;
+  KBwd p;
+  p.a = a;
+  p.H = g.H; p.B = g.B; p.Bpad = g.Bpad; p.nslice = g.nslice; p.nkbs = g.H / 2 / 64; p.ngl = g.ngl;
+  uint32_t cols = 32;
+  while ((int)cols < g.H / 4 + g.Bpad) cols <<= 1;
+  p.tmem_cols = cols;
+  p.variant = ts_variant();
+  size_t smem = (size_t)p.nkbs * g.Bpad * 128 + (size_t)CL * TSU * g.Bpad * 4 + (size_t)2 * g.Bpad * 4 * TSU * 2 + 1024;
+  if (smem < 120 * 1024) smem = 120 * 1024;                        // one CTA per SM
+  RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
+  RS_CHECK_CUDA(cudaFuncSetAttribute(rec_ts_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g.nslice);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int nclusters = 0;
+  RS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, rec_ts_bwd_kernel, &cfg));
+  RS_REQUIRE(nclusters * CL >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_ts_backward: %d CTAs cannot be co-resident (%d clusters)",
+             g.nslice, nclusters);
+  CUtensorMap ts_hi, ts_lo;
+  if ((rc = tmap_store3_bf16(&ts_hi, a.dg_hi, g.H, 4, a.T * g.B, (size_t)g.H * 2, (size_t)4 * g.H * 2, TSU, 4, g.B)) != RS_OK) return rc;
+  if ((rc = tmap_store3_bf16(&ts_lo, a.dg_lo, g.H, 4, a.T * g.B, (size_t)g.H * 2, (size_t)4 * g.H * 2, TSU, 4, g.B)) != RS_OK) return rc;
+  RS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rec_ts_bwd_kernel, tg, ts_hi, ts_lo, p));
+  count_launch();
+  return RS_OK;
+}
+
+}  // namespace rs

@@ -89,8 +89,10 @@ void carve(const rs_am* am, void* reserve, void* ws, bool training, TcBufs* b, s
   b->x_hi = act.take<bf16>(TB * Fp); b->x_lo = act.take<bf16>(TB * Fp);
   for (int l = 0; l < L; ++l) {
     b->xin_hi[l] = act.take<bf16>(TB * H); b->xin_lo[l] = act.take<bf16>(TB * H);
-    b->hp_hi[l] = act.take<bf16>((TB + B) * H); b->hp_lo[l] = act.take<bf16>((TB + B) * H);
-    if (training) { b->gates[l] = act.take<float>(TB * 4 * H); b->cs[l] = act.take<float>(TB * H); }
+    if (am->tc.ts) { b->hp_hi[l] = act.take<bf16>(2 * (TB + B) * H); b->hp_lo[l] = b->hp_hi[l] + H; }   // [rows][hi | lo]
+    else { b->hp_hi[l] = act.take<bf16>((TB + B) * H); b->hp_lo[l] = act.take<bf16>((TB + B) * H); }
+    if (training && am->tc.ts) { b->gates[l] = act.take<float>(rec_ts_blob_floats(am->tc, T)); b->cs[l] = nullptr; }
+    else if (training) { b->gates[l] = act.take<float>(TB * 4 * H); b->cs[l] = act.take<float>(TB * H); }
     else { b->gates[l] = nullptr; b->cs[l] = nullptr; }
   }
   b->top_hi = act.take<bf16>(TB * H); b->top_lo = act.take<bf16>(TB * H);
@@ -100,11 +102,12 @@ void carve(const rs_am* am, void* reserve, void* ws, bool training, TcBufs* b, s
 }
 
 // planes <- split(dropout(hi + lo)); in == out allowed
-__global__ void dropout_planes_kernel(const bf16* __restrict__ ihi, const bf16* __restrict__ ilo, bf16* __restrict__ ohi,
-                                      bf16* __restrict__ olo, int64_t n, uint64_t key, uint32_t sa, uint32_t thr_a,
-                                      float inv_a, uint32_t sb, uint32_t thr_b, float inv_b) {
+__global__ void dropout_planes_kernel(const bf16* __restrict__ ihi, const bf16* __restrict__ ilo, int cols, int ld_in,
+                                      bf16* __restrict__ ohi, bf16* __restrict__ olo, int64_t n, uint64_t key, uint32_t sa,
+                                      uint32_t thr_a, float inv_a, uint32_t sb, uint32_t thr_b, float inv_b) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float v = __bfloat162float(ihi[i]) + __bfloat162float(ilo[i]);
+    const int64_t ii = (ld_in == cols) ? i : (i / cols) * ld_in + (i % cols);
+    float v = __bfloat162float(ihi[ii]) + __bfloat162float(ilo[ii]);
     if (thr_a != 0xffffffffu) v = dropout_keep(key, sa, (uint64_t)i, thr_a) ? v * inv_a : 0.f;
     if (thr_b != 0xffffffffu) v = dropout_keep(key, sb, (uint64_t)i, thr_b) ? v * inv_b : 0.f;
     bf16 h, l;
@@ -127,10 +130,11 @@ inline int ew_grid(int64_t n) {
   const int cap = sm_count() * 16;
   return grid > cap ? cap : grid;
 }
-int dropout_planes(const bf16* ihi, const bf16* ilo, bf16* ohi, bf16* olo, int64_t n, uint64_t seed, int sa,
-                   float keep_a, int sb, float keep_b, cudaStream_t st) {
+// in: rows of `cols` elements with row stride ld_in; out: contiguous
+int dropout_planes(const bf16* ihi, const bf16* ilo, int cols, int ld_in, bf16* ohi, bf16* olo, int64_t n, uint64_t seed,
+                   int sa, float keep_a, int sb, float keep_b, cudaStream_t st) {
   const uint32_t ta = sa >= 0 ? thr24(keep_a) : 0xffffffffu, tb = sb >= 0 ? thr24(keep_b) : 0xffffffffu;
-  dropout_planes_kernel<<<ew_grid(n), 256, 0, st>>>(ihi, ilo, ohi, olo, n, splitmix64(seed), (uint32_t)(sa < 0 ? 0 : sa),
+  dropout_planes_kernel<<<ew_grid(n), 256, 0, st>>>(ihi, ilo, cols, ld_in, ohi, olo, n, splitmix64(seed), (uint32_t)(sa < 0 ? 0 : sa),
                                                     ta, 1.0f / keep_a, (uint32_t)(sb < 0 ? 0 : sb), tb, 1.0f / keep_b);
   RS_CHECK_LAUNCH();
   return RS_OK;
@@ -155,6 +159,23 @@ __global__ void split_rows_kernel(const float* __restrict__ in, int R, int C, in
     hi[i] = h;
     if (lo) lo[i] = l;
   }
+}
+// [R, C] fp32 contiguous -> planes with row stride ld_out, touching only the C columns of each row
+__global__ void split_rows_strided_kernel(const float* __restrict__ in, int R, int C, bf16* __restrict__ hi,
+                                          bf16* __restrict__ lo, int ld_out) {
+  const int64_t n = (int64_t)R * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i - (int64_t)r * C);
+    bf16 h, l;
+    tc::split_bf16(in[i], h, l);
+    hi[(size_t)r * ld_out + c] = h;
+    lo[(size_t)r * ld_out + c] = l;
+  }
+}
+int split_rows_strided(const float* in, int R, int C, bf16* hi, bf16* lo, int ld_out, cudaStream_t st) {
+  split_rows_strided_kernel<<<ew_grid((int64_t)R * C), 256, 0, st>>>(in, R, C, hi, lo, ld_out);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
 }
 int split_rows(const float* in, int R, int C, int ld_in, bf16* hi, bf16* lo, int ld_out, cudaStream_t st) {
   split_rows_kernel<<<ew_grid((int64_t)R * ld_out), 256, 0, st>>>(in, R, C, ld_in, hi, lo, ld_out);
@@ -209,13 +230,15 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     GemmTcOut o{};
     o.mode = GEMM_OUT_SPLIT; o.Chi = bf.xin_hi[0]; o.Clo = bf.xin_lo[0]; o.ldc = H; o.bias = params_d + am->off_input_b;
     RC(gemm_tc_nt(A, Bm, TB, H, F, 3, o, st));
-    if (drop_in) RC(dropout_planes(bf.xin_hi[0], bf.xin_lo[0], bf.xin_hi[0], bf.xin_lo[0], nTBH, seed, 0, keep_in, -1, 1.f, st));
+    if (drop_in) RC(dropout_planes(bf.xin_hi[0], bf.xin_lo[0], H, H, bf.xin_hi[0], bf.xin_lo[0], nTBH, seed, 0, keep_in, -1, 1.f, st));
   }
+  const int hld = am->tc.ts ? 2 * H : H;            // row stride of the h planes
   const bf16 *cur_hi = bf.xin_hi[0], *cur_lo = bf.xin_lo[0];
+  int cur_ld = H;
   for (int l = 0; l < L; ++l) {
     // hoisted input half: gx = xin @ K[:H] + b, written in the recurrent kernel's layout
     {
-      SplitMat A{cur_hi, cur_lo, TB, H, H}, Bm{bf.wx_hi[l], bf.wx_lo[l], 4 * H, H, H};
+      SplitMat A{cur_hi, cur_lo, TB, H, cur_ld}, Bm{bf.wx_hi[l], bf.wx_lo[l], 4 * H, H, H};
       GemmTcOut o{};
       o.mode = GEMM_OUT_REC; o.C = bf.gx; o.bias = params_d + am->off_bias[l];
       o.recB = B; o.recBpad = am->tc.Bpad; o.recH = H; o.recU = am->tc.U;
@@ -224,32 +247,33 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     // carried-in h -> slot 0 of the h planes
     const float* c0 = bf.state0 + ((size_t)l * 2 + 0) * B * H;
     const float* h0 = bf.state0 + ((size_t)l * 2 + 1) * B * H;
-    RC(split_planes(h0, bf.hp_hi[l], bf.hp_lo[l], (int64_t)B * H, st));
+    RC(split_rows_strided(h0, B, H, bf.hp_hi[l], bf.hp_lo[l], hld, st));
     RecTcFwdArgs a;
     a.gx = bf.gx; a.wrec_hi = bf.wrec_hi[l]; a.wrec_lo = bf.wrec_lo[l];
-    a.h_hi = bf.hp_hi[l]; a.h_lo = bf.hp_lo[l]; a.len = len_d; a.c0 = c0; a.h0 = h0;
+    a.h_hi = bf.hp_hi[l]; a.h_lo = bf.hp_lo[l]; a.h_ld = hld; a.len = len_d; a.c0 = c0; a.h0 = h0;
     a.cT = state_out_d ? state_out_d + ((size_t)l * 2 + 0) * B * H : nullptr;
     a.hT = state_out_d ? state_out_d + ((size_t)l * 2 + 1) * B * H : nullptr;
     a.gates = bf.gates[l]; a.cs = bf.cs[l]; a.barrier = bf.barrier; a.T = T;
     a.dbg = (l == 0) ? am->dbg_fwd : nullptr;
     if (am->timing) RS_CHECK_CUDA(cudaEventRecord(am->ev[0][l][0], st));
-    RC(lstm_rec_tc_forward(am->tc, a, st));
+    if (am->tc.ts) RC(lstm_rec_ts_forward(am->tc, a, st));
+    else RC(lstm_rec_tc_forward(am->tc, a, st));
     if (am->timing) { RS_CHECK_CUDA(cudaEventRecord(am->ev[0][l][1], st)); am->ev_valid[0][l] = 1; }
     // the hop to the next consumer: identity (alias slots 1..T) or dropout(s)
-    const bf16 *o_hi = bf.hp_hi[l] + (size_t)B * H, *o_lo = bf.hp_lo[l] + (size_t)B * H;
+    const bf16 *o_hi = bf.hp_hi[l] + (size_t)B * hld, *o_lo = bf.hp_lo[l] + (size_t)B * hld;
     const bool last = l + 1 == L;
     const bool hop_drop = last ? drop_out : (drop_out || drop_in);
     if (!hop_drop) {
-      cur_hi = o_hi; cur_lo = o_lo;
+      cur_hi = o_hi; cur_lo = o_lo; cur_ld = hld;
     } else {
       bf16 *d_hi = last ? bf.top_hi : bf.xin_hi[l + 1], *d_lo = last ? bf.top_lo : bf.xin_lo[l + 1];
-      RC(dropout_planes(o_hi, o_lo, d_hi, d_lo, nTBH, seed, drop_out ? 2 * l + 1 : -1, keep_out,
+      RC(dropout_planes(o_hi, o_lo, H, hld, d_hi, d_lo, nTBH, seed, drop_out ? 2 * l + 1 : -1, keep_out,
                         (!last && drop_in) ? 2 * (l + 1) : -1, keep_in, st));
-      cur_hi = d_hi; cur_lo = d_lo;
+      cur_hi = d_hi; cur_lo = d_lo; cur_ld = H;
     }
   }
   // output dense                                               (models/AcousticModel.py:308-309)
-  SplitMat A{cur_hi, cur_lo, TB, H, H}, Bm{bf.wo_hi, bf.wo_lo, C, H, H};
+  SplitMat A{cur_hi, cur_lo, TB, H, cur_ld}, Bm{bf.wo_hi, bf.wo_lo, C, H, H};
   GemmTcOut o{};
   o.mode = GEMM_OUT_F32; o.C = logits_d; o.ldc = C; o.bias = params_d + am->off_output_b;
   return gemm_tc_nt(A, Bm, TB, C, H, 3, o, st);
@@ -267,7 +291,8 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   carve(am, reserve_d, ws_d, true, &bf, nullptr, &need_ws);
   RS_REQUIRE(ws_bytes >= need_ws, RS_ERR_WORKSPACE, "rs_am_backward: workspace %zu < %zu", ws_bytes, need_ws);
   RecTcBwdGeom bg;
-  RS_REQUIRE(rec_tc_bwd_geometry(H, B, &bg), RS_ERR_UNSUPPORTED, "rs_am_backward: shape outside the tensor-core path");
+  if (am->tc.ts) { bg.H = H; bg.B = B; bg.Bpad = am->tc.Bpad; bg.nslice = am->tc.nslice; bg.stages = 1; bg.smem_bytes = 0; }
+  else RS_REQUIRE(rec_tc_bwd_geometry(H, B, &bg), RS_ERR_UNSUPPORTED, "rs_am_backward: shape outside the tensor-core path");
   const bool drop_in = keep_in < 1.f, drop_out = keep_out < 1.f;
 
   // weights as stored (K-major for the "multiply by W^T" GEMMs)
@@ -278,22 +303,25 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     RC(split_planes(K + (size_t)H * 4 * H, bf.whs_hi[l], nullptr, (int64_t)H * 4 * H, st));
   }
   // where forward left each layer's input / the top activations
+  const int hld = am->tc.ts ? 2 * H : H;
   const bf16 *xin_hi[64], *xin_lo[64], *top_hi, *top_lo;
-  xin_hi[0] = bf.xin_hi[0]; xin_lo[0] = bf.xin_lo[0];
+  int xin_ld[64], top_ld = H;
+  xin_hi[0] = bf.xin_hi[0]; xin_lo[0] = bf.xin_lo[0]; xin_ld[0] = H;
   for (int l = 0; l < L; ++l) {
     const bool last = l + 1 == L;
     const bool hop_drop = last ? drop_out : (drop_out || drop_in);
-    const bf16 *o_hi = bf.hp_hi[l] + (size_t)B * H, *o_lo = bf.hp_lo[l] + (size_t)B * H;
+    const bf16 *o_hi = bf.hp_hi[l] + (size_t)B * hld, *o_lo = bf.hp_lo[l] + (size_t)B * hld;
     const bf16* n_hi = hop_drop ? (last ? bf.top_hi : bf.xin_hi[l + 1]) : o_hi;
     const bf16* n_lo = hop_drop ? (last ? bf.top_lo : bf.xin_lo[l + 1]) : o_lo;
-    if (last) { top_hi = n_hi; top_lo = n_lo; } else { xin_hi[l + 1] = n_hi; xin_lo[l + 1] = n_lo; }
+    const int n_ld = hop_drop ? H : hld;
+    if (last) { top_hi = n_hi; top_lo = n_lo; top_ld = n_ld; } else { xin_hi[l + 1] = n_hi; xin_lo[l + 1] = n_lo; xin_ld[l + 1] = n_ld; }
   }
 
   // ---- output dense: dW_o += top^T dlogits, db_o += colsum, dtop = dlogits w_o^T
   RC(split_rows(dlogits_d, TB, C, C, bf.dl_hi, bf.dl_lo, Cp, st));
   RC(split_planes_transposed(dlogits_d, TB, C, C, bf.dlT_hi, bf.dlT_lo, TBp, st));                  // [C][TBp]
-  RC(transpose_bf16(top_hi, TB, H, H, bf.actT_hi, TBp, st));
-  RC(transpose_bf16(top_lo, TB, H, H, bf.actT_lo, TBp, st));
+  RC(transpose_bf16(top_hi, TB, H, top_ld, bf.actT_hi, TBp, st));
+  RC(transpose_bf16(top_lo, TB, H, top_ld, bf.actT_lo, TBp, st));
   {
     SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp}, Bm{bf.dlT_hi, bf.dlT_lo, C, TB, TBp};
     GemmTcOut o{};
@@ -340,7 +368,8 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     a.wh_hi = bf.whs_hi[l]; a.dg_hi = bf.dg_hi[set]; a.dg_lo = bf.dg_lo[set]; a.len = len_d; a.barrier = bf.barrier; a.T = T;
     a.dbg = (l == 0) ? am->dbg_bwd : nullptr;
     if (am->timing) RS_CHECK_CUDA(cudaEventRecord(am->ev[1][l][0], st));
-    RC(lstm_rec_tc_backward(bg, a, st));
+    if (am->tc.ts) RC(lstm_rec_ts_backward(am->tc, a, st));
+    else RC(lstm_rec_tc_backward(bg, a, st));
     if (am->timing) { RS_CHECK_CUDA(cudaEventRecord(am->ev[1][l][1], st)); am->ev_valid[1][l] = 1; }
     RS_CHECK_CUDA(cudaEventRecord(am->ev_rec[l], st));
     // ---- critical path: dxin = dg @ K[:H]^T feeds the next layer's recurrence
@@ -357,16 +386,16 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     SplitMat G{bf.dgT_hi, bf.dgT_lo, 4 * H, TB, TBp};
     float* gK = grads_d + am->off_kernel[l];
     {
-      RC(transpose_bf16(xin_hi[l], TB, H, H, bf.actT_hi, TBp, side));
-      RC(transpose_bf16(xin_lo[l], TB, H, H, bf.actT_lo, TBp, side));
+      RC(transpose_bf16(xin_hi[l], TB, H, xin_ld[l], bf.actT_hi, TBp, side));
+      RC(transpose_bf16(xin_lo[l], TB, H, xin_ld[l], bf.actT_lo, TBp, side));
       SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp};
       GemmTcOut o{};
       o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = side_ctas;
       RC(gemm_tc_nt(A, G, H, 4 * H, TB, 3, o, side));
     }
     {
-      RC(transpose_bf16(bf.hp_hi[l], TB, H, H, bf.actT_hi, TBp, side));       // slots 0..T-1 = h_{t-1}
-      RC(transpose_bf16(bf.hp_lo[l], TB, H, H, bf.actT_lo, TBp, side));
+      RC(transpose_bf16(bf.hp_hi[l], TB, H, hld, bf.actT_hi, TBp, side));     // slots 0..T-1 = h_{t-1}
+      RC(transpose_bf16(bf.hp_lo[l], TB, H, hld, bf.actT_lo, TBp, side));
       SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp};
       GemmTcOut o{};
       o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = side_ctas;

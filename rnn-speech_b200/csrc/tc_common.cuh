@@ -98,6 +98,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// lane l of the warp writes 8 consecutive 32-bit columns of TMEM lane (lane field of taddr + l)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors --------------------------------------------------------------------
 // K-major SWIZZLE_128B operand tile (rows x 64 bf16, 128 B per row, 1024 B per 8-row group)
@@ -137,6 +144,63 @@ __device__ __forceinline__ void mma_bf16_ss_warp(uint32_t d_tmem, uint64_t a_des
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand resident in TMEM ("TS" form): A[M=128, K=16] bf16 occupies lanes 0..127 x 8 columns
+// (column c of a row holds K elements 2c | 2c+1 << 16); a_tmem = address of its first column.
+__device__ __forceinline__ void mma_bf16_ts_warp(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Four consecutive K = 16 steps of one 64-element K-block in ONE asm block (one elect, no
+// per-MMA compiler glue): A advances 8 TMEM columns / 32 bytes per step, B 32 bytes.
+__device__ __forceinline__ void mma4_bf16_ts_warp(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t"
+      ".reg .b32 a1, a2, a3;\n\t"
+      ".reg .b64 b1, b2, b3;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %3, %3;\n\t"
+      "add.u32 a1, %1, 8;\n\t"
+      "add.u32 a2, %1, 16;\n\t"
+      "add.u32 a3, %1, 24;\n\t"
+      "add.u64 b1, %2, 2;\n\t"
+      "add.u64 b2, %2, 4;\n\t"
+      "add.u64 b3, %2, 6;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %3, t;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
+__device__ __forceinline__ void mma4_bf16_ss_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %3, %3;\n\t"
+      "add.u64 a1, %1, 2;\n\t"
+      "add.u64 a2, %1, 4;\n\t"
+      "add.u64 a3, %1, 6;\n\t"
+      "add.u64 b1, %2, 2;\n\t"
+      "add.u64 b2, %2, 4;\n\t"
+      "add.u64 b3, %2, 6;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit_warp(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
@@ -162,6 +226,30 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// 4-D tiled load (coordinates innermost first)
+__device__ __forceinline__ void tma_load_4d_warp(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// 2-D tiled store shared -> global (bulk async-group completion); one thread issues
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread complete (writes performed), not just their shared-memory reads
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // converged-warp variants: every lane executes, one elected lane issues
 __device__ __forceinline__ void tma_load_2d_warp(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {

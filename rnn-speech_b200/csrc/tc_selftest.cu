@@ -181,3 +181,104 @@ extern "C" int rs_tc_mma_bench(int M, int N, int count, int variant, int nacc, v
   RS_CHECK_LAUNCH();
   return RS_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// "TS" self-test: the A operand lives in TMEM (written with tcgen05.st), stacked the way the
+// TMEM-resident recurrent kernels stack it: sub-partition q holds rows 16q..16q+15 of A_hi in
+// lanes 32q..32q+15 and the same rows of A_lo in lanes 32q+16..32q+31.  B is the stacked
+// [B_hi (32 rows); B_lo (32 rows)] N = 64 tile in shared memory.  The raw accumulator
+// D[128 lanes][64] comes back so the test can pin every quadrant (hi*hi, hi*lo, lo*hi, lo*lo).
+// Also reports the cycles of `reps` back-to-back passes over K (issue -> completion).
+// ---------------------------------------------------------------------------------------
+namespace rs {
+namespace {
+__global__ void __launch_bounds__(128, 1)
+tc_ts_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int K, int variant,
+                      int reps, long long* out_cycles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = K / 64;
+  constexpr uint32_t B_KB_BYTES = 64 * 128;
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  for (int e = tid; e < 32 * K; e += 128) {
+    const int r = e / K, k = e % K;
+    __nv_bfloat16 hi, lo;
+    tc::split_bf16(B[e], hi, lo);
+    unsigned char* tile = smem + (size_t)(k / 64) * B_KB_BYTES;
+    *reinterpret_cast<__nv_bfloat16*>(tile + tc::swz_off(r, k % 64)) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(tile + tc::swz_off(32 + r, k % 64)) = lo;
+  }
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tmemD = tmem + ((variant >> 8) ? (uint32_t)(variant >> 8) : 448u);     // variant >> 8: accumulator column
+  {
+    // this thread's TMEM lane = tid: row 16*warp + (lane & 15), hi plane for lane < 16, lo otherwise
+    const int row = 16 * warp + (lane & 15);
+    const bool is_lo = lane >= 16;
+    for (int c0 = 0; c0 < K / 2; c0 += 8) {
+      uint32_t r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        tc::split_bf16(A[(size_t)row * K + 2 * (c0 + i)], h0, l0);
+        tc::split_bf16(A[(size_t)row * K + 2 * (c0 + i) + 1], h1, l1);
+        const __nv_bfloat16 e0 = is_lo ? l0 : h0, e1 = is_lo ? l1 : h1;
+        r[i] = (variant & 1) ? tc::pack_bf16(e1, e0) : tc::pack_bf16(e0, e1);
+      }
+      tc::tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+    }
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  if (warp == 1) {
+    const uint32_t idesc = tc::instr_desc_bf16(128, 64);
+    const uint64_t db0 = tc::smem_desc_sw128(tc::smem_u32(smem));
+    long long t0 = clock64();
+    for (int rep = 0; rep < reps; ++rep)
+      for (int kb = 0; kb < nkb; ++kb)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc::mma_bf16_ts_warp(tmemD, tmem + (uint32_t)(kb * 32 + k * 8), db0 + (uint64_t)kb * (B_KB_BYTES >> 4) + 2 * k, idesc,
+                               (uint32_t)((kb | k) != 0));
+    long long t1 = clock64();
+    tc::mma_commit_warp(&bar);
+    tc::mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    if (lane == 0 && out_cycles) { out_cycles[0] = t1 - t0; out_cycles[1] = t2 - t0; }
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+  for (int c = 0; c < 4; ++c) {
+    float v[16];
+    tc::tmem_ld16(tmemD + ((uint32_t)(32 * warp) << 16) + (uint32_t)(c * 16), v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[(size_t)tid * 64 + c * 16 + i] = v[i];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace
+}  // namespace rs
+
+// A_d [64,K], B_d [32,K] fp32; D_d [128,64] fp32 raw accumulator (TMEM lane, column); K multiple of 64, <= 768.
+// variant bit0: swap the two bf16 halves of each TMEM column.  out_cycles_d: int64[2] or NULL.
+extern "C" int rs_tc_ts_selftest(const float* A_d, const float* B_d, float* D_d, int K, int variant, int reps,
+                                 void* out_cycles_d, void* stream) {
+  RS_REQUIRE(A_d && B_d && D_d, RS_ERR_INVALID, "rs_tc_ts_selftest: NULL argument");
+  RS_REQUIRE(K >= 64 && K % 64 == 0 && K <= 768 && reps >= 1, RS_ERR_INVALID, "rs_tc_ts_selftest: K=%d unsupported", K);
+  size_t smem = (size_t)(K / 64) * 64 * 128 + 1024;
+  RS_CHECK_CUDA(cudaFuncSetAttribute(tc_ts_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_ts_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A_d, B_d, D_d, K, variant, reps, (long long*)out_cycles_d);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}

@@ -155,8 +155,8 @@ def model_diag(which):
         m.create_training_rnn(1.0, 1.0, 1, 3e-4, 0.33)
         m.load_flat_params(flat)
         m.enable_timing()
-        dbg_f = torch.zeros((T, 16), dtype=torch.int64, device=dev)
-        dbg_b = torch.zeros((T, 16), dtype=torch.int64, device=dev)
+        dbg_f = torch.zeros((2 * T, 16), dtype=torch.int64, device=dev)
+        dbg_b = torch.zeros((2 * T, 16), dtype=torch.int64, device=dev)
         rs._lib.call("rs_am_set_debug_timeline", m._handle, dbg_f.data_ptr(), dbg_b.data_ptr())
         print("cfg2: tensor cores:", m.uses_tensor_cores)
         xd, ld = torch.from_numpy(x).to(dev), torch.from_numpy(lens).to(dev)
@@ -213,6 +213,107 @@ def mma_bench():
                 "warp+elect " if variant else "one thread ", M, N, nacc, c[0] / count, c[1] / count))
 
 
+def rec_diag():
+    """cfg-2 recurrent kernels: per-variant kernel times, bitwise comparison against variant 0,
+    and the in-kernel timelines (CTA 0 and the last CTA, all 16 stamps)."""
+    L, H, F, C, B, T = 3, 768, 120, 80, 32, 998
+    rng = np.random.default_rng(0)
+    p = model.init_params(L, H, F, C, seed=0)
+    flat = model.flatten(p, L, H, F, C)
+    x = rng.standard_normal((T, B, F)).astype(np.float32)
+    lens = np.full(B, T, np.int32)
+    lens[1::4] = rng.integers(T // 2, T, size=len(lens[1::4]))
+    if os.environ.get("RS_TS_GKB"):
+        print("RS_TS_GKB =", os.environ["RS_TS_GKB"])
+    m = rs.AcousticModel(L, H, B, 1000, 600, F, False, C, device=dev)
+    m.create_training_rnn(1.0, 1.0, 1, 3e-4, 0.33)
+    m.load_flat_params(flat)
+    m.enable_timing()
+    dbg_f = torch.zeros((2 * T, 16), dtype=torch.int64, device=dev)
+    dbg_b = torch.zeros((2 * T, 16), dtype=torch.int64, device=dev)
+    rs._lib.call("rs_am_set_debug_timeline", m._handle, dbg_f.data_ptr(), dbg_b.data_ptr())
+    xd, ld = torch.from_numpy(x).to(dev), torch.from_numpy(lens).to(dev)
+    labs = [np.append(rng.integers(1, 79, size=rng.integers(60, 121)), 79).astype(np.int32) for _ in range(B)]
+    ref = None
+    variants = [int(v) for v in os.environ.get("RS_DIAG_VARIANTS", "0").split(",")]
+    for variant in variants:
+        os.environ["RS_TS_VARIANT"] = str(variant)
+        for it in range(2):
+            m.rnn_state.zero_()
+            dbg_f.zero_(); dbg_b.zero_()
+            logits = m.forward(xd, ld, training=True, keep_state=False)
+            loss, grad = m.ctc_loss(logits, labs, ld)
+            m.grads.zero_()
+            m.backward(xd, ld, grad)
+            torch.cuda.synchronize()
+        got = (logits.clone(), m.grads.clone())
+        if ref is None:
+            ref = got
+        print("variant %d: rec ms fwd/bwd %s ; logits bitwise == variant %d: %s ; grads bitwise: %s ; grads finite %s" % (
+            variant, m.recurrent_ms(), variants[0], bool(torch.equal(got[0], ref[0])), bool(torch.equal(got[1], ref[1])),
+            bool(torch.isfinite(got[1]).all())))
+        for tag, d in (("fwd", dbg_f.cpu().numpy()), ("bwd", dbg_b.cpu().numpy())):
+            steps = [400, 401] if tag == "fwd" else [405, 404]
+            t0 = int(d[steps[0], 0])
+            print("  timeline %s variant %d (ns relative to CTA0 step %d ev0); events 0..15" % (tag, variant, steps[0]))
+            for cta, base in (("cta0", 0), ("ctaN", T)):
+                for sidx in steps:
+                    print("    %s step %d:" % (cta, sidx), " ".join(
+                        "%6d" % (int(d[base + sidx, e]) - t0) if d[base + sidx, e] else "     ." for e in range(16)))
+            per = np.diff(d[100:900, 0].astype(np.int64))
+            print("    mean step period %.0f ns" % np.abs(per).mean())
+            if tag == "fwd" and d[900, 15] and d[100, 15]:
+                print("    SM clock during the kernel: %.0f MHz (clock64 vs globaltimer over steps 100..900)" % (
+                    (int(d[900, 15]) - int(d[100, 15])) / max(1, int(d[900, 7]) - int(d[100, 7])) * 1e3))
+
+
+def bf16_round(x):
+    return torch.from_numpy(np.asarray(x, np.float32)).to(torch.bfloat16).to(torch.float32).numpy().astype(np.float64)
+
+
+def ts_diag():
+    """TMEM-resident A operand: pin the TMEM layout of a bf16 A and time the M128 N64 TS MMA."""
+    out = torch.zeros(2, dtype=torch.int64, device=dev)
+    for K in (64, 256, 768):
+        rng = np.random.default_rng(K)
+        A = rng.standard_normal((64, K)).astype(np.float32)
+        B = rng.standard_normal((32, K)).astype(np.float32)
+        Ah = bf16_round(A); Al = bf16_round(A.astype(np.float64) - Ah)
+        Bh = bf16_round(B); Bl = bf16_round(B.astype(np.float64) - Bh)
+        want = np.zeros((128, 64))
+        for q in range(4):
+            rows = slice(16 * q, 16 * q + 16)
+            want[32 * q:32 * q + 16, :32] = Ah[rows] @ Bh.T
+            want[32 * q:32 * q + 16, 32:] = Ah[rows] @ Bl.T
+            want[32 * q + 16:32 * q + 32, :32] = Al[rows] @ Bh.T
+            want[32 * q + 16:32 * q + 32, 32:] = Al[rows] @ Bl.T
+        Ad, Bd = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
+        for variant in (0, 1):
+            D = torch.full((128, 64), float("nan"), dtype=torch.float32, device=dev)
+            rs._lib.call("rs_tc_ts_selftest", Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), K, variant, 1, out.data_ptr(),
+                         torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got = D.cpu().numpy().astype(np.float64)
+            e = np.abs(got - want)
+            quad = [e[np.ix_([32 * q + i + off for q in range(4) for i in range(16)], range(c0, c0 + 32))].max() / np.abs(want).max()
+                    for off in (0, 16) for c0 in (0, 32)]
+            full = got[[32 * q + i for q in range(4) for i in range(16)]]
+            lo = got[[32 * q + 16 + i for q in range(4) for i in range(16)]]
+            tot = full[:, :32] + full[:, 32:] + lo[:, :32]
+            ref = A.astype(np.float64) @ B.astype(np.float64).T
+            print("ts K=%d variant=%d: quadrant rel err hh %.2e hl %.2e lh %.2e ll %.2e ; x3 sum vs fp64 %.2e ; nan %d" % (
+                K, variant, quad[0], quad[1], quad[2], quad[3], np.abs(tot - ref).max() / np.abs(ref).max(), int(np.isnan(got).sum())))
+        for dcol in (448, 384, 416):
+          for reps in (1, 8):
+            rs._lib.call("rs_tc_ts_selftest", Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), K, dcol << 8, reps, out.data_ptr(),
+                         torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            c = out.cpu().numpy()
+            n = reps * K // 16
+            print("   ts timing K=%d reps=%d D@col %d: %d MMAs (M128 N64 K16, A in TMEM): issue %.1f, complete %.1f cycles/MMA" % (
+                K, reps, dcol, n, c[0] / n, c[1] / n))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ctc", "fbank"]
     if "ctc" in which:
@@ -223,6 +324,10 @@ if __name__ == "__main__":
         tc_diag()
     if "gemm" in which:
         gemm_diag()
+    if "rec" in which:
+        rec_diag()
+    if "ts" in which:
+        ts_diag()
     if "mma" in which:
         mma_bench()
     if "cfg1" in which or "cfg2" in which:
