@@ -127,8 +127,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       tc::tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
-      int rt = 0, rb = 0;
-      if (o.mode == GEMM_OUT_REC) { rt = m / o.recB; rb = m - rt * o.recB; }
+      // GEMM_OUT_REC: this thread's row is a permuted gate row; its bias entry is g*H + unit
+      float rec_bias = 0.f;
+      if (o.mode == GEMM_OUT_REC && row_ok && o.bias) {
+        const int r4u = 4 * o.recU, sl = m / r4u, r = m - sl * r4u;
+        rec_bias = __ldg(o.bias + (size_t)(r & 3) * o.recH + sl * o.recU + (r >> 2));
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 16; ++c) {
         float v[16];
@@ -136,7 +140,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tc::tmem_ld_wait();
         const int nb = n0 + c * 16;
         if (row_ok && nb < p.N) {
-        if (o.bias) {
+        if (o.mode == GEMM_OUT_REC) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += rec_bias;
+        } else if (o.bias) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) if (nb + i < p.N) v[i] += __ldg(o.bias + nb + i);
         }
@@ -158,15 +165,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (nb + i < p.N) cp[i] = o.accumulate ? cp[i] + v[i] : v[i];
           }
         } else if (o.mode == GEMM_OUT_REC) {
-          const int nslice = o.recH / o.recU;
+          // column n = t*B + b -> gx[(t*4H + m)*Bpad + b]: 16 consecutive b of one step are 64 contiguous bytes
+          const int t = nb / o.recB, b0 = nb - t * o.recB;
+          float* cp = o.C + ((size_t)t * 4 * o.recH + m) * (size_t)o.recBpad + b0;
+          if (b0 + 15 < o.recB && nb + 15 < p.N && ((b0 | o.recBpad) & 3) == 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int n = nb + i;
-            if (n < p.N) {
-              const int g = n / o.recH, unit = n - g * o.recH;
-              const size_t idx = (((size_t)rt * nslice + unit / o.recU) * (4 * o.recU) + (unit % o.recU) * 4 + g) *
-                                     (size_t)o.recBpad + rb;
-              o.C[idx] = v[i];
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = nb + i;
+              if (n < p.N) {
+                const int tt = n / o.recB, bb = n - tt * o.recB;
+                o.C[((size_t)tt * 4 * o.recH + m) * (size_t)o.recBpad + bb] = v[i];
+              }
             }
           }
         } else {

@@ -26,8 +26,9 @@ struct GemmTcOut {
   int ldc;
   const float* bias;       // [N] or nullptr
   int accumulate;          // GEMM_OUT_F32 only
-  // GEMM_OUT_REC: row m = t*B + b, col n = g*H + unit ->
-  //   ((t*nslice + unit/U)*(4U) + (unit%U)*4 + g) * Bpad + b
+  // GEMM_OUT_REC (transposed product): row m = permuted gate row (unit/U)*4U + (unit%U)*4 + g (the A operand
+  //   is the pack_wrec() layout of the weights), col n = t*B + b -> C[(t*4H + m) * Bpad + b];
+  //   bias is indexed in the original order g*H + unit
   int recB, recBpad, recH, recU;
   int max_ctas;            // 0 = one CTA per SM; otherwise cap the persistent grid (side-stream GEMMs)
 };

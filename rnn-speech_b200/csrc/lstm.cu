@@ -95,7 +95,15 @@ extern "C" int rs_am_create(rs_am** out, int num_layers, int hidden_size, int in
   am->n_params = off;
   am->timing = 0;
   am->dbg_fwd = am->dbg_bwd = nullptr;
-  am->side_ready = 0;
+  am->streams_ready = 0;
+  am->ev_next = 0;
+  {
+    const char* v = getenv("RS_TC_CHUNK");
+    am->chunk = v ? atoi(v) : 128;
+    v = getenv("RS_TC_WINDOW");
+    am->window = v ? atoi(v) : 2;
+    if (am->window < 1) am->window = 1;
+  }
   // tensor-core path when the shape fits it (RS_DISABLE_TC=1 forces the FFMA kernels)
   {
     RecTcBwdGeom bg;
@@ -107,19 +115,20 @@ extern "C" int rs_am_create(rs_am** out, int num_layers, int hidden_size, int in
                             rec_tc_bwd_geometry(hidden_size, batch_size, &bg)));
   }
   for (int d = 0; d < 2; ++d)
-    for (int l = 0; l < 64; ++l) am->ev_valid[d][l] = 0;
+    for (int l = 0; l < 64; ++l) am->tev_used[d][l] = 0;
   *out = am;
   return RS_OK;
 }
 
 extern "C" void rs_am_destroy(rs_am* am) {
   if (!am) return;
-  if (am->timing)
-    for (int d = 0; d < 2; ++d)
-      for (int l = 0; l < am->L; ++l) { cudaEventDestroy(am->ev[d][l][0]); cudaEventDestroy(am->ev[d][l][1]); }
-  if (am->side_ready) {
-    for (int l = 0; l < am->L; ++l) { cudaEventDestroy(am->ev_rec[l]); cudaEventDestroy(am->ev_side[l]); }
-    cudaEventDestroy(am->ev_fork);
+  for (int d = 0; d < 2; ++d)
+    for (int l = 0; l < 64; ++l)
+      for (cudaEvent_t e : am->tev[d][l]) cudaEventDestroy(e);
+  for (cudaEvent_t e : am->evpool) cudaEventDestroy(e);
+  if (am->streams_ready) {
+    for (int l = 0; l < am->L; ++l) cudaStreamDestroy(am->lane[l]);
+    cudaStreamDestroy(am->gemm_st);
     cudaStreamDestroy(am->side);
   }
   delete am;
@@ -127,14 +136,7 @@ extern "C" void rs_am_destroy(rs_am* am) {
 
 extern "C" int rs_am_enable_timing(rs_am* am, int enable) {
   RS_REQUIRE(am != nullptr, RS_ERR_INVALID, "rs_am_enable_timing: NULL handle");
-  if (enable && !am->timing) {
-    for (int d = 0; d < 2; ++d)
-      for (int l = 0; l < am->L; ++l) {
-        RS_CHECK_CUDA(cudaEventCreate(&am->ev[d][l][0]));
-        RS_CHECK_CUDA(cudaEventCreate(&am->ev[d][l][1]));
-      }
-    am->timing = 1;
-  }
+  am->timing = enable ? 1 : 0;
   return RS_OK;
 }
 
@@ -151,9 +153,17 @@ extern "C" int rs_am_recurrent_ms(rs_am* am, int backward, int layer, float* ms)
   RS_REQUIRE(am && ms && am->timing, RS_ERR_INVALID, "rs_am_recurrent_ms: timing not enabled");
   RS_REQUIRE(layer >= 0 && layer < am->L && (backward == 0 || backward == 1), RS_ERR_INVALID,
              "rs_am_recurrent_ms: bad index");
-  RS_REQUIRE(am->ev_valid[backward][layer], RS_ERR_INVALID, "rs_am_recurrent_ms: kernel has not run");
-  RS_CHECK_CUDA(cudaEventSynchronize(am->ev[backward][layer][1]));
-  RS_CHECK_CUDA(cudaEventElapsedTime(ms, am->ev[backward][layer][0], am->ev[backward][layer][1]));
+  const int used = am->tev_used[backward][layer];
+  RS_REQUIRE(used >= 2, RS_ERR_INVALID, "rs_am_recurrent_ms: kernel has not run");
+  // sum over the (chunk) launches of the last call
+  float total = 0.f;
+  for (int i = 0; i + 1 < used; i += 2) {
+    float part = 0.f;
+    RS_CHECK_CUDA(cudaEventSynchronize(am->tev[backward][layer][i + 1]));
+    RS_CHECK_CUDA(cudaEventElapsedTime(&part, am->tev[backward][layer][i], am->tev[backward][layer][i + 1]));
+    total += part;
+  }
+  *ms = total;
   return RS_OK;
 }
 
@@ -249,6 +259,7 @@ extern "C" int rs_am_forward(rs_am* am, const float* params_d, const float* x_d,
   RS_REQUIRE(T > 0 && T <= am->Tmax, RS_ERR_INVALID, "rs_am_forward: T=%d outside [1,%d]", T, am->Tmax);
   RS_REQUIRE(keep_in > 0.f && keep_in <= 1.f && keep_out > 0.f && keep_out <= 1.f, RS_ERR_INVALID,
              "rs_am_forward: keep probabilities must be in (0,1]");
+  tev_begin(am, 0);
   if (am->use_tc)
     return am_tc_forward(am, params_d, x_d, len_d, T, state_in_d, state_out_d, keep_in, keep_out, seed, logits_d,
                          reserve_d, ws_d, ws_bytes, (cudaStream_t)stream);
@@ -296,9 +307,9 @@ extern "C" int rs_am_forward(rs_am* am, const float* params_d, const float* x_d,
     a.cs = bf.cs[l];
     a.barrier = bf.barrier;
     a.T = T; a.B = B; a.H = H;
-    if (am->timing) RS_CHECK_CUDA(cudaEventRecord(am->ev[0][l][0], st));
+    { int trc = tev_record(am, 0, l, st); if (trc != RS_OK) return trc; }
     if ((rc = lstm_rec_forward(a, st)) != RS_OK) return rc;
-    if (am->timing) { RS_CHECK_CUDA(cudaEventRecord(am->ev[0][l][1], st)); am->ev_valid[0][l] = 1; }
+    { int trc = tev_record(am, 0, l, st); if (trc != RS_OK) return trc; }
     // cell-output dropout, then the next cell's input dropout   (DropoutWrapper, :232-233)
     float* next = (l + 1 < L) ? bf.xin[l + 1] : bf.top;
     if (next == bf.out[l]) continue;   // identity hop, aliased
@@ -323,6 +334,7 @@ extern "C" int rs_am_backward(rs_am* am, const float* params_d, const float* x_d
   RS_REQUIRE(T > 0 && T <= am->Tmax, RS_ERR_INVALID, "rs_am_backward: T=%d outside [1,%d]", T, am->Tmax);
   RS_REQUIRE(keep_in > 0.f && keep_in <= 1.f && keep_out > 0.f && keep_out <= 1.f, RS_ERR_INVALID,
              "rs_am_backward: keep probabilities must be in (0,1]");
+  tev_begin(am, 1);
   if (am->use_tc)
     return am_tc_backward(am, params_d, x_d, len_d, T, keep_in, keep_out, seed, dlogits_d, reserve_d, grads_d, ws_d,
                           ws_bytes, (cudaStream_t)stream);
@@ -367,9 +379,9 @@ extern "C" int rs_am_backward(rs_am* am, const float* params_d, const float* x_d
     a.len = len_d;
     a.barrier = bf.barrier;
     a.T = T; a.B = B; a.H = H;
-    if (am->timing) RS_CHECK_CUDA(cudaEventRecord(am->ev[1][l][0], st));
+    { int trc = tev_record(am, 1, l, st); if (trc != RS_OK) return trc; }
     if ((rc = lstm_rec_backward(a, st)) != RS_OK) return rc;
-    if (am->timing) { RS_CHECK_CUDA(cudaEventRecord(am->ev[1][l][1], st)); am->ev_valid[1][l] = 1; }
+    { int trc = tev_record(am, 1, l, st); if (trc != RS_OK) return trc; }
     const float* dg = bf.gates[l];
     // dK[:H] += xin^T @ dgates ; dK[H:] += hprev^T @ dgates ; db += colsum(dgates)
     if ((rc = sgemm(1, 0, H, 4 * H, TB, bf.xin[l], H, dg, 4 * H, gK, 4 * H, nullptr, 1, st)) != RS_OK) return rc;

@@ -2,22 +2,28 @@
 #pragma once
 #include "common.cuh"
 #include "lstm_rec_tc.cuh"
+#include <vector>
 
 struct rs_am {
   int L, H, F, C, B, Tmax;
   int64_t n_params;
   int64_t off_input_w, off_input_b, off_output_w, off_output_b;
   int64_t off_kernel[64], off_bias[64];
-  // optional per-kernel timing of the recurrent kernels (CUDA events on the launch stream)
+  // optional per-launch timing of the recurrent kernels (CUDA events on the launching stream):
+  // tev[fwd|bwd][layer] holds (start, stop) pairs, one pair per (chunk) launch of the last call
   int timing;
-  cudaEvent_t ev[2][64][2];     // [fwd|bwd][layer][start|stop]
-  int ev_valid[2][64];
+  std::vector<cudaEvent_t> tev[2][64];
+  int tev_used[2][64];          // events recorded by the last call (2 per launch)
   // tensor-core path (H % 64 == 0, B <= 64, weights fit in shared memory); else FFMA kernels
   int use_tc;
-  // side stream for the weight-gradient work that overlaps the next layer's recurrence
-  cudaStream_t side;
-  cudaEvent_t ev_rec[64], ev_side[64], ev_fork;
-  int side_ready;
+  // Streams of the pipelined schedule (lstm_tc.cu): one per layer for the chunked recurrent launches, one for the
+  // chunk GEMMs between layers, one for the weight-gradient work; events come from a pool that is reused every call.
+  cudaStream_t lane[64], gemm_st, side;
+  int streams_ready;
+  std::vector<cudaEvent_t> evpool;
+  size_t ev_next;
+  int chunk;                     // time steps per chunked launch (RS_TC_CHUNK; 0 = one launch per layer)
+  int window;                    // recurrent launches allowed in flight (RS_TC_WINDOW)
   unsigned long long* dbg_fwd;   // optional device buffers [T][8] for kernel timelines (layer 0)
   unsigned long long* dbg_bwd;
   rs::RecTcGeom tc;
@@ -25,6 +31,23 @@ struct rs_am {
 
 
 namespace rs {
+
+// Timed (start, stop) event pairs around the recurrent launches; tev_begin() at the top of a forward / backward call.
+inline void tev_begin(rs_am* am, int dir) {
+  for (int l = 0; l < 64; ++l) am->tev_used[dir][l] = 0;
+}
+inline int tev_record(rs_am* am, int dir, int l, cudaStream_t st) {
+  if (!am->timing) return RS_OK;
+  int& u = am->tev_used[dir][l];
+  if ((size_t)u >= am->tev[dir][l].size()) {
+    cudaEvent_t e;
+    RS_CHECK_CUDA(cudaEventCreate(&e));
+    am->tev[dir][l].push_back(e);
+  }
+  RS_CHECK_CUDA(cudaEventRecord(am->tev[dir][l][u], st));
+  ++u;
+  return RS_OK;
+}
 
 // Tensor-core path (lstm_tc.cu).  Same contract as rs_am_forward / rs_am_backward.
 size_t am_tc_reserve_bytes(const rs_am* am);

@@ -583,7 +583,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   if (warp == 8) tc::tmem_dealloc(tmem, 32);
 }
 
-// wrec[(unit/U)*4U + (unit%U)*4 + g][k] = Wh[k][g*H + unit]; Wh = kernel + H*4H (row-major [H,4H])
+// wrec[(unit/U)*4U + (unit%U)*4 + g][k] = W[k][g*H + unit]; W = one half of the TF kernel (row-major [H,4H])
 __global__ void pack_wrec_kernel(const float* __restrict__ Wh, int H, int U, __nv_bfloat16* __restrict__ hi,
                                  __nv_bfloat16* __restrict__ lo) {
   __shared__ float tile[32][33];
@@ -643,8 +643,8 @@ bool rec_tc_geometry(int H, int B, RecTcGeom* g) {
   return found;
 }
 
-int pack_wrec(const float* kernel, int H, int U, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st) {
-  pack_wrec_kernel<<<dim3(cdiv(4 * H, 32), cdiv(H, 32)), dim3(32, 8), 0, st>>>(kernel + (size_t)H * 4 * H, H, U, hi, lo);
+int pack_wrec(const float* W, int H, int U, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st) {
+  pack_wrec_kernel<<<dim3(cdiv(4 * H, 32), cdiv(H, 32)), dim3(32, 8), 0, st>>>(W, H, U, hi, lo);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }

@@ -41,6 +41,10 @@ struct RecTcFwdArgs {
   unsigned* barrier;
   int T;
   unsigned long long* dbg;         // optional [T][8] globaltimer stamps of CTA 0 (nullptr = off)
+  // Time-chunked launches (TMEM-resident kernels only; 0 / 0 = one launch over all T steps): this launch runs the
+  // steps [t0, t0 + T) of a sequence of Ttot steps.  Every per-step array (gx, h planes, reserve blob) is indexed
+  // by the absolute step; c0 / h0 hold the state after step t0 - 1 (cT / hT may alias them).
+  int t0, Ttot;
 };
 
 int lstm_rec_tc_forward(const RecTcGeom& g, const RecTcFwdArgs& a, cudaStream_t st);
@@ -66,6 +70,12 @@ struct RecTcBwdArgs {
   unsigned* barrier;
   int T;
   unsigned long long* dbg;         // optional [T][8] globaltimer stamps of CTA 0
+  // Time-chunked launches (TMEM-resident kernels only): this launch runs the steps t0 + T - 1 down to t0 of Ttot.
+  // A launch with t0 + T < Ttot starts from dgates_{t0+T} (already in the planes) and from the cell-state gradient
+  // the previous launch left in dc_carry (rec_ts_dc_carry_floats() floats, private layout); every launch with
+  // dc_carry != nullptr leaves its own there.
+  int t0, Ttot;
+  float* dc_carry;
 };
 int lstm_rec_tc_backward(const RecTcBwdGeom& g, const RecTcBwdArgs& a, cudaStream_t st);
 
@@ -74,11 +84,12 @@ int lstm_rec_tc_backward(const RecTcBwdGeom& g, const RecTcBwdArgs& a, cudaStrea
 // Geometry: H % 128 == 0, B <= 64; false -> use the shared-memory-resident kernels above.
 bool rec_ts_geometry(int H, int B, RecTcGeom* g);
 size_t rec_ts_blob_floats(const RecTcGeom& g, int T);
+size_t rec_ts_dc_carry_floats(const RecTcGeom& g);
 int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a, cudaStream_t st);
 int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a, cudaStream_t st);
 
-// Wh (rows H..2H-1 of the TF kernel [2H,4H]) -> wrec planes
-int pack_wrec(const float* kernel, int H, int U, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+// W = one [H,4H] half of the TF kernel [2H,4H] (K for the input half, K + H*4H for Wh) -> wrec planes
+int pack_wrec(const float* W, int H, int U, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 
 // defined in gemm_tc.cu
 int tmap_2d_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols, int ld, int box_rows);

@@ -188,13 +188,14 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     __syncwarp();
     const unsigned per_step = gridDim.x * (unsigned)(Bpad / 8);
     uint32_t git = 0;
-    for (int t = 0; t < T; ++t) {
-      if (t > 0) {
-        wait_counter(a.barrier, per_step * (unsigned)t, p.variant);
+    for (int ti = 0; ti < T; ++ti) {
+      const int t = a.t0 + ti;
+      if (ti > 0) {
+        wait_counter(a.barrier, per_step * (unsigned)ti, p.variant);
         __syncwarp();
         if (!(p.variant & 8)) tc::fence_proxy_async_all();     // other CTAs' generic-proxy stores of h_{t-1} -> TMA reads
       }
-      if (lane == 0) RS_STAMP(a.dbg, t, 0);
+      if (lane == 0) RS_STAMP(a.dbg, ti, 0);
       __syncwarp();
       for (int grp = 0; grp < ngroups; ++grp, ++git) {
         const int s = git % p.slots;
@@ -204,7 +205,7 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         // one box = gkb stacked tiles [kb][plane][Bpad rows][64]; row t*B = slot t = h_{t-1}
         tc::tma_load_4d_warp(sRing + (size_t)s * slot_bytes, &tmH, 0, t * B, 0, grp * gkb, &full_bar[s]);
       }
-      if (lane == 0) RS_STAMP(a.dbg, t, 1);
+      if (lane == 0) RS_STAMP(a.dbg, ti, 1);
       __syncwarp();
     }
   } else if (warp == 9) {
@@ -265,7 +266,8 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     float2* blob = reinterpret_cast<float2*>(a.gates);
     const unsigned nstore = (unsigned)(4 * Bpad);         // 16-byte chunks of the staged h tile
 
-    for (int t = 0; t < T; ++t) {
+    for (int ti = 0; ti < T; ++ti) {
+      const int t = a.t0 + ti;
       // hoisted input projection for this step (independent of the recurrence: issue early)
       float4 gxv[MAXG][2];
 #pragma unroll
@@ -281,9 +283,9 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         }
       }
       float2 keep[MAXG][BLOB_ITEMS];
-      tc::mbar_wait(&tfull_bar, (uint32_t)(t & 1));
+      tc::mbar_wait(&tfull_bar, (uint32_t)(ti & 1));
       tc::tc_fence_after();
-      if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 4);
+      if (threadIdx.x == 0) RS_STAMP(a.dbg, ti, 4);
 #pragma unroll
       for (int gl = 0; gl < MAXG; ++gl) {
         const int gi = hf + 2 * gl;
@@ -349,7 +351,7 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           RS_STAMP(a.dbg, t, 9);
           tc::bulk_wait_all();
           RS_STAMP(a.dbg, t, 10);
-          if (t + 1 < T) red_relaxed_add(a.barrier, (unsigned)(Bpad / 8));
+          if (ti + 1 < T) red_relaxed_add(a.barrier, (unsigned)(Bpad / 8));
         }
       } else if (threadIdx.x < nstore) {
         // publish h_t: 16-byte coalesced stores of the staged tile, one release per storing warp
@@ -363,7 +365,7 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         if (!(p.variant & 1)) tc::fence_proxy_async_all();
         __syncwarp();
         if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 10);
-        if (lane == 0 && t + 1 < T) red_release_add(a.barrier, 1u);
+        if (lane == 0 && ti + 1 < T) red_release_add(a.barrier, 1u);
       }
       if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 6);
       // reserve for backward (not on the critical path of the recurrence)
@@ -425,6 +427,9 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   __nv_bfloat16* sDG = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(sR) + (size_t)CL * TSU * Bpad * 4);
                                                                              // [2 planes][Bpad][4 gates][16 units]
   const uint32_t colD = (uint32_t)(H / 4);
+  const int t1 = a.t0 + T;                                // this launch: steps t1 - 1 down to t0
+  const bool primed = t1 < a.Ttot;                        // dh_{t1-1} comes from dgates_{t1} of the previous launch
+  const int ts_first = primed ? t1 : t1 - 1;              // first dgates step streamed through the tensor core
 
   if (threadIdx.x == 0) {
     tc::mbar_init(&full_bar, 1);
@@ -458,11 +463,13 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     __syncwarp();
     const unsigned per_step = gridDim.x * 8u;
     unsigned epoch = 0;
-    for (int t = T - 1; t >= 1; --t) {        // dh_{t-1} from dgates_t
-      ++epoch;
-      wait_counter(a.barrier, per_step * epoch, p.variant);
-      __syncwarp();
-      if (!(p.variant & 8)) tc::fence_proxy_async_all();
+    for (int t = ts_first; t >= a.t0 + 1; --t) {        // dh_{t-1} from dgates_t
+      if (t < t1) {                                       // dgates_t comes from this launch: grid barrier
+        ++epoch;
+        wait_counter(a.barrier, per_step * epoch, p.variant);
+        __syncwarp();
+        if (!(p.variant & 8)) tc::fence_proxy_async_all();
+      }
       if (lane == 0) RS_STAMP(a.dbg, t, 0);
       __syncwarp();
       tc::mbar_arrive_expect_tx_warp(&full_bar, (uint32_t)nkbs * kb_bytes);
@@ -475,7 +482,7 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const uint64_t dg0 = tc::smem_desc_sw128(tc::smem_u32(sG));
     const uint32_t tmemD = tmem + colD;
     uint32_t n = 0;
-    for (int t = T - 1; t >= 1; --t, ++n) {
+    for (int t = ts_first; t >= a.t0 + 1; --t, ++n) {
       tc::mbar_wait(&full_bar, n & 1);
       tc::tc_fence_after();
       if (lane == 0) RS_STAMP(a.dbg, t, 2);
@@ -509,9 +516,17 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         lenr[gl][k] = ((hf + 2 * gl) < ng && b < B) ? a.len[b] : 0;
         dc[gl][k] = 0.f;
       }
+    float2* carry = reinterpret_cast<float2*>(a.dc_carry);
+    if (primed && carry) {
+#pragma unroll
+      for (int gl = 0; gl < MAXG; ++gl) {
+        const float2 x = carry[(((size_t)j * MAXG + gl) * 8 + warp) * 32 + lane];
+        dc[gl][0] = x.x; dc[gl][1] = x.y;
+      }
+    }
     const unsigned nchunk = (unsigned)(2 * Bpad * 4 * 2);     // 16-byte chunks of the staged dgates tile
-    uint32_t n = 0;
-    for (int t = T - 1; t >= 0; --t, ++n) {
+    uint32_t n = primed ? 1u : 0u;                            // n - 1 = index of the MMA batch this step consumes
+    for (int t = t1 - 1; t >= a.t0; --t, ++n) {
       // operands of the cell backward (independent of the recurrence: issue before waiting)
       float2 it2[MAXG][BLOB_ITEMS], cp2[MAXG];
       float dy[MAXG][2];
@@ -622,7 +637,7 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
           RS_STAMP(a.dbg, t, 11);
           tc::bulk_wait_all();
           RS_STAMP(a.dbg, t, 12);
-          if (t > 0) red_relaxed_add(a.barrier, 8u);
+          if (t > a.t0) red_relaxed_add(a.barrier, 8u);
           RS_STAMP(a.dbg, t, 6);
         }
         continue;
@@ -640,10 +655,15 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       if (!(p.variant & 1)) tc::fence_proxy_async_all();
       __syncwarp();
       if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 12);
-      if (lane == 0 && t > 0) red_release_add(a.barrier, 1u);
+      if (lane == 0 && t > a.t0) red_release_add(a.barrier, 1u);
       if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 6);
       // (the staged tile is rewritten only after the next tfull wait, i.e. after the grid barrier
       //  that needs all eight releases above, each of which follows its warp's reads of the tile)
+    }
+    if (carry) {
+#pragma unroll
+      for (int gl = 0; gl < MAXG; ++gl)
+        carry[(((size_t)j * MAXG + gl) * 8 + warp) * 32 + lane] = make_float2(dc[gl][0], dc[gl][1]);
     }
   }
   tc::tc_fence_before();
@@ -709,13 +729,17 @@ size_t rec_ts_blob_floats(const RecTcGeom& g, int T) {
   return (size_t)T * g.nslice * g.ngl * BLOB_ITEMS * 8 * 32 * 2;
 }
 
-int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a, cudaStream_t st) {
-  RS_REQUIRE(a.T > 0, RS_ERR_INVALID, "lstm_rec_ts_forward: T=%d", a.T);
+size_t rec_ts_dc_carry_floats(const RecTcGeom& g) { return (size_t)g.nslice * MAXG * 8 * 32 * 2; }
+
+int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a_in, cudaStream_t st) {
+  RecTcFwdArgs a = a_in;
+  if (a.Ttot <= 0) { a.Ttot = a.T; a.t0 = 0; }
+  RS_REQUIRE(a.T > 0 && a.t0 >= 0 && a.t0 + a.T <= a.Ttot, RS_ERR_INVALID, "lstm_rec_ts_forward: T=%d t0=%d Ttot=%d", a.T, a.t0, a.Ttot);
   RS_REQUIRE(a.h_ld == 2 * g.H && a.h_lo == a.h_hi + g.H, RS_ERR_INVALID,
              "lstm_rec_ts_forward: h planes must be row-interleaved ([rows][hi H | lo H])");
   CUtensorMap th, ts;
   int rc;
-  const int hrows = (a.T + 1) * g.B;
+  const int hrows = (a.Ttot + 1) * g.B;
   if ((rc = tmap_stacked_bf16(&th, a.h_hi, hrows, g.H, g.Bpad, g.gkb)) != RS_OK) return rc;
   if ((rc = tmap_store3_bf16(&ts, a.h_hi, g.H, 2, hrows, (size_t)g.H * 2, (size_t)2 * g.H * 2, TSU, 2, g.B)) != RS_OK) return rc;
   KFwd p;
@@ -727,24 +751,39 @@ int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a, cudaStream_t 
   p.kb_bytes = 2u * (uint32_t)g.Bpad * 128;
   p.variant = ts_variant();
   RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
-  int dev = 0, per_sm = 0, nsm = 0;
-  RS_CHECK_CUDA(cudaGetDevice(&dev));
-  RS_CHECK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  RS_CHECK_CUDA(cudaFuncSetAttribute(rec_ts_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-  RS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rec_ts_fwd_kernel, NTHREADS, g.smem_bytes));
-  RS_REQUIRE(per_sm * nsm >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_ts_forward: %d CTAs cannot be co-resident", g.nslice);
-  void* kargs[] = {(void*)&th, (void*)&ts, (void*)&p};
-  RS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)rec_ts_fwd_kernel, dim3(g.nslice), dim3(NTHREADS), kargs,
-                                            g.smem_bytes, st));
+  static size_t checked_smem = 0;          // attribute + co-residency check once per shared-memory size
+  static int checked_cap = 0;
+  if (checked_smem != g.smem_bytes) {
+    int per_sm = 0;
+    RS_CHECK_CUDA(cudaFuncSetAttribute(rec_ts_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    RS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rec_ts_fwd_kernel, NTHREADS, g.smem_bytes));
+    checked_cap = per_sm * sm_count();
+    checked_smem = g.smem_bytes;
+  }
+  RS_REQUIRE(checked_cap >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_ts_forward: %d CTAs cannot be co-resident", g.nslice);
+  // A plain launch: the grid barrier is the kernel's own counter, co-residency was checked above (one CTA per SM,
+  // nslice <= SM count), and plain launches of different layers run side by side (RS_TS_COOP=1: cooperative launch).
+  static const bool coop = [] { const char* v = getenv("RS_TS_COOP"); return v && v[0] == '1'; }();
+  if (coop) {
+    void* kargs[] = {(void*)&th, (void*)&ts, (void*)&p};
+    RS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)rec_ts_fwd_kernel, dim3(g.nslice), dim3(NTHREADS), kargs,
+                                              g.smem_bytes, st));
+  } else {
+    rec_ts_fwd_kernel<<<dim3(g.nslice), dim3(NTHREADS), g.smem_bytes, st>>>(th, ts, p);
+    RS_CHECK_CUDA(cudaGetLastError());
+  }
   count_launch();
   return RS_OK;
 }
 
-int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a, cudaStream_t st) {
-  RS_REQUIRE(a.T > 0, RS_ERR_INVALID, "lstm_rec_ts_backward: T=%d", a.T);
+int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStream_t st) {
+  RecTcBwdArgs a = a_in;
+  if (a.Ttot <= 0) { a.Ttot = a.T; a.t0 = 0; }
+  RS_REQUIRE(a.T > 0 && a.t0 >= 0 && a.t0 + a.T <= a.Ttot, RS_ERR_INVALID, "lstm_rec_ts_backward: T=%d t0=%d Ttot=%d", a.T, a.t0, a.Ttot);
+  RS_REQUIRE(a.t0 + a.T == a.Ttot || a.dc_carry, RS_ERR_INVALID, "lstm_rec_ts_backward: a continued launch needs dc_carry");
   CUtensorMap tg;
   int rc;
-  if ((rc = tmap_2d_bf16(&tg, a.dg_hi, a.T * g.B, 4 * g.H, 4 * g.H, g.Bpad)) != RS_OK) return rc;
+  if ((rc = tmap_2d_bf16(&tg, a.dg_hi, a.Ttot * g.B, 4 * g.H, 4 * g.H, g.Bpad)) != RS_OK) return rc;
   KBwd p;
   p.a = a;
   p.H = g.H; p.B = g.B; p.Bpad = g.Bpad; p.nslice = g.nslice; p.nkbs = g.H / 2 / 64; p.ngl = g.ngl;
@@ -755,7 +794,10 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a, cudaStream_t
   size_t smem = (size_t)p.nkbs * g.Bpad * 128 + (size_t)CL * TSU * g.Bpad * 4 + (size_t)2 * g.Bpad * 4 * TSU * 2 + 1024;
   if (smem < 120 * 1024) smem = 120 * 1024;                        // one CTA per SM
   RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
-  RS_CHECK_CUDA(cudaFuncSetAttribute(rec_ts_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t attr_smem = 0;
+  if (attr_smem != smem) {
+    RS_CHECK_CUDA(cudaFuncSetAttribute(rec_ts_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g.nslice);
   cfg.blockDim = dim3(NTHREADS);
@@ -766,13 +808,16 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a, cudaStream_t
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  int nclusters = 0;
-  RS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, rec_ts_bwd_kernel, &cfg));
+  static int nclusters = 0;
+  if (attr_smem != smem) {
+    RS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, rec_ts_bwd_kernel, &cfg));
+    attr_smem = smem;
+  }
   RS_REQUIRE(nclusters * CL >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_ts_backward: %d CTAs cannot be co-resident (%d clusters)",
              g.nslice, nclusters);
   CUtensorMap ts_hi, ts_lo;
-  if ((rc = tmap_store3_bf16(&ts_hi, a.dg_hi, g.H, 4, a.T * g.B, (size_t)g.H * 2, (size_t)4 * g.H * 2, TSU, 4, g.B)) != RS_OK) return rc;
-  if ((rc = tmap_store3_bf16(&ts_lo, a.dg_lo, g.H, 4, a.T * g.B, (size_t)g.H * 2, (size_t)4 * g.H * 2, TSU, 4, g.B)) != RS_OK) return rc;
+  if ((rc = tmap_store3_bf16(&ts_hi, a.dg_hi, g.H, 4, a.Ttot * g.B, (size_t)g.H * 2, (size_t)4 * g.H * 2, TSU, 4, g.B)) != RS_OK) return rc;
+  if ((rc = tmap_store3_bf16(&ts_lo, a.dg_lo, g.H, 4, a.Ttot * g.B, (size_t)g.H * 2, (size_t)4 * g.H * 2, TSU, 4, g.B)) != RS_OK) return rc;
   RS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rec_ts_bwd_kernel, tg, ts_hi, ts_lo, p));
   count_launch();
   return RS_OK;

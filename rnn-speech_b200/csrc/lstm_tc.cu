@@ -33,23 +33,25 @@ inline int up8(int x) { return (x + 7) / 8 * 8; }
 
 struct TcBufs {
   // ---- workspace
-  unsigned* barrier;
-  float* gx;                      // rec layout [T][4H][Bpad]
-  bf16 *wx_hi[64], *wx_lo[64];    // K[:H]^T  [4H][H]
+  unsigned* barrier[64];          // one grid-barrier counter block per layer (layers run concurrently)
+  float* gx[64];                  // rec layout [T][4H][Bpad], per layer
+  bf16 *wx_hi[64], *wx_lo[64];    // K[:H]^T  [4H][H] permuted rows (pack_wrec)
   bf16 *wrec_hi[64], *wrec_lo[64];// [4H][H] permuted rows
   bf16 *wi_hi, *wi_lo;            // w_i^T [H][Fp]
   bf16 *wo_hi, *wo_lo;            // w_o^T [C][H]
+  float* run_state;               // [L,2,B,H] state carried from one chunked launch to the next
   // backward-only workspace
   bf16 *wxs_hi[64], *wxs_lo[64];  // K[:H] as stored [H][4H]
   bf16 *whs_hi[64];               // K[H:] as stored [H][4H] (hi)
   bf16 *wos_hi, *wos_lo;          // w_o as stored [H][Cp]
-  bf16 *dg_hi[2], *dg_lo[2];      // [T*B][4H], ping-pong over layers (the side stream still reads layer l's)
+  bf16 *dg_hi[64], *dg_lo[64];    // [T*B][4H] per layer
   bf16 *dgT_hi, *dgT_lo;          // [4H][TBp]
   bf16 *actT_hi, *actT_lo;        // [H][TBp] transposed activations
   bf16 *dl_hi, *dl_lo;            // dlogits planes [T*B][Cp]
   bf16 *dlT_hi, *dlT_lo;          // [C][TBp]
   bf16 *xT_hi, *xT_lo;            // [F][TBp]
-  float *dcur, *dtmp;             // [T*B][H]
+  float* din[65];                 // [T*B][H]: din[l] = gradient wrt layer l's input, din[L] = wrt the top activations
+  float* dc_carry[64];
   // ---- reserve
   bf16 *x_hi, *x_lo;              // [T*B][Fp]
   bf16 *xin_hi[64], *xin_lo[64];  // [T*B][H]
@@ -65,24 +67,30 @@ void carve(const rs_am* am, void* reserve, void* ws, bool training, TcBufs* b, s
   const size_t TB = (size_t)T * B, TBp = (size_t)up8((int)TB);
   const int Fp = up8(F), Cp = up8(C);
   Bump w(ws);
-  b->barrier = w.take<unsigned>(256);
-  b->gx = w.take<float>((size_t)T * 4 * H * am->tc.Bpad);
   for (int l = 0; l < L; ++l) {
+    b->barrier[l] = w.take<unsigned>(256);
+    b->gx[l] = w.take<float>((size_t)T * 4 * H * am->tc.Bpad);
     b->wx_hi[l] = w.take<bf16>((size_t)4 * H * H); b->wx_lo[l] = w.take<bf16>((size_t)4 * H * H);
     b->wrec_hi[l] = w.take<bf16>((size_t)4 * H * H); b->wrec_lo[l] = w.take<bf16>((size_t)4 * H * H);
-    b->wxs_hi[l] = w.take<bf16>((size_t)4 * H * H); b->wxs_lo[l] = w.take<bf16>((size_t)4 * H * H);
-    b->whs_hi[l] = w.take<bf16>((size_t)4 * H * H);
   }
   b->wi_hi = w.take<bf16>((size_t)H * Fp); b->wi_lo = w.take<bf16>((size_t)H * Fp);
   b->wo_hi = w.take<bf16>((size_t)C * H); b->wo_lo = w.take<bf16>((size_t)C * H);
-  b->wos_hi = w.take<bf16>((size_t)H * Cp); b->wos_lo = w.take<bf16>((size_t)H * Cp);
-  for (int i = 0; i < 2; ++i) { b->dg_hi[i] = w.take<bf16>(TB * 4 * H); b->dg_lo[i] = w.take<bf16>(TB * 4 * H); }
-  b->dgT_hi = w.take<bf16>((size_t)4 * H * TBp); b->dgT_lo = w.take<bf16>((size_t)4 * H * TBp);
-  b->actT_hi = w.take<bf16>((size_t)H * TBp); b->actT_lo = w.take<bf16>((size_t)H * TBp);
-  b->dl_hi = w.take<bf16>(TB * Cp); b->dl_lo = w.take<bf16>(TB * Cp);
-  b->dlT_hi = w.take<bf16>((size_t)C * TBp); b->dlT_lo = w.take<bf16>((size_t)C * TBp);
-  b->xT_hi = w.take<bf16>((size_t)F * TBp); b->xT_lo = w.take<bf16>((size_t)F * TBp);
-  b->dcur = w.take<float>(TB * H); b->dtmp = w.take<float>(TB * H);
+  b->run_state = w.take<float>((size_t)L * 2 * B * H);
+  if (training) {
+    for (int l = 0; l < L; ++l) {
+      b->wxs_hi[l] = w.take<bf16>((size_t)4 * H * H); b->wxs_lo[l] = w.take<bf16>((size_t)4 * H * H);
+      b->whs_hi[l] = w.take<bf16>((size_t)4 * H * H);
+      b->dg_hi[l] = w.take<bf16>(TB * 4 * H); b->dg_lo[l] = w.take<bf16>(TB * 4 * H);
+      b->dc_carry[l] = w.take<float>(am->tc.ts ? rec_ts_dc_carry_floats(am->tc) : 1);
+    }
+    b->wos_hi = w.take<bf16>((size_t)H * Cp); b->wos_lo = w.take<bf16>((size_t)H * Cp);
+    b->dgT_hi = w.take<bf16>((size_t)4 * H * TBp); b->dgT_lo = w.take<bf16>((size_t)4 * H * TBp);
+    b->actT_hi = w.take<bf16>((size_t)H * TBp); b->actT_lo = w.take<bf16>((size_t)H * TBp);
+    b->dl_hi = w.take<bf16>(TB * Cp); b->dl_lo = w.take<bf16>(TB * Cp);
+    b->dlT_hi = w.take<bf16>((size_t)C * TBp); b->dlT_lo = w.take<bf16>((size_t)C * TBp);
+    b->xT_hi = w.take<bf16>((size_t)F * TBp); b->xT_lo = w.take<bf16>((size_t)F * TBp);
+    for (int l = 0; l <= L; ++l) b->din[l] = w.take<float>(TB * H);
+  }
   // activations: in the reserve when training, behind the workspace otherwise
   Bump r(reserve);
   Bump& act = training ? r : w;
@@ -103,24 +111,24 @@ void carve(const rs_am* am, void* reserve, void* ws, bool training, TcBufs* b, s
 
 // planes <- split(dropout(hi + lo)); in == out allowed
 __global__ void dropout_planes_kernel(const bf16* __restrict__ ihi, const bf16* __restrict__ ilo, int cols, int ld_in,
-                                      bf16* __restrict__ ohi, bf16* __restrict__ olo, int64_t n, uint64_t key, uint32_t sa,
-                                      uint32_t thr_a, float inv_a, uint32_t sb, uint32_t thr_b, float inv_b) {
+                                      bf16* __restrict__ ohi, bf16* __restrict__ olo, int64_t n, int64_t i0, uint64_t key,
+                                      uint32_t sa, uint32_t thr_a, float inv_a, uint32_t sb, uint32_t thr_b, float inv_b) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t ii = (ld_in == cols) ? i : (i / cols) * ld_in + (i % cols);
     float v = __bfloat162float(ihi[ii]) + __bfloat162float(ilo[ii]);
-    if (thr_a != 0xffffffffu) v = dropout_keep(key, sa, (uint64_t)i, thr_a) ? v * inv_a : 0.f;
-    if (thr_b != 0xffffffffu) v = dropout_keep(key, sb, (uint64_t)i, thr_b) ? v * inv_b : 0.f;
+    if (thr_a != 0xffffffffu) v = dropout_keep(key, sa, (uint64_t)(i0 + i), thr_a) ? v * inv_a : 0.f;
+    if (thr_b != 0xffffffffu) v = dropout_keep(key, sb, (uint64_t)(i0 + i), thr_b) ? v * inv_b : 0.f;
     bf16 h, l;
     tc::split_bf16(v, h, l);
     ohi[i] = h; olo[i] = l;
   }
 }
-__global__ void dropout_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n, uint64_t key,
+__global__ void dropout_f32_kernel(const float* in, float* out, int64_t n, int64_t i0, uint64_t key,
                                    uint32_t sa, uint32_t thr_a, float inv_a, uint32_t sb, uint32_t thr_b, float inv_b) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = in[i];
-    if (thr_a != 0xffffffffu) v = dropout_keep(key, sa, (uint64_t)i, thr_a) ? v * inv_a : 0.f;
-    if (thr_b != 0xffffffffu) v = dropout_keep(key, sb, (uint64_t)i, thr_b) ? v * inv_b : 0.f;
+    if (thr_a != 0xffffffffu) v = dropout_keep(key, sa, (uint64_t)(i0 + i), thr_a) ? v * inv_a : 0.f;
+    if (thr_b != 0xffffffffu) v = dropout_keep(key, sb, (uint64_t)(i0 + i), thr_b) ? v * inv_b : 0.f;
     out[i] = v;
   }
 }
@@ -130,19 +138,20 @@ inline int ew_grid(int64_t n) {
   const int cap = sm_count() * 16;
   return grid > cap ? cap : grid;
 }
-// in: rows of `cols` elements with row stride ld_in; out: contiguous
-int dropout_planes(const bf16* ihi, const bf16* ilo, int cols, int ld_in, bf16* ohi, bf16* olo, int64_t n, uint64_t seed,
-                   int sa, float keep_a, int sb, float keep_b, cudaStream_t st) {
+// in: rows of `cols` elements with row stride ld_in; out: contiguous.  The pointers address element i0 of the full
+// tensor (chunked calls): the mask of element i0 + i does not depend on how the tensor is cut into calls.
+int dropout_planes(const bf16* ihi, const bf16* ilo, int cols, int ld_in, bf16* ohi, bf16* olo, int64_t n, int64_t i0,
+                   uint64_t seed, int sa, float keep_a, int sb, float keep_b, cudaStream_t st) {
   const uint32_t ta = sa >= 0 ? thr24(keep_a) : 0xffffffffu, tb = sb >= 0 ? thr24(keep_b) : 0xffffffffu;
-  dropout_planes_kernel<<<ew_grid(n), 256, 0, st>>>(ihi, ilo, cols, ld_in, ohi, olo, n, splitmix64(seed), (uint32_t)(sa < 0 ? 0 : sa),
+  dropout_planes_kernel<<<ew_grid(n), 256, 0, st>>>(ihi, ilo, cols, ld_in, ohi, olo, n, i0, splitmix64(seed), (uint32_t)(sa < 0 ? 0 : sa),
                                                     ta, 1.0f / keep_a, (uint32_t)(sb < 0 ? 0 : sb), tb, 1.0f / keep_b);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }
-int dropout_f32(const float* in, float* out, int64_t n, uint64_t seed, int sa, float keep_a, int sb, float keep_b,
+int dropout_f32(const float* in, float* out, int64_t n, int64_t i0, uint64_t seed, int sa, float keep_a, int sb, float keep_b,
                 cudaStream_t st) {
   const uint32_t ta = sa >= 0 ? thr24(keep_a) : 0xffffffffu, tb = sb >= 0 ? thr24(keep_b) : 0xffffffffu;
-  dropout_f32_kernel<<<ew_grid(n), 256, 0, st>>>(in, out, n, splitmix64(seed), (uint32_t)(sa < 0 ? 0 : sa), ta,
+  dropout_f32_kernel<<<ew_grid(n), 256, 0, st>>>(in, out, n, i0, splitmix64(seed), (uint32_t)(sa < 0 ? 0 : sa), ta,
                                                  1.0f / keep_a, (uint32_t)(sb < 0 ? 0 : sb), tb, 1.0f / keep_b);
   RS_CHECK_LAUNCH();
   return RS_OK;
@@ -185,6 +194,49 @@ int split_rows(const float* in, int R, int C, int ld_in, bf16* hi, bf16* lo, int
 
 #define RC(x) do { int _rc = (x); if (_rc != RS_OK) return _rc; } while (0)
 
+// ---- streams and events of the pipelined schedule
+int ensure_streams(rs_am* am) {
+  if (am->streams_ready) return RS_OK;
+  int lo = 0, hi = 0;
+  RS_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // lo = least urgent, hi = most urgent
+  for (int l = 0; l < am->L; ++l) RS_CHECK_CUDA(cudaStreamCreateWithPriority(&am->lane[l], cudaStreamNonBlocking, hi));
+  RS_CHECK_CUDA(cudaStreamCreateWithPriority(&am->gemm_st, cudaStreamNonBlocking, hi));
+  RS_CHECK_CUDA(cudaStreamCreateWithPriority(&am->side, cudaStreamNonBlocking, lo));
+  am->streams_ready = 1;
+  return RS_OK;
+}
+// next event of the per-call pool (created on demand, reused by every call)
+int ev_get(rs_am* am, cudaEvent_t* e) {
+  if (am->ev_next >= am->evpool.size()) {
+    cudaEvent_t n;
+    RS_CHECK_CUDA(cudaEventCreateWithFlags(&n, cudaEventDisableTiming));
+    am->evpool.push_back(n);
+  }
+  *e = am->evpool[am->ev_next++];
+  return RS_OK;
+}
+int ev_record(rs_am* am, cudaEvent_t* e, cudaStream_t st) {
+  RC(ev_get(am, e));
+  RS_CHECK_CUDA(cudaEventRecord(*e, st));
+  return RS_OK;
+}
+
+// The time axis is cut into chunks of am->chunk steps (TMEM-resident kernels only).  Layer l's chunk c needs
+// layer l's chunk c -+ 1 and the GEMM that turns layer l -+ 1's chunk c into its input, so the layers run as a
+// wavefront: `window` recurrent launches in flight (nslice SMs each), the chunk GEMMs on the remaining SMs.
+struct Sched {
+  int Tc, NC, gemm_ctas, side_ctas;
+};
+Sched make_sched(const rs_am* am, int T) {
+  Sched s;
+  s.Tc = (am->tc.ts && am->chunk > 0 && am->chunk < T) ? am->chunk : T;
+  s.NC = cdiv(T, s.Tc);
+  const int spare = sm_count() - (s.NC > 1 ? am->window : 1) * am->tc.nslice;
+  s.gemm_ctas = s.NC > 1 ? (spare > 16 ? spare : 16) : 0;          // 0 = one CTA per SM
+  s.side_ctas = spare > 32 ? spare : 32;
+  return s;
+}
+
 }  // namespace
 
 size_t am_tc_reserve_bytes(const rs_am* am) {
@@ -214,14 +266,15 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
   const size_t state_n = (size_t)L * 2 * B * H;
   if (state_in_d) RS_CHECK_CUDA(cudaMemcpyAsync(bf.state0, state_in_d, state_n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   else RS_CHECK_CUDA(cudaMemsetAsync(bf.state0, 0, state_n * sizeof(float), st));
+  RS_CHECK_CUDA(cudaMemcpyAsync(bf.run_state, bf.state0, state_n * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
   // weight planes (the parameters change every step: repack; 57 MB read at cfg-2)
   RC(split_planes_transposed(params_d + am->off_input_w, F, H, H, bf.wi_hi, bf.wi_lo, Fp, st));      // w_i^T [H][Fp]
   RC(split_planes_transposed(params_d + am->off_output_w, H, C, C, bf.wo_hi, bf.wo_lo, H, st));      // w_o^T [C][H]
   for (int l = 0; l < L; ++l) {
     const float* K = params_d + am->off_kernel[l];
-    RC(split_planes_transposed(K, H, 4 * H, 4 * H, bf.wx_hi[l], bf.wx_lo[l], H, st));               // K[:H]^T [4H][H]
-    RC(pack_wrec(K, H, am->tc.U, bf.wrec_hi[l], bf.wrec_lo[l], st));
+    RC(pack_wrec(K, H, am->tc.U, bf.wx_hi[l], bf.wx_lo[l], st));                                     // K[:H]^T, rows in rec order
+    RC(pack_wrec(K + (size_t)H * 4 * H, H, am->tc.U, bf.wrec_hi[l], bf.wrec_lo[l], st));
   }
   // input dense -> xin[0] planes                                 (models/AcousticModel.py:247-250)
   RC(split_rows(x_d, TB, F, F, bf.x_hi, bf.x_lo, Fp, st));
@@ -230,50 +283,98 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     GemmTcOut o{};
     o.mode = GEMM_OUT_SPLIT; o.Chi = bf.xin_hi[0]; o.Clo = bf.xin_lo[0]; o.ldc = H; o.bias = params_d + am->off_input_b;
     RC(gemm_tc_nt(A, Bm, TB, H, F, 3, o, st));
-    if (drop_in) RC(dropout_planes(bf.xin_hi[0], bf.xin_lo[0], H, H, bf.xin_hi[0], bf.xin_lo[0], nTBH, seed, 0, keep_in, -1, 1.f, st));
+    if (drop_in) RC(dropout_planes(bf.xin_hi[0], bf.xin_lo[0], H, H, bf.xin_hi[0], bf.xin_lo[0], nTBH, 0, seed, 0, keep_in, -1, 1.f, st));
   }
   const int hld = am->tc.ts ? 2 * H : H;            // row stride of the h planes
-  const bf16 *cur_hi = bf.xin_hi[0], *cur_lo = bf.xin_lo[0];
-  int cur_ld = H;
+  // carried-in h -> slot 0 of every layer's h planes
+  for (int l = 0; l < L; ++l)
+    RC(split_rows_strided(bf.state0 + ((size_t)l * 2 + 1) * B * H, B, H, bf.hp_hi[l], bf.hp_lo[l], hld, st));
+
+  // where each layer reads its input / where the stack's output ends up (identity hops alias the h planes)
+  const bf16 *in_hi[65], *in_lo[65];
+  int in_ld[65];
+  bool hop_drop[64];
+  in_hi[0] = bf.xin_hi[0]; in_lo[0] = bf.xin_lo[0]; in_ld[0] = H;
   for (int l = 0; l < L; ++l) {
-    // hoisted input half: gx = xin @ K[:H] + b, written in the recurrent kernel's layout
-    {
-      SplitMat A{cur_hi, cur_lo, TB, H, cur_ld}, Bm{bf.wx_hi[l], bf.wx_lo[l], 4 * H, H, H};
-      GemmTcOut o{};
-      o.mode = GEMM_OUT_REC; o.C = bf.gx; o.bias = params_d + am->off_bias[l];
-      o.recB = B; o.recBpad = am->tc.Bpad; o.recH = H; o.recU = am->tc.U;
-      RC(gemm_tc_nt(A, Bm, TB, 4 * H, H, 3, o, st));
-    }
-    // carried-in h -> slot 0 of the h planes
-    const float* c0 = bf.state0 + ((size_t)l * 2 + 0) * B * H;
-    const float* h0 = bf.state0 + ((size_t)l * 2 + 1) * B * H;
-    RC(split_rows_strided(h0, B, H, bf.hp_hi[l], bf.hp_lo[l], hld, st));
-    RecTcFwdArgs a;
-    a.gx = bf.gx; a.wrec_hi = bf.wrec_hi[l]; a.wrec_lo = bf.wrec_lo[l];
-    a.h_hi = bf.hp_hi[l]; a.h_lo = bf.hp_lo[l]; a.h_ld = hld; a.len = len_d; a.c0 = c0; a.h0 = h0;
-    a.cT = state_out_d ? state_out_d + ((size_t)l * 2 + 0) * B * H : nullptr;
-    a.hT = state_out_d ? state_out_d + ((size_t)l * 2 + 1) * B * H : nullptr;
-    a.gates = bf.gates[l]; a.cs = bf.cs[l]; a.barrier = bf.barrier; a.T = T;
-    a.dbg = (l == 0) ? am->dbg_fwd : nullptr;
-    if (am->timing) RS_CHECK_CUDA(cudaEventRecord(am->ev[0][l][0], st));
-    if (am->tc.ts) RC(lstm_rec_ts_forward(am->tc, a, st));
-    else RC(lstm_rec_tc_forward(am->tc, a, st));
-    if (am->timing) { RS_CHECK_CUDA(cudaEventRecord(am->ev[0][l][1], st)); am->ev_valid[0][l] = 1; }
-    // the hop to the next consumer: identity (alias slots 1..T) or dropout(s)
-    const bf16 *o_hi = bf.hp_hi[l] + (size_t)B * hld, *o_lo = bf.hp_lo[l] + (size_t)B * hld;
     const bool last = l + 1 == L;
-    const bool hop_drop = last ? drop_out : (drop_out || drop_in);
-    if (!hop_drop) {
-      cur_hi = o_hi; cur_lo = o_lo; cur_ld = hld;
-    } else {
-      bf16 *d_hi = last ? bf.top_hi : bf.xin_hi[l + 1], *d_lo = last ? bf.top_lo : bf.xin_lo[l + 1];
-      RC(dropout_planes(o_hi, o_lo, H, hld, d_hi, d_lo, nTBH, seed, drop_out ? 2 * l + 1 : -1, keep_out,
-                        (!last && drop_in) ? 2 * (l + 1) : -1, keep_in, st));
-      cur_hi = d_hi; cur_lo = d_lo; cur_ld = H;
-    }
+    hop_drop[l] = last ? drop_out : (drop_out || drop_in);
+    if (hop_drop[l]) { in_hi[l + 1] = last ? bf.top_hi : bf.xin_hi[l + 1]; in_lo[l + 1] = last ? bf.top_lo : bf.xin_lo[l + 1]; in_ld[l + 1] = H; }
+    else { in_hi[l + 1] = bf.hp_hi[l] + (size_t)B * hld; in_lo[l + 1] = bf.hp_lo[l] + (size_t)B * hld; in_ld[l + 1] = hld; }
   }
+
+  // ---- the recurrent stack as a wavefront over (layer, time chunk)
+  const Sched sc = make_sched(am, T);
+  const int NC = sc.NC;
+  RC(ensure_streams(am));
+  am->ev_next = 0;
+  cudaEvent_t e_fork;
+  RC(ev_record(am, &e_fork, st));
+  for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(am->lane[l], e_fork, 0));
+  RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_fork, 0));
+  std::vector<cudaEvent_t> e_gx((size_t)L * NC), e_out((size_t)L * NC), done;
+
+  // hoisted input half of chunk c: gx = xin @ K[:H] + b, written in the recurrent kernel's layout
+  auto issue_gemm = [&](int l, int c) -> int {
+    const int t0 = c * sc.Tc, n = (t0 + sc.Tc <= T ? sc.Tc : T - t0);
+    if (l > 0) RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_out[(size_t)(l - 1) * NC + c], 0));
+    SplitMat A{bf.wx_hi[l], bf.wx_lo[l], 4 * H, H, H};
+    SplitMat Bm{in_hi[l] + (size_t)t0 * B * in_ld[l], in_lo[l] + (size_t)t0 * B * in_ld[l], n * B, H, in_ld[l]};
+    GemmTcOut o{};
+    o.mode = GEMM_OUT_REC; o.C = bf.gx[l] + (size_t)t0 * 4 * H * am->tc.Bpad; o.bias = params_d + am->off_bias[l];
+    o.recB = B; o.recBpad = am->tc.Bpad; o.recH = H; o.recU = am->tc.U;
+    o.max_ctas = sc.gemm_ctas;
+    RC(gemm_tc_nt(A, Bm, 4 * H, n * B, H, 3, o, am->gemm_st));
+    return ev_record(am, &e_gx[(size_t)l * NC + c], am->gemm_st);
+  };
+  auto issue_rec = [&](int l, int c) -> int {
+    const int t0 = c * sc.Tc, n = (t0 + sc.Tc <= T ? sc.Tc : T - t0);
+    cudaStream_t ls = am->lane[l];
+    RS_CHECK_CUDA(cudaStreamWaitEvent(ls, e_gx[(size_t)l * NC + c], 0));
+    if (NC > 1 && (int)done.size() >= am->window) RS_CHECK_CUDA(cudaStreamWaitEvent(ls, done[done.size() - am->window], 0));
+    float* cst = bf.run_state + ((size_t)l * 2 + 0) * B * H;
+    float* hst = bf.run_state + ((size_t)l * 2 + 1) * B * H;
+    RecTcFwdArgs a{};
+    a.gx = bf.gx[l]; a.wrec_hi = bf.wrec_hi[l]; a.wrec_lo = bf.wrec_lo[l];
+    a.h_hi = bf.hp_hi[l]; a.h_lo = bf.hp_lo[l]; a.h_ld = hld; a.len = len_d;
+    // state after step t0 - 1 in (the call's initial state for the first chunk), after step t0 + n - 1 out
+    a.c0 = c == 0 ? bf.state0 + ((size_t)l * 2 + 0) * B * H : cst;
+    a.h0 = c == 0 ? bf.state0 + ((size_t)l * 2 + 1) * B * H : hst;
+    a.cT = cst; a.hT = hst;
+    a.gates = bf.gates[l]; a.cs = bf.cs[l]; a.barrier = bf.barrier[l];
+    a.T = n; a.t0 = t0; a.Ttot = T;
+    a.dbg = (l == 0 && NC == 1) ? am->dbg_fwd : nullptr;
+    RC(tev_record(am, 0, l, ls));
+    if (am->tc.ts) RC(lstm_rec_ts_forward(am->tc, a, ls));
+    else RC(lstm_rec_tc_forward(am->tc, a, ls));
+    RC(tev_record(am, 0, l, ls));
+    if (hop_drop[l]) {
+      // the hop to the next consumer: dropout(s) of h_t for the steps of this chunk
+      const bool last = l + 1 == L;
+      bf16 *d_hi = (last ? bf.top_hi : bf.xin_hi[l + 1]) + (size_t)t0 * B * H, *d_lo = (last ? bf.top_lo : bf.xin_lo[l + 1]) + (size_t)t0 * B * H;
+      const bf16 *o_hi = bf.hp_hi[l] + (size_t)(t0 + 1) * B * hld, *o_lo = bf.hp_lo[l] + (size_t)(t0 + 1) * B * hld;
+      RC(dropout_planes(o_hi, o_lo, H, hld, d_hi, d_lo, (int64_t)n * B * H, (int64_t)t0 * B * H, seed, drop_out ? 2 * l + 1 : -1,
+                        keep_out, (!last && drop_in) ? 2 * (l + 1) : -1, keep_in, ls));
+    }
+    cudaEvent_t e;
+    RC(ev_record(am, &e, ls));
+    e_out[(size_t)l * NC + c] = e;
+    done.push_back(e);
+    return RS_OK;
+  };
+  tev_begin(am, 0);
+  for (int c = 0; c < NC; ++c) RC(issue_gemm(0, c));               // layer 0's input is complete: no dependencies
+  for (int d = 0; d < NC + L - 1; ++d)
+    for (int l = 0; l < L; ++l) {
+      const int c = d - l;
+      if (c < 0 || c >= NC) continue;
+      if (l > 0) RC(issue_gemm(l, c));
+      RC(issue_rec(l, c));
+    }
+  for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(st, e_out[(size_t)l * NC + NC - 1], 0));
+  if (state_out_d) RS_CHECK_CUDA(cudaMemcpyAsync(state_out_d, bf.run_state, state_n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
   // output dense                                               (models/AcousticModel.py:308-309)
-  SplitMat A{cur_hi, cur_lo, TB, H, cur_ld}, Bm{bf.wo_hi, bf.wo_lo, C, H, H};
+  SplitMat A{in_hi[L], in_lo[L], TB, H, in_ld[L]}, Bm{bf.wo_hi, bf.wo_lo, C, H, H};
   GemmTcOut o{};
   o.mode = GEMM_OUT_F32; o.C = logits_d; o.ldc = C; o.bias = params_d + am->off_output_b;
   return gemm_tc_nt(A, Bm, TB, C, H, 3, o, st);
@@ -304,93 +405,102 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   }
   // where forward left each layer's input / the top activations
   const int hld = am->tc.ts ? 2 * H : H;
-  const bf16 *xin_hi[64], *xin_lo[64], *top_hi, *top_lo;
-  int xin_ld[64], top_ld = H;
-  xin_hi[0] = bf.xin_hi[0]; xin_lo[0] = bf.xin_lo[0]; xin_ld[0] = H;
+  const bf16 *in_hi[65], *in_lo[65];
+  int in_ld[65];
+  bool hop_drop[64];
+  in_hi[0] = bf.xin_hi[0]; in_lo[0] = bf.xin_lo[0]; in_ld[0] = H;
   for (int l = 0; l < L; ++l) {
     const bool last = l + 1 == L;
-    const bool hop_drop = last ? drop_out : (drop_out || drop_in);
-    const bf16 *o_hi = bf.hp_hi[l] + (size_t)B * hld, *o_lo = bf.hp_lo[l] + (size_t)B * hld;
-    const bf16* n_hi = hop_drop ? (last ? bf.top_hi : bf.xin_hi[l + 1]) : o_hi;
-    const bf16* n_lo = hop_drop ? (last ? bf.top_lo : bf.xin_lo[l + 1]) : o_lo;
-    const int n_ld = hop_drop ? H : hld;
-    if (last) { top_hi = n_hi; top_lo = n_lo; top_ld = n_ld; } else { xin_hi[l + 1] = n_hi; xin_lo[l + 1] = n_lo; xin_ld[l + 1] = n_ld; }
+    hop_drop[l] = last ? drop_out : (drop_out || drop_in);
+    if (hop_drop[l]) { in_hi[l + 1] = last ? bf.top_hi : bf.xin_hi[l + 1]; in_lo[l + 1] = last ? bf.top_lo : bf.xin_lo[l + 1]; in_ld[l + 1] = H; }
+    else { in_hi[l + 1] = bf.hp_hi[l] + (size_t)B * hld; in_lo[l + 1] = bf.hp_lo[l] + (size_t)B * hld; in_ld[l + 1] = hld; }
   }
 
   // ---- output dense: dW_o += top^T dlogits, db_o += colsum, dtop = dlogits w_o^T
   RC(split_rows(dlogits_d, TB, C, C, bf.dl_hi, bf.dl_lo, Cp, st));
   RC(split_planes_transposed(dlogits_d, TB, C, C, bf.dlT_hi, bf.dlT_lo, TBp, st));                  // [C][TBp]
-  RC(transpose_bf16(top_hi, TB, H, top_ld, bf.actT_hi, TBp, st));
-  RC(transpose_bf16(top_lo, TB, H, top_ld, bf.actT_lo, TBp, st));
-  {
-    SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp}, Bm{bf.dlT_hi, bf.dlT_lo, C, TB, TBp};
-    GemmTcOut o{};
-    o.mode = GEMM_OUT_F32; o.C = grads_d + am->off_output_w; o.ldc = C; o.accumulate = 1;
-    RC(gemm_tc_nt(A, Bm, H, C, TB, 3, o, st));
-    RC(rowsum_planes(bf.dlT_hi, bf.dlT_lo, C, TB, TBp, grads_d + am->off_output_b, 1, st));
-  }
   {
     SplitMat A{bf.dl_hi, bf.dl_lo, TB, C, Cp}, Bm{bf.wos_hi, bf.wos_lo, H, C, Cp};
     GemmTcOut o{};
-    o.mode = GEMM_OUT_F32; o.C = bf.dcur; o.ldc = H;
+    o.mode = GEMM_OUT_F32; o.C = bf.din[L]; o.ldc = H;
     RC(gemm_tc_nt(A, Bm, TB, H, C, 3, o, st));
   }
-  // Weight-gradient work (transposes, dK GEMMs, bias sums) is off the critical path: it runs on
-  // a side stream, on the SMs the 48-CTA recurrent kernel of the next layer leaves idle.
-  if (!am->side_ready) {
-    RS_CHECK_CUDA(cudaStreamCreateWithFlags(&am->side, cudaStreamNonBlocking));
-    for (int l = 0; l < L; ++l) {
-      RS_CHECK_CUDA(cudaEventCreateWithFlags(&am->ev_rec[l], cudaEventDisableTiming));
-      RS_CHECK_CUDA(cudaEventCreateWithFlags(&am->ev_side[l], cudaEventDisableTiming));
-    }
-    RS_CHECK_CUDA(cudaEventCreateWithFlags(&am->ev_fork, cudaEventDisableTiming));
-    am->side_ready = 1;
-  }
+  const Sched sc = make_sched(am, T);
+  const int NC = sc.NC;
+  RC(ensure_streams(am));
+  am->ev_next = 0;
   cudaStream_t side = am->side;
-  const int side_ctas = sm_count() - bg.nslice > 16 ? sm_count() - bg.nslice : 16;
-  RS_CHECK_CUDA(cudaEventRecord(am->ev_fork, st));
-  RS_CHECK_CUDA(cudaStreamWaitEvent(side, am->ev_fork, 0));
-  for (int l = L - 1; l >= 0; --l) {
-    const bool last = l + 1 == L;
-    const bool hop_drop = last ? drop_out : (drop_out || drop_in);
-    const float* dout = bf.dcur;
-    if (hop_drop) {
-      RC(dropout_f32(bf.dcur, bf.dtmp, nTBH, seed, drop_out ? 2 * l + 1 : -1, keep_out,
-                     (!last && drop_in) ? 2 * (l + 1) : -1, keep_in, st));
-      dout = bf.dtmp;
+  cudaEvent_t e_fork;
+  RC(ev_record(am, &e_fork, st));
+  for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(am->lane[l], e_fork, 0));
+  RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_fork, 0));
+  RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_fork, 0));
+  // Weight-gradient work (transposes, dK GEMMs, bias sums) is off the critical path: it runs on the side stream,
+  // on the SMs the recurrent launches leave idle.  First the output dense's.
+  RC(transpose_bf16(in_hi[L], TB, H, in_ld[L], bf.actT_hi, TBp, side));
+  RC(transpose_bf16(in_lo[L], TB, H, in_ld[L], bf.actT_lo, TBp, side));
+  {
+    SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp}, Bm{bf.dlT_hi, bf.dlT_lo, C, TB, TBp};
+    GemmTcOut o{};
+    o.mode = GEMM_OUT_F32; o.C = grads_d + am->off_output_w; o.ldc = C; o.accumulate = 1; o.max_ctas = sc.side_ctas;
+    RC(gemm_tc_nt(A, Bm, H, C, TB, 3, o, side));
+    RC(rowsum_planes(bf.dlT_hi, bf.dlT_lo, C, TB, TBp, grads_d + am->off_output_b, 1, side));
+  }
+
+  std::vector<cudaEvent_t> e_rec((size_t)L * NC), e_dx((size_t)L * NC), done;
+  auto issue_rec = [&](int l, int c) -> int {
+    const int t0 = c * sc.Tc, n = (t0 + sc.Tc <= T ? sc.Tc : T - t0);
+    cudaStream_t ls = am->lane[l];
+    if (l + 1 < L) RS_CHECK_CUDA(cudaStreamWaitEvent(ls, e_dx[(size_t)(l + 1) * NC + c], 0));
+    // gradient wrt out_t of this layer: through the hop's dropout mask(s), in place
+    float* dout = bf.din[l + 1];
+    if (hop_drop[l]) {
+      const bool last = l + 1 == L;
+      float* dchunk = dout + (size_t)t0 * B * H;
+      RC(dropout_f32(dchunk, dchunk, (int64_t)n * B * H, (int64_t)t0 * B * H, seed, drop_out ? 2 * l + 1 : -1, keep_out,
+                     (!last && drop_in) ? 2 * (l + 1) : -1, keep_in, ls));
     }
-    const int set = l & 1;
-    // this dg set was last read by the side work of layer l+2
-    if (l + 2 < L) RS_CHECK_CUDA(cudaStreamWaitEvent(st, am->ev_side[l + 2], 0));
-    RecTcBwdArgs a;
+    if (NC > 1 && (int)done.size() >= am->window) RS_CHECK_CUDA(cudaStreamWaitEvent(ls, done[done.size() - am->window], 0));
+    RecTcBwdArgs a{};
     a.dout = dout; a.gates = bf.gates[l]; a.cs = bf.cs[l];
     a.c0 = bf.state0 + ((size_t)l * 2 + 0) * B * H;
-    a.wh_hi = bf.whs_hi[l]; a.dg_hi = bf.dg_hi[set]; a.dg_lo = bf.dg_lo[set]; a.len = len_d; a.barrier = bf.barrier; a.T = T;
-    a.dbg = (l == 0) ? am->dbg_bwd : nullptr;
-    if (am->timing) RS_CHECK_CUDA(cudaEventRecord(am->ev[1][l][0], st));
-    if (am->tc.ts) RC(lstm_rec_ts_backward(am->tc, a, st));
-    else RC(lstm_rec_tc_backward(bg, a, st));
-    if (am->timing) { RS_CHECK_CUDA(cudaEventRecord(am->ev[1][l][1], st)); am->ev_valid[1][l] = 1; }
-    RS_CHECK_CUDA(cudaEventRecord(am->ev_rec[l], st));
-    // ---- critical path: dxin = dg @ K[:H]^T feeds the next layer's recurrence
-    {
-      SplitMat A{bf.dg_hi[set], bf.dg_lo[set], TB, 4 * H, 4 * H}, Bm{bf.wxs_hi[l], bf.wxs_lo[l], H, 4 * H, 4 * H};
-      GemmTcOut o{};
-      o.mode = GEMM_OUT_F32; o.C = bf.dcur; o.ldc = H;
-      RC(gemm_tc_nt(A, Bm, TB, H, 4 * H, 3, o, st));
-    }
-    // ---- side stream: dK[:H] += xin^T dg ; dK[H:] += hprev^T dg ; db += colsum(dg)
-    RS_CHECK_CUDA(cudaStreamWaitEvent(side, am->ev_rec[l], 0));
-    RC(transpose_bf16(bf.dg_hi[set], TB, 4 * H, 4 * H, bf.dgT_hi, TBp, side));
-    RC(transpose_bf16(bf.dg_lo[set], TB, 4 * H, 4 * H, bf.dgT_lo, TBp, side));
+    a.wh_hi = bf.whs_hi[l]; a.dg_hi = bf.dg_hi[l]; a.dg_lo = bf.dg_lo[l]; a.len = len_d; a.barrier = bf.barrier[l];
+    a.T = n; a.t0 = t0; a.Ttot = T; a.dc_carry = NC > 1 ? bf.dc_carry[l] : nullptr;
+    a.dbg = (l == 0 && NC == 1) ? am->dbg_bwd : nullptr;
+    RC(tev_record(am, 1, l, ls));
+    if (am->tc.ts) RC(lstm_rec_ts_backward(am->tc, a, ls));
+    else RC(lstm_rec_tc_backward(bg, a, ls));
+    RC(tev_record(am, 1, l, ls));
+    cudaEvent_t e;
+    RC(ev_record(am, &e, ls));
+    e_rec[(size_t)l * NC + c] = e;
+    done.push_back(e);
+    return RS_OK;
+  };
+  // critical path between layers: din[l] = dg @ K[:H]^T for the steps of chunk c
+  auto issue_dx = [&](int l, int c) -> int {
+    const int t0 = c * sc.Tc, n = (t0 + sc.Tc <= T ? sc.Tc : T - t0);
+    RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_rec[(size_t)l * NC + c], 0));
+    SplitMat A{bf.dg_hi[l] + (size_t)t0 * B * 4 * H, bf.dg_lo[l] + (size_t)t0 * B * 4 * H, n * B, 4 * H, 4 * H};
+    SplitMat Bm{bf.wxs_hi[l], bf.wxs_lo[l], H, 4 * H, 4 * H};
+    GemmTcOut o{};
+    o.mode = GEMM_OUT_F32; o.C = bf.din[l] + (size_t)t0 * B * H; o.ldc = H; o.max_ctas = sc.gemm_ctas;
+    RC(gemm_tc_nt(A, Bm, n * B, H, 4 * H, 3, o, am->gemm_st));
+    return ev_record(am, &e_dx[(size_t)l * NC + c], am->gemm_st);
+  };
+  // side stream: dK[:H] += xin^T dg ; dK[H:] += hprev^T dg ; db += colsum(dg), once the layer's dgates are complete
+  auto issue_side = [&](int l) -> int {
+    RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_rec[(size_t)l * NC + 0], 0));
+    RC(transpose_bf16(bf.dg_hi[l], TB, 4 * H, 4 * H, bf.dgT_hi, TBp, side));
+    RC(transpose_bf16(bf.dg_lo[l], TB, 4 * H, 4 * H, bf.dgT_lo, TBp, side));
     SplitMat G{bf.dgT_hi, bf.dgT_lo, 4 * H, TB, TBp};
     float* gK = grads_d + am->off_kernel[l];
     {
-      RC(transpose_bf16(xin_hi[l], TB, H, xin_ld[l], bf.actT_hi, TBp, side));
-      RC(transpose_bf16(xin_lo[l], TB, H, xin_ld[l], bf.actT_lo, TBp, side));
+      RC(transpose_bf16(in_hi[l], TB, H, in_ld[l], bf.actT_hi, TBp, side));
+      RC(transpose_bf16(in_lo[l], TB, H, in_ld[l], bf.actT_lo, TBp, side));
       SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp};
       GemmTcOut o{};
-      o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = side_ctas;
+      o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas;
       RC(gemm_tc_nt(A, G, H, 4 * H, TB, 3, o, side));
     }
     {
@@ -398,20 +508,30 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
       RC(transpose_bf16(bf.hp_lo[l], TB, H, hld, bf.actT_lo, TBp, side));
       SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp};
       GemmTcOut o{};
-      o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = side_ctas;
+      o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas;
       RC(gemm_tc_nt(A, G, H, 4 * H, TB, 3, o, side));
     }
-    RC(rowsum_planes(bf.dgT_hi, bf.dgT_lo, 4 * H, TB, TBp, grads_d + am->off_bias[l], 1, side));
-    RS_CHECK_CUDA(cudaEventRecord(am->ev_side[l], side));
-  }
+    return rowsum_planes(bf.dgT_hi, bf.dgT_lo, 4 * H, TB, TBp, grads_d + am->off_bias[l], 1, side);
+  };
+  tev_begin(am, 1);
+  for (int d = 0; d < NC + L - 1; ++d)
+    for (int l = L - 1; l >= 0; --l) {
+      const int c = NC - 1 - (d - (L - 1 - l));
+      if (c < 0 || c >= NC) continue;
+      RC(issue_rec(l, c));
+      RC(issue_dx(l, c));
+      if (c == 0) RC(issue_side(l));
+    }
   // join: the input-dense gradient below reuses actT, and the caller's stream owns grads_d afterwards
-  for (int l = 0; l < L && l < 2; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(st, am->ev_side[l], 0));
+  cudaEvent_t e_side, e_gemm;
+  RC(ev_record(am, &e_side, side));
+  RC(ev_record(am, &e_gemm, am->gemm_st));
+  RS_CHECK_CUDA(cudaStreamWaitEvent(st, e_side, 0));
+  RS_CHECK_CUDA(cudaStreamWaitEvent(st, e_gemm, 0));
+  for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(st, e_rec[(size_t)l * NC + 0], 0));
   // through layer 0's input dropout, then the input dense: dw_i += x^T drnn, db_i += colsum
-  const float* drnn = bf.dcur;
-  if (drop_in) {
-    RC(dropout_f32(bf.dcur, bf.dtmp, nTBH, seed, 0, keep_in, -1, 1.f, st));
-    drnn = bf.dtmp;
-  }
+  float* drnn = bf.din[0];
+  if (drop_in) RC(dropout_f32(drnn, drnn, nTBH, 0, seed, 0, keep_in, -1, 1.f, st));
   RC(split_planes_transposed(drnn, TB, H, H, bf.actT_hi, bf.actT_lo, TBp, st));                     // [H][TBp]
   RC(transpose_bf16(bf.x_hi, TB, F, Fp, bf.xT_hi, TBp, st));
   RC(transpose_bf16(bf.x_lo, TB, F, Fp, bf.xT_lo, TBp, st));

@@ -155,3 +155,34 @@ def test_cfg2_shape_forward_against_oracle(pkg, cuda):
           % (err, rel.max(), ties, int(lens.sum())))
     assert err < 1e-3
     assert rel.max() < 1e-3
+
+
+@pytest.mark.parametrize("L,H,B,T,chunk", [(3, 256, 8, 150, 32), (2, 128, 16, 97, 20)])
+def test_time_chunked_wavefront_is_bitwise_the_single_launch_schedule(pkg, cuda, monkeypatch, L, H, B, T, chunk):
+    """The pipelined schedule (time chunks, layers as a wavefront on several streams) only reorders launches:
+    logits, carried state and gradients must be bit-identical to one launch per layer (RS_TC_CHUNK=0), with
+    dropout, ragged lengths and a carried-in state."""
+    F, C = 40, 30
+    rng = np.random.default_rng(5)
+    flat = model.flatten(model.init_params(L, H, F, C, seed=6), L, H, F, C)
+    x = _dev(rng.standard_normal((T, B, F)), cuda, np.float32)
+    lens_np = rng.integers(T // 3, T + 1, size=B).astype(np.int32)
+    lens_np[0] = T
+    lens = _dev(lens_np, cuda, np.int32)
+    st0 = _dev(0.1 * rng.standard_normal((L, 2, B, H)), cuda, np.float32)
+    dl = _dev(rng.standard_normal((T, B, C)) * (np.arange(T)[:, None, None] < lens_np[None, :, None]), cuda, np.float32)
+    out = []
+    for ch in (0, chunk):
+        monkeypatch.setenv("RS_TC_CHUNK", str(ch))
+        m = _build(pkg, cuda, L, H, F, C, B, T, flat, training=True, ki=0.8, ko=0.5)
+        assert m.uses_tensor_cores
+        m.rnn_state.copy_(st0)
+        logits = m.forward(x, lens, training=True)
+        m.grads.zero_()
+        m.backward(x, lens, dl)
+        torch.cuda.synchronize()
+        out.append((logits.clone(), m.rnn_state.clone(), m.grads.clone()))
+    assert torch.equal(out[0][0], out[1][0]), "logits differ"
+    assert torch.equal(out[0][1], out[1][1]), "carried state differs"
+    assert torch.equal(out[0][2], out[1][2]), "gradients differ"
+    assert bool(torch.isfinite(out[1][2]).all())

@@ -225,6 +225,7 @@ def rec_diag():
     lens[1::4] = rng.integers(T // 2, T, size=len(lens[1::4]))
     if os.environ.get("RS_TS_GKB"):
         print("RS_TS_GKB =", os.environ["RS_TS_GKB"])
+    os.environ.setdefault("RS_TC_CHUNK", "0")          # timelines are stamped by single-launch kernels only
     m = rs.AcousticModel(L, H, B, 1000, 600, F, False, C, device=dev)
     m.create_training_rnn(1.0, 1.0, 1, 3e-4, 0.33)
     m.load_flat_params(flat)
