@@ -128,11 +128,14 @@ int rs_am_forward(rs_am* am, const float* params_d, const float* x_d, const int3
                   const float* state_in_d, float* state_out_d,
                   float keep_in, float keep_out, uint64_t seed,
                   float* logits_d, void* reserve_d, void* ws_d, size_t ws_bytes, void* stream);
-/* Measurement hooks: when enabled, CUDA events are recorded on the launch stream around
- * each recurrent kernel; rs_am_recurrent_ms returns the last duration (synchronises on
- * that event only).  backward = 0 | 1. */
+/* Measurement hooks: when enabled, CUDA events are recorded on the launching stream around
+ * each recurrent kernel launch (one per layer, or one per time chunk of a layer in the
+ * pipelined schedule).  rs_am_recurrent_ms returns the summed duration of a layer's launches
+ * in the last call; rs_am_recurrent_trace writes (start, stop) of each launch in ms after the
+ * top of that call and returns how many launches it wrote.  backward = 0 | 1. */
 int rs_am_enable_timing(rs_am* am, int enable);
 int rs_am_recurrent_ms(rs_am* am, int backward, int layer, float* ms);
+int rs_am_recurrent_trace(rs_am* am, int backward, int layer, float* start_stop_ms, int max_launches);
 /* Debug: %globaltimer stamps [T][8] (uint64) of CTA 0 of the layer-0 recurrent kernels. */
 int rs_am_set_debug_timeline(rs_am* am, void* fwd_d, void* bwd_d);
 /* keep_in / keep_out / seed must repeat the values given to the matching forward

@@ -43,6 +43,7 @@ SIGNATURES = {
     "rs_am_enable_timing": (c_int, [c_void_p, c_int]),
     "rs_am_set_debug_timeline": (c_int, [c_void_p, c_void_p, c_void_p]),
     "rs_am_recurrent_ms": (c_int, [c_void_p, c_int, c_int, POINTER(c_float)]),
+    "rs_am_recurrent_trace": (c_int, [c_void_p, c_int, c_int, POINTER(c_float), c_int]),
     "rs_fbank_workspace_bytes": (c_size_t, [c_int, c_int64, c_int]),
     "rs_fbank_num_frames": (c_int64, [c_int64, c_int]),
     "rs_fbank_tables_host": (c_int, [c_int, POINTER(c_float), POINTER(c_float), POINTER(c_int), POINTER(c_int)]),

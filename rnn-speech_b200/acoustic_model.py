@@ -384,6 +384,19 @@ class AcousticModel(object):
                 out[d].append(ms.value)
         return out
 
+    def recurrent_trace(self, max_launches=256):
+        """[direction][layer] -> list of (start_ms, stop_ms) of every recurrent launch of the last step,
+        measured from the top of the forward / backward call (the pipelined schedule's timeline)."""
+        out = ([], [])
+        buf = (_lib.ctypes.c_float * (2 * max_launches))()
+        for d in (0, 1):
+            for l in range(self.num_layers):
+                n = _lib.raw("rs_am_recurrent_trace")(self._handle, d, l, buf, max_launches)
+                if n < 0:
+                    _lib.check(n)
+                out[d].append([(buf[2 * i], buf[2 * i + 1]) for i in range(n)])
+        return out
+
     # ------------------------------------------------------- step protocol
     def start_batch(self, session=None, is_training=True, run_options=None, run_metadata=None):
         """models/AcousticModel.py:662-670"""

@@ -9,16 +9,23 @@
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace rs {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int STAGES = 3;
+// Output tile 128 x BN, BN = 256 or 128.  A tcgen05.mma with both operands in shared memory reads
+// (128 + BN) x 16 bf16 per instruction; at BN = 128 that is 128 B per clock -- all of the shared-memory
+// bandwidth -- so the 128-wide tile cannot reach the tensor pipe's rate and the 256-wide one (96 B per
+// clock) is the default.  BN = 128 (3 stages) stays for narrow outputs.
+constexpr int BM = 128, BK = 64;
 constexpr int TILE_A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int TILE_B_BYTES = BN * BK * 2;   // 16 KB
-constexpr int STAGE_BYTES = 2 * TILE_A_BYTES + 2 * TILE_B_BYTES;
 constexpr int NTHREADS = 256;
+template <int BN> struct Cfg {
+  static constexpr int STAGES = BN == 256 ? 2 : 3;
+  static constexpr int TILE_B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * TILE_A_BYTES + 2 * TILE_B_BYTES;
+};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -40,9 +47,11 @@ struct KParams {
   GemmTcOut out;
 };
 
+template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, KParams p) {
+  constexpr int STAGES = Cfg<BN>::STAGES, TILE_B_BYTES = Cfg<BN>::TILE_B_BYTES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
@@ -359,10 +368,11 @@ int tmap_stacked_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols
   return RS_OK;
 }
 
-int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
-               cudaStream_t st) {
-  if (M <= 0 || N <= 0) return RS_OK;
-  RS_REQUIRE(K > 0, RS_ERR_INVALID, "gemm_tc_nt: K=%d", K);
+namespace {
+
+template <int BN>
+int gemm_launch(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
+                cudaStream_t st) {
   // bf16x3 degrades gracefully to the planes that exist: hi*hi (+ hi*B_lo) (+ A_lo*hi)
   products = (products == 3 ? ((B.lo ? 1 : 0) | (A.lo ? 2 : 0)) : 0);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -380,11 +390,26 @@ int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int pr
   int grid = sm_count();
   if (out.max_ctas > 0 && grid > out.max_ctas) grid = out.max_ctas;
   if (grid > ntiles) grid = ntiles;
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-  RS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gemm_tc_kernel<<<grid, NTHREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  const size_t smem = (size_t)Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    RS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  gemm_tc_kernel<BN><<<grid, NTHREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   RS_CHECK_LAUNCH();
   return RS_OK;
+}
+
+}  // namespace
+
+int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
+               cudaStream_t st) {
+  if (M <= 0 || N <= 0) return RS_OK;
+  RS_REQUIRE(K > 0, RS_ERR_INVALID, "gemm_tc_nt: K=%d", K);
+  static const int force_bn = [] { const char* v = getenv("RS_GEMM_BN"); return v ? atoi(v) : 0; }();
+  const bool wide = force_bn ? force_bn == 256 : N > 128;
+  return wide ? gemm_launch<256>(A, B, M, N, K, products, out, st) : gemm_launch<128>(A, B, M, N, K, products, out, st);
 }
 
 int split_planes(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t st) {

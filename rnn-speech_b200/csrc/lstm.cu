@@ -96,6 +96,7 @@ extern "C" int rs_am_create(rs_am** out, int num_layers, int hidden_size, int in
   am->timing = 0;
   am->dbg_fwd = am->dbg_bwd = nullptr;
   am->streams_ready = 0;
+  am->tev_base_ready = 0;
   am->ev_next = 0;
   {
     const char* v = getenv("RS_TC_CHUNK");
@@ -126,10 +127,12 @@ extern "C" void rs_am_destroy(rs_am* am) {
     for (int l = 0; l < 64; ++l)
       for (cudaEvent_t e : am->tev[d][l]) cudaEventDestroy(e);
   for (cudaEvent_t e : am->evpool) cudaEventDestroy(e);
+  if (am->tev_base_ready) { cudaEventDestroy(am->tev_base[0]); cudaEventDestroy(am->tev_base[1]); }
   if (am->streams_ready) {
     for (int l = 0; l < am->L; ++l) cudaStreamDestroy(am->lane[l]);
     cudaStreamDestroy(am->gemm_st);
     cudaStreamDestroy(am->side);
+    cudaStreamDestroy(am->tr_st);
   }
   delete am;
 }
@@ -165,6 +168,21 @@ extern "C" int rs_am_recurrent_ms(rs_am* am, int backward, int layer, float* ms)
   }
   *ms = total;
   return RS_OK;
+}
+
+// (start, stop) of every recurrent launch of the last call, in ms after the top of that call; returns the number
+// of launches written (<= max_launches) or a negative error.
+extern "C" int rs_am_recurrent_trace(rs_am* am, int backward, int layer, float* start_stop_ms, int max_launches) {
+  RS_REQUIRE(am && start_stop_ms && am->timing && am->tev_base_ready, RS_ERR_INVALID, "rs_am_recurrent_trace: timing not enabled");
+  RS_REQUIRE(layer >= 0 && layer < am->L && (backward == 0 || backward == 1), RS_ERR_INVALID, "rs_am_recurrent_trace: bad index");
+  const int used = am->tev_used[backward][layer];
+  int n = 0;
+  for (int i = 0; i + 1 < used && n < max_launches; i += 2, ++n) {
+    RS_CHECK_CUDA(cudaEventSynchronize(am->tev[backward][layer][i + 1]));
+    RS_CHECK_CUDA(cudaEventElapsedTime(&start_stop_ms[2 * n], am->tev_base[backward], am->tev[backward][layer][i]));
+    RS_CHECK_CUDA(cudaEventElapsedTime(&start_stop_ms[2 * n + 1], am->tev_base[backward], am->tev[backward][layer][i + 1]));
+  }
+  return n;
 }
 
 extern "C" int64_t rs_am_param_count(const rs_am* am) { return am ? am->n_params : -1; }
@@ -259,7 +277,7 @@ extern "C" int rs_am_forward(rs_am* am, const float* params_d, const float* x_d,
   RS_REQUIRE(T > 0 && T <= am->Tmax, RS_ERR_INVALID, "rs_am_forward: T=%d outside [1,%d]", T, am->Tmax);
   RS_REQUIRE(keep_in > 0.f && keep_in <= 1.f && keep_out > 0.f && keep_out <= 1.f, RS_ERR_INVALID,
              "rs_am_forward: keep probabilities must be in (0,1]");
-  tev_begin(am, 0);
+  tev_begin(am, 0, (cudaStream_t)stream);
   if (am->use_tc)
     return am_tc_forward(am, params_d, x_d, len_d, T, state_in_d, state_out_d, keep_in, keep_out, seed, logits_d,
                          reserve_d, ws_d, ws_bytes, (cudaStream_t)stream);
@@ -334,7 +352,7 @@ extern "C" int rs_am_backward(rs_am* am, const float* params_d, const float* x_d
   RS_REQUIRE(T > 0 && T <= am->Tmax, RS_ERR_INVALID, "rs_am_backward: T=%d outside [1,%d]", T, am->Tmax);
   RS_REQUIRE(keep_in > 0.f && keep_in <= 1.f && keep_out > 0.f && keep_out <= 1.f, RS_ERR_INVALID,
              "rs_am_backward: keep probabilities must be in (0,1]");
-  tev_begin(am, 1);
+  tev_begin(am, 1, (cudaStream_t)stream);
   if (am->use_tc)
     return am_tc_backward(am, params_d, x_d, len_d, T, keep_in, keep_out, seed, dlogits_d, reserve_d, grads_d, ws_d,
                           ws_bytes, (cudaStream_t)stream);

@@ -14,11 +14,13 @@ struct rs_am {
   int timing;
   std::vector<cudaEvent_t> tev[2][64];
   int tev_used[2][64];          // events recorded by the last call (2 per launch)
+  cudaEvent_t tev_base[2];      // recorded on the caller's stream at the top of the call (time origin of a trace)
+  int tev_base_ready;
   // tensor-core path (H % 64 == 0, B <= 64, weights fit in shared memory); else FFMA kernels
   int use_tc;
   // Streams of the pipelined schedule (lstm_tc.cu): one per layer for the chunked recurrent launches, one for the
   // chunk GEMMs between layers, one for the weight-gradient work; events come from a pool that is reused every call.
-  cudaStream_t lane[64], gemm_st, side;
+  cudaStream_t lane[64], gemm_st, side, tr_st;
   int streams_ready;
   std::vector<cudaEvent_t> evpool;
   size_t ev_next;
@@ -33,8 +35,12 @@ struct rs_am {
 namespace rs {
 
 // Timed (start, stop) event pairs around the recurrent launches; tev_begin() at the top of a forward / backward call.
-inline void tev_begin(rs_am* am, int dir) {
+inline void tev_begin(rs_am* am, int dir, cudaStream_t st = nullptr) {
   for (int l = 0; l < 64; ++l) am->tev_used[dir][l] = 0;
+  if (am->timing) {
+    if (!am->tev_base_ready) { cudaEventCreate(&am->tev_base[0]); cudaEventCreate(&am->tev_base[1]); am->tev_base_ready = 1; }
+    cudaEventRecord(am->tev_base[dir], st);
+  }
 }
 inline int tev_record(rs_am* am, int dir, int l, cudaStream_t st) {
   if (!am->timing) return RS_OK;

@@ -45,8 +45,10 @@ struct TcBufs {
   bf16 *whs_hi[64];               // K[H:] as stored [H][4H] (hi)
   bf16 *wos_hi, *wos_lo;          // w_o as stored [H][Cp]
   bf16 *dg_hi[64], *dg_lo[64];    // [T*B][4H] per layer
-  bf16 *dgT_hi, *dgT_lo;          // [4H][TBp]
-  bf16 *actT_hi, *actT_lo;        // [H][TBp] transposed activations
+  bf16 *dgT_hi[64], *dgT_lo[64];  // [4H][TBp] per layer
+  bf16 *xT2_hi[64], *xT2_lo[64];  // [H][TBp] transposed layer input, per layer
+  bf16 *hT_hi[64], *hT_lo[64];    // [H][TBp] transposed h_{t-1}, per layer
+  bf16 *actT_hi, *actT_lo;        // [H][TBp] transposed activations (output / input dense)
   bf16 *dl_hi, *dl_lo;            // dlogits planes [T*B][Cp]
   bf16 *dlT_hi, *dlT_lo;          // [C][TBp]
   bf16 *xT_hi, *xT_lo;            // [F][TBp]
@@ -82,9 +84,11 @@ void carve(const rs_am* am, void* reserve, void* ws, bool training, TcBufs* b, s
       b->whs_hi[l] = w.take<bf16>((size_t)4 * H * H);
       b->dg_hi[l] = w.take<bf16>(TB * 4 * H); b->dg_lo[l] = w.take<bf16>(TB * 4 * H);
       b->dc_carry[l] = w.take<float>(am->tc.ts ? rec_ts_dc_carry_floats(am->tc) : 1);
+      b->dgT_hi[l] = w.take<bf16>((size_t)4 * H * TBp); b->dgT_lo[l] = w.take<bf16>((size_t)4 * H * TBp);
+      b->xT2_hi[l] = w.take<bf16>((size_t)H * TBp); b->xT2_lo[l] = w.take<bf16>((size_t)H * TBp);
+      b->hT_hi[l] = w.take<bf16>((size_t)H * TBp); b->hT_lo[l] = w.take<bf16>((size_t)H * TBp);
     }
     b->wos_hi = w.take<bf16>((size_t)H * Cp); b->wos_lo = w.take<bf16>((size_t)H * Cp);
-    b->dgT_hi = w.take<bf16>((size_t)4 * H * TBp); b->dgT_lo = w.take<bf16>((size_t)4 * H * TBp);
     b->actT_hi = w.take<bf16>((size_t)H * TBp); b->actT_lo = w.take<bf16>((size_t)H * TBp);
     b->dl_hi = w.take<bf16>(TB * Cp); b->dl_lo = w.take<bf16>(TB * Cp);
     b->dlT_hi = w.take<bf16>((size_t)C * TBp); b->dlT_lo = w.take<bf16>((size_t)C * TBp);
@@ -202,6 +206,7 @@ int ensure_streams(rs_am* am) {
   for (int l = 0; l < am->L; ++l) RS_CHECK_CUDA(cudaStreamCreateWithPriority(&am->lane[l], cudaStreamNonBlocking, hi));
   RS_CHECK_CUDA(cudaStreamCreateWithPriority(&am->gemm_st, cudaStreamNonBlocking, hi));
   RS_CHECK_CUDA(cudaStreamCreateWithPriority(&am->side, cudaStreamNonBlocking, lo));
+  RS_CHECK_CUDA(cudaStreamCreateWithPriority(&am->tr_st, cudaStreamNonBlocking, lo));
   am->streams_ready = 1;
   return RS_OK;
 }
@@ -225,15 +230,30 @@ int ev_record(rs_am* am, cudaEvent_t* e, cudaStream_t st) {
 // layer l's chunk c -+ 1 and the GEMM that turns layer l -+ 1's chunk c into its input, so the layers run as a
 // wavefront: `window` recurrent launches in flight (nslice SMs each), the chunk GEMMs on the remaining SMs.
 struct Sched {
-  int Tc, NC, gemm_ctas, side_ctas;
+  int Tc, NC, gemm_ctas, fwd_gemm_ctas, side_ctas;
 };
 Sched make_sched(const rs_am* am, int T) {
   Sched s;
-  s.Tc = (am->tc.ts && am->chunk > 0 && am->chunk < T) ? am->chunk : T;
+  int Tc = (am->chunk + 7) / 8 * 8;                    // chunk starts stay 16-byte aligned in the transposed planes
+  s.Tc = (am->tc.ts && am->chunk > 0 && Tc < T) ? Tc : T;
   s.NC = cdiv(T, s.Tc);
   const int spare = sm_count() - (s.NC > 1 ? am->window : 1) * am->tc.nslice;
-  s.gemm_ctas = s.NC > 1 ? (spare > 16 ? spare : 16) : 0;          // 0 = one CTA per SM
-  s.side_ctas = spare > 32 ? spare : 32;
+  if (s.NC > 1) {
+    // The SMs the recurrent launches leave idle serve the chunk GEMMs on the critical path (a third of the backward
+    // GEMM work, in short bursts) and the weight-gradient GEMMs of the side stream.  Measured at cfg-2 (52 spare
+    // SMs): 16 + 48 CTAs -- slightly oversubscribed, the bursts of the first fill the gaps of the second -- beats
+    // every exact split (tools/gpu_diag.py trace, RS_TC_DX_CTAS / RS_TC_SIDE_CTAS).
+    static const int dx_env = [] { const char* v = getenv("RS_TC_DX_CTAS"); return v ? atoi(v) : 0; }();
+    static const int side_env = [] { const char* v = getenv("RS_TC_SIDE_CTAS"); return v ? atoi(v) : 0; }();
+    const int sp = spare > 24 ? spare : 24;
+    s.gemm_ctas = dx_env > 0 ? dx_env : (sp * 5 / 16 > 8 ? sp * 5 / 16 : 8);
+    s.side_ctas = side_env > 0 ? side_env : (sp - 4 > 8 ? sp - 4 : 8);
+    s.fwd_gemm_ctas = sp;
+  } else {
+    s.gemm_ctas = 0;                                     // 0 = one CTA per SM
+    s.fwd_gemm_ctas = 0;
+    s.side_ctas = spare > 32 ? spare : 32;
+  }
   return s;
 }
 
@@ -322,7 +342,7 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     GemmTcOut o{};
     o.mode = GEMM_OUT_REC; o.C = bf.gx[l] + (size_t)t0 * 4 * H * am->tc.Bpad; o.bias = params_d + am->off_bias[l];
     o.recB = B; o.recBpad = am->tc.Bpad; o.recH = H; o.recU = am->tc.U;
-    o.max_ctas = sc.gemm_ctas;
+    o.max_ctas = sc.fwd_gemm_ctas;
     RC(gemm_tc_nt(A, Bm, 4 * H, n * B, H, 3, o, am->gemm_st));
     return ev_record(am, &e_gx[(size_t)l * NC + c], am->gemm_st);
   };
@@ -361,7 +381,6 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     done.push_back(e);
     return RS_OK;
   };
-  tev_begin(am, 0);
   for (int c = 0; c < NC; ++c) RC(issue_gemm(0, c));               // layer 0's input is complete: no dependencies
   for (int d = 0; d < NC + L - 1; ++d)
     for (int l = 0; l < L; ++l) {
@@ -435,6 +454,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(am->lane[l], e_fork, 0));
   RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_fork, 0));
   RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_fork, 0));
+  RS_CHECK_CUDA(cudaStreamWaitEvent(am->tr_st, e_fork, 0));
   // Weight-gradient work (transposes, dK GEMMs, bias sums) is off the critical path: it runs on the side stream,
   // on the SMs the recurrent launches leave idle.  First the output dense's.
   RC(transpose_bf16(in_hi[L], TB, H, in_ld[L], bf.actT_hi, TBp, side));
@@ -488,46 +508,58 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     RC(gemm_tc_nt(A, Bm, n * B, H, 4 * H, 3, o, am->gemm_st));
     return ev_record(am, &e_dx[(size_t)l * NC + c], am->gemm_st);
   };
-  // side stream: dK[:H] += xin^T dg ; dK[H:] += hprev^T dg ; db += colsum(dg), once the layer's dgates are complete
-  auto issue_side = [&](int l) -> int {
-    RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_rec[(size_t)l * NC + 0], 0));
-    RC(transpose_bf16(bf.dg_hi[l], TB, 4 * H, 4 * H, bf.dgT_hi, TBp, side));
-    RC(transpose_bf16(bf.dg_lo[l], TB, 4 * H, 4 * H, bf.dgT_lo, TBp, side));
-    SplitMat G{bf.dgT_hi, bf.dgT_lo, 4 * H, TB, TBp};
+  // side stream: dK[:H] += xin^T dg ; dK[H:] += hprev^T dg ; db += colsum(dg) over the steps of chunk c, as soon as
+  // that chunk's dgates exist (fp32 accumulation into the gradient buffer, chunk after chunk)
+  auto issue_side = [&](int l, int c) -> int {
+    const int t0 = c * sc.Tc, n = (t0 + sc.Tc <= T ? sc.Tc : T - t0);
+    const size_t r0 = (size_t)t0 * B;                   // first (t, b) row of the chunk = first column of the transposes
+    const int nb = n * B;
+    // transposes (K-major operands for the tensor core) and the bias sums: small CTAs that share SMs with the
+    // recurrent launches, on their own stream so that the side stream is GEMMs back to back
+    cudaStream_t tr = am->tr_st;
+    RS_CHECK_CUDA(cudaStreamWaitEvent(tr, e_rec[(size_t)l * NC + c], 0));
+    RC(transpose_bf16(bf.dg_hi[l] + r0 * 4 * H, nb, 4 * H, 4 * H, bf.dgT_hi[l] + r0, TBp, tr));
+    RC(transpose_bf16(bf.dg_lo[l] + r0 * 4 * H, nb, 4 * H, 4 * H, bf.dgT_lo[l] + r0, TBp, tr));
+    RC(transpose_bf16(in_hi[l] + r0 * in_ld[l], nb, H, in_ld[l], bf.xT2_hi[l] + r0, TBp, tr));
+    RC(transpose_bf16(in_lo[l] + r0 * in_ld[l], nb, H, in_ld[l], bf.xT2_lo[l] + r0, TBp, tr));
+    RC(transpose_bf16(bf.hp_hi[l] + r0 * hld, nb, H, hld, bf.hT_hi[l] + r0, TBp, tr));        // slots t0..t0+n-1 = h_{t-1}
+    RC(transpose_bf16(bf.hp_lo[l] + r0 * hld, nb, H, hld, bf.hT_lo[l] + r0, TBp, tr));
+    cudaEvent_t e_tr;
+    RC(ev_record(am, &e_tr, tr));
+    RC(rowsum_planes(bf.dgT_hi[l] + r0, bf.dgT_lo[l] + r0, 4 * H, nb, TBp, grads_d + am->off_bias[l], 1, tr));
+    RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_tr, 0));
+    SplitMat G{bf.dgT_hi[l] + r0, bf.dgT_lo[l] + r0, 4 * H, nb, TBp};
     float* gK = grads_d + am->off_kernel[l];
     {
-      RC(transpose_bf16(in_hi[l], TB, H, in_ld[l], bf.actT_hi, TBp, side));
-      RC(transpose_bf16(in_lo[l], TB, H, in_ld[l], bf.actT_lo, TBp, side));
-      SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp};
+      SplitMat A{bf.xT2_hi[l] + r0, bf.xT2_lo[l] + r0, H, nb, TBp};
       GemmTcOut o{};
       o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas;
-      RC(gemm_tc_nt(A, G, H, 4 * H, TB, 3, o, side));
+      RC(gemm_tc_nt(A, G, H, 4 * H, nb, 3, o, side));
     }
     {
-      RC(transpose_bf16(bf.hp_hi[l], TB, H, hld, bf.actT_hi, TBp, side));     // slots 0..T-1 = h_{t-1}
-      RC(transpose_bf16(bf.hp_lo[l], TB, H, hld, bf.actT_lo, TBp, side));
-      SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp};
+      SplitMat A{bf.hT_hi[l] + r0, bf.hT_lo[l] + r0, H, nb, TBp};
       GemmTcOut o{};
       o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas;
-      RC(gemm_tc_nt(A, G, H, 4 * H, TB, 3, o, side));
+      RC(gemm_tc_nt(A, G, H, 4 * H, nb, 3, o, side));
     }
-    return rowsum_planes(bf.dgT_hi, bf.dgT_lo, 4 * H, TB, TBp, grads_d + am->off_bias[l], 1, side);
+    return RS_OK;
   };
-  tev_begin(am, 1);
   for (int d = 0; d < NC + L - 1; ++d)
     for (int l = L - 1; l >= 0; --l) {
       const int c = NC - 1 - (d - (L - 1 - l));
       if (c < 0 || c >= NC) continue;
       RC(issue_rec(l, c));
       RC(issue_dx(l, c));
-      if (c == 0) RC(issue_side(l));
+      RC(issue_side(l, c));
     }
   // join: the input-dense gradient below reuses actT, and the caller's stream owns grads_d afterwards
-  cudaEvent_t e_side, e_gemm;
+  cudaEvent_t e_side, e_gemm, e_trj;
   RC(ev_record(am, &e_side, side));
   RC(ev_record(am, &e_gemm, am->gemm_st));
+  RC(ev_record(am, &e_trj, am->tr_st));
   RS_CHECK_CUDA(cudaStreamWaitEvent(st, e_side, 0));
   RS_CHECK_CUDA(cudaStreamWaitEvent(st, e_gemm, 0));
+  RS_CHECK_CUDA(cudaStreamWaitEvent(st, e_trj, 0));
   for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(st, e_rec[(size_t)l * NC + 0], 0));
   // through layer 0's input dropout, then the input dense: dw_i += x^T drnn, db_i += colsum
   float* drnn = bf.din[0];

@@ -160,8 +160,9 @@ def test_cfg2_shape_forward_against_oracle(pkg, cuda):
 @pytest.mark.parametrize("L,H,B,T,chunk", [(3, 256, 8, 150, 32), (2, 128, 16, 97, 20)])
 def test_time_chunked_wavefront_is_bitwise_the_single_launch_schedule(pkg, cuda, monkeypatch, L, H, B, T, chunk):
     """The pipelined schedule (time chunks, layers as a wavefront on several streams) only reorders launches:
-    logits, carried state and gradients must be bit-identical to one launch per layer (RS_TC_CHUNK=0), with
-    dropout, ragged lengths and a carried-in state."""
+    logits and carried state must be bit-identical to one launch per layer (RS_TC_CHUNK=0), with dropout, ragged
+    lengths and a carried-in state.  Weight gradients are summed chunk after chunk instead of in one GEMM, which
+    regroups the fp32 additions: equal to 1e-5 of the largest entry."""
     F, C = 40, 30
     rng = np.random.default_rng(5)
     flat = model.flatten(model.init_params(L, H, F, C, seed=6), L, H, F, C)
@@ -184,5 +185,6 @@ def test_time_chunked_wavefront_is_bitwise_the_single_launch_schedule(pkg, cuda,
         out.append((logits.clone(), m.rnn_state.clone(), m.grads.clone()))
     assert torch.equal(out[0][0], out[1][0]), "logits differ"
     assert torch.equal(out[0][1], out[1][1]), "carried state differs"
-    assert torch.equal(out[0][2], out[1][2]), "gradients differ"
+    gdiff = float((out[0][2] - out[1][2]).abs().max() / out[0][2].abs().max())
+    assert gdiff < 1e-5, "gradients differ by %g of the largest entry" % gdiff
     assert bool(torch.isfinite(out[1][2]).all())

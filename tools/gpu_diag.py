@@ -268,6 +268,40 @@ def rec_diag():
                     (int(d[900, 15]) - int(d[100, 15])) / max(1, int(d[900, 7]) - int(d[100, 7])) * 1e3))
 
 
+def trace_diag():
+    """cfg-2 training step: where the recurrent launches of the pipelined schedule sit in time (CUDA events on the
+    launching streams, ms after the top of the forward / backward call) and how long each phase of the step takes."""
+    L, H, F, C, B, T = 3, 768, 120, 80, 32, 998
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.standard_normal((T, B, F)).astype(np.float32)).to(dev)
+    lens = torch.full((B,), T, dtype=torch.int32, device=dev)
+    labs = [np.append(rng.integers(1, 79, size=rng.integers(60, 121)), 79).astype(np.int32) for _ in range(B)]
+    m = rs.AcousticModel(L, H, B, 1000, 600, F, False, C, device=dev)
+    m.create_training_rnn(0.8, 0.5, 1, 3e-4, 0.33)
+    m.initialize(None)
+    m.enable_timing()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    for it in range(3):
+        m.grads.zero_()
+        ev[0].record()
+        logits = m.forward(x, lens, training=True, keep_state=False)
+        ev[1].record()
+        loss, grad = m.ctc_loss(logits, labs, lens)
+        ev[2].record()
+        m.backward(x, lens, grad)
+        ev[3].record()
+        m.apply_gradients()
+        ev[4].record()
+        torch.cuda.synchronize()
+    print("RS_TC_CHUNK=%s RS_TC_WINDOW=%s: forward %.2f ms, ctc %.2f ms, backward %.2f ms, clip+adam %.2f ms" % (
+        os.environ.get("RS_TC_CHUNK", "default"), os.environ.get("RS_TC_WINDOW", "default"),
+        ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), ev[3].elapsed_time(ev[4])))
+    tr = m.recurrent_trace()
+    for d, tag in ((0, "fwd"), (1, "bwd")):
+        for l in range(L):
+            print("  %s layer %d: %s" % (tag, l, " ".join("[%.2f-%.2f]" % (a, b) for a, b in tr[d][l])))
+
+
 def bf16_round(x):
     return torch.from_numpy(np.asarray(x, np.float32)).to(torch.bfloat16).to(torch.float32).numpy().astype(np.float64)
 
@@ -329,6 +363,8 @@ if __name__ == "__main__":
         rec_diag()
     if "ts" in which:
         ts_diag()
+    if "trace" in which:
+        trace_diag()
     if "mma" in which:
         mma_bench()
     if "cfg1" in which or "cfg2" in which:
