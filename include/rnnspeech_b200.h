@@ -202,6 +202,11 @@ int rs_tc_ts_selftest(const float* A_d, const float* B_d, float* D_d, int K, int
  * scratch_d: 2*(M*K + N*K)*2 + 64 bytes.  K multiple of 8. */
 int rs_gemm_tc_test(const float* A_d, const float* B_d, const float* bias_d, float* C_d, int M, int N, int K,
                     int products, void* scratch_d, size_t scratch_bytes, void* stream);
+/* Measurement hook: average ms of `reps` launches of the same GEMM (operands split once); bn = 0 | 128 | 256
+ * forces the tile width, max_ctas / tiles_per_cta shape the grid. */
+int rs_gemm_tc_bench(const float* A_d, const float* B_d, float* C_d, int M, int N, int K, int products,
+                     int bn, int max_ctas, int tiles_per_cta, int accumulate, int reps, void* scratch_d,
+                     size_t scratch_bytes, float* ms_out, void* stream);
 
 #ifdef __cplusplus
 }

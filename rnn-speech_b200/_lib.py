@@ -73,6 +73,8 @@ SIGNATURES = {
     "rs_tc_ts_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rs_gemm_tc_test": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
                                 c_void_p]),
+    "rs_gemm_tc_bench": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_void_p, c_size_t, POINTER(c_float), c_void_p]),
     "rs_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "rs_clip_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
                                   c_float, c_float, c_float, c_int64, c_void_p]),

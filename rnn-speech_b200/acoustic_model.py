@@ -387,9 +387,9 @@ class AcousticModel(object):
     def recurrent_trace(self, max_launches=256):
         """[direction][layer] -> list of (start_ms, stop_ms) of every recurrent launch of the last step,
         measured from the top of the forward / backward call (the pipelined schedule's timeline)."""
-        out = ([], [])
+        out = ([], [], [], [])       # forward rec, backward rec, backward weight-gradient GEMM pairs, backward dx GEMMs
         buf = (_lib.ctypes.c_float * (2 * max_launches))()
-        for d in (0, 1):
+        for d in (0, 1, 2, 3):
             for l in range(self.num_layers):
                 n = _lib.raw("rs_am_recurrent_trace")(self._handle, d, l, buf, max_launches)
                 if n < 0:

@@ -44,6 +44,7 @@ EncodeTiledFn encode_fn() {
 struct KParams {
   int M, N, K, products;
   int tiles_m, tiles_n;
+  int base_ctas;            // elastic launches: CTAs that work when the machine is shared
   GemmTcOut out;
 };
 
@@ -59,6 +60,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = p.tiles_m * p.tiles_n;
   const int nkb = (p.K + BK - 1) / BK;
+  // how many CTAs of this grid work (all of them, or the first base_ctas of an elastic launch): decided once per
+  // launch by whichever CTA comes first, so that every CTA strides over the tiles by the same count
+  __shared__ int s_nctas;
+  int nctas = gridDim.x;
+  if (p.out.elastic) {
+    if (threadIdx.x == 0) {
+      const int want = (*reinterpret_cast<volatile int*>(p.out.elastic) != 0) ? (int)gridDim.x : p.base_ctas;
+      const int old = atomicCAS(p.out.elastic + 1 + p.out.elastic_id, 0, want);
+      s_nctas = old ? old : want;
+    }
+    __syncthreads();
+    nctas = s_nctas;
+    if ((int)blockIdx.x >= nctas) return;
+  }
   const bool use_blo = (p.products & 1) != 0, use_alo = (p.products & 2) != 0;   // extra terms A_hi*B_lo / A_lo*B_hi
 
   if (warp == 0 && lane == 0) {
@@ -81,7 +96,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     {   // converged warp; one elected lane issues each TMA / arrive
       uint32_t it = 0;
       const uint32_t tx = (uint32_t)(TILE_A_BYTES + TILE_B_BYTES + (use_alo ? TILE_A_BYTES : 0) + (use_blo ? TILE_B_BYTES : 0));
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < ntiles; tile += nctas) {
         const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
@@ -100,7 +115,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     {   // converged warp, elect.sync inside each issue
       const uint32_t idesc = tc::instr_desc_bf16(BM, BN);
       uint32_t it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+      for (int tile = blockIdx.x; tile < ntiles; tile += nctas, ++tl) {
         const int as = tl & 1;
         tc::mbar_wait(&tempty_bar[as], ((tl >> 1) & 1) ^ 1);
         tc::tc_fence_after();
@@ -129,7 +144,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int q = warp & 3;                       // TMEM lane quadrant of this warp
     const GemmTcOut& o = p.out;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += nctas, ++tl) {
       const int as = tl & 1;
       const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
       tc::mbar_wait(&tfull_bar[as], (tl >> 1) & 1);
@@ -389,7 +404,10 @@ int gemm_launch(const SplitMat& A, const SplitMat& B, int M, int N, int K, int p
   const int ntiles = p.tiles_m * p.tiles_n;
   int grid = sm_count();
   if (out.max_ctas > 0 && grid > out.max_ctas) grid = out.max_ctas;
+  if (out.tiles_per_cta > 0) grid = cdiv(ntiles, out.tiles_per_cta);
   if (grid > ntiles) grid = ntiles;
+  p.base_ctas = grid;
+  if (out.elastic) { grid = sm_count(); if (grid > ntiles) grid = ntiles; if (grid < p.base_ctas) grid = p.base_ctas; }
   const size_t smem = (size_t)Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 1024;
   static bool attr_done = false;
   if (!attr_done) {
@@ -403,11 +421,14 @@ int gemm_launch(const SplitMat& A, const SplitMat& B, int M, int N, int K, int p
 
 }  // namespace
 
+static int g_force_bn = -1;     // test hook override of RS_GEMM_BN
+
 int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
                cudaStream_t st) {
   if (M <= 0 || N <= 0) return RS_OK;
   RS_REQUIRE(K > 0, RS_ERR_INVALID, "gemm_tc_nt: K=%d", K);
-  static const int force_bn = [] { const char* v = getenv("RS_GEMM_BN"); return v ? atoi(v) : 0; }();
+  static const int env_bn = [] { const char* v = getenv("RS_GEMM_BN"); return v ? atoi(v) : 0; }();
+  const int force_bn = g_force_bn >= 0 ? g_force_bn : env_bn;
   const bool wide = force_bn ? force_bn == 256 : N > 128;
   return wide ? gemm_launch<256>(A, B, M, N, K, products, out, st) : gemm_launch<128>(A, B, M, N, K, products, out, st);
 }
@@ -469,4 +490,43 @@ extern "C" int rs_gemm_tc_test(const float* A_d, const float* B_d, const float* 
   GemmTcOut o{};
   o.mode = GEMM_OUT_F32; o.C = C_d; o.ldc = N; o.bias = bias_d; o.accumulate = 0;
   return gemm_tc_nt(A, B, M, N, K, products, o, st);
+}
+
+// Measurement hook: split once, then time `reps` GEMMs C = A B^T (K-major fp32 inputs) with CUDA events on `stream`.
+// bn = 0 | 128 | 256 forces the tile width; max_ctas / tiles_per_cta / accumulate as in GemmTcOut.
+extern "C" int rs_gemm_tc_bench(const float* A_d, const float* B_d, float* C_d, int M, int N, int K, int products,
+                                int bn, int max_ctas, int tiles_per_cta, int accumulate, int reps, void* scratch_d,
+                                size_t scratch_bytes, float* ms_out, void* stream) {
+  RS_REQUIRE(A_d && B_d && C_d && scratch_d && ms_out && reps > 0, RS_ERR_INVALID, "rs_gemm_tc_bench: bad argument");
+  RS_REQUIRE(K % 8 == 0, RS_ERR_INVALID, "rs_gemm_tc_bench: K must be a multiple of 8");
+  const size_t need = 2 * ((size_t)M * K + (size_t)N * K) * sizeof(__nv_bfloat16) + 64;
+  RS_REQUIRE(scratch_bytes >= need, RS_ERR_WORKSPACE, "rs_gemm_tc_bench: scratch %zu < %zu", scratch_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* ah = (__nv_bfloat16*)scratch_d;
+  __nv_bfloat16* al = ah + (size_t)M * K;
+  __nv_bfloat16* bh = al + (size_t)M * K;
+  __nv_bfloat16* bl = bh + (size_t)N * K;
+  int rc;
+  if ((rc = split_planes(A_d, ah, al, (int64_t)M * K, st)) != RS_OK) return rc;
+  if ((rc = split_planes(B_d, bh, bl, (int64_t)N * K, st)) != RS_OK) return rc;
+  SplitMat A{ah, al, M, K, K}, B{bh, bl, N, K, K};
+  GemmTcOut o{};
+  o.mode = GEMM_OUT_F32; o.C = C_d; o.ldc = N; o.accumulate = accumulate; o.max_ctas = max_ctas; o.tiles_per_cta = tiles_per_cta;
+  cudaEvent_t e0, e1;
+  RS_CHECK_CUDA(cudaEventCreate(&e0));
+  RS_CHECK_CUDA(cudaEventCreate(&e1));
+  g_force_bn = bn;
+  rc = gemm_tc_nt(A, B, M, N, K, products, o, st);          // warm-up
+  RS_CHECK_CUDA(cudaEventRecord(e0, st));
+  for (int i = 0; i < reps && rc == RS_OK; ++i) rc = gemm_tc_nt(A, B, M, N, K, products, o, st);
+  RS_CHECK_CUDA(cudaEventRecord(e1, st));
+  g_force_bn = -1;
+  if (rc != RS_OK) return rc;
+  RS_CHECK_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  RS_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_out = ms / reps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return RS_OK;
 }

@@ -31,6 +31,14 @@ struct GemmTcOut {
   //   bias is indexed in the original order g*H + unit
   int recB, recBpad, recH, recU;
   int max_ctas;            // 0 = one CTA per SM; otherwise cap the persistent grid (side-stream GEMMs)
+  // Elastic grid: with `elastic` set the launch has one CTA per SM, but only the first max_ctas of them work unless
+  // elastic[0] != 0 when the first CTA looks (the pipelined schedule raises it once its recurrent launches are done,
+  // so that the GEMMs still queued behind them take the whole machine).  elastic[1 + elastic_id] records the
+  // decision for the launch (zeroed by the caller before the step).
+  int* elastic;
+  int elastic_id;
+  int tiles_per_cta;       // > 0: grid = ceil(tiles / tiles_per_cta) short-lived CTAs instead of a persistent grid, so
+                           // that the block scheduler can place them wherever (and whenever) SMs are free
 };
 
 // C[M,N] = A[M,K] * B[N,K]^T, both operands K-major (row-major with K contiguous).

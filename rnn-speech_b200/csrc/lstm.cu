@@ -115,7 +115,7 @@ extern "C" int rs_am_create(rs_am** out, int num_layers, int hidden_size, int in
                            (rec_tc_geometry(hidden_size, batch_size, &am->tc) &&
                             rec_tc_bwd_geometry(hidden_size, batch_size, &bg)));
   }
-  for (int d = 0; d < 2; ++d)
+  for (int d = 0; d < 4; ++d)
     for (int l = 0; l < 64; ++l) am->tev_used[d][l] = 0;
   *out = am;
   return RS_OK;
@@ -123,7 +123,7 @@ extern "C" int rs_am_create(rs_am** out, int num_layers, int hidden_size, int in
 
 extern "C" void rs_am_destroy(rs_am* am) {
   if (!am) return;
-  for (int d = 0; d < 2; ++d)
+  for (int d = 0; d < 4; ++d)
     for (int l = 0; l < 64; ++l)
       for (cudaEvent_t e : am->tev[d][l]) cudaEventDestroy(e);
   for (cudaEvent_t e : am->evpool) cudaEventDestroy(e);
@@ -174,13 +174,13 @@ extern "C" int rs_am_recurrent_ms(rs_am* am, int backward, int layer, float* ms)
 // of launches written (<= max_launches) or a negative error.
 extern "C" int rs_am_recurrent_trace(rs_am* am, int backward, int layer, float* start_stop_ms, int max_launches) {
   RS_REQUIRE(am && start_stop_ms && am->timing && am->tev_base_ready, RS_ERR_INVALID, "rs_am_recurrent_trace: timing not enabled");
-  RS_REQUIRE(layer >= 0 && layer < am->L && (backward == 0 || backward == 1), RS_ERR_INVALID, "rs_am_recurrent_trace: bad index");
+  RS_REQUIRE(layer >= 0 && layer < am->L && backward >= 0 && backward < 4, RS_ERR_INVALID, "rs_am_recurrent_trace: bad index");
   const int used = am->tev_used[backward][layer];
   int n = 0;
   for (int i = 0; i + 1 < used && n < max_launches; i += 2, ++n) {
     RS_CHECK_CUDA(cudaEventSynchronize(am->tev[backward][layer][i + 1]));
-    RS_CHECK_CUDA(cudaEventElapsedTime(&start_stop_ms[2 * n], am->tev_base[backward], am->tev[backward][layer][i]));
-    RS_CHECK_CUDA(cudaEventElapsedTime(&start_stop_ms[2 * n + 1], am->tev_base[backward], am->tev[backward][layer][i + 1]));
+    RS_CHECK_CUDA(cudaEventElapsedTime(&start_stop_ms[2 * n], am->tev_base[backward ? 1 : 0], am->tev[backward][layer][i]));
+    RS_CHECK_CUDA(cudaEventElapsedTime(&start_stop_ms[2 * n + 1], am->tev_base[backward ? 1 : 0], am->tev[backward][layer][i + 1]));
   }
   return n;
 }

@@ -12,8 +12,8 @@ struct rs_am {
   // optional per-launch timing of the recurrent kernels (CUDA events on the launching stream):
   // tev[fwd|bwd][layer] holds (start, stop) pairs, one pair per (chunk) launch of the last call
   int timing;
-  std::vector<cudaEvent_t> tev[2][64];
-  int tev_used[2][64];          // events recorded by the last call (2 per launch)
+  std::vector<cudaEvent_t> tev[4][64];   // [fwd rec | bwd rec | bwd weight-gradient GEMMs | bwd dx GEMMs][layer]
+  int tev_used[4][64];          // events recorded by the last call (2 per launch)
   cudaEvent_t tev_base[2];      // recorded on the caller's stream at the top of the call (time origin of a trace)
   int tev_base_ready;
   // tensor-core path (H % 64 == 0, B <= 64, weights fit in shared memory); else FFMA kernels
@@ -37,6 +37,7 @@ namespace rs {
 // Timed (start, stop) event pairs around the recurrent launches; tev_begin() at the top of a forward / backward call.
 inline void tev_begin(rs_am* am, int dir, cudaStream_t st = nullptr) {
   for (int l = 0; l < 64; ++l) am->tev_used[dir][l] = 0;
+  if (dir == 1) for (int l = 0; l < 64; ++l) am->tev_used[2][l] = am->tev_used[3][l] = 0;
   if (am->timing) {
     if (!am->tev_base_ready) { cudaEventCreate(&am->tev_base[0]); cudaEventCreate(&am->tev_base[1]); am->tev_base_ready = 1; }
     cudaEventRecord(am->tev_base[dir], st);

@@ -54,6 +54,7 @@ struct TcBufs {
   bf16 *xT_hi, *xT_lo;            // [F][TBp]
   float* din[65];                 // [T*B][H]: din[l] = gradient wrt layer l's input, din[L] = wrt the top activations
   float* dc_carry[64];
+  int* elastic;                   // [0] = recurrent launches done, [1 + i] = grid decision of the i-th elastic GEMM
   // ---- reserve
   bf16 *x_hi, *x_lo;              // [T*B][Fp]
   bf16 *xin_hi[64], *xin_lo[64];  // [T*B][H]
@@ -89,6 +90,7 @@ void carve(const rs_am* am, void* reserve, void* ws, bool training, TcBufs* b, s
       b->hT_hi[l] = w.take<bf16>((size_t)H * TBp); b->hT_lo[l] = w.take<bf16>((size_t)H * TBp);
     }
     b->wos_hi = w.take<bf16>((size_t)H * Cp); b->wos_lo = w.take<bf16>((size_t)H * Cp);
+    b->elastic = w.take<int>(4096);
     b->actT_hi = w.take<bf16>((size_t)H * TBp); b->actT_lo = w.take<bf16>((size_t)H * TBp);
     b->dl_hi = w.take<bf16>(TB * Cp); b->dl_lo = w.take<bf16>(TB * Cp);
     b->dlT_hi = w.take<bf16>((size_t)C * TBp); b->dlT_lo = w.take<bf16>((size_t)C * TBp);
@@ -204,7 +206,7 @@ int ensure_streams(rs_am* am) {
   int lo = 0, hi = 0;
   RS_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // lo = least urgent, hi = most urgent
   for (int l = 0; l < am->L; ++l) RS_CHECK_CUDA(cudaStreamCreateWithPriority(&am->lane[l], cudaStreamNonBlocking, hi));
-  RS_CHECK_CUDA(cudaStreamCreateWithPriority(&am->gemm_st, cudaStreamNonBlocking, hi));
+  RS_CHECK_CUDA(cudaStreamCreateWithPriority(&am->gemm_st, cudaStreamNonBlocking, hi < lo - 1 ? hi + 1 : hi));
   RS_CHECK_CUDA(cudaStreamCreateWithPriority(&am->side, cudaStreamNonBlocking, lo));
   RS_CHECK_CUDA(cudaStreamCreateWithPriority(&am->tr_st, cudaStreamNonBlocking, lo));
   am->streams_ready = 1;
@@ -231,6 +233,7 @@ int ev_record(rs_am* am, cudaEvent_t* e, cudaStream_t st) {
 // wavefront: `window` recurrent launches in flight (nslice SMs each), the chunk GEMMs on the remaining SMs.
 struct Sched {
   int Tc, NC, gemm_ctas, fwd_gemm_ctas, side_ctas;
+  int side_tpc, dx_tpc, gx_tpc;           // tiles per CTA (0 = persistent grid with the caps above)
 };
 Sched make_sched(const rs_am* am, int T) {
   Sched s;
@@ -249,7 +252,12 @@ Sched make_sched(const rs_am* am, int T) {
     s.gemm_ctas = dx_env > 0 ? dx_env : (sp * 5 / 16 > 8 ? sp * 5 / 16 : 8);
     s.side_ctas = side_env > 0 ? side_env : (sp - 4 > 8 ? sp - 4 : 8);
     s.fwd_gemm_ctas = sp;
+    static const int side_tpc = [] { const char* v = getenv("RS_TC_SIDE_TPC"); return v ? atoi(v) : 0; }();
+    static const int dx_tpc = [] { const char* v = getenv("RS_TC_DX_TPC"); return v ? atoi(v) : 0; }();
+    static const int gx_tpc = [] { const char* v = getenv("RS_TC_GX_TPC"); return v ? atoi(v) : 0; }();
+    s.side_tpc = side_tpc; s.dx_tpc = dx_tpc; s.gx_tpc = gx_tpc;
   } else {
+    s.side_tpc = s.dx_tpc = s.gx_tpc = 0;
     s.gemm_ctas = 0;                                     // 0 = one CTA per SM
     s.fwd_gemm_ctas = 0;
     s.side_ctas = spare > 32 ? spare : 32;
@@ -342,7 +350,7 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     GemmTcOut o{};
     o.mode = GEMM_OUT_REC; o.C = bf.gx[l] + (size_t)t0 * 4 * H * am->tc.Bpad; o.bias = params_d + am->off_bias[l];
     o.recB = B; o.recBpad = am->tc.Bpad; o.recH = H; o.recU = am->tc.U;
-    o.max_ctas = sc.fwd_gemm_ctas;
+    o.max_ctas = sc.fwd_gemm_ctas; o.tiles_per_cta = sc.gx_tpc;
     RC(gemm_tc_nt(A, Bm, 4 * H, n * B, H, 3, o, am->gemm_st));
     return ev_record(am, &e_gx[(size_t)l * NC + c], am->gemm_st);
   };
@@ -449,6 +457,9 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   RC(ensure_streams(am));
   am->ev_next = 0;
   cudaStream_t side = am->side;
+  RS_CHECK_CUDA(cudaMemsetAsync(bf.elastic, 0, 4096 * sizeof(int), st));
+  int elastic_next = 0;
+  const bool use_elastic = NC > 1 && sc.side_tpc == 0 && 2 * L * NC + 8 < 4096;
   cudaEvent_t e_fork;
   RC(ev_record(am, &e_fork, st));
   for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(am->lane[l], e_fork, 0));
@@ -504,8 +515,10 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     SplitMat A{bf.dg_hi[l] + (size_t)t0 * B * 4 * H, bf.dg_lo[l] + (size_t)t0 * B * 4 * H, n * B, 4 * H, 4 * H};
     SplitMat Bm{bf.wxs_hi[l], bf.wxs_lo[l], H, 4 * H, 4 * H};
     GemmTcOut o{};
-    o.mode = GEMM_OUT_F32; o.C = bf.din[l] + (size_t)t0 * B * H; o.ldc = H; o.max_ctas = sc.gemm_ctas;
+    o.mode = GEMM_OUT_F32; o.C = bf.din[l] + (size_t)t0 * B * H; o.ldc = H; o.max_ctas = sc.gemm_ctas; o.tiles_per_cta = sc.dx_tpc;
+    RC(tev_record(am, 3, l, am->gemm_st));
     RC(gemm_tc_nt(A, Bm, n * B, H, 4 * H, 3, o, am->gemm_st));
+    RC(tev_record(am, 3, l, am->gemm_st));
     return ev_record(am, &e_dx[(size_t)l * NC + c], am->gemm_st);
   };
   // side stream: dK[:H] += xin^T dg ; dK[H:] += hprev^T dg ; db += colsum(dg) over the steps of chunk c, as soon as
@@ -528,27 +541,32 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     RC(ev_record(am, &e_tr, tr));
     RC(rowsum_planes(bf.dgT_hi[l] + r0, bf.dgT_lo[l] + r0, 4 * H, nb, TBp, grads_d + am->off_bias[l], 1, tr));
     RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_tr, 0));
+    RC(tev_record(am, 2, l, side));
     SplitMat G{bf.dgT_hi[l] + r0, bf.dgT_lo[l] + r0, 4 * H, nb, TBp};
     float* gK = grads_d + am->off_kernel[l];
     {
       SplitMat A{bf.xT2_hi[l] + r0, bf.xT2_lo[l] + r0, H, nb, TBp};
       GemmTcOut o{};
-      o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas;
+      o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas; o.tiles_per_cta = sc.side_tpc;
+      if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
       RC(gemm_tc_nt(A, G, H, 4 * H, nb, 3, o, side));
     }
     {
       SplitMat A{bf.hT_hi[l] + r0, bf.hT_lo[l] + r0, H, nb, TBp};
       GemmTcOut o{};
-      o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas;
+      o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas; o.tiles_per_cta = sc.side_tpc;
+      if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
       RC(gemm_tc_nt(A, G, H, 4 * H, nb, 3, o, side));
     }
-    return RS_OK;
+    return tev_record(am, 2, l, side);
   };
   for (int d = 0; d < NC + L - 1; ++d)
     for (int l = L - 1; l >= 0; --l) {
       const int c = NC - 1 - (d - (L - 1 - l));
       if (c < 0 || c >= NC) continue;
       RC(issue_rec(l, c));
+      // the last recurrent launch of the call is done: the GEMMs still queued may take the whole machine
+      if (l == 0 && c == 0 && use_elastic) RS_CHECK_CUDA(cudaMemsetAsync(bf.elastic, 1, sizeof(int), am->lane[0]));
       RC(issue_dx(l, c));
       RC(issue_side(l, c));
     }

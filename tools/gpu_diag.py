@@ -108,6 +108,32 @@ def gemm_diag():
                 print("   first bad entries", bad[:5].tolist(), "of", len(bad))
 
 
+def gemm_bench():
+    """The tcgen05 GEMM alone (operands split once, CUDA events around `reps` launches) on the shapes of the
+    pipelined schedule: tile width, grid size and CTA lifetime."""
+    import ctypes
+    shapes = [("dK chunk", 768, 3072, 4096, 1), ("dK full", 768, 3072, 31936, 1), ("dx chunk", 4096, 768, 3072, 0),
+              ("gx chunk", 3072, 4096, 768, 0), ("gx full", 3072, 31936, 768, 0)]
+    for name, M, N, K, acc in shapes:
+        g = torch.Generator(device=dev); g.manual_seed(1)
+        A = torch.randn((M, K), device=dev, generator=g)
+        B = torch.randn((N, K), device=dev, generator=g)
+        C = torch.zeros((M, N), device=dev)
+        scratch = torch.empty(2 * (M * K + N * K) * 2 + 64, dtype=torch.uint8, device=dev)
+        for products in (3, 1):
+            row = []
+            for bn in (128, 256):
+                for ctas, tpc in ((0, 0), (52, 0), (36, 0), (0, 1)):
+                    ms = ctypes.c_float()
+                    rs._lib.call("rs_gemm_tc_bench", A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, products, bn, ctas,
+                                 tpc, acc, 10, scratch.data_ptr(), scratch.numel(), ctypes.byref(ms),
+                                 torch.cuda.current_stream().cuda_stream)
+                    n_sm = 148 if (ctas == 0) else ctas
+                    tf = 2.0 * M * N * K * (3 if products == 3 else 1) / (ms.value * 1e-3) / 1e12
+                    row.append("bn%d/%s: %.3f ms %4.0f TF (%.1f/SM)" % (bn, ("tpc1" if tpc else "g%d" % n_sm), ms.value, tf, tf / n_sm))
+            print("%-9s %dx%dx%d products=%d\n    %s\n    %s" % (name, M, N, K, products, " | ".join(row[:4]), " | ".join(row[4:])))
+
+
 def model_diag(which):
     def golden(name):
         return np.load(os.path.join(ROOT, "tests", "golden", name))
@@ -297,7 +323,7 @@ def trace_diag():
         os.environ.get("RS_TC_CHUNK", "default"), os.environ.get("RS_TC_WINDOW", "default"),
         ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), ev[3].elapsed_time(ev[4])))
     tr = m.recurrent_trace()
-    for d, tag in ((0, "fwd"), (1, "bwd")):
+    for d, tag in ((0, "fwd"), (1, "bwd"), (2, "dK "), (3, "dx ")):
         for l in range(L):
             print("  %s layer %d: %s" % (tag, l, " ".join("[%.2f-%.2f]" % (a, b) for a, b in tr[d][l])))
 
@@ -363,6 +389,8 @@ if __name__ == "__main__":
         rec_diag()
     if "ts" in which:
         ts_diag()
+    if "gemmbench" in which:
+        gemm_bench()
     if "trace" in which:
         trace_diag()
     if "mma" in which:
