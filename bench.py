@@ -253,6 +253,8 @@ def run_b200(args):
         sampler.start()
     ms, launches = timed(step_resident, args.steps)
     rec_f, rec_b = m.recurrent_ms()
+    trace = m.recurrent_trace()
+    chunk = int(os.environ.get("RS_TC_CHUNK", "128"))
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -271,22 +273,39 @@ def run_b200(args):
         pass
     tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
-    # dominant kernel: the recurrent kernels (forward + backward), one launch per layer per direction.
-    rec_flops_fwd = 2.0 * c["B"] * c["H"] * 4 * c["H"] * T          # h_{t-1} @ Wh over T steps, per launch
+    # dominant kernels: the recurrent kernels (forward + backward).  With the pipelined schedule one layer is
+    # `chunks` launches of <= `chunk` steps each; launch_ms below is per layer (its launches summed), `achieved`
+    # uses the algorithmic flops of a layer (2*B*H*4H*T) over that sum, i.e. the per-launch rate.
+    rec_flops_layer = 2.0 * c["B"] * c["H"] * 4 * c["H"] * T        # h_{t-1} @ Wh over T steps
     rec_ms = float(np.mean(rec_f + rec_b))
-    achieved = rec_flops_fwd / (rec_ms / 1e3) / 1e12
+    achieved = rec_flops_layer / (rec_ms / 1e3) / 1e12
     tc = bool(m.uses_tensor_cores)
-    roofline = {"kernel": ("rec_tc_fwd_kernel / rec_tc_bwd_kernel (tcgen05 persistent recurrent kernels, one launch "
-                           "per layer per direction)") if tc else "lstm_rec_fwd_kernel / lstm_rec_bwd_kernel (fp32 FFMA)",
+    n_launch = [len(x) for x in trace[0]] + [len(x) for x in trace[1]]
+
+    def busy(intervals):
+        """length of the union of (start, stop) intervals"""
+        tot, end = 0.0, -1e30
+        for a, b in sorted(intervals):
+            if b > end:
+                tot += b - max(a, end)
+                end = b
+        return tot
+    rec_busy = busy([iv for l in trace[0] for iv in l]) + busy([iv for l in trace[1] for iv in l])
+    roofline = {"kernel": ("rec_ts_fwd_kernel / rec_ts_bwd_kernel (persistent tcgen05 recurrent kernels, weights resident "
+                           "in tensor memory; %d launches per layer per direction, <= %d steps each, layers overlapped as a "
+                           "wavefront)" % (max(n_launch), chunk)) if tc else "lstm_rec_fwd_kernel / lstm_rec_bwd_kernel (fp32 FFMA)",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak,
-                # dram__bytes_read+write per launch from profiles/r01_ncu_recurrent_kernels.txt (fwd 946 MB, bwd 961 MB)
-                "traffic": 953.0e6 if tc else None, "peak_source": peak_src,
-                "launch_ms": {"fwd": rec_f, "bwd": rec_b}, "share_of_step": (sum(rec_f) + sum(rec_b)) / (ms / args.steps),
-                "note": "algorithmic flops = 2*B*H*4H*T per launch (150.7 GFLOP at cfg-2; the bf16x3 forward issues 3x "
-                        "that on the tensor pipe); the recurrence is a chain of T dependent steps with a grid-wide "
-                        "exchange of h per step, so it is latency-bound, not tensor-bound: see DESIGN.md 'Recurrent "
-                        "step budget' for the measured per-step timeline"}
+                # dram__bytes_read+write per layer from profiles/r01b_ncu_rec_ts_kernels.txt (fwd 948 MB, bwd 961 MB)
+                "traffic": 954.0e6 if tc else None, "peak_source": peak_src,
+                "launch_ms": {"fwd": rec_f, "bwd": rec_b}, "launches_per_layer": max(n_launch),
+                "sum_launch_ms": sum(rec_f) + sum(rec_b),
+                "share_of_step": rec_busy / (ms / args.steps),
+                "note": "algorithmic flops = 2*B*H*4H*T per layer (150.7 GFLOP at cfg-2; the bf16x3 forward issues 3x "
+                        "that on the tensor pipe).  The recurrence is a chain of T dependent steps with a grid-wide "
+                        "exchange of h per step: latency-bound, not tensor-bound (DESIGN.md 'Recurrent step budget'); "
+                        "launch_ms sums a layer's chunk launches, which run concurrently with other layers' (sum_launch_ms "
+                        "exceeds the step); share_of_step = time during which at least one recurrent launch is running"}
     line = {
         "metric": "utterances/sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -295,6 +314,8 @@ def run_b200(args):
                    "arithmetic": ("bf16 tensor cores with a 3-term hi/lo split (fp32-grade products, fp32 accumulate) "
                                   "forward and in all batched GEMMs; plain bf16 in the backward dh recurrence; fp64 "
                                   "feature extraction; fp32 CTC / Adam") if tc else "fp32",
+                   "schedule": "time chunks of %d steps, layers as a wavefront (2 recurrent launches in flight), chunk GEMMs "
+                               "and weight-gradient GEMMs on the remaining SMs" % chunk,
                    "l2": "per-step working set (activations 2.1 GB + 57 MB params x4) exceeds the 126 MB L2; no flush needed",
                    "train_tflop_per_step": train_flops_per_utt(c, T) * c["B"] * world / 1e12},
         "e2e": {"value": e2e, "unit": "utt/s", "ms_per_step": ms_e2e / args.steps,

@@ -3,13 +3,14 @@
 # Usage (on the GPU box): bash tools/profile_round.sh <tag>
 TAG=${1:-r01}
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${TAG}_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_launches_bench.log 2>&1
 for k in rec_ts_fwd_kernel rec_ts_bwd_kernel; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o gpurun_out/${TAG}_$k \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 30 -c 1 -f -o gpurun_out/${TAG}_$k \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_$k.log 2>&1
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_kernel|ctc_lattice_kernel|fbank_logmel_kernel|clip_adam_kernel' -s 40 -c 24 -f -o gpurun_out/${TAG}_others \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_kernel|ctc_lattice_kernel|fbank_logmel_kernel|clip_adam_kernel' -s 150 -c 30 -f -o gpurun_out/${TAG}_others \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_others.log 2>&1
 RS_DIAG_VARIANTS=29 timeout 300 python tools/gpu_diag.py rec > gpurun_out/${TAG}_timeline.txt 2>&1
+timeout 300 python tools/gpu_diag.py trace > gpurun_out/${TAG}_trace.txt 2>&1
 ls -la gpurun_out
