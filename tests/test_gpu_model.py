@@ -188,3 +188,36 @@ def test_time_chunked_wavefront_is_bitwise_the_single_launch_schedule(pkg, cuda,
     gdiff = float((out[0][2] - out[1][2]).abs().max() / out[0][2].abs().max())
     assert gdiff < 1e-5, "gradients differ by %g of the largest entry" % gdiff
     assert bool(torch.isfinite(out[1][2]).all())
+
+
+def test_cfg4_shape_wavefront_against_oracle(pkg, cuda, monkeypatch):
+    """BASELINE config 4's model (5x1024 LSTM, 120-dim input, per-GPU batch 16, ragged utterance lengths as a
+    duration-bucketed batch gives) at a frame count the float64 oracle finishes in seconds, through the pipelined
+    schedule (time chunks of 16 steps: 64 CTAs per layer, two layers in flight, one K-block of the forward weights in
+    shared memory because 1024 columns exceed tensor memory): logits, CTC loss, greedy labels and gradients."""
+    L, H, F, C, B, T = 5, 1024, 120, 80, 16, 56
+    monkeypatch.setenv("RS_TC_CHUNK", "16")
+    rng = np.random.default_rng(44)
+    p = model.init_params(L, H, F, C, seed=3, dtype=np.float64)
+    flat = model.flatten(p, L, H, F, C)
+    x = rng.standard_normal((T, B, F))
+    lens = np.sort(rng.integers(T // 2, T + 1, size=B))[::-1].astype(np.int32)      # sorted by duration, longest first
+    lens[0] = T
+    labs = [np.append(rng.integers(1, 79, size=rng.integers(3, 9)), 79).astype(np.int32) for _ in range(B)]
+    m = _build(pkg, cuda, L, H, F, C, B, T, flat, training=True)
+    assert m.uses_tensor_cores
+    xd, ld = _dev(x, cuda, np.float32), _dev(lens, cuda, np.int32)
+    logits = m.forward(xd, ld, training=True)
+    want, _, cache = model.forward(p, x, lens, L, H)
+    got = logits.cpu().numpy()
+    assert np.abs(got - want).max() < 3e-4
+    _assert_labels_match(got, want, lens)
+    loss, grad = m.ctc_loss(logits, labs, ld)
+    want_loss, dl = ctc.ctc_loss_and_grad(want, labs, lens)
+    assert (np.abs(loss.cpu().numpy() - want_loss) / np.abs(want_loss)).max() < 1e-4
+    m.grads.zero_()
+    m.backward(xd, ld, _dev(dl, cuda, np.float32))
+    gw = model.flatten(model.backward(p, cache, dl, L, H), L, H, F, C)
+    err = np.abs(m.grads.cpu().numpy() - gw).max() / np.abs(gw).max()
+    print("cfg-4 shape: gradient error %.2e of the largest entry" % err)
+    assert err < 2e-3
