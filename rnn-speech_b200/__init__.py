@@ -10,7 +10,7 @@ AudioProcessor / AcousticModel / label-codec interfaces.
 from . import _lib                      # noqa: F401  (fails loudly if the .so is missing)
 from ._lib import RnnSpeechError, LIB_PATH      # noqa: F401
 from .labels import ENGLISH_CHAR_MAP, get_labels_str, get_str_labels, get_str_to_one_hot_encoded  # noqa: F401
-from .audioprocessor import AudioProcessor      # noqa: F401
+from .audioprocessor import AudioProcessor, BatchPrefetcher      # noqa: F401
 from .acoustic_model import AcousticModel, OutOfRangeError, levenshtein   # noqa: F401
 from .hyperparams import HyperParameterHandler  # noqa: F401
 

@@ -58,6 +58,9 @@ def levenshtein(a, b):
     return int(prev[-1])
 
 
+TC_MAX_BATCH = 64      # utterances per launch of the tensor-core recurrent kernels (csrc/lstm_rec_ts.cu)
+
+
 class AcousticModel(object):
     def __init__(self, num_layers, hidden_size, batch_size, max_input_seq_length,
                  max_target_seq_length, input_dim, normalization, num_labels, device=None, seed=0):
@@ -113,15 +116,42 @@ class AcousticModel(object):
         if self.rnn_created:
             logging.fatal("Trying to create the acoustic RNN but it is already.")
             return
-        h = _lib.c_void_p()
-        _lib.call("rs_am_create", _lib.ctypes.byref(h), self.num_layers, self.hidden_size, self.input_dim,
-                  self.num_labels, self.batch_size, self.max_input_seq_length)
+        def create(batch):
+            hh = _lib.c_void_p()
+            _lib.call("rs_am_create", _lib.ctypes.byref(hh), self.num_layers, self.hidden_size, self.input_dim,
+                      self.num_labels, batch, self.max_input_seq_length)
+            return hh
+        # The tensor-core recurrent kernels take up to TC_MAX_BATCH utterances; a larger mini-batch (BASELINE
+        # config 5: 256 clips) runs as batch tiles of that size, one handle per tile size, sharing parameters,
+        # gradients and workspace (utterances are independent: SURVEY 8e).
+        self._tiles = None
+        h = None
+        if self.batch_size > TC_MAX_BATCH:
+            probe = create(TC_MAX_BATCH)
+            if bool(_lib.raw("rs_am_uses_tensor_cores")(probe)):
+                bounds = list(range(0, self.batch_size, TC_MAX_BATCH)) + [self.batch_size]
+                self._tiles = []
+                rest = None
+                for b0, b1 in zip(bounds[:-1], bounds[1:]):
+                    if b1 - b0 == TC_MAX_BATCH:
+                        th = probe
+                    else:
+                        rest = rest if rest is not None else create(b1 - b0)
+                        th = rest
+                    self._tiles.append({"b0": b0, "b1": b1, "handle": th, "reserve": None})
+                self._tile_handles = [probe] + ([rest] if rest is not None else [])
+                h = probe
+            else:
+                _lib.raw("rs_am_destroy")(probe)
+        if h is None:
+            h = create(self.batch_size)
         self._handle = h
         self.uses_tensor_cores = bool(_lib.raw("rs_am_uses_tensor_cores")(h))
         n = _lib.raw("rs_am_param_count")(h)
         self.n_params = int(n)
         self.params = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
-        self._ws = torch.empty(int(_lib.raw("rs_am_workspace_bytes")(h)), dtype=torch.uint8, device=self.device)
+        ws_bytes = max(int(_lib.raw("rs_am_workspace_bytes")(th)) for th in (getattr(self, "_tile_handles", None) or [h]))
+        self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         self.rnn_state = torch.zeros((self.num_layers, 2, self.batch_size, self.hidden_size), dtype=torch.float32,
                                      device=self.device)
         self._ctc_ws = None
@@ -142,7 +172,13 @@ class AcousticModel(object):
         self.lr_decay_factor = float(lr_decay_factor)
         self.use_iterator = use_iterator
         h = self._handle
-        self._reserve = torch.empty(int(_lib.raw("rs_am_reserve_bytes")(h)), dtype=torch.uint8, device=self.device)
+        if self._tiles is None:
+            self._reserve = torch.empty(int(_lib.raw("rs_am_reserve_bytes")(h)), dtype=torch.uint8, device=self.device)
+        else:
+            self._reserve = None
+            for t in self._tiles:       # one backward per forward PER TILE: each tile keeps its own activations
+                t["reserve"] = torch.empty(int(_lib.raw("rs_am_reserve_bytes")(t["handle"])), dtype=torch.uint8,
+                                           device=self.device)
         self.grads = torch.zeros_like(self.params)
         self.adam_m = torch.zeros_like(self.params)
         self.adam_v = torch.zeros_like(self.params)
@@ -154,7 +190,8 @@ class AcousticModel(object):
     def __del__(self):
         try:
             if self._handle is not None:
-                _lib.raw("rs_am_destroy")(self._handle)
+                for th in (getattr(self, "_tile_handles", None) or [self._handle]):
+                    _lib.raw("rs_am_destroy")(th)
                 self._handle = None
         except Exception:
             pass
@@ -291,18 +328,44 @@ class AcousticModel(object):
         self._dropout_calls += 1
         seed = (int(self.seed) * 1000003 + self._dropout_calls) & 0xFFFFFFFFFFFFFFFF
         self._last_fwd = (keep_in, keep_out, seed, T)
-        _lib.call("rs_am_forward", self._handle, self.params.data_ptr(), x_d.data_ptr(), len_d.data_ptr(), T,
-                  self.rnn_state.data_ptr(), self.rnn_state.data_ptr() if keep_state else None,
-                  keep_in, keep_out, seed, logits.data_ptr(),
-                  self._reserve.data_ptr() if training else None, self._ws.data_ptr(), self._ws.numel(),
-                  _stream_ptr())
+        if self._tiles is None:
+            _lib.call("rs_am_forward", self._handle, self.params.data_ptr(), x_d.data_ptr(), len_d.data_ptr(), T,
+                      self.rnn_state.data_ptr(), self.rnn_state.data_ptr() if keep_state else None,
+                      keep_in, keep_out, seed, logits.data_ptr(),
+                      self._reserve.data_ptr() if training else None, self._ws.data_ptr(), self._ws.numel(),
+                      _stream_ptr())
+            return logits
+        for i, t in enumerate(self._tiles):
+            b0, b1 = t["b0"], t["b1"]
+            x_t = x_d[:T, b0:b1].contiguous()
+            len_t = len_d[b0:b1].contiguous()
+            st_t = self.rnn_state[:, :, b0:b1].contiguous()
+            lg_t = torch.empty((T, b1 - b0, self.num_labels), dtype=torch.float32, device=self.device)
+            _lib.call("rs_am_forward", t["handle"], self.params.data_ptr(), x_t.data_ptr(), len_t.data_ptr(), T,
+                      st_t.data_ptr(), st_t.data_ptr() if keep_state else None,
+                      keep_in, keep_out, (seed + 0x9E3779B97F4A7C15 * (i + 1)) & 0xFFFFFFFFFFFFFFFF, lg_t.data_ptr(),
+                      t["reserve"].data_ptr() if training else None, self._ws.data_ptr(), self._ws.numel(),
+                      _stream_ptr())
+            logits[:T, b0:b1] = lg_t
+            if keep_state:
+                self.rnn_state[:, :, b0:b1] = st_t
+            t["x"], t["len"] = (x_t, len_t) if training else (None, None)
         return logits
 
     def backward(self, x_d, len_d, dlogits):
         keep_in, keep_out, seed, T = self._last_fwd
-        _lib.call("rs_am_backward", self._handle, self.params.data_ptr(), x_d.data_ptr(), len_d.data_ptr(), T,
-                  keep_in, keep_out, seed, dlogits.data_ptr(), self._reserve.data_ptr(), self.grads.data_ptr(),
-                  self._ws.data_ptr(), self._ws.numel(), _stream_ptr())
+        if self._tiles is None:
+            _lib.call("rs_am_backward", self._handle, self.params.data_ptr(), x_d.data_ptr(), len_d.data_ptr(), T,
+                      keep_in, keep_out, seed, dlogits.data_ptr(), self._reserve.data_ptr(), self.grads.data_ptr(),
+                      self._ws.data_ptr(), self._ws.numel(), _stream_ptr())
+            return
+        for i, t in enumerate(self._tiles):
+            b0, b1 = t["b0"], t["b1"]
+            dl_t = dlogits[:T, b0:b1].contiguous()
+            _lib.call("rs_am_backward", t["handle"], self.params.data_ptr(), t["x"].data_ptr(), t["len"].data_ptr(), T,
+                      keep_in, keep_out, (seed + 0x9E3779B97F4A7C15 * (i + 1)) & 0xFFFFFFFFFFFFFFFF, dl_t.data_ptr(),
+                      t["reserve"].data_ptr(), self.grads.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                      _stream_ptr())
 
     def ctc_loss(self, logits, label_rows, len_d, want_grad=True):
         """tf.nn.ctc_loss(..., ignore_longer_outputs_than_inputs=True) + gradient.

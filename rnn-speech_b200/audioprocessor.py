@@ -115,12 +115,34 @@ class AudioProcessor(object):
                     raise ValueError("delta(mode='interp') needs at least 9 frames, got %d" % self.num_frames(n, sr))
         offsets = np.zeros(len(signals) + 1, dtype=np.int64)
         np.cumsum(lens, out=offsets[1:])
-        host = torch.empty((int(offsets[-1]),), dtype=torch.float32, pin_memory=True)
+        total = int(offsets[-1])
+        # Pinned staging, allocated once and reused (page-locking 20 MB per call costs more than the copy); two
+        # buffers alternate so that the copy of the previous call may still be in flight, and each utterance's
+        # H2D copy is issued as soon as it is staged so that staging and DMA overlap.
+        slot = self._stage_next = (getattr(self, "_stage_next", 0) + 1) % 2
+        stage = getattr(self, "_stage", None)
+        if stage is None:
+            stage = self._stage = [None, None]
+            self._stage_ev = [None, None]
+        opos = (total + 1) // 2 * 2                          # 8-byte aligned home of the int64 offsets
+        if stage[slot] is None or stage[slot].numel() < opos + len(offsets) * 2:
+            stage[slot] = torch.empty((max(opos + len(offsets) * 2, 1 << 16),), dtype=torch.float32, pin_memory=True)
+            self._stage_ev[slot] = torch.cuda.Event()
+        else:
+            self._stage_ev[slot].synchronize()              # the copy that last used this buffer has finished
+        host = stage[slot]
         hview = host.numpy()
+        pcm_d = torch.empty((total,), dtype=torch.float32, device=dev)
         for s, o in zip(signals, offsets[:-1]):
-            hview[o:o + len(s)] = np.asarray(s, dtype=np.float32)
-        pcm_d = host.to(dev, non_blocking=True)
-        off_d = torch.from_numpy(offsets).to(dev, non_blocking=True)
+            n = len(s)
+            hview[o:o + n] = s if isinstance(s, np.ndarray) and s.dtype == np.float32 else np.asarray(s, dtype=np.float32)
+            pcm_d[o:o + n].copy_(host[o:o + n], non_blocking=True)
+        # the int64 offsets ride in the tail of the same pinned buffer
+        oview = hview[opos:opos + len(offsets) * 2].view(np.int64)
+        oview[:] = offsets
+        off_d = torch.empty((len(offsets),), dtype=torch.int64, device=dev)
+        off_d.copy_(host[opos:opos + len(offsets) * 2].view(torch.int64), non_blocking=True)
+        self._stage_ev[slot].record()
         return self.features_device(pcm_d, off_d, len(signals), max(lens), sr, time_major=time_major)
 
     # ---------------------------------------------------------- reference API
@@ -146,3 +168,48 @@ class AudioProcessor(object):
         from .audiofile import load_audio
         sig, sr = load_audio(file_name)
         return self.process_signal(sig, sr)
+
+
+class BatchPrefetcher(object):
+    """Input prefetch, the counterpart of the reference pipeline's ``.map(..., num_parallel_calls=2).prefetch(30)``
+    (models/AcousticModel.py:819-822): staging, the host-to-device copy and the feature kernels of the NEXT
+    mini-batch run on a worker thread and a low-priority side stream while the model trains on the current one.
+
+        pre = BatchPrefetcher(audio_processor)
+        ticket = pre.submit(signals, sr)            # returns at once
+        ...                                         # train on the previous batch
+        feats, nframes = ticket.result()            # current stream waits for the side stream's event
+    """
+
+    class _Ticket(object):
+        def __init__(self, future):
+            self._future = future
+
+        def result(self):
+            feats, nframes, ev = self._future.result()
+            cur = torch.cuda.current_stream(feats.device)
+            cur.wait_event(ev)
+            feats.record_stream(cur)
+            nframes.record_stream(cur)
+            return feats, nframes
+
+    def __init__(self, audio_processor):
+        from concurrent.futures import ThreadPoolExecutor
+        self.audio_processor = audio_processor
+        self.device = audio_processor._dev()
+        self.stream = torch.cuda.Stream(device=self.device, priority=0)      # 0 = least urgent
+        self._pool = ThreadPoolExecutor(max_workers=1)
+
+    def _work(self, signals, sr, time_major):
+        torch.cuda.set_device(self.device)
+        with torch.cuda.stream(self.stream):
+            feats, nframes = self.audio_processor.process_batch(signals, sr, time_major=time_major)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return feats, nframes, ev
+
+    def submit(self, signals, sr, time_major=True):
+        return BatchPrefetcher._Ticket(self._pool.submit(self._work, signals, sr, time_major))
+
+    def close(self):
+        self._pool.shutdown(wait=True)

@@ -38,21 +38,32 @@ class AudioBatchDataset(object):
         from .audiofile import load_audio
         return load_audio(audio)
 
+    def _submit(self, prefetcher, start):
+        """Load one mini-batch on the host and hand its staging / H2D / feature kernels to the prefetcher."""
+        chunk = self.items[start:start + self.batch_size]
+        sigs, srs, labs = [], [], []
+        for audio, label in chunk:
+            sig, sr = self._load(audio)
+            sigs.append(sig)
+            srs.append(sr)
+            labs.append(labelcodec.get_str_labels(self.char_map, label) if isinstance(label, str)
+                        else list(label))
+        if len(set(srs)) != 1:
+            raise ValueError("all utterances of a mini-batch must share one sample rate, got %s" % sorted(set(srs)))
+        return prefetcher.submit(sigs, srs[0], time_major=True), labs, len(sigs)
+
     def __iter__(self):
+        """The next mini-batch's features are computed on a side stream while the caller trains on the current one
+        (the reference pipeline prefetches too: models/AcousticModel.py:819-822)."""
+        from .audioprocessor import BatchPrefetcher
         B = self.batch_size
-        for start in range(0, len(self.items), B):
-            chunk = self.items[start:start + B]
-            sigs, srs, labs = [], [], []
-            for audio, label in chunk:
-                sig, sr = self._load(audio)
-                sigs.append(sig)
-                srs.append(sr)
-                labs.append(labelcodec.get_str_labels(self.char_map, label) if isinstance(label, str)
-                            else list(label))
-            if len(set(srs)) != 1:
-                raise ValueError("all utterances of a mini-batch must share one sample rate, got %s" % sorted(set(srs)))
-            n_real = len(sigs)
-            feats, nframes = self.audio_processor.process_batch(sigs, srs[0], time_major=True)
+        prefetcher = BatchPrefetcher(self.audio_processor)
+        starts = list(range(0, len(self.items), B))
+        pending = self._submit(prefetcher, starts[0]) if starts else None
+        for i in range(len(starts)):
+            ticket, labs, n_real = pending
+            pending = self._submit(prefetcher, starts[i + 1]) if i + 1 < len(starts) else None
+            feats, nframes = ticket.result()
             if n_real < B:      # pad the batch (features 0, length 0)
                 full = torch.zeros((feats.shape[0], B, feats.shape[2]), dtype=feats.dtype, device=feats.device)
                 full[:, :n_real] = feats
@@ -68,6 +79,7 @@ class AudioBatchDataset(object):
                 nframes = torch.clamp(nframes, max=self.max_input_seq_length)
             width = max([len(l) for l in labs] + [1])
             dense = np.zeros((n_real, width), dtype=np.int32)
-            for i, l in enumerate(labs):
-                dense[i, :len(l)] = l
+            for i2, l in enumerate(labs):
+                dense[i2, :len(l)] = l
             yield feats, nframes, dense
+        prefetcher.close()

@@ -221,3 +221,56 @@ def test_cfg4_shape_wavefront_against_oracle(pkg, cuda, monkeypatch):
     err = np.abs(m.grads.cpu().numpy() - gw).max() / np.abs(gw).max()
     print("cfg-4 shape: gradient error %.2e of the largest entry" % err)
     assert err < 2e-3
+
+
+def test_batch_tiles_training_against_oracle(pkg, cuda):
+    """A mini-batch above the tensor-core kernels' 64 utterances runs as batch tiles (64 + 36 here) that share
+    parameters, gradients and workspace: logits, carried state and the accumulated gradient against the oracle."""
+    L, H, F, C, B, T = 2, 128, 40, 30, 100, 19
+    rng = np.random.default_rng(9)
+    p = model.init_params(L, H, F, C, seed=2, dtype=np.float64)
+    flat = model.flatten(p, L, H, F, C)
+    x = rng.standard_normal((T, B, F))
+    lens = rng.integers(1, T + 1, size=B).astype(np.int32)
+    lens[0] = T
+    state = [(rng.standard_normal((B, H)) * .3, rng.standard_normal((B, H)) * .3) for _ in range(L)]
+    m = _build(pkg, cuda, L, H, F, C, B, T, flat, training=True)
+    assert m.uses_tensor_cores and m._tiles is not None and len(m._tiles) == 2
+    m.rnn_state.copy_(_dev(np.stack([np.stack([c, h]) for c, h in state]), cuda, np.float32))
+    xd, ld = _dev(x, cuda, np.float32), _dev(lens, cuda, np.int32)
+    logits = m.forward(xd, ld, training=True)
+    want, new_state, cache = model.forward(p, x, lens, L, H, state=state)
+    np.testing.assert_allclose(logits.cpu().numpy(), want, atol=3e-4)
+    for l in range(L):
+        np.testing.assert_allclose(m.rnn_state[l, 0].cpu().numpy(), new_state[l][0], atol=2e-4)
+        np.testing.assert_allclose(m.rnn_state[l, 1].cpu().numpy(), new_state[l][1], atol=2e-4)
+    dl = rng.standard_normal(want.shape) * (np.arange(T)[:, None, None] < lens[None, :, None])
+    m.grads.zero_()
+    m.backward(xd, ld, _dev(dl, cuda, np.float32))
+    gw = model.flatten(model.backward(p, cache, dl, L, H), L, H, F, C)
+    assert np.abs(m.grads.cpu().numpy() - gw).max() < 2e-3 * np.abs(gw).max()
+
+
+def test_cfg5_shape_inference_greedy_labels(pkg, cuda):
+    """BASELINE config 5 (forward only, batch 256, 3x768) at a frame count the float64 oracle finishes in seconds:
+    four batch tiles through the tensor-core path; logits and greedy label ids (process_input) against the oracle."""
+    L, H, F, C, B, T = 3, 768, 120, 80, 256, 20
+    rng = np.random.default_rng(55)
+    p = model.init_params(L, H, F, C, seed=8, dtype=np.float64)
+    flat = model.flatten(p, L, H, F, C)
+    x = rng.standard_normal((T, B, F)).astype(np.float32)
+    lens = rng.integers(T // 2, T + 1, size=B).astype(np.int32)
+    m = _build(pkg, cuda, L, H, F, C, B, T, flat, training=False)
+    assert m.uses_tensor_cores and len(m._tiles) == 4
+    logits = m.forward(_dev(x, cuda, np.float32), _dev(lens, cuda, np.int32), training=False, keep_state=False)
+    want, _, _ = model.forward(p, x.astype(np.float64), lens, L, H, keep_cache=False)
+    got = logits.cpu().numpy()
+    assert np.abs(got - want).max() < 3e-4
+    _assert_labels_match(got, want, lens)
+    pred = m.process_input(None, x, lens)
+    ref = ctc.greedy_decode(want, lens)
+    margin_ok = (ctc.top2_margin(want, lens) > MARGIN) | (np.arange(T)[:, None] >= lens[None, :])
+    for b in range(B):
+        if margin_ok[:, b].all():
+            row = pred[b]
+            np.testing.assert_array_equal(row[row != C], np.asarray(ref[b]))

@@ -328,6 +328,31 @@ def trace_diag():
             print("  %s layer %d: %s" % (tag, l, " ".join("[%.2f-%.2f]" % (a, b) for a, b in tr[d][l])))
 
 
+def e2e_diag():
+    """Host-side cost of the public-API training step at cfg-2: how long each call takes to RETURN (enqueue time)
+    versus the device time of the step."""
+    import time
+    L, H, F, C, B, n = 3, 768, 120, 80, 32, 160000
+    rng = np.random.default_rng(0)
+    sigs = [(0.1 * rng.standard_normal(n)).astype(np.float32) for _ in range(B)]
+    labs = [np.append(rng.integers(1, 79, size=rng.integers(60, 121)), 79).astype(np.int32) for _ in range(B)]
+    ap = rs.AudioProcessor(1000, "fbank", device=dev)
+    m = rs.AcousticModel(L, H, B, 1000, 600, F, False, C, device=dev)
+    m.create_training_rnn(0.8, 0.5, 1, 3e-4, 0.33)
+    m.initialize(None)
+    for it in range(6):
+        torch.cuda.synchronize()
+        t = [time.perf_counter()]
+        f, nf = ap.process_batch(sigs, 16000, time_major=True); t.append(time.perf_counter())
+        m.start_batch(None, True); t.append(time.perf_counter())
+        m.step_on_batch(f, nf, labs, compute_gradients=True, compute_error_rate=False); t.append(time.perf_counter())
+        loss = m.end_batch(None, True, rnn_state_reset_ratio=1.0)[0]; t.append(time.perf_counter())
+        if it >= 2:
+            d = np.diff(t) * 1e3
+            print("e2e host ms: process_batch %.2f  start_batch %.2f  step_on_batch (enqueue) %.2f  end_batch (sync + read) %.2f"
+                  "  total %.2f" % (d[0], d[1], d[2], d[3], (t[-1] - t[0]) * 1e3))
+
+
 def bf16_round(x):
     return torch.from_numpy(np.asarray(x, np.float32)).to(torch.bfloat16).to(torch.float32).numpy().astype(np.float64)
 
@@ -391,6 +416,8 @@ if __name__ == "__main__":
         ts_diag()
     if "gemmbench" in which:
         gemm_bench()
+    if "e2e" in which:
+        e2e_diag()
     if "trace" in which:
         trace_diag()
     if "mma" in which:
