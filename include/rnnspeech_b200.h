@@ -170,6 +170,16 @@ int rs_ctc_loss_grad(const float* logits_d, const int32_t* labels_d, const int32
 /* out_d int32 [B, T] (decoded ids, row-padded with -1), out_len_d int32 [B] */
 int rs_ctc_greedy_decode(const float* logits_d, const int32_t* len_d, int T, int B, int C, int blank,
                          int32_t* out_d, int32_t* out_len_d, void* stream);
+/* Beam search decoder.  Replaces tf.nn.ctc_beam_search_decoder(logits, seq_len) -- the reference's `prediction`
+ * (models/AcousticModel.py:312-314: beam_width 100, top_paths 1, merge_repeated True, blank = C-1).
+ *   normalize   1: log-softmax the scores per frame (TF >= 1.12), 0: subtract the maximum only; the decoded
+ *               path is the same, only out_score_d differs
+ *   out_d       int32 [B, T] top path, row-padded with -1;  out_len_d int32 [B];  out_score_d float32 [B] or NULL
+ *   limits      beam_width <= 128, C <= 128, beam_width * C <= 8184 */
+size_t rs_ctc_beam_workspace_bytes(int T, int B);
+int rs_ctc_beam_search(const float* logits_d, const int32_t* len_d, int T, int B, int C, int beam_width,
+                       int merge_repeated, int normalize, int32_t* out_d, int32_t* out_len_d,
+                       float* out_score_d, void* ws_d, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * Update rule.  Replaces tf.clip_by_global_norm + AdamOptimizer.apply_gradients

@@ -173,3 +173,116 @@ def top2_margin(logits, seq_len):
     gap = part[..., C - 1] - part[..., C - 2]
     mask = np.arange(T)[:, None] < np.asarray(seq_len)[None, :]
     return np.where(mask, gap, np.inf)
+
+
+# --------------------------------------------------------------------------------------
+# CTC beam search: tf.nn.ctc_beam_search_decoder(logits, seq_len, beam_width=100, top_paths=1,
+# merge_repeated=True) as called at /root/reference/models/AcousticModel.py:312 (defaults).
+# Restates tensorflow/core/util/ctc/ctc_beam_search.h (CTCBeamSearchDecoder::Step / TopPaths,
+# BeamEntry::LabelSeq) with the default scorer (all expansion scores 0) [3P, TensorFlow is absent
+# from the reference tree and not installable here: parity unpinned upstream].
+#   * per step the class scores are the logits minus their maximum (TF >= 1.12 also subtracts the
+#     log-sum-exp; every beam holds exactly one emission per step, so either way adds the same
+#     constant to all beams: the ranking and the decoded path do not depend on it -- `normalize`);
+#   * each beam entry keeps log P(blank-ended), log P(label-ended) and their sum;
+#   * an entry's label-ended mass also receives its parent's mass when the parent is still in the
+#     beam ("Active"); an extension that already exists as an active entry is not created twice;
+#   * the beam is the `beam_width` best of (updated entries + new extensions) by total, incumbents
+#     win ties (TopN is filled with the updated entries first, a new leaf must be strictly better
+#     than the bottom);
+#   * top path = best total; merge_repeated=True collapses equal neighbours of the OUTPUT labels
+#     (LabelSeq), which is TF's documented quirk.
+# float32 arithmetic like TF; tie order among exactly equal totals is unspecified in TF (heap) and
+# fixed here as: updated entries before new extensions, then lower beam slot, then lower label.
+class _BeamEntry(object):
+    __slots__ = ("parent", "label", "children", "oldp", "newp")
+
+    def __init__(self, parent, label):
+        self.parent, self.label, self.children = parent, label, None
+        ninf = np.float32(-np.inf)
+        self.oldp = [ninf, ninf, ninf]      # total, blank, label
+        self.newp = [ninf, ninf, ninf]
+
+    def active(self):
+        return self.newp[0] != -np.inf
+
+
+def _lse32(a, b):
+    a, b = np.float32(a), np.float32(b)
+    if a == -np.inf:
+        return b
+    if b == -np.inf:
+        return a
+    m = max(a, b)
+    return np.float32(m + np.log1p(np.exp(np.float32(-abs(a - b)), dtype=np.float32), dtype=np.float32))
+
+
+def beam_search_decode(logits, seq_len, beam_width=100, merge_repeated=True, blank=None, normalize=True):
+    """Returns (list of B int32 arrays: the top path, float32 [B]: its log score)."""
+    logits = np.asarray(logits, dtype=np.float32)
+    T, B, C = logits.shape
+    blank = C - 1 if blank is None else blank
+    assert blank == C - 1, "TF's decoder fixes the blank at num_classes - 1"
+    outs, scores = [], np.zeros(B, np.float32)
+    for b in range(B):
+        root = _BeamEntry(None, -1)
+        root.newp = [np.float32(0.0), np.float32(0.0), np.float32(-np.inf)]
+        leaves = [root]
+        for t in range(int(seq_len[b])):
+            raw = logits[t, b]
+            inp = raw - raw.max()
+            if normalize:
+                inp = inp - np.log(np.exp(inp, dtype=np.float32).sum(dtype=np.float32), dtype=np.float32)
+            inp = inp.astype(np.float32)
+            branches = leaves           # kept sorted by newp.total, descending
+            for e in branches:
+                e.oldp = list(e.newp)
+            for e in branches:
+                if e.parent is not None:
+                    if e.parent.active():
+                        prev = e.parent.oldp[1] if e.label == e.parent.label else e.parent.oldp[0]
+                        e.newp[2] = _lse32(e.newp[2], prev)
+                    e.newp[2] = np.float32(e.newp[2] + inp[e.label])
+                e.newp[1] = np.float32(e.oldp[0] + inp[blank])
+                e.newp[0] = _lse32(e.newp[1], e.newp[2])
+            cands = [(e.newp[0], 0, i, -1, e) for i, e in enumerate(branches)]
+            for i, e in enumerate(branches):
+                if e.children is None:
+                    e.children = {}
+                for c in range(C - 1):
+                    ch = e.children.get(c)
+                    if ch is not None and ch.active():
+                        continue
+                    prev = e.oldp[1] if c == e.label else e.oldp[0]
+                    tot = np.float32(inp[c] + prev)
+                    if tot > -np.inf:
+                        cands.append((tot, 1, i, c, e))
+            # beam_width best by total; incumbents first on ties, then slot, then label
+            cands.sort(key=lambda x: (-float(x[0]), x[1], x[2], x[3]))
+            keep = cands[:beam_width]
+            new_leaves, kept_ids = [], set()
+            for tot, kind, i, c, e in keep:
+                if kind == 0:
+                    new_leaves.append(e)
+                    kept_ids.add(id(e))
+                else:
+                    ch = e.children.get(c)
+                    if ch is None:
+                        ch = e.children[c] = _BeamEntry(e, c)
+                    ch.newp = [tot, np.float32(-np.inf), tot]
+                    new_leaves.append(ch)
+                    kept_ids.add(id(ch))
+            for e in branches:
+                if id(e) not in kept_ids:           # evicted: "bottom->newp.Reset()"
+                    e.newp = [np.float32(-np.inf)] * 3
+            leaves = new_leaves
+        best = leaves[0]
+        scores[b] = best.newp[0]
+        seq, prev_label, e = [], -1, best
+        while e.parent is not None:
+            if not merge_repeated or e.label != prev_label:
+                seq.append(e.label)
+            prev_label = e.label
+            e = e.parent
+        outs.append(np.array(seq[::-1], dtype=np.int32))
+    return outs, scores

@@ -92,6 +92,7 @@ class AcousticModel(object):
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.seed = seed
         self.beta_skip = _lib.CTC_BETA_SOURCE
+        self.decoder = "beam"            # the reference's prediction op; "greedy" = per-frame argmax path
 
         self.input_keep_prob = self.output_keep_prob = 1.0
         self.grad_clip = None
@@ -393,11 +394,33 @@ class AcousticModel(object):
                   out.data_ptr(), out_len.data_ptr(), _stream_ptr())
         return out, out_len
 
+    def beam_search_decode(self, logits, len_d, beam_width=100, merge_repeated=True, normalize=True):
+        """tf.nn.ctc_beam_search_decoder(logits, seq_len) with its defaults (models/AcousticModel.py:312): the top
+        path per item.  Returns (ids [B,T] int32 padded with -1, lengths [B], log scores [B]) on the device."""
+        T, B, C = logits.shape
+        out = torch.empty((B, T), dtype=torch.int32, device=self.device)
+        out_len = torch.empty((B,), dtype=torch.int32, device=self.device)
+        score = torch.empty((B,), dtype=torch.float32, device=self.device)
+        need = int(_lib.raw("rs_ctc_beam_workspace_bytes")(T, B))
+        if getattr(self, "_beam_ws", None) is None or self._beam_ws.numel() < need:
+            self._beam_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.call("rs_ctc_beam_search", logits.data_ptr(), len_d.data_ptr(), T, B, C, int(beam_width),
+                  1 if merge_repeated else 0, 1 if normalize else 0, out.data_ptr(), out_len.data_ptr(),
+                  score.data_ptr(), self._beam_ws.data_ptr(), self._beam_ws.numel(), _stream_ptr())
+        return out, out_len, score
+
+    def predict(self, logits, len_d):
+        """The reference's `prediction` (models/AcousticModel.py:312-314): beam search, width 100, top path;
+        self.decoder = "greedy" selects the per-frame argmax path instead."""
+        if self.decoder == "greedy":
+            return self.greedy_decode(logits, len_d)
+        ids, lens, _ = self.beam_search_decode(logits, len_d)
+        return ids, lens
+
     def _error_rate(self, logits, len_d, label_rows):
         """mean over the batch of edit_distance(prediction, truth) / len(truth)
-        (tf.edit_distance(normalize=True), models/AcousticModel.py:370); the
-        prediction here is the greedy path (the reference uses beam search)."""
-        ids, lens = self.greedy_decode(logits, len_d)
+        (tf.edit_distance(normalize=True), models/AcousticModel.py:370)."""
+        ids, lens = self.predict(logits, len_d)
         ids = ids.cpu().numpy()
         lens = lens.cpu().numpy()
         rates = []
@@ -549,7 +572,7 @@ class AcousticModel(object):
         x = torch.as_tensor(np.ascontiguousarray(np.asarray(inputs, dtype=np.float32))).to(self.device)
         lens = torch.as_tensor(np.asarray(input_seq_lengths, dtype=np.int32)).to(self.device)
         logits = self.forward(x, lens, training=False, keep_state=False)
-        ids, out_len = self.greedy_decode(logits, lens)
+        ids, out_len = self.predict(logits, lens)
         ids = ids.cpu().numpy()
         out_len = out_len.cpu().numpy()
         width = int(out_len.max()) if len(out_len) else 0

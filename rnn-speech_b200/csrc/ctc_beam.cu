@@ -1,0 +1,307 @@
+// CTC beam search decoder for sm_100a.
+//
+// Replaces decoded, _ = tf.nn.ctc_beam_search_decoder(logits, input_seq_lengths) -- the reference's
+// `prediction` (/root/reference/models/AcousticModel.py:312-314; defaults beam_width = 100,
+// top_paths = 1, merge_repeated = True), which also feeds its error rate (:370).  The algorithm is
+// TensorFlow's (core/util/ctc/ctc_beam_search.h: CTCBeamSearchDecoder::Step / TopPaths,
+// BeamEntry::LabelSeq) with the default scorer; oracle/ctc.py::beam_search_decode restates it rule
+// by rule and is what the tests compare with.  TF is absent from the reference tree: parity unpinned
+// upstream.
+//
+// One CTA per utterance, the beam (<= 128 entries) in shared memory.  Per time step:
+//   1. class scores = logits - max (- log-sum-exp), one warp;
+//   2. every entry: old <- new; label-ended mass += parent's mass if the parent is still in the beam
+//      (parents are found through a 256-slot hash table of the entries' prefix hashes -- an entry's
+//      identity is the 64-bit hash of its label sequence, so a prefix that leaves the beam and comes
+//      back is the same node, as in TF's prefix tree); blank-ended mass; total;
+//   3. extensions (entry x label) that do not already exist as entries are scored; only those above
+//      the lowest updated total can enter a full beam (exactly TF's is_candidate test), they are
+//      compacted into a candidate list behind the updated entries;
+//   4. bitonic sort of the list by (total desc, incumbents first, slot, label) -- usually a few
+//      hundred elements, 8192 at worst (near-uniform scores) -- and the best beam_width become the new
+//      beam; (previous slot, label) of every new entry goes to a [T][W] history in the workspace;
+//   5. after the last frame the history is walked back from slot 0 (the best total).
+#include "common.cuh"
+
+namespace rs {
+namespace {
+
+constexpr int kMaxW = 128;          // beam entries
+constexpr int kMaxC = 128;          // classes
+constexpr int kHash = 256;          // hash-table slots (>= 2 * kMaxW)
+constexpr int kThreads = 256;
+constexpr int kRankMax = 1024;      // candidate lists up to this size are ordered by counting ranks
+constexpr int kMaxCand = 8192;      // >= kMaxW + kMaxW * (kMaxC - 1) is not needed: W * (C - 1) + W <= 8192 is checked
+constexpr float kNegInf = -INFINITY;
+
+__device__ __forceinline__ float lse2f(float a, float b) {      // TF LogSumExp
+  if (a == kNegInf) return b;
+  if (b == kNegInf) return a;
+  return fmaxf(a, b) + log1pf(expf(-fabsf(a - b)));
+}
+__device__ __forceinline__ unsigned long long mix64(unsigned long long h, int label) {
+  unsigned long long z = (h ^ (unsigned long long)(label + 1)) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z ? z : 1ull;               // 0 marks an empty hash slot
+}
+
+struct Beam {                        // structure of arrays, one set per buffer
+  unsigned long long node[kMaxW], parent[kMaxW];
+  int label[kMaxW];
+  float tot[kMaxW], blk[kMaxW], lab[kMaxW];
+};
+
+// (key desc, id asc): ids < kMaxW are updated entries (incumbents), id = kMaxW + slot * (C-1) + label otherwise
+__device__ __forceinline__ bool before(float ka, int ia, float kb, int ib) {
+  return (ka > kb) || (ka == kb && ia < ib);
+}
+
+__global__ void __launch_bounds__(kThreads)
+ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, int T, int B, int C, int W,
+                int merge_repeated, int normalize, unsigned char* __restrict__ hist, int* __restrict__ out,
+                int* __restrict__ out_len, float* __restrict__ out_score) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  float* ckey = reinterpret_cast<float*>(dyn);                 // [kMaxCand]
+  int* cid = reinterpret_cast<int*>(ckey + kMaxCand);          // [kMaxCand]
+  __shared__ Beam beam[2];
+  __shared__ float old_tot[kMaxW], old_blk[kMaxW], old_lab[kMaxW];
+  __shared__ unsigned long long hkey[kHash];
+  __shared__ int hslot[kHash];
+  __shared__ unsigned childmask[kMaxW][4];
+  __shared__ float in[kMaxC];
+  __shared__ int s_count;
+  __shared__ float s_lb;
+  __shared__ float vals[2 * kMaxW];
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = min(len[b], T);
+  const int blank = C - 1, nlab = C - 1;
+  unsigned char* hprev = hist + (size_t)b * 2 * T * kMaxW;     // [T][kMaxW] previous slot (255 = none)
+  unsigned char* hlab = hprev + (size_t)T * kMaxW;             // [T][kMaxW] appended label (255 = none)
+
+  int cur = 0, n = 1;
+  if (tid == 0) {
+    Beam& r = beam[0];
+    r.node[0] = 0x243F6A8885A308D3ull; r.parent[0] = 0ull; r.label[0] = -1;
+    r.tot[0] = 0.f; r.blk[0] = 0.f; r.lab[0] = kNegInf;
+  }
+  __syncthreads();
+
+  for (int t = 0; t < L; ++t) {
+    Beam& bm = beam[cur];
+    Beam& nx = beam[cur ^ 1];
+    // ---- 1. class scores
+    if (warp == 0) {
+      const float* row = logits + ((size_t)t * B + b) * C;
+      float m = kNegInf;
+      for (int k = lane; k < C; k += 32) m = fmaxf(m, row[k]);
+      m = warp_max(m);
+      float s = 0.f;
+      if (normalize) {
+        for (int k = lane; k < C; k += 32) s += expf(row[k] - m);
+        s = logf(warp_sum(s));
+      }
+      for (int k = lane; k < C; k += 32) in[k] = (row[k] - m) - s;
+    }
+    // hash table of the entries' prefixes; old <- new
+    for (int i = tid; i < kHash; i += kThreads) hkey[i] = 0ull;
+    for (int i = tid; i < kMaxW * 4; i += kThreads) (&childmask[0][0])[i] = 0u;
+    if (tid < n) { old_tot[tid] = bm.tot[tid]; old_blk[tid] = bm.blk[tid]; old_lab[tid] = bm.lab[tid]; }
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    if (tid < n) {
+      unsigned h = (unsigned)(bm.node[tid] >> 17) & (kHash - 1);
+      while (true) {
+        const unsigned long long prev = atomicCAS(&hkey[h], 0ull, bm.node[tid]);
+        if (prev == 0ull) { hslot[h] = tid; break; }
+        h = (h + 1) & (kHash - 1);
+      }
+    }
+    __syncthreads();
+    // ---- 2. update the entries
+    float my_tot = kNegInf;
+    if (tid < n) {
+      const int lab = bm.label[tid];
+      float nl = old_lab[tid];
+      if (lab >= 0) {
+        int ps = -1;
+        const unsigned long long pk = bm.parent[tid];
+        unsigned h = (unsigned)(pk >> 17) & (kHash - 1);
+        while (hkey[h] != 0ull) {
+          if (hkey[h] == pk) { ps = hslot[h]; break; }
+          h = (h + 1) & (kHash - 1);
+        }
+        if (ps >= 0) {
+          const float previous = (lab == bm.label[ps]) ? old_blk[ps] : old_tot[ps];
+          nl = lse2f(nl, previous);
+          atomicOr(&childmask[ps][lab >> 5], 1u << (lab & 31));
+        }
+        nl += in[lab];
+      }
+      const float nb = old_tot[tid] + in[blank];
+      const float nt = lse2f(nb, nl);
+      bm.lab[tid] = nl; bm.blk[tid] = nb; bm.tot[tid] = nt;
+      ckey[tid] = nt; cid[tid] = tid;
+      my_tot = nt;
+    }
+    // ---- 2b. a bound on what can enter the beam.  The beam_width-th best of (updated totals + each entry's
+    // best new extension) is reached by at least beam_width candidates, so nothing below it can be kept.  (TF's
+    // own test -- a new leaf must beat the current bottom of a full beam -- prunes less and keeps the same set.)
+    {
+      const int slot = tid >> 1, half = tid & 1;
+      float best = kNegInf;
+      if (slot < n) {
+        const int lab = bm.label[slot];
+        const float pt = old_tot[slot], pb = old_blk[slot];
+        for (int c = half; c < nlab; c += 2) {
+          if (childmask[slot][c >> 5] & (1u << (c & 31))) continue;
+          best = fmaxf(best, in[c] + ((c == lab) ? pb : pt));
+        }
+      }
+      best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 1));
+      if (half == 0) vals[kMaxW + slot] = (slot < n) ? best : kNegInf;
+      if (tid < kMaxW) vals[tid] = (tid < n) ? my_tot : kNegInf;
+    }
+    __syncthreads();
+    {
+      // rank of vals[tid] among the 2 * kMaxW values (descending, index breaks ties): one thread finds the bound
+      const float v = vals[tid];
+      int rank = 0;
+      for (int j = 0; j < 2 * kMaxW; ++j) {
+        const float u = vals[j];
+        rank += (u > v || (u == v && j < tid)) ? 1 : 0;
+      }
+      if (tid == 0) s_lb = kNegInf;
+      __syncthreads();
+      if (rank == W - 1) s_lb = v;                        // -inf when fewer than W finite values exist
+    }
+    __syncthreads();
+    // ---- 3. extensions
+    const float lbv = s_lb;
+    const int next = n * nlab;
+    for (int idx = tid; idx < next; idx += kThreads) {
+      const int slot = idx / nlab, c = idx - slot * nlab;
+      if (childmask[slot][c >> 5] & (1u << (c & 31))) continue;       // exists as an active entry: handled in 2.
+      const float previous = (c == bm.label[slot]) ? old_blk[slot] : old_tot[slot];
+      const float tot = in[c] + previous;
+      if (tot > kNegInf && tot >= lbv) {
+        const int pos = n + atomicAdd(&s_count, 1);
+        ckey[pos] = tot;
+        cid[pos] = kMaxW + idx;
+      }
+    }
+    __syncthreads();
+    const int count = n + s_count;
+    const int newn = min(W, count);
+    const float* skey = ckey;
+    const int* sid = cid;
+    if (count <= kRankMax) {
+      // ---- 4a. few candidates (the usual case): rank by counting, the best newn land in order in the upper half
+      float* okey = ckey + kMaxCand / 2;
+      int* oid = cid + kMaxCand / 2;
+      for (int i = tid; i < count; i += kThreads) {
+        const float v = ckey[i];
+        const int id = cid[i];
+        int rank = 0;
+        for (int j = 0; j < count; ++j) rank += before(ckey[j], cid[j], v, id) ? 1 : 0;
+        if (rank < newn) { okey[rank] = v; oid[rank] = id; }
+      }
+      skey = okey; sid = oid;
+      __syncthreads();
+    } else {
+      // ---- 4b. bitonic sort, best first
+      int p2 = 32;
+      while (p2 < count) p2 <<= 1;
+      for (int i = count + tid; i < p2; i += kThreads) { ckey[i] = kNegInf; cid[i] = 0x7fffffff; }
+      __syncthreads();
+      for (int k = 2; k <= p2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < p2; i += kThreads) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const float ka = ckey[i], kb = ckey[ixj];
+              const int ia = cid[i], ib = cid[ixj];
+              const bool up = (i & k) == 0;                 // this block ends up best-first
+              const bool swap = up ? before(kb, ib, ka, ia) : before(ka, ia, kb, ib);
+              if (swap) { ckey[i] = kb; ckey[ixj] = ka; cid[i] = ib; cid[ixj] = ia; }
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+    if (tid < newn) {
+      const int id = sid[tid];
+      if (id < kMaxW) {                                   // an updated entry stays
+        nx.node[tid] = bm.node[id]; nx.parent[tid] = bm.parent[id]; nx.label[tid] = bm.label[id];
+        nx.tot[tid] = bm.tot[id]; nx.blk[tid] = bm.blk[id]; nx.lab[tid] = bm.lab[id];
+        hprev[(size_t)t * kMaxW + tid] = (unsigned char)id;
+        hlab[(size_t)t * kMaxW + tid] = 255;
+      } else {                                            // a new extension enters
+        const int idx = id - kMaxW, slot = idx / nlab, c = idx - slot * nlab;
+        nx.node[tid] = mix64(bm.node[slot], c); nx.parent[tid] = bm.node[slot]; nx.label[tid] = c;
+        nx.tot[tid] = skey[tid]; nx.blk[tid] = kNegInf; nx.lab[tid] = skey[tid];
+        hprev[(size_t)t * kMaxW + tid] = (unsigned char)slot;
+        hlab[(size_t)t * kMaxW + tid] = (unsigned char)c;
+      }
+    }
+    n = newn;
+    cur ^= 1;
+    __syncthreads();
+  }
+
+  // ---- 5. walk the history back from the best entry (slot 0), then LabelSeq(merge_repeated)
+  if (tid == 0) {
+    int* seq = out + (size_t)b * T;
+    int m = 0, s = 0;
+    for (int t = L - 1; t >= 0; --t) {
+      const int lab = hlab[(size_t)t * kMaxW + s];
+      if (lab != 255) seq[m++] = lab;                    // reversed order for now
+      s = hprev[(size_t)t * kMaxW + s];
+    }
+    for (int i = 0; i < m / 2; ++i) { const int x = seq[i]; seq[i] = seq[m - 1 - i]; seq[m - 1 - i] = x; }
+    int w = 0;
+    for (int i = 0; i < m; ++i)
+      if (!merge_repeated || i == 0 || seq[i] != seq[i - 1]) seq[w++] = seq[i];
+    for (int i = w; i < T; ++i) seq[i] = -1;
+    out_len[b] = w;
+    if (out_score) out_score[b] = (L > 0) ? beam[cur].tot[0] : 0.f;
+  }
+}
+
+}  // namespace
+}  // namespace rs
+
+using namespace rs;
+
+extern "C" size_t rs_ctc_beam_workspace_bytes(int T, int B) {
+  if (T <= 0 || B <= 0) return 0;
+  return (size_t)B * 2 * T * kMaxW;
+}
+
+extern "C" int rs_ctc_beam_search(const float* logits_d, const int32_t* len_d, int T, int B, int C, int beam_width,
+                                  int merge_repeated, int normalize, int32_t* out_d, int32_t* out_len_d,
+                                  float* out_score_d, void* ws_d, size_t ws_bytes, void* stream) {
+  RS_REQUIRE(logits_d && len_d && out_d && out_len_d && ws_d, RS_ERR_INVALID, "rs_ctc_beam_search: NULL argument");
+  RS_REQUIRE(T > 0 && B > 0 && C > 1, RS_ERR_INVALID, "rs_ctc_beam_search: bad shape T=%d B=%d C=%d", T, B, C);
+  RS_REQUIRE(C <= kMaxC, RS_ERR_UNSUPPORTED, "rs_ctc_beam_search: %d classes > %d", C, kMaxC);
+  RS_REQUIRE(beam_width >= 1 && beam_width <= kMaxW, RS_ERR_UNSUPPORTED, "rs_ctc_beam_search: beam_width %d outside [1,%d]",
+             beam_width, kMaxW);
+  RS_REQUIRE(beam_width + beam_width * (C - 1) + 8 <= kMaxCand, RS_ERR_UNSUPPORTED,
+             "rs_ctc_beam_search: beam_width * classes = %d candidates > %d", beam_width * C, kMaxCand);
+  RS_REQUIRE(ws_bytes >= rs_ctc_beam_workspace_bytes(T, B), RS_ERR_WORKSPACE, "rs_ctc_beam_search: workspace %zu < %zu",
+             ws_bytes, rs_ctc_beam_workspace_bytes(T, B));
+  const size_t smem = (size_t)kMaxCand * (sizeof(float) + sizeof(int));
+  static bool attr_done = false;
+  if (!attr_done) {
+    RS_CHECK_CUDA(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  ctc_beam_kernel<<<B, kThreads, smem, (cudaStream_t)stream>>>(logits_d, len_d, T, B, C, beam_width, merge_repeated ? 1 : 0,
+                                                               normalize ? 1 : 0, (unsigned char*)ws_d, out_d, out_len_d,
+                                                               out_score_d);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}

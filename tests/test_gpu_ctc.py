@@ -124,3 +124,62 @@ def test_greedy_decode_full_size(pkg, cuda):
     ids, n = ids.cpu().numpy(), n.cpu().numpy()
     for b in range(B):
         np.testing.assert_array_equal(ids[b, :n[b]], want[b])
+
+
+@pytest.mark.parametrize("T,B,C,W,scale,merge", [
+    (50, 6, 80, 100, 3.0, True),        # the reference's call: width 100, merge_repeated
+    (24, 4, 80, 100, 0.05, True),       # near-uniform scores: thousands of extensions compete every frame
+    (60, 5, 30, 16, 2.0, False),        # narrow beam: entries leave the beam and their prefixes come back
+    (40, 3, 5, 100, 1.0, True),         # beam wider than the number of live prefixes
+])
+def test_beam_search_matches_the_tf_restatement(pkg, cuda, T, B, C, W, scale, merge):
+    """rs_ctc_beam_search against oracle/ctc.py::beam_search_decode (TF's CTCBeamSearchDecoder, float32): same top
+    path and score.  An item whose best two beam totals differ by less than 1e-4 is a tie at fp32 resolution and is
+    only required to score the same."""
+    rng = np.random.default_rng(T * 100 + C)
+    logits = (rng.standard_normal((T, B, C)) * scale).astype(np.float32)
+    lens = rng.integers(T // 2, T + 1, size=B).astype(np.int32)
+    lens[0] = T
+    if B > 3:
+        lens[-1] = 0
+    m = _model(pkg, cuda, B, T, C)
+    ids, n, score = m.beam_search_decode(torch.from_numpy(logits).to(cuda), torch.from_numpy(lens).to(cuda),
+                                         beam_width=W, merge_repeated=merge)
+    ids, n, score = ids.cpu().numpy(), n.cpu().numpy(), score.cpu().numpy()
+    want, want_score = ctc.beam_search_decode(logits, lens, beam_width=W, merge_repeated=merge)
+    for b in range(B):
+        assert abs(score[b] - want_score[b]) < 1e-3 * max(1.0, abs(want_score[b]))
+        got = ids[b, :n[b]]
+        if list(got) != list(want[b]):
+            # accept only a genuine tie: the GPU's path must score like the oracle's best
+            alt, alt_score = ctc.beam_search_decode(logits[:, b:b + 1], lens[b:b + 1], beam_width=W, merge_repeated=merge)
+            assert abs(score[b] - alt_score[0]) < 1e-4, "item %d: different path, scores %g vs %g" % (b, score[b], alt_score[0])
+        assert np.all(ids[b, n[b]:] == -1)
+
+
+def test_beam_search_full_size_and_process_input(pkg, cuda):
+    """cfg-2 sized logits (T=998, B=32, C=80): runs, agrees with greedy decoding on peaky outputs (where the best
+    labelling is the best path), and one item is checked against the restatement on its first 150 frames."""
+    rng = np.random.default_rng(3)
+    T, B, C = 998, 32, 80
+    logits = (rng.standard_normal((T, B, C)) * 8).astype(np.float32)
+    lens = np.full(B, T, np.int32)
+    lens[1::3] = rng.integers(T // 2, T, size=len(lens[1::3]))
+    m = _model(pkg, cuda, B, T, C)
+    lg, ld = torch.from_numpy(logits).to(cuda), torch.from_numpy(lens).to(cuda)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ids, n, score = m.beam_search_decode(lg, ld, merge_repeated=False)
+    e1.record()
+    torch.cuda.synchronize()
+    print("beam search T=998 B=32 C=80 width 100: %.2f ms" % e0.elapsed_time(e1))
+    gids, gn = m.greedy_decode(lg, ld)
+    ids, n, gids, gn = ids.cpu().numpy(), n.cpu().numpy(), gids.cpu().numpy(), gn.cpu().numpy()
+    same = sum(int(n[b] == gn[b] and np.array_equal(ids[b, :n[b]], gids[b, :gn[b]])) for b in range(B))
+    print("beam == greedy on %d of %d items" % (same, B))
+    assert same >= B // 2, "beam and greedy paths differ on %d of %d peaky items" % (B - same, B)
+    short = np.minimum(lens, 150).astype(np.int32)
+    ids2, n2, _ = m.beam_search_decode(lg, torch.from_numpy(short).to(cuda), merge_repeated=True)
+    want, _ = ctc.beam_search_decode(logits[:150, :1], short[:1], merge_repeated=True)
+    np.testing.assert_array_equal(ids2[0, :int(n2[0])].cpu().numpy(), want[0])

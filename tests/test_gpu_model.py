@@ -267,6 +267,7 @@ def test_cfg5_shape_inference_greedy_labels(pkg, cuda):
     got = logits.cpu().numpy()
     assert np.abs(got - want).max() < 3e-4
     _assert_labels_match(got, want, lens)
+    m.decoder = "greedy"
     pred = m.process_input(None, x, lens)
     ref = ctc.greedy_decode(want, lens)
     margin_ok = (ctc.top2_margin(want, lens) > MARGIN) | (np.arange(T)[:, None] >= lens[None, :])
@@ -274,3 +275,37 @@ def test_cfg5_shape_inference_greedy_labels(pkg, cuda):
         if margin_ok[:, b].all():
             row = pred[b]
             np.testing.assert_array_equal(row[row != C], np.asarray(ref[b]))
+
+
+def test_stale_tile_stress(pkg, cuda):
+    """The recurrent kernels exchange h_t / dgates_t between CTAs through TMA stores, a counter and TMA loads.  A
+    consumer that fetches a tile before the producer's store is visible reads what the PREVIOUS call left there, so
+    two inputs alternate: every repetition must reproduce the first run of its input bit for bit (logits, carried
+    state and gradients; cfg-2 shape, dropout on, the pipelined schedule)."""
+    L, H, F, C, B, T = 3, 768, 120, 80, 32, 998
+    rng = np.random.default_rng(21)
+    flat = model.flatten(model.init_params(L, H, F, C, seed=0), L, H, F, C)
+    x = torch.from_numpy(rng.standard_normal((T, B, F)).astype(np.float32)).to(cuda)
+    lens_np = np.full(B, T, np.int32)
+    lens_np[1::4] = rng.integers(T // 2, T, size=len(lens_np[1::4]))
+    lens = torch.from_numpy(lens_np).to(cuda)
+    dl = torch.from_numpy((rng.standard_normal((T, B, C)) * (np.arange(T)[:, None, None] < lens_np[None, :, None]))
+                          .astype(np.float32)).to(cuda)
+    xs = [x, torch.flip(x, dims=[0]) * 0.7]
+    dls = [dl, torch.flip(dl, dims=[1]) * 1.3]
+    m = _build(pkg, cuda, L, H, F, C, B, 1000, flat, training=True, ki=0.8, ko=0.5)
+    refs = [None, None]
+    for it in range(16):
+        k = it & 1
+        m.rnn_state.zero_()
+        m._dropout_calls = 0
+        logits = m.forward(xs[k], lens, training=True)
+        m.grads.zero_()
+        m.backward(xs[k], lens, dls[k])
+        torch.cuda.synchronize()
+        got = (logits.clone(), m.rnn_state.clone(), m.grads.clone())
+        if refs[k] is None:
+            refs[k] = got
+            continue
+        for a, b, what in zip(got, refs[k], ("logits", "state", "gradients")):
+            assert torch.equal(a, b), "repetition %d: %s differ from the first run of the same input" % (it, what)

@@ -353,6 +353,55 @@ def e2e_diag():
                   "  total %.2f" % (d[0], d[1], d[2], d[3], (t[-1] - t[0]) * 1e3))
 
 
+def stress_diag():
+    """Run-to-run determinism of the cfg-2 forward + backward under the pipelined schedule: every repetition must
+    reproduce the first one bit for bit (logits) / to fp32 regrouping (gradients are summed chunk by chunk in a fixed
+    order, so they are bitwise stable too).  Prints the repetitions that differ."""
+    L, H, F, C, B, T = 3, 768, 120, 80, 32, 998
+    reps = int(os.environ.get("RS_STRESS_REPS", "40"))
+    rng = np.random.default_rng(0)
+    p = model.init_params(L, H, F, C, seed=0)
+    flat = model.flatten(p, L, H, F, C)
+    x = torch.from_numpy(rng.standard_normal((T, B, F)).astype(np.float32)).to(dev)
+    lens_np = np.full(B, T, np.int32)
+    lens_np[1::4] = rng.integers(T // 2, T, size=len(lens_np[1::4]))
+    lens = torch.from_numpy(lens_np).to(dev)
+    dl = torch.from_numpy((rng.standard_normal((T, B, C)) * (np.arange(T)[:, None, None] < lens_np[None, :, None])).astype(np.float32)).to(dev)
+    m = rs.AcousticModel(L, H, B, 1000, 600, F, False, C, device=dev)
+    m.create_training_rnn(0.8, 0.5, 1, 3e-4, 0.33)
+    m.load_flat_params(flat)
+    # two different inputs alternate, so that data left over from the previous repetition is WRONG data: a read that
+    # races ahead of its producer shows up as a difference from the first run of the same input
+    xs = [x, torch.flip(x, dims=[0]) * 0.7]
+    dls = [dl, torch.flip(dl, dims=[1]) * 1.3]
+    refs = [None, None]
+    bad = 0
+    for it in range(reps):
+        k = it & 1
+        m.rnn_state.zero_()
+        m._dropout_calls = 0
+        logits = m.forward(xs[k], lens, training=True, keep_state=False)
+        m.grads.zero_()
+        m.backward(xs[k], lens, dls[k])
+        junk = torch.randn(1 << 24, device=dev).sum()
+        torch.cuda.synchronize()
+        got = (logits.clone(), m.grads.clone())
+        if refs[k] is None:
+            refs[k] = got
+            continue
+        ref = refs[k]
+        dlg = float((got[0] - ref[0]).abs().max())
+        dgr = float((got[1] - ref[1]).abs().max() / ref[1].abs().max())
+        if dlg != 0.0 or dgr != 0.0:
+            bad += 1
+            idx = (got[0] - ref[0]).abs().amax(dim=(1, 2)).nonzero().flatten()
+            if bad <= 3:
+                print("  rep %d: max |dlogit| %.3e (first differing step t=%s), grad rel diff %.3e" % (
+                    it, dlg, int(idx[0]) if len(idx) else None, dgr))
+    print("stress: %d of %d repetitions differ from the first run of their input (RS_TC_CHUNK=%s RS_TS_VARIANT=%s)" % (
+        bad, reps - 2, os.environ.get("RS_TC_CHUNK", "default"), os.environ.get("RS_TS_VARIANT", "default")))
+
+
 def bf16_round(x):
     return torch.from_numpy(np.asarray(x, np.float32)).to(torch.bfloat16).to(torch.float32).numpy().astype(np.float64)
 
@@ -416,6 +465,8 @@ if __name__ == "__main__":
         ts_diag()
     if "gemmbench" in which:
         gemm_bench()
+    if "stress" in which:
+        stress_diag()
     if "e2e" in which:
         e2e_diag()
     if "trace" in which:
