@@ -277,18 +277,28 @@ class AcousticModel(object):
         return path
 
     def restore(self, session, checkpoint_dir):
-        """models/AcousticModel.py:489-499"""
+        """models/AcousticModel.py:489-499.  Reads this library's .npz archives and the reference's own TensorFlow
+        checkpoints (tensor bundle, or the constants embedded in the shipped .meta: tf_checkpoint.py)."""
         state = os.path.join(checkpoint_dir, "checkpoint")
         if os.path.exists(state):
             line = open(state).readline()
             name = line.split('"')[1]
-            data = np.load(os.path.join(checkpoint_dir, name))
+            path = name if os.path.isabs(name) else os.path.join(checkpoint_dir, name)
+            if name.endswith(".npz"):
+                data = np.load(path)
+                source = "npz"
+            else:
+                from .tf_checkpoint import load_reference_checkpoint
+                data, source = load_reference_checkpoint(path)
             for k, v in self.param_views().items():
-                v.copy_(torch.from_numpy(data[k]).to(self.device))
-            self.global_step = int(data["global_step"])
+                if tuple(data[k].shape) != tuple(v.shape):
+                    raise ValueError("checkpoint variable %s has shape %s, the model expects %s"
+                                     % (k, tuple(data[k].shape), tuple(v.shape)))
+                v.copy_(torch.from_numpy(np.ascontiguousarray(data[k], dtype=np.float32)).to(self.device))
+            self.global_step = int(np.asarray(data["global_step"]).reshape(-1)[0])
             if self.learning_rate_var is not None:
-                self.learning_rate_var = float(data["learning_rate"])
-            logging.info("Restored model parameters from %s (global_step id %d)", name, self.global_step)
+                self.learning_rate_var = float(np.asarray(data["learning_rate"]).reshape(-1)[0])
+            logging.info("Restored model parameters from %s [%s] (global_step id %d)", name, source, self.global_step)
         else:
             logging.info("Created model with fresh parameters.")
 

@@ -142,3 +142,28 @@ def test_checkpoint_roundtrip(pkg, cuda, tmp_path):
     assert torch.equal(m.params, n.params) and n.global_step == 41 and abs(n.get_learning_rate() - 3e-4) < 1e-9
     names = set(m.param_views())
     assert "rnn/multi_rnn_cell/cell_1/basic_lstm_cell/kernel" in names and "Input_Layer/input_w" in names
+
+
+def test_restore_from_a_tensorflow_bundle(pkg, cuda, tmp_path):
+    """AcousticModel.restore reads the reference's own checkpoint format (tensor bundle written here with the layout
+    TF writes; the shipped checkpoint's index is parsed in tests/test_tf_checkpoint.py)."""
+    from test_tf_checkpoint import _write_bundle
+    L, H, F, C = 2, 64, 20, 30
+    rng = np.random.default_rng(3)
+    tensors = {"Input_Layer/input_w": rng.standard_normal((F, H)).astype(np.float32),
+               "Input_Layer/input_b": rng.standard_normal(H).astype(np.float32),
+               "Output_layer/output_w": rng.standard_normal((H, C)).astype(np.float32),
+               "Output_layer/output_b": rng.standard_normal(C).astype(np.float32),
+               "global_step": np.array(4321, np.int32), "learning_rate": np.array(2.5e-4, np.float32)}
+    for l in range(L):
+        tensors["rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % l] = rng.standard_normal((2 * H, 4 * H)).astype(np.float32)
+        tensors["rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/bias" % l] = rng.standard_normal(4 * H).astype(np.float32)
+    _write_bundle(str(tmp_path / "acousticmodel.ckpt"), tensors)
+    (tmp_path / "checkpoint").write_text('model_checkpoint_path: "acousticmodel.ckpt"\n')
+    m = pkg.AcousticModel(L, H, 4, 50, 600, F, False, C, device=cuda)
+    m.create_training_rnn(1.0, 1.0, 1, 3e-4, 0.33)
+    m.initialize(None)
+    m.restore(None, str(tmp_path))
+    assert m.global_step == 4321 and abs(m.learning_rate_var - 2.5e-4) < 1e-9
+    for k, v in m.param_views().items():
+        np.testing.assert_array_equal(v.cpu().numpy(), tensors[k])
