@@ -27,6 +27,13 @@ def ctc_diag():
         ln = torch.from_numpy(lens).to(dev)
         loss, grad = m.ctc_loss(lg, labs, ln)
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            m.ctc_loss(lg, labs, ln)
+        e1.record()
+        torch.cuda.synchronize()
+        print("CTC T=%d B=%d: %.3f ms per loss+grad call" % (T, B, e0.elapsed_time(e1) / 5))
         wl, wg = ctc.ctc_loss_and_grad(logits, labs, lens)
         loss, grad = loss.cpu().numpy(), grad.cpu().numpy()
         print("CTC T=%d B=%d full=%s: loss rel err per item %s" % (T, B, full, np.array2string(np.abs(loss - wl) / np.abs(wl), precision=2)))
