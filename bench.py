@@ -300,11 +300,14 @@ def run_b200(args):
     tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
     # dominant kernels: the recurrent kernels (forward + backward).  With the pipelined schedule one layer is
-    # `chunks` launches of <= `chunk` steps each; launch_ms below is per layer (its launches summed), `achieved`
-    # uses the algorithmic flops of a layer (2*B*H*4H*T) over that sum, i.e. the per-launch rate.
-    rec_flops_layer = 2.0 * c["B"] * c["H"] * 4 * c["H"] * T        # h_{t-1} @ Wh over T steps
-    rec_ms = float(np.mean(rec_f + rec_b))
-    achieved = rec_flops_layer / (rec_ms / 1e3) / 1e12
+    # several launches of <= `chunk` steps each: `achieved` = algorithmic flops of one launch (2*B*H*4H per step) over
+    # the average launch duration (CUDA events on the launching streams); launch_ms lists the per-layer sums.
+    durs = [b - a for d in (0, 1) for l in trace[d] for (a, b) in l]          # every recurrent launch of the step, ms
+    n_launches = max(1, len(durs))
+    steps_per_launch = T * 2.0 * c["L"] / n_launches                        # = the chunk length, averaged
+    rec_flops_launch = 2.0 * c["B"] * c["H"] * 4 * c["H"] * steps_per_launch   # h_{t-1} @ Wh per launch
+    rec_ms = float(np.mean(durs)) if durs else float(np.mean(rec_f + rec_b))
+    achieved = rec_flops_launch / (rec_ms / 1e3) / 1e12
     tc = bool(m.uses_tensor_cores)
     n_launch = [len(x) for x in trace[0]] + [len(x) for x in trace[1]]
 
@@ -322,13 +325,14 @@ def run_b200(args):
                            "wavefront)" % (max(n_launch), chunk)) if tc else "lstm_rec_fwd_kernel / lstm_rec_bwd_kernel (fp32 FFMA)",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak,
-                # dram__bytes_read+write per layer from profiles/r01b_ncu_rec_ts_kernels.txt (fwd 948 MB, bwd 961 MB)
-                "traffic": 954.0e6 if tc else None, "peak_source": peak_src,
+                # dram__bytes_read+write per launch of 128 steps from profiles/r01d_ncu_final.txt (fwd 88.7 MB, bwd 102.7 MB)
+                "traffic": 95.7e6 if tc else None, "peak_source": peak_src, "avg_launch_ms": rec_ms,
+                "steps_per_launch": steps_per_launch,
                 "launch_ms": {"fwd": rec_f, "bwd": rec_b}, "launches_per_layer": max(n_launch),
                 "sum_launch_ms": sum(rec_f) + sum(rec_b),
                 "share_of_step": rec_busy / (ms / args.steps),
-                "note": "algorithmic flops = 2*B*H*4H*T per layer (150.7 GFLOP at cfg-2; the bf16x3 forward issues 3x "
-                        "that on the tensor pipe).  The recurrence is a chain of T dependent steps with a grid-wide "
+                "note": "algorithmic flops = 2*B*H*4H per step (151 MFLOP at cfg-2, 19.3 GFLOP per 128-step launch; the "
+                        "bf16x3 forward issues 3x that on the tensor pipe).  The recurrence is a chain of T dependent steps with a grid-wide "
                         "exchange of h per step: latency-bound, not tensor-bound (DESIGN.md 'Recurrent step budget'); "
                         "launch_ms sums a layer's chunk launches, which run concurrently with other layers' (sum_launch_ms "
                         "exceeds the step); share_of_step = time during which at least one recurrent launch is running"}

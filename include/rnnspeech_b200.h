@@ -122,6 +122,10 @@ int64_t rs_am_param_offset(const rs_am* am, int which, int layer);
 /* 1 if this shape runs on the tcgen05 kernels (hidden_size % 64 == 0, batch <= 64, weights
  * fit in shared memory), 0 if it runs on the fp32 FFMA kernels. */
 int rs_am_uses_tensor_cores(const rs_am* am);
+/* Batch normalisation of the stack's input over the batch axis, no scale / offset, eps 1e-3 (the reference's
+ * `normalization` constructor argument, models/AcousticModel.py:253-259; config.ini batch_normalization).  Call
+ * before sizing the reserve / workspace. */
+int rs_am_set_normalization(rs_am* am, int enable);
 size_t rs_am_reserve_bytes(const rs_am* am);
 size_t rs_am_workspace_bytes(const rs_am* am);
 int rs_am_forward(rs_am* am, const float* params_d, const float* x_d, const int32_t* len_d, int T,

@@ -58,6 +58,7 @@ SIGNATURES = {
     "rs_am_param_count": (c_int64, [c_void_p]),
     "rs_am_param_offset": (c_int64, [c_void_p, c_int, c_int]),
     "rs_am_uses_tensor_cores": (c_int, [c_void_p]),
+    "rs_am_set_normalization": (c_int, [c_void_p, c_int]),
     "rs_am_reserve_bytes": (c_size_t, [c_void_p]),
     "rs_am_workspace_bytes": (c_size_t, [c_void_p]),
     "rs_am_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_float,

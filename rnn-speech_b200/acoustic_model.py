@@ -84,9 +84,6 @@ class AcousticModel(object):
         self.input_dim = input_dim
         self.normalization = normalization
         self.num_labels = num_labels
-        if normalization:
-            # models/AcousticModel.py:253-259 -- off by default (config.ini:88); not on the B200 path yet
-            raise NotImplementedError("batch_normalization=True is not supported by the B200 kernels")
         if not torch.cuda.is_available():
             raise RuntimeError("rnnspeech_b200.AcousticModel needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -121,13 +118,16 @@ class AcousticModel(object):
             hh = _lib.c_void_p()
             _lib.call("rs_am_create", _lib.ctypes.byref(hh), self.num_layers, self.hidden_size, self.input_dim,
                       self.num_labels, batch, self.max_input_seq_length)
+            if self.normalization:       # models/AcousticModel.py:253-259 (config.ini batch_normalization)
+                _lib.call("rs_am_set_normalization", hh, 1)
             return hh
         # The tensor-core recurrent kernels take up to TC_MAX_BATCH utterances; a larger mini-batch (BASELINE
         # config 5: 256 clips) runs as batch tiles of that size, one handle per tile size, sharing parameters,
         # gradients and workspace (utterances are independent: SURVEY 8e).
         self._tiles = None
         h = None
-        if self.batch_size > TC_MAX_BATCH:
+        # (batch normalisation takes its statistics over the whole mini-batch: no tiling then)
+        if self.batch_size > TC_MAX_BATCH and not self.normalization:
             probe = create(TC_MAX_BATCH)
             if bool(_lib.raw("rs_am_uses_tensor_cores")(probe)):
                 bounds = list(range(0, self.batch_size, TC_MAX_BATCH)) + [self.batch_size]

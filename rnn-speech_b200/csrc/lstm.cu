@@ -43,7 +43,7 @@ int dropout2(const float* in, float* out, int64_t n, uint64_t seed, int sa, floa
 
 // Buffer plan.  Everything is in floats; TBH = Tmax*B*H.
 struct Plan {
-  size_t TBH, TB4H, state;
+  size_t TBH, TB4H, state, TH;
   // reserve (per layer): xin | out | gates | cs ; then top
   size_t res_layer;      // floats per layer
   size_t res_total;      // floats
@@ -59,7 +59,8 @@ Plan make_plan(const rs_am* am) {
   p.TB4H = 4 * p.TBH;
   p.res_layer = p.TBH /*xin*/ + p.TBH /*out*/ + p.TB4H /*gates*/ + p.TBH /*cs*/;
   p.state = align_up((size_t)am->L * 2 * am->B * am->H, 64);
-  p.res_total = p.res_layer * am->L + p.TBH /*top*/ + p.TBH /*rnn_in*/ + p.state /*initial state copy*/;
+  p.TH = align_up((size_t)am->Tmax * am->H, 64);
+  p.res_total = p.res_layer * am->L + p.TBH /*top*/ + p.TBH /*rnn_in*/ + p.state /*initial state copy*/ + p.TH /*bn 1/std*/;
   p.ws_fixed = 256 + (p.TB4H + 3 * p.TBH) * sizeof(float);
   // inference (reserve == NULL): ping-pong activations + the state copy live in the workspace
   p.ws_total = p.ws_fixed + (3 * p.TBH + p.state) * sizeof(float);
@@ -82,6 +83,7 @@ extern "C" int rs_am_create(rs_am** out, int num_layers, int hidden_size, int in
   rs_am* am = new rs_am();
   am->L = num_layers; am->H = hidden_size; am->F = input_dim; am->C = num_labels;
   am->B = batch_size; am->Tmax = max_T;
+  am->normalization = 0;
   int64_t off = 0;
   const int64_t H = hidden_size;
   am->off_input_w = off; off += (int64_t)input_dim * H;
@@ -135,6 +137,15 @@ extern "C" void rs_am_destroy(rs_am* am) {
     cudaStreamDestroy(am->tr_st);
   }
   delete am;
+}
+
+// Batch normalisation of the stack's input over the batch axis (models/AcousticModel.py:253-259; the reference's
+// `normalization` constructor argument).  Set before the first forward; the statistics are per call (no moving
+// averages in the reference either).
+extern "C" int rs_am_set_normalization(rs_am* am, int enable) {
+  RS_REQUIRE(am != nullptr, RS_ERR_INVALID, "rs_am_set_normalization: NULL handle");
+  am->normalization = enable ? 1 : 0;
+  return RS_OK;
 }
 
 extern "C" int rs_am_enable_timing(rs_am* am, int enable) {
@@ -217,6 +228,7 @@ struct Bufs {
   float* rnn_in;
   float* top;
   float* state0;   // [L,2,B,H] copy of the initial state of this call
+  float* bn_istd;  // [T,H] batch-norm 1/std (training) or nullptr
   float *xin[64], *out[64], *gates[64], *cs[64];
 };
 
@@ -240,7 +252,8 @@ Bufs carve(const rs_am* am, const Plan& p, void* reserve, void* ws) {
     }
     b.top = r; r += p.TBH;
     b.rnn_in = r; r += p.TBH;
-    b.state0 = r;
+    b.state0 = r; r += p.state;
+    b.bn_istd = r;
   } else {
     // inference: layer l reads xin from one ping-pong buffer and writes out to the other
     float* t0 = f; float* t1 = f + p.TBH; float* t2 = f + 2 * p.TBH;
@@ -253,6 +266,7 @@ Bufs carve(const rs_am* am, const Plan& p, void* reserve, void* ws) {
     b.top = t2;
     b.rnn_in = t2;
     b.state0 = f + 3 * p.TBH;
+    b.bn_istd = nullptr;
   }
   return b;
 }
@@ -304,6 +318,8 @@ extern "C" int rs_am_forward(rs_am* am, const float* params_d, const float* x_d,
   float* rnn_in = drop_in ? bf.rnn_in : bf.xin[0];
   if ((rc = sgemm(0, 0, TB, H, F, x_d, F, params_d + am->off_input_w, H, rnn_in, H,
                   params_d + am->off_input_b, 0, st)) != RS_OK) return rc;
+  if (am->normalization)                                        // (models/AcousticModel.py:253-259)
+    if ((rc = bn_forward(rnn_in, bf.bn_istd, T, B, H, st)) != RS_OK) return rc;
   if (drop_in)
     if ((rc = dropout2(rnn_in, bf.xin[0], nTBH, seed, 0, keep_in, -1, 1.f, st)) != RS_OK) return rc;
 
@@ -418,6 +434,11 @@ extern "C" int rs_am_backward(rs_am* am, const float* params_d, const float* x_d
   if (drop_in) {
     drnn = bf.bufB;
     if ((rc = dropout2(dcur, drnn, nTBH, seed, 0, keep_in, -1, 1.f, st)) != RS_OK) return rc;
+  }
+  if (am->normalization) {
+    // x_hat is what forward left in rnn_in (with input dropout) or in xin[0] (without)
+    const float* xhat = drop_in ? bf.rnn_in : bf.xin[0];
+    if ((rc = bn_backward(drnn, xhat, bf.bn_istd, T, B, H, st)) != RS_OK) return rc;
   }
   if ((rc = sgemm(1, 0, F, H, TB, x_d, F, drnn, H, grads_d + am->off_input_w, H, nullptr, 1, st)) != RS_OK) return rc;
   return colsum(drnn, TB, H, H, grads_d + am->off_input_b, 1, st);

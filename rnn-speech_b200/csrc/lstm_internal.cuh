@@ -6,6 +6,7 @@
 
 struct rs_am {
   int L, H, F, C, B, Tmax;
+  int normalization;             // batch-norm of the stack's input (models/AcousticModel.py:253-259), default off
   int64_t n_params;
   int64_t off_input_w, off_input_b, off_output_w, off_output_b;
   int64_t off_kernel[64], off_bias[64];
@@ -55,6 +56,10 @@ inline int tev_record(rs_am* am, int dir, int l, cudaStream_t st) {
   ++u;
   return RS_OK;
 }
+
+// batchnorm.cu: x [T,B,H] -> x_hat in place (+ 1/std [T,H]); d -> gradient wrt x in place
+int bn_forward(float* x, float* istd, int T, int B, int H, cudaStream_t st);
+int bn_backward(float* d, const float* xhat, const float* istd, int T, int B, int H, cudaStream_t st);
 
 // Tensor-core path (lstm_tc.cu).  Same contract as rs_am_forward / rs_am_backward.
 size_t am_tc_reserve_bytes(const rs_am* am);

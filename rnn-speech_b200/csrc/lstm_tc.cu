@@ -62,6 +62,7 @@ struct TcBufs {
   float *gates[64], *cs[64];
   bf16 *top_hi, *top_lo;
   float* state0;                  // [L,2,B,H]
+  float *bn_xhat, *bn_istd;       // batch-norm: normalised input [T*B][H] fp32, 1/std [T][H] (only with normalization)
 };
 
 // One carve function defines the layout for sizing (null bases) and for use.
@@ -111,6 +112,8 @@ void carve(const rs_am* am, void* reserve, void* ws, bool training, TcBufs* b, s
   }
   b->top_hi = act.take<bf16>(TB * H); b->top_lo = act.take<bf16>(TB * H);
   b->state0 = act.take<float>((size_t)L * 2 * B * H);
+  if (am->normalization) { b->bn_xhat = act.take<float>(TB * H); b->bn_istd = act.take<float>((size_t)T * H); }
+  else { b->bn_xhat = nullptr; b->bn_istd = nullptr; }
   if (res_bytes) *res_bytes = align_up(r.off, 1024);
   if (ws_bytes) *ws_bytes = align_up(w.off, 1024);
 }
@@ -309,8 +312,17 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
   {
     SplitMat A{bf.x_hi, bf.x_lo, TB, F, Fp}, Bm{bf.wi_hi, bf.wi_lo, H, F, Fp};
     GemmTcOut o{};
-    o.mode = GEMM_OUT_SPLIT; o.Chi = bf.xin_hi[0]; o.Clo = bf.xin_lo[0]; o.ldc = H; o.bias = params_d + am->off_input_b;
-    RC(gemm_tc_nt(A, Bm, TB, H, F, 3, o, st));
+    if (am->normalization) {
+      // batch norm over the batch axis (models/AcousticModel.py:253-259): fp32 out, normalise in place (x_hat and
+      // 1/std stay for backward), then the planes the recurrent stack reads
+      o.mode = GEMM_OUT_F32; o.C = bf.bn_xhat; o.ldc = H; o.bias = params_d + am->off_input_b;
+      RC(gemm_tc_nt(A, Bm, TB, H, F, 3, o, st));
+      RC(bn_forward(bf.bn_xhat, bf.bn_istd, T, B, H, st));
+      RC(split_rows(bf.bn_xhat, TB, H, H, bf.xin_hi[0], bf.xin_lo[0], H, st));
+    } else {
+      o.mode = GEMM_OUT_SPLIT; o.Chi = bf.xin_hi[0]; o.Clo = bf.xin_lo[0]; o.ldc = H; o.bias = params_d + am->off_input_b;
+      RC(gemm_tc_nt(A, Bm, TB, H, F, 3, o, st));
+    }
     if (drop_in) RC(dropout_planes(bf.xin_hi[0], bf.xin_lo[0], H, H, bf.xin_hi[0], bf.xin_lo[0], nTBH, 0, seed, 0, keep_in, -1, 1.f, st));
   }
   const int hld = am->tc.ts ? 2 * H : H;            // row stride of the h planes
@@ -582,6 +594,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   // through layer 0's input dropout, then the input dense: dw_i += x^T drnn, db_i += colsum
   float* drnn = bf.din[0];
   if (drop_in) RC(dropout_f32(drnn, drnn, nTBH, 0, seed, 0, keep_in, -1, 1.f, st));
+  if (am->normalization) RC(bn_backward(drnn, bf.bn_xhat, bf.bn_istd, T, B, H, st));
   RC(split_planes_transposed(drnn, TB, H, H, bf.actT_hi, bf.actT_lo, TBp, st));                     // [H][TBp]
   RC(transpose_bf16(bf.x_hi, TB, F, Fp, bf.xT_hi, TBp, st));
   RC(transpose_bf16(bf.x_lo, TB, F, Fp, bf.xT_lo, TBp, st));

@@ -309,3 +309,38 @@ def test_stale_tile_stress(pkg, cuda):
             continue
         for a, b, what in zip(got, refs[k], ("logits", "state", "gradients")):
             assert torch.equal(a, b), "repetition %d: %s differ from the first run of the same input" % (it, what)
+
+
+@pytest.mark.parametrize("L,H,F,C,B,T,ki", [
+    (2, 128, 40, 30, 12, 23, 0.8),     # tensor-core path, input dropout after the normalisation
+    (1, 50, 20, 50, 5, 17, 1.0),       # FFMA path (H not a multiple of 64)
+])
+def test_batch_normalization_against_oracle(pkg, cuda, L, H, F, C, B, T, ki):
+    """normalization=True (models/AcousticModel.py:253-259, config.ini batch_normalization): moments over the batch
+    axis per (t, h), eps 1e-3, no scale / offset, padded frames included -- logits and every gradient against
+    oracle/model.py."""
+    rng = np.random.default_rng(H)
+    p = model.init_params(L, H, F, C, seed=5, dtype=np.float64)
+    p["input_b"] = rng.standard_normal(H) * 0.2
+    flat = model.flatten(p, L, H, F, C)
+    x = rng.standard_normal((T, B, F)) * (1.0 + np.arange(B)[None, :, None] * 0.3)      # different scales per item
+    lens = rng.integers(T // 2, T + 1, size=B).astype(np.int32)
+    lens[0] = T
+    x = x * (np.arange(T)[:, None, None] < lens[None, :, None])                          # padded frames are zeros
+    m = pkg.AcousticModel(L, H, B, T, 600, F, True, C, device=cuda)
+    m.create_training_rnn(ki, 1.0, 1, 3e-4, 0.33)
+    m.load_flat_params(flat)
+    xd, ld = _dev(x, cuda, np.float32), _dev(lens, cuda, np.int32)
+    logits = m.forward(xd, ld, training=True)
+    keep_in, keep_out, seed, _ = m._last_fwd
+    want, _, cache = model.forward(p, x, lens, L, H, keep_in=keep_in, keep_out=keep_out, seed=seed, normalization=True)
+    np.testing.assert_allclose(logits.cpu().numpy(), want, atol=5e-4)
+    dl = rng.standard_normal(want.shape) * (np.arange(T)[:, None, None] < lens[None, :, None])
+    m.grads.zero_()
+    m.backward(xd, ld, _dev(dl, cuda, np.float32))
+    gw = model.flatten(model.backward(p, cache, dl, L, H), L, H, F, C)
+    got = m.grads.cpu().numpy()
+    assert np.abs(got - gw).max() < 2e-3 * np.abs(gw).max()
+    # the input-dense gradients are the ones that pass through the normalisation
+    n_in = F * H + H
+    assert np.abs(got[:n_in] - gw[:n_in]).max() < 2e-3 * np.abs(gw[:n_in]).max()
