@@ -185,6 +185,14 @@ int rs_ctc_beam_search(const float* logits_d, const int32_t* len_d, int T, int B
                        int merge_repeated, int normalize, int32_t* out_d, int32_t* out_len_d,
                        float* out_score_d, void* ws_d, size_t ws_bytes, void* stream);
 
+/* Edit distance between decoded and reference label sequences.  Replaces tf.edit_distance(prediction,
+ * sparse_labels, normalize=True), the reference's error rate (models/AcousticModel.py:370).
+ *   hyp_d [B, hyp_ld] int32 (as written by the decoders), hyp_len_d [B]; truth_d flat int32 + truth_offsets_d [B+1]
+ *   dist_d int32 [B];  rate_d float32 [B] = dist / len(truth) (inf: empty truth, non-empty hypothesis) or NULL */
+int rs_edit_distance(const int32_t* hyp_d, const int32_t* hyp_len_d, int hyp_ld, const int32_t* truth_d,
+                     const int32_t* truth_offsets_d, int B, int max_truth_len, int32_t* dist_d, float* rate_d,
+                     void* stream);
+
 /* ------------------------------------------------------------------------
  * Update rule.  Replaces tf.clip_by_global_norm + AdamOptimizer.apply_gradients
  * (models/AcousticModel.py:388,404-406).

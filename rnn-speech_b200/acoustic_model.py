@@ -427,18 +427,24 @@ class AcousticModel(object):
         ids, lens, _ = self.beam_search_decode(logits, len_d)
         return ids, lens
 
+    def edit_distance(self, ids, lens, label_rows):
+        """Levenshtein distance of every decoded row to its truth, on the device.  Returns (distance int32 [B],
+        rate float32 [B] = distance / len(truth))."""
+        flat, offs, maxlen = self._labels_to_device(label_rows)
+        B = int(ids.shape[0])
+        dist = torch.empty((B,), dtype=torch.int32, device=self.device)
+        rate = torch.empty((B,), dtype=torch.float32, device=self.device)
+        _lib.call("rs_edit_distance", ids.data_ptr(), lens.data_ptr(), int(ids.shape[1]), flat.data_ptr(), offs.data_ptr(),
+                  B, int(maxlen), dist.data_ptr(), rate.data_ptr(), _stream_ptr())
+        return dist, rate
+
     def _error_rate(self, logits, len_d, label_rows):
         """mean over the batch of edit_distance(prediction, truth) / len(truth)
-        (tf.edit_distance(normalize=True), models/AcousticModel.py:370)."""
+        (tf.edit_distance(normalize=True), models/AcousticModel.py:370): decoder and distance on the device, the
+        result stays there (no host round trip inside the step)."""
         ids, lens = self.predict(logits, len_d)
-        ids = ids.cpu().numpy()
-        lens = lens.cpu().numpy()
-        rates = []
-        for b, truth in enumerate(label_rows):
-            hyp = ids[b, :lens[b]]
-            d = levenshtein(hyp, truth)
-            rates.append(d / float(len(truth)) if len(truth) else (float("inf") if d else 0.0))
-        return float(np.mean(rates))
+        _, rate = self.edit_distance(ids, lens, label_rows)
+        return rate.mean()
 
     def step_on_batch(self, x_d, len_d, label_rows, compute_gradients=True, compute_error_rate=True):
         """One mini-batch of run_step (models/AcousticModel.py:634-660) on explicit

@@ -183,3 +183,38 @@ def test_beam_search_full_size_and_process_input(pkg, cuda):
     ids2, n2, _ = m.beam_search_decode(lg, torch.from_numpy(short).to(cuda), merge_repeated=True)
     want, _ = ctc.beam_search_decode(logits[:150, :1], short[:1], merge_repeated=True)
     np.testing.assert_array_equal(ids2[0, :int(n2[0])].cpu().numpy(), want[0])
+
+
+def test_edit_distance_matches_host_levenshtein(pkg, cuda):
+    """rs_edit_distance (tf.edit_distance(normalize=True), models/AcousticModel.py:370) against the host DP on random
+    pairs: empty sequences, long truths (600 labels, max_target_seq_length), near-identical and unrelated pairs."""
+    rng = np.random.default_rng(17)
+    B, ld = 40, 700
+    truths, hyps = [], []
+    for b in range(B):
+        n = [0, 1, 600, 37][b] if b < 4 else int(rng.integers(0, 200))
+        t = rng.integers(0, 79, size=n).astype(np.int32)
+        if b % 3 == 0 and n > 0:                      # a noisy copy: substitutions, deletions, insertions
+            keep = rng.random(n) > 0.1
+            hseq = np.where(rng.random(n) < 0.1, rng.integers(0, 79, size=n), t)[keep]
+            hseq = np.insert(hseq, rng.integers(0, len(hseq) + 1, size=3), rng.integers(0, 79, size=3))
+        else:
+            hseq = rng.integers(0, 79, size=int(rng.integers(0, 150)))
+        if b == 1:
+            hseq = np.zeros(0, np.int64)
+        truths.append(t)
+        hyps.append(hseq.astype(np.int32))
+    ids = np.full((B, ld), -1, np.int32)
+    for b, hseq in enumerate(hyps):
+        ids[b, :len(hseq)] = hseq
+    lens = np.array([len(hseq) for hseq in hyps], np.int32)
+    m = _model(pkg, cuda, B, 50)
+    dist, rate = m.edit_distance(torch.from_numpy(ids).to(cuda), torch.from_numpy(lens).to(cuda), truths)
+    dist, rate = dist.cpu().numpy(), rate.cpu().numpy()
+    for b in range(B):
+        want = pkg.levenshtein(hyps[b], truths[b])
+        assert dist[b] == want, "item %d: %d vs %d" % (b, dist[b], want)
+        if len(truths[b]):
+            assert abs(rate[b] - want / len(truths[b])) < 1e-6
+        else:
+            assert rate[b] == (np.inf if want else 0.0)
