@@ -48,7 +48,8 @@ struct TcBufs {
   bf16 *dgT_hi[64], *dgT_lo[64];  // [4H][TBp] per layer
   bf16 *xT2_hi[64], *xT2_lo[64];  // [H][TBp] transposed layer input, per layer
   bf16 *hT_hi[64], *hT_lo[64];    // [H][TBp] transposed h_{t-1}, per layer
-  bf16 *actT_hi, *actT_lo;        // [H][TBp] transposed activations (output / input dense)
+  bf16 *actT_hi, *actT_lo;        // [H][TBp] transposed top activations (output dense)
+  bf16 *drT_hi, *drT_lo;          // [H][TBp] transposed gradient wrt the input dense's output
   bf16 *dl_hi, *dl_lo;            // dlogits planes [T*B][Cp]
   bf16 *dlT_hi, *dlT_lo;          // [C][TBp]
   bf16 *xT_hi, *xT_lo;            // [F][TBp]
@@ -93,6 +94,7 @@ void carve(const rs_am* am, void* reserve, void* ws, bool training, TcBufs* b, s
     b->wos_hi = w.take<bf16>((size_t)H * Cp); b->wos_lo = w.take<bf16>((size_t)H * Cp);
     b->elastic = w.take<int>(4096);
     b->actT_hi = w.take<bf16>((size_t)H * TBp); b->actT_lo = w.take<bf16>((size_t)H * TBp);
+    b->drT_hi = w.take<bf16>((size_t)H * TBp); b->drT_lo = w.take<bf16>((size_t)H * TBp);
     b->dl_hi = w.take<bf16>(TB * Cp); b->dl_lo = w.take<bf16>(TB * Cp);
     b->dlT_hi = w.take<bf16>((size_t)C * TBp); b->dlT_lo = w.take<bf16>((size_t)C * TBp);
     b->xT_hi = w.take<bf16>((size_t)F * TBp); b->xT_lo = w.take<bf16>((size_t)F * TBp);
@@ -471,7 +473,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   cudaStream_t side = am->side;
   RS_CHECK_CUDA(cudaMemsetAsync(bf.elastic, 0, 4096 * sizeof(int), st));
   int elastic_next = 0;
-  const bool use_elastic = NC > 1 && sc.side_tpc == 0 && 2 * L * NC + 8 < 4096;
+  const bool use_elastic = NC > 1 && sc.side_tpc == 0 && 2 * L * NC + NC + 8 < 4096;
   cudaEvent_t e_fork;
   RC(ev_record(am, &e_fork, st));
   for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(am->lane[l], e_fork, 0));
@@ -572,6 +574,31 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     }
     return tev_record(am, 2, l, side);
   };
+  // the input dense's gradient, chunk by chunk behind layer 0: through the input dropout (and the batch norm),
+  // dw_i += x^T drnn, db_i += colsum(drnn); elementwise work and transposes on the transposer stream, the GEMM on
+  // the side stream
+  auto issue_input = [&](int c) -> int {
+    const int t0 = c * sc.Tc, n = (t0 + sc.Tc <= T ? sc.Tc : T - t0);
+    const size_t r0 = (size_t)t0 * B;
+    const int nb = n * B;
+    cudaStream_t tr = am->tr_st;
+    RS_CHECK_CUDA(cudaStreamWaitEvent(tr, e_dx[(size_t)0 * NC + c], 0));
+    float* drnn = bf.din[0] + r0 * H;
+    if (drop_in) RC(dropout_f32(drnn, drnn, (int64_t)nb * H, (int64_t)r0 * H, seed, 0, keep_in, -1, 1.f, tr));
+    if (am->normalization) RC(bn_backward(drnn, bf.bn_xhat + r0 * H, bf.bn_istd + (size_t)t0 * H, n, B, H, tr));
+    RC(split_planes_transposed(drnn, nb, H, H, bf.drT_hi + r0, bf.drT_lo + r0, TBp, tr));             // [H][chunk]
+    RC(transpose_bf16(bf.x_hi + r0 * Fp, nb, F, Fp, bf.xT_hi + r0, TBp, tr));
+    RC(transpose_bf16(bf.x_lo + r0 * Fp, nb, F, Fp, bf.xT_lo + r0, TBp, tr));
+    cudaEvent_t e_in;
+    RC(ev_record(am, &e_in, tr));
+    RC(rowsum_planes(bf.drT_hi + r0, bf.drT_lo + r0, H, nb, TBp, grads_d + am->off_input_b, 1, tr));
+    RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_in, 0));
+    SplitMat A{bf.xT_hi + r0, bf.xT_lo + r0, F, nb, TBp}, Bm{bf.drT_hi + r0, bf.drT_lo + r0, H, nb, TBp};
+    GemmTcOut o{};
+    o.mode = GEMM_OUT_F32; o.C = grads_d + am->off_input_w; o.ldc = H; o.accumulate = 1; o.max_ctas = sc.side_ctas;
+    if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
+    return gemm_tc_nt(A, Bm, F, H, nb, 3, o, side);
+  };
   for (int d = 0; d < NC + L - 1; ++d)
     for (int l = L - 1; l >= 0; --l) {
       const int c = NC - 1 - (d - (L - 1 - l));
@@ -581,8 +608,9 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
       if (l == 0 && c == 0 && use_elastic) RS_CHECK_CUDA(cudaMemsetAsync(bf.elastic, 1, sizeof(int), am->lane[0]));
       RC(issue_dx(l, c));
       RC(issue_side(l, c));
+      if (l == 0) RC(issue_input(c));
     }
-  // join: the input-dense gradient below reuses actT, and the caller's stream owns grads_d afterwards
+  // join: the caller's stream owns grads_d afterwards
   cudaEvent_t e_side, e_gemm, e_trj;
   RC(ev_record(am, &e_side, side));
   RC(ev_record(am, &e_gemm, am->gemm_st));
@@ -591,18 +619,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   RS_CHECK_CUDA(cudaStreamWaitEvent(st, e_gemm, 0));
   RS_CHECK_CUDA(cudaStreamWaitEvent(st, e_trj, 0));
   for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(st, e_rec[(size_t)l * NC + 0], 0));
-  // through layer 0's input dropout, then the input dense: dw_i += x^T drnn, db_i += colsum
-  float* drnn = bf.din[0];
-  if (drop_in) RC(dropout_f32(drnn, drnn, nTBH, 0, seed, 0, keep_in, -1, 1.f, st));
-  if (am->normalization) RC(bn_backward(drnn, bf.bn_xhat, bf.bn_istd, T, B, H, st));
-  RC(split_planes_transposed(drnn, TB, H, H, bf.actT_hi, bf.actT_lo, TBp, st));                     // [H][TBp]
-  RC(transpose_bf16(bf.x_hi, TB, F, Fp, bf.xT_hi, TBp, st));
-  RC(transpose_bf16(bf.x_lo, TB, F, Fp, bf.xT_lo, TBp, st));
-  SplitMat A{bf.xT_hi, bf.xT_lo, F, TB, TBp}, Bm{bf.actT_hi, bf.actT_lo, H, TB, TBp};
-  GemmTcOut o{};
-  o.mode = GEMM_OUT_F32; o.C = grads_d + am->off_input_w; o.ldc = H; o.accumulate = 1;
-  RC(gemm_tc_nt(A, Bm, F, H, TB, 3, o, st));
-  return rowsum_planes(bf.actT_hi, bf.actT_lo, H, TB, TBp, grads_d + am->off_input_b, 1, st);
+  return RS_OK;
 }
 
 }  // namespace rs
