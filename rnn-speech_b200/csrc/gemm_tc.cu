@@ -21,8 +21,10 @@ namespace {
 constexpr int BM = 128, BK = 64;
 constexpr int TILE_A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int NTHREADS = 256;
-template <int BN> struct Cfg {
-  static constexpr int STAGES = BN == 256 ? 2 : 3;
+// (BN, stages): (128, 3) and (256, 2) fill an SM's shared memory; (128, 2) leaves room -- 129 KB, 256 TMEM columns --
+// to share an SM with a backward recurrent CTA (50 KB, 256 columns, 128 registers), whose tensor pipe is ~5 % busy.
+template <int BN, int ST> struct Cfg {
+  static constexpr int STAGES = ST;
   static constexpr int TILE_B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * TILE_A_BYTES + 2 * TILE_B_BYTES;
 };
@@ -48,11 +50,11 @@ struct KParams {
   GemmTcOut out;
 };
 
-template <int BN>
+template <int BN, int ST>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, KParams p) {
-  constexpr int STAGES = Cfg<BN>::STAGES, TILE_B_BYTES = Cfg<BN>::TILE_B_BYTES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
+  constexpr int STAGES = Cfg<BN, ST>::STAGES, TILE_B_BYTES = Cfg<BN, ST>::TILE_B_BYTES, STAGE_BYTES = Cfg<BN, ST>::STAGE_BYTES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
@@ -385,7 +387,7 @@ int tmap_stacked_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols
 
 namespace {
 
-template <int BN>
+template <int BN, int ST>
 int gemm_launch(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
                 cudaStream_t st) {
   // bf16x3 degrades gracefully to the planes that exist: hi*hi (+ hi*B_lo) (+ A_lo*hi)
@@ -408,13 +410,13 @@ int gemm_launch(const SplitMat& A, const SplitMat& B, int M, int N, int K, int p
   if (grid > ntiles) grid = ntiles;
   p.base_ctas = grid;
   if (out.elastic) { grid = sm_count(); if (grid > ntiles) grid = ntiles; if (grid < p.base_ctas) grid = p.base_ctas; }
-  const size_t smem = (size_t)Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + 1024;
+  const size_t smem = (size_t)Cfg<BN, ST>::STAGES * Cfg<BN, ST>::STAGE_BYTES + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    RS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  gemm_tc_kernel<BN><<<grid, NTHREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  gemm_tc_kernel<BN, ST><<<grid, NTHREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }
@@ -434,7 +436,8 @@ int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int pr
   int ctas = sm_count();
   if (out.max_ctas > 0 && out.max_ctas < ctas && !out.elastic) ctas = out.max_ctas;
   const bool wide = force_bn ? force_bn == 256 : (N > 128 && cdiv(M, BM) * cdiv(N, 256) >= ctas);
-  return wide ? gemm_launch<256>(A, B, M, N, K, products, out, st) : gemm_launch<128>(A, B, M, N, K, products, out, st);
+  if (out.coresident) return gemm_launch<128, 2>(A, B, M, N, K, products, out, st);
+  return wide ? gemm_launch<256, 2>(A, B, M, N, K, products, out, st) : gemm_launch<128, 3>(A, B, M, N, K, products, out, st);
 }
 
 int split_planes(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t st) {

@@ -37,6 +37,7 @@ struct GemmTcOut {
   // decision for the launch (zeroed by the caller before the step).
   int* elastic;
   int elastic_id;
+  int coresident;          // 1: the 129 KB / 256-TMEM-column variant that shares SMs with the backward recurrent CTAs
   int tiles_per_cta;       // > 0: grid = ceil(tiles / tiles_per_cta) short-lived CTAs instead of a persistent grid, so
                            // that the block scheduler can place them wherever (and whenever) SMs are free
 };

@@ -411,7 +411,9 @@ struct KBwd {
   uint32_t tmem_cols;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+// 128 registers (no spills; 168 unconstrained) x 320 threads and ~50 KB of shared memory: with RS_TC_CORES=1 a 256-thread
+// GEMM CTA (gemm_tc_kernel<128, 2>) fits on the same SM
+__global__ void __maxnreg__(128)
 rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmS_hi,
                   const __grid_constant__ CUtensorMap tmS_lo, KBwd p) {
   extern __shared__ unsigned char smem_raw[];
@@ -806,7 +808,11 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
   p.tmem_cols = cols;
   p.variant = ts_variant();
   size_t smem = (size_t)p.nkbs * g.Bpad * 128 + (size_t)CL * TSU * g.Bpad * 4 + (size_t)2 * g.Bpad * 4 * TSU * 2 + 1024;
-  if (smem < 120 * 1024) smem = 120 * 1024;                        // one CTA per SM
+  // (two of these cannot share an SM: 2 x 320 x 128 registers exceed the register file)
+  static const bool share = [] { const char* v = getenv("RS_TC_CORES"); return v && v[0] == '1'; }();
+  // keep the SM to this CTA unless sharing is asked for (RS_TC_CORES=1) and a GEMM CTA can really share it (256 free
+  // tensor-memory columns); sharing measured slower at cfg-2, see lstm_tc.cu
+  if ((!share || cols > 256) && smem < 120 * 1024) smem = 120 * 1024;
   RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
   static size_t attr_smem = 0;
   if (attr_smem != smem) {

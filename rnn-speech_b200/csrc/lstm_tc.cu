@@ -239,6 +239,8 @@ int ev_record(rs_am* am, cudaEvent_t* e, cudaStream_t st) {
 struct Sched {
   int Tc, NC, gemm_ctas, fwd_gemm_ctas, side_ctas;
   int side_tpc, dx_tpc, gx_tpc;           // tiles per CTA (0 = persistent grid with the caps above)
+  int cores;                              // backward GEMMs share SMs with the recurrent CTAs (RS_TC_CORES=1; measured
+                                          // slower than keeping them apart: 1432 vs 1502 utt/s, so off by default)
 };
 Sched make_sched(const rs_am* am, int T) {
   Sched s;
@@ -261,8 +263,13 @@ Sched make_sched(const rs_am* am, int T) {
     static const int dx_tpc = [] { const char* v = getenv("RS_TC_DX_TPC"); return v ? atoi(v) : 0; }();
     static const int gx_tpc = [] { const char* v = getenv("RS_TC_GX_TPC"); return v ? atoi(v) : 0; }();
     s.side_tpc = side_tpc; s.dx_tpc = dx_tpc; s.gx_tpc = gx_tpc;
+    static const int cores = [] { const char* v = getenv("RS_TC_CORES"); return v ? atoi(v) : 0; }();
+    // only while the backward recurrent kernel leaves 256 tensor-memory columns free (H/4 + Bpad <= 256): a GEMM CTA
+    // on the same SM would otherwise sit in tcgen05.alloc until the recurrent launch ends
+    s.cores = (am->tc.ts && am->H / 4 + am->tc.Bpad <= 256) ? cores : 0;
   } else {
     s.side_tpc = s.dx_tpc = s.gx_tpc = 0;
+    s.cores = 0;
     s.gemm_ctas = 0;                                     // 0 = one CTA per SM
     s.fwd_gemm_ctas = 0;
     s.side_ctas = spare > 32 ? spare : 32;
@@ -473,7 +480,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   cudaStream_t side = am->side;
   RS_CHECK_CUDA(cudaMemsetAsync(bf.elastic, 0, 4096 * sizeof(int), st));
   int elastic_next = 0;
-  const bool use_elastic = NC > 1 && sc.side_tpc == 0 && 2 * L * NC + NC + 8 < 4096;
+  const bool use_elastic = NC > 1 && !sc.cores && sc.side_tpc == 0 && 2 * L * NC + NC + 8 < 4096;
   cudaEvent_t e_fork;
   RC(ev_record(am, &e_fork, st));
   for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(am->lane[l], e_fork, 0));
@@ -529,7 +536,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     SplitMat A{bf.dg_hi[l] + (size_t)t0 * B * 4 * H, bf.dg_lo[l] + (size_t)t0 * B * 4 * H, n * B, 4 * H, 4 * H};
     SplitMat Bm{bf.wxs_hi[l], bf.wxs_lo[l], H, 4 * H, 4 * H};
     GemmTcOut o{};
-    o.mode = GEMM_OUT_F32; o.C = bf.din[l] + (size_t)t0 * B * H; o.ldc = H; o.max_ctas = sc.gemm_ctas; o.tiles_per_cta = sc.dx_tpc;
+    o.mode = GEMM_OUT_F32; o.C = bf.din[l] + (size_t)t0 * B * H; o.ldc = H; o.max_ctas = sc.cores ? 0 : sc.gemm_ctas; o.tiles_per_cta = sc.dx_tpc; o.coresident = sc.cores;
     RC(tev_record(am, 3, l, am->gemm_st));
     RC(gemm_tc_nt(A, Bm, n * B, H, 4 * H, 3, o, am->gemm_st));
     RC(tev_record(am, 3, l, am->gemm_st));
@@ -561,14 +568,14 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     {
       SplitMat A{bf.xT2_hi[l] + r0, bf.xT2_lo[l] + r0, H, nb, TBp};
       GemmTcOut o{};
-      o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas; o.tiles_per_cta = sc.side_tpc;
+      o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.cores ? 0 : sc.side_ctas; o.tiles_per_cta = sc.side_tpc; o.coresident = sc.cores;
       if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
       RC(gemm_tc_nt(A, G, H, 4 * H, nb, 3, o, side));
     }
     {
       SplitMat A{bf.hT_hi[l] + r0, bf.hT_lo[l] + r0, H, nb, TBp};
       GemmTcOut o{};
-      o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas; o.tiles_per_cta = sc.side_tpc;
+      o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.cores ? 0 : sc.side_ctas; o.tiles_per_cta = sc.side_tpc; o.coresident = sc.cores;
       if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
       RC(gemm_tc_nt(A, G, H, 4 * H, nb, 3, o, side));
     }
@@ -595,7 +602,8 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_in, 0));
     SplitMat A{bf.xT_hi + r0, bf.xT_lo + r0, F, nb, TBp}, Bm{bf.drT_hi + r0, bf.drT_lo + r0, H, nb, TBp};
     GemmTcOut o{};
-    o.mode = GEMM_OUT_F32; o.C = grads_d + am->off_input_w; o.ldc = H; o.accumulate = 1; o.max_ctas = sc.side_ctas;
+    o.mode = GEMM_OUT_F32; o.C = grads_d + am->off_input_w; o.ldc = H; o.accumulate = 1; o.max_ctas = sc.cores ? 0 : sc.side_ctas;
+    o.coresident = sc.cores;
     if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
     return gemm_tc_nt(A, Bm, F, H, nb, 3, o, side);
   };
