@@ -371,6 +371,15 @@ def run_b200(args):
     print(json.dumps(line))
 
 
+def _shutdown():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -384,6 +393,7 @@ def main():
         run_reference(args)
     else:
         run_b200(args)
+        _shutdown()
 
 
 if __name__ == "__main__":
