@@ -127,12 +127,21 @@ ctc_lattice_kernel(const float* __restrict__ logits, const float* __restrict__ l
     if (lane == 0) wmax[warp] = mloc;
     if (threadIdx.x == 0) offs[0] = 0.0;
     __syncthreads();
-    for (int t = 1; t < L; ++t) {
+    // The emission log-probability of this thread's lattice state does not depend on the recurrence, but a gather
+    // issued where it is used puts an L2 round trip on the chain of T dependent steps (ncu: half of the kernel's
+    // stall samples).  It is loaded two steps ahead instead -- the loop is unrolled by two so that the two values in
+    // flight live in fixed registers (moving a register whose load is pending would wait for it).
+    const int u0 = threadIdx.x;
+    const int l_u0 = (u0 < U) ? lp[u0] : blank;
+    // raw (logit, log-sum-exp) pair: the subtraction happens where the value is used, after the step's barrier
+    auto emission = [&](int t) -> float2 {
+      return (t < L) ? make_float2(logits[((size_t)t * B + b) * C + l_u0], lse[t * B + b]) : make_float2(0.f, 0.f);
+    };
+    auto alpha_step = [&](int t, float2 em) {
       const float M = row_max((t - 1) & 1);
       O += (double)M;
       if (threadIdx.x == 0) offs[t] = O;
       const float* lgt = logits + ((size_t)t * B + b) * C;
-      const float lt = lse[t * B + b];
       const int lo = max(0, U - 2 * (L - t)), hi = min(U, 2 * (t + 1));
       mloc = kNegInf;
       for (int u = threadIdx.x; u < U; u += blockDim.x) {
@@ -141,7 +150,8 @@ ctc_lattice_kernel(const float* __restrict__ logits, const float* __restrict__ l
           const int l = lp[u];
           const bool skip = (u > 1) && (l != blank) && (l != lp[u - 2]);
           const float a0 = prev[u], a1 = prev[u - 1], a2 = skip ? prev[u - 2] : kNegInf;
-          v = (lse3(a0, a1, a2) - M) + (lgt[l] - lt);
+          const float e = (u == u0) ? (em.x - em.y) : (lgt[l] - lse[t * B + b]);
+          v = (lse3(a0, a1, a2) - M) + e;
         }
         cur[u] = v;
         out[(size_t)t * Upad + u] = v;
@@ -151,7 +161,14 @@ ctc_lattice_kernel(const float* __restrict__ logits, const float* __restrict__ l
       if (lane == 0) wmax[(t & 1) * 32 + warp] = mloc;
       __syncthreads();
       float* tmp = prev; prev = cur; cur = tmp;
+    };
+    float2 em_a = emission(1), em_b = emission(2);
+    int t = 1;
+    for (; t + 1 < L; t += 2) {
+      { const float2 e = em_a; em_a = emission(t + 2); alpha_step(t, e); }
+      { const float2 e = em_b; em_b = emission(t + 3); alpha_step(t + 1, e); }
     }
+    if (t < L) alpha_step(t, em_a);
   } else {
     float* prev = rowbuf;            // beta~[t+1] + logp[t+1]  ("nxt" in the oracle), offset Ob[t+1]
     float* cur = rowbuf + stride;
@@ -171,12 +188,16 @@ ctc_lattice_kernel(const float* __restrict__ logits, const float* __restrict__ l
     if (lane == 0) wmax[((L - 1) & 1) * 32 + warp] = mloc;
     if (threadIdx.x == 0) offs[L - 1] = 0.0;
     __syncthreads();
-    for (int t = L - 2; t >= 0; --t) {
+    const int u0 = threadIdx.x;                         // emission gathered two steps ahead: see the alpha loop
+    const int l_u0 = (u0 < U) ? lp[u0] : blank;
+    auto emission = [&](int t) -> float2 {
+      return (t >= 0) ? make_float2(logits[((size_t)t * B + b) * C + l_u0], lse[t * B + b]) : make_float2(0.f, 0.f);
+    };
+    auto beta_step = [&](int t, float2 em) {
       const float M = row_max((t + 1) & 1);
       O += (double)M;
       if (threadIdx.x == 0) offs[t] = O;
       const float* lgt = logits + ((size_t)t * B + b) * C;
-      const float lt = lse[t * B + b];
       const int lo = max(0, U - 2 * (L - t)), hi = min(U, 2 * (t + 1));
       mloc = kNegInf;
       for (int u = threadIdx.x; u < U; u += blockDim.x) {
@@ -192,7 +213,7 @@ ctc_lattice_kernel(const float* __restrict__ logits, const float* __restrict__ l
           v = lse3(b0, b1, b2) - M;
         }
         out[(size_t)t * Upad + u] = v;
-        const float nx = v + (lgt[l] - lt);   // becomes "nxt" for row t-1
+        const float nx = v + ((u == u0) ? (em.x - em.y) : (lgt[l] - lse[t * B + b]));   // becomes "nxt" for row t-1
         cur[u] = nx;
         mloc = fmaxf(mloc, nx);
       }
@@ -200,7 +221,14 @@ ctc_lattice_kernel(const float* __restrict__ logits, const float* __restrict__ l
       if (lane == 0) wmax[(t & 1) * 32 + warp] = mloc;
       __syncthreads();
       float* tmp = prev; prev = cur; cur = tmp;
+    };
+    float2 em_a = emission(L - 2), em_b = emission(L - 3);
+    int t = L - 2;
+    for (; t - 1 >= 0; t -= 2) {
+      { const float2 e = em_a; em_a = emission(t - 2); beta_step(t, e); }
+      { const float2 e = em_b; em_b = emission(t - 3); beta_step(t - 1, e); }
     }
+    if (t >= 0) beta_step(t, em_a);
     // log p(z|x) = LSE_u(alpha[0,u] + beta[0,u]); alpha[0,u] = logp[0,l'u] for u in {0,1}
     // and prev[u] now holds beta~[0,u] + logp[0,l'u] (offset O = Ob[0]).
     if (threadIdx.x == 0) {
