@@ -136,8 +136,7 @@ fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ o
   const int nuse = min(frame_length, kNfft);       // rfft(frames, 512) crops or zero-pads
   const int span = (kFramesPerCta - 1) * frame_step + nuse;
   double* sfft = reinterpret_cast<double*>(sm_raw);              // [8][2][512]
-  double* spw = sfft + kFbankWarps * 2 * kNfft;                  // [8][2][260]
-  double* scol = spw + kFbankWarps * 2 * 260;                    // [8][40] per-warp column sums
+  double* scol = sfft + kFbankWarps * 2 * kNfft;                 // [8][40] per-warp column sums
   float* spcm = reinterpret_cast<float*>(scol + kFbankWarps * kNfilt);   // [span + 1], spcm[i] = x[s0 - 1 + i]
   const int64_t s0 = (int64_t)t0 * frame_step;
   const float* x = pcm + off;
@@ -151,7 +150,6 @@ fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ o
 
   double* re = sfft + warp * 2 * kNfft;
   double* im = re + kNfft;
-  double* pw = spw + warp * 2 * 260;
   const double* __restrict__ win = tab->window;
   const double* __restrict__ twr = tab->tw_re;
   const double* __restrict__ twi = tab->tw_im;
@@ -206,16 +204,20 @@ fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ o
       }
       __syncwarp();
     }
-    // unpack the two real spectra, power = |X|^2 / 512
+    // unpack the two real spectra, power = |X|^2 / 512.  Bin k only needs the FFT outputs k and 512 - k, and no other
+    // bin needs them, so the two power spectra overwrite re[0..256] / im[0..256] in place (no second buffer: the
+    // CTA's shared memory drops from 122 KB to 89 KB and two CTAs fit on an SM).
     for (int k = lane; k < kBins; k += 32) {
       const int nk = (kNfft - k) & (kNfft - 1);
       const double zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
       const double ar = 0.5 * (zr + yr), ai = 0.5 * (zi - yi);
       const double br = 0.5 * (zi + yi), bi = -0.5 * (zr - yr);
-      pw[k] = (ar * ar + ai * ai) * (1.0 / kNfft);
-      pw[260 + k] = (br * br + bi * bi) * (1.0 / kNfft);
+      re[k] = (ar * ar + ai * ai) * (1.0 / kNfft);
+      im[k] = (br * br + bi * bi) * (1.0 / kNfft);
     }
     __syncwarp();
+    const double* pw = re;
+    const double* pwb = im;
     // 40 triangular filters; one lane owns filter m for BOTH frames of the pair so the
     // per-warp column sums are accumulated in a fixed order (deterministic).
     for (int m = lane; m < kNfilt; m += 32) {
@@ -225,7 +227,7 @@ fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ o
       for (int k = tab->mstart[m]; k < k1; ++k) {
         const double wk = w[k];
         acc_a = fma(pw[k], wk, acc_a);
-        acc_b = fma(pw[260 + k], wk, acc_b);
+        acc_b = fma(pwb[k], wk, acc_b);
       }
       if (acc_a == 0.0) acc_a = 2.220446049250313e-16;   // util/audioprocessor.py:135
       if (acc_b == 0.0) acc_b = 2.220446049250313e-16;
@@ -384,10 +386,13 @@ extern "C" int rs_fbank_forward(const float* pcm_d, const int64_t* offsets_d, in
 
   const int nuse = fp.frame_length < kNfft ? fp.frame_length : kNfft;
   const int span = (kFramesPerCta - 1) * fp.frame_step + nuse;
-  size_t smem = (size_t)(kFbankWarps * 2 * kNfft + kFbankWarps * 2 * 260 + kFbankWarps * kNfilt) * sizeof(double) +
+  size_t smem = (size_t)(kFbankWarps * 2 * kNfft + kFbankWarps * kNfilt) * sizeof(double) +
                 (size_t)(span + 1 + 3) * sizeof(float);
   RS_REQUIRE(smem <= 220 * 1024, RS_ERR_UNSUPPORTED, "rs_fbank_forward: sr %d needs %zu B smem", sr, smem);
   RS_CHECK_CUDA(cudaFuncSetAttribute(fbank_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // (two 89 KB CTAs per SM; measured: occupancy does not move this kernel -- 0.39 ms either way -- its radix-2 stages
+  //  are bound by 64-bit shared-memory traffic, see DESIGN.md "what comes next")
+  RS_CHECK_CUDA(cudaFuncSetAttribute(fbank_logmel_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   fbank_logmel_kernel<<<dim3(nblk, B), kFbankWarps * 32, smem, st>>>(pcm_d, offsets_d, tab_d, fp.frame_length,
                                                                      fp.frame_step, Tfull, nblk, logmel, partial,
                                                                      nframes_d);
