@@ -44,6 +44,9 @@ const char* rs_last_error(void);
 int rs_sm_count(void);
 /* Number of kernels this library has launched in this process so far. */
 uint64_t rs_launch_count(void);
+/* CRC-32C of a host buffer, continuing from `crc` (0 to start): TensorFlow's tensor-bundle checksum, for the
+ * checkpoint writer (rnn-speech_b200/tf_checkpoint.py). */
+uint32_t rs_crc32c(const void* data, size_t n, uint32_t crc);
 
 /* ------------------------------------------------------------------------
  * (a) Feature extraction.  Replaces AudioProcessor.process_signal(sig, sr)

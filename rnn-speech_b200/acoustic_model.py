@@ -262,17 +262,24 @@ class AcousticModel(object):
         self.is_training = bool(is_training)
 
     # ----------------------------------------------------------- checkpointing
-    def save(self, session, checkpoint_dir):
-        """models/AcousticModel.py:483-487.  Writes the same variable set (weights,
-        global_step, learning_rate; no Adam slots, no RNN state) as a numpy archive
-        named like the TF checkpoint prefix."""
-        path = os.path.join(checkpoint_dir, "acousticmodel.ckpt-%d.npz" % self.global_step)
+    def save(self, session, checkpoint_dir, fmt="npz"):
+        """models/AcousticModel.py:483-487.  Writes the same variable set (weights, global_step, learning_rate; no
+        Adam slots, no RNN state) under the TF checkpoint prefix: fmt="npz" a numpy archive, fmt="tf" the reference's
+        own tensor-bundle format (acousticmodel.ckpt-N.index / .data-00000-of-00001, tf_checkpoint.write_bundle)."""
         arrays = {k: v.detach().cpu().numpy() for k, v in self.param_views().items()}
-        arrays["global_step"] = np.int64(self.global_step)
-        arrays["learning_rate"] = np.float32(self.learning_rate_var if self.learning_rate_var is not None else 0.0)
-        np.savez(path, **arrays)
+        arrays["global_step"] = np.array(self.global_step, np.int32)
+        arrays["learning_rate"] = np.array(self.learning_rate_var if self.learning_rate_var is not None else 0.0, np.float32)
+        if fmt == "tf":
+            from .tf_checkpoint import write_bundle
+            name = "acousticmodel.ckpt-%d" % self.global_step
+            path = os.path.join(checkpoint_dir, name)
+            write_bundle(path, arrays, accel=_lib.raw("rs_crc32c"))
+        else:
+            name = "acousticmodel.ckpt-%d.npz" % self.global_step
+            path = os.path.join(checkpoint_dir, name)
+            np.savez(path, **arrays)
         with open(os.path.join(checkpoint_dir, "checkpoint"), "w") as fh:
-            fh.write('model_checkpoint_path: "%s"\n' % os.path.basename(path))
+            fh.write('model_checkpoint_path: "%s"\n' % name)
         logging.info("Checkpoint saved")
         return path
 

@@ -198,3 +198,136 @@ def load_reference_checkpoint(prefix):
         if not values:
             raise bundle_error
         return values, "meta"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Writer: the same tensor-bundle layout, so that the reference (tf.train.Saver.restore, models/AcousticModel.py:489-499)
+# can read what this library trained.  Checksums are CRC-32C, stored masked as TensorFlow / LevelDB do
+# (rot-right 15 plus 0xa282ead8); the convention is pinned against the block trailers of the index file shipped
+# with the reference (tests/test_tf_checkpoint.py).  TensorFlow itself is not available here: what is verified is the
+# byte layout (round trip through the reader above) and every checksum rule against that TF-written file.
+_CRC_TABLE = None
+
+
+def crc32c(data, crc=0, accel=None):
+    """CRC-32C of bytes-like `data` continuing from `crc`.  `accel(data_ptr, n, crc) -> crc` (the library's
+    rs_crc32c) is used for large buffers when given; the pure-Python table walk otherwise."""
+    global _CRC_TABLE
+    if accel is not None and len(data) >= 4096:
+        buf = np.frombuffer(data, dtype=np.uint8)
+        return int(accel(buf.ctypes.data, buf.size, crc))
+    if _CRC_TABLE is None:
+        tab = []
+        for i in range(256):
+            c = i
+            for _ in range(8):
+                c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+            tab.append(c)
+        _CRC_TABLE = tab
+    c = crc ^ 0xFFFFFFFF
+    tab = _CRC_TABLE
+    for b in bytes(data):
+        c = (c >> 8) ^ tab[(c ^ b) & 0xFF]
+    return c ^ 0xFFFFFFFF
+
+
+def mask_crc(crc):
+    return (((crc >> 15) | (crc << 17)) + 0xa282ead8) & 0xFFFFFFFF
+
+
+def _enc_varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+_DTYPE_ENUM = {np.dtype(np.float32): 1, np.dtype(np.float64): 2, np.dtype(np.int32): 3, np.dtype(np.int64): 9}
+
+
+def _table_block(items, restart_interval=16):
+    """One LevelDB table block: prefix-compressed entries, restart offsets, restart count."""
+    out, restarts, prev = bytearray(), [], b""
+    for i, (key, value) in enumerate(items):
+        shared = 0
+        if i % restart_interval == 0:
+            restarts.append(len(out))
+        else:
+            while shared < min(len(key), len(prev)) and key[shared] == prev[shared]:
+                shared += 1
+        out += _enc_varint(shared) + _enc_varint(len(key) - shared) + _enc_varint(len(value)) + key[shared:] + value
+        prev = key
+    if not restarts:
+        restarts = [0]
+    for r in restarts:
+        out += struct.pack("<I", r)
+    out += struct.pack("<I", len(restarts))
+    return bytes(out)
+
+
+def _with_trailer(block):
+    """block + compression type (0 = none) + masked CRC-32C of both."""
+    return block + b"\x00" + struct.pack("<I", mask_crc(crc32c(block + b"\x00")))
+
+
+def write_bundle(prefix, tensors, accel=None):
+    """Write `tensors` (name -> ndarray; float32 / float64 / int32 / int64) as `<prefix>.index` +
+    `<prefix>.data-00000-of-00001`.  Returns the list of names written, in file order."""
+    names = sorted(tensors)
+    items = [(b"", b"\x08\x01\x1a\x02\x08\x01")]           # BundleHeaderProto: num_shards 1, version.producer 1
+    offset = 0
+    with open(prefix + ".data-00000-of-00001", "wb") as fh:
+        for name in names:
+            arr = np.asarray(tensors[name])
+            if arr.ndim and not arr.flags.c_contiguous:      # (ascontiguousarray would turn a scalar into shape (1,))
+                arr = np.ascontiguousarray(arr)
+            if arr.dtype not in _DTYPE_ENUM:
+                raise ValueError("tensor %s: dtype %s is not supported by the bundle writer" % (name, arr.dtype))
+            raw = arr.tobytes()
+            shape = b"".join(b"\x12" + _enc_varint(len(b"\x08" + _enc_varint(d))) + b"\x08" + _enc_varint(d)
+                             for d in arr.shape)
+            ent = b"\x08" + _enc_varint(_DTYPE_ENUM[arr.dtype]) + b"\x12" + _enc_varint(len(shape)) + shape
+            if offset:
+                ent += b"\x20" + _enc_varint(offset)
+            ent += b"\x28" + _enc_varint(len(raw)) + b"\x35" + struct.pack("<I", mask_crc(crc32c(raw, accel=accel)))
+            items.append((name.encode("utf-8"), ent))
+            fh.write(raw)
+            offset += len(raw)
+    data_block = _table_block(items)
+    body = _with_trailer(data_block)
+    meta_off = len(body)
+    meta_block = _table_block([])
+    body += _with_trailer(meta_block)
+    # index block: one entry whose key is >= the last key of the data block
+    index_block = _table_block([(items[-1][0] + b"\x00", _enc_varint(0) + _enc_varint(len(data_block)))], 1)
+    idx_off = len(body)
+    body += _with_trailer(index_block)
+    footer = _enc_varint(meta_off) + _enc_varint(len(meta_block)) + _enc_varint(idx_off) + _enc_varint(len(index_block))
+    footer += b"\x00" * (40 - len(footer)) + struct.pack("<Q", _MAGIC)
+    with open(prefix + ".index", "wb") as fh:
+        fh.write(body + footer)
+    return names
+
+
+def verify_table_checksums(path):
+    """Check the masked CRC-32C trailer of every block of a table file; returns the number of blocks checked."""
+    buf = open(path, "rb").read()
+    footer = buf[-48:]
+    meta_off, pos = _varint(footer, 0)
+    meta_size, pos = _varint(footer, pos)
+    idx_off, pos = _varint(footer, pos)
+    idx_size, pos = _varint(footer, pos)
+    handles = [(meta_off, meta_size), (idx_off, idx_size)]
+    for _key, handle in _block_entries(buf, idx_off, idx_size):
+        off, p = _varint(handle, 0)
+        size, p = _varint(handle, p)
+        handles.append((off, size))
+    for off, size in handles:
+        want = struct.unpack_from("<I", buf, off + size + 1)[0]
+        got = mask_crc(crc32c(buf[off:off + size + 1]))
+        if want != got:
+            raise ValueError("%s: block at %d: checksum %08x, expected %08x" % (path, off, got, want))
+    return len(handles)

@@ -167,3 +167,31 @@ def test_restore_from_a_tensorflow_bundle(pkg, cuda, tmp_path):
     assert m.global_step == 4321 and abs(m.learning_rate_var - 2.5e-4) < 1e-9
     for k, v in m.param_views().items():
         np.testing.assert_array_equal(v.cpu().numpy(), tensors[k])
+
+
+def test_save_in_the_reference_format_and_restore(pkg, cuda, tmp_path):
+    """save(fmt="tf") writes the reference's tensor-bundle checkpoint (checksums through the library's rs_crc32c);
+    every block verifies and restore() brings the parameters back bit for bit."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("tfck2", os.path.join(root, "rnn-speech_b200", "tf_checkpoint.py"))
+    tfck = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tfck)
+    L, H, F, C = 2, 128, 40, 30
+    m = pkg.AcousticModel(L, H, 4, 50, 600, F, False, C, device=cuda, seed=3)
+    m.create_training_rnn(1.0, 1.0, 1, 3e-4, 0.33)
+    m.initialize(None)
+    m.global_step = 77
+    want = m.params.clone()
+    path = m.save(None, str(tmp_path), fmt="tf")
+    assert tfck.verify_table_checksums(path + ".index") == 3
+    # payload checksum of one tensor as stored in its entry (accelerated CRC == pure-Python CRC)
+    w = m.param_views()["Output_layer/output_w"].cpu().numpy().tobytes()
+    assert tfck.struct.pack("<I", tfck.mask_crc(tfck.crc32c(w))) in open(path + ".index", "rb").read()
+    m2 = pkg.AcousticModel(L, H, 4, 50, 600, F, False, C, device=cuda, seed=9)
+    m2.create_training_rnn(1.0, 1.0, 1, 1e-3, 0.33)
+    m2.initialize(None)
+    m2.restore(None, str(tmp_path))
+    assert m2.global_step == 77 and abs(m2.learning_rate_var - 3e-4) < 1e-9
+    assert torch.equal(m2.params, want)

@@ -132,3 +132,37 @@ def test_shipped_model_is_readable_from_its_meta_file():
     bias = values["rnn/multi_rnn_cell/cell_0/basic_lstm_cell/bias"].reshape(4, 1024)
     assert abs(float(bias[1].mean())) < 0.01
     assert sum(int(np.prod(v.shape)) for k, v in values.items() if k not in ("global_step", "learning_rate")) == 25384016
+
+
+def test_crc32c_known_answers_and_tf_written_block_trailers():
+    # RFC 3720 check value, and the 32 zero bytes vector
+    assert tfck.crc32c(b"123456789") == 0xE3069283
+    assert tfck.crc32c(bytes(32)) == 0x8A9136AA
+    assert tfck.crc32c(b"6789", tfck.crc32c(b"12345")) == 0xE3069283          # continuation
+    # the masking rule and "block + type byte" coverage are TensorFlow's: every block of the index file that TF wrote
+    # for the reference's shipped checkpoint verifies
+    assert tfck.verify_table_checksums(os.path.join(ROOT, "tests", "golden", "tf_bundle", "acousticmodel.ckpt.index")) == 3
+
+
+def test_written_bundle_reads_back_and_verifies(tmp_path):
+    rng = np.random.default_rng(1)
+    tensors = {"Input_Layer/input_w": rng.standard_normal((5, 7)).astype(np.float32),
+               "rnn/multi_rnn_cell/cell_0/basic_lstm_cell/kernel": rng.standard_normal((14, 28)).astype(np.float32),
+               "rnn/multi_rnn_cell/cell_0/basic_lstm_cell/bias": rng.standard_normal(28).astype(np.float32),
+               "global_step": np.array(123, np.int32), "learning_rate": np.array(3e-4, np.float32)}
+    for i in range(40):                                     # enough keys for several restart points
+        tensors["extra/var_%02d" % i] = np.full((i % 3 + 1,), i, np.int64)
+    prefix = str(tmp_path / "acousticmodel.ckpt-123")
+    names = tfck.write_bundle(prefix, tensors)
+    assert names == sorted(tensors)
+    assert tfck.verify_table_checksums(prefix + ".index") == 3
+    entries, shards = tfck.read_bundle_index(prefix)
+    assert shards == 1 and sorted(entries) == sorted(tensors)
+    got = tfck.read_bundle(prefix)
+    for k in tensors:
+        assert got[k].shape == np.asarray(tensors[k]).shape and got[k].dtype == np.asarray(tensors[k]).dtype
+        np.testing.assert_array_equal(got[k], tensors[k])
+    # the per-tensor checksum in the entry is the masked CRC-32C of the payload
+    raw = open(prefix + ".index", "rb").read()
+    w = tensors["Input_Layer/input_w"].tobytes()
+    assert struct.pack("<I", tfck.mask_crc(tfck.crc32c(w))) in raw
