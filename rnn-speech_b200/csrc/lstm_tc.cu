@@ -238,6 +238,7 @@ int ev_record(rs_am* am, cudaEvent_t* e, cudaStream_t st) {
 // wavefront: `window` recurrent launches in flight (nslice SMs each), the chunk GEMMs on the remaining SMs.
 struct Sched {
   int Tc, NC, gemm_ctas, fwd_gemm_ctas, side_ctas;
+  std::vector<int> start;                 // chunk c covers the steps [start[c], start[c + 1])
   int side_tpc, dx_tpc, gx_tpc;           // tiles per CTA (0 = persistent grid with the caps above)
   int cores;                              // backward GEMMs share SMs with the recurrent CTAs (RS_TC_CORES=1; measured
                                           // slower than keeping them apart: 1432 vs 1502 utt/s, so off by default)
@@ -246,7 +247,31 @@ Sched make_sched(const rs_am* am, int T) {
   Sched s;
   int Tc = (am->chunk + 7) / 8 * 8;                    // chunk starts stay 16-byte aligned in the transposed planes
   s.Tc = (am->tc.ts && am->chunk > 0 && Tc < T) ? Tc : T;
-  s.NC = cdiv(T, s.Tc);
+  // Chunk boundaries: uniform.  (While the wavefront fills and drains fewer launches are runnable than lanes, for as
+  // long as the first and the last chunk last; RS_TC_RAMP=1 makes those short -- 48, 80 steps at each end.  Measured at
+  // cfg-2: forward 8.59 -> 8.49 ms, backward 11.37 -> 11.77 ms, 1513 -> 1500 utt/s, so it is off.)
+  s.start.clear();
+  s.start.push_back(0);
+  static const int ramp = [] { const char* v = getenv("RS_TC_RAMP"); return v ? atoi(v) : 0; }();
+  if (s.Tc < T && ramp && T >= 4 * s.Tc) {
+    const int head[2] = {(s.Tc * 3 / 8 + 7) / 8 * 8, (s.Tc * 5 / 8 + 7) / 8 * 8};
+    const int h_end = head[0] + head[1];                       // every boundary but T is a multiple of 8
+    const int tail1 = (T - h_end) / 8 * 8, tail2 = (T - head[0]) / 8 * 8;
+    s.start.push_back(head[0]);
+    s.start.push_back(h_end);
+    const int mid = tail1 - h_end;
+    const int nmid = cdiv(mid, s.Tc);
+    const int each = (cdiv(mid, nmid) + 7) / 8 * 8;
+    for (int i = 1; i < nmid; ++i)
+      if (h_end + i * each < tail1) s.start.push_back(h_end + i * each);
+    s.start.push_back(tail1);
+    if (tail2 > tail1) s.start.push_back(tail2);
+    s.start.push_back(T);
+  } else {
+    for (int t = s.Tc; t < T; t += s.Tc) s.start.push_back(t);
+    s.start.push_back(T);
+  }
+  s.NC = (int)s.start.size() - 1;
   const int spare = sm_count() - (s.NC > 1 ? am->window : 1) * am->tc.nslice;
   if (s.NC > 1) {
     // The SMs the recurrent launches leave idle serve the chunk GEMMs on the critical path (a third of the backward
@@ -364,7 +389,7 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
 
   // hoisted input half of chunk c: gx = xin @ K[:H] + b, written in the recurrent kernel's layout
   auto issue_gemm = [&](int l, int c) -> int {
-    const int t0 = c * sc.Tc, n = (t0 + sc.Tc <= T ? sc.Tc : T - t0);
+    const int t0 = sc.start[c], n = sc.start[c + 1] - sc.start[c];
     if (l > 0) RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_out[(size_t)(l - 1) * NC + c], 0));
     SplitMat A{bf.wx_hi[l], bf.wx_lo[l], 4 * H, H, H};
     SplitMat Bm{in_hi[l] + (size_t)t0 * B * in_ld[l], in_lo[l] + (size_t)t0 * B * in_ld[l], n * B, H, in_ld[l]};
@@ -376,7 +401,7 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     return ev_record(am, &e_gx[(size_t)l * NC + c], am->gemm_st);
   };
   auto issue_rec = [&](int l, int c) -> int {
-    const int t0 = c * sc.Tc, n = (t0 + sc.Tc <= T ? sc.Tc : T - t0);
+    const int t0 = sc.start[c], n = sc.start[c + 1] - sc.start[c];
     cudaStream_t ls = am->lane[l];
     RS_CHECK_CUDA(cudaStreamWaitEvent(ls, e_gx[(size_t)l * NC + c], 0));
     if (NC > 1 && (int)done.size() >= am->window) RS_CHECK_CUDA(cudaStreamWaitEvent(ls, done[done.size() - am->window], 0));
@@ -501,7 +526,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
 
   std::vector<cudaEvent_t> e_rec((size_t)L * NC), e_dx((size_t)L * NC), done;
   auto issue_rec = [&](int l, int c) -> int {
-    const int t0 = c * sc.Tc, n = (t0 + sc.Tc <= T ? sc.Tc : T - t0);
+    const int t0 = sc.start[c], n = sc.start[c + 1] - sc.start[c];
     cudaStream_t ls = am->lane[l];
     if (l + 1 < L) RS_CHECK_CUDA(cudaStreamWaitEvent(ls, e_dx[(size_t)(l + 1) * NC + c], 0));
     // gradient wrt out_t of this layer: through the hop's dropout mask(s), in place
@@ -531,7 +556,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   };
   // critical path between layers: din[l] = dg @ K[:H]^T for the steps of chunk c
   auto issue_dx = [&](int l, int c) -> int {
-    const int t0 = c * sc.Tc, n = (t0 + sc.Tc <= T ? sc.Tc : T - t0);
+    const int t0 = sc.start[c], n = sc.start[c + 1] - sc.start[c];
     RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_rec[(size_t)l * NC + c], 0));
     SplitMat A{bf.dg_hi[l] + (size_t)t0 * B * 4 * H, bf.dg_lo[l] + (size_t)t0 * B * 4 * H, n * B, 4 * H, 4 * H};
     SplitMat Bm{bf.wxs_hi[l], bf.wxs_lo[l], H, 4 * H, 4 * H};
@@ -545,7 +570,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   // side stream: dK[:H] += xin^T dg ; dK[H:] += hprev^T dg ; db += colsum(dg) over the steps of chunk c, as soon as
   // that chunk's dgates exist (fp32 accumulation into the gradient buffer, chunk after chunk)
   auto issue_side = [&](int l, int c) -> int {
-    const int t0 = c * sc.Tc, n = (t0 + sc.Tc <= T ? sc.Tc : T - t0);
+    const int t0 = sc.start[c], n = sc.start[c + 1] - sc.start[c];
     const size_t r0 = (size_t)t0 * B;                   // first (t, b) row of the chunk = first column of the transposes
     const int nb = n * B;
     // transposes (K-major operands for the tensor core) and the bias sums: small CTAs that share SMs with the
@@ -585,7 +610,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   // dw_i += x^T drnn, db_i += colsum(drnn); elementwise work and transposes on the transposer stream, the GEMM on
   // the side stream
   auto issue_input = [&](int c) -> int {
-    const int t0 = c * sc.Tc, n = (t0 + sc.Tc <= T ? sc.Tc : T - t0);
+    const int t0 = sc.start[c], n = sc.start[c + 1] - sc.start[c];
     const size_t r0 = (size_t)t0 * B;
     const int nb = n * B;
     cudaStream_t tr = am->tr_st;
