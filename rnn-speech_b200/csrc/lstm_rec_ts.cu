@@ -112,6 +112,27 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint
                : "memory");
 }
 
+// n TMEM-resident K-blocks (64 elements each = four K16 MMAs) issued back to back: A block i at a0 + 32 i columns,
+// B block i at b0 + i * bstep.  Fully unrolled for the usual counts so that no per-block address arithmetic sits
+// between two tcgen05.mma.
+template <int N>
+__device__ __forceinline__ void issue_ts_n(uint32_t d, uint32_t a0, uint64_t b0, uint64_t bstep, uint32_t idesc,
+                                           uint32_t acc_first) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    tc::mma4_bf16_ts_warp(d, a0 + (uint32_t)(i * 32), b0 + (uint64_t)i * bstep, idesc, i ? 1u : acc_first);
+}
+// (only the count of the benchmark shape is unrolled in each kernel: every extra case is a few hundred more instructions
+//  in kernels whose hot loops should stay in the instruction cache -- with eight cases the gain was gone)
+template <int NFAST>
+__device__ __forceinline__ void issue_ts_blocks(int n, uint32_t d, uint32_t a0, uint64_t b0, uint64_t bstep,
+                                                uint32_t idesc, uint32_t acc_first) {
+  if (n == NFAST) issue_ts_n<NFAST>(d, a0, b0, bstep, idesc, acc_first);
+  else
+    for (int i = 0; i < n; ++i)
+      tc::mma4_bf16_ts_warp(d, a0 + (uint32_t)(i * 32), b0 + (uint64_t)i * bstep, idesc, i ? 1u : acc_first);
+}
+
 struct KFwd {
   RecTcFwdArgs a;
   int H, B, Bpad, nslice, slots, nkb, nkb_t, ngroups, ngl, gkb;
@@ -225,11 +246,19 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         if (lane == 0 && grp == 0) RS_STAMP(a.dbg, t, 2);
         if (lane == 0 && grp >= 1 && grp <= 3) RS_STAMP(a.dbg, t, 10 + grp);       // 11..13: later groups landed
         __syncwarp();
-        for (int i = 0; i < gkb; ++i) {
-          const int kb = grp * gkb + i;
-          const uint64_t dh = dring0 + (uint64_t)s * (slot_bytes >> 4) + (uint64_t)i * kb_u;
-          if (kb < nkb_t) tc::mma4_bf16_ts_warp(tmemD, tmem + (uint32_t)(kb * 32), dh, idesc, (uint32_t)(kb != 0));
-          else tc::mma4_bf16_ss_warp(tmemD, dA0 + (uint64_t)(kb - nkb_t) * (16384 >> 4), dh, idesc, (uint32_t)(kb != 0));
+        {
+          // TMEM-resident blocks of this group first (unrolled for the usual counts: the descriptors of all blocks are
+          // ready before the first issue -- a rolled loop spent ~16 cycles per MMA on them, 4.64 -> 4.26 ms per layer
+          // at cfg-2), then the blocks that live in shared memory
+          const int kb0 = grp * gkb;
+          const int nts = min(max(nkb_t - kb0, 0), gkb);
+          const uint64_t dbase = dring0 + (uint64_t)s * (slot_bytes >> 4);
+          issue_ts_blocks<12>(nts, tmemD, tmem + (uint32_t)(kb0 * 32), dbase, kb_u, idesc, (uint32_t)(kb0 != 0));   // 12: H = 768
+          for (int i = nts; i < gkb; ++i) {
+            const int kb = kb0 + i;
+            tc::mma4_bf16_ss_warp(tmemD, dA0 + (uint64_t)(kb - nkb_t) * (16384 >> 4), dbase + (uint64_t)i * kb_u, idesc,
+                                  (uint32_t)(kb != 0));
+          }
         }
         if (lane == 0 && grp == 0) RS_STAMP(a.dbg, t, 14);                          // group 0 MMAs issued
         __syncwarp();
@@ -493,8 +522,7 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       tc::tc_fence_after();
       if (lane == 0) RS_STAMP(a.dbg, t, 2);
       __syncwarp();
-      for (int i = 0; i < nkbs; ++i)
-        tc::mma4_bf16_ts_warp(tmemD, tmem + (uint32_t)(i * 32), dg0 + (uint64_t)i * (kb_bytes >> 4), idesc, (uint32_t)(i != 0));
+      issue_ts_blocks<6>(nkbs, tmemD, tmem, dg0, (uint64_t)(kb_bytes >> 4), idesc, 0u);                                // 6: H = 768
       tc::mma_commit_warp(&tfull_bar);
       if (lane == 0) RS_STAMP(a.dbg, t, 3);
       __syncwarp();
