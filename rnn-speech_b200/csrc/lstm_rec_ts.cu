@@ -59,7 +59,7 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 // timeline stamps of CTA 0 (rows [0,T)) and of the last CTA (rows [T,2T)); 16 events per step
-#define RS_STAMP(dbgp, step, ev) do { if ((dbgp) && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) \
+#define RS_STAMP(dbgp, step, ev) do { if constexpr (STAMP) if ((dbgp) && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) \
     (dbgp)[((size_t)(blockIdx.x ? a.T : 0) + (size_t)(step)) * 16 + (ev)] = gtime(); } while (0)
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
@@ -151,6 +151,8 @@ __device__ __forceinline__ size_t blob_idx(int t, int nslice, int j, int ngl, in
 // up = lane >> 4 -> columns [8 up, 8 up + 8) of the group.  After the quad exchange the lane owns
 // the two cells (unit ul, batch b = 16 gi + 8 up + 2 g + k), k = 0, 1.
 
+// STAMP: the instantiation with the timeline stamps compiled in is launched only when a debug buffer is attached
+template <bool STAMP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmS, KFwd p) {
   extern __shared__ unsigned char smem_raw[];
@@ -412,7 +414,8 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         }
       }
       if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 7);
-      if (threadIdx.x == 0 && a.dbg && blockIdx.x == 0) a.dbg[(size_t)t * 16 + 15] = (unsigned long long)clock64();   // SM clock vs globaltimer
+      if constexpr (STAMP)
+        if (threadIdx.x == 0 && a.dbg && blockIdx.x == 0) a.dbg[(size_t)t * 16 + 15] = (unsigned long long)clock64();   // SM clock vs globaltimer
     }
 #pragma unroll
     for (int gl = 0; gl < MAXG; ++gl)
@@ -442,6 +445,7 @@ struct KBwd {
 
 // 128 registers (no spills; 168 unconstrained) x 320 threads and ~50 KB of shared memory: with RS_TC_CORES=1 a 256-thread
 // GEMM CTA (gemm_tc_kernel<128, 2>) fits on the same SM
+template <bool STAMP>
 __global__ void __maxnreg__(128)
 rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmS_hi,
                   const __grid_constant__ CUtensorMap tmS_lo, KBwd p) {
@@ -795,25 +799,26 @@ int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a_in, cudaStream
   p.kb_bytes = 2u * (uint32_t)g.Bpad * 128;
   p.variant = ts_variant();
   RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
-  static size_t checked_smem = 0;          // attribute + co-residency check once per shared-memory size
-  static int checked_cap = 0;
-  if (checked_smem != g.smem_bytes) {
+  const int si = a.dbg ? 1 : 0;
+  auto kern = a.dbg ? rec_ts_fwd_kernel<true> : rec_ts_fwd_kernel<false>;
+  static size_t checked_smem[2] = {0, 0};  // attribute + co-residency check once per shared-memory size
+  static int checked_cap[2] = {0, 0};
+  if (checked_smem[si] != g.smem_bytes) {
     int per_sm = 0;
-    RS_CHECK_CUDA(cudaFuncSetAttribute(rec_ts_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    RS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rec_ts_fwd_kernel, NTHREADS, g.smem_bytes));
-    checked_cap = per_sm * sm_count();
-    checked_smem = g.smem_bytes;
+    RS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    RS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NTHREADS, g.smem_bytes));
+    checked_cap[si] = per_sm * sm_count();
+    checked_smem[si] = g.smem_bytes;
   }
-  RS_REQUIRE(checked_cap >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_ts_forward: %d CTAs cannot be co-resident", g.nslice);
+  RS_REQUIRE(checked_cap[si] >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_ts_forward: %d CTAs cannot be co-resident", g.nslice);
   // A plain launch: the grid barrier is the kernel's own counter, co-residency was checked above (one CTA per SM,
   // nslice <= SM count), and plain launches of different layers run side by side (RS_TS_COOP=1: cooperative launch).
   static const bool coop = [] { const char* v = getenv("RS_TS_COOP"); return v && v[0] == '1'; }();
   if (coop) {
     void* kargs[] = {(void*)&th, (void*)&ts, (void*)&p};
-    RS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)rec_ts_fwd_kernel, dim3(g.nslice), dim3(NTHREADS), kargs,
-                                              g.smem_bytes, st));
+    RS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(g.nslice), dim3(NTHREADS), kargs, g.smem_bytes, st));
   } else {
-    rec_ts_fwd_kernel<<<dim3(g.nslice), dim3(NTHREADS), g.smem_bytes, st>>>(th, ts, p);
+    kern<<<dim3(g.nslice), dim3(NTHREADS), g.smem_bytes, st>>>(th, ts, p);
     RS_CHECK_CUDA(cudaGetLastError());
   }
   count_launch();
@@ -842,9 +847,11 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
   // tensor-memory columns); sharing measured slower at cfg-2, see lstm_tc.cu
   if ((!share || cols > 256) && smem < 120 * 1024) smem = 120 * 1024;
   RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
-  static size_t attr_smem = 0;
-  if (attr_smem != smem) {
-    RS_CHECK_CUDA(cudaFuncSetAttribute(rec_ts_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int si = a.dbg ? 1 : 0;
+  auto kern = a.dbg ? rec_ts_bwd_kernel<true> : rec_ts_bwd_kernel<false>;
+  static size_t attr_smem[2] = {0, 0};
+  if (attr_smem[si] != smem) {
+    RS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g.nslice);
@@ -856,17 +863,18 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int nclusters = 0;
-  if (attr_smem != smem) {
-    RS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, rec_ts_bwd_kernel, &cfg));
-    attr_smem = smem;
+  static int nclusters_s[2] = {0, 0};
+  if (attr_smem[si] != smem) {
+    RS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nclusters_s[si], kern, &cfg));
+    attr_smem[si] = smem;
   }
+  const int nclusters = nclusters_s[si];
   RS_REQUIRE(nclusters * CL >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_ts_backward: %d CTAs cannot be co-resident (%d clusters)",
              g.nslice, nclusters);
   CUtensorMap ts_hi, ts_lo;
   if ((rc = tmap_store3_bf16(&ts_hi, a.dg_hi, g.H, 4, a.Ttot * g.B, (size_t)g.H * 2, (size_t)4 * g.H * 2, TSU, 4, g.B)) != RS_OK) return rc;
   if ((rc = tmap_store3_bf16(&ts_lo, a.dg_lo, g.H, 4, a.Ttot * g.B, (size_t)g.H * 2, (size_t)4 * g.H * 2, TSU, 4, g.B)) != RS_OK) return rc;
-  RS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rec_ts_bwd_kernel, tg, ts_hi, ts_lo, p));
+  RS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tg, ts_hi, ts_lo, p));
   count_launch();
   return RS_OK;
 }
