@@ -66,3 +66,38 @@ def test_mfcc_oracle_shape_and_dct():
     np.testing.assert_allclose(basis @ basis.T, np.eye(128), atol=1e-12)
     w = features.mel_filterbank_slaney(16000, 400)
     assert w.shape == (128, 201) and (w >= 0).all()
+
+
+def test_mfcc_restatement_against_torchaudio():
+    """librosa is absent, torchaudio is not: its MFCC transform with librosa's settings (centred reflect-padded
+    frames of n_fft = 0.025 sr, periodic Hann, 128 Slaney mel bands with Slaney normalisation, power_to_db with
+    top_db 80, orthonormal DCT-II, 20 coefficients) is an independent implementation of what
+    util/audioprocessor.py:63-75 calls; oracle/features.py::mfcc agrees with it to float32 resolution."""
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    rng = np.random.default_rng(0)
+    for sr, n in ((16000, 16000), (16000, 9000), (22050, 22050)):
+        sig = (0.1 * rng.standard_normal(n)).astype(np.float32)
+        got = features.mfcc(sig, sr, 10000)
+        got = got[0] if isinstance(got, tuple) else got
+        tr = torchaudio.transforms.MFCC(
+            sample_rate=sr, n_mfcc=20, dct_type=2, norm="ortho", log_mels=False,
+            melkwargs=dict(n_fft=int(round(0.025 * sr)), hop_length=int(round(0.01 * sr)), n_mels=128, f_min=0.0,
+                           f_max=sr / 2, center=True, pad_mode="reflect", power=2.0, norm="slaney",
+                           mel_scale="slaney", window_fn=torch.hann_window))
+        want = tr(torch.from_numpy(sig)).numpy().T
+        assert want.shape == got.shape
+        assert np.abs(got - want).max() < 2e-5 * np.abs(want).max() + 1e-3
+
+
+def test_delta_edge_mode_is_the_replicate_padded_fir():
+    """DELTA_EDGE (librosa <= 0.6.0) is the width-9 regression FIR over edge-replicated frames; torchaudio's
+    compute_deltas(mode='replicate') is that filter with the textbook 1/60 normalisation, old librosa divided by
+    sum|w| = 20: the two differ by exactly the factor 3."""
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((40, 57))
+    got = features.delta(x, mode=features.DELTA_EDGE)
+    want = torchaudio.functional.compute_deltas(torch.from_numpy(x), win_length=9, mode="replicate").numpy() * 3.0
+    np.testing.assert_allclose(got, want, atol=1e-12)
