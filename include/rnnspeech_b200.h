@@ -89,6 +89,43 @@ int rs_mfcc_forward(const float* pcm_d, const int64_t* offsets_d, int B, int64_t
                     float* out_d, int32_t* nframes_d, void* ws_d, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * (a0) Audio front door.  Replaces what AudioProcessor.process_audio_file reaches
+ *     through librosa.load(file_name, mono=True) (util/audioprocessor.py:49) AFTER
+ *     the container has been decoded to PCM: int16 -> float32 (x * 2^-15), mean over
+ *     channels, and resampling to 22 050 Hz with resampy's 'kaiser_best' band-limited
+ *     sinc interpolation (64 zero crossings, 512 table samples per crossing, Kaiser
+ *     beta 14.7696..., roll-off 0.94759...), padded to ceil(n * ratio) samples like
+ *     librosa.util.fix_length.  The output feeds rs_fbank_forward / rs_mfcc_forward
+ *     on the device without a host round trip.
+ *
+ *   pcm_d       RS_PCM_F32: float32 mono samples;  RS_PCM_S16: int16, `channels` interleaved
+ *   offsets_d   int64[B+1] FRAME offsets (samples per channel) of the utterances in pcm_d
+ *   out_offsets_d int64[B+1]: out_offsets[b+1] - out_offsets[b] = rs_resample_num_samples(n_b, ...)
+ *   max_out_samples  host copy of the longest output length (grid sizing)
+ * ------------------------------------------------------------------------ */
+#define RS_PCM_F32 0
+#define RS_PCM_S16 1
+
+size_t rs_resample_workspace_bytes(int B, int64_t max_out_samples);
+/* ceil(n * sr_out / sr_in): the length librosa.load returns */
+int64_t rs_resample_num_samples(int64_t n_samples, int sr_in, int sr_out);
+/* host-only: the one-sided interpolation filter [64*512+1] the kernels build (CPU tests) */
+int rs_resample_filter_host(double* win_out, int* num_table);
+int rs_resample_forward(const void* pcm_d, int pcm_format, int channels, const int64_t* offsets_d, int B,
+                        int64_t max_out_samples, int sr_in, int sr_out, float* out_d,
+                        const int64_t* out_offsets_d, void* ws_d, size_t ws_bytes, void* stream);
+/* Host-only FLAC decoder (the container librosa.load opens through audioread / soundfile for the LibriSpeech
+ * files the reference trains on, util/audioprocessor.py:49, util/dataprocessor.py:207-243).  data / nbytes: a whole
+ * .flac file in HOST memory;  out: interleaved int32 samples [frames * channels] in HOST memory, or NULL to read the
+ * stream parameters only;  md5: the 16-byte signature of the unencoded audio from STREAMINFO (zeros if unset).
+ * Every frame's CRC-8 / CRC-16 is checked; a mismatch is RS_ERR_INVALID. */
+int rs_flac_decode_host(const uint8_t* data, size_t nbytes, int32_t* out, int64_t out_capacity,
+                        int* sample_rate, int* channels, int* bits_per_sample, int64_t* total_frames,
+                        uint8_t* md5);
+/* int16 interleaved -> float32 mono without a rate change (files already at the target rate) */
+int rs_pcm16_to_f32(const int16_t* pcm_d, int64_t frames, int channels, float* out_d, void* stream);
+
+/* ------------------------------------------------------------------------
  * (b) Acoustic model: input dense -> L x LSTM (TF BasicLSTMCell semantics,
  *     gate order i,j,f,o, forget_bias 1.0, per-step in/out dropout,
  *     dynamic_rnn sequence-length masking, persistent state in/out) ->

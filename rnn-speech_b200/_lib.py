@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "librnnspeech_b200.so")
 
 RS_OK = 0
 DELTA_INTERP, DELTA_EDGE = 0, 1
+PCM_F32, PCM_S16 = 0, 1
 CTC_BETA_SOURCE, CTC_BETA_DEST = 0, 1
 FBANK_DIM = 120
 
@@ -54,6 +55,14 @@ SIGNATURES = {
     "rs_mfcc_num_frames": (c_int64, [c_int64, c_int]),
     "rs_mfcc_forward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int, c_void_p,
                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rs_resample_workspace_bytes": (c_size_t, [c_int, c_int64]),
+    "rs_resample_num_samples": (c_int64, [c_int64, c_int, c_int]),
+    "rs_resample_filter_host": (c_int, [POINTER(c_double), POINTER(c_int)]),
+    "rs_resample_forward": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rs_flac_decode_host": (c_int, [c_void_p, c_size_t, c_void_p, c_int64, POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                    POINTER(c_int64), c_void_p]),
+    "rs_pcm16_to_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "rs_am_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int]),
     "rs_am_destroy": (None, [c_void_p]),
     "rs_am_param_count": (c_int64, [c_void_p]),

@@ -160,14 +160,28 @@ class AudioProcessor(object):
         return feat[0, :keep].cpu().numpy(), length
 
     def process_audio_file(self, file_name):
-        """util/audioprocessor.py:41-50.  The reference decodes with
-        librosa.load(file, mono=True), i.e. resampled to 22 050 Hz; decode and
-        resampling are a SURVEY section-8(f) 'next' row.  WAV files are read with
-        the standard library and resampled with a polyphase filter (NOT
-        bit-identical to librosa's kaiser_best)."""
-        from .audiofile import load_audio
-        sig, sr = load_audio(file_name)
-        return self.process_signal(sig, sr)
+        """util/audioprocessor.py:41-50: ``sig, sr = librosa.load(file_name, mono=True)`` then process_signal.
+        The container (RIFF/WAVE, FLAC) is parsed on the host; the int16 -> float32 conversion, the mono mix, the
+        resampling to 22 050 Hz (resampy 'kaiser_best' restated, csrc/resample.cu) and the features all run on
+        the device, with the decoded PCM as the only host-to-device copy."""
+        feats, lengths = self.process_audio_files([file_name], time_major=False)
+        length = int(lengths.cpu()[0])
+        keep = min(length, int(self.max_input_seq_length))
+        return feats[0, :keep].cpu().numpy(), length
+
+    def process_audio_files(self, file_names, time_major=True, sr=None):
+        """A batch of files in one go: returns device tensors (features [Tmax,B,F] or [B,Tmax,F], nframes [B]).
+        sr: target rate (default 22 050 like librosa.load; pass the corpus rate, e.g. 16 000, to skip resampling)."""
+        from . import audiofile
+        dev = self._dev()
+        decoded = [audiofile.decode_file(f) for f in file_names]
+        target = audiofile.TARGET_SR if sr is None else int(sr)
+        pcm_d, off_d, lens, out_sr = audiofile.load_batch_device(decoded, dev, sr=target)
+        if self.feature_type == "fbank" and self.delta_mode == "interp":
+            for n in lens:
+                if self.num_frames(n, out_sr) < 9:
+                    raise ValueError("delta(mode='interp') needs at least 9 frames, got %d" % self.num_frames(n, out_sr))
+        return self.features_device(pcm_d, off_d, len(lens), max(lens), out_sr, time_major=time_major)
 
 
 class BatchPrefetcher(object):
@@ -208,8 +222,20 @@ class BatchPrefetcher(object):
             ev.record(self.stream)
         return feats, nframes, ev
 
+    def _work_files(self, file_names, time_major):
+        torch.cuda.set_device(self.device)
+        with torch.cuda.stream(self.stream):
+            feats, nframes = self.audio_processor.process_audio_files(file_names, time_major=time_major)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return feats, nframes, ev
+
     def submit(self, signals, sr, time_major=True):
         return BatchPrefetcher._Ticket(self._pool.submit(self._work, signals, sr, time_major))
+
+    def submit_files(self, file_names, time_major=True):
+        """Decode (host), then convert / resample / featurise (device, side stream) a mini-batch of audio files."""
+        return BatchPrefetcher._Ticket(self._pool.submit(self._work_files, file_names, time_major))
 
     def close(self):
         self._pool.shutdown(wait=True)

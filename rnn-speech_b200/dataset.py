@@ -41,6 +41,11 @@ class AudioBatchDataset(object):
     def _submit(self, prefetcher, start):
         """Load one mini-batch on the host and hand its staging / H2D / feature kernels to the prefetcher."""
         chunk = self.items[start:start + self.batch_size]
+        if all(not isinstance(audio, (tuple, list)) for audio, _ in chunk):
+            # files: decoded on the worker thread, resampled and featurised on the device without a host round trip
+            labs = [labelcodec.get_str_labels(self.char_map, label) if isinstance(label, str) else list(label)
+                    for _, label in chunk]
+            return prefetcher.submit_files([audio for audio, _ in chunk], time_major=True), labs, len(chunk)
         sigs, srs, labs = [], [], []
         for audio, label in chunk:
             sig, sr = self._load(audio)

@@ -1,0 +1,160 @@
+"""CPU: the audio front door's oracle (oracle/resample.py) and host-side pieces.
+
+librosa / resampy are absent and unpinned by the reference (parity unpinned upstream), so the restated
+'kaiser_best' resampler is anchored on (a) signal-processing properties and (b) torchaudio's Kaiser-windowed sinc
+resampler given resampy's constants -- a different formulation of the same filter, hence the loose tolerance."""
+import ctypes
+import io
+import wave
+
+import numpy as np
+import pytest
+
+import flac_writer
+from oracle import resample as R
+
+
+def _tone_mix(n, sr, seed=0):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / float(sr)
+    return (0.3 * np.sin(2 * np.pi * 440 * t) + 0.2 * np.sin(2 * np.pi * 3000 * t) +
+            0.05 * rng.standard_normal(n)).astype(np.float32)
+
+
+def test_output_length_is_librosa_loads():
+    assert R.resampled_length(16000, 16000, 22050) == (22050, 22050)
+    assert R.resampled_length(3001, 16000, 22050) == (4135, 4136)          # resampy writes floor, fix_length pads to ceil
+    y = R.resample_kaiser_best(np.ones(3001, np.float32), 16000, 22050)
+    assert y.shape == (4136,) and y.dtype == np.float32 and y[-1] == 0.0
+
+
+# 48 kHz: resampy walks the table with the TRUNCATED stride int(ratio * 512) = 235 instead of 235.2, which stretches
+# the filter by 0.085 % and leaves a gain error of ~5e-4 -- restated as is
+@pytest.mark.parametrize("sr_in,atol", [(8000, 5e-6), (16000, 5e-6), (44100, 5e-6), (48000, 1e-3)])
+def test_pure_tone_survives_resampling(sr_in, atol):
+    n = sr_in // 2
+    x = np.sin(2 * np.pi * 1000 * np.arange(n) / sr_in).astype(np.float32)
+    y = R.resample_kaiser_best(x, sr_in, 22050)
+    want = np.sin(2 * np.pi * 1000 * np.arange(len(y)) / 22050.0)
+    np.testing.assert_allclose(y[600:-600], want[600:-600], atol=atol)       # away from the edges: the passband gain is 1
+
+
+def test_tone_above_the_new_nyquist_is_removed():
+    x = np.sin(2 * np.pi * 15000 * np.arange(22050) / 44100.0).astype(np.float32)
+    y = R.resample_kaiser_best(x, 44100, 22050)
+    assert np.abs(y[600:-600]).max() < 1e-4
+
+
+@pytest.mark.parametrize("sr_in", [16000, 44100])
+def test_against_torchaudio_kaiser_sinc(sr_in):
+    torch = pytest.importorskip("torch")
+    ta = pytest.importorskip("torchaudio")
+    x = _tone_mix(sr_in, sr_in)
+    y = R.resample_kaiser_best(x, sr_in, 22050)
+    z = ta.functional.resample(torch.from_numpy(x), sr_in, 22050, lowpass_filter_width=R.NUM_ZEROS,
+                               rolloff=R.KAISER_BEST_ROLLOFF, resampling_method="sinc_interp_kaiser",
+                               beta=R.KAISER_BEST_BETA).numpy()
+    m = min(len(y), len(z))
+    np.testing.assert_allclose(y[:m], z[:m], atol=1.5e-3)
+
+
+def test_linearity_and_shift():
+    a, b = _tone_mix(4000, 16000, 1), _tone_mix(4000, 16000, 2)
+    ya, yb = R.resample_kaiser_best(a, 16000, 22050), R.resample_kaiser_best(b, 16000, 22050)
+    yab = R.resample_kaiser_best((a + 2 * b).astype(np.float32), 16000, 22050)
+    np.testing.assert_allclose(yab, ya + 2 * yb, atol=2e-6)
+
+
+def test_pcm16_to_float_mono():
+    pcm = np.array([32767, -32768, 100, 300, -5, 6], dtype=np.int16)
+    np.testing.assert_array_equal(R.pcm16_to_float_mono(pcm, 1), pcm.astype(np.float32) / 32768.0)
+    np.testing.assert_array_equal(R.pcm16_to_float_mono(pcm, 2),
+                                  np.array([-0.5, 200.0, 0.5], np.float32) / np.float32(32768.0))
+
+
+def test_library_filter_table_matches_oracle(pkg):
+    win = (ctypes.c_double * (R.NUM_ZEROS * 2 ** R.PRECISION + 1))()
+    num_table = ctypes.c_int()
+    pkg._lib.call("rs_resample_filter_host", win, ctypes.byref(num_table))
+    want, nt = R.kaiser_best_filter()
+    assert num_table.value == nt == 512
+    np.testing.assert_allclose(np.frombuffer(win, np.float64), want, rtol=0, atol=1e-14)
+    for n, a, b in ((16000, 16000, 22050), (3001, 16000, 22050), (5000, 44100, 22050), (7, 22050, 22050)):
+        assert pkg._lib.raw("rs_resample_num_samples")(n, a, b) == (n if a == b else R.resampled_length(n, a, b)[1])
+    assert pkg._lib.raw("rs_resample_workspace_bytes")(32, 220500) >= 32769 * 16 + 32 * 216 * 8
+
+
+# ------------------------------------------------------------------ containers (host decode)
+def _signal16(n, seed=0):
+    rng = np.random.default_rng(seed)
+    return (8000 * np.sin(np.arange(n) * 0.05) + 500 * rng.standard_normal(n)).astype(np.int16)
+
+
+_KINDS = [{"kind": "verbatim"}, {"kind": "fixed", "order": 0}, {"kind": "fixed", "order": 1, "porder": 2},
+          {"kind": "fixed", "order": 2, "porder": 3, "method": 1},
+          {"kind": "fixed", "order": 3, "escape_first": True, "porder": 1}, {"kind": "fixed", "order": 4, "porder": 2},
+          {"kind": "lpc", "coefs": [900, -420], "shift": 9, "precision": 12, "porder": 2}]
+
+
+def _plan(i, nch):
+    return {"stereo": [None, "ls", "sr", "ms"][i % 4], "sub": [_KINDS[(i + c) % len(_KINDS)] for c in range(nch)]}
+
+
+@pytest.mark.parametrize("channels,blocksize,n", [(1, 1152, 5000), (2, 576, 5000), (2, 1000, 4321), (1, 4096, 100)])
+def test_flac_decoder_round_trip(pkg, channels, blocksize, n):
+    from rnn_speech_b200 import audiofile
+    x = _signal16(n)
+    samples = x if channels == 1 else np.stack([x, (0.5 * x).astype(np.int16) + _signal16(n, 1) // 16], 1)
+    d = audiofile.decode_flac(flac_writer.encode(samples, 16000, blocksize=blocksize, plan=_plan))
+    assert (d.sr, d.channels, d.frames, d.fmt) == (16000, channels, n, "s16")
+    np.testing.assert_array_equal(d.samples, np.asarray(samples).reshape(-1))
+
+
+def test_flac_constant_wasted_bits_id3_and_24_bit(pkg):
+    from rnn_speech_b200 import audiofile
+    c = np.full(1152, -77, np.int16)
+    w = (_signal16(1152) // 8 * 8).astype(np.int16)
+    plan = lambda i, n: {"stereo": None, "sub": [{"kind": "constant"}, {"kind": "fixed", "order": 2, "wasted": 3}]}
+    d = audiofile.decode_flac(flac_writer.encode(np.stack([c, w], 1), 22050, plan=plan, id3=True))
+    np.testing.assert_array_equal(d.samples.reshape(-1, 2), np.stack([c, w], 1))
+    x24 = _signal16(3000).astype(np.int64) * 200
+    d = audiofile.decode_flac(flac_writer.encode(x24, 16000, bps=24))
+    assert d.fmt == "f32" and d.channels == 1
+    np.testing.assert_array_equal(d.samples, (x24 / float(1 << 23)).astype(np.float32))
+
+
+def test_flac_corruption_is_detected(pkg):
+    from rnn_speech_b200 import audiofile
+    data = bytearray(flac_writer.encode(_signal16(3000), 16000))
+    data[len(data) // 2] ^= 0x10
+    with pytest.raises(ValueError, match="CRC|subframe|sync"):
+        audiofile.decode_flac(bytes(data))
+    good = flac_writer.encode(_signal16(3000), 16000)
+    tampered = bytearray(good)
+    tampered[4 + 4 + 18] ^= 0xFF                                             # first byte of STREAMINFO's MD5
+    with pytest.raises(ValueError, match="MD5"):
+        audiofile.decode_flac(bytes(tampered))
+    with pytest.raises(ValueError):
+        audiofile.decode_flac(b"fLaC" + b"\x00" * 60)
+
+
+def test_wav_decoder(pkg, tmp_path):
+    from rnn_speech_b200 import audiofile
+    x = np.stack([_signal16(2000), _signal16(2000, 3)], 1)
+    buf = io.BytesIO()
+    with wave.open(buf, "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(2)
+        w.setframerate(16000)
+        w.writeframes(x.tobytes())
+    d = audiofile.decode_wav(buf.getvalue())
+    assert (d.sr, d.channels, d.frames, d.fmt) == (16000, 2, 2000, "s16")
+    np.testing.assert_array_equal(d.samples, x.reshape(-1))
+    p = tmp_path / "a.wav"
+    p.write_bytes(buf.getvalue())
+    assert audiofile.decode_file(str(p)).frames == 2000
+    (tmp_path / "b.ogg").write_bytes(b"OggS" + b"\x00" * 100)
+    with pytest.raises(NotImplementedError):
+        audiofile.decode_file(str(tmp_path / "b.ogg"))
+    with pytest.raises(ValueError):
+        audiofile.decode_wav(b"RIFF\x00\x00\x00\x00WAVE")
