@@ -16,6 +16,10 @@ Pinning status (see DESIGN.md "Oracle"):
                            (librosa<=0.6.0) is restated from memory: unpinned.
   * features.mfcc       -- librosa is absent: restated from its published
                            algorithm, PARITY UNPINNED.
+  * resample            -- librosa.load's post-decode half (resampy 'kaiser_best'):
+                           third-party, absent, restated; cross-checked against
+                           torchaudio's Kaiser-sinc resampler and signal
+                           properties, PARITY UNPINNED.
   * lstm / ctc / optim  -- TensorFlow 1.x is absent: restated, PARITY UNPINNED
                            upstream; cross-checked here against torch-CPU
                            autograd (LSTM grads) and torch ctc_loss (labels
