@@ -109,6 +109,45 @@ def decode_file(path):
                               "also opens whatever audioread/ffmpeg can)" % (path,))
 
 
+def duration_seconds(path):
+    """Length of an audio file in seconds from its header alone (what the reference asks mutagen for,
+    util/dataprocessor.py:232-241, to order the training set by duration); 0 if the file is not recognised."""
+    try:
+        with open(path, "rb") as fh:
+            head = fh.read(1 << 16)
+        if head[:4] == b"RIFF" and head[8:12] == b"WAVE":
+            pos, block_align, sr = 12, None, None
+            while pos + 8 <= len(head):
+                cid, size = head[pos:pos + 4], struct.unpack("<I", head[pos + 4:pos + 8])[0]
+                if cid == b"fmt " and pos + 24 <= len(head):
+                    _, nch, sr, _, block_align, _ = struct.unpack("<HHIIHH", head[pos + 8:pos + 24])
+                elif cid == b"data":
+                    if not block_align or not sr:
+                        return 0
+                    import os
+                    size = min(size, os.path.getsize(path) - (pos + 8))
+                    return (size // block_align) / float(sr)
+                pos += 8 + size + (size & 1)
+            return 0
+        if head[:4] == b"fLaC" or head[:3] == b"ID3":
+            sr, nch, bps, frames = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+            buf = np.frombuffer(head, dtype=np.uint8)
+            if head[:3] == b"ID3":                      # the tag may be longer than what was read
+                with open(path, "rb") as fh:
+                    buf = np.frombuffer(fh.read(), dtype=np.uint8)
+            try:
+                _lib.call("rs_flac_decode_host", buf.ctypes.data, buf.size, None, 0, ctypes.byref(sr), ctypes.byref(nch),
+                          ctypes.byref(bps), ctypes.byref(frames), None)
+            except ValueError:
+                # total_samples unknown in STREAMINFO (the header-only call then walks frames and runs out of data)
+                d = decode_file(path)
+                return d.frames / float(d.sr)
+            return frames.value / float(sr.value)
+    except (OSError, ValueError, RuntimeError, struct.error):
+        pass
+    return 0
+
+
 def load_batch_device(decoded, device, sr=TARGET_SR):
     """librosa.load's post-decode half for a list of DecodedAudio, on the device.
 

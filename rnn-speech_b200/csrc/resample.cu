@@ -125,8 +125,15 @@ resample_kernel(const T* __restrict__ pcm, const int64_t* __restrict__ offsets, 
   const int64_t n_out = (int64_t)((double)n_orig * plan.sample_ratio);       // int(n * ratio): what resampy writes
   const int64_t t0 = (int64_t)blockIdx.x * kOutPerBlock;
   if (t0 >= n_fix) return;
-  const double start = t0 < n_out ? ckpt[(size_t)b * nblk + blockIdx.x] : 0.0;
-  if (threadIdx.x == 0) {                    // the time register of every output of this block, add for add
+  // ckpt == nullptr (ratio >= 1): t * time_increment stands in for the running sum.  The two can only disagree on
+  // which neighbour of an exact integer position they pick, and with the table stride at exactly 512 both choices
+  // address the same taps (x[n] with the tap at 0 vs x[n-1]'s successor at the end of its interval): the filter is
+  // continuous there, so nothing is lost and the serial replay is skipped.
+  const double start = ckpt == nullptr ? (double)t0 * plan.time_increment
+                                       : (t0 < n_out ? ckpt[(size_t)b * nblk + blockIdx.x] : 0.0);
+  if (ckpt == nullptr) {
+    for (int j = threadIdx.x; j < kOutPerBlock; j += kResampleThreads) times[j] = (double)(t0 + j) * plan.time_increment;
+  } else if (threadIdx.x == 0) {             // the time register of every output of this block, add for add
     double tr = start;
     for (int j = 0; j < kOutPerBlock; ++j) {
       times[j] = tr;
@@ -236,9 +243,12 @@ extern "C" int rs_resample_forward(const void* pcm_d, int pcm_format, int channe
   resample_table_kernel<<<cdiv(kNwin, 256), 256, 0, st>>>(table, plan.sample_ratio < 1.0 ? plan.sample_ratio : 1.0);
   RS_CHECK_LAUNCH();
   const int nblk = resample_blocks(max_out_samples);
-  double* ckpt = (double*)((char*)ws_d + resample_table_bytes());
-  resample_time_kernel<<<B, 32, 0, st>>>(offsets_d, B, plan, nblk, ckpt);
-  RS_CHECK_LAUNCH();
+  double* ckpt = nullptr;
+  if (plan.sample_ratio < 1.0) {            // see resample_time_kernel: only a truncated table stride makes it matter
+    ckpt = (double*)((char*)ws_d + resample_table_bytes());
+    resample_time_kernel<<<B, 32, 0, st>>>(offsets_d, B, plan, nblk, ckpt);
+    RS_CHECK_LAUNCH();
+  }
   const dim3 grid((unsigned)nblk, (unsigned)B);
   if (pcm_format == RS_PCM_S16) {
     RS_CHECK_CUDA(cudaFuncSetAttribute(resample_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

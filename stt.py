@@ -28,8 +28,19 @@ from random import shuffle
 import numpy as np
 
 
-def load_dataset_dirs(dirs):
-    """[audio path, transcript, duration-unknown] items from a comma separated dir list."""
+def clean_label(_str):
+    """util/dataprocessor.py:73-95"""
+    _str = _str.strip().lower()
+    for ch in ".,?!:":
+        _str = _str.replace(ch, "")
+    return _str.replace("-", " ").replace("_", " ").replace("  ", " ")
+
+
+def load_dataset_dirs(dirs, with_durations=False):
+    """[audio path, transcript, duration] items from a comma separated dir list: a `manifest.tsv`
+    (path<TAB>text) or a LibriSpeech tree (`*.trans.txt` beside `.flac` files -- or `.wav` -- as the reference's
+    walker expects, util/dataprocessor.py:263-278).  Durations (header reads, the reference's mutagen pass
+    :232-249) are only filled in when the training set is ordered by size."""
     items = []
     for d in [x.strip() for x in dirs.split(",") if x.strip()]:
         manifest = os.path.join(d, "manifest.tsv")
@@ -41,15 +52,34 @@ def load_dataset_dirs(dirs):
                 path, text = line.split("\t", 1)
                 items.append([path if os.path.isabs(path) else os.path.join(d, path), text, None])
             continue
-        for root, _, files in os.walk(d):
-            for f in files:
+        for root, _, files in sorted(os.walk(d)):
+            for f in sorted(files):
                 if f.endswith(".trans.txt"):
                     for line in open(os.path.join(root, f), encoding="utf-8"):
                         key, _, text = line.strip().partition(" ")
-                        wav = os.path.join(root, key + ".wav")
-                        if os.path.exists(wav):
-                            items.append([wav, text.lower(), None])
+                        for ext in (".flac", ".wav"):
+                            audio = os.path.join(root, key + ext)
+                            if os.path.exists(audio):
+                                items.append([audio, clean_label(text), None])
+                                break
+    if with_durations:
+        from rnn_speech_b200.audiofile import duration_seconds
+        for item in items:
+            item[2] = duration_seconds(item[0])
     return items
+
+
+def split_acoustic_dataset(train_set, test_set, ordered, train_frac):
+    """models/SpeechRecognizer.py:80-95: order by duration or shuffle, then carve the test set out of the training
+    set when no test directory is configured."""
+    if ordered:
+        train_set = sorted(train_set, key=lambda x: x[2] or 0)
+    else:
+        shuffle(train_set)
+    if not test_set and train_frac is not None:
+        num_train = max(1, int(np.floor(train_frac * len(train_set))))
+        train_set, test_set = train_set[:num_train], train_set[num_train:]
+    return train_set, test_set
 
 
 def synthetic_dataset(n_items, seconds, sr, seed=0):
@@ -255,10 +285,10 @@ def main(argv=None):
             split = max(1, int(0.9 * len(items)))
             train_set, test_set = items[:split], items[split:]
         else:
-            train_set = load_dataset_dirs(hyper_params["training_dataset_dirs"])
+            ordered = hyper_params["dataset_size_ordering"] in ['True', 'First_run_only']       # stt.py:34-37
+            train_set = load_dataset_dirs(hyper_params["training_dataset_dirs"], with_durations=ordered)
             test_set = load_dataset_dirs(hyper_params["test_dataset_dirs"]) if hyper_params["test_dataset_dirs"] else []
-            if hyper_params["dataset_size_ordering"] in ['False']:
-                shuffle(train_set)
+            train_set, test_set = split_acoustic_dataset(train_set, test_set, ordered, hyper_params.get("train_frac"))
         train_acoustic_rnn(rs, train_set, test_set, hyper_params, prog_params)
     elif prog_params['file'] is not None:
         process_file(rs, audio_processor, hyper_params, prog_params['file'])

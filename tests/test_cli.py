@@ -41,6 +41,35 @@ def test_manifest_loader(tmp_path):
     assert len(syn) == 3 and len(syn[0][0][0]) == 8000 and isinstance(syn[0][1], str)
 
 
+def test_librispeech_tree_with_flac_durations_and_ordering(pkg, tmp_path):
+    """util/dataprocessor.py:263-278 (walker), :232-249 (durations), models/SpeechRecognizer.py:80-95 (order / split)."""
+    import wave
+    import numpy as np
+    import flac_writer
+    from rnn_speech_b200 import audiofile
+    d = tmp_path / "LibriSpeech" / "train" / "19" / "198"
+    d.mkdir(parents=True)
+    (d / "19-198.trans.txt").write_text("19-198-0000 NORTHANGER ABBEY\n19-198-0001 THIS LITTLE WORK, WAS FINISHED\n"
+                                        "19-198-0002 MISSING FILE\n19-198-0003 A WAV ONE\n")
+    rng = np.random.default_rng(0)
+    (d / "19-198-0000.flac").write_bytes(flac_writer.encode(rng.integers(-900, 900, 24000).astype(np.int16), 16000))
+    (d / "19-198-0001.flac").write_bytes(flac_writer.encode(rng.integers(-900, 900, 8000).astype(np.int16), 16000))
+    with wave.open(str(d / "19-198-0003.wav"), "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(2)
+        w.setframerate(8000)
+        w.writeframes(rng.integers(-900, 900, 2 * 8000).astype("<i2").tobytes())
+    items = stt.load_dataset_dirs(str(tmp_path / "LibriSpeech"), with_durations=True)
+    assert [os.path.basename(i[0]) for i in items] == ["19-198-0000.flac", "19-198-0001.flac", "19-198-0003.wav"]
+    assert [i[1] for i in items] == ["northanger abbey", "this little work was finished", "a wav one"]
+    assert [i[2] for i in items] == [1.5, 0.5, 1.0]
+    assert audiofile.duration_seconds(str(d / "19-198.trans.txt")) == 0          # unrecognised: like the mutagen miss
+    train, test = stt.split_acoustic_dataset(list(items), [], True, 0.67)
+    assert [i[2] for i in train] == [0.5, 1.0] and [i[2] for i in test] == [1.5]
+    train, test = stt.split_acoustic_dataset(list(items), [], False, None)
+    assert sorted(i[2] for i in train) == [0.5, 1.0, 1.5] and test == []
+
+
 def test_repo_config_ini_parses(pkg):
     hp = pkg.HyperParameterHandler.read_config_file(os.path.join(ROOT, "config.ini"))
     assert hp["num_layers"] == 3 and hp["hidden_size"] == 768 and hp["signal_processing"] == "fbank"
