@@ -50,6 +50,8 @@ def _resample_gpu(pkg, dev, sigs, sr_in, sr_out, fmt="f32", channels=1):
     (48000, 22050, [24000, 7001]),             # truncated table stride + time-register rounding (see resample.cu)
     (22050, 16000, [11025, 2500]),
     (16000, 22050, [160000]),                  # 10 s: many blocks per utterance
+    (11025, 22050, [3000, 17]),                # phase period 2 (shared-weights kernel, S = 256)
+    (16000, 22051, [5000]),                    # coprime rates: period > 1024, per-output kernel without the replay
 ])
 def test_resample_matches_oracle(pkg, cuda, sr_in, sr_out, lens):
     rng = np.random.default_rng(len(lens) + sr_in)
