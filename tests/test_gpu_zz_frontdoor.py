@@ -137,3 +137,35 @@ def test_process_audio_file_is_librosa_load_then_process_signal(pkg, cuda, tmp_p
     want, want_len = features.fbank(R.pcm16_to_float_mono(mono, 1), 16000, delta_mode=features.DELTA_INTERP)
     assert int(nframes[0]) == want_len
     np.testing.assert_allclose(feats[:want.shape[0], 0].cpu().numpy(), want.astype(np.float32), rtol=0, atol=1e-4)
+
+
+def test_dataset_over_audio_files_matches_direct_extraction(pkg, cuda, tmp_path):
+    """AcousticModel.build_dataset over file names (models/AcousticModel.py:801-840): each mini-batch is decoded on the
+    prefetch thread and converted / resampled / featurised on its side stream; the result must be what
+    process_audio_files gives for the same files, the last batch padded with zero features / length 0 (:147-152)."""
+    rng = np.random.default_rng(11)
+    names, texts = [], ["it'll do", "coffee", "we've"]
+    for i, n in enumerate((12000, 9000, 15000)):
+        pcm = (4000 * np.sin(np.arange(n) * (0.02 + 0.01 * i)) + 500 * rng.standard_normal(n)).astype(np.int16)
+        path = tmp_path / ("u%d.%s" % (i, "flac" if i % 2 else "wav"))
+        if i % 2:
+            path.write_bytes(flac_writer.encode(pcm, 16000))
+        else:
+            _write_wav(path, pcm, 16000)
+        names.append(str(path))
+    Tmax, B = 160, 2
+    ds = pkg.AcousticModel.build_dataset([[n, t, None] for n, t in zip(names, texts)], B, Tmax, 600, "fbank",
+                                         pkg.ENGLISH_CHAR_MAP, device=cuda)
+    ap = pkg.AudioProcessor(Tmax, "fbank", device=cuda)
+    want, want_len = ap.process_audio_files(names, time_major=True)
+    torch.cuda.synchronize()
+    batches = list(ds)
+    assert len(batches) == 2
+    got = torch.cat([b[0] for b in batches], dim=1)
+    lens = torch.cat([b[1] for b in batches])
+    assert got.shape == (Tmax, 4, 120) and lens.shape == (4,)
+    np.testing.assert_array_equal(lens.cpu().numpy(), list(want_len.cpu().numpy()) + [0])
+    np.testing.assert_allclose(got[:, :3].cpu().numpy(), want.cpu().numpy(), rtol=0, atol=1e-4)
+    assert bool((got[:, 3] == 0).all())
+    assert batches[0][2].shape[0] == 2 and batches[1][2].shape[0] == 1
+    assert list(batches[1][2][0]) == pkg.get_str_labels(pkg.ENGLISH_CHAR_MAP, "we've")
