@@ -117,7 +117,7 @@ int rs_resample_forward(const void* pcm_d, int pcm_format, int channels, const i
 /* Host-only FLAC decoder (the container librosa.load opens through audioread / soundfile for the LibriSpeech
  * files the reference trains on, util/audioprocessor.py:49, util/dataprocessor.py:207-243).  data / nbytes: a whole
  * .flac file in HOST memory;  out: interleaved int32 samples [frames * channels] in HOST memory, or NULL to read the
- * stream parameters only;  md5: the 16-byte signature of the unencoded audio from STREAMINFO (zeros if unset).
+ * stream parameters only (out_capacity < 0 with out == NULL: walk every frame and count instead of trusting STREAMINFO);  md5: the 16-byte signature of the unencoded audio from STREAMINFO (zeros if unset).
  * Every frame's CRC-8 / CRC-16 is checked; a mismatch is RS_ERR_INVALID. */
 int rs_flac_decode_host(const uint8_t* data, size_t nbytes, int32_t* out, int64_t out_capacity,
                         int* sample_rate, int* channels, int* bits_per_sample, int64_t* total_frames,

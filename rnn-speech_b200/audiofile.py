@@ -86,6 +86,9 @@ def decode_flac(data, verify_md5=True):
     md5 = (ctypes.c_uint8 * 16)()
     args = (ctypes.byref(sr), ctypes.byref(nch), ctypes.byref(bps), ctypes.byref(frames), md5)
     _lib.call("rs_flac_decode_host", buf.ctypes.data, buf.size, None, 0, *args)
+    if frames.value * nch.value > 64 * buf.size:
+        # more than 64 samples per stored byte: silence, or a damaged header -- count the frames before allocating
+        _lib.call("rs_flac_decode_host", buf.ctypes.data, buf.size, None, -1, *args)
     out = np.empty(frames.value * nch.value, dtype=np.int32)
     _lib.call("rs_flac_decode_host", buf.ctypes.data, buf.size, out.ctypes.data, out.size, *args)
     out = out[:frames.value * nch.value]

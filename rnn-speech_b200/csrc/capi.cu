@@ -42,19 +42,24 @@ extern "C" int rs_sm_count(void) {
 
 // CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the checksum of TensorFlow's tensor-bundle
 // files (table blocks and tensor payloads), used by rnn-speech_b200/tf_checkpoint.py::write_bundle.  Slicing-by-8.
-extern "C" uint32_t rs_crc32c(const void* data, size_t n, uint32_t crc) {
-  static uint32_t table[8][256];
-  static bool ready = false;
-  if (!ready) {
+namespace {
+struct Crc32cTable {
+  uint32_t v[8][256];
+  Crc32cTable() {
     for (uint32_t i = 0; i < 256; ++i) {
       uint32_t c = i;
       for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
-      table[0][i] = c;
+      v[0][i] = c;
     }
     for (uint32_t i = 0; i < 256; ++i)
-      for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xff];
-    ready = true;
+      for (int t = 1; t < 8; ++t) v[t][i] = (v[t - 1][i] >> 8) ^ v[0][v[t - 1][i] & 0xff];
   }
+};
+}  // namespace
+
+extern "C" uint32_t rs_crc32c(const void* data, size_t n, uint32_t crc) {
+  static const Crc32cTable tab;                     // initialised once, thread-safe (C++11 static local)
+  const uint32_t (*table)[256] = tab.v;
   const unsigned char* p = (const unsigned char*)data;
   uint32_t c = ~crc;
   while (n >= 8) {

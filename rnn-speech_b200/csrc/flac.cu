@@ -68,19 +68,21 @@ uint8_t crc8(const uint8_t* d, size_t n) {          // polynomial x^8 + x^2 + x 
   return c;
 }
 
-uint16_t crc16(const uint8_t* d, size_t n) {        // polynomial x^16 + x^15 + x^2 + 1
-  static uint16_t table[256];
-  static bool ready = false;
-  if (!ready) {
+struct Crc16Table {                                 // polynomial x^16 + x^15 + x^2 + 1
+  uint16_t v[256];
+  Crc16Table() {
     for (int i = 0; i < 256; ++i) {
       uint16_t c = (uint16_t)(i << 8);
       for (int k = 0; k < 8; ++k) c = (c & 0x8000) ? (uint16_t)((c << 1) ^ 0x8005) : (uint16_t)(c << 1);
-      table[i] = c;
+      v[i] = c;
     }
-    ready = true;
   }
+};
+
+uint16_t crc16(const uint8_t* d, size_t n) {
+  static const Crc16Table table;                    // initialised once, thread-safe (C++11 static local)
   uint16_t c = 0;
-  for (size_t i = 0; i < n; ++i) c = (uint16_t)((c << 8) ^ table[((c >> 8) ^ d[i]) & 0xff]);
+  for (size_t i = 0; i < n; ++i) c = (uint16_t)((c << 8) ^ table.v[((c >> 8) ^ d[i]) & 0xff]);
   return c;
 }
 
@@ -166,7 +168,7 @@ bool read_subframe(BitReader& br, int64_t* s, int blocksize, int bps) {
 using namespace rs;
 
 // data / nbytes: a whole .flac file in host memory.  out: interleaved int32 samples, capacity out_capacity VALUES
-// (frames * channels), or NULL to parse / count only.  Returns RS_OK and fills sample_rate, channels,
+// (frames * channels), or NULL to parse only (out_capacity >= 0: trust STREAMINFO's count; < 0: walk and count).  Returns RS_OK and fills sample_rate, channels,
 // bits_per_sample, total_frames (decoded count when out != NULL or the header does not state it) and md5[16]
 // (STREAMINFO's signature of the unencoded audio, all zero when the encoder did not write one).
 extern "C" int rs_flac_decode_host(const uint8_t* data, size_t nbytes, int32_t* out, int64_t out_capacity,
@@ -210,7 +212,7 @@ extern "C" int rs_flac_decode_host(const uint8_t* data, size_t nbytes, int32_t* 
   if (sample_rate) *sample_rate = sr;
   if (channels) *channels = nch;
   if (bits_per_sample) *bits_per_sample = bps;
-  if (out == nullptr && total > 0) {
+  if (out == nullptr && total > 0 && out_capacity >= 0) {      // out_capacity < 0: walk the frames and count anyway
     if (total_frames) *total_frames = total;
     return RS_OK;
   }

@@ -185,6 +185,42 @@ def test_flac_corruption_is_detected(pkg):
         audiofile.decode_flac(b"fLaC" + b"\x00" * 60)
 
 
+def test_flac_decoder_survives_damaged_streams(pkg):
+    """Byte flips, truncations and garbage must end in an error (or, rarely, a clean decode), never in a crash or an
+    out-of-bounds write: the decoder is fed files from disk."""
+    from rnn_speech_b200 import audiofile
+    x = np.stack([_signal16(3000), _signal16(3000, 2)], 1)
+    good = flac_writer.encode(x, 16000, blocksize=576, plan=_plan)
+    rng = np.random.default_rng(0)
+    outcomes = {"error": 0, "ok": 0}
+    for trial in range(300):
+        data = bytearray(good)
+        kind = trial % 3
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                data[int(rng.integers(4, len(data)))] ^= int(rng.integers(1, 256))
+        elif kind == 1:
+            data = data[:int(rng.integers(0, len(data)))]
+        else:
+            start = int(rng.integers(42, len(data) - 8))
+            data[start:start + 8] = bytes(rng.integers(0, 256, 8, dtype=np.uint8))
+        try:
+            audiofile.decode_flac(bytes(data))
+            outcomes["ok"] += 1
+        except (ValueError, pkg.RnnSpeechError):
+            outcomes["error"] += 1
+    assert outcomes["error"] > 250
+    huge = bytearray(good)
+    huge[4 + 4 + 13] |= 0x0F                                                  # STREAMINFO: total samples ~ 2^35
+    with pytest.raises(ValueError):
+        audiofile.decode_flac(bytes(huge))
+    silence = flac_writer.encode(np.zeros(40000, np.int16), 16000, blocksize=4096,
+                                 plan=lambda i, n: {"stereo": None, "sub": [{"kind": "constant"}]})
+    assert len(silence) < 40000 // 64
+    d = audiofile.decode_flac(silence)
+    assert d.frames == 40000 and not d.samples.any()
+
+
 def test_wav_decoder(pkg, tmp_path):
     from rnn_speech_b200 import audiofile
     x = np.stack([_signal16(2000), _signal16(2000, 3)], 1)
