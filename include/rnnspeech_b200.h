@@ -98,7 +98,7 @@ int rs_mfcc_forward(const float* pcm_d, const int64_t* offsets_d, int B, int64_t
  *     librosa.util.fix_length.  The output feeds rs_fbank_forward / rs_mfcc_forward
  *     on the device without a host round trip.
  *
- *   pcm_d       RS_PCM_F32: float32 mono samples;  RS_PCM_S16: int16, `channels` interleaved
+ *   pcm_d       RS_PCM_F32: float32 samples, RS_PCM_S16: int16 samples; `channels` (1..8) interleaved
  *   offsets_d   int64[B+1] FRAME offsets (samples per channel) of the utterances in pcm_d
  *   out_offsets_d int64[B+1]: out_offsets[b+1] - out_offsets[b] = rs_resample_num_samples(n_b, ...)
  *   max_out_samples  host copy of the longest output length (grid sizing)
@@ -124,6 +124,8 @@ int rs_flac_decode_host(const uint8_t* data, size_t nbytes, int32_t* out, int64_
                         uint8_t* md5);
 /* int16 interleaved -> float32 mono without a rate change (files already at the target rate) */
 int rs_pcm16_to_f32(const int16_t* pcm_d, int64_t frames, int channels, float* out_d, void* stream);
+/* float32 interleaved -> float32 mono (mean over channels), likewise */
+int rs_pcm_f32_to_mono(const float* pcm_d, int64_t frames, int channels, float* out_d, void* stream);
 
 /* ------------------------------------------------------------------------
  * (b) Acoustic model: input dense -> L x LSTM (TF BasicLSTMCell semantics,

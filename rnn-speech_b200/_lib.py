@@ -63,6 +63,7 @@ SIGNATURES = {
     "rs_flac_decode_host": (c_int, [c_void_p, c_size_t, c_void_p, c_int64, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                     POINTER(c_int64), c_void_p]),
     "rs_pcm16_to_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "rs_pcm_f32_to_mono": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "rs_am_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int]),
     "rs_am_destroy": (None, [c_void_p]),
     "rs_am_param_count": (c_int64, [c_void_p]),

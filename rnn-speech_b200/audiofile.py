@@ -23,18 +23,17 @@ TARGET_SR = 22050      # librosa.load's default sr
 
 
 class DecodedAudio(object):
-    """samples: int16 interleaved [frames * channels] (fmt 's16') or float32 mono [frames] (fmt 'f32')."""
+    """samples: interleaved [frames * channels], int16 (fmt 's16', scaled by 2^-15 on the device) or float32 already
+    scaled to [-1, 1) (fmt 'f32': sample formats other than 16-bit).  The mono mix always happens on the device."""
     __slots__ = ("samples", "fmt", "channels", "sr", "frames")
 
     def __init__(self, samples, fmt, channels, sr, frames):
         self.samples, self.fmt, self.channels, self.sr, self.frames = samples, fmt, channels, sr, frames
 
 
-def _float_mono(x, channels, scale):
-    y = x.astype(np.float32) * np.float32(scale)
-    if channels > 1:
-        y = y.reshape(-1, channels).mean(axis=1, dtype=np.float32)
-    return np.ascontiguousarray(y, dtype=np.float32)
+def _to_float(x, scale):
+    """Sample-format conversion of the decode step (what audioread / soundfile hand librosa): integer -> float32."""
+    return np.ascontiguousarray(x.astype(np.float32) * np.float32(scale), dtype=np.float32)
 
 
 def decode_wav(data):
@@ -65,16 +64,16 @@ def decode_wav(data):
         return DecodedAudio(np.frombuffer(body, dtype="<i2"), "s16", nch, sr, frames)
     if tag == 1 and bits == 8:
         x = np.frombuffer(body, dtype=np.uint8).astype(np.int16) - 128
-        return DecodedAudio(_float_mono(x, nch, 1.0 / 128.0), "f32", 1, sr, frames)
+        return DecodedAudio(_to_float(x, 1.0 / 128.0), "f32", nch, sr, frames)
     if tag == 1 and bits == 24:
         b = np.frombuffer(body, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
         x = (b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16))
         x = np.where(x >= 1 << 23, x - (1 << 24), x)
-        return DecodedAudio(_float_mono(x, nch, 1.0 / (1 << 23)), "f32", 1, sr, frames)
+        return DecodedAudio(_to_float(x, 1.0 / (1 << 23)), "f32", nch, sr, frames)
     if tag == 1 and bits == 32:
-        return DecodedAudio(_float_mono(np.frombuffer(body, dtype="<i4"), nch, 1.0 / (1 << 31)), "f32", 1, sr, frames)
+        return DecodedAudio(_to_float(np.frombuffer(body, dtype="<i4"), 1.0 / (1 << 31)), "f32", nch, sr, frames)
     if tag == 3 and bits == 32:
-        return DecodedAudio(_float_mono(np.frombuffer(body, dtype="<f4"), nch, 1.0), "f32", 1, sr, frames)
+        return DecodedAudio(np.ascontiguousarray(np.frombuffer(body, dtype="<f4")), "f32", nch, sr, frames)
     raise ValueError("unsupported WAVE encoding (format tag %d, %d bits)" % (tag, bits))
 
 
@@ -98,7 +97,7 @@ def decode_flac(data, verify_md5=True):
         if verify_md5 and any(want) and hashlib.md5(pcm.tobytes()).digest() != want:
             raise ValueError("FLAC stream decodes, but its audio MD5 does not match STREAMINFO")
         return DecodedAudio(pcm, "s16", nch.value, sr.value, frames.value)
-    return DecodedAudio(_float_mono(out, nch.value, 1.0 / (1 << (bps.value - 1))), "f32", 1, sr.value, frames.value)
+    return DecodedAudio(_to_float(out, 1.0 / (1 << (bps.value - 1))), "f32", nch.value, sr.value, frames.value)
 
 
 def decode_file(path):
@@ -183,11 +182,8 @@ def load_batch_device(decoded, device, sr=TARGET_SR):
             first, last = run[0], run[-1]
             if same_rate:
                 dst = pcm_d[int(out_off[first]):int(out_off[last + 1])]
-                if fmt == "s16":
-                    _lib.call("rs_pcm16_to_f32", src_d.data_ptr(), int(sum(decoded[i].frames for i in run)), nch,
-                              dst.data_ptr(), stream)
-                else:
-                    dst.copy_(src_d)
+                _lib.call("rs_pcm16_to_f32" if fmt == "s16" else "rs_pcm_f32_to_mono", src_d.data_ptr(),
+                          int(sum(decoded[i].frames for i in run)), nch, dst.data_ptr(), stream)
                 continue
             in_off = np.zeros(len(run) + 1, dtype=np.int64)
             np.cumsum([decoded[i].frames for i in run], out=in_off[1:])

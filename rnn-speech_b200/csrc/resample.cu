@@ -79,7 +79,14 @@ static ResamplePlan make_plan(int sr_in, int sr_out) {
 
 template <typename T> struct PcmLoad;
 template <> struct PcmLoad<float> {
-  static __device__ __forceinline__ float at(const float* base, int64_t frame, int) { return __ldg(base + frame); }
+  // to_mono on already-scaled samples: float32 sum over the channels, divided by their number
+  static __device__ __forceinline__ float at(const float* base, int64_t frame, int nch) {
+    if (nch == 1) return __ldg(base + frame);
+    const float* p = base + frame * nch;
+    float s = 0.0f;
+    for (int c = 0; c < nch; ++c) s += __ldg(p + c);
+    return s / (float)nch;
+  }
 };
 template <> struct PcmLoad<int16_t> {
   // buf_to_float then to_mono: float32 sum of x_c * 2^-15 over the channels, divided by their number
@@ -142,7 +149,7 @@ resample_kernel(const T* __restrict__ pcm, const int64_t* __restrict__ offsets, 
   }
   // input window of this block: [w0, w0 + window)
   const int64_t w0 = (int64_t)start - plan.wing - 1;
-  const T* base = pcm + in0 * (int64_t)(sizeof(T) == 2 ? nch : 1);
+  const T* base = pcm + in0 * (int64_t)nch;
   for (int i = threadIdx.x; i < plan.window; i += kResampleThreads) {
     const int64_t f = w0 + i;
     xs[i] = (f >= 0 && f < n_orig) ? PcmLoad<T>::at(base, f, nch) : 0.0f;
@@ -205,7 +212,7 @@ resample_periodic_kernel(const T* __restrict__ pcm, const int64_t* __restrict__ 
   const int64_t t0 = (int64_t)blockIdx.x * (kPhaseOutputs * S);
   if (t0 >= n_fix) return;
   const int64_t w0 = (t0 * sr_in) / sr_out - plan.wing - 1;
-  const T* base = pcm + in0 * (int64_t)(sizeof(T) == 2 ? nch : 1);
+  const T* base = pcm + in0 * (int64_t)nch;
   for (int i = threadIdx.x; i < window; i += kResampleThreads) {
     const int64_t f = w0 + i;
     xs[i] = (f >= 0 && f < n_orig) ? PcmLoad<T>::at(base, f, nch) : 0.0f;      // zeros outside the utterance
@@ -252,11 +259,12 @@ resample_periodic_kernel(const T* __restrict__ pcm, const int64_t* __restrict__ 
   }
 }
 
-// interleaved int16 -> float32 mono, no rate change (file already at the target rate)
-__global__ void pcm16_to_f32_kernel(const int16_t* __restrict__ pcm, int64_t frames, int nch, float* __restrict__ out) {
+// interleaved int16 / float32 -> float32 mono, no rate change (file already at the target rate)
+template <typename T>
+__global__ void pcm_to_mono_kernel(const T* __restrict__ pcm, int64_t frames, int nch, float* __restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < frames; f += stride)
-    out[f] = PcmLoad<int16_t>::at(pcm, f, nch);
+    out[f] = PcmLoad<T>::at(pcm, f, nch);
 }
 
 }  // namespace rs
@@ -293,8 +301,7 @@ extern "C" int rs_resample_forward(const void* pcm_d, int pcm_format, int channe
              sr_in, sr_out);
   RS_REQUIRE(pcm_format == RS_PCM_F32 || pcm_format == RS_PCM_S16, RS_ERR_INVALID,
              "rs_resample_forward: unknown pcm_format %d", pcm_format);
-  RS_REQUIRE(channels >= 1 && channels <= 8 && (pcm_format == RS_PCM_S16 || channels == 1), RS_ERR_INVALID,
-             "rs_resample_forward: %d channels (float input must be mono, int16 up to 8)", channels);
+  RS_REQUIRE(channels >= 1 && channels <= 8, RS_ERR_INVALID, "rs_resample_forward: %d channels (1..8)", channels);
   RS_REQUIRE(sr_in != sr_out, RS_ERR_INVALID, "rs_resample_forward: sr_in == sr_out (use rs_pcm16_to_f32 / no call)");
   RS_REQUIRE(max_out_samples < ((int64_t)1 << 40), RS_ERR_INVALID, "rs_resample_forward: max_out_samples %lld",
              (long long)max_out_samples);
@@ -324,7 +331,7 @@ extern "C" int rs_resample_forward(const void* pcm_d, int pcm_format, int channe
           (const int16_t*)pcm_d, offsets_d, channels, table, plan, sr_in, sr_out, S, step_in, window, out_d, out_offsets_d);
     else
       resample_periodic_kernel<float><<<pgrid, kResampleThreads, psmem, st>>>(
-          (const float*)pcm_d, offsets_d, 1, table, plan, sr_in, sr_out, S, step_in, window, out_d, out_offsets_d);
+          (const float*)pcm_d, offsets_d, channels, table, plan, sr_in, sr_out, S, step_in, window, out_d, out_offsets_d);
     RS_CHECK_LAUNCH();
     return RS_OK;
   }
@@ -342,7 +349,7 @@ extern "C" int rs_resample_forward(const void* pcm_d, int pcm_format, int channe
                                                                   plan, nblk, ckpt, out_d, out_offsets_d);
   } else {
     RS_CHECK_CUDA(cudaFuncSetAttribute(resample_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    resample_kernel<float><<<grid, kResampleThreads, smem, st>>>((const float*)pcm_d, offsets_d, 1, table, plan, nblk, ckpt,
+    resample_kernel<float><<<grid, kResampleThreads, smem, st>>>((const float*)pcm_d, offsets_d, channels, table, plan, nblk, ckpt,
                                                                 out_d, out_offsets_d);
   }
   RS_CHECK_LAUNCH();
@@ -356,7 +363,19 @@ extern "C" int rs_pcm16_to_f32(const int16_t* pcm_d, int64_t frames, int channel
   int64_t blocks = (frames + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  pcm16_to_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pcm_d, frames, channels, out_d);
+  pcm_to_mono_kernel<int16_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pcm_d, frames, channels, out_d);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+extern "C" int rs_pcm_f32_to_mono(const float* pcm_d, int64_t frames, int channels, float* out_d, void* stream) {
+  RS_REQUIRE(frames >= 0 && channels >= 1 && channels <= 8, RS_ERR_INVALID, "rs_pcm_f32_to_mono: frames=%lld channels=%d",
+             (long long)frames, channels);
+  if (frames == 0) return RS_OK;
+  int64_t blocks = (frames + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  pcm_to_mono_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pcm_d, frames, channels, out_d);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }

@@ -82,6 +82,21 @@ def test_int16_interleaved_input(pkg, cuda, channels):
     np.testing.assert_array_equal(out.cpu().numpy(), R.pcm16_to_float_mono(pcm[0], channels))
 
 
+def test_float_interleaved_input(pkg, cuda):
+    """Sample formats other than 16-bit reach the device as scaled float32, still interleaved: same mono mix."""
+    rng = np.random.default_rng(9)
+    x = (0.2 * rng.standard_normal(4000 * 2)).astype(np.float32)
+    mono = x.reshape(-1, 2).mean(axis=1, dtype=np.float32)
+    got = _resample_gpu(pkg, cuda, [x], 16000, 22050, fmt="f32", channels=2)[0]
+    np.testing.assert_allclose(got, R.resample_kaiser_best(mono, 16000, 22050), rtol=0, atol=ATOL)
+    got = _resample_gpu(pkg, cuda, [x], 44100, 22050, fmt="f32", channels=2)[0]
+    np.testing.assert_allclose(got, R.resample_kaiser_best(mono, 44100, 22050), rtol=0, atol=ATOL)
+    src = torch.from_numpy(x).to(cuda)
+    out = torch.empty((4000,), dtype=torch.float32, device=cuda)
+    pkg._lib.call("rs_pcm_f32_to_mono", src.data_ptr(), 4000, 2, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    np.testing.assert_array_equal(out.cpu().numpy(), mono)
+
+
 def test_resample_argument_errors(pkg, cuda):
     lib = pkg._lib
     x = torch.zeros(100, device=cuda)
@@ -94,7 +109,7 @@ def test_resample_argument_errors(pkg, cuda):
     with pytest.raises(ValueError):
         lib.call("rs_resample_forward", *args(fmt=7))
     with pytest.raises(ValueError):
-        lib.call("rs_resample_forward", *args(ch=2))                  # float input must be mono
+        lib.call("rs_resample_forward", *args(ch=9))                  # 1..8 channels
     with pytest.raises(pkg.RnnSpeechError):
         lib.call("rs_resample_forward", *args(ws=16))
 

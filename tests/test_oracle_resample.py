@@ -168,6 +168,10 @@ def test_flac_constant_wasted_bits_id3_and_24_bit(pkg):
     d = audiofile.decode_flac(flac_writer.encode(x24, 16000, bps=24))
     assert d.fmt == "f32" and d.channels == 1
     np.testing.assert_array_equal(d.samples, (x24 / float(1 << 23)).astype(np.float32))
+    st24 = np.stack([x24, -x24 // 2], 1)
+    d = audiofile.decode_flac(flac_writer.encode(st24, 16000, bps=24, plan=_plan))
+    assert (d.fmt, d.channels, d.frames) == ("f32", 2, 3000)                 # interleaved: the mono mix is the device's
+    np.testing.assert_array_equal(d.samples, (st24.reshape(-1) / float(1 << 23)).astype(np.float32))
 
 
 def test_flac_corruption_is_detected(pkg):
