@@ -432,7 +432,7 @@ int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int pr
   static const int env_bn = [] { const char* v = getenv("RS_GEMM_BN"); return v ? atoi(v) : 0; }();
   const int force_bn = g_force_bn >= 0 ? g_force_bn : env_bn;
   // 128 x 256 tiles read a quarter fewer operand bytes per flop, but only pay off while there are at least as many
-  // of them as CTAs (measured: tools/gpu_diag.py gemmbench -- the 768 x 3072 weight-gradient GEMMs prefer 128 x 128)
+  // of them as CTAs (measured: tests/gpu_diag.py gemmbench -- the 768 x 3072 weight-gradient GEMMs prefer 128 x 128)
   int ctas = sm_count();
   if (out.max_ctas > 0 && out.max_ctas < ctas && !out.elastic) ctas = out.max_ctas;
   const bool wide = force_bn ? force_bn == 256 : (N > 128 && cdiv(M, BM) * cdiv(N, 256) >= ctas);

@@ -155,7 +155,7 @@ extern "C" int rs_am_enable_timing(rs_am* am, int enable) {
 }
 
 // Debug: device buffers ([T][8] uint64 each) that receive %globaltimer stamps of CTA 0 of the
-// layer-0 tensor-core recurrent kernels (see tools/gpu_diag.py timeline); NULL disables.
+// layer-0 tensor-core recurrent kernels (see tests/gpu_diag.py timeline); NULL disables.
 extern "C" int rs_am_set_debug_timeline(rs_am* am, void* fwd_d, void* bwd_d) {
   RS_REQUIRE(am != nullptr, RS_ERR_INVALID, "rs_am_set_debug_timeline: NULL handle");
   am->dbg_fwd = (unsigned long long*)fwd_d;

@@ -24,7 +24,7 @@
 // 16 lanes of each of the four 32-lane sub-partitions; epilogue warp w reads sub-partition
 // w%4 and only its lanes 0..15 carry rows.
 //
-// Measured on B200 (tools/gpu_diag.py timeline): one tcgen05.mma with a 128-row SS operand
+// Measured on B200 (tests/gpu_diag.py timeline): one tcgen05.mma with a 128-row SS operand
 // costs ~44 cycles (shared-memory operand bandwidth), one mbarrier wait + commit round ~400
 // cycles: hence M = 64 and four K-blocks per barrier.
 #include "lstm_rec_tc.cuh"

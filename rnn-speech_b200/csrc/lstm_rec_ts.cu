@@ -738,7 +738,7 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 // The writer side needs 32.  Completion of a bulk group makes the stored tile visible to the issuing thread only;
 // with a relaxed signal (the round's earlier default, 29) other CTAs' TMA loads occasionally fetched the previous
 // contents of the tile -- invisible to a bitwise comparison of two runs on the same input (stale == fresh), caught
-// by tools/gpu_diag.py stress (alternating inputs): 36 of 38 backward passes differed.  With the release the
+// by tests/gpu_diag.py stress (alternating inputs): 36 of 38 backward passes differed.  With the release the
 // stress run is clean with or without the reader-side fences (tests/test_gpu_model.py::test_stale_tile_stress).
 constexpr int kDefaultVariant = 317;
 static int ts_variant() {

@@ -277,7 +277,7 @@ Sched make_sched(const rs_am* am, int T) {
     // The SMs the recurrent launches leave idle serve the chunk GEMMs on the critical path (a third of the backward
     // GEMM work, in short bursts) and the weight-gradient GEMMs of the side stream.  Measured at cfg-2 (52 spare
     // SMs): 16 + 48 CTAs -- slightly oversubscribed, the bursts of the first fill the gaps of the second -- beats
-    // every exact split (tools/gpu_diag.py trace, RS_TC_DX_CTAS / RS_TC_SIDE_CTAS).
+    // every exact split (tests/gpu_diag.py trace, RS_TC_DX_CTAS / RS_TC_SIDE_CTAS).
     static const int dx_env = [] { const char* v = getenv("RS_TC_DX_CTAS"); return v ? atoi(v) : 0; }();
     static const int side_env = [] { const char* v = getenv("RS_TC_SIDE_CTAS"); return v ? atoi(v) : 0; }();
     const int sp = spare > 24 ? spare : 24;

@@ -1,5 +1,7 @@
 """Diagnostics run on the GPU box: prints error magnitudes of each kernel family
-against the oracle (more detail than the pass/fail of pytest)."""
+against the oracle (more detail than the pass/fail of pytest) plus timing traces.
+Test tooling (lives under tests/ because it uses the oracle as its checker); not
+collected by pytest, run as `python tests/gpu_diag.py <mode>`."""
 import os
 import sys
 

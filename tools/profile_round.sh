@@ -11,6 +11,6 @@ for k in rec_ts_fwd_kernel rec_ts_bwd_kernel; do
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_kernel|ctc_lattice_kernel|fbank_logmel_kernel|clip_adam_kernel' -s 150 -c 30 -f -o gpurun_out/${TAG}_others \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_others.log 2>&1
-RS_DIAG_VARIANTS=317 timeout 300 python tools/gpu_diag.py rec > gpurun_out/${TAG}_timeline.txt 2>&1
-timeout 300 python tools/gpu_diag.py trace > gpurun_out/${TAG}_trace.txt 2>&1
+RS_DIAG_VARIANTS=317 timeout 300 python tests/gpu_diag.py rec > gpurun_out/${TAG}_timeline.txt 2>&1
+timeout 300 python tests/gpu_diag.py trace > gpurun_out/${TAG}_trace.txt 2>&1
 ls -la gpurun_out
