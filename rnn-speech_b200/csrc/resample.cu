@@ -302,6 +302,7 @@ extern "C" int rs_resample_forward(const void* pcm_d, int pcm_format, int channe
   RS_REQUIRE(pcm_format == RS_PCM_F32 || pcm_format == RS_PCM_S16, RS_ERR_INVALID,
              "rs_resample_forward: unknown pcm_format %d", pcm_format);
   RS_REQUIRE(channels >= 1 && channels <= 8, RS_ERR_INVALID, "rs_resample_forward: %d channels (1..8)", channels);
+  RS_REQUIRE(B <= 65535, RS_ERR_UNSUPPORTED, "rs_resample_forward: at most 65535 utterances per call, got %d", B);
   RS_REQUIRE(sr_in != sr_out, RS_ERR_INVALID, "rs_resample_forward: sr_in == sr_out (use rs_pcm16_to_f32 / no call)");
   RS_REQUIRE(max_out_samples < ((int64_t)1 << 40), RS_ERR_INVALID, "rs_resample_forward: max_out_samples %lld",
              (long long)max_out_samples);
