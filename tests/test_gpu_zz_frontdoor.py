@@ -82,21 +82,6 @@ def test_int16_interleaved_input(pkg, cuda, channels):
     np.testing.assert_array_equal(out.cpu().numpy(), R.pcm16_to_float_mono(pcm[0], channels))
 
 
-def test_float_interleaved_input(pkg, cuda):
-    """Sample formats other than 16-bit reach the device as scaled float32, still interleaved: same mono mix."""
-    rng = np.random.default_rng(9)
-    x = (0.2 * rng.standard_normal(4000 * 2)).astype(np.float32)
-    mono = x.reshape(-1, 2).mean(axis=1, dtype=np.float32)
-    got = _resample_gpu(pkg, cuda, [x], 16000, 22050, fmt="f32", channels=2)[0]
-    np.testing.assert_allclose(got, R.resample_kaiser_best(mono, 16000, 22050), rtol=0, atol=ATOL)
-    got = _resample_gpu(pkg, cuda, [x], 44100, 22050, fmt="f32", channels=2)[0]
-    np.testing.assert_allclose(got, R.resample_kaiser_best(mono, 44100, 22050), rtol=0, atol=ATOL)
-    src = torch.from_numpy(x).to(cuda)
-    out = torch.empty((4000,), dtype=torch.float32, device=cuda)
-    pkg._lib.call("rs_pcm_f32_to_mono", src.data_ptr(), 4000, 2, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
-    np.testing.assert_array_equal(out.cpu().numpy(), mono)
-
-
 def test_resample_argument_errors(pkg, cuda):
     lib = pkg._lib
     x = torch.zeros(100, device=cuda)
@@ -184,3 +169,18 @@ def test_dataset_over_audio_files_matches_direct_extraction(pkg, cuda, tmp_path)
     assert bool((got[:, 3] == 0).all())
     assert batches[0][2].shape[0] == 2 and batches[1][2].shape[0] == 1
     assert list(batches[1][2][0]) == pkg.get_str_labels(pkg.ENGLISH_CHAR_MAP, "we've")
+
+
+def test_float_interleaved_input(pkg, cuda):
+    """Sample formats other than 16-bit reach the device as scaled float32, still interleaved: same mono mix."""
+    rng = np.random.default_rng(9)
+    x = (0.2 * rng.standard_normal(4000 * 2)).astype(np.float32)
+    mono = x.reshape(-1, 2).mean(axis=1, dtype=np.float32)
+    got = _resample_gpu(pkg, cuda, [x], 16000, 22050, fmt="f32", channels=2)[0]
+    np.testing.assert_allclose(got, R.resample_kaiser_best(mono, 16000, 22050), rtol=0, atol=ATOL)
+    got = _resample_gpu(pkg, cuda, [x], 44100, 22050, fmt="f32", channels=2)[0]
+    np.testing.assert_allclose(got, R.resample_kaiser_best(mono, 44100, 22050), rtol=0, atol=ATOL)
+    src = torch.from_numpy(x).to(cuda)
+    out = torch.empty((4000,), dtype=torch.float32, device=cuda)
+    pkg._lib.call("rs_pcm_f32_to_mono", src.data_ptr(), 4000, 2, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    np.testing.assert_array_equal(out.cpu().numpy(), mono)
