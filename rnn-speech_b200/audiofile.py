@@ -111,6 +111,25 @@ def decode_file(path):
                               "also opens whatever audioread/ffmpeg can)" % (path,))
 
 
+_POOL = None
+
+
+def decode_files(paths, workers=None):
+    """decode_file over a list, on a small thread pool: reading, the FLAC decoder (a ctypes call), numpy conversions
+    and hashlib all release the GIL, so the files of a mini-batch decode in parallel (one core decodes ~200 ten-second
+    FLAC utterances per second; a B200 trains on ~1600)."""
+    global _POOL
+    paths = list(paths)
+    if len(paths) < 2 or workers == 1:
+        return [decode_file(p) for p in paths]
+    if _POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=workers or max(2, min(16, (os.cpu_count() or 2))),
+                                   thread_name_prefix="rs-decode")
+    return list(_POOL.map(decode_file, paths))
+
+
 def duration_seconds(path):
     """Length of an audio file in seconds from its header alone (what the reference asks mutagen for,
     util/dataprocessor.py:232-241, to order the training set by duration); 0 if the file is not recognised."""

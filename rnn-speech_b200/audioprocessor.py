@@ -174,7 +174,7 @@ class AudioProcessor(object):
         sr: target rate (default 22 050 like librosa.load; pass the corpus rate, e.g. 16 000, to skip resampling)."""
         from . import audiofile
         dev = self._dev()
-        decoded = [audiofile.decode_file(f) for f in file_names]
+        decoded = audiofile.decode_files(file_names)
         target = audiofile.TARGET_SR if sr is None else int(sr)
         pcm_d, off_d, lens, out_sr = audiofile.load_batch_device(decoded, dev, sr=target)
         if self.feature_type == "fbank" and self.delta_mode == "interp":

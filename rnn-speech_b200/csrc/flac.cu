@@ -15,29 +15,37 @@
 namespace rs {
 namespace {
 
+// MSB-first bit reader over a byte buffer: a 64-bit accumulator holds the next `cnt` bits left-aligned.
 struct BitReader {
   const uint8_t* p;
-  size_t n, pos;          // pos in BITS
+  size_t n, next;         // next: index of the first byte not yet in the accumulator
+  uint64_t acc;
+  int cnt;
   bool fail;
-  BitReader(const uint8_t* data, size_t bytes, size_t start_byte) : p(data), n(bytes), pos(start_byte * 8), fail(false) {}
-  inline uint32_t bit() {
-    if ((pos >> 3) >= n) { fail = true; return 0; }
-    const uint32_t b = (p[pos >> 3] >> (7 - (pos & 7))) & 1u;
-    ++pos;
-    return b;
-  }
-  inline uint64_t bits(int k) {             // k <= 57
-    uint64_t v = 0;
-    while (k > 0) {
-      if ((pos >> 3) >= n) { fail = true; return 0; }
-      const int avail = 8 - (int)(pos & 7);
-      const int take = k < avail ? k : avail;
-      const uint32_t byte = p[pos >> 3];
-      v = (v << take) | ((byte >> (avail - take)) & ((1u << take) - 1u));
-      pos += take;
-      k -= take;
+  BitReader(const uint8_t* data, size_t bytes, size_t start_byte)
+      : p(data), n(bytes), next(start_byte < bytes ? start_byte : bytes), acc(0), cnt(0), fail(false) {}
+  inline void refill() {
+    while (cnt <= 56 && next < n) {
+      acc |= (uint64_t)p[next++] << (56 - cnt);
+      cnt += 8;
     }
+  }
+  inline uint64_t take(int k) {             // 1 <= k <= 32
+    if (cnt < k) {
+      refill();
+      if (cnt < k) { fail = true; cnt = 0; acc = 0; return 0; }
+    }
+    const uint64_t v = acc >> (64 - k);
+    acc <<= k;
+    cnt -= k;
     return v;
+  }
+  inline uint32_t bit() { return (uint32_t)take(1); }
+  inline uint64_t bits(int k) {             // k <= 64
+    if (k <= 0) return 0;
+    if (k <= 32) return take(k);
+    const uint64_t hi = take(k - 32);
+    return (hi << 32) | take(32);
   }
   inline int64_t sbits(int k) {
     if (k == 0) return 0;
@@ -47,16 +55,29 @@ struct BitReader {
   }
   inline uint32_t unary() {                 // number of 0 bits before the next 1
     uint32_t q = 0;
-    while (!fail) {
-      // fast path: skip whole zero bytes
-      if ((pos & 7) == 0 && (pos >> 3) < n && p[pos >> 3] == 0) { q += 8; pos += 8; continue; }
-      if (bit()) break;
-      ++q;
+    for (;;) {
+      if (cnt == 0) {
+        refill();
+        if (cnt == 0) { fail = true; return q; }
+      }
+      if (acc == 0) {                       // all `cnt` buffered bits are zero
+        q += (uint32_t)cnt;
+        cnt = 0;
+        continue;
+      }
+      const int z = __builtin_clzll(acc);   // z < cnt: bits below the valid ones are kept zero
+      q += (uint32_t)z;
+      acc = z == 63 ? 0 : acc << (z + 1);   // a shift by 64 is undefined
+      cnt -= z + 1;
+      return q;
     }
-    return q;
   }
-  inline void align() { pos = (pos + 7) & ~(size_t)7; }
-  inline size_t byte_pos() const { return pos >> 3; }
+  inline void align() {
+    const int drop = cnt & 7;
+    acc <<= drop;
+    cnt -= drop;
+  }
+  inline size_t byte_pos() const { return next - (size_t)(cnt >> 3); }   // meaningful when byte-aligned
 };
 
 uint8_t crc8(const uint8_t* d, size_t n) {          // polynomial x^8 + x^2 + x + 1

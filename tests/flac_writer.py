@@ -75,7 +75,7 @@ def _rice_param(res):
     return k
 
 
-def _put_residual(bw, res, blocksize, order, porder, method=0, escape_first=False):
+def _put_residual(bw, res, blocksize, order, porder, method=0, escape_first=False, rice_k=None):
     bw.put(method, 2)
     bw.put(porder, 4)
     pbits = 4 if method == 0 else 5
@@ -91,7 +91,7 @@ def _put_residual(bw, res, blocksize, order, porder, method=0, escape_first=Fals
             for v in chunk:
                 bw.put(v, raw)
             continue
-        k = _rice_param(np.asarray(chunk))
+        k = _rice_param(np.asarray(chunk)) if rice_k is None else rice_k
         bw.put(k, pbits)
         for v in chunk:
             u = (v << 1) if v >= 0 else ((-v) << 1) - 1
@@ -155,7 +155,7 @@ def _put_subframe(bw, x, bps, spec):
     porder = spec.get("porder", 0)
     if n % (1 << porder) or (n >> porder) <= order:
         porder = 0                                   # a short last block cannot be split evenly
-    _put_residual(bw, res, n, order, porder, spec.get("method", 0), spec.get("escape_first", False))
+    _put_residual(bw, res, n, order, porder, spec.get("method", 0), spec.get("escape_first", False), spec.get("rice_k"))
 
 
 def _blocksize_code(n):

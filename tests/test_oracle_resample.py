@@ -174,6 +174,18 @@ def test_flac_constant_wasted_bits_id3_and_24_bit(pkg):
     np.testing.assert_array_equal(d.samples, (st24.reshape(-1) / float(1 << 23)).astype(np.float32))
 
 
+@pytest.mark.parametrize("rice_k", [0, 1, 3])
+def test_flac_long_unary_runs_at_every_alignment(pkg, rice_k):
+    """Rice quotients of 0..260 zero bits with a tiny parameter: runs that start at every bit offset and cross one,
+    two or more 64-bit refills of the decoder's bit reader."""
+    from rnn_speech_b200 import audiofile
+    rng = np.random.default_rng(rice_k)
+    x = np.concatenate([np.arange(-130, 131), rng.integers(-130, 131, size=2043), [63, -32, 64, -33, 31, 32]]).astype(np.int16)
+    plan = lambda i, n: {"stereo": None, "sub": [{"kind": "fixed", "order": 0, "rice_k": rice_k}]}
+    d = audiofile.decode_flac(flac_writer.encode(x, 8000, blocksize=577, plan=plan))
+    np.testing.assert_array_equal(d.samples, x)
+
+
 def test_flac_corruption_is_detected(pkg):
     from rnn_speech_b200 import audiofile
     data = bytearray(flac_writer.encode(_signal16(3000), 16000))
@@ -223,6 +235,24 @@ def test_flac_decoder_survives_damaged_streams(pkg):
     assert len(silence) < 40000 // 64
     d = audiofile.decode_flac(silence)
     assert d.frames == 40000 and not d.samples.any()
+
+
+def test_decode_files_in_parallel_keeps_order(pkg, tmp_path):
+    from rnn_speech_b200 import audiofile
+    paths, want = [], []
+    for i in range(12):
+        x = _signal16(1000 + 37 * i, seed=i)
+        p = tmp_path / ("f%02d.flac" % i)
+        p.write_bytes(flac_writer.encode(x, 16000, blocksize=576))
+        paths.append(str(p))
+        want.append(x)
+    got = audiofile.decode_files(paths)
+    assert [d.frames for d in got] == [len(x) for x in want]
+    for d, x in zip(got, want):
+        np.testing.assert_array_equal(d.samples, x)
+    assert [d.frames for d in audiofile.decode_files(paths[:1])] == [1000]
+    with pytest.raises(FileNotFoundError):
+        audiofile.decode_files(paths + [str(tmp_path / "missing.flac")])
 
 
 def test_wav_decoder(pkg, tmp_path):
