@@ -14,6 +14,7 @@ their published algorithms (oracle/resample.py is the checker) -- parity unpinne
 import ctypes
 import hashlib
 import struct
+import threading
 
 import numpy as np
 
@@ -88,9 +89,14 @@ def decode_flac(data, verify_md5=True):
     if frames.value * nch.value > 64 * buf.size:
         # more than 64 samples per stored byte: silence, or a damaged header -- count the frames before allocating
         _lib.call("rs_flac_decode_host", buf.ctypes.data, buf.size, None, -1, *args)
-    out = np.empty(frames.value * nch.value, dtype=np.int32)
-    _lib.call("rs_flac_decode_host", buf.ctypes.data, buf.size, out.ctypes.data, out.size, *args)
-    out = out[:frames.value * nch.value]
+    # int32 scratch kept per thread: a fresh large array per file costs page faults and an munmap, which serialise the
+    # decoder threads on the address-space lock (measured: 1.1 -> 4.5 ms per file with four threads)
+    need = frames.value * nch.value
+    scratch = getattr(_TLS, "scratch", None)
+    if scratch is None or scratch.size < need:
+        scratch = _TLS.scratch = np.empty(max(need, 1 << 18), dtype=np.int32)
+    _lib.call("rs_flac_decode_host", buf.ctypes.data, buf.size, scratch.ctypes.data, scratch.size, *args)
+    out = scratch[:frames.value * nch.value]
     if bps.value == 16:
         pcm = out.astype("<i2")
         want = bytes(md5)
@@ -112,6 +118,7 @@ def decode_file(path):
 
 
 _POOL = None
+_TLS = threading.local()
 
 
 def decode_files(paths, workers=None):

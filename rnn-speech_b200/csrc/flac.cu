@@ -238,7 +238,10 @@ extern "C" int rs_flac_decode_host(const uint8_t* data, size_t nbytes, int32_t* 
     return RS_OK;
   }
 
-  std::vector<int64_t> buf((size_t)nch * 65536);
+  // per-thread scratch, kept across calls (a fresh 0.5-4 MB vector per file means an mmap / munmap pair per call, which
+  // serialises decoder threads on the process's address-space lock)
+  static thread_local std::vector<int64_t> buf;
+  if (buf.size() < (size_t)nch * 65536) buf.resize((size_t)nch * 65536);
   int64_t done = 0;                                        // frames decoded so far
   while (pos + 2 <= nbytes) {
     if (!(data[pos] == 0xFF && (data[pos + 1] & 0xFE) == 0xF8)) {
