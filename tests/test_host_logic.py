@@ -90,3 +90,55 @@ def test_levenshtein_against_plain_dp(pkg):
 
 def test_mfcc_length_estimate(pkg):
     assert pkg.AudioProcessor.get_mfcc_length_from_duration(10.0) == int(10.0 // 0.01) - 1    # util/audioprocessor.py:29-39
+
+
+def test_dataset_iteration_over_file_names_host_logic(pkg, monkeypatch):
+    """AudioBatchDataset with file-name items (the reference's [audio_file, label, length] rows,
+    models/AcousticModel.py:801-840): the file branch hands whole mini-batches to submit_files, pads the last batch
+    with zero features / length 0 and builds zero-padded dense labels.  The device work is replaced by a stand-in
+    so that the host logic runs on a CPU box."""
+    import torch
+    from rnn_speech_b200 import audioprocessor, dataset
+
+    calls = []
+
+    class FakeTicket(object):
+        def __init__(self, value):
+            self.value = value
+
+        def result(self):
+            return self.value
+
+    class FakePrefetcher(object):
+        def __init__(self, audio_processor):
+            self.ap = audio_processor
+
+        def submit_files(self, file_names, time_major=True):
+            calls.append(list(file_names))
+            n = len(file_names)
+            feats = torch.stack([torch.full((20, 120), float(len(f))) for f in file_names], dim=1)
+            lens = torch.tensor([10 + i for i in range(n)], dtype=torch.int32)
+            assert time_major and feats.shape == (20, n, 120)
+            return FakeTicket((feats, lens))
+
+        def submit(self, *a, **k):
+            raise AssertionError("in-memory branch taken for file items")
+
+        def close(self):
+            calls.append("closed")
+
+    monkeypatch.setattr(audioprocessor, "BatchPrefetcher", FakePrefetcher)
+    items = [["a.flac", "hello", 1.0], ["bb.wav", "it's", 2.0], ["ccc.flac", "we", None]]
+    ds = dataset.AudioBatchDataset(items, 2, 20, 600, "fbank", pkg.ENGLISH_CHAR_MAP)
+    assert len(ds) == 2
+    batches = list(ds)
+    assert calls == [["a.flac", "bb.wav"], ["ccc.flac"], "closed"]
+    (f0, l0, d0), (f1, l1, d1) = batches
+    assert f0.shape == (20, 2, 120) and list(l0) == [10, 11]
+    assert f1.shape == (20, 2, 120) and list(l1) == [10, 0]                  # padded to batch_size, length 0
+    assert float(f1[:, 0].min()) == 8.0 and float(f1[:, 1].abs().max()) == 0.0
+    hello = pkg.get_str_labels(pkg.ENGLISH_CHAR_MAP, "hello")
+    its = pkg.get_str_labels(pkg.ENGLISH_CHAR_MAP, "it's")
+    assert d0.shape == (2, max(len(hello), len(its)))
+    assert list(d0[0, :len(hello)]) == hello and list(d0[1, :len(its)]) == its
+    assert d1.shape[0] == 1 and list(d1[0]) == pkg.get_str_labels(pkg.ENGLISH_CHAR_MAP, "we")
