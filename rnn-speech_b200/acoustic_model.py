@@ -653,6 +653,30 @@ class AcousticModel(object):
         h = [ord(c) for c in second_string.replace(" ", "")]
         return levenshtein(r, h)
 
+    def _iter_features(self, eval_dataset, audio_processor):
+        """(features [T', F], pre-truncation length) per item of eval_dataset, in order -- what the reference gets from
+        process_audio_file one file at a time (models/AcousticModel.py:737-741).  Runs of file names are decoded,
+        resampled and featurised batch_size at a time (one launch sequence and one device-to-host copy per chunk);
+        in-memory (signal, sample_rate) items go through process_signal."""
+        chunk = max(1, int(self.batch_size))
+        i, n_items = 0, len(eval_dataset)
+        while i < n_items:
+            audio = eval_dataset[i][0]
+            if isinstance(audio, (tuple, list)):
+                yield audio_processor.process_signal(audio[0], audio[1])
+                i += 1
+                continue
+            j = i
+            while j < n_items and j - i < chunk and not isinstance(eval_dataset[j][0], (tuple, list)):
+                j += 1
+            feats, lens = audio_processor.process_audio_files([eval_dataset[k][0] for k in range(i, j)],
+                                                              time_major=False)
+            feats, lens = feats.cpu().numpy(), lens.cpu().numpy()
+            for k in range(j - i):
+                length = int(lens[k])
+                yield feats[k, :min(length, int(audio_processor.max_input_seq_length))], length
+            i = j
+
     def evaluate_full(self, sess, eval_dataset, input_seq_length, signal_processing, char_map,
                       run_options=None, run_metadata=None):
         """models/AcousticModel.py:723-777: WER / CER (percent) over a list of
@@ -661,12 +685,8 @@ class AcousticModel(object):
         wer_list, cer_list = [], []
         feats, lens, labs = [], [], []
         file_number = 0
-        for item in eval_dataset:
+        for item, (feat_vec, feat_len) in zip(eval_dataset, self._iter_features(eval_dataset, audio_processor)):
             audio, label = item[0], item[1]
-            if isinstance(audio, (tuple, list)):
-                feat_vec, feat_len = audio_processor.process_signal(audio[0], audio[1])
-            else:
-                feat_vec, feat_len = audio_processor.process_audio_file(audio)
             file_number += 1
             if len(label) > self.max_target_seq_length or feat_len > self.max_input_seq_length:
                 logging.warning("Warning - sample too long : %s (input : %d / text : %s)", audio, feat_len, len(label))

@@ -142,3 +142,56 @@ def test_dataset_iteration_over_file_names_host_logic(pkg, monkeypatch):
     assert d0.shape == (2, max(len(hello), len(its)))
     assert list(d0[0, :len(hello)]) == hello and list(d0[1, :len(its)]) == its
     assert d1.shape[0] == 1 and list(d1[0]) == pkg.get_str_labels(pkg.ENGLISH_CHAR_MAP, "we")
+
+
+def test_evaluate_full_host_logic_with_file_batches(pkg, monkeypatch):
+    """evaluate_full (models/AcousticModel.py:723-777): files are featurised batch_size at a time, too-long samples
+    are skipped, the last batch is padded with empty items, WER / CER are averaged in percent.  Device work is
+    replaced by stand-ins so the control flow runs on a CPU box."""
+    import types
+    import torch
+    from rnn_speech_b200 import acoustic_model
+
+    extract_calls, forward_calls = [], []
+    truth = {"a.flac": "hello world", "b.wav": "it's", "long.flac": "we", "c.flac": "coffee"}
+    frames = {"a.flac": 12, "b.wav": 7, "long.flac": 99, "c.flac": 9}
+
+    class FakeAP(object):
+        def __init__(self, max_input_seq_length, feature_type="mfcc", device=None):
+            self.max_input_seq_length, self.feature_size = max_input_seq_length, 120
+
+        def process_audio_files(self, names, time_major=True):
+            extract_calls.append(list(names))
+            assert not time_major
+            feats = torch.zeros((len(names), self.max_input_seq_length, 120))
+            for i, n in enumerate(names):
+                feats[i, :min(frames[n], self.max_input_seq_length)] = float(frames[n])
+            return feats, torch.tensor([frames[n] for n in names], dtype=torch.int32)
+
+        def process_signal(self, sig, sr):
+            return np.full((5, 120), 5.0, np.float32), 5
+
+    def process_input(sess, batch, lens):
+        forward_calls.append((batch.shape, list(lens), [float(batch[0, b, 0]) for b in range(batch.shape[1])]))
+        # item 0 of every batch is recognised perfectly, the others come out empty
+        first = [k for k, v in frames.items() if v == lens[0]] or ["sig"]
+        text = truth.get(first[0], "ab")
+        ids = pkg.get_str_labels(pkg.ENGLISH_CHAR_MAP, text)[:-1]
+        out = np.full((batch.shape[1], max(len(ids), 1)), 80, dtype=np.int32)
+        out[0, :len(ids)] = ids
+        return out
+
+    monkeypatch.setattr(acoustic_model, "AudioProcessor", FakeAP)
+    am = acoustic_model.AcousticModel
+    fake = types.SimpleNamespace(batch_size=2, max_input_seq_length=20, max_target_seq_length=600, device=None,
+                                 process_input=process_input, calculate_wer=am.calculate_wer,
+                                 calculate_cer=am.calculate_cer)
+    fake._iter_features = types.MethodType(am._iter_features, fake)
+    data = [["a.flac", truth["a.flac"], None], ["b.wav", truth["b.wav"], None], ["long.flac", truth["long.flac"], None],
+            [(np.zeros(10, np.float32), 16000), "ab", None], ["c.flac", truth["c.flac"], None]]
+    wer, cer = am.evaluate_full(fake, None, data, 20, "fbank", pkg.ENGLISH_CHAR_MAP)
+    assert extract_calls == [["a.flac", "b.wav"], ["long.flac"], ["c.flac"]]           # runs of files, batch_size at a time
+    assert [c[1] for c in forward_calls] == [[12, 7], [5, 9]]                          # long.flac skipped (99 > 20 frames)
+    assert forward_calls[0][0] == (20, 2, 120) and forward_calls[1][2] == [5.0, 9.0]
+    # batch 1: "hello world" right, "it's" -> "" ; batch 2: "ab" right, "coffee" -> ""
+    assert wer == pytest.approx(50.0) and cer == pytest.approx(50.0)
