@@ -21,7 +21,8 @@ import numpy as np
 TARGET_SR = 22050                       # librosa.load default sr
 
 # resampy's shipped 'kaiser_best' filter = sinc_window(num_zeros=64, precision=9,
-# window=kaiser(beta), rolloff) with these two optimised constants
+# window=kaiser(beta), rolloff) with these two optimised constants (beta is also
+# torchaudio's default for its Kaiser resampler, functional.py: 14.769656459379492)
 KAISER_BEST_BETA = 14.769656459379492
 KAISER_BEST_ROLLOFF = 0.9475937167399596
 NUM_ZEROS = 64
