@@ -248,6 +248,34 @@ int rs_clip_adam_step(float* params_d, const float* grads_d, float* m_d, float* 
                       float eps, int64_t step, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Step-protocol helpers, so that a training step launches no framework kernels.
+ *   rs_accumulate_mean: dst_d[0] += (1/n) sum_i v_d[i] / (div_d ? div_d[i] : 1); count_d[0] += 1 when given.
+ *       Replaces acc_mean_loss_op / acc_error_rate_op / increase_mini_batch_op
+ *       (models/AcousticModel.py:361-383: mean_loss = mean(ctc_loss / seq_len), accumulated over mini-batches).
+ *   rs_memset_zero: replaces the accumulator / gradient-accumulator zeroing ops of start_batch (:662-670).
+ *   rs_memcpy_h2d_async: ONE asynchronous copy of a staged (pinned) mini-batch to the device
+ *       (the feed of models/AcousticModel.py:147-152 / the tf.data prefetch of :819-827).
+ * ------------------------------------------------------------------------ */
+int rs_accumulate_mean(const float* v_d, const int32_t* div_d, int n, float* dst_d, float* count_d, void* stream);
+int rs_memset_zero(void* dst_d, size_t bytes, void* stream);
+int rs_memcpy_h2d_async(void* dst_d, const void* src_host, size_t bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Data parallelism (not in the reference: SURVEY 8e).  One process per GPU; ONE all-reduce(SUM, fp32) of the flat
+ * gradient buffer per optimizer step -- summing over ranks is the reference's gradient accumulation over
+ * mini_batch_size mini-batches (models/AcousticModel.py:386-401).  NCCL is bound at run time (dlopen of
+ * libnccl.so.2, RS_NCCL_LIB overrides); the library links only cudart.
+ *   rs_comm_unique_id: rank 0 creates the 128-byte id and hands it to the other ranks out of band
+ *   rs_comm_init:      collective over all ranks, on the current device
+ *   rs_allreduce_sum:  in place, enqueued on `stream`
+ * ------------------------------------------------------------------------ */
+#define RS_COMM_ID_BYTES 128
+int rs_comm_unique_id(void* id_out, size_t id_bytes);
+int rs_comm_init(void** comm_out, const void* unique_id, size_t id_bytes, int rank, int world);
+int rs_allreduce_sum(void* comm, float* buf_d, int64_t n, void* stream);
+void rs_comm_destroy(void* comm);
+
+/* ------------------------------------------------------------------------
  * Self-test of the tcgen05 / TMEM / descriptor plumbing (used by the GPU tests):
  * D[128,N] = A[128,K] * B[N,K]^T on one CTA; split != 0 uses the bf16x3 split.
  * ------------------------------------------------------------------------ */

@@ -43,7 +43,10 @@ def dropout_mask(seed, stream_id, T, B, H, keep):
     restate bit for bit (csrc/common.cuh: rs_dropout_keep).  TF's own RNG stream
     cannot be matched; any i.i.d. Bernoulli(keep) mask drawn fresh per time step
     is the same computation (tf.nn.dropout: x * floor(keep + U[0,1)) / keep).
-    stream_id = 2*layer + (0: cell input, 1: cell output)."""
+    stream_id = 2*layer + (0: cell input, 1: cell output).  `keep` is taken at float32 precision, which is what
+    the reference feeds (a float32 placeholder, models/AcousticModel.py:648-652) and what the C ABI receives: the
+    threshold int(keep * 2^24) of 0.8 differs by one between float32 and float64."""
+    keep = float(np.float32(keep))
     if keep >= 1.0:
         return None
     idx = np.arange(T * B * H, dtype=np.uint64)
@@ -104,6 +107,7 @@ def forward(params, x, seq_len, L, H, state=None, keep_in=1.0, keep_out=1.0, see
     x = np.asarray(x, dtype=dtype)
     T, B, F = x.shape
     seq_len = np.asarray(seq_len)
+    keep_in, keep_out = float(np.float32(keep_in)), float(np.float32(keep_out))   # float32 placeholders in the reference
     p = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
     valid = (np.arange(T)[:, None] < seq_len[None, :])                     # [T,B]
     cur = (x.reshape(T * B, F) @ p["input_w"] + p["input_b"]).reshape(T, B, H)

@@ -91,6 +91,13 @@ SIGNATURES = {
                                 c_void_p]),
     "rs_gemm_tc_bench": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_void_p, c_size_t, POINTER(c_float), c_void_p]),
+    "rs_accumulate_mean": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "rs_memset_zero": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "rs_memcpy_h2d_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rs_comm_unique_id": (c_int, [c_void_p, c_size_t]),
+    "rs_comm_init": (c_int, [POINTER(c_void_p), c_void_p, c_size_t, c_int, c_int]),
+    "rs_allreduce_sum": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "rs_comm_destroy": (None, [c_void_p]),
     "rs_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "rs_clip_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
                                   c_float, c_float, c_float, c_int64, c_void_p]),

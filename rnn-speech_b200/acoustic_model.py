@@ -27,7 +27,7 @@ import torch
 from . import _lib
 from . import labels as labelcodec
 from .audioprocessor import AudioProcessor
-from .dist import allreduce_sum_
+from .dist import allreduce_sum_, world as dist_world
 
 
 def _stream_ptr():
@@ -108,6 +108,13 @@ class AcousticModel(object):
         self.params = self.grads = self.adam_m = self.adam_v = None
         self.rnn_state = None
         self._dropout_calls = 0
+        # TF re-initialises Adam's beta powers and slots on restore (they are not in the reference's save_list,
+        # models/AcousticModel.py:515-527), so the bias-correction step restarts with the slots
+        self._adam_step = 0
+        self._mini_batches = 0           # host copy of the mini-batch counter (models/AcousticModel.py:378-380)
+        self._err_stream = None          # side stream of the prediction + edit-distance ops
+        self._err_event = None
+        self._dataset_empty = False
 
     # ------------------------------------------------------------ construction
     def _create_common(self):
@@ -184,8 +191,9 @@ class AcousticModel(object):
         self.adam_m = torch.zeros_like(self.params)
         self.adam_v = torch.zeros_like(self.params)
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
-        # accumulators (models/AcousticModel.py:364-383): [mean_loss, error_rate, mini_batch]
-        self._acc = torch.zeros(3, dtype=torch.float32, device=self.device)
+        # accumulators (models/AcousticModel.py:364-383): [mean_loss, error_rate, mini_batch, ranks out of data]
+        self._acc = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._one = torch.ones(1, dtype=torch.float32, device=self.device)
         self.training_created = True
 
     def __del__(self):
@@ -269,17 +277,26 @@ class AcousticModel(object):
         arrays = {k: v.detach().cpu().numpy() for k, v in self.param_views().items()}
         arrays["global_step"] = np.array(self.global_step, np.int32)
         arrays["learning_rate"] = np.array(self.learning_rate_var if self.learning_rate_var is not None else 0.0, np.float32)
+        # every file is written under a temporary name and renamed: a reader (or a crash) never sees half a checkpoint
         if fmt == "tf":
             from .tf_checkpoint import write_bundle
             name = "acousticmodel.ckpt-%d" % self.global_step
             path = os.path.join(checkpoint_dir, name)
-            write_bundle(path, arrays, accel=_lib.raw("rs_crc32c"))
+            tmp = os.path.join(checkpoint_dir, ".tmp-" + name)
+            write_bundle(tmp, arrays, accel=_lib.raw("rs_crc32c"))
+            for suffix in (".data-00000-of-00001", ".index"):
+                os.replace(tmp + suffix, path + suffix)
         else:
             name = "acousticmodel.ckpt-%d.npz" % self.global_step
             path = os.path.join(checkpoint_dir, name)
-            np.savez(path, **arrays)
-        with open(os.path.join(checkpoint_dir, "checkpoint"), "w") as fh:
+            tmp = os.path.join(checkpoint_dir, ".tmp-" + name)
+            with open(tmp, "wb") as fh:
+                np.savez(fh, **arrays)
+            os.replace(tmp, path)
+        state_tmp = os.path.join(checkpoint_dir, ".tmp-checkpoint")
+        with open(state_tmp, "w") as fh:
             fh.write('model_checkpoint_path: "%s"\n' % name)
+        os.replace(state_tmp, os.path.join(checkpoint_dir, "checkpoint"))
         logging.info("Checkpoint saved")
         return path
 
@@ -303,6 +320,10 @@ class AcousticModel(object):
                                      % (k, tuple(data[k].shape), tuple(v.shape)))
                 v.copy_(torch.from_numpy(np.ascontiguousarray(data[k], dtype=np.float32)).to(self.device))
             self.global_step = int(np.asarray(data["global_step"]).reshape(-1)[0])
+            self._adam_step = 0
+            if self.adam_m is not None:
+                self.adam_m.zero_()
+                self.adam_v.zero_()
             if self.learning_rate_var is not None:
                 self.learning_rate_var = float(np.asarray(data["learning_rate"]).reshape(-1)[0])
             logging.info("Restored model parameters from %s [%s] (global_step id %d)", name, source, self.global_step)
@@ -344,7 +365,8 @@ class AcousticModel(object):
         keep_in = self.input_keep_prob if training else 1.0
         keep_out = self.output_keep_prob if training else 1.0
         self._dropout_calls += 1
-        seed = (int(self.seed) * 1000003 + self._dropout_calls) & 0xFFFFFFFFFFFFFFFF
+        # fresh masks per call, and per rank under data parallelism (N ranks = N independent mini-batches)
+        seed = (int(self.seed) * 1000003 + self._dropout_calls + dist_world()[0] * 0x632BE59BD9B4E019) & 0xFFFFFFFFFFFFFFFF
         self._last_fwd = (keep_in, keep_out, seed, T)
         if self._tiles is None:
             _lib.call("rs_am_forward", self._handle, self.params.data_ptr(), x_d.data_ptr(), len_d.data_ptr(), T,
@@ -451,32 +473,69 @@ class AcousticModel(object):
         result stays there (no host round trip inside the step)."""
         ids, lens = self.predict(logits, len_d)
         _, rate = self.edit_distance(ids, lens, label_rows)
-        return rate.mean()
+        return rate
+
+    def _accumulate_error_rate_async(self, logits, len_d, label_rows):
+        """acc_error_rate_op (models/AcousticModel.py:370-376, fetched by every run_step :641): the prediction (beam
+        search) and the edit distance only need the logits, so they run on a low-priority side stream while the
+        caller's stream goes on with the CTC loss and the backward pass; end_batch waits for them."""
+        cur = torch.cuda.current_stream(self.device)
+        if self._err_stream is None:
+            self._err_stream = torch.cuda.Stream(device=self.device, priority=0)
+        side = self._err_stream
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            rate = self._error_rate(logits, len_d, label_rows)
+            _lib.call("rs_accumulate_mean", rate.data_ptr(), None, int(rate.numel()), self._acc.data_ptr() + 4, None,
+                      side.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(side)
+        logits.record_stream(side)
+        len_d.record_stream(side)
+        self._err_event = done
+
+    def _phase_mark(self, name):
+        ev = getattr(self, "_phase_events", None)
+        if ev is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(self.device))
+            ev.append((name, e))
 
     def step_on_batch(self, x_d, len_d, label_rows, compute_gradients=True, compute_error_rate=True):
         """One mini-batch of run_step (models/AcousticModel.py:634-660) on explicit
         device tensors: forward, CTC, (backward + gradient accumulation),
         accumulate mean loss / error rate / mini-batch count, keep the RNN state."""
+        self._phase_mark("forward")
         logits = self.forward(x_d, len_d, training=compute_gradients, keep_state=True)
+        if compute_error_rate:
+            self._accumulate_error_rate_async(logits, len_d, label_rows)
+        self._phase_mark("ctc")
         loss, grad = self.ctc_loss(logits, label_rows, len_d, want_grad=compute_gradients)
+        self._phase_mark("backward")
         if compute_gradients:
             self.backward(x_d, len_d, grad)
-        # display loss: mean(loss[b] / len[b])            (models/AcousticModel.py:361-362)
-        self._acc[0] += (loss / len_d.to(torch.float32)).mean()
-        if compute_error_rate:
-            self._acc[1] += self._error_rate(logits, len_d, label_rows)
-        self._acc[2] += 1.0
+        self._phase_mark("bookkeeping")
+        # display loss: mean(loss[b] / len[b]), and the mini-batch counter        (models/AcousticModel.py:361-383)
+        _lib.call("rs_accumulate_mean", loss.data_ptr(), len_d.data_ptr(), int(loss.numel()), self._acc.data_ptr(),
+                  self._acc.data_ptr() + 8, _stream_ptr())
+        self._mini_batches += 1
         return loss
 
     def apply_gradients(self):
         """train_step_op (models/AcousticModel.py:404-406): all-reduce (data parallel),
         clip the ACCUMULATED gradient by its global norm, Adam, global_step += 1."""
+        self._phase_mark("allreduce")
         allreduce_sum_(self.grads)
+        self._phase_mark("clip_adam")
         self.global_step += 1
+        self._adam_step += 1
         _lib.call("rs_sumsq", self.grads.data_ptr(), self.n_params, self._sumsq.data_ptr(), _stream_ptr())
         _lib.call("rs_clip_adam_step", self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
                   self.adam_v.data_ptr(), self.n_params, self._sumsq.data_ptr(), self.grad_clip,
-                  self.learning_rate_var, 0.9, 0.999, 1e-8, self.global_step, _stream_ptr())
+                  self.learning_rate_var, 0.9, 0.999, 1e-8, self._adam_step, _stream_ptr())
+        self._phase_mark("end")
 
     # ---------------------------------------------------------- measurement
     def enable_timing(self):
@@ -509,10 +568,12 @@ class AcousticModel(object):
     # ------------------------------------------------------- step protocol
     def start_batch(self, session=None, is_training=True, run_options=None, run_metadata=None):
         """models/AcousticModel.py:662-670"""
-        self._acc.zero_()
+        _lib.call("rs_memset_zero", self._acc.data_ptr(), 16, _stream_ptr())
+        self._mini_batches = 0
+        self._dataset_empty = False
         self.set_is_training(session, is_training)
         if is_training:
-            self.grads.zero_()
+            _lib.call("rs_memset_zero", self.grads.data_ptr(), 4 * self.n_params, _stream_ptr())
 
     def _next_batch(self):
         it = self._train_iter if self.is_training else self._valid_iter
@@ -525,25 +586,37 @@ class AcousticModel(object):
 
     def run_step(self, session=None, compute_gradients=True, run_options=None, run_metadata=None,
                  compute_error_rate=True):
-        """models/AcousticModel.py:634-660: one mini-batch pulled from the attached dataset."""
+        """models/AcousticModel.py:634-660: one mini-batch pulled from the attached dataset.  Returns the number of
+        mini-batches accumulated so far (kept on the host: no device read inside the step)."""
         start_time = time.time()
         x_d, len_d, dense_labels = self._next_batch()
         rows = self.sparse_labels_from_dense(dense_labels, fill_empty=True)
         self.step_on_batch(x_d, len_d, rows, compute_gradients, compute_error_rate)
-        mini_batch_num = float(self._acc[2].item())
         logging.debug("Step duration : %.2f", time.time() - start_time)
-        return mini_batch_num
+        return float(self._mini_batches)
 
     def end_batch(self, session=None, is_training=True, run_options=None, run_metadata=None,
                   rnn_state_reset_ratio=1.0):
-        """models/AcousticModel.py:672-703"""
-        if is_training:
+        """models/AcousticModel.py:672-703.  Data parallel: the four accumulators (mean loss, error rate, mini-batch
+        count, ranks whose dataset ran dry) are summed over the ranks FIRST, so that every rank takes the same
+        decision -- apply the (all-reduced) gradient iff any rank accumulated a mini-batch -- and the collectives
+        of all ranks stay in lockstep whatever the shard sizes."""
+        cur = torch.cuda.current_stream(self.device)
+        if self._err_event is not None:
+            cur.wait_event(self._err_event)
+            self._err_event = None
+        if self._dataset_empty:
+            _lib.call("rs_accumulate_mean", self._one.data_ptr(), None, 1, self._acc.data_ptr() + 12, None, _stream_ptr())
+        acc = allreduce_sum_(self._acc).cpu().numpy()
+        batchs_count = float(acc[2])
+        self._ranks_empty = int(round(float(acc[3])))
+        if is_training and batchs_count > 0:
             self.apply_gradients()
             # Reset the hidden state at the given random ratio (default to always)   (:681-682)
             if randint(1, int(1 // rnn_state_reset_ratio)) == 1:
-                self.rnn_state.zero_()
-        acc = allreduce_sum_(self._acc.clone()).cpu().numpy()
-        batchs_count = acc[2]
+                _lib.call("rs_memset_zero", self.rnn_state.data_ptr(), 4 * self.rnn_state.numel(), _stream_ptr())
+        if batchs_count <= 0:
+            return 0.0, 0.0, self.global_step
         mean_loss = acc[0] / batchs_count
         mean_error_rate = acc[1] / batchs_count
         return mean_loss, mean_error_rate, self.global_step
@@ -562,9 +635,13 @@ class AcousticModel(object):
         except OutOfRangeError:
             logging.debug("Dataset empty, exiting train step")
             dataset_empty = True
-        if mini_batch_num > 0:
+        self._dataset_empty = dataset_empty
+        if mini_batch_num > 0 or dist_world()[1] > 1:
+            # (data parallel: a rank without a mini-batch still joins the collectives, with a zero gradient, and
+            #  every rank ends its epoch as soon as any rank's shard ran dry)
             mean_loss, mean_error_rate, current_step = self.end_batch(sess, True,
                                                                       rnn_state_reset_ratio=rnn_state_reset_ratio)
+            dataset_empty = dataset_empty or self._ranks_empty > 0
             logging.info("Batch %d : loss %.5f - error_rate %.5f - duration %.2f",
                          current_step, mean_loss, mean_error_rate, time.time() - start_time)
             return mean_loss, mean_error_rate, current_step, dataset_empty
@@ -583,7 +660,8 @@ class AcousticModel(object):
         except OutOfRangeError:
             logging.debug("Dataset empty, exiting evaluation step")
         mean_loss, mean_error_rate, current_step = self.end_batch(sess, False, rnn_state_reset_ratio=1.0)
-        self.rnn_state.zero_()     # always reset the RNN state after evaluation (:793-795)
+        # always reset the RNN state after evaluation (:793-795)
+        _lib.call("rs_memset_zero", self.rnn_state.data_ptr(), 4 * self.rnn_state.numel(), _stream_ptr())
         logging.info("Evaluation at step %d : loss %.5f - error_rate %.5f - duration %.2f",
                      current_step, mean_loss, mean_error_rate, time.time() - start_time)
         return mean_loss, mean_error_rate, current_step
@@ -603,6 +681,47 @@ class AcousticModel(object):
         for b, n in enumerate(out_len):
             pred[b, :n] = ids[b, :n]
         return pred
+
+    # ------------------------------------------------------------ inference
+    def infer_pcm_device(self, audio_processor, pcm_d, offsets_d, batch, max_samples, sr, decoder="greedy"):
+        """The stt.py --file / --evaluate path for a whole batch with the PCM already on the device
+        (stt.py:239-264, models/AcousticModel.py:705-777): feature kernels -> forward -> decode, batch tile by batch
+        tile (no gather / scatter copies between the stages: every tile's features, logits and decoded rows are
+        produced where the next stage reads them).  The RNN state is not carried (process_input semantics).
+        Returns (ids int32 [B, T] padded with -1, lengths int32 [B]) on the device."""
+        assert batch == self.batch_size
+        Tmax = int(self.max_input_seq_length)
+        T = min(Tmax, audio_processor.num_frames(int(max_samples), sr))
+        ids = torch.empty((batch, T), dtype=torch.int32, device=self.device)
+        out_len = torch.empty((batch,), dtype=torch.int32, device=self.device)
+        tiles = self._tiles if self._tiles is not None else [{"b0": 0, "b1": batch, "handle": self._handle}]
+        clamp = audio_processor.num_frames(int(max_samples), sr) > Tmax
+        for t in tiles:
+            b0, b1 = t["b0"], t["b1"]
+            bt = b1 - b0
+            feats, nframes = audio_processor.features_device(pcm_d, offsets_d[b0:b1 + 1], bt, max_samples, sr, time_major=True)
+            lens = torch.clamp(nframes, max=Tmax) if clamp else nframes
+            logits = torch.empty((T, bt, self.num_labels), dtype=torch.float32, device=self.device)
+            _lib.call("rs_am_forward", t["handle"], self.params.data_ptr(), feats.data_ptr(), lens.data_ptr(), T,
+                      None, None, 1.0, 1.0, 0, logits.data_ptr(), None, self._ws.data_ptr(), self._ws.numel(), _stream_ptr())
+            if decoder == "greedy":
+                _lib.call("rs_ctc_greedy_decode", logits.data_ptr(), lens.data_ptr(), T, bt, self.num_labels,
+                          self.num_labels - 1, ids[b0:b1].data_ptr(), out_len[b0:b1].data_ptr(), _stream_ptr())
+            else:
+                need = int(_lib.raw("rs_ctc_beam_workspace_bytes")(T, bt))
+                if getattr(self, "_beam_ws", None) is None or self._beam_ws.numel() < need:
+                    self._beam_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+                _lib.call("rs_ctc_beam_search", logits.data_ptr(), lens.data_ptr(), T, bt, self.num_labels, 100, 1, 1,
+                          ids[b0:b1].data_ptr(), out_len[b0:b1].data_ptr(), None, self._beam_ws.data_ptr(),
+                          self._beam_ws.numel(), _stream_ptr())
+        return ids, out_len
+
+    def infer_signals(self, audio_processor, signals, sr, decoder="greedy"):
+        """Host PCM in, decoded label ids on the host out (numpy int32 [B, T] padded with -1, lengths [B]): one pinned
+        staging buffer and ONE host-to-device copy for the whole batch, then infer_pcm_device."""
+        pcm_d, off_d, lens = audio_processor.stage_batch(signals, sr)
+        ids, out_len = self.infer_pcm_device(audio_processor, pcm_d, off_d, len(signals), max(lens), sr, decoder=decoder)
+        return ids.cpu().numpy(), out_len.cpu().numpy()
 
     # ------------------------------------------------------------- datasets
     @staticmethod

@@ -28,11 +28,15 @@ def _stream_ptr():
 
 
 class AudioProcessor(object):
-    def __init__(self, max_input_seq_length, feature_type="mfcc", delta_mode="interp", device=None):
+    def __init__(self, max_input_seq_length, feature_type="mfcc", delta_mode="interp", device=None, n_mfcc=20):
         """
         feature_type - string options are: mfcc, fbank
         mfcc is a 20-dim input
         fbank is 120-dim input (mel filterbank with delta and double delta)
+
+        n_mfcc - number of cepstral coefficients kept by the mfcc extractor.  The reference calls
+            librosa.feature.mfcc without n_mfcc (util/audioprocessor.py:65-66), i.e. 20 (feature_size = 20, :21);
+            its README speaks of 40, and BASELINE config 1 is quoted at 40: pass n_mfcc=40 for that.
 
         delta_mode - which librosa.feature.delta the fbank path reproduces:
             "interp" (librosa >= 0.6.1, scipy savgol_filter mode='interp') or
@@ -41,7 +45,9 @@ class AudioProcessor(object):
         self.max_input_seq_length = max_input_seq_length
         self.feature_type = feature_type
         if self.feature_type == "mfcc":
-            self.feature_size = 20
+            if not 1 <= int(n_mfcc) <= 128:
+                raise ValueError("n_mfcc must be in [1, 128] (128 mel bands), got %r" % (n_mfcc,))
+            self.feature_size = int(n_mfcc)
         elif self.feature_type == "fbank":
             self.feature_size = 120
         else:
@@ -104,6 +110,11 @@ class AudioProcessor(object):
     def process_batch(self, signals, sr, time_major=True):
         """signals: list of 1-D float arrays (host).  One H2D copy, one launch
         sequence; returns device tensors (features, nframes)."""
+        pcm_d, off_d, lens = self.stage_batch(signals, sr)
+        return self.features_device(pcm_d, off_d, len(signals), max(lens), sr, time_major=time_major)
+
+    def stage_batch(self, signals, sr):
+        """Host PCM of a mini-batch -> device: returns (pcm_d float32 [sum n], offsets_d int64 [B+1], lengths)."""
         dev = self._dev()
         lens = [int(len(s)) for s in signals]
         if min(lens) < 1:
@@ -117,33 +128,32 @@ class AudioProcessor(object):
         np.cumsum(lens, out=offsets[1:])
         total = int(offsets[-1])
         # Pinned staging, allocated once and reused (page-locking 20 MB per call costs more than the copy); two
-        # buffers alternate so that the copy of the previous call may still be in flight, and each utterance's
-        # H2D copy is issued as soon as it is staged so that staging and DMA overlap.
+        # buffers alternate so that the copy of the previous call may still be in flight.  The whole mini-batch --
+        # PCM of every utterance, then the int64 offsets -- is assembled in ONE pinned buffer and goes to the
+        # device with ONE cudaMemcpyAsync issued by the library (rs_memcpy_h2d_async).
         slot = self._stage_next = (getattr(self, "_stage_next", 0) + 1) % 2
         stage = getattr(self, "_stage", None)
         if stage is None:
             stage = self._stage = [None, None]
             self._stage_ev = [None, None]
         opos = (total + 1) // 2 * 2                          # 8-byte aligned home of the int64 offsets
-        if stage[slot] is None or stage[slot].numel() < opos + len(offsets) * 2:
-            stage[slot] = torch.empty((max(opos + len(offsets) * 2, 1 << 16),), dtype=torch.float32, pin_memory=True)
+        nfloats = opos + len(offsets) * 2
+        if stage[slot] is None or stage[slot].numel() < nfloats:
+            stage[slot] = torch.empty((max(nfloats, 1 << 16),), dtype=torch.float32, pin_memory=True)
             self._stage_ev[slot] = torch.cuda.Event()
         else:
             self._stage_ev[slot].synchronize()              # the copy that last used this buffer has finished
         host = stage[slot]
         hview = host.numpy()
-        pcm_d = torch.empty((total,), dtype=torch.float32, device=dev)
         for s, o in zip(signals, offsets[:-1]):
-            n = len(s)
-            hview[o:o + n] = s if isinstance(s, np.ndarray) and s.dtype == np.float32 else np.asarray(s, dtype=np.float32)
-            pcm_d[o:o + n].copy_(host[o:o + n], non_blocking=True)
-        # the int64 offsets ride in the tail of the same pinned buffer
-        oview = hview[opos:opos + len(offsets) * 2].view(np.int64)
-        oview[:] = offsets
-        off_d = torch.empty((len(offsets),), dtype=torch.int64, device=dev)
-        off_d.copy_(host[opos:opos + len(offsets) * 2].view(torch.int64), non_blocking=True)
+            hview[o:o + len(s)] = s                         # (casts to float32 when the source is not)
+        hview[opos:nfloats].view(np.int64)[:] = offsets
+        batch_d = torch.empty((nfloats,), dtype=torch.float32, device=dev)
+        _lib.call("rs_memcpy_h2d_async", batch_d.data_ptr(), host.data_ptr(), 4 * nfloats, _stream_ptr())
         self._stage_ev[slot].record()
-        return self.features_device(pcm_d, off_d, len(signals), max(lens), sr, time_major=time_major)
+        pcm_d = batch_d[:total]
+        off_d = batch_d[opos:nfloats].view(torch.int64)
+        return pcm_d, off_d, lens
 
     # ---------------------------------------------------------- reference API
     def process_signal(self, sig, sr):

@@ -385,6 +385,25 @@ int tmap_stacked_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols
   return RS_OK;
 }
 
+// The same stacked box over two separate plane arrays [rows][ld] (hi at base_hi, lo plane_stride_bytes later).
+int tmap_stacked2_bf16(void* map64, const __nv_bfloat16* base_hi, size_t plane_stride_bytes, int rows, int cols, int ld,
+                       int box_rows, int box_kb) {
+  EncodeTiledFn fn = encode_fn();
+  RS_REQUIRE(fn != nullptr, RS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  RS_REQUIRE((cols % 64) == 0 && (ld % 8) == 0 && (reinterpret_cast<uintptr_t>(base_hi) & 15) == 0 &&
+             (plane_stride_bytes % 16) == 0 && plane_stride_bytes > 0, RS_ERR_INVALID,
+             "stacked TMA map needs cols %% 64 == 0, ld %% 8 == 0, 16-byte aligned planes");
+  cuuint64_t gdim[4] = {64, (cuuint64_t)rows, 2, (cuuint64_t)(cols / 64)};
+  cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride_bytes, 128};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 2, (cuuint32_t)box_kb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map64), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base_hi),
+                  gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RS_REQUIRE(r == CUDA_SUCCESS, RS_ERR_CUDA, "cuTensorMapEncodeTiled (stacked2) failed with %d (rows=%d cols=%d)", (int)r, rows, cols);
+  return RS_OK;
+}
+
 namespace {
 
 template <int BN, int ST>

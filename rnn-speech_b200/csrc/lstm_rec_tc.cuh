@@ -64,6 +64,8 @@ struct RecTcBwdArgs {
   const float* cs;                 // [T,B,H]
   const float* c0;                 // [B,H]
   const __nv_bfloat16* wh_hi;      // [H][4H]  Wh as stored (row = hidden unit k)
+  const __nv_bfloat16* wh_lo;      // [H][4H]  low plane of the same (TMEM-resident kernel: bf16x3 dh recurrence);
+                                   //          nullptr = one bf16 product (the shared-memory-resident kernel ignores it)
   __nv_bfloat16* dg_hi;            // [T*B][4H]
   __nv_bfloat16* dg_lo;            // [T*B][4H]
   const int* len;
@@ -97,5 +99,8 @@ int tmap_store_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols, 
 int tmap_store3_bf16(void* map64, const __nv_bfloat16* base, int d0, int d1, int d2, size_t s1_bytes, size_t s2_bytes,
                      int b0, int b1, int b2);
 int tmap_stacked_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols, int box_rows, int box_kb);
+// same box, planes in two separate [rows][ld] arrays `plane_stride_bytes` apart (lo after hi)
+int tmap_stacked2_bf16(void* map64, const __nv_bfloat16* base_hi, size_t plane_stride_bytes, int rows, int cols, int ld,
+                       int box_rows, int box_kb);
 
 }  // namespace rs

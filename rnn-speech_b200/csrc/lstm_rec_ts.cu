@@ -19,7 +19,11 @@
 //
 // Backward.  dh_{t-1}^T[k, b] = sum_n Wh[k, n] dgates_t[b, n]: M = 128 hidden units k per
 // CLUSTER of 8 CTAs, K = 4H split 8 ways over the cluster (CTA s holds Wh[128 rows, its H/2
-// columns] in TMEM: 24 MMAs of M128 N=Bpad at H = 768 instead of 192).  The eight partial
+// columns] in TMEM: 24 MMAs of M128 at H = 768 instead of 192).  The product is bf16x3 like forward's
+// (the reference's BPTT is fp32, models/AcousticModel.py:386-401): dgates_t streams in as a stacked B tile
+// (rows 0..Bpad-1 = hi plane, Bpad..2Bpad-1 = lo plane), Wh_hi x [dg_hi | dg_lo] is one N = 2 Bpad MMA per 16
+// K-elements and Wh_lo -- a second resident A block, in tensor memory as far as the 512 columns go, in shared
+// memory beyond -- x dg_hi accumulates onto the first Bpad columns.  The eight partial
 // accumulators are reduce-scattered through distributed shared memory with st.async
 // (complete_tx on the owner's mbarrier): CTA s of the cluster ends up with the 16 units
 // [128i+16s, +16) and does their cell backward.  Each CTA streams only its K-segment of
@@ -447,13 +451,16 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
 struct KBwd {
   RecTcBwdArgs a;
   int H, B, Bpad, nslice, nkbs, ngl;       // nkbs = K-blocks of this CTA's K segment (H/2 / 64)
+  int x3;                                  // 1: bf16x3 product (Wh_lo resident, dgates lo plane streamed); 0: one product
+  int nlo_t;                               // K-blocks of Wh_lo resident in tensor memory (the other nkbs - nlo_t in smem)
   int variant;
   uint32_t tmem_cols;
 };
 
 // 128 registers (no spills; 168 unconstrained) x 320 threads and ~50 KB of shared memory: with RS_TC_CORES=1 a 256-thread
 // GEMM CTA (gemm_tc_kernel<128, 2>) fits on the same SM
-template <bool STAMP, int VARIANT, int BPAD, int HH>
+// X3: 1 / 0 = the product's term count fixed at compile time (1 with HH > 0: every Wh_lo block in tensor memory), -1 = from the arguments
+template <bool STAMP, int VARIANT, int BPAD, int HH, int X3>
 __global__ void __maxnreg__(128)
 rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmS_hi,
                   const __grid_constant__ CUtensorMap tmS_lo, KBwd p) {
@@ -470,12 +477,17 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const int blk = blockIdx.x / CL;
   const int j = blk * CL + (int)rank;                   // 16-unit slice (same numbering as forward)
   const int kseg0 = (int)rank * (H / 2);                // first dgates column of this CTA's K segment
-  const uint32_t kb_bytes = (uint32_t)Bpad * 128;
-  unsigned char* sG = smem;                                                  // [nkbs][Bpad x 128 B] dgates_t K segment
-  float* sR = reinterpret_cast<float*>(smem + (size_t)nkbs * kb_bytes);      // [CL src][16 units][Bpad] partial dh
+  const bool x3 = X3 >= 0 ? (X3 != 0) : (p.x3 != 0);
+  const int nlo_t = !x3 ? 0 : ((X3 == 1 && HH > 0) ? HH / 128 : p.nlo_t);
+  const int nlo_s = x3 ? nkbs - nlo_t : 0;
+  const uint32_t kb_bytes = (uint32_t)Bpad * 128 * (x3 ? 2u : 1u);          // one streamed K-block: hi rows (; lo rows)
+  unsigned char* sG = smem;                                                  // [nkbs][planes][Bpad x 128 B] dgates_t K segment
+  unsigned char* sAlo = smem + (size_t)nkbs * kb_bytes;                      // [nlo_s][128 rows x 128 B] Wh_lo blocks outside TMEM
+  float* sR = reinterpret_cast<float*>(sAlo + (size_t)nlo_s * 16384);        // [CL src][16 units][Bpad] partial dh
   __nv_bfloat16* sDG = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(sR) + (size_t)CL * TSU * Bpad * 4);
                                                                              // [2 planes][Bpad][4 gates][16 units]
-  const uint32_t colD = (uint32_t)(H / 4);
+  const uint32_t colLo = (uint32_t)(H / 4);              // Wh_hi: columns [0, H/4); Wh_lo: nlo_t blocks of 32 columns behind
+  const uint32_t colD = colLo + (uint32_t)nlo_t * 32;
   const int t1 = a.t0 + T;                                // this launch: steps t1 - 1 down to t0
   const bool primed = t1 < a.Ttot;                        // dh_{t1-1} comes from dgates_{t1} of the previous launch
   const int ts_first = primed ? t1 : t1 - 1;              // first dgates step streamed through the tensor core
@@ -500,6 +512,22 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
       tc::tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
     }
+    if (x3) {
+      const __nv_bfloat16* srcl = a.wh_lo + (size_t)(blk * 128 + (int)threadIdx.x) * G + kseg0;
+      for (int c0 = 0; c0 < nlo_t * 32; c0 += 8) {
+        const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(srcl + 2 * c0));
+        const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(srcl + 2 * c0 + 8));
+        const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        tc::tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + colLo + (uint32_t)c0, r);
+      }
+      for (int kb = nlo_t; kb < nkbs; ++kb) {
+        unsigned char* tile = sAlo + (size_t)(kb - nlo_t) * 16384 + (size_t)threadIdx.x * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(tile + ((c ^ (threadIdx.x & 7)) << 4)) = __ldg(reinterpret_cast<const uint4*>(srcl + kb * 64 + c * 8));
+      }
+      if (nlo_s > 0) tc::fence_proxy_async_smem();
+    }
     tc::tmem_st_wait();
   }
   tc::tc_fence_before();
@@ -522,13 +550,16 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       if (lane == 0) RS_STAMP(a.dbg, t, 0);
       __syncwarp();
       tc::mbar_arrive_expect_tx_warp(&full_bar, (uint32_t)nkbs * kb_bytes);
-      for (int i = 0; i < nkbs; ++i) tc::tma_load_2d_warp(sG + (size_t)i * kb_bytes, &tmG, kseg0 + i * 64, t * B, &full_bar);
+      if (x3) tc::tma_load_4d_warp(sG, &tmG, 0, t * B, 0, kseg0 / 64, &full_bar);       // one box: [kb][plane][Bpad][64]
+      else for (int i = 0; i < nkbs; ++i) tc::tma_load_2d_warp(sG + (size_t)i * kb_bytes, &tmG, kseg0 + i * 64, t * B, &full_bar);
       if (lane == 0) RS_STAMP(a.dbg, t, 1);
       __syncwarp();
     }
   } else if (warp == 9) {
-    const uint32_t idesc = tc::instr_desc_bf16(128, Bpad);
+    const uint32_t idesc = tc::instr_desc_bf16(128, Bpad);               // N = one plane
+    const uint32_t idesc2 = tc::instr_desc_bf16(128, 2 * Bpad);          // N = both planes stacked
     const uint64_t dg0 = tc::smem_desc_sw128(tc::smem_u32(sG));
+    const uint64_t dAlo0 = tc::smem_desc_sw128(tc::smem_u32(sAlo));
     const uint32_t tmemD = tmem + colD;
     uint32_t n = 0;
     for (int t = ts_first; t >= a.t0 + 1; --t, ++n) {
@@ -536,7 +567,14 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       tc::tc_fence_after();
       if (lane == 0) RS_STAMP(a.dbg, t, 2);
       __syncwarp();
-      issue_ts_blocks<6>(nkbs, tmemD, tmem, dg0, (uint64_t)(kb_bytes >> 4), idesc, 0u);                                // 6: H = 768
+      if (x3) {
+        // D[:, 0:2Bpad) = Wh_hi [dg_hi | dg_lo] ; D[:, 0:Bpad) += Wh_lo dg_hi
+        issue_ts_blocks<6>(nkbs, tmemD, tmem, dg0, (uint64_t)(kb_bytes >> 4), idesc2, 0u);                             // 6: H = 768
+        issue_ts_blocks<6>(nlo_t, tmemD, tmem + colLo, dg0, (uint64_t)(kb_bytes >> 4), idesc, 1u);
+        for (int i = nlo_t; i < nkbs; ++i)
+          tc::mma4_bf16_ss_warp(tmemD, dAlo0 + (uint64_t)(i - nlo_t) * (16384 >> 4), dg0 + (uint64_t)i * (kb_bytes >> 4), idesc, 1u);
+      } else
+      issue_ts_blocks<6>(nkbs, tmemD, tmem, dg0, (uint64_t)(kb_bytes >> 4), idesc, 0u);
       tc::mma_commit_warp(&tfull_bar);
       if (lane == 0) RS_STAMP(a.dbg, t, 3);
       __syncwarp();
@@ -613,7 +651,15 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
           if (gi < ng) {
             float v[16];
             tc::tmem_ld16(tmemD + (uint32_t)(gi * 16), v);
-            tc::tmem_ld_wait();
+            if (x3) {
+              float w[16];
+              tc::tmem_ld16(tmemD + (uint32_t)(Bpad + gi * 16), w);      // Wh_hi dg_lo
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += w[i];
+            } else {
+              tc::tmem_ld_wait();
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               st_async_v4(push_base + (uint32_t)(gi * 16 + 4 * i) * 4u, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]),
@@ -779,8 +825,9 @@ bool rec_ts_geometry(int H, int B, RecTcGeom* g) {
   g->gkb = gkb;
   g->nkb_t = nkb_t;
   g->ngl = (Bpad / 16 + 1) / 2;
-  // backward: TMEM columns = H/4 (Wh segment) + Bpad (accumulator) must fit
-  if (H / 4 + Bpad > 512) return false;
+  // backward: TMEM columns = H/4 (Wh_hi segment) + 2 Bpad (accumulator of the stacked planes) must fit; Wh_lo takes
+  // what is left and shared memory beyond that
+  if (H / 4 + 2 * Bpad > 512) return false;
   return true;
 }
 
@@ -843,27 +890,51 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
   if (a.Ttot <= 0) { a.Ttot = a.T; a.t0 = 0; }
   RS_REQUIRE(a.T > 0 && a.t0 >= 0 && a.t0 + a.T <= a.Ttot, RS_ERR_INVALID, "lstm_rec_ts_backward: T=%d t0=%d Ttot=%d", a.T, a.t0, a.Ttot);
   RS_REQUIRE(a.t0 + a.T == a.Ttot || a.dc_carry, RS_ERR_INVALID, "lstm_rec_ts_backward: a continued launch needs dc_carry");
-  CUtensorMap tg;
-  int rc;
-  if ((rc = tmap_2d_bf16(&tg, a.dg_hi, a.Ttot * g.B, 4 * g.H, 4 * g.H, g.Bpad)) != RS_OK) return rc;
+  // bf16x3 (default) needs both weight planes; RS_BWD_X3=0 or a missing low plane: one bf16 product
+  static const bool x3_env = [] { const char* v = getenv("RS_BWD_X3"); return !(v && v[0] == '0'); }();
+  const bool x3 = x3_env && a.wh_lo != nullptr;
   KBwd p;
   p.a = a;
   p.H = g.H; p.B = g.B; p.Bpad = g.Bpad; p.nslice = g.nslice; p.nkbs = g.H / 2 / 64; p.ngl = g.ngl;
+  p.x3 = x3 ? 1 : 0;
+  // tensor-memory columns: Wh_hi (H/4) + as many 32-column blocks of Wh_lo as fit + the accumulator (N = planes x Bpad)
+  const int dcols = (x3 ? 2 : 1) * g.Bpad;
+  int nlo_t = 0;
+  if (x3) {
+    nlo_t = (512 - g.H / 4 - dcols) / 32;
+    if (nlo_t > p.nkbs) nlo_t = p.nkbs;
+    RS_REQUIRE(nlo_t >= 0, RS_ERR_UNSUPPORTED, "lstm_rec_ts_backward: H=%d does not fit tensor memory", g.H);
+  }
+  p.nlo_t = nlo_t;
+  const int nlo_s = x3 ? p.nkbs - nlo_t : 0;
   uint32_t cols = 32;
-  while ((int)cols < g.H / 4 + g.Bpad) cols <<= 1;
+  while ((int)cols < g.H / 4 + nlo_t * 32 + dcols) cols <<= 1;
   p.tmem_cols = cols;
   p.variant = ts_variant();
-  size_t smem = (size_t)p.nkbs * g.Bpad * 128 + (size_t)CL * TSU * g.Bpad * 4 + (size_t)2 * g.Bpad * 4 * TSU * 2 + 1024;
+  CUtensorMap tg;
+  int rc;
+  if (x3) {
+    RS_REQUIRE(a.dg_lo > a.dg_hi, RS_ERR_INVALID, "lstm_rec_ts_backward: the low dgates plane must follow the high one");
+    if ((rc = tmap_stacked2_bf16(&tg, a.dg_hi, (size_t)((const char*)a.dg_lo - (const char*)a.dg_hi), a.Ttot * g.B, 4 * g.H,
+                                 4 * g.H, g.Bpad, p.nkbs)) != RS_OK) return rc;
+  } else {
+    if ((rc = tmap_2d_bf16(&tg, a.dg_hi, a.Ttot * g.B, 4 * g.H, 4 * g.H, g.Bpad)) != RS_OK) return rc;
+  }
+  size_t smem = (size_t)p.nkbs * g.Bpad * 128 * (x3 ? 2 : 1) + (size_t)nlo_s * 16384 + (size_t)CL * TSU * g.Bpad * 4 +
+                (size_t)2 * g.Bpad * 4 * TSU * 2 + 1024;
+  RS_REQUIRE(smem <= 227 * 1024 - 2048, RS_ERR_UNSUPPORTED, "lstm_rec_ts_backward: H=%d B=%d needs %zu bytes of shared memory", g.H, g.B, smem);
   // (two of these cannot share an SM: 2 x 320 x 128 registers exceed the register file)
   static const bool share = [] { const char* v = getenv("RS_TC_CORES"); return v && v[0] == '1'; }();
   // keep the SM to this CTA unless sharing is asked for (RS_TC_CORES=1) and a GEMM CTA can really share it (256 free
   // tensor-memory columns); sharing measured slower at cfg-2, see lstm_tc.cu
   if ((!share || cols > 256) && smem < 120 * 1024) smem = 120 * 1024;
   RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
-  const bool fast = !a.dbg && p.variant == kDefaultVariant && g.Bpad == 32 && g.H == 768;
-  const int si = a.dbg ? 1 : (fast ? 2 : 0);
-  auto kern = a.dbg ? rec_ts_bwd_kernel<true, -1, 0, 0> : (fast ? rec_ts_bwd_kernel<false, kDefaultVariant, 32, 768> : rec_ts_bwd_kernel<false, -1, 0, 0>);
-  static size_t attr_smem[3] = {0, 0, 0};
+  const bool fast = !a.dbg && p.variant == kDefaultVariant && g.Bpad == 32 && g.H == 768 && (!x3 || nlo_t == p.nkbs);
+  const int si = a.dbg ? 1 : (fast ? (x3 ? 2 : 3) : 0);
+  auto kern = a.dbg ? rec_ts_bwd_kernel<true, -1, 0, 0, -1>
+                    : (fast ? (x3 ? rec_ts_bwd_kernel<false, kDefaultVariant, 32, 768, 1> : rec_ts_bwd_kernel<false, kDefaultVariant, 32, 768, 0>)
+                            : rec_ts_bwd_kernel<false, -1, 0, 0, -1>);
+  static size_t attr_smem[4] = {0, 0, 0, 0};
   if (attr_smem[si] != smem) {
     RS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -877,7 +948,7 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int nclusters_s[3] = {0, 0, 0};
+  static int nclusters_s[4] = {0, 0, 0, 0};
   if (attr_smem[si] != smem) {
     RS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nclusters_s[si], kern, &cfg));
     attr_smem[si] = smem;

@@ -5,8 +5,8 @@
 //
 // Activations travel between kernels as "planes" (x ~= hi + lo, two bf16 arrays): that is
 // what TMA feeds to the tensor cores, and with the bf16x3 product it carries fp32-grade
-// accuracy through the forward pass.  The backward recurrence dh_{t-1} = dgates_t Wh^T
-// uses plain bf16 operands (gradient-grade accuracy); all other backward GEMMs are bf16x3.
+// accuracy through the forward pass.  Backward likewise: the recurrence dh_{t-1} = dgates_t Wh^T
+// (TMEM-resident kernel) and all batched backward GEMMs are bf16x3.
 #include "lstm_internal.cuh"
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
@@ -42,7 +42,7 @@ struct TcBufs {
   float* run_state;               // [L,2,B,H] state carried from one chunked launch to the next
   // backward-only workspace
   bf16 *wxs_hi[64], *wxs_lo[64];  // K[:H] as stored [H][4H]
-  bf16 *whs_hi[64];               // K[H:] as stored [H][4H] (hi)
+  bf16 *whs_hi[64], *whs_lo[64];  // K[H:] as stored [H][4H]
   bf16 *wos_hi, *wos_lo;          // w_o as stored [H][Cp]
   bf16 *dg_hi[64], *dg_lo[64];    // [T*B][4H] per layer
   bf16 *dgT_hi[64], *dgT_lo[64];  // [4H][TBp] per layer
@@ -84,7 +84,7 @@ void carve(const rs_am* am, void* reserve, void* ws, bool training, TcBufs* b, s
   if (training) {
     for (int l = 0; l < L; ++l) {
       b->wxs_hi[l] = w.take<bf16>((size_t)4 * H * H); b->wxs_lo[l] = w.take<bf16>((size_t)4 * H * H);
-      b->whs_hi[l] = w.take<bf16>((size_t)4 * H * H);
+      b->whs_hi[l] = w.take<bf16>((size_t)4 * H * H); b->whs_lo[l] = w.take<bf16>((size_t)4 * H * H);
       b->dg_hi[l] = w.take<bf16>(TB * 4 * H); b->dg_lo[l] = w.take<bf16>(TB * 4 * H);
       b->dc_carry[l] = w.take<float>(am->tc.ts ? rec_ts_dc_carry_floats(am->tc) : 1);
       b->dgT_hi[l] = w.take<bf16>((size_t)4 * H * TBp); b->dgT_lo[l] = w.take<bf16>((size_t)4 * H * TBp);
@@ -474,7 +474,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   for (int l = 0; l < L; ++l) {
     const float* K = params_d + am->off_kernel[l];
     RC(split_planes(K, bf.wxs_hi[l], bf.wxs_lo[l], (int64_t)H * 4 * H, st));
-    RC(split_planes(K + (size_t)H * 4 * H, bf.whs_hi[l], nullptr, (int64_t)H * 4 * H, st));
+    RC(split_planes(K + (size_t)H * 4 * H, bf.whs_hi[l], bf.whs_lo[l], (int64_t)H * 4 * H, st));
   }
   // where forward left each layer's input / the top activations
   const int hld = am->tc.ts ? 2 * H : H;
@@ -541,7 +541,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     RecTcBwdArgs a{};
     a.dout = dout; a.gates = bf.gates[l]; a.cs = bf.cs[l];
     a.c0 = bf.state0 + ((size_t)l * 2 + 0) * B * H;
-    a.wh_hi = bf.whs_hi[l]; a.dg_hi = bf.dg_hi[l]; a.dg_lo = bf.dg_lo[l]; a.len = len_d; a.barrier = bf.barrier[l];
+    a.wh_hi = bf.whs_hi[l]; a.wh_lo = bf.whs_lo[l]; a.dg_hi = bf.dg_hi[l]; a.dg_lo = bf.dg_lo[l]; a.len = len_d; a.barrier = bf.barrier[l];
     a.T = n; a.t0 = t0; a.Ttot = T; a.dc_carry = NC > 1 ? bf.dc_carry[l] : nullptr;
     a.dbg = (l == 0 && NC == 1) ? am->dbg_bwd : nullptr;
     RC(tev_record(am, 1, l, ls));

@@ -23,7 +23,7 @@ import logging
 import os
 import sys
 import time
-from random import shuffle
+from random import Random
 
 import numpy as np
 
@@ -50,7 +50,9 @@ def load_dataset_dirs(dirs, with_durations=False):
                 if not line:
                     continue
                 path, text = line.split("\t", 1)
-                items.append([path if os.path.isabs(path) else os.path.join(d, path), text, None])
+                # transcripts go through the corpus walkers' clean_label (util/dataprocessor.py:73-95): upper case or
+                # punctuation would otherwise end the label at the first unknown character
+                items.append([path if os.path.isabs(path) else os.path.join(d, path), clean_label(text), None])
             continue
         for root, _, files in sorted(os.walk(d)):
             for f in sorted(files):
@@ -69,13 +71,24 @@ def load_dataset_dirs(dirs, with_durations=False):
     return items
 
 
+SHUFFLE_SEED = 20171103      # shared by every rank: the permutation must be the same in all processes
+
+
+def shuffled(items, epoch):
+    """The same permutation in every process (data parallel: the ranks shard ONE order; an unseeded shuffle per
+    process would make the shards overlap and leak held-out items into other ranks' training sets)."""
+    out = list(items)
+    Random(SHUFFLE_SEED + epoch).shuffle(out)
+    return out
+
+
 def split_acoustic_dataset(train_set, test_set, ordered, train_frac):
     """models/SpeechRecognizer.py:80-95: order by duration or shuffle, then carve the test set out of the training
     set when no test directory is configured."""
     if ordered:
         train_set = sorted(train_set, key=lambda x: x[2] or 0)
     else:
-        shuffle(train_set)
+        train_set = shuffled(train_set, 0)
     if not test_set and train_frac is not None:
         num_train = max(1, int(np.floor(train_frac * len(train_set))))
         train_set, test_set = train_set[:num_train], train_set[num_train:]
@@ -137,7 +150,10 @@ def train_acoustic_rnn(rs, train_set, test_set, hyper_params, prog_params):
     rank, world, local = dist_setup()
     import torch
     device = torch.device("cuda", local)
-    train_set = train_set[rank::world]            # data parallel: every rank owns a shard
+    from rnn_speech_b200 import dist as rsdist
+    global_train_set = train_set
+    # data parallel: every rank owns a shard of the SAME global order, all shards of equal size (lockstep collectives)
+    train_set = rsdist.shard(global_train_set, rank, world)
     ckpt_dir = os.path.join(hyper_params["checkpoint_dir"], "acoustic")
     os.makedirs(ckpt_dir, exist_ok=True)
     model, build, has_valid = build_acoustic_training_rnn(rs, hyper_params, prog_params, train_set, test_set, device)
@@ -161,7 +177,8 @@ def train_acoustic_rnn(rs, train_set, test_set, hyper_params, prog_params):
                     break
                 if hyper_params["dataset_size_ordering"] in ['False', 'First_run_only']:
                     logging.info("Shuffling the training dataset")
-                    shuffle(train_set)
+                    global_train_set = shuffled(global_train_set, epoch)          # same order on every rank, re-sharded
+                    train_set = rsdist.shard(global_train_set, rank, world)
                     model._train_dataset = build(train_set)
                 else:
                     logging.info("Reuse the same training dataset")

@@ -16,9 +16,8 @@ L, H, F, C, T, B = 1, 16, 12, 10, 14, 4
 
 
 def _dist_module():
-    spec = importlib.util.spec_from_file_location("_rs_dist", os.path.join(ROOT, "rnn-speech_b200", "dist.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
+    import rnn_speech_b200
+    from rnn_speech_b200 import dist as mod
     return mod
 
 

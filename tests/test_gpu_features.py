@@ -108,3 +108,24 @@ def test_mfcc_matches_oracle(pkg, cuda, sr, lens):
     short = pkg.AudioProcessor(40, "mfcc", device=cuda)
     f40, l40 = short.process_signal(sigs[0], sr)
     assert f40.shape == (40, 20) and l40 == nframes[0]          # truncated features, untruncated length
+
+
+def test_mfcc_40_coefficients_baseline_config_1(pkg, cuda):
+    """BASELINE config 1 as it is written ("40-dim MFCC", batch 2 of 1 s at 16 kHz): the reference's code keeps
+    librosa's 20 coefficients (util/audioprocessor.py:21,65-66) while its README says 40; AudioProcessor(n_mfcc=40)
+    runs the latter.  The first 20 of the 40 are the 20-coefficient result (a DCT truncation)."""
+    rng = np.random.default_rng(40)
+    sigs = [(0.1 * rng.standard_normal(16000)).astype(np.float32) for _ in range(2)]
+    ap40 = pkg.AudioProcessor(200, "mfcc", device=cuda, n_mfcc=40)
+    ap20 = pkg.AudioProcessor(200, "mfcc", device=cuda)
+    assert ap40.feature_size == 40
+    f40, n40 = ap40.process_batch(sigs, 16000, time_major=True)
+    f20, _ = ap20.process_batch(sigs, 16000, time_major=True)
+    assert tuple(f40.shape) == (200, 2, 40) and int(n40[0]) == 101
+    f40, f20 = f40.cpu().numpy(), f20.cpu().numpy()
+    for b, s in enumerate(sigs):
+        want, T = features.mfcc(s, 16000, 200, n_mfcc=40)
+        assert np.abs(f40[:T, b] - want).max() < 2e-3
+    np.testing.assert_allclose(f40[:, :, :20], f20, atol=1e-5)
+    with pytest.raises(ValueError):
+        pkg.AudioProcessor(200, "mfcc", n_mfcc=0)

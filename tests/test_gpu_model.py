@@ -157,6 +157,51 @@ def test_cfg2_shape_forward_against_oracle(pkg, cuda):
     assert rel.max() < 1e-3
 
 
+def cfg2_backward_parity(pkg, cuda, keep_in, keep_out, tag):
+    """One forward + backward at BASELINE config 2's shape (3x768, B=32, T=998, ragged lengths) through the C ABI,
+    dlogits from the ORACLE's CTC on the oracle's logits, every gradient tensor against oracle.model.backward
+    (float64; models/AcousticModel.py:386-401).  Returns the per-tensor report."""
+    from parity_util import format_report, grad_report, keep_artifact, tie_report
+    L, H, F, C, B, T = 3, 768, 120, 80, 32, 998
+    rng = np.random.default_rng(7)
+    p = model.init_params(L, H, F, C, seed=0, dtype=np.float64)
+    flat = model.flatten(p, L, H, F, C)
+    x = rng.standard_normal((T, B, F))
+    lens = np.full(B, T, np.int32)
+    lens[1::4] = rng.integers(T // 2, T, size=len(lens[1::4]))
+    lens[2] = 301
+    labs = [np.append(rng.integers(1, 79, size=rng.integers(60, 121)), 79).astype(np.int32) for _ in range(B)]
+    m = _build(pkg, cuda, L, H, F, C, B, 1000, flat, training=True, ki=keep_in, ko=keep_out)
+    assert m.uses_tensor_cores
+    xd, ld = _dev(x, cuda, np.float32), _dev(lens, cuda, np.int32)
+    logits = m.forward(xd, ld, training=True)
+    ki, ko, seed, _ = m._last_fwd
+    want, _, cache = model.forward(p, x.astype(np.float32), lens, L, H, keep_in=ki, keep_out=ko, seed=seed)
+    got = logits.cpu().numpy()
+    frames, ties, mism = tie_report(got, want, lens, MARGIN)
+    want_loss, dl = ctc.ctc_loss_and_grad(want, labs, lens)
+    m.grads.zero_()
+    m.backward(xd, ld, _dev(dl, cuda, np.float32))
+    gw = model.flatten(model.backward(p, cache, dl, L, H), L, H, F, C)
+    rows = grad_report(m.grads.cpu().numpy(), gw, L, H, F, C)
+    title = ("cfg-2 shape backward vs float64 oracle [%s, keep %.1f/%.1f]: max |logit err| %.2e, %d frames, %d near ties, "
+             "%d argmax mismatches" % (tag, keep_in, keep_out, np.abs(got - want).max(), frames, ties, mism))
+    print(format_report(rows, title))
+    keep_artifact("r02_grad_parity_%s.json" % tag, {"title": title, "rows": rows})
+    return rows, np.abs(got - want).max(), mism
+
+
+@pytest.mark.parametrize("keep_in,keep_out,tag", [(1.0, 1.0, "nodrop"), (0.8, 0.5, "dropout")])
+def test_cfg2_shape_backward_against_oracle(pkg, cuda, keep_in, keep_out, tag):
+    """VERDICT r01 item 1 / SURVEY a15: the gradients the headline number leans on, at the benchmarked shape.
+    Gate: relative L2 error <= 1e-3 and cosine >= 1 - 1e-6 for EVERY parameter tensor."""
+    rows, err, mism = cfg2_backward_parity(pkg, cuda, keep_in, keep_out, tag)
+    assert err < 1e-3 and mism == 0
+    for r in rows:
+        assert r["rel_l2"] <= 1e-3, "%s: relative L2 error %.3e" % (r["tensor"], r["rel_l2"])
+        assert r["cosine"] >= 1.0 - 1e-6, "%s: cosine %.9f" % (r["tensor"], r["cosine"])
+
+
 @pytest.mark.parametrize("L,H,B,T,chunk", [(3, 256, 8, 150, 32), (2, 128, 16, 97, 20)])
 def test_time_chunked_wavefront_is_bitwise_the_single_launch_schedule(pkg, cuda, monkeypatch, L, H, B, T, chunk):
     """The pipelined schedule (time chunks, layers as a wavefront on several streams) only reorders launches:

@@ -10,6 +10,7 @@ from oracle import ctc, model, optim
 
 
 def _torch_forward(p, x, lens, L, H, state, ki, ko, seed):
+    ki, ko = float(np.float32(ki)), float(np.float32(ko))      # float32 keep probabilities, as the oracle takes them
     T, B, F = x.shape
     tp = {k: torch.tensor(v, requires_grad=True) for k, v in p.items()}
     cur = (torch.tensor(x).reshape(T * B, F) @ tp["input_w"] + tp["input_b"]).reshape(T, B, H)
@@ -109,3 +110,26 @@ def test_clip_and_adam_against_torch():
         opt.step()
     # torch puts eps inside the bias-corrected denominator, TF outside: equal to O(eps)
     np.testing.assert_allclose(th, tt.detach().numpy(), atol=5e-8)
+
+
+
+@pytest.mark.parametrize("ki,ko", [(1.0, 1.0), (0.8, 0.5)])
+def test_torch_cpu_leg_equals_numpy_oracle(ki, ko):
+    """oracle/model_torch.py (the MKL leg of bench.py's CPU baseline) is the same arithmetic as oracle/model.py."""
+    from oracle import model_torch
+    L, H, F, C, T, B = 2, 16, 12, 10, 11, 4
+    rng = np.random.default_rng(3)
+    p = model.init_params(L, H, F, C, seed=7, dtype=np.float64)
+    for k in p:
+        if p[k].ndim == 1:
+            p[k] = rng.standard_normal(p[k].shape) * 0.1
+    x = rng.standard_normal((T, B, F))
+    lens = np.array([11, 7, 0, 10])
+    logits, _, cache = model.forward(p, x, lens, L, H, keep_in=ki, keep_out=ko, seed=9)
+    tl, tcache = model_torch.forward(p, x, lens, L, H, keep_in=ki, keep_out=ko, seed=9, dtype=torch.float64)
+    np.testing.assert_allclose(tl.numpy(), logits, rtol=1e-11, atol=1e-12)
+    dl = rng.standard_normal(logits.shape) * (np.arange(T)[:, None, None] < lens[None, :, None])
+    want = model.backward(p, cache, dl, L, H)
+    got = model_torch.backward(tcache, dl, L, H)
+    for k in want:
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-10, atol=1e-11)
