@@ -548,8 +548,8 @@ class AcousticModel(object):
         for d in (0, 1):
             for l in range(self.num_layers):
                 ms = _lib.ctypes.c_float()
-                _lib.call("rs_am_recurrent_ms", self._handle, d, l, _lib.ctypes.byref(ms))
-                out[d].append(ms.value)
+                rc = _lib.raw("rs_am_recurrent_ms")(self._handle, d, l, _lib.ctypes.byref(ms))
+                out[d].append(ms.value if rc == 0 else 0.0)       # (a direction that has not run: inference)
         return out
 
     def recurrent_trace(self, max_launches=256):

@@ -50,7 +50,10 @@ struct KParams {
   GemmTcOut out;
 };
 
-template <int BN, int ST>
+// MN = true: both operands MN-major ("TN" product C = A^T B of two matrices stored [K][M] and [K][N] row-major --
+// the weight-gradient GEMMs x^T dgates, whose operands the other kernels write with K = (t, b) as the ROW index):
+// every 64-column block of an operand tile is its own TMA box {64 mn, 64 k}.
+template <int BN, int ST, bool MN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, KParams p) {
@@ -106,16 +109,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           unsigned char* st = smem + (size_t)s * STAGE_BYTES;
           tc::mbar_arrive_expect_tx_warp(&full_bar[s], tx);
+          if constexpr (MN) {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) {
+              tc::tma_load_2d_warp(st + i * 8192, &tmA_hi, m0 + 64 * i, kb * BK, &full_bar[s]);
+              if (use_alo) tc::tma_load_2d_warp(st + TILE_A_BYTES + i * 8192, &tmA_lo, m0 + 64 * i, kb * BK, &full_bar[s]);
+            }
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) {
+              tc::tma_load_2d_warp(st + 2 * TILE_A_BYTES + i * 8192, &tmB_hi, n0 + 64 * i, kb * BK, &full_bar[s]);
+              if (use_blo) tc::tma_load_2d_warp(st + 2 * TILE_A_BYTES + TILE_B_BYTES + i * 8192, &tmB_lo, n0 + 64 * i, kb * BK, &full_bar[s]);
+            }
+          } else {
           tc::tma_load_2d_warp(st, &tmA_hi, kb * BK, m0, &full_bar[s]);
           tc::tma_load_2d_warp(st + 2 * TILE_A_BYTES, &tmB_hi, kb * BK, n0, &full_bar[s]);
           if (use_alo) tc::tma_load_2d_warp(st + TILE_A_BYTES, &tmA_lo, kb * BK, m0, &full_bar[s]);
           if (use_blo) tc::tma_load_2d_warp(st + 2 * TILE_A_BYTES + TILE_B_BYTES, &tmB_lo, kb * BK, n0, &full_bar[s]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     {   // converged warp, elect.sync inside each issue
-      const uint32_t idesc = tc::instr_desc_bf16(BM, BN);
+      const uint32_t idesc = MN ? tc::instr_desc_bf16_mn(BM, BN) : tc::instr_desc_bf16(BM, BN);
       uint32_t it = 0, tl = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += nctas, ++tl) {
         const int as = tl & 1;
@@ -128,14 +144,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tc::mbar_wait(&full_bar[s], ph);
           tc::tc_fence_after();
           const uint32_t sa = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint64_t dah = tc::smem_desc_sw128(sa), dal = tc::smem_desc_sw128(sa + TILE_A_BYTES);
-          const uint64_t dbh = tc::smem_desc_sw128(sa + 2 * TILE_A_BYTES);
-          const uint64_t dbl = tc::smem_desc_sw128(sa + 2 * TILE_A_BYTES + TILE_B_BYTES);
+          // K-major: 16 K elements = 32 bytes along the row; MN-major: 16 K rows = two 8-row groups = 2048 bytes
+          constexpr uint32_t KSTEP = MN ? (2048 >> 4) : 2;
+          const uint64_t dah = MN ? tc::smem_desc_sw128_mn(sa, 8192, 1024) : tc::smem_desc_sw128(sa);
+          const uint64_t dal = MN ? tc::smem_desc_sw128_mn(sa + TILE_A_BYTES, 8192, 1024) : tc::smem_desc_sw128(sa + TILE_A_BYTES);
+          const uint64_t dbh = MN ? tc::smem_desc_sw128_mn(sa + 2 * TILE_A_BYTES, 8192, 1024) : tc::smem_desc_sw128(sa + 2 * TILE_A_BYTES);
+          const uint64_t dbl = MN ? tc::smem_desc_sw128_mn(sa + 2 * TILE_A_BYTES + TILE_B_BYTES, 8192, 1024)
+                                  : tc::smem_desc_sw128(sa + 2 * TILE_A_BYTES + TILE_B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            tc::mma_bf16_ss_warp(d, dah + 2 * k, dbh + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-            if (use_blo) tc::mma_bf16_ss_warp(d, dah + 2 * k, dbl + 2 * k, idesc, 1u);
-            if (use_alo) tc::mma_bf16_ss_warp(d, dal + 2 * k, dbh + 2 * k, idesc, 1u);
+            tc::mma_bf16_ss_warp(d, dah + KSTEP * k, dbh + KSTEP * k, idesc, (uint32_t)((kb | k) != 0));
+            if (use_blo) tc::mma_bf16_ss_warp(d, dah + KSTEP * k, dbl + KSTEP * k, idesc, 1u);
+            if (use_alo) tc::mma_bf16_ss_warp(d, dal + KSTEP * k, dbh + KSTEP * k, idesc, 1u);
           }
           tc::mma_commit_warp(&empty_bar[s]);
         }
@@ -310,6 +330,52 @@ __global__ void rowsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const
   if (lane == 0) out[row] = accumulate ? out[row] + s : s;
 }
 
+// one block per 64 columns, all rows: deterministic (one writer per column, fixed summation order).  Thread (cx, ry):
+// 8 columns (one 16-byte load per plane and row), rows ry, ry + 32, ...
+__global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                                            int R, int C, int ld, float* __restrict__ out, int accumulate) {
+  __shared__ float red[32][65];
+  const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
+  const int c = blockIdx.x * 64 + 8 * cx;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  if (c + 7 < C) {
+#pragma unroll 4
+    for (int r = ry; r < R; r += 32) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + (size_t)r * ld + c));
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s[2 * i] += __uint_as_float(w[i] << 16); s[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u); }
+      if (lo) {
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(lo + (size_t)r * ld + c));
+        const uint32_t v[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { s[2 * i] += __uint_as_float(v[i] << 16); s[2 * i + 1] += __uint_as_float(v[i] & 0xffff0000u); }
+      }
+    }
+  } else {
+    for (int r = ry; r < R; r += 32)
+      for (int i = 0; i < 8; ++i)
+        if (c + i < C) {
+          s[i] += __bfloat162float(hi[(size_t)r * ld + c + i]);
+          if (lo) s[i] += __bfloat162float(lo[(size_t)r * ld + c + i]);
+        }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[ry][8 * cx + i] = s[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+      out[cc] = accumulate ? out[cc] + t : t;
+    }
+  }
+}
+
 int make_tmap(CUtensorMap* map, const __nv_bfloat16* base, int rows, int cols, int ld, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   RS_REQUIRE(fn != nullptr, RS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
@@ -328,6 +394,24 @@ int make_tmap(CUtensorMap* map, const __nv_bfloat16* base, int rows, int cols, i
 }
 
 }  // namespace
+
+// MN-major operand: the matrix is [krows][cols] row-major (cols = the M / N index, contiguous); box {64 cols, 64 k rows}
+int make_tmap_mn(CUtensorMap* map, const __nv_bfloat16* base, int krows, int cols, int ld) {
+  EncodeTiledFn fn = encode_fn();
+  RS_REQUIRE(fn != nullptr, RS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  RS_REQUIRE((ld % 8) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, RS_ERR_INVALID,
+             "TMA operand needs ld %% 8 == 0 and a 16-byte aligned base (ld=%d)", ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)krows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RS_REQUIRE(r == CUDA_SUCCESS, RS_ERR_CUDA, "cuTensorMapEncodeTiled (mn) failed with %d (krows=%d cols=%d ld=%d)", (int)r,
+             krows, cols, ld);
+  return RS_OK;
+}
 
 int tmap_2d_bf16(void* map64, const __nv_bfloat16* base, int rows, int cols, int ld, int box_rows) {
   return make_tmap(reinterpret_cast<CUtensorMap*>(map64), base, rows, cols, ld, box_rows);
@@ -406,18 +490,23 @@ int tmap_stacked2_bf16(void* map64, const __nv_bfloat16* base_hi, size_t plane_s
 
 namespace {
 
-template <int BN, int ST>
+template <int BN, int ST, bool MN>
 int gemm_launch(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
                 cudaStream_t st) {
   // bf16x3 degrades gracefully to the planes that exist: hi*hi (+ hi*B_lo) (+ A_lo*hi)
   products = (products == 3 ? ((B.lo ? 1 : 0) | (A.lo ? 2 : 0)) : 0);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
-  if ((rc = make_tmap(&ta_hi, A.hi, M, K, A.ld, BM)) != RS_OK) return rc;
-  if ((rc = make_tmap(&tb_hi, B.hi, N, K, B.ld, BN)) != RS_OK) return rc;
+  if (MN) {
+    if ((rc = make_tmap_mn(&ta_hi, A.hi, K, M, A.ld)) != RS_OK) return rc;
+    if ((rc = make_tmap_mn(&tb_hi, B.hi, K, N, B.ld)) != RS_OK) return rc;
+  } else {
+    if ((rc = make_tmap(&ta_hi, A.hi, M, K, A.ld, BM)) != RS_OK) return rc;
+    if ((rc = make_tmap(&tb_hi, B.hi, N, K, B.ld, BN)) != RS_OK) return rc;
+  }
   ta_lo = ta_hi; tb_lo = tb_hi;
-  if (products & 2) if ((rc = make_tmap(&ta_lo, A.lo, M, K, A.ld, BM)) != RS_OK) return rc;
-  if (products & 1) if ((rc = make_tmap(&tb_lo, B.lo, N, K, B.ld, BN)) != RS_OK) return rc;
+  if (products & 2) if ((rc = MN ? make_tmap_mn(&ta_lo, A.lo, K, M, A.ld) : make_tmap(&ta_lo, A.lo, M, K, A.ld, BM)) != RS_OK) return rc;
+  if (products & 1) if ((rc = MN ? make_tmap_mn(&tb_lo, B.lo, K, N, B.ld) : make_tmap(&tb_lo, B.lo, N, K, B.ld, BN)) != RS_OK) return rc;
   KParams p;
   p.M = M; p.N = N; p.K = K; p.products = products;
   p.tiles_m = cdiv(M, BM); p.tiles_n = cdiv(N, BN);
@@ -432,10 +521,10 @@ int gemm_launch(const SplitMat& A, const SplitMat& B, int M, int N, int K, int p
   const size_t smem = (size_t)Cfg<BN, ST>::STAGES * Cfg<BN, ST>::STAGE_BYTES + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    RS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, ST, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  gemm_tc_kernel<BN, ST><<<grid, NTHREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  gemm_tc_kernel<BN, ST, MN><<<grid, NTHREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }
@@ -455,8 +544,22 @@ int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int pr
   int ctas = sm_count();
   if (out.max_ctas > 0 && out.max_ctas < ctas && !out.elastic) ctas = out.max_ctas;
   const bool wide = force_bn ? force_bn == 256 : (N > 128 && cdiv(M, BM) * cdiv(N, 256) >= ctas);
-  if (out.coresident) return gemm_launch<128, 2>(A, B, M, N, K, products, out, st);
-  return wide ? gemm_launch<256, 2>(A, B, M, N, K, products, out, st) : gemm_launch<128, 3>(A, B, M, N, K, products, out, st);
+  if (out.coresident) return gemm_launch<128, 2, false>(A, B, M, N, K, products, out, st);
+  return wide ? gemm_launch<256, 2, false>(A, B, M, N, K, products, out, st) : gemm_launch<128, 3, false>(A, B, M, N, K, products, out, st);
+}
+
+// C[M,N] = A^T B with A stored [K][M] and B stored [K][N] (row-major, ld in elements): both operands MN-major.
+int gemm_tc_tn(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
+               cudaStream_t st) {
+  if (M <= 0 || N <= 0) return RS_OK;
+  RS_REQUIRE(K > 0, RS_ERR_INVALID, "gemm_tc_tn: K=%d", K);
+  RS_REQUIRE(out.mode == GEMM_OUT_F32 && !out.coresident, RS_ERR_INVALID, "gemm_tc_tn: fp32 output only");
+  static const int env_bn = [] { const char* v = getenv("RS_GEMM_BN"); return v ? atoi(v) : 0; }();
+  const int force_bn = g_force_bn >= 0 ? g_force_bn : env_bn;
+  int ctas = sm_count();
+  if (out.max_ctas > 0 && out.max_ctas < ctas && !out.elastic) ctas = out.max_ctas;
+  const bool wide = force_bn ? force_bn == 256 : (N > 128 && cdiv(M, BM) * cdiv(N, 256) >= ctas);
+  return wide ? gemm_launch<256, 2, true>(A, B, M, N, K, products, out, st) : gemm_launch<128, 3, true>(A, B, M, N, K, products, out, st);
 }
 
 int split_planes(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t st) {
@@ -484,6 +587,16 @@ int transpose_bf16(const __nv_bfloat16* in, int R, int C, int ld_in, __nv_bfloat
   return RS_OK;
 }
 
+int colsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int R, int C, int ld, float* out, int accumulate,
+                  cudaStream_t st) {
+  if (C <= 0) return RS_OK;
+  RS_REQUIRE((ld % 8) == 0 && (reinterpret_cast<uintptr_t>(hi) & 15) == 0 && (!lo || (reinterpret_cast<uintptr_t>(lo) & 15) == 0),
+             RS_ERR_INVALID, "colsum_planes: planes must be 16-byte aligned with a row stride that is a multiple of 8");
+  colsum_planes_kernel<<<cdiv(C, 64), 256, 0, st>>>(hi, lo, R, C, ld, out, accumulate);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
 int rowsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int R, int C, int ld, float* out, int accumulate,
                   cudaStream_t st) {
   if (R <= 0) return RS_OK;
@@ -498,9 +611,27 @@ using namespace rs;
 
 // Test hook: C[M,N] = A[M,K] * B[N,K]^T (+bias) from fp32 inputs; scratch_d must hold
 // 2*(M*Kp + N*Kp) bf16 with Kp = K rounded up to 8.
+// products >= 16 selects the MN-major form (A_d is [K][M], B_d is [K][N], M and N multiples of 8; products - 16 = 1 | 3).
 extern "C" int rs_gemm_tc_test(const float* A_d, const float* B_d, const float* bias_d, float* C_d, int M, int N,
                                int K, int products, void* scratch_d, size_t scratch_bytes, void* stream) {
   RS_REQUIRE(A_d && B_d && C_d && scratch_d, RS_ERR_INVALID, "rs_gemm_tc_test: NULL argument");
+  if (products >= 16) {
+    RS_REQUIRE(M % 8 == 0 && N % 8 == 0, RS_ERR_INVALID, "rs_gemm_tc_test (MN-major): M and N must be multiples of 8");
+    const size_t need_mn = 2 * ((size_t)M * K + (size_t)N * K) * sizeof(__nv_bfloat16) + 64;
+    RS_REQUIRE(scratch_bytes >= need_mn, RS_ERR_WORKSPACE, "rs_gemm_tc_test: scratch %zu < %zu", scratch_bytes, need_mn);
+    cudaStream_t st2 = (cudaStream_t)stream;
+    __nv_bfloat16* ah2 = (__nv_bfloat16*)scratch_d;
+    __nv_bfloat16* al2 = ah2 + (size_t)M * K;
+    __nv_bfloat16* bh2 = al2 + (size_t)M * K;
+    __nv_bfloat16* bl2 = bh2 + (size_t)N * K;
+    int rc2;
+    if ((rc2 = split_planes(A_d, ah2, al2, (int64_t)M * K, st2)) != RS_OK) return rc2;
+    if ((rc2 = split_planes(B_d, bh2, bl2, (int64_t)N * K, st2)) != RS_OK) return rc2;
+    SplitMat A2{ah2, al2, K, M, M}, B2{bh2, bl2, K, N, N};
+    GemmTcOut o2{};
+    o2.mode = GEMM_OUT_F32; o2.C = C_d; o2.ldc = N; o2.bias = bias_d; o2.accumulate = 0;
+    return gemm_tc_tn(A2, B2, M, N, K, products - 16, o2, st2);
+  }
   RS_REQUIRE(K % 8 == 0, RS_ERR_INVALID, "rs_gemm_tc_test: K must be a multiple of 8");
   const size_t need = 2 * ((size_t)M * K + (size_t)N * K) * sizeof(__nv_bfloat16) + 64;
   RS_REQUIRE(scratch_bytes >= need, RS_ERR_WORKSPACE, "rs_gemm_tc_test: scratch %zu < %zu", scratch_bytes, need);

@@ -50,6 +50,15 @@ struct GemmTcOut {
 int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
                cudaStream_t st);
 
+// C[M,N] = A^T B with both operands stored K-outermost ("MN-major"): A is [K][M], B is [K][N], row-major, ld in
+// elements (SplitMat.rows = K).  The weight-gradient products x^T dgates read x, h and dgates exactly as the
+// forward / backward kernels wrote them ((t, b) as the row index): no transposed copies.  fp32 output only.
+int gemm_tc_tn(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
+               cudaStream_t st);
+// out[c] (+)= sum_r (hi[r][c] + lo[r][c]) over a [R, C] plane pair (lo may be nullptr): bias gradients from dgates
+int colsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int R, int C, int ld, float* out, int accumulate,
+                  cudaStream_t st);
+
 // out planes <- split(in * scale) elementwise; optional dropout masks as in lstm.cu
 int split_planes(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t st);
 // transpose + split: in [R,C] row-major (ld_in) -> planes [C,R] row-major (ld_out)

@@ -205,6 +205,13 @@ int split_rows(const float* in, int R, int C, int ld_in, bf16* hi, bf16* lo, int
 
 #define RC(x) do { int _rc = (x); if (_rc != RS_OK) return _rc; } while (0)
 
+// Weight-gradient GEMMs read their operands as the other kernels wrote them ((t, b) as the row index: MN-major
+// operands of gemm_tc_tn) -- no transposed copies.  RS_TC_TN=0 brings back the transposing kernels + gemm_tc_nt.
+bool use_tn() {
+  static const bool v = [] { const char* e = getenv("RS_TC_TN"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
 // ---- streams and events of the pipelined schedule
 int ensure_streams(rs_am* am) {
   if (am->streams_ready) return RS_OK;
@@ -490,8 +497,9 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   }
 
   // ---- output dense: dW_o += top^T dlogits, db_o += colsum, dtop = dlogits w_o^T
+  const bool tn = use_tn();
   RC(split_rows(dlogits_d, TB, C, C, bf.dl_hi, bf.dl_lo, Cp, st));
-  RC(split_planes_transposed(dlogits_d, TB, C, C, bf.dlT_hi, bf.dlT_lo, TBp, st));                  // [C][TBp]
+  if (!tn) RC(split_planes_transposed(dlogits_d, TB, C, C, bf.dlT_hi, bf.dlT_lo, TBp, st));                  // [C][TBp]
   {
     SplitMat A{bf.dl_hi, bf.dl_lo, TB, C, Cp}, Bm{bf.wos_hi, bf.wos_lo, H, C, Cp};
     GemmTcOut o{};
@@ -512,11 +520,17 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_fork, 0));
   RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_fork, 0));
   RS_CHECK_CUDA(cudaStreamWaitEvent(am->tr_st, e_fork, 0));
-  // Weight-gradient work (transposes, dK GEMMs, bias sums) is off the critical path: it runs on the side stream,
-  // on the SMs the recurrent launches leave idle.  First the output dense's.
-  RC(transpose_bf16(in_hi[L], TB, H, in_ld[L], bf.actT_hi, TBp, side));
-  RC(transpose_bf16(in_lo[L], TB, H, in_ld[L], bf.actT_lo, TBp, side));
-  {
+  // Weight-gradient work (dK GEMMs, bias sums) is off the critical path: it runs on the side stream,
+  // on the SMs the recurrent launches leave idle.  First the output dense's: dW_o += top^T dlogits, db_o += colsum.
+  if (tn) {
+    SplitMat A{in_hi[L], in_lo[L], TB, H, in_ld[L]}, Bm{bf.dl_hi, bf.dl_lo, TB, C, Cp};
+    GemmTcOut o{};
+    o.mode = GEMM_OUT_F32; o.C = grads_d + am->off_output_w; o.ldc = C; o.accumulate = 1; o.max_ctas = sc.side_ctas;
+    RC(gemm_tc_tn(A, Bm, H, C, TB, 3, o, side));
+    RC(colsum_planes(bf.dl_hi, bf.dl_lo, TB, C, Cp, grads_d + am->off_output_b, 1, side));
+  } else {
+    RC(transpose_bf16(in_hi[L], TB, H, in_ld[L], bf.actT_hi, TBp, side));
+    RC(transpose_bf16(in_lo[L], TB, H, in_ld[L], bf.actT_lo, TBp, side));
     SplitMat A{bf.actT_hi, bf.actT_lo, H, TB, TBp}, Bm{bf.dlT_hi, bf.dlT_lo, C, TB, TBp};
     GemmTcOut o{};
     o.mode = GEMM_OUT_F32; o.C = grads_d + am->off_output_w; o.ldc = C; o.accumulate = 1; o.max_ctas = sc.side_ctas;
@@ -573,6 +587,32 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     const int t0 = sc.start[c], n = sc.start[c + 1] - sc.start[c];
     const size_t r0 = (size_t)t0 * B;                   // first (t, b) row of the chunk = first column of the transposes
     const int nb = n * B;
+    float* gK = grads_d + am->off_kernel[l];
+    if (tn) {
+      // bias sums on the transposer stream (small CTAs beside the recurrent launches); the GEMMs read the planes
+      // in place: x / h_{t-1} are [nb][H] with (t, b) rows, dgates [nb][4H]
+      cudaStream_t tr = am->tr_st;
+      RS_CHECK_CUDA(cudaStreamWaitEvent(tr, e_rec[(size_t)l * NC + c], 0));
+      RC(colsum_planes(bf.dg_hi[l] + r0 * 4 * H, bf.dg_lo[l] + r0 * 4 * H, nb, 4 * H, 4 * H, grads_d + am->off_bias[l], 1, tr));
+      RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_rec[(size_t)l * NC + c], 0));
+      RC(tev_record(am, 2, l, side));
+      SplitMat G{bf.dg_hi[l] + r0 * 4 * H, bf.dg_lo[l] + r0 * 4 * H, nb, 4 * H, 4 * H};
+      {
+        SplitMat A{in_hi[l] + r0 * in_ld[l], in_lo[l] + r0 * in_ld[l], nb, H, in_ld[l]};
+        GemmTcOut o{};
+        o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas; o.tiles_per_cta = sc.side_tpc;
+        if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
+        RC(gemm_tc_tn(A, G, H, 4 * H, nb, 3, o, side));
+      }
+      {
+        SplitMat A{bf.hp_hi[l] + r0 * hld, bf.hp_lo[l] + r0 * hld, nb, H, hld};       // slots t0..t0+n-1 = h_{t-1}
+        GemmTcOut o{};
+        o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas; o.tiles_per_cta = sc.side_tpc;
+        if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
+        RC(gemm_tc_tn(A, G, H, 4 * H, nb, 3, o, side));
+      }
+      return tev_record(am, 2, l, side);
+    }
     // transposes (K-major operands for the tensor core) and the bias sums: small CTAs that share SMs with the
     // recurrent launches, on their own stream so that the side stream is GEMMs back to back
     cudaStream_t tr = am->tr_st;
@@ -589,7 +629,6 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_tr, 0));
     RC(tev_record(am, 2, l, side));
     SplitMat G{bf.dgT_hi[l] + r0, bf.dgT_lo[l] + r0, 4 * H, nb, TBp};
-    float* gK = grads_d + am->off_kernel[l];
     {
       SplitMat A{bf.xT2_hi[l] + r0, bf.xT2_lo[l] + r0, H, nb, TBp};
       GemmTcOut o{};
@@ -618,6 +657,20 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     float* drnn = bf.din[0] + r0 * H;
     if (drop_in) RC(dropout_f32(drnn, drnn, (int64_t)nb * H, (int64_t)r0 * H, seed, 0, keep_in, -1, 1.f, tr));
     if (am->normalization) RC(bn_backward(drnn, bf.bn_xhat + r0 * H, bf.bn_istd + (size_t)t0 * H, n, B, H, tr));
+    if (tn) {
+      // drnn planes in place of the transposed ones ([nb][H], the buffers are the same size)
+      bf16 *dr_hi = bf.drT_hi + r0 * H, *dr_lo = bf.drT_lo + r0 * H;
+      RC(split_rows(drnn, nb, H, H, dr_hi, dr_lo, H, tr));
+      cudaEvent_t e_in;
+      RC(ev_record(am, &e_in, tr));
+      RC(colsum_planes(dr_hi, dr_lo, nb, H, H, grads_d + am->off_input_b, 1, tr));
+      RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_in, 0));
+      SplitMat A{bf.x_hi + r0 * Fp, bf.x_lo + r0 * Fp, nb, F, Fp}, Bm{dr_hi, dr_lo, nb, H, H};
+      GemmTcOut o{};
+      o.mode = GEMM_OUT_F32; o.C = grads_d + am->off_input_w; o.ldc = H; o.accumulate = 1; o.max_ctas = sc.side_ctas;
+      if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
+      return gemm_tc_tn(A, Bm, F, H, nb, 3, o, side);
+    }
     RC(split_planes_transposed(drnn, nb, H, H, bf.drT_hi + r0, bf.drT_lo + r0, TBp, tr));             // [H][chunk]
     RC(transpose_bf16(bf.x_hi + r0 * Fp, nb, F, Fp, bf.xT_hi + r0, TBp, tr));
     RC(transpose_bf16(bf.x_lo + r0 * Fp, nb, F, Fp, bf.xT_lo + r0, TBp, tr));

@@ -117,9 +117,25 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
   return d;
 }
+// MN-major SWIZZLE_128B operand tile: the operand is stored with its M (or N) index contiguous -- 64 of them per
+// 128-byte row, one row per K index, 8-row groups of 1024 bytes (what a TMA box {64 mn, 64 k} of a [K][MN] row-major
+// matrix lands as).  Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: LBO = distance between
+// 64-element MN blocks, SBO = distance between 8-row K groups.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // kind::f16, A = B = bf16 (K-major), D = fp32, shape M x N x 16
 __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// the same with both operands MN-major (bit 15: A, bit 16: B)
+__host__ __device__ constexpr uint32_t instr_desc_bf16_mn(int M, int N) {
+  return instr_desc_bf16(M, N) | (1u << 15) | (1u << 16);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues
