@@ -174,6 +174,12 @@ int rs_am_forward(rs_am* am, const float* params_d, const float* x_d, const int3
                   const float* state_in_d, float* state_out_d,
                   float keep_in, float keep_out, uint64_t seed,
                   float* logits_d, void* reserve_d, void* ws_d, size_t ws_bytes, void* stream);
+/* Weight planes (the bf16 hi/lo images of the parameters the kernels read) are kept in the caller's workspace.  By
+ * default they are re-packed on every rs_am_forward / rs_am_backward.  A caller that sets a non-zero version vouches
+ * that params_d only changes when the version does and that nothing else writes the workspace between calls; the
+ * planes are then re-packed once per version (the reference's variables likewise change only in train_step_op,
+ * models/AcousticModel.py:404-406). */
+int rs_am_set_params_version(rs_am* am, uint64_t version);
 /* Measurement hooks: when enabled, CUDA events are recorded on the launching stream around
  * each recurrent kernel launch (one per layer, or one per time chunk of a layer in the
  * pipelined schedule).  rs_am_recurrent_ms returns the summed duration of a layer's launches

@@ -42,6 +42,7 @@ SIGNATURES = {
     "rs_sm_count": (c_int, []),
     "rs_launch_count": (c_uint64, []),
     "rs_crc32c": (ctypes.c_uint32, [c_void_p, c_size_t, ctypes.c_uint32]),
+    "rs_am_set_params_version": (c_int, [c_void_p, c_uint64]),
     "rs_am_enable_timing": (c_int, [c_void_p, c_int]),
     "rs_am_set_debug_timeline": (c_int, [c_void_p, c_void_p, c_void_p]),
     "rs_am_recurrent_ms": (c_int, [c_void_p, c_int, c_int, POINTER(c_float)]),

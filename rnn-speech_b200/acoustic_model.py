@@ -163,6 +163,12 @@ class AcousticModel(object):
         self.rnn_state = torch.zeros((self.num_layers, 2, self.batch_size, self.hidden_size), dtype=torch.float32,
                                      device=self.device)
         self._ctc_ws = None
+        # version of the parameter buffer (rs_am_set_params_version): the kernels' weight planes are re-packed when it
+        # changes -- once per optimizer step -- instead of on every forward / backward call.  Every method of this
+        # class that writes self.params bumps it; code that writes the buffer directly calls params_changed().  With
+        # batch tiles of two sizes the tiles' handles lay the shared workspace out differently: no caching then.
+        self._params_version = 1
+        self._cache_planes = len(getattr(self, "_tile_handles", None) or [h]) == 1
         self.rnn_created = True
 
     def create_forward_rnn(self):
@@ -235,6 +241,15 @@ class AcousticModel(object):
         finally:
             self.params = saved
 
+    def params_changed(self):
+        """Tell the library that self.params was modified (see _create_common)."""
+        self._params_version += 1
+
+    def _sync_params_version(self):
+        v = self._params_version if self._cache_planes else 0
+        for th in (getattr(self, "_tile_handles", None) or [self._handle]):
+            _lib.call("rs_am_set_params_version", th, v)
+
     def initialize(self, sess=None):
         """Xavier / glorot-uniform weights, zero biases (models/AcousticModel.py:242-245,
         :303-306, BasicLSTMCell defaults); deterministic in self.seed."""
@@ -249,11 +264,13 @@ class AcousticModel(object):
                 v.zero_()
         self.global_step = 0
         self.rnn_state.zero_()
+        self.params_changed()
 
     def load_flat_params(self, flat):
         flat = torch.as_tensor(np.asarray(flat, dtype=np.float32))
         assert flat.numel() == self.n_params
         self.params.copy_(flat.to(self.device))
+        self.params_changed()
 
     def get_learning_rate(self):
         return self.learning_rate_var
@@ -320,6 +337,7 @@ class AcousticModel(object):
                                      % (k, tuple(data[k].shape), tuple(v.shape)))
                 v.copy_(torch.from_numpy(np.ascontiguousarray(data[k], dtype=np.float32)).to(self.device))
             self.global_step = int(np.asarray(data["global_step"]).reshape(-1)[0])
+            self.params_changed()
             self._adam_step = 0
             if self.adam_m is not None:
                 self.adam_m.zero_()
@@ -368,6 +386,7 @@ class AcousticModel(object):
         # fresh masks per call, and per rank under data parallelism (N ranks = N independent mini-batches)
         seed = (int(self.seed) * 1000003 + self._dropout_calls + dist_world()[0] * 0x632BE59BD9B4E019) & 0xFFFFFFFFFFFFFFFF
         self._last_fwd = (keep_in, keep_out, seed, T)
+        self._sync_params_version()
         if self._tiles is None:
             _lib.call("rs_am_forward", self._handle, self.params.data_ptr(), x_d.data_ptr(), len_d.data_ptr(), T,
                       self.rnn_state.data_ptr(), self.rnn_state.data_ptr() if keep_state else None,
@@ -394,6 +413,7 @@ class AcousticModel(object):
 
     def backward(self, x_d, len_d, dlogits):
         keep_in, keep_out, seed, T = self._last_fwd
+        self._sync_params_version()
         if self._tiles is None:
             _lib.call("rs_am_backward", self._handle, self.params.data_ptr(), x_d.data_ptr(), len_d.data_ptr(), T,
                       keep_in, keep_out, seed, dlogits.data_ptr(), self._reserve.data_ptr(), self.grads.data_ptr(),
@@ -535,6 +555,7 @@ class AcousticModel(object):
         _lib.call("rs_clip_adam_step", self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
                   self.adam_v.data_ptr(), self.n_params, self._sumsq.data_ptr(), self.grad_clip,
                   self.learning_rate_var, 0.9, 0.999, 1e-8, self._adam_step, _stream_ptr())
+        self.params_changed()
         self._phase_mark("end")
 
     # ---------------------------------------------------------- measurement
@@ -696,6 +717,7 @@ class AcousticModel(object):
         out_len = torch.empty((batch,), dtype=torch.int32, device=self.device)
         tiles = self._tiles if self._tiles is not None else [{"b0": 0, "b1": batch, "handle": self._handle}]
         clamp = audio_processor.num_frames(int(max_samples), sr) > Tmax
+        self._sync_params_version()
         for t in tiles:
             b0, b1 = t["b0"], t["b1"]
             bt = b1 - b0

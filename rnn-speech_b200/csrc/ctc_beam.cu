@@ -30,7 +30,10 @@ constexpr int kMaxW = 128;          // beam entries
 constexpr int kMaxC = 128;          // classes
 constexpr int kHash = 256;          // hash-table slots (>= 2 * kMaxW)
 constexpr int kThreads = 256;
-constexpr int kRankMax = 1024;      // candidate lists up to this size are ordered by counting ranks
+constexpr int kRankMax = 256;       // candidate lists up to this size are ordered by counting ranks (one candidate per
+                                    // thread, <= 256 comparisons each); longer lists go through the bitonic sort, whose
+                                    // cost grows with n log^2 n instead of n^2 / 256 (round 1 ranked up to 1024: with the
+                                    // flat posteriors of an untrained model that was most of the kernel's 24 ms)
 constexpr int kMaxCand = 8192;      // >= kMaxW + kMaxW * (kMaxC - 1) is not needed: W * (C - 1) + W <= 8192 is checked
 constexpr float kNegInf = -INFINITY;
 
@@ -119,7 +122,6 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
         h = (h + 1) & (kHash - 1);
       }
     }
-    __syncthreads();
     // ---- 2. update the entries
     float my_tot = kNegInf;
     if (tid < n) {
@@ -187,7 +189,13 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
       const float previous = (c == bm.label[slot]) ? old_blk[slot] : old_tot[slot];
       const float tot = in[c] + previous;
       if (tot > kNegInf && tot >= lbv) {
-        const int pos = n + atomicAdd(&s_count, 1);
+        // append, one shared-memory atomic per warp and iteration (the lanes that pass agree on their positions by vote)
+        const unsigned act = __activemask();
+        const int leader = __ffs(act) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&s_count, __popc(act));
+        base = __shfl_sync(act, base, leader);
+        const int pos = n + base + __popc(act & ((1u << lane) - 1u));
         ckey[pos] = tot;
         cid[pos] = kMaxW + idx;
       }
@@ -293,7 +301,11 @@ extern "C" int rs_ctc_beam_search(const float* logits_d, const int32_t* len_d, i
              "rs_ctc_beam_search: beam_width * classes = %d candidates > %d", beam_width * C, kMaxCand);
   RS_REQUIRE(ws_bytes >= rs_ctc_beam_workspace_bytes(T, B), RS_ERR_WORKSPACE, "rs_ctc_beam_search: workspace %zu < %zu",
              ws_bytes, rs_ctc_beam_workspace_bytes(T, B));
-  const size_t smem = (size_t)kMaxCand * (sizeof(float) + sizeof(int));
+  // The decoder runs on a side stream under the backward pass.  Its CTAs are compute loops: sharing an SM with a CTA of
+  // the latency-critical recurrent kernels slows every recurrent step (measured: the training step went from 26 to 65 ms
+  // when they co-resided), so the candidate list is padded to a size that gives the CTA its SM to itself.
+  const size_t smem = 120 * 1024;
+  static_assert((size_t)kMaxCand * (sizeof(float) + sizeof(int)) <= 120 * 1024, "candidate list");
   static bool attr_done = false;
   if (!attr_done) {
     RS_CHECK_CUDA(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

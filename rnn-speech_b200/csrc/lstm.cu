@@ -103,6 +103,11 @@ extern "C" int rs_am_create(rs_am** out, int num_layers, int hidden_size, int in
   {
     const char* v = getenv("RS_TC_CHUNK");
     am->chunk = v ? atoi(v) : 128;
+    am->chunk_is_default = v ? 0 : 1;
+    am->params_version = 0;
+    am->packed_version[0] = am->packed_version[1] = 0;
+    am->packed_ws[0] = am->packed_ws[1] = nullptr;
+    am->packed_params[0] = am->packed_params[1] = nullptr;
     v = getenv("RS_TC_WINDOW");
     am->window = v ? atoi(v) : 2;
     if (am->window < 1) am->window = 1;
@@ -145,6 +150,13 @@ extern "C" void rs_am_destroy(rs_am* am) {
 extern "C" int rs_am_set_normalization(rs_am* am, int enable) {
   RS_REQUIRE(am != nullptr, RS_ERR_INVALID, "rs_am_set_normalization: NULL handle");
   am->normalization = enable ? 1 : 0;
+  return RS_OK;
+}
+
+// See rs_am::params_version.  0 (the default) = always re-pack.
+extern "C" int rs_am_set_params_version(rs_am* am, uint64_t version) {
+  RS_REQUIRE(am != nullptr, RS_ERR_INVALID, "rs_am_set_params_version: NULL handle");
+  am->params_version = version;
   return RS_OK;
 }
 

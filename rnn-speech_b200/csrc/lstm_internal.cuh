@@ -26,10 +26,19 @@ struct rs_am {
   std::vector<cudaEvent_t> evpool;
   size_t ev_next;
   int chunk;                     // time steps per chunked launch (RS_TC_CHUNK; 0 = one launch per layer)
+  int chunk_is_default;          // RS_TC_CHUNK not set: the forward phase schedule picks its own chunk length
   int window;                    // recurrent launches allowed in flight (RS_TC_WINDOW)
   unsigned long long* dbg_fwd;   // optional device buffers [T][8] for kernel timelines (layer 0)
   unsigned long long* dbg_bwd;
   rs::RecTcGeom tc;
+  // Weight planes (bf16 hi/lo, packed for the kernels) live in the caller's workspace.  With a non-zero
+  // params_version (rs_am_set_params_version) the caller vouches that the parameters only change when the version
+  // does and that nobody else writes the workspace between calls: the planes are then re-packed once per version
+  // instead of once per forward / backward call.
+  unsigned long long params_version;
+  unsigned long long packed_version[2];      // [forward set | backward set]
+  const void* packed_ws[2];
+  const void* packed_params[2];
 };
 
 

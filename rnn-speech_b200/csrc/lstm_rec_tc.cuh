@@ -45,6 +45,16 @@ struct RecTcFwdArgs {
   // steps [t0, t0 + T) of a sequence of Ttot steps.  Every per-step array (gx, h planes, reserve blob) is indexed
   // by the absolute step; c0 / h0 hold the state after step t0 - 1 (cT / hT may alias them).
   int t0, Ttot;
+  // Fused hop to the next consumer (TMEM-resident kernel only; drop_hi == nullptr: off).  The cell output -- 0 past the
+  // sequence end -- goes through the cell's output dropout (stream sa) and the next cell's input dropout (stream sb)
+  // (DropoutWrapper, /root/reference/models/AcousticModel.py:232-233; the mask of element (t, b, h) is
+  // dropout_keep(key, stream, (t*B + b)*H + h, thr), as oracle/model.py::dropout_mask) and is written as bf16 planes
+  // drop_hi / drop_lo [Ttot*B][H] (row t*B + b).  thr == 0xffffffff: that mask is off.
+  __nv_bfloat16* drop_hi;
+  __nv_bfloat16* drop_lo;
+  unsigned long long drop_key;
+  unsigned drop_sa, drop_thr_a, drop_sb, drop_thr_b;
+  float drop_inv_a, drop_inv_b;
 };
 
 int lstm_rec_tc_forward(const RecTcGeom& g, const RecTcFwdArgs& a, cudaStream_t st);
@@ -78,6 +88,11 @@ struct RecTcBwdArgs {
   // dc_carry != nullptr leaves its own there.
   int t0, Ttot;
   float* dc_carry;
+  // Fused dropout backward of the hop above (TMEM-resident kernel only): dout is multiplied by the same masks as it is
+  // read (thr == 0xffffffff: off), instead of being rewritten in place by a separate kernel.
+  unsigned long long drop_key;
+  unsigned drop_sa, drop_thr_a, drop_sb, drop_thr_b;
+  float drop_inv_a, drop_inv_b;
 };
 int lstm_rec_tc_backward(const RecTcBwdGeom& g, const RecTcBwdArgs& a, cudaStream_t st);
 

@@ -162,12 +162,14 @@ __device__ __forceinline__ size_t blob_idx(int t, int nslice, int j, int ngl, in
 // HH > 0: hidden size fixed at compile time, with all of K in tensor memory as one TMA group (nkb = nkb_t = gkb = HH/64)
 template <bool STAMP, int VARIANT, int BPAD, int HH>
 __global__ void __launch_bounds__(NTHREADS, 1)
-rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmS, KFwd p) {
+rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmS,
+                  const __grid_constant__ CUtensorMap tmD, KFwd p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[MAXSLOTS], empty_bar[MAXSLOTS], tfull_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(128) __nv_bfloat16 sH[64][2][TSU];          // staged h_t [b][plane][unit]
+  __shared__ __align__(128) __nv_bfloat16 sD[64][2][TSU];          // staged dropout(out_t) for the next consumer
   const RecTcFwdArgs& a = p.a;
   const int variant = VARIANT >= 0 ? VARIANT : p.variant;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -326,6 +328,7 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         }
       }
       float2 keep[MAXG][BLOB_ITEMS];
+      float hout[MAXG][2];
       tc::mbar_wait(&tfull_bar, (uint32_t)(ti & 1));
       tc::tc_fence_after();
       if (threadIdx.x == 0) RS_STAMP(a.dbg, ti, 4);
@@ -375,6 +378,7 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             tc::split_bf16(valid ? h_new : 0.f, hh, hlo);
             sH[b][0][ul] = hh;
             sH[b][1][ul] = hlo;
+            hout[gl][k] = valid ? h_new : 0.f;
             gv[0][k] = ig; gv[1][k] = jg; gv[2][k] = fg; gv[3][k] = og; cn[k] = c_new;
           }
 #pragma unroll
@@ -385,6 +389,9 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 5);
       tc::tc_fence_before();
       if (variant & 16) tc::fence_proxy_async_smem();
+      // (thread 0 arrives here after its previous bulk groups -- the hop store of step t-1 among them -- have read
+      //  their shared-memory source, so sD may be rewritten behind this barrier)
+      if (a.drop_hi && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       epi_bar_sync();
       if (variant & 16) {
         // publish h_t (both planes) with one TMA store; the bulk-group wait returns when the writes are performed
@@ -425,10 +432,38 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           }
         }
       }
+      // fused hop (off the critical path of the recurrence): dropout(out_t) planes for the next layer / the output dense
+      if (a.drop_hi) {
+#pragma unroll
+        for (int gl = 0; gl < MAXG; ++gl) {
+          const int gi = hf + 2 * gl;
+          if (gi < ng) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int b = gi * 16 + 8 * up + 2 * g + k;
+              float v = hout[gl][k];
+              const unsigned long long idx = ((unsigned long long)t * B + b) * H + unit;
+              if (a.drop_thr_a != 0xffffffffu) v = dropout_keep(a.drop_key, a.drop_sa, idx, a.drop_thr_a) ? v * a.drop_inv_a : 0.f;
+              if (a.drop_thr_b != 0xffffffffu) v = dropout_keep(a.drop_key, a.drop_sb, idx, a.drop_thr_b) ? v * a.drop_inv_b : 0.f;
+              __nv_bfloat16 dh_, dl_;
+              tc::split_bf16(v, dh_, dl_);
+              sD[b][0][ul] = dh_;
+              sD[b][1][ul] = dl_;
+            }
+          }
+        }
+        tc::fence_proxy_async_smem();
+        epi_bar_sync();
+        if (threadIdx.x == 0) {
+          tc::tma_store_3d(&tmD, &sD[0][0][0], j * TSU, 0, t * B);
+          tc::bulk_commit();
+        }
+      }
       if (threadIdx.x == 0) RS_STAMP(a.dbg, t, 7);
       if constexpr (STAMP)
         if (threadIdx.x == 0 && a.dbg && blockIdx.x == 0) a.dbg[(size_t)t * 16 + 15] = (unsigned long long)clock64();   // SM clock vs globaltimer
     }
+    if (a.drop_hi && threadIdx.x == 0) tc::bulk_wait_all();          // the last hop store is performed before the kernel ends
 #pragma unroll
     for (int gl = 0; gl < MAXG; ++gl)
 #pragma unroll
@@ -627,7 +662,12 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const int b = gi * 16 + 8 * up + 2 * g + k;
-            dy[gl][k] = (b < B) ? __ldg(a.dout + ((size_t)t * B + b) * H + unit) : 0.f;
+            float d = (b < B) ? __ldg(a.dout + ((size_t)t * B + b) * H + unit) : 0.f;
+            // backward of the hop's dropout(s): the same masks, applied as the gradient is read
+            const unsigned long long idx = ((unsigned long long)t * B + b) * H + unit;
+            if (a.drop_thr_a != 0xffffffffu) d = dropout_keep(a.drop_key, a.drop_sa, idx, a.drop_thr_a) ? d * a.drop_inv_a : 0.f;
+            if (a.drop_thr_b != 0xffffffffu) d = dropout_keep(a.drop_key, a.drop_sb, idx, a.drop_thr_b) ? d * a.drop_inv_b : 0.f;
+            dy[gl][k] = d;
             cpv[k] = (t == 0 && b < B) ? __ldg(a.c0 + (size_t)b * H + unit) : 0.f;
           }
           if (t == 0) cp2[gl] = make_float2(cpv[0], cpv[1]);
@@ -848,6 +888,12 @@ int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a_in, cudaStream
   const int hrows = (a.Ttot + 1) * g.B;
   if ((rc = tmap_stacked_bf16(&th, a.h_hi, hrows, g.H, g.Bpad, g.gkb)) != RS_OK) return rc;
   if ((rc = tmap_store3_bf16(&ts, a.h_hi, g.H, 2, hrows, (size_t)g.H * 2, (size_t)2 * g.H * 2, TSU, 2, g.B)) != RS_OK) return rc;
+  CUtensorMap td = ts;
+  if (a.drop_hi) {
+    RS_REQUIRE(a.drop_lo > a.drop_hi, RS_ERR_INVALID, "lstm_rec_ts_forward: the low hop plane must follow the high one");
+    if ((rc = tmap_store3_bf16(&td, a.drop_hi, g.H, 2, a.Ttot * g.B, (size_t)((const char*)a.drop_lo - (const char*)a.drop_hi),
+                               (size_t)g.H * 2, TSU, 2, g.B)) != RS_OK) return rc;
+  }
   KFwd p;
   p.a = a;
   p.H = g.H; p.B = g.B; p.Bpad = g.Bpad; p.nslice = g.nslice; p.slots = g.stages; p.nkb = g.H / 64; p.nkb_t = g.nkb_t;
@@ -875,10 +921,10 @@ int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a_in, cudaStream
   // nslice <= SM count), and plain launches of different layers run side by side (RS_TS_COOP=1: cooperative launch).
   static const bool coop = [] { const char* v = getenv("RS_TS_COOP"); return v && v[0] == '1'; }();
   if (coop) {
-    void* kargs[] = {(void*)&th, (void*)&ts, (void*)&p};
+    void* kargs[] = {(void*)&th, (void*)&ts, (void*)&td, (void*)&p};
     RS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(g.nslice), dim3(NTHREADS), kargs, g.smem_bytes, st));
   } else {
-    kern<<<dim3(g.nslice), dim3(NTHREADS), g.smem_bytes, st>>>(th, ts, p);
+    kern<<<dim3(g.nslice), dim3(NTHREADS), g.smem_bytes, st>>>(th, ts, td, p);
     RS_CHECK_CUDA(cudaGetLastError());
   }
   count_launch();

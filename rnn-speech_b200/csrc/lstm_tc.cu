@@ -207,6 +207,22 @@ int split_rows(const float* in, int R, int C, int ld_in, bf16* hi, bf16* lo, int
 
 // Weight-gradient GEMMs read their operands as the other kernels wrote them ((t, b) as the row index: MN-major
 // operands of gemm_tc_tn) -- no transposed copies.  RS_TC_TN=0 brings back the transposing kernels + gemm_tc_nt.
+// weight planes of set `which` (0 forward, 1 backward) are still valid in this workspace
+bool planes_cached(const rs_am* am, int which, const void* params_d, const void* ws_d) {
+  return am->params_version != 0 && am->packed_version[which] == am->params_version && am->packed_ws[which] == ws_d &&
+         am->packed_params[which] == params_d;
+}
+void planes_packed(rs_am* am, int which, const void* params_d, const void* ws_d) {
+  am->packed_version[which] = am->params_version;
+  am->packed_ws[which] = ws_d;
+  am->packed_params[which] = params_d;
+}
+// Dropout of the hop between layers inside the recurrent kernels (forward: epilogue; backward: as dout is read).
+// RS_TC_FUSE_DROPOUT=0 brings back the separate elementwise kernels.
+bool fuse_dropout() {
+  static const bool v = [] { const char* e = getenv("RS_TC_FUSE_DROPOUT"); return !(e && e[0] == '0'); }();
+  return v;
+}
 bool use_tn() {
   static const bool v = [] { const char* e = getenv("RS_TC_TN"); return !(e && e[0] == '0'); }();
   return v;
@@ -245,15 +261,34 @@ int ev_record(rs_am* am, cudaEvent_t* e, cudaStream_t st) {
 // wavefront: `window` recurrent launches in flight (nslice SMs each), the chunk GEMMs on the remaining SMs.
 struct Sched {
   int Tc, NC, gemm_ctas, fwd_gemm_ctas, side_ctas;
+  int window;                             // recurrent launches in flight: RS_TC_WINDOW clamped to what the device can co-host
+                                          // (each launch spins on its own grid barrier: all of its CTAs must be resident)
   std::vector<int> start;                 // chunk c covers the steps [start[c], start[c + 1])
   int side_tpc, dx_tpc, gx_tpc;           // tiles per CTA (0 = persistent grid with the caps above)
   int cores;                              // backward GEMMs share SMs with the recurrent CTAs (RS_TC_CORES=1; measured
                                           // slower than keeping them apart: 1432 vs 1502 utt/s, so off by default)
+  int phases;                             // 1: waves of L recurrent launches (every layer in flight) alternate with bursts
+                                          // of the chunk GEMMs on the whole machine (RS_TC_PHASES, default on when
+                                          // L * nslice CTAs fit the device)
 };
-Sched make_sched(const rs_am* am, int T) {
+// forward = true: the forward pass's schedule.  Forward and backward cut the time axis independently (every per-step
+// array is indexed by the absolute step).
+Sched make_sched(const rs_am* am, int T, bool forward) {
   Sched s;
-  int Tc = (am->chunk + 7) / 8 * 8;                    // chunk starts stay 16-byte aligned in the transposed planes
-  s.Tc = (am->tc.ts && am->chunk > 0 && Tc < T) ? Tc : T;
+  // Measured at cfg-2 (profiles/r02_sweep4*.log): the phase schedule -- every layer in flight, chunk GEMMs as bursts on
+  // the whole machine between waves -- wins in forward (7.48 -> 6.9 ms; 6.7 ms with chunks of 96 steps: the waves are
+  // shorter, so is the fill of the wavefront), where the chunk GEMMs need a fifth of the SMs the two-launch window leaves
+  // them.  In backward it loses (10.4 -> 13.3 ms): the weight-gradient GEMMs need those SMs all the time, and the
+  // asynchronous schedule is within 10 % of the SM-time the kernels need.
+  static const int phases_env = [] { const char* v = getenv("RS_TC_PHASES"); return v ? atoi(v) : 1; }();      // bit 0: forward, bit 1: backward
+  static const int chunk_fwd_env = [] { const char* v = getenv("RS_TC_CHUNK_FWD"); return v ? atoi(v) : 0; }();
+  const bool can_phase = am->tc.ts && am->chunk > 0 && am->L * am->tc.nslice <= sm_count();
+  const bool want_phase = can_phase && ((phases_env >> (forward ? 0 : 1)) & 1);
+  int chunk = am->chunk;
+  if (forward && chunk > 0 && chunk_fwd_env > 0) chunk = chunk_fwd_env;
+  else if (forward && want_phase && am->chunk_is_default) chunk = 96;
+  int Tc = (chunk + 7) / 8 * 8;                        // chunk starts stay 16-byte aligned in the transposed planes
+  s.Tc = (am->tc.ts && chunk > 0 && Tc < T) ? Tc : T;
   // Chunk boundaries: uniform.  (While the wavefront fills and drains fewer launches are runnable than lanes, for as
   // long as the first and the last chunk last; RS_TC_RAMP=1 makes those short -- 48, 80 steps at each end.  Measured at
   // cfg-2: forward 8.59 -> 8.49 ms, backward 11.37 -> 11.77 ms, 1513 -> 1500 utt/s, so it is off.)
@@ -279,7 +314,11 @@ Sched make_sched(const rs_am* am, int T) {
     s.start.push_back(T);
   }
   s.NC = (int)s.start.size() - 1;
-  const int spare = sm_count() - (s.NC > 1 ? am->window : 1) * am->tc.nslice;
+  s.phases = (want_phase && s.NC > 1) ? 1 : 0;
+  s.window = am->window;
+  if (am->tc.nslice > 0 && s.window > sm_count() / am->tc.nslice) s.window = sm_count() / am->tc.nslice;
+  if (s.window < 1) s.window = 1;
+  const int spare = sm_count() - (s.NC > 1 ? s.window : 1) * am->tc.nslice;
   if (s.NC > 1) {
     // The SMs the recurrent launches leave idle serve the chunk GEMMs on the critical path (a third of the backward
     // GEMM work, in short bursts) and the weight-gradient GEMMs of the side stream.  Measured at cfg-2 (52 spare
@@ -340,13 +379,17 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
   else RS_CHECK_CUDA(cudaMemsetAsync(bf.state0, 0, state_n * sizeof(float), st));
   RS_CHECK_CUDA(cudaMemcpyAsync(bf.run_state, bf.state0, state_n * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
-  // weight planes (the parameters change every step: repack; 57 MB read at cfg-2)
-  RC(split_planes_transposed(params_d + am->off_input_w, F, H, H, bf.wi_hi, bf.wi_lo, Fp, st));      // w_i^T [H][Fp]
-  RC(split_planes_transposed(params_d + am->off_output_w, H, C, C, bf.wo_hi, bf.wo_lo, H, st));      // w_o^T [C][H]
-  for (int l = 0; l < L; ++l) {
-    const float* K = params_d + am->off_kernel[l];
-    RC(pack_wrec(K, H, am->tc.U, bf.wx_hi[l], bf.wx_lo[l], st));                                     // K[:H]^T, rows in rec order
-    RC(pack_wrec(K + (size_t)H * 4 * H, H, am->tc.U, bf.wrec_hi[l], bf.wrec_lo[l], st));
+  // weight planes: re-packed when the parameters may have changed (every call unless the caller versions them:
+  // rs_am_set_params_version; 57 MB read, 8 launches at cfg-2)
+  if (!planes_cached(am, 0, params_d, ws_d)) {
+    RC(split_planes_transposed(params_d + am->off_input_w, F, H, H, bf.wi_hi, bf.wi_lo, Fp, st));      // w_i^T [H][Fp]
+    RC(split_planes_transposed(params_d + am->off_output_w, H, C, C, bf.wo_hi, bf.wo_lo, H, st));      // w_o^T [C][H]
+    for (int l = 0; l < L; ++l) {
+      const float* K = params_d + am->off_kernel[l];
+      RC(pack_wrec(K, H, am->tc.U, bf.wx_hi[l], bf.wx_lo[l], st));                                     // K[:H]^T, rows in rec order
+      RC(pack_wrec(K + (size_t)H * 4 * H, H, am->tc.U, bf.wrec_hi[l], bf.wrec_lo[l], st));
+    }
+    planes_packed(am, 0, params_d, ws_d);
   }
   // input dense -> xin[0] planes                                 (models/AcousticModel.py:247-250)
   RC(split_rows(x_d, TB, F, F, bf.x_hi, bf.x_lo, Fp, st));
@@ -384,7 +427,7 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
   }
 
   // ---- the recurrent stack as a wavefront over (layer, time chunk)
-  const Sched sc = make_sched(am, T);
+  const Sched sc = make_sched(am, T, true);
   const int NC = sc.NC;
   RC(ensure_streams(am));
   am->ev_next = 0;
@@ -403,15 +446,17 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     GemmTcOut o{};
     o.mode = GEMM_OUT_REC; o.C = bf.gx[l] + (size_t)t0 * 4 * H * am->tc.Bpad; o.bias = params_d + am->off_bias[l];
     o.recB = B; o.recBpad = am->tc.Bpad; o.recH = H; o.recU = am->tc.U;
-    o.max_ctas = sc.fwd_gemm_ctas; o.tiles_per_cta = sc.gx_tpc;
+    o.max_ctas = sc.phases ? 0 : sc.fwd_gemm_ctas; o.tiles_per_cta = sc.gx_tpc;
     RC(gemm_tc_nt(A, Bm, 4 * H, n * B, H, 3, o, am->gemm_st));
     return ev_record(am, &e_gx[(size_t)l * NC + c], am->gemm_st);
   };
+  cudaEvent_t e_phase = nullptr;           // phase schedule: the GEMM burst before the current wave has finished
   auto issue_rec = [&](int l, int c) -> int {
     const int t0 = sc.start[c], n = sc.start[c + 1] - sc.start[c];
     cudaStream_t ls = am->lane[l];
     RS_CHECK_CUDA(cudaStreamWaitEvent(ls, e_gx[(size_t)l * NC + c], 0));
-    if (NC > 1 && (int)done.size() >= am->window) RS_CHECK_CUDA(cudaStreamWaitEvent(ls, done[done.size() - am->window], 0));
+    if (sc.phases) { if (e_phase) RS_CHECK_CUDA(cudaStreamWaitEvent(ls, e_phase, 0)); }
+    else if (NC > 1 && (int)done.size() >= sc.window) RS_CHECK_CUDA(cudaStreamWaitEvent(ls, done[done.size() - sc.window], 0));
     float* cst = bf.run_state + ((size_t)l * 2 + 0) * B * H;
     float* hst = bf.run_state + ((size_t)l * 2 + 1) * B * H;
     RecTcFwdArgs a{};
@@ -424,11 +469,22 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     a.gates = bf.gates[l]; a.cs = bf.cs[l]; a.barrier = bf.barrier[l];
     a.T = n; a.t0 = t0; a.Ttot = T;
     a.dbg = (l == 0 && NC == 1) ? am->dbg_fwd : nullptr;
+    // the hop to the next consumer (dropout(s) of the cell output) is fused into the TMEM-resident kernel's epilogue
+    const bool fused_hop = hop_drop[l] && am->tc.ts && fuse_dropout();
+    a.drop_hi = nullptr; a.drop_lo = nullptr;
+    if (fused_hop) {
+      const bool last = l + 1 == L;
+      a.drop_hi = last ? bf.top_hi : bf.xin_hi[l + 1];
+      a.drop_lo = last ? bf.top_lo : bf.xin_lo[l + 1];
+      a.drop_key = splitmix64(seed);
+      a.drop_sa = (uint32_t)(2 * l + 1); a.drop_thr_a = drop_out ? thr24(keep_out) : 0xffffffffu; a.drop_inv_a = 1.0f / keep_out;
+      a.drop_sb = (uint32_t)(2 * (l + 1)); a.drop_thr_b = (!last && drop_in) ? thr24(keep_in) : 0xffffffffu; a.drop_inv_b = 1.0f / keep_in;
+    }
     RC(tev_record(am, 0, l, ls));
     if (am->tc.ts) RC(lstm_rec_ts_forward(am->tc, a, ls));
     else RC(lstm_rec_tc_forward(am->tc, a, ls));
     RC(tev_record(am, 0, l, ls));
-    if (hop_drop[l]) {
+    if (hop_drop[l] && !fused_hop) {
       // the hop to the next consumer: dropout(s) of h_t for the steps of this chunk
       const bool last = l + 1 == L;
       bf16 *d_hi = (last ? bf.top_hi : bf.xin_hi[l + 1]) + (size_t)t0 * B * H, *d_lo = (last ? bf.top_lo : bf.xin_lo[l + 1]) + (size_t)t0 * B * H;
@@ -442,6 +498,31 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     done.push_back(e);
     return RS_OK;
   };
+  if (sc.phases) {
+    // Waves: in wave d every layer l runs its chunk d - l (L launches side by side, L * nslice SMs); between two waves
+    // the chunk GEMMs the next wave needs run as one burst on the whole machine -- the gate pre-activations of layer 0's
+    // next chunk and of the chunks the layers above have just been handed.  The recurrent launches of a wave wait for the
+    // burst to end, so that all their CTAs find free SMs at once.
+    RC(issue_gemm(0, 0));
+    RC(ev_record(am, &e_phase, am->gemm_st));
+    for (int d = 0; d < NC + L - 1; ++d) {
+      for (int l = 0; l < L; ++l) {
+        const int c = d - l;
+        if (c >= 0 && c < NC) RC(issue_rec(l, c));
+      }
+      // the burst starts when the slowest launch of the wave has finished: GEMM CTAs must not take SMs from it
+      for (int l = 0; l < L; ++l) {
+        const int c = d - l;
+        if (c >= 0 && c < NC) RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_out[(size_t)l * NC + c], 0));
+      }
+      if (d + 1 < NC) RC(issue_gemm(0, d + 1));
+      for (int l = 1; l < L; ++l) {
+        const int c = d - (l - 1);
+        if (c >= 0 && c < NC) RC(issue_gemm(l, c));               // input = layer l - 1's chunk c of this wave
+      }
+      RC(ev_record(am, &e_phase, am->gemm_st));
+    }
+  } else {
   for (int c = 0; c < NC; ++c) RC(issue_gemm(0, c));               // layer 0's input is complete: no dependencies
   for (int d = 0; d < NC + L - 1; ++d)
     for (int l = 0; l < L; ++l) {
@@ -450,6 +531,7 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
       if (l > 0) RC(issue_gemm(l, c));
       RC(issue_rec(l, c));
     }
+  }
   for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(st, e_out[(size_t)l * NC + NC - 1], 0));
   if (state_out_d) RS_CHECK_CUDA(cudaMemcpyAsync(state_out_d, bf.run_state, state_n * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
@@ -477,11 +559,14 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   const bool drop_in = keep_in < 1.f, drop_out = keep_out < 1.f;
 
   // weights as stored (K-major for the "multiply by W^T" GEMMs)
-  RC(split_rows(params_d + am->off_output_w, H, C, C, bf.wos_hi, bf.wos_lo, Cp, st));
-  for (int l = 0; l < L; ++l) {
-    const float* K = params_d + am->off_kernel[l];
-    RC(split_planes(K, bf.wxs_hi[l], bf.wxs_lo[l], (int64_t)H * 4 * H, st));
-    RC(split_planes(K + (size_t)H * 4 * H, bf.whs_hi[l], bf.whs_lo[l], (int64_t)H * 4 * H, st));
+  if (!planes_cached(am, 1, params_d, ws_d)) {
+    RC(split_rows(params_d + am->off_output_w, H, C, C, bf.wos_hi, bf.wos_lo, Cp, st));
+    for (int l = 0; l < L; ++l) {
+      const float* K = params_d + am->off_kernel[l];
+      RC(split_planes(K, bf.wxs_hi[l], bf.wxs_lo[l], (int64_t)H * 4 * H, st));
+      RC(split_planes(K + (size_t)H * 4 * H, bf.whs_hi[l], bf.whs_lo[l], (int64_t)H * 4 * H, st));
+    }
+    planes_packed(am, 1, params_d, ws_d);
   }
   // where forward left each layer's input / the top activations
   const int hld = am->tc.ts ? 2 * H : H;
@@ -506,14 +591,14 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     o.mode = GEMM_OUT_F32; o.C = bf.din[L]; o.ldc = H;
     RC(gemm_tc_nt(A, Bm, TB, H, C, 3, o, st));
   }
-  const Sched sc = make_sched(am, T);
+  const Sched sc = make_sched(am, T, false);
   const int NC = sc.NC;
   RC(ensure_streams(am));
   am->ev_next = 0;
   cudaStream_t side = am->side;
   RS_CHECK_CUDA(cudaMemsetAsync(bf.elastic, 0, 4096 * sizeof(int), st));
   int elastic_next = 0;
-  const bool use_elastic = NC > 1 && !sc.cores && sc.side_tpc == 0 && 2 * L * NC + NC + 8 < 4096;
+  const bool use_elastic = NC > 1 && !sc.cores && !sc.phases && sc.side_tpc == 0 && 2 * L * NC + NC + 8 < 4096;
   cudaEvent_t e_fork;
   RC(ev_record(am, &e_fork, st));
   for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(am->lane[l], e_fork, 0));
@@ -539,24 +624,38 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   }
 
   std::vector<cudaEvent_t> e_rec((size_t)L * NC), e_dx((size_t)L * NC), done;
+  cudaEvent_t e_phase = nullptr;           // phase schedule: the dx burst before the current wave has finished
+  // phase schedule: weight-gradient GEMMs as short-lived CTAs (one tile each) on the lowest-priority stream -- they fill
+  // whatever SMs the waves leave idle (fill and drain of the wavefront, the 4 SMs beside three launches) and give
+  // them back within a tile's time when a wave starts
+  const int side_tpc = sc.phases ? (sc.side_tpc > 0 ? sc.side_tpc : 1) : sc.side_tpc;
   auto issue_rec = [&](int l, int c) -> int {
     const int t0 = sc.start[c], n = sc.start[c + 1] - sc.start[c];
     cudaStream_t ls = am->lane[l];
     if (l + 1 < L) RS_CHECK_CUDA(cudaStreamWaitEvent(ls, e_dx[(size_t)(l + 1) * NC + c], 0));
     // gradient wrt out_t of this layer: through the hop's dropout mask(s), in place
     float* dout = bf.din[l + 1];
-    if (hop_drop[l]) {
+    const bool fused_hop = hop_drop[l] && am->tc.ts && fuse_dropout();
+    if (hop_drop[l] && !fused_hop) {
       const bool last = l + 1 == L;
       float* dchunk = dout + (size_t)t0 * B * H;
       RC(dropout_f32(dchunk, dchunk, (int64_t)n * B * H, (int64_t)t0 * B * H, seed, drop_out ? 2 * l + 1 : -1, keep_out,
                      (!last && drop_in) ? 2 * (l + 1) : -1, keep_in, ls));
     }
-    if (NC > 1 && (int)done.size() >= am->window) RS_CHECK_CUDA(cudaStreamWaitEvent(ls, done[done.size() - am->window], 0));
+    if (sc.phases) { if (e_phase) RS_CHECK_CUDA(cudaStreamWaitEvent(ls, e_phase, 0)); }
+    else if (NC > 1 && (int)done.size() >= sc.window) RS_CHECK_CUDA(cudaStreamWaitEvent(ls, done[done.size() - sc.window], 0));
     RecTcBwdArgs a{};
     a.dout = dout; a.gates = bf.gates[l]; a.cs = bf.cs[l];
     a.c0 = bf.state0 + ((size_t)l * 2 + 0) * B * H;
     a.wh_hi = bf.whs_hi[l]; a.wh_lo = bf.whs_lo[l]; a.dg_hi = bf.dg_hi[l]; a.dg_lo = bf.dg_lo[l]; a.len = len_d; a.barrier = bf.barrier[l];
     a.T = n; a.t0 = t0; a.Ttot = T; a.dc_carry = NC > 1 ? bf.dc_carry[l] : nullptr;
+    a.drop_thr_a = a.drop_thr_b = 0xffffffffu;
+    if (fused_hop) {
+      const bool last = l + 1 == L;
+      a.drop_key = splitmix64(seed);
+      a.drop_sa = (uint32_t)(2 * l + 1); a.drop_thr_a = drop_out ? thr24(keep_out) : 0xffffffffu; a.drop_inv_a = 1.0f / keep_out;
+      a.drop_sb = (uint32_t)(2 * (l + 1)); a.drop_thr_b = (!last && drop_in) ? thr24(keep_in) : 0xffffffffu; a.drop_inv_b = 1.0f / keep_in;
+    }
     a.dbg = (l == 0 && NC == 1) ? am->dbg_bwd : nullptr;
     RC(tev_record(am, 1, l, ls));
     if (am->tc.ts) RC(lstm_rec_ts_backward(am->tc, a, ls));
@@ -575,7 +674,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     SplitMat A{bf.dg_hi[l] + (size_t)t0 * B * 4 * H, bf.dg_lo[l] + (size_t)t0 * B * 4 * H, n * B, 4 * H, 4 * H};
     SplitMat Bm{bf.wxs_hi[l], bf.wxs_lo[l], H, 4 * H, 4 * H};
     GemmTcOut o{};
-    o.mode = GEMM_OUT_F32; o.C = bf.din[l] + (size_t)t0 * B * H; o.ldc = H; o.max_ctas = sc.cores ? 0 : sc.gemm_ctas; o.tiles_per_cta = sc.dx_tpc; o.coresident = sc.cores;
+    o.mode = GEMM_OUT_F32; o.C = bf.din[l] + (size_t)t0 * B * H; o.ldc = H; o.max_ctas = (sc.cores || sc.phases) ? 0 : sc.gemm_ctas; o.tiles_per_cta = sc.dx_tpc; o.coresident = sc.cores;
     RC(tev_record(am, 3, l, am->gemm_st));
     RC(gemm_tc_nt(A, Bm, n * B, H, 4 * H, 3, o, am->gemm_st));
     RC(tev_record(am, 3, l, am->gemm_st));
@@ -600,14 +699,14 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
       {
         SplitMat A{in_hi[l] + r0 * in_ld[l], in_lo[l] + r0 * in_ld[l], nb, H, in_ld[l]};
         GemmTcOut o{};
-        o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas; o.tiles_per_cta = sc.side_tpc;
+        o.mode = GEMM_OUT_F32; o.C = gK; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas; o.tiles_per_cta = side_tpc;
         if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
         RC(gemm_tc_tn(A, G, H, 4 * H, nb, 3, o, side));
       }
       {
         SplitMat A{bf.hp_hi[l] + r0 * hld, bf.hp_lo[l] + r0 * hld, nb, H, hld};       // slots t0..t0+n-1 = h_{t-1}
         GemmTcOut o{};
-        o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas; o.tiles_per_cta = sc.side_tpc;
+        o.mode = GEMM_OUT_F32; o.C = gK + (size_t)H * 4 * H; o.ldc = 4 * H; o.accumulate = 1; o.max_ctas = sc.side_ctas; o.tiles_per_cta = side_tpc;
         if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
         RC(gemm_tc_tn(A, G, H, 4 * H, nb, 3, o, side));
       }
@@ -667,7 +766,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
       RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_in, 0));
       SplitMat A{bf.x_hi + r0 * Fp, bf.x_lo + r0 * Fp, nb, F, Fp}, Bm{dr_hi, dr_lo, nb, H, H};
       GemmTcOut o{};
-      o.mode = GEMM_OUT_F32; o.C = grads_d + am->off_input_w; o.ldc = H; o.accumulate = 1; o.max_ctas = sc.side_ctas;
+      o.mode = GEMM_OUT_F32; o.C = grads_d + am->off_input_w; o.ldc = H; o.accumulate = 1; o.max_ctas = sc.side_ctas; o.tiles_per_cta = side_tpc;
       if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
       return gemm_tc_tn(A, Bm, F, H, nb, 3, o, side);
     }
@@ -685,6 +784,32 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
     return gemm_tc_nt(A, Bm, F, H, nb, 3, o, side);
   };
+  if (sc.phases) {
+    // Waves of L recurrent launches (layer l runs chunk NC-1 - (d - (L-1-l)) in wave d); between two waves ONE burst of
+    // the dx GEMMs the next wave needs on the whole machine.  The weight-gradient GEMMs of a wave are queued behind it
+    // on the lowest-priority stream.
+    for (int d = 0; d < NC + L - 1; ++d) {
+      for (int l = L - 1; l >= 0; --l) {
+        const int c = NC - 1 - (d - (L - 1 - l));
+        if (c >= 0 && c < NC) RC(issue_rec(l, c));
+      }
+      for (int l = L - 1; l >= 0; --l) {
+        const int c = NC - 1 - (d - (L - 1 - l));
+        if (c >= 0 && c < NC) RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_rec[(size_t)l * NC + c], 0));
+      }
+      for (int l = L - 1; l >= 0; --l) {
+        const int c = NC - 1 - (d - (L - 1 - l));
+        if (c >= 0 && c < NC) RC(issue_dx(l, c));
+      }
+      RC(ev_record(am, &e_phase, am->gemm_st));
+      for (int l = L - 1; l >= 0; --l) {
+        const int c = NC - 1 - (d - (L - 1 - l));
+        if (c < 0 || c >= NC) continue;
+        RC(issue_side(l, c));
+        if (l == 0) RC(issue_input(c));
+      }
+    }
+  } else
   for (int d = 0; d < NC + L - 1; ++d)
     for (int l = L - 1; l >= 0; --l) {
       const int c = NC - 1 - (d - (L - 1 - l));

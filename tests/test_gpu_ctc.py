@@ -157,6 +157,33 @@ def test_beam_search_matches_the_tf_restatement(pkg, cuda, T, B, C, W, scale, me
         assert np.all(ids[b, n[b]:] == -1)
 
 
+@pytest.mark.parametrize("W,C", [(8, 6), (100, 80)])
+def test_beam_search_with_exactly_tied_scores(pkg, cuda, W, C):
+    """Frames whose logits are small integers give MANY extensions exactly the same total: the selection has to cut the
+    tie at the beam boundary by candidate id (the radix select's id digits), stay within the beam width, and still
+    return a path whose score is the oracle's best (which labels win a tie is unspecified in TF)."""
+    T, B = 30, 4
+    rng = np.random.default_rng(W + C)
+    logits = rng.integers(0, 3, size=(T, B, C)).astype(np.float32)
+    logits[5:9] = 0.0                                                    # completely flat frames
+    lens = np.array([T, T - 3, T, 11], np.int32)
+    m = _model(pkg, cuda, B, T, C)
+    runs = []
+    for _ in range(2):
+        ids, n, score = m.beam_search_decode(torch.from_numpy(logits).to(cuda), torch.from_numpy(lens).to(cuda),
+                                             beam_width=W, merge_repeated=True)
+        runs.append((ids.cpu().numpy(), n.cpu().numpy(), score.cpu().numpy()))
+    np.testing.assert_array_equal(runs[0][0], runs[1][0])               # deterministic whatever the thread timing
+    ids, n, score = runs[0]
+    _, want_score = ctc.beam_search_decode(logits, lens, beam_width=W, merge_repeated=True)
+    for b in range(B):
+        assert np.isfinite(score[b]) and 0 <= n[b] <= lens[b]
+        if W >= 100:
+            # a wide beam holds every prefix that matters: the best total does not depend on how ties were cut
+            assert abs(score[b] - want_score[b]) < 1e-3 * max(1.0, abs(want_score[b]))
+        assert np.all(ids[b, n[b]:] == -1) and np.all((ids[b, :n[b]] >= 0) & (ids[b, :n[b]] < C - 1))
+
+
 def test_beam_search_full_size_and_process_input(pkg, cuda):
     """cfg-2 sized logits (T=998, B=32, C=80): runs, agrees with greedy decoding on peaky outputs (where the best
     labelling is the best path), and one item is checked against the restatement on its first 150 frames."""

@@ -1,0 +1,100 @@
+"""Realistic-weight parity (SURVEY 8c "golden weights"): the reference's shipped 3x1024 model
+(trained_models/english/acoustic/, restored as models/AcousticModel.py:489-499 does) on speech-like synthetic audio --
+logits, greedy label ids and beam-search ids against the float64 oracle.  Trained weights give PEAKED posteriors, the
+realistic case for "bit-exact greedy labels"; the other model tests use Xavier weights (flat posteriors).
+
+The weights are a local fixture (tools/extract_trained_weights.py -> tests/golden/_local/, git-ignored, shipped to the GPU
+box with the snapshot); the test skips when it is absent.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import ctc, model
+
+pytestmark = pytest.mark.gpu
+FIXTURE = os.path.join(GOLDEN, "_local", "trained_3x1024.npz")
+MARGIN = 1e-3
+
+
+def _speechlike(rng, seconds, sr):
+    """Voiced segments (a harmonic stack under a moving two-formant envelope) separated by pauses, plus noise."""
+    n = int(seconds * sr)
+    t = np.arange(n) / sr
+    f0 = 110.0 + 30.0 * np.sin(2 * np.pi * 0.7 * t + rng.uniform(0, 6.28))
+    phase = 2 * np.pi * np.cumsum(f0) / sr
+    sig = np.zeros(n)
+    f1 = 500 + 250 * np.sin(2 * np.pi * 1.3 * t + rng.uniform(0, 6.28))
+    f2 = 1500 + 600 * np.sin(2 * np.pi * 0.9 * t + rng.uniform(0, 6.28))
+    for k in range(1, 30):
+        fk = k * f0
+        gain = np.exp(-((fk - f1) / 180.0) ** 2) + 0.6 * np.exp(-((fk - f2) / 300.0) ** 2) + 0.02
+        sig += gain * np.sin(k * phase)
+    syll = (np.sin(2 * np.pi * 3.1 * t + rng.uniform(0, 6.28)) > -0.2).astype(np.float64)
+    env = np.convolve(syll, np.hanning(int(0.03 * sr)), mode="same")
+    env /= max(env.max(), 1e-9)
+    sig = 0.08 * sig * env + 0.004 * rng.standard_normal(n)
+    return sig.astype(np.float32)
+
+
+def test_shipped_3x1024_model_forward_greedy_beam(pkg, cuda):
+    if not os.path.exists(FIXTURE):
+        pytest.skip("tests/golden/_local/trained_3x1024.npz absent (python tools/extract_trained_weights.py)")
+    from parity_util import keep_artifact, tie_report
+    w = np.load(FIXTURE)
+    L, H, F, C = 3, 1024, 120, 80
+    p = {"input_w": w["Input_Layer/input_w"], "input_b": w["Input_Layer/input_b"],
+         "output_w": w["Output_layer/output_w"], "output_b": w["Output_layer/output_b"]}
+    for l in range(L):
+        p["kernel_%d" % l] = w["rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % l]
+        p["bias_%d" % l] = w["rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/bias" % l]
+    assert p["kernel_0"].shape == (2 * H, 4 * H) and int(w["global_step"]) == 67600
+    flat = model.flatten(p, L, H, F, C)
+    rng = np.random.default_rng(2024)
+    sr, B, Tmax = 22050, 4, 320                     # librosa.load's rate: the rate the model was trained at
+    sigs = [_speechlike(rng, s, sr) for s in (3.0, 2.4, 2.8, 1.7)]
+    ap = pkg.AudioProcessor(Tmax, "fbank", device=cuda)
+    feats, nframes = ap.process_batch(sigs, sr, time_major=True)
+    lens = nframes.cpu().numpy()
+    T = int(lens.max())
+    x = feats[:T].contiguous()
+    m = pkg.AcousticModel(L, H, B, T, 600, F, False, C, device=cuda)
+    m.create_forward_rnn()
+    m.load_flat_params(flat)
+    assert m.uses_tensor_cores
+    logits = m.forward(x, nframes, training=False, keep_state=False)
+    want, _, _ = model.forward(p, x.cpu().numpy(), lens, L, H, keep_cache=False)
+    got = logits.cpu().numpy()
+    err = float(np.abs(got - want).max())
+    frames, ties, mism = tie_report(got, want, lens, MARGIN)
+    # how peaked the posteriors are: mean probability of the arg-max class over the valid frames
+    prob = np.exp(want - want.max(-1, keepdims=True))
+    prob /= prob.sum(-1, keepdims=True)
+    valid = np.arange(T)[:, None] < lens[None, :]
+    peak = float(prob.max(-1)[valid].mean())
+    ids, n = m.greedy_decode(logits, nframes)
+    ref = ctc.greedy_decode(want, lens)
+    greedy_same = 0
+    for b in range(B):
+        same = list(ids[b, :int(n[b])].cpu().numpy()) == list(ref[b])
+        greedy_same += int(same)
+    bids, bn, bscore = m.beam_search_decode(logits, nframes)
+    wids, wscore = ctc.beam_search_decode(want.astype(np.float32), lens)
+    beam_same = sum(int(list(bids[b, :int(bn[b])].cpu().numpy()) == list(wids[b])) for b in range(B))
+    texts = [pkg.get_labels_str(pkg.ENGLISH_CHAR_MAP, list(wids[b])) for b in range(B)]
+    report = {"max_abs_logit_err": err, "frames": frames, "near_tie_frames": ties, "argmax_mismatches": mism,
+              "mean_top_probability": peak, "greedy_rows_identical": greedy_same, "beam_rows_identical": beam_same,
+              "beam_score_gpu": [float(v) for v in bscore.cpu().numpy()], "beam_score_oracle": [float(v) for v in wscore],
+              "decoded_text_oracle_beam": texts}
+    print("shipped 3x1024 model: max |logit err| %.2e over %d frames (%d near ties, %d argmax mismatches), mean top "
+          "probability %.3f, greedy rows identical %d/%d, beam rows identical %d/%d" %
+          (err, frames, ties, mism, peak, greedy_same, B, beam_same, B))
+    keep_artifact("r02_trained_weight_parity.json", report)
+    assert err < 2e-3 and mism == 0
+    if ties == 0:
+        assert greedy_same == B
+    for b in range(B):
+        assert abs(float(bscore[b]) - float(wscore[b])) < 2e-3 * max(1.0, abs(float(wscore[b])))
