@@ -281,8 +281,11 @@ int rs_comm_init(void** comm_out, const void* unique_id, size_t id_bytes, int ra
 int rs_allreduce_sum(void* comm, float* buf_d, int64_t n, void* stream);
 void rs_comm_destroy(void* comm);
 
+#ifdef RS_DIAG
 /* ------------------------------------------------------------------------
- * Self-test of the tcgen05 / TMEM / descriptor plumbing (used by the GPU tests):
+ * Diagnostics: NOT part of the product library.  These hooks exist only in librnnspeech_b200_diag.so (the same
+ * sources built with -DRS_DIAG; rnn-speech_b200/build.py builds both), which the GPU tests and tests/gpu_diag.py load.
+ * Self-test of the tcgen05 / TMEM / descriptor plumbing:
  * D[128,N] = A[128,K] * B[N,K]^T on one CTA; split != 0 uses the bf16x3 split.
  * ------------------------------------------------------------------------ */
 int rs_tc_selftest(const float* A_d, const float* B_d, float* D_d, int N, int K, int split, void* stream);
@@ -305,6 +308,8 @@ int rs_gemm_tc_test(const float* A_d, const float* B_d, const float* bias_d, flo
 int rs_gemm_tc_bench(const float* A_d, const float* B_d, float* C_d, int M, int N, int K, int products,
                      int bn, int max_ctas, int tiles_per_cta, int accumulate, int reps, void* scratch_d,
                      size_t scratch_bytes, float* ms_out, void* stream);
+
+#endif /* RS_DIAG */
 
 #ifdef __cplusplus
 }

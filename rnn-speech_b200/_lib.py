@@ -85,13 +85,6 @@ SIGNATURES = {
     "rs_ctc_beam_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
     "rs_edit_distance": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "rs_tc_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "rs_tc_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "rs_tc_ts_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "rs_gemm_tc_test": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
-                                c_void_p]),
-    "rs_gemm_tc_bench": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                 c_int, c_void_p, c_size_t, POINTER(c_float), c_void_p]),
     "rs_accumulate_mean": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "rs_memset_zero": (c_int, [c_void_p, c_size_t, c_void_p]),
     "rs_memcpy_h2d_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -103,6 +96,46 @@ SIGNATURES = {
     "rs_clip_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
                                   c_float, c_float, c_float, c_int64, c_void_p]),
 }
+
+# Diagnostic hooks (self-tests, micro-benchmarks): only in librnnspeech_b200_diag.so, loaded on demand by the tests.
+DIAG_LIB_PATH = os.path.join(_HERE, "librnnspeech_b200_diag.so")
+DIAG_SIGNATURES = {
+    "rs_tc_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rs_tc_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rs_tc_ts_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rs_gemm_tc_test": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
+                                c_void_p]),
+    "rs_gemm_tc_bench": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_void_p, c_size_t, POINTER(c_float), c_void_p]),
+}
+_diag = None
+
+
+def diag():
+    """The diagnostic build of the library (the product library + the RS_DIAG hooks)."""
+    global _diag
+    if _diag is None:
+        if not os.path.exists(DIAG_LIB_PATH):
+            raise ImportError("librnnspeech_b200_diag.so is missing (python rnn-speech_b200/build.py)")
+        lib = ctypes.CDLL(DIAG_LIB_PATH)
+        for name, (res, args) in DIAG_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        lib.rs_last_error.restype = c_char_p
+        _diag = lib
+    return _diag
+
+
+def diag_call(name, *args):
+    """Call a status-returning diagnostic hook and raise on failure."""
+    lib = diag()
+    code = getattr(lib, name)(*args)
+    if code != RS_OK:
+        msg = lib.rs_last_error()
+        raise RnnSpeechError(code, msg.decode("utf-8", "replace") if msg else "")
+    return code
+
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(_lib, _name)          # AttributeError here == symbol missing from the .so

@@ -13,6 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librnnspeech_b200.so")
+LIB_DIAG = os.path.join(HERE, "librnnspeech_b200_diag.so")      # + the diagnostic hooks (-DRS_DIAG), for tests only
+DIAG_SOURCES = ("tc_selftest.cu", "gemm_tc.cu")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -36,7 +38,8 @@ def _digest():
 
 def build(force=False, verbose=False):
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
+    if not force and os.path.exists(LIB) and os.path.exists(LIB_DIAG) and os.path.exists(STAMP) \
+            and open(STAMP).read().strip() == digest:
         return LIB
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     objs = []
@@ -46,6 +49,12 @@ def build(force=False, verbose=False):
         objs.append(obj)
         cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    diag_objs = {}
+    for name in DIAG_SOURCES:
+        obj = os.path.join(HERE, "build", "diag_" + name[:-3] + ".o")
+        diag_objs[name[:-3] + ".o"] = obj
+        cmd = [NVCC] + FLAGS + ["-DRS_DIAG", "-c", os.path.join(CSRC, name), "-o", obj]
+        procs.append((name + " (diag)", subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False
     for src, p in procs:
@@ -60,6 +69,10 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed, see rnn-speech_b200/build/nvcc.log")
     cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+    subprocess.check_call(cmd)
+    # the diagnostic library: the same objects, with the two translation units that carry hooks rebuilt with -DRS_DIAG
+    dobjs = [diag_objs.get(os.path.basename(o), o) for o in objs]
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_DIAG] + dobjs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     with open(STAMP, "w") as fh:
         fh.write(digest)

@@ -122,6 +122,7 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
         h = (h + 1) & (kHash - 1);
       }
     }
+    __syncthreads();
     // ---- 2. update the entries
     float my_tot = kNegInf;
     if (tid < n) {
@@ -143,7 +144,8 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
         nl += in[lab];
       }
       const float nb = old_tot[tid] + in[blank];
-      const float nt = lse2f(nb, nl);
+      float nt = lse2f(nb, nl);
+      if (!(nt == nt)) nt = kNegInf;      // NaN logits (a diverged model): keep the order total, the kernel memory-safe
       bm.lab[tid] = nl; bm.blk[tid] = nb; bm.tot[tid] = nt;
       ckey[tid] = nt; cid[tid] = tid;
       my_tot = nt;

@@ -609,6 +609,7 @@ int rowsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int R, int C
 
 using namespace rs;
 
+#ifdef RS_DIAG   // test / measurement hooks: in librnnspeech_b200_diag.so only
 // Test hook: C[M,N] = A[M,K] * B[N,K]^T (+bias) from fp32 inputs; scratch_d must hold
 // 2*(M*Kp + N*Kp) bf16 with Kp = K rounded up to 8.
 // products >= 16 selects the MN-major form (A_d is [K][M], B_d is [K][N], M and N multiples of 8; products - 16 = 1 | 3).
@@ -687,3 +688,4 @@ extern "C" int rs_gemm_tc_bench(const float* A_d, const float* B_d, float* C_d, 
   cudaEventDestroy(e1);
   return RS_OK;
 }
+#endif  // RS_DIAG

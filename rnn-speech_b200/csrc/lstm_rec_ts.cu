@@ -481,6 +481,256 @@ rec_ts_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------
+// Forward, two chains.  The utterances of a mini-batch never interact inside the recurrence, so a batch of 17..32 is
+// run as TWO independent recurrences over 16 rows each (chain X = batch rows [16X, 16X + 16)) that share the CTA's
+// resident weights: each chain has its own producer warp, MMA warp, four epilogue warps, accumulator columns, shared
+// memory slot, mbarriers and grid-barrier counter.  A step of one chain is the same dependent sequence as before
+// (counter seen -> TMA box -> 48 MMAs -> epilogue -> publish -> release), but while one chain waits for its exchange
+// through L2 (~60 % of a step) the other one computes: the tensor pipe, the TMA unit and the epilogue issue slots are
+// idle most of a step in the one-chain kernel.  Per chain N = 2 x 16 (hi | lo planes of 16 rows), its box is 48 KB.
+// Requires Bpad == 32 and one TMA group per step (all of K in one box); other shapes use rec_ts_fwd_kernel.
+// ------------------------------------------------------------------------------------
+constexpr int NTHREADS2 = 384;   // warps 0-3 / 4-7: epilogue of chain 0 / 1; 8, 9: TMA + MMA of chain 0; 10, 11: of chain 1
+constexpr int CHB = 16;          // batch rows per chain
+
+struct KFwd2 {
+  RecTcFwdArgs a;
+  int H, B, nslice, nkb, nkb_t;
+  int rows1;                      // valid batch rows of chain 1 (B - 16)
+};
+
+__device__ __forceinline__ void chain_bar_sync(int chain) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + chain) : "memory");
+}
+
+template <int HH>
+__global__ void __launch_bounds__(NTHREADS2, 1)
+rec_ts_fwd2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmS0,
+                   const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmD0,
+                   const __grid_constant__ CUtensorMap tmD1, KFwd2 p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[2], tfull_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(128) __nv_bfloat16 sH[2][CHB][2][TSU];       // staged h_t per chain [b][plane][unit]
+  __shared__ __align__(128) __nv_bfloat16 sD[2][CHB][2][TSU];       // staged dropout(out_t) per chain
+  const RecTcFwdArgs& a = p.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x;
+  const int H = HH > 0 ? HH : p.H, B = p.B, T = a.T;
+  const int nkb = HH > 0 ? HH / 64 : p.nkb, nkb_t = HH > 0 ? HH / 64 : p.nkb_t, nslice = HH > 0 ? HH / TSU : p.nslice;
+  const int nkb_s = nkb - nkb_t;
+  constexpr uint32_t kb_bytes = 2u * CHB * 128u;                     // one K-block of a chain: hi rows, lo rows
+  const uint32_t slot_bytes = (uint32_t)nkb * kb_bytes;
+  unsigned char* sA = smem;                                          // [nkb_s][128 rows x 128 B] weight blocks outside TMEM
+  unsigned char* sRing = smem + (size_t)nkb_s * 16384;               // [2 chains][nkb][2 planes][16 rows x 128 B]
+  const uint32_t colD = (uint32_t)nkb_t * 32;
+
+  if (threadIdx.x == 0) {
+    for (int x = 0; x < 2; ++x) { tc::mbar_init(&full_bar[x], 1); tc::mbar_init(&tfull_bar[x], 1); }
+    tc::fence_mbar_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    // resident weights, as in rec_ts_fwd_kernel: TMEM lane = threadIdx.x; gate row 16q + (lane & 15), hi plane for lane < 16
+    const int row = j * 64 + 16 * warp + (lane & 15);
+    const __nv_bfloat16* src = ((lane < 16) ? a.wrec_hi : a.wrec_lo) + (size_t)row * H;
+    for (int c0 = 0; c0 < nkb_t * 32; c0 += 8) {
+      const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0));
+      const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0 + 8));
+      const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      tc::tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+    }
+    for (int kb = nkb_t; kb < nkb; ++kb) {
+      unsigned char* tile = sA + (size_t)(kb - nkb_t) * 16384 + (size_t)threadIdx.x * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(tile + ((c ^ (threadIdx.x & 7)) << 4)) = __ldg(reinterpret_cast<const uint4*>(src + kb * 64 + c * 8));
+    }
+    tc::tmem_st_wait();
+    tc::fence_proxy_async_smem();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+
+  if (warp == 8 || warp == 10) {
+    // ------------------------------------------------------------------ TMA producer of chain X
+    const int X = (warp - 8) >> 1;
+    if (lane == 0) tc::tma_prefetch_desc(&tmH);
+    __syncwarp();
+    const unsigned per_step = gridDim.x * 2u;                        // every CTA adds CHB / 8 per chain and step
+    const unsigned* ctr = a.barrier + 32 * X;
+    for (int ti = 0; ti < T; ++ti) {
+      const int t = a.t0 + ti;
+      if (ti > 0) {
+        while (ld_relaxed_u32(ctr) < per_step * (unsigned)ti) {}
+        __syncwarp();
+      }
+      tc::mbar_arrive_expect_tx_warp(&full_bar[X], slot_bytes);
+      // one box = nkb stacked tiles [kb][plane][16 rows][64]; row t*B + 16X = h_{t-1} of the chain's first utterance
+      tc::tma_load_4d_warp(sRing + (size_t)X * slot_bytes, &tmH, 0, t * B + CHB * X, 0, 0, &full_bar[X]);
+    }
+  } else if (warp == 9 || warp == 11) {
+    // ------------------------------------------------------------------ MMA issuer of chain X (converged warp)
+    const int X = (warp - 9) >> 1;
+    const uint32_t idesc = tc::instr_desc_bf16(128, 2 * CHB);
+    const uint64_t dA0 = tc::smem_desc_sw128(tc::smem_u32(sA));
+    const uint64_t dB0 = tc::smem_desc_sw128(tc::smem_u32(sRing + (size_t)X * slot_bytes));
+    constexpr uint64_t kb_u = kb_bytes >> 4;
+    const uint32_t tmemD = tmem + colD + (uint32_t)(2 * CHB * X);
+    for (int t = 0; t < T; ++t) {
+      tc::mbar_wait(&full_bar[X], (uint32_t)(t & 1));
+      tc::tc_fence_after();
+      issue_ts_blocks<12>(nkb_t, tmemD, tmem, dB0, kb_u, idesc, 0u);                                       // 12: H = 768
+      for (int kb = nkb_t; kb < nkb; ++kb)
+        tc::mma4_bf16_ss_warp(tmemD, dA0 + (uint64_t)(kb - nkb_t) * (16384 >> 4), dB0 + (uint64_t)kb * kb_u, idesc, (uint32_t)(kb != 0));
+      tc::mma_commit_warp(&tfull_bar[X]);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps of chain X = warp >> 2
+    const int q = warp & 3, X = warp >> 2, l16 = lane & 15, up = lane >> 4;
+    const int m = q * 16 + l16;                 // gate row (hi copy in lanes 0..15, lo copy in 16..31)
+    const int g = lane & 3;                     // gate of this row: 0 i, 1 j, 2 f, 3 o
+    const int ul = m >> 2;                      // unit inside the slice
+    const int unit = j * TSU + ul;
+    const uint32_t tmemD = tmem + colD + (uint32_t)(2 * CHB * X) + ((uint32_t)(q * 32) << 16);
+    const bool leader = (threadIdx.x & 127) == 0;
+    const CUtensorMap* tmS = X ? &tmS1 : &tmS0;
+    const CUtensorMap* tmD = X ? &tmD1 : &tmD0;
+    unsigned* ctr = a.barrier + 32 * X;
+    float c[2], hl[2];
+    int lenr[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int b = X * CHB + 8 * up + 2 * g + k;
+      const bool ok = b < B;
+      c[k] = ok ? a.c0[(size_t)b * H + unit] : 0.f;
+      hl[k] = ok ? a.h0[(size_t)b * H + unit] : 0.f;
+      lenr[k] = ok ? a.len[b] : 0;
+    }
+    const float fbias = (g == 2) ? 1.0f : 0.0f;          // forget_bias
+    const float pre = (g == 1) ? 2.0f : 1.0f;            // tanh(x) = 2*sigmoid(2x) - 1
+    const float post_m = (g == 1) ? 2.0f : 1.0f, post_a = (g == 1) ? -1.0f : 0.0f;
+    float2* blob = reinterpret_cast<float2*>(a.gates);
+
+    for (int ti = 0; ti < T; ++ti) {
+      const int t = a.t0 + ti;
+      // hoisted input projection for this step (independent of the recurrence: issue early); Bpad = 32, group X
+      const float4* gp = reinterpret_cast<const float4*>(a.gx + (((size_t)t * nslice + j) * 64 + m) * 32 + X * 16 + 8 * up);
+      const float4 gx0 = __ldg(gp), gx1 = __ldg(gp + 1);
+      tc::mbar_wait(&tfull_bar[X], (uint32_t)(ti & 1));
+      tc::tc_fence_after();
+      float v[16], w[16];
+      tc::tmem_ld16(tmemD, v);                               // hi rows: W_hi h_hi ; lo rows: W_lo h_hi
+      tc::tmem_ld16(tmemD + (uint32_t)CHB, w);               // hi rows: W_hi h_lo
+      tc::tmem_ld_wait();
+      float act[8];
+      const float xs[8] = {gx0.x, gx0.y, gx0.z, gx0.w, gx1.x, gx1.y, gx1.z, gx1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float s_a = v[i] + w[i], s_b = v[8 + i] + w[8 + i];
+        const float got = __shfl_xor_sync(0xffffffffu, up ? v[i] : s_b, 16);
+        const float z = ((up ? (got + v[8 + i]) : (s_a + got)) + xs[i] + fbias) * pre;
+        act[i] = fmaf(fast_sigmoid(z), post_m, post_a);
+      }
+      float own[2], rcv[3][2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) own[k] = pick4(g, act[k], act[2 + k], act[4 + k], act[6 + k]);
+#pragma unroll
+      for (int d = 1; d < 4; ++d)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float snd = pick4(g ^ d, act[k], act[2 + k], act[4 + k], act[6 + k]);
+          rcv[d - 1][k] = __shfl_xor_sync(0xffffffffu, snd, d);
+        }
+      float2 keep[BLOB_ITEMS];
+      float gv[4][2], cn[2], hout[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float ig = pick4(g ^ 0, own[k], rcv[0][k], rcv[1][k], rcv[2][k]);
+        const float jg = pick4(g ^ 1, own[k], rcv[0][k], rcv[1][k], rcv[2][k]);
+        const float fg = pick4(g ^ 2, own[k], rcv[0][k], rcv[1][k], rcv[2][k]);
+        const float og = pick4(g ^ 3, own[k], rcv[0][k], rcv[1][k], rcv[2][k]);
+        const int bl = 8 * up + 2 * g + k;                   // row inside the chain
+        const float c_new = c[k] * fg + ig * jg;
+        const float h_new = fast_tanh(c_new) * og;
+        const bool valid = t < lenr[k];
+        if (valid) { c[k] = c_new; hl[k] = h_new; }
+        __nv_bfloat16 hh, hlo;
+        tc::split_bf16(valid ? h_new : 0.f, hh, hlo);
+        sH[X][bl][0][ul] = hh;
+        sH[X][bl][1][ul] = hlo;
+        hout[k] = valid ? h_new : 0.f;
+        gv[0][k] = ig; gv[1][k] = jg; gv[2][k] = fg; gv[3][k] = og; cn[k] = c_new;
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) keep[it] = make_float2(gv[it][0], gv[it][1]);
+      keep[4] = make_float2(cn[0], cn[1]);
+      tc::tc_fence_before();
+      tc::fence_proxy_async_smem();
+      // (the chain's leader arrives after its earlier bulk groups -- the hop store of step t-1 -- have read sD)
+      if (a.drop_hi && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      chain_bar_sync(X);
+      if (leader) {
+        // publish the chain's h_t (both planes) with one TMA store; completion of the bulk group + a release on the
+        // chain's counter (see ts_variant(): the writer side of the exchange protocol)
+        tc::tma_store_3d(tmS, &sH[X][0][0][0], j * TSU, 0, (t + 1) * B + CHB * X);
+        tc::bulk_commit();
+        tc::bulk_wait_all();
+        if (ti + 1 < T) {
+          tc::fence_proxy_async_global();
+          red_release_add(ctr, 2u);
+        }
+      }
+      // reserve for backward (not on the critical path of the recurrence)
+      if (blob) {
+#pragma unroll
+        for (int it = 0; it < BLOB_ITEMS; ++it) blob[blob_idx(t, nslice, j, 1, 0, it, warp, lane)] = keep[it];
+      }
+      // fused hop: dropout(out_t) planes for the next layer / the output dense
+      if (a.drop_hi) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int bl = 8 * up + 2 * g + k;
+          float dv = hout[k];
+          const unsigned long long idx = ((unsigned long long)t * B + (X * CHB + bl)) * H + unit;
+          if (a.drop_thr_a != 0xffffffffu) dv = dropout_keep(a.drop_key, a.drop_sa, idx, a.drop_thr_a) ? dv * a.drop_inv_a : 0.f;
+          if (a.drop_thr_b != 0xffffffffu) dv = dropout_keep(a.drop_key, a.drop_sb, idx, a.drop_thr_b) ? dv * a.drop_inv_b : 0.f;
+          __nv_bfloat16 dh_, dl_;
+          tc::split_bf16(dv, dh_, dl_);
+          sD[X][bl][0][ul] = dh_;
+          sD[X][bl][1][ul] = dl_;
+        }
+        tc::fence_proxy_async_smem();
+        chain_bar_sync(X);
+        if (leader) {
+          tc::tma_store_3d(tmD, &sD[X][0][0][0], j * TSU, 0, t * B + CHB * X);
+          tc::bulk_commit();
+        }
+      }
+    }
+    if (a.drop_hi && leader) tc::bulk_wait_all();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int b = X * CHB + 8 * up + 2 * g + k;
+      if (b < B) {
+        if (a.cT) a.cT[(size_t)b * H + unit] = c[k];
+        if (a.hT) a.hT[(size_t)b * H + unit] = hl[k];
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------
 struct KBwd {
@@ -886,6 +1136,42 @@ int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a_in, cudaStream
   CUtensorMap th, ts;
   int rc;
   const int hrows = (a.Ttot + 1) * g.B;
+  // two independent 16-row chains per CTA (rec_ts_fwd2_kernel) when the batch allows it; RS_TS_CHAINS=0: one chain
+  static const bool chains_env = [] { const char* v = getenv("RS_TS_CHAINS"); return !(v && v[0] == '0'); }();
+  if (chains_env && !a.dbg && ts_variant() == kDefaultVariant && g.Bpad == 32 && g.B > CHB && g.gkb == g.H / 64 && g.stages == 1) {
+    CUtensorMap ts0, ts1, td0, td1;
+    if ((rc = tmap_stacked_bf16(&th, a.h_hi, hrows, g.H, CHB, g.gkb)) != RS_OK) return rc;
+    if ((rc = tmap_store3_bf16(&ts0, a.h_hi, g.H, 2, hrows, (size_t)g.H * 2, (size_t)2 * g.H * 2, TSU, 2, CHB)) != RS_OK) return rc;
+    if ((rc = tmap_store3_bf16(&ts1, a.h_hi, g.H, 2, hrows, (size_t)g.H * 2, (size_t)2 * g.H * 2, TSU, 2, g.B - CHB)) != RS_OK) return rc;
+    td0 = ts0; td1 = ts1;
+    if (a.drop_hi) {
+      RS_REQUIRE(a.drop_lo > a.drop_hi, RS_ERR_INVALID, "lstm_rec_ts_forward: the low hop plane must follow the high one");
+      const size_t pstride = (size_t)((const char*)a.drop_lo - (const char*)a.drop_hi);
+      if ((rc = tmap_store3_bf16(&td0, a.drop_hi, g.H, 2, a.Ttot * g.B, pstride, (size_t)g.H * 2, TSU, 2, CHB)) != RS_OK) return rc;
+      if ((rc = tmap_store3_bf16(&td1, a.drop_hi, g.H, 2, a.Ttot * g.B, pstride, (size_t)g.H * 2, TSU, 2, g.B - CHB)) != RS_OK) return rc;
+    }
+    KFwd2 p2;
+    p2.a = a;
+    p2.H = g.H; p2.B = g.B; p2.nslice = g.nslice; p2.nkb = g.H / 64; p2.nkb_t = g.nkb_t; p2.rows1 = g.B - CHB;
+    RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
+    const bool fast2 = g.H == 768 && g.nkb_t == 12;
+    auto kern2 = fast2 ? rec_ts_fwd2_kernel<768> : rec_ts_fwd2_kernel<0>;
+    static size_t checked2_smem[2] = {0, 0};
+    static int checked2_cap[2] = {0, 0};
+    const int s2 = fast2 ? 1 : 0;
+    if (checked2_smem[s2] != g.smem_bytes) {
+      int per_sm = 0;
+      RS_CHECK_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+      RS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern2, NTHREADS2, g.smem_bytes));
+      checked2_cap[s2] = per_sm * sm_count();
+      checked2_smem[s2] = g.smem_bytes;
+    }
+    RS_REQUIRE(checked2_cap[s2] >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_ts_forward: %d CTAs cannot be co-resident", g.nslice);
+    kern2<<<dim3(g.nslice), dim3(NTHREADS2), g.smem_bytes, st>>>(th, ts0, ts1, td0, td1, p2);
+    RS_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return RS_OK;
+  }
   if ((rc = tmap_stacked_bf16(&th, a.h_hi, hrows, g.H, g.Bpad, g.gkb)) != RS_OK) return rc;
   if ((rc = tmap_store3_bf16(&ts, a.h_hi, g.H, 2, hrows, (size_t)g.H * 2, (size_t)2 * g.H * 2, TSU, 2, g.B)) != RS_OK) return rc;
   CUtensorMap td = ts;

@@ -1,3 +1,5 @@
+// Compiled into librnnspeech_b200_diag.so only (-DRS_DIAG): self-tests and micro-benchmarks of the tcgen05 plumbing.
+#ifdef RS_DIAG
 // Single-CTA tcgen05 self-test: D[128,N] = A[128,K] * B[N,K]^T through the same
 // descriptor / swizzle / TMEM helpers the production kernels use (tc_common.cuh).
 // Exists so that tests/test_gpu_tc.py can validate the encodings in isolation.
@@ -282,3 +284,5 @@ extern "C" int rs_tc_ts_selftest(const float* A_d, const float* B_d, float* D_d,
   RS_CHECK_LAUNCH();
   return RS_OK;
 }
+
+#endif  // RS_DIAG

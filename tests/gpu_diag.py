@@ -72,7 +72,7 @@ def tc_diag():
         Ad, Bd = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
         for split in (0, 1):
             D = torch.full((128, N), float("nan"), dtype=torch.float32, device=dev)
-            rs._lib.call("rs_tc_selftest", Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), N, K, split,
+            rs._lib.diag_call("rs_tc_selftest", Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), N, K, split,
                          torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
             got = D.cpu().numpy()
@@ -100,13 +100,13 @@ def gemm_diag():
             C = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev)
             args = (Ad.data_ptr(), Bd.data_ptr(), bd.data_ptr(), C.data_ptr(), M, N, K, products, scratch.data_ptr(),
                     scratch.numel(), torch.cuda.current_stream().cuda_stream)
-            rs._lib.call("rs_gemm_tc_test", *args)
+            rs._lib.diag_call("rs_gemm_tc_test", *args)
             torch.cuda.synchronize()
             got = C.cpu().numpy()
             e = np.abs(got - want)
             t0 = time.perf_counter()
             for _ in range(5):
-                rs._lib.call("rs_gemm_tc_test", *args)
+                rs._lib.diag_call("rs_gemm_tc_test", *args)
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / 5
             print("gemm %dx%dx%d products=%d: rel err %.3e nan %d; %.3f ms incl. split (%.1f TFLOP/s useful)" % (
@@ -134,7 +134,7 @@ def gemm_bench():
             for bn in (128, 256):
                 for ctas, tpc in ((0, 0), (52, 0), (36, 0), (0, 1)):
                     ms = ctypes.c_float()
-                    rs._lib.call("rs_gemm_tc_bench", A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, products, bn, ctas,
+                    rs._lib.diag_call("rs_gemm_tc_bench", A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, products, bn, ctas,
                                  tpc, acc, 10, scratch.data_ptr(), scratch.numel(), ctypes.byref(ms),
                                  torch.cuda.current_stream().cuda_stream)
                     n_sm = 148 if (ctas == 0) else ctas
@@ -241,7 +241,7 @@ def mma_bench():
             count = 576
             for rep in range(2):
                 out.zero_()
-                rs._lib.call("rs_tc_mma_bench", M, N, count, variant, nacc, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                rs._lib.diag_call("rs_tc_mma_bench", M, N, count, variant, nacc, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
                 torch.cuda.synchronize()
             c = out.cpu().numpy()
             print("   %s M=%3d N=%3d nacc=%d: issue %.1f, complete %.1f cycles/MMA" % (
@@ -434,7 +434,7 @@ def ts_diag():
         Ad, Bd = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
         for variant in (0, 1):
             D = torch.full((128, 64), float("nan"), dtype=torch.float32, device=dev)
-            rs._lib.call("rs_tc_ts_selftest", Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), K, variant, 1, out.data_ptr(),
+            rs._lib.diag_call("rs_tc_ts_selftest", Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), K, variant, 1, out.data_ptr(),
                          torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
             got = D.cpu().numpy().astype(np.float64)
@@ -449,7 +449,7 @@ def ts_diag():
                 K, variant, quad[0], quad[1], quad[2], quad[3], np.abs(tot - ref).max() / np.abs(ref).max(), int(np.isnan(got).sum())))
         for dcol in (448, 384, 416):
           for reps in (1, 8):
-            rs._lib.call("rs_tc_ts_selftest", Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), K, dcol << 8, reps, out.data_ptr(),
+            rs._lib.diag_call("rs_tc_ts_selftest", Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), K, dcol << 8, reps, out.data_ptr(),
                          torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
             c = out.cpu().numpy()

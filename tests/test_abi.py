@@ -9,9 +9,16 @@ import numpy as np
 from conftest import ROOT
 
 
-def _declared_symbols():
+def _declared_symbols(diag=False):
+    """Symbols the header declares: the product ABI, or (diag=True) the hooks inside its #ifdef RS_DIAG block."""
     text = open(os.path.join(ROOT, "include", "rnnspeech_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    m = re.search(r"#ifdef RS_DIAG(.*?)#endif", text, flags=re.S)
+    block = m.group(1) if m else ""
+    if diag:
+        text = block
+    elif m:
+        text = text[:m.start()] + text[m.end():]
     return sorted(set(re.findall(r"\b(rs_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -25,6 +32,20 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_ctypes_table_matches_header(pkg):
     assert sorted(pkg._lib.SIGNATURES) == _declared_symbols()
+
+
+def test_diagnostic_hooks_live_in_their_own_library(pkg):
+    """The self-test / micro-benchmark hooks are behind -DRS_DIAG: absent from the product library, present in
+    librnnspeech_b200_diag.so (which also carries the whole product ABI)."""
+    names = _declared_symbols(diag=True)
+    assert sorted(pkg._lib.DIAG_SIGNATURES) == names and len(names) >= 5
+    product = ctypes.CDLL(pkg.LIB_PATH)
+    diag = pkg._lib.diag()
+    for name in names:
+        assert not hasattr(product, name), "diagnostic hook exported by the product library: " + name
+        assert hasattr(diag, name)
+    for name in _declared_symbols():
+        assert hasattr(diag, name)
 
 
 def test_version_and_error_string(pkg):

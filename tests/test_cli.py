@@ -73,3 +73,32 @@ def test_librispeech_tree_with_flac_durations_and_ordering(pkg, tmp_path):
 def test_repo_config_ini_parses(pkg):
     hp = pkg.HyperParameterHandler.read_config_file(os.path.join(ROOT, "config.ini"))
     assert hp["num_layers"] == 3 and hp["hidden_size"] == 768 and hp["signal_processing"] == "fbank"
+
+
+def test_data_parallel_sharding_is_consistent_across_processes(pkg, tmp_path):
+    """every rank must shard ONE order (an unseeded shuffle per process makes the shards overlap and leaks
+    held-out items into other ranks' training sets), all shards must have the same size (same number of optimizer
+    steps per rank), and manifest transcripts go through clean_label."""
+    import subprocess
+    import sys
+    import stt
+    from rnn_speech_b200 import dist as rsdist
+    items = [["f%03d.wav" % i, "t%d" % i, float(i)] for i in range(65)]
+    # the same permutation in two different interpreter processes (hash randomisation, no shared state)
+    code = ("import sys; sys.path.insert(0, %r); import stt; "
+            "print(','.join(x[0] for x in stt.shuffled([['f%%03d.wav' %% i, '', 0.0] for i in range(65)], 3)))" % ROOT)
+    outs = {subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout for _ in range(2)}
+    assert len(outs) == 1
+    here = ",".join(x[0] for x in stt.shuffled(items, 3)) + "\n"
+    assert outs == {here} and stt.shuffled(items, 3) != stt.shuffled(items, 4)
+    train, test = stt.split_acoustic_dataset(list(items), [], False, 0.8)
+    assert len(train) == 52 and len(test) == 13 and not {x[0] for x in train} & {x[0] for x in test}
+    # equal, disjoint shards of the common order: 65 items on 2 ranks -> 32 + 32 (one item left out this epoch)
+    shards = [rsdist.shard(train, r, 3) for r in range(3)]
+    assert [len(s) for s in shards] == [17, 17, 17]
+    assert len({x[0] for s in shards for x in s}) == 51
+    # manifest transcripts are cleaned like the corpus walkers' (upper case / punctuation would end the label early)
+    d = tmp_path / "m"
+    d.mkdir()
+    (d / "manifest.tsv").write_text("a.wav\tHello, World!\n")
+    assert stt.load_dataset_dirs(str(d))[0][1] == "hello world"

@@ -18,7 +18,7 @@ def test_tcgen05_selftest_matches_fp64_matmul(pkg, cuda, N, K):
     scale = np.abs(want).max()
     for split, tol in ((0, 2e-2), (1, 3e-5)):
         D = torch.full((128, N), float("nan"), dtype=torch.float32, device=cuda)
-        pkg._lib.call("rs_tc_selftest", Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), N, K, split,
+        pkg._lib.diag_call("rs_tc_selftest", Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), N, K, split,
                       torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         err = np.abs(D.cpu().numpy() - want).max() / scale
@@ -39,7 +39,7 @@ def test_tcgen05_gemm_against_fp64(pkg, cuda, M, N, K):
     scratch = torch.empty(2 * (M * K + N * K) * 2 + 64, dtype=torch.uint8, device=cuda)
     for products, tol in ((1, 2e-2), (3, 2e-5)):
         C = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
-        pkg._lib.call("rs_gemm_tc_test", Ad.data_ptr(), Bd.data_ptr(), bd.data_ptr(), C.data_ptr(), M, N, K, products,
+        pkg._lib.diag_call("rs_gemm_tc_test", Ad.data_ptr(), Bd.data_ptr(), bd.data_ptr(), C.data_ptr(), M, N, K, products,
                       scratch.data_ptr(), scratch.numel(), torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         got = C.cpu().numpy()
@@ -63,7 +63,7 @@ def test_tcgen05_gemm_mn_major_against_fp64(pkg, cuda, M, N, K):
     scratch = torch.empty(2 * (M * K + N * K) * 2 + 64, dtype=torch.uint8, device=cuda)
     for products, tol in ((1, 2e-2), (3, 2e-5)):
         C = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
-        pkg._lib.call("rs_gemm_tc_test", Ad.data_ptr(), Bd.data_ptr(), bd.data_ptr(), C.data_ptr(), M, N, K, 16 + products,
+        pkg._lib.diag_call("rs_gemm_tc_test", Ad.data_ptr(), Bd.data_ptr(), bd.data_ptr(), C.data_ptr(), M, N, K, 16 + products,
                       scratch.data_ptr(), scratch.numel(), torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         got = C.cpu().numpy()

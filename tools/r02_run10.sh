@@ -1,0 +1,21 @@
+#!/bin/bash
+# round 2, GPU call 10: two-chain forward recurrent kernel -- parity (model suite), stale-tile stress, A/B
+mkdir -p gpurun_out
+echo "== model + train tests (two chains default)"; timeout 1200 python -m pytest tests/test_gpu_model.py tests/test_gpu_train.py tests/test_gpu_trained.py -x -q -s 2>&1 | grep -i "passed\|failed\|error\|shipped\|argmax\|rel-L2\|kernel_\|input_w\|output_w" | tail -30 | tee gpurun_out/r02_model_tests_run10.log
+run() { echo "== bench $*"; env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/last.err | tail -1 > gpurun_out/last.json; python - <<'PY'
+import json
+try:
+    d = json.load(open('gpurun_out/last.json')); r = d['roofline']; f = r['families']
+    print('   value %.1f utt/s  %.2f ms/step  e2e %.1f  err-rate step %.2f ms  launches/step %d  fwd %.2f bwd %.2f ms  rec fwd %s bwd %s frac %.4f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['with_error_rate']['ms_per_step'], d['gpu_launches'] / d['steps'], [v for k, v in f.items() if k.startswith('lstm_stack_f')][0]['ms_per_step'], [v for k, v in f.items() if k.startswith('lstm_stack_b')][0]['ms_per_step'], ['%.2f' % x for x in r['launch_ms']['fwd']], ['%.2f' % x for x in r['launch_ms']['bwd']], r['frac']))
+except Exception as e:
+    print('   FAILED', e); print(open('gpurun_out/last.err').read()[-1500:])
+PY
+}
+run RS_TS_CHAINS=1 2>&1 | tee -a gpurun_out/r02_sweep10.log
+cp gpurun_out/last.json gpurun_out/r02_bench_cfg2_run10.json
+run RS_TS_CHAINS=0 2>&1 | tee -a gpurun_out/r02_sweep10.log
+run RS_TS_CHAINS=1 RS_TC_CHUNK_FWD=128 2>&1 | tee -a gpurun_out/r02_sweep10.log
+run RS_TS_CHAINS=1 RS_TC_PHASES=0 2>&1 | tee -a gpurun_out/r02_sweep10.log
+echo "== cfg5"; timeout 300 python bench.py --config cfg5 --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.readline()); print('   cfg5 %.0f clips/s  %.2f ms/step  e2e %.0f  p50 %.1f ms' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['latency_ms']['p50']))"
