@@ -92,8 +92,13 @@ def test_shipped_3x1024_model_forward_greedy_beam(pkg, cuda):
     print("shipped 3x1024 model: max |logit err| %.2e over %d frames (%d near ties, %d argmax mismatches), mean top "
           "probability %.3f, greedy rows identical %d/%d, beam rows identical %d/%d" %
           (err, frames, ties, mism, peak, greedy_same, B, beam_same, B))
+    # Tolerance: the trained model's logits span -80 .. +550 on this input.  tools/emulate_bf16x3_trained.py (CPU) puts
+    # the kernels' arithmetic -- six-product input dense, bf16x3 elsewhere -- 0.012 away from float64 and plain fp32
+    # (TensorFlow's arithmetic) 0.002 away; a two-piece split of the dB-scaled features alone gave 0.08 (round 2 finding).
+    span = float(np.abs(want[valid]).max())
+    report["logit_span"] = span
     keep_artifact("r02_trained_weight_parity.json", report)
-    assert err < 2e-3 and mism == 0
+    assert err < 3e-2 and err < 1e-4 * span and mism == 0
     if ties == 0:
         assert greedy_same == B
     for b in range(B):
