@@ -25,6 +25,12 @@ int sm_count() {
   return n;
 }
 
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev % kMaxDevices;
+}
+
 }  // namespace rs
 
 namespace rs { unsigned long long launch_count(); }

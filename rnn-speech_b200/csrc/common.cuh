@@ -41,6 +41,10 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 int sm_count();
+// ordinal of the current device, clamped to [0, kMaxDevices): index of the per-device caches of function attributes and
+// occupancy results (they are per-device state: a per-process cache would be wrong for a second device in the process)
+constexpr int kMaxDevices = 64;
+int device_slot();
 
 // ---- dropout mask: counter hash restated bit for bit by oracle/model.py ----
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {

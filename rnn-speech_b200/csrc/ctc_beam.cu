@@ -61,24 +61,49 @@ __device__ __forceinline__ bool before(float ka, int ia, float kb, int ib) {
   return (ka > kb) || (ka == kb && ia < ib);
 }
 
-__global__ void __launch_bounds__(kThreads)
+// kGroups utterances per CTA (groups of kThreads threads, each with its own state and its own named barrier).  The
+// kernel is latency-bound -- ~12 dependent phases per frame, 8 warps, ncu: issue slots 19 % busy (profiles/r02_ncu_*) --
+// but two groups per SM were measured SLOWER (20.0 vs 16.7 ms per 32 x 998 frames), and what the training step with the
+// error rate waits for is the decoder's duration, not the SMs it holds (24.7 vs 24.2 ms per step): one group.
+constexpr int kGroups = 1;
+
+struct BeamShared {
+  Beam beam[2];
+  float old_tot[kMaxW], old_blk[kMaxW], old_lab[kMaxW];
+  unsigned long long hkey[kHash];
+  int hslot[kHash];
+  unsigned childmask[kMaxW][4];
+  float in[kMaxC];
+  int s_count;
+  float s_lb;
+  float vals[2 * kMaxW];
+};
+
+__device__ __forceinline__ void group_sync(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kThreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kGroups * kThreads)
 ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, int T, int B, int C, int W,
                 int merge_repeated, int normalize, unsigned char* __restrict__ hist, int* __restrict__ out,
                 int* __restrict__ out_len, float* __restrict__ out_score) {
   extern __shared__ __align__(16) unsigned char dyn[];
-  float* ckey = reinterpret_cast<float*>(dyn);                 // [kMaxCand]
-  int* cid = reinterpret_cast<int*>(ckey + kMaxCand);          // [kMaxCand]
-  __shared__ Beam beam[2];
-  __shared__ float old_tot[kMaxW], old_blk[kMaxW], old_lab[kMaxW];
-  __shared__ unsigned long long hkey[kHash];
-  __shared__ int hslot[kHash];
-  __shared__ unsigned childmask[kMaxW][4];
-  __shared__ float in[kMaxC];
-  __shared__ int s_count;
-  __shared__ float s_lb;
-  __shared__ float vals[2 * kMaxW];
-
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ BeamShared shared_state[kGroups];
+  const int grp = threadIdx.x / kThreads;
+  const int b = blockIdx.x * kGroups + grp, tid = threadIdx.x - grp * kThreads, lane = tid & 31, warp = tid >> 5;
+  if (b >= B) return;                                          // (a whole group leaves: its barrier is its own)
+  BeamShared& S = shared_state[grp];
+  float* ckey = reinterpret_cast<float*>(dyn) + (size_t)grp * 2 * kMaxCand;      // [kMaxCand] per group
+  int* cid = reinterpret_cast<int*>(ckey + kMaxCand);                            // [kMaxCand]
+  Beam (&beam)[2] = S.beam;
+  float (&old_tot)[kMaxW] = S.old_tot; float (&old_blk)[kMaxW] = S.old_blk; float (&old_lab)[kMaxW] = S.old_lab;
+  unsigned long long (&hkey)[kHash] = S.hkey;
+  int (&hslot)[kHash] = S.hslot;
+  unsigned (&childmask)[kMaxW][4] = S.childmask;
+  float (&in)[kMaxC] = S.in;
+  int& s_count = S.s_count;
+  float& s_lb = S.s_lb;
+  float (&vals)[2 * kMaxW] = S.vals;
   const int L = min(len[b], T);
   const int blank = C - 1, nlab = C - 1;
   unsigned char* hprev = hist + (size_t)b * 2 * T * kMaxW;     // [T][kMaxW] previous slot (255 = none)
@@ -90,7 +115,7 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
     r.node[0] = 0x243F6A8885A308D3ull; r.parent[0] = 0ull; r.label[0] = -1;
     r.tot[0] = 0.f; r.blk[0] = 0.f; r.lab[0] = kNegInf;
   }
-  __syncthreads();
+  group_sync(grp);
 
   for (int t = 0; t < L; ++t) {
     Beam& bm = beam[cur];
@@ -113,7 +138,7 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
     for (int i = tid; i < kMaxW * 4; i += kThreads) (&childmask[0][0])[i] = 0u;
     if (tid < n) { old_tot[tid] = bm.tot[tid]; old_blk[tid] = bm.blk[tid]; old_lab[tid] = bm.lab[tid]; }
     if (tid == 0) s_count = 0;
-    __syncthreads();
+    group_sync(grp);
     if (tid < n) {
       unsigned h = (unsigned)(bm.node[tid] >> 17) & (kHash - 1);
       while (true) {
@@ -122,7 +147,7 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
         h = (h + 1) & (kHash - 1);
       }
     }
-    __syncthreads();
+    group_sync(grp);
     // ---- 2. update the entries
     float my_tot = kNegInf;
     if (tid < n) {
@@ -168,7 +193,7 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
       if (half == 0) vals[kMaxW + slot] = (slot < n) ? best : kNegInf;
       if (tid < kMaxW) vals[tid] = (tid < n) ? my_tot : kNegInf;
     }
-    __syncthreads();
+    group_sync(grp);
     {
       // rank of vals[tid] among the 2 * kMaxW values (descending, index breaks ties): one thread finds the bound
       const float v = vals[tid];
@@ -178,10 +203,10 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
         rank += (u > v || (u == v && j < tid)) ? 1 : 0;
       }
       if (tid == 0) s_lb = kNegInf;
-      __syncthreads();
+      group_sync(grp);
       if (rank == W - 1) s_lb = v;                        // -inf when fewer than W finite values exist
     }
-    __syncthreads();
+    group_sync(grp);
     // ---- 3. extensions
     const float lbv = s_lb;
     const int next = n * nlab;
@@ -202,7 +227,7 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
         cid[pos] = kMaxW + idx;
       }
     }
-    __syncthreads();
+    group_sync(grp);
     const int count = n + s_count;
     const int newn = min(W, count);
     const float* skey = ckey;
@@ -219,13 +244,13 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
         if (rank < newn) { okey[rank] = v; oid[rank] = id; }
       }
       skey = okey; sid = oid;
-      __syncthreads();
+      group_sync(grp);
     } else {
       // ---- 4b. bitonic sort, best first
       int p2 = 32;
       while (p2 < count) p2 <<= 1;
       for (int i = count + tid; i < p2; i += kThreads) { ckey[i] = kNegInf; cid[i] = 0x7fffffff; }
-      __syncthreads();
+      group_sync(grp);
       for (int k = 2; k <= p2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
           for (int i = tid; i < p2; i += kThreads) {
@@ -238,7 +263,7 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
               if (swap) { ckey[i] = kb; ckey[ixj] = ka; cid[i] = ib; cid[ixj] = ia; }
             }
           }
-          __syncthreads();
+          group_sync(grp);
         }
       }
     }
@@ -259,7 +284,7 @@ ctc_beam_kernel(const float* __restrict__ logits, const int* __restrict__ len, i
     }
     n = newn;
     cur ^= 1;
-    __syncthreads();
+    group_sync(grp);
   }
 
   // ---- 5. walk the history back from the best entry (slot 0), then LabelSeq(merge_repeated)
@@ -306,14 +331,16 @@ extern "C" int rs_ctc_beam_search(const float* logits_d, const int32_t* len_d, i
   // The decoder runs on a side stream under the backward pass.  Its CTAs are compute loops: sharing an SM with a CTA of
   // the latency-critical recurrent kernels slows every recurrent step (measured: the training step went from 26 to 65 ms
   // when they co-resided), so the candidate list is padded to a size that gives the CTA its SM to itself.
-  const size_t smem = 120 * 1024;
-  static_assert((size_t)kMaxCand * (sizeof(float) + sizeof(int)) <= 120 * 1024, "candidate list");
-  static bool attr_done = false;
-  if (!attr_done) {
+  // (padded to 120 KB: more than a recurrent CTA leaves free on its SM)
+  const size_t list_bytes = (size_t)kGroups * kMaxCand * (sizeof(float) + sizeof(int));
+  const size_t smem = list_bytes > 120 * 1024 ? list_bytes : 120 * 1024;
+  static bool attr_done[kMaxDevices] = {};
+  const int dev = device_slot();
+  if (!attr_done[dev]) {
     RS_CHECK_CUDA(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done[dev] = true;
   }
-  ctc_beam_kernel<<<B, kThreads, smem, (cudaStream_t)stream>>>(logits_d, len_d, T, B, C, beam_width, merge_repeated ? 1 : 0,
+  ctc_beam_kernel<<<cdiv(B, kGroups), kGroups * kThreads, smem, (cudaStream_t)stream>>>(logits_d, len_d, T, B, C, beam_width, merge_repeated ? 1 : 0,
                                                                normalize ? 1 : 0, (unsigned char*)ws_d, out_d, out_len_d,
                                                                out_score_d);
   RS_CHECK_LAUNCH();

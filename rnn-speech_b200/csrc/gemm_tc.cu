@@ -330,19 +330,27 @@ __global__ void rowsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const
   if (lane == 0) out[row] = accumulate ? out[row] + s : s;
 }
 
-// one block per 64 columns, all rows: deterministic (one writer per column, fixed summation order).  Thread (cx, ry):
-// 8 columns (one 16-byte load per plane and row), rows ry, ry + 32, ...
+// Column sums of a (hi, lo) plane pair, bit-reproducible: block (x, y) sums a slab of rows of 64 columns (thread (cx, ry):
+// 8 columns -- one 16-byte load per plane and row --, rows ry, ry + 32, ... of the slab), writes the 64 partial sums to
+// scratch[y][C], and the block that arrives last at the column block's counter adds the slabs in slab order: one writer
+// per column, a fixed summation order whatever the block schedule.  (One block per 64 columns over ALL rows -- the first
+// version -- took 172 us per 4096 x 3072 call, 10 % of a step's kernel time: too little memory parallelism.)
+constexpr int kColsumSlabs = 8;
 __global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                                            int R, int C, int ld, float* __restrict__ out, int accumulate) {
+                                                            int R, int C, int ld, float* __restrict__ out, int accumulate,
+                                                            float* __restrict__ scratch, unsigned* __restrict__ counters) {
   __shared__ float red[32][65];
+  __shared__ unsigned s_ticket;
   const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
   const int c = blockIdx.x * 64 + 8 * cx;
+  const int rows_per = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
   float s[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = 0.f;
   if (c + 7 < C) {
 #pragma unroll 4
-    for (int r = ry; r < R; r += 32) {
+    for (int r = r0 + ry; r < r1; r += 32) {
       const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + (size_t)r * ld + c));
       const uint32_t w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16*
       }
     }
   } else {
-    for (int r = ry; r < R; r += 32)
+    for (int r = r0 + ry; r < r1; r += 32)
       for (int i = 0; i < 8; ++i)
         if (c + i < C) {
           s[i] += __bfloat162float(hi[(size_t)r * ld + c + i]);
@@ -365,15 +373,25 @@ __global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16*
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[ry][8 * cx + i] = s[i];
   __syncthreads();
-  if (threadIdx.x < 64) {
-    const int cc = blockIdx.x * 64 + threadIdx.x;
-    if (cc < C) {
-      float t = 0.f;
+  const int cc = blockIdx.x * 64 + threadIdx.x;
+  if (threadIdx.x < 64 && cc < C) {
+    float t = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
-      out[cc] = accumulate ? out[cc] + t : t;
-    }
+    for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+    scratch[(size_t)blockIdx.y * C + cc] = t;
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&counters[blockIdx.x], 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.y - 1) return;
+  __threadfence();
+  if (threadIdx.x < 64 && cc < C) {
+    float t = 0.f;
+    for (unsigned y = 0; y < gridDim.y; ++y) t += __ldcg(scratch + (size_t)y * C + cc);
+    out[cc] = accumulate ? out[cc] + t : t;
+  }
+  if (threadIdx.x == 0) counters[blockIdx.x] = 0u;          // ready for the next call on this scratch
 }
 
 int make_tmap(CUtensorMap* map, const __nv_bfloat16* base, int rows, int cols, int ld, int box_rows) {
@@ -519,10 +537,11 @@ int gemm_launch(const SplitMat& A, const SplitMat& B, int M, int N, int K, int p
   p.base_ctas = grid;
   if (out.elastic) { grid = sm_count(); if (grid > ntiles) grid = ntiles; if (grid < p.base_ctas) grid = p.base_ctas; }
   const size_t smem = (size_t)Cfg<BN, ST>::STAGES * Cfg<BN, ST>::STAGE_BYTES + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {};
+  const int dev = device_slot();
+  if (!attr_done[dev]) {
     RS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, ST, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done[dev] = true;
   }
   gemm_tc_kernel<BN, ST, MN><<<grid, NTHREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   RS_CHECK_LAUNCH();
@@ -587,12 +606,23 @@ int transpose_bf16(const __nv_bfloat16* in, int R, int C, int ld_in, __nv_bfloat
   return RS_OK;
 }
 
+// scratch layout: [kColsumCounters column-block counters][kColsumSlabs x C partial sums].  The counters come FIRST, at a
+// place that does not depend on C: calls with different C share one scratch, and a counter must never sit where another
+// call's partial sums go.
+constexpr int kColsumCounters = 1024;
+size_t colsum_scratch_bytes(int C) { return ((size_t)kColsumCounters + (size_t)kColsumSlabs * C) * sizeof(float); }
+
 int colsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int R, int C, int ld, float* out, int accumulate,
-                  cudaStream_t st) {
+                  void* scratch, cudaStream_t st) {
   if (C <= 0) return RS_OK;
   RS_REQUIRE((ld % 8) == 0 && (reinterpret_cast<uintptr_t>(hi) & 15) == 0 && (!lo || (reinterpret_cast<uintptr_t>(lo) & 15) == 0),
              RS_ERR_INVALID, "colsum_planes: planes must be 16-byte aligned with a row stride that is a multiple of 8");
-  colsum_planes_kernel<<<cdiv(C, 64), 256, 0, st>>>(hi, lo, R, C, ld, out, accumulate);
+  RS_REQUIRE(scratch != nullptr, RS_ERR_INVALID, "colsum_planes: scratch (colsum_scratch_bytes, counters zeroed) is required");
+  RS_REQUIRE(cdiv(C, 64) <= kColsumCounters, RS_ERR_UNSUPPORTED, "colsum_planes: %d columns", C);
+  unsigned* counters = reinterpret_cast<unsigned*>(scratch);
+  float* part = reinterpret_cast<float*>(scratch) + kColsumCounters;
+  const int slabs = R >= 64 * kColsumSlabs ? kColsumSlabs : 1;
+  colsum_planes_kernel<<<dim3(cdiv(C, 64), slabs), 256, 0, st>>>(hi, lo, R, C, ld, out, accumulate, part, counters);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }

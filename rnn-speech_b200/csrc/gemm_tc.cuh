@@ -55,9 +55,13 @@ int gemm_tc_nt(const SplitMat& A, const SplitMat& B, int M, int N, int K, int pr
 // forward / backward kernels wrote them ((t, b) as the row index): no transposed copies.  fp32 output only.
 int gemm_tc_tn(const SplitMat& A, const SplitMat& B, int M, int N, int K, int products, const GemmTcOut& out,
                cudaStream_t st);
-// out[c] (+)= sum_r (hi[r][c] + lo[r][c]) over a [R, C] plane pair (lo may be nullptr): bias gradients from dgates
+// out[c] (+)= sum_r (hi[r][c] + lo[r][c]) over a [R, C] plane pair (lo may be nullptr): bias gradients from dgates.
+// Bit-reproducible.  scratch: colsum_scratch_bytes(C) bytes whose leading 1024 counter words are zero before the first
+// call (the kernel leaves them zero); calls that may run concurrently need separate scratch, consecutive calls (any C up
+// to the one the scratch was sized for) may share it.
+size_t colsum_scratch_bytes(int C);
 int colsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int R, int C, int ld, float* out, int accumulate,
-                  cudaStream_t st);
+                  void* scratch, cudaStream_t st);
 
 // out planes <- split(in * scale) elementwise; optional dropout masks as in lstm.cu
 int split_planes(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t st);

@@ -1156,9 +1156,9 @@ int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a_in, cudaStream
     RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
     const bool fast2 = g.H == 768 && g.nkb_t == 12;
     auto kern2 = fast2 ? rec_ts_fwd2_kernel<768> : rec_ts_fwd2_kernel<0>;
-    static size_t checked2_smem[2] = {0, 0};
-    static int checked2_cap[2] = {0, 0};
-    const int s2 = fast2 ? 1 : 0;
+    static size_t checked2_smem[kMaxDevices * 2] = {};
+    static int checked2_cap[kMaxDevices * 2] = {};
+    const int s2 = device_slot() * 2 + (fast2 ? 1 : 0);
     if (checked2_smem[s2] != g.smem_bytes) {
       int per_sm = 0;
       RS_CHECK_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
@@ -1192,9 +1192,9 @@ int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a_in, cudaStream
   // the benchmark shape's instantiation: H = 768 (all twelve K-blocks in tensor memory, one TMA group), Bpad = 32
   const bool fast = !a.dbg && p.variant == kDefaultVariant && g.Bpad == 32 && g.H == 768 && g.gkb == 12 && g.nkb_t == 12 && g.stages == 1;
   auto kern = a.dbg ? rec_ts_fwd_kernel<true, -1, 0, 0> : (fast ? rec_ts_fwd_kernel<false, kDefaultVariant, 32, 768> : rec_ts_fwd_kernel<false, -1, 0, 0>);
-  const int si = a.dbg ? 1 : (fast ? 2 : 0);
-  static size_t checked_smem[3] = {0, 0, 0};  // attribute + co-residency check once per shared-memory size
-  static int checked_cap[3] = {0, 0, 0};
+  const int si = device_slot() * 3 + (a.dbg ? 1 : (fast ? 2 : 0));
+  static size_t checked_smem[kMaxDevices * 3] = {};  // attribute + co-residency check once per device and shared-memory size
+  static int checked_cap[kMaxDevices * 3] = {};
   if (checked_smem[si] != g.smem_bytes) {
     int per_sm = 0;
     RS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
@@ -1262,11 +1262,11 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
   if ((!share || cols > 256) && smem < 120 * 1024) smem = 120 * 1024;
   RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
   const bool fast = !a.dbg && p.variant == kDefaultVariant && g.Bpad == 32 && g.H == 768 && (!x3 || nlo_t == p.nkbs);
-  const int si = a.dbg ? 1 : (fast ? (x3 ? 2 : 3) : 0);
+  const int si = device_slot() * 4 + (a.dbg ? 1 : (fast ? (x3 ? 2 : 3) : 0));
   auto kern = a.dbg ? rec_ts_bwd_kernel<true, -1, 0, 0, -1>
                     : (fast ? (x3 ? rec_ts_bwd_kernel<false, kDefaultVariant, 32, 768, 1> : rec_ts_bwd_kernel<false, kDefaultVariant, 32, 768, 0>)
                             : rec_ts_bwd_kernel<false, -1, 0, 0, -1>);
-  static size_t attr_smem[4] = {0, 0, 0, 0};
+  static size_t attr_smem[kMaxDevices * 4] = {};
   if (attr_smem[si] != smem) {
     RS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -1280,7 +1280,7 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int nclusters_s[4] = {0, 0, 0, 0};
+  static int nclusters_s[kMaxDevices * 4] = {};
   if (attr_smem[si] != smem) {
     RS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nclusters_s[si], kern, &cfg));
     attr_smem[si] = smem;

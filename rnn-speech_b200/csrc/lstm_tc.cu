@@ -56,6 +56,7 @@ struct TcBufs {
   float* din[65];                 // [T*B][H]: din[l] = gradient wrt layer l's input, din[L] = wrt the top activations
   float* dc_carry[64];
   int* elastic;                   // [0] = recurrent launches done, [1 + i] = grid decision of the i-th elastic GEMM
+  char* colsum_ws[2];             // colsum_planes scratch: [0] transposer stream, [1] side stream (the two may overlap)
   // ---- reserve
   bf16 *x6;                       // the features in three bf16 pieces, six K segments [T*B][6 Fp] = hi|mid|lo|hi|hi|mid;
   bf16 *x_hi, *x_lo;              //   x_hi = x6 (hi piece), x_lo = x6 + Fp (mid piece): the (hi, lo) planes of the backward GEMM, ld 6 Fp
@@ -94,6 +95,7 @@ void carve(const rs_am* am, void* reserve, void* ws, bool training, TcBufs* b, s
     }
     b->wos_hi = w.take<bf16>((size_t)H * Cp); b->wos_lo = w.take<bf16>((size_t)H * Cp);
     b->elastic = w.take<int>(4096);
+    for (int i = 0; i < 2; ++i) b->colsum_ws[i] = w.take<char>(colsum_scratch_bytes(4 * H > C ? 4 * H : C));
     b->actT_hi = w.take<bf16>((size_t)H * TBp); b->actT_lo = w.take<bf16>((size_t)H * TBp);
     b->drT_hi = w.take<bf16>((size_t)H * TBp); b->drT_lo = w.take<bf16>((size_t)H * TBp);
     b->dl_hi = w.take<bf16>(TB * Cp); b->dl_lo = w.take<bf16>(TB * Cp);
@@ -639,6 +641,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   am->ev_next = 0;
   cudaStream_t side = am->side;
   RS_CHECK_CUDA(cudaMemsetAsync(bf.elastic, 0, 4096 * sizeof(int), st));
+  for (int i = 0; i < 2; ++i) RS_CHECK_CUDA(cudaMemsetAsync(bf.colsum_ws[i], 0, colsum_scratch_bytes(4 * H > C ? 4 * H : C), st));
   int elastic_next = 0;
   const bool use_elastic = NC > 1 && !sc.cores && !sc.phases && sc.side_tpc == 0 && 2 * L * NC + NC + 8 < 4096;
   cudaEvent_t e_fork;
@@ -654,7 +657,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     GemmTcOut o{};
     o.mode = GEMM_OUT_F32; o.C = grads_d + am->off_output_w; o.ldc = C; o.accumulate = 1; o.max_ctas = sc.side_ctas;
     RC(gemm_tc_tn(A, Bm, H, C, TB, 3, o, side));
-    RC(colsum_planes(bf.dl_hi, bf.dl_lo, TB, C, Cp, grads_d + am->off_output_b, 1, side));
+    RC(colsum_planes(bf.dl_hi, bf.dl_lo, TB, C, Cp, grads_d + am->off_output_b, 1, bf.colsum_ws[1], side));
   } else {
     RC(transpose_bf16(in_hi[L], TB, H, in_ld[L], bf.actT_hi, TBp, side));
     RC(transpose_bf16(in_lo[L], TB, H, in_ld[L], bf.actT_lo, TBp, side));
@@ -734,7 +737,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
       // in place: x / h_{t-1} are [nb][H] with (t, b) rows, dgates [nb][4H]
       cudaStream_t tr = am->tr_st;
       RS_CHECK_CUDA(cudaStreamWaitEvent(tr, e_rec[(size_t)l * NC + c], 0));
-      RC(colsum_planes(bf.dg_hi[l] + r0 * 4 * H, bf.dg_lo[l] + r0 * 4 * H, nb, 4 * H, 4 * H, grads_d + am->off_bias[l], 1, tr));
+      RC(colsum_planes(bf.dg_hi[l] + r0 * 4 * H, bf.dg_lo[l] + r0 * 4 * H, nb, 4 * H, 4 * H, grads_d + am->off_bias[l], 1, bf.colsum_ws[0], tr));
       RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_rec[(size_t)l * NC + c], 0));
       RC(tev_record(am, 2, l, side));
       SplitMat G{bf.dg_hi[l] + r0 * 4 * H, bf.dg_lo[l] + r0 * 4 * H, nb, 4 * H, 4 * H};
@@ -804,7 +807,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
       RC(split_rows(drnn, nb, H, H, dr_hi, dr_lo, H, tr));
       cudaEvent_t e_in;
       RC(ev_record(am, &e_in, tr));
-      RC(colsum_planes(dr_hi, dr_lo, nb, H, H, grads_d + am->off_input_b, 1, tr));
+      RC(colsum_planes(dr_hi, dr_lo, nb, H, H, grads_d + am->off_input_b, 1, bf.colsum_ws[0], tr));
       RS_CHECK_CUDA(cudaStreamWaitEvent(side, e_in, 0));
       SplitMat A{bf.x_hi + r0 * 6 * Fp, bf.x_lo + r0 * 6 * Fp, nb, F, 6 * Fp}, Bm{dr_hi, dr_lo, nb, H, H};
       GemmTcOut o{};
