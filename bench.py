@@ -471,7 +471,9 @@ def run_train(args, name):
         sampler.start()
     ms, launches = h.timed(step_resident, args.steps, launch_count)
     T_last = res[(state["i"] - 1) % NB]["T"]
-    roofline = recurrent_roofline(h, m, c, T_last, ms / args.steps, (0, 1), 95.7e6 if name == "cfg2" else None) \
+    # dram__bytes_read + write per recurrent launch from profiles/r02_ncu_recurrent_kernels.txt: backward 110.4 MB per
+    # 128-step launch, forward 25.8 MB per 38-step launch = 65 MB per 96 steps; weighted by 24 / 33 launches per step
+    roofline = recurrent_roofline(h, m, c, T_last, ms / args.steps, (0, 1), 84.0e6 if name == "cfg2" else None) \
         if rank == 0 else None
     clocks = sampler.stop() if rank == 0 else None
     # the product's default training step: with the reference's per-mini-batch prediction + error rate
