@@ -42,6 +42,35 @@ def _assert_labels_match(logits_gpu, logits_oracle, lens):
     return n_tie
 
 
+def _lev(a, b):
+    """Plain host Levenshtein distance (test-side checker)."""
+    prev = list(range(len(b) + 1))
+    for i, x in enumerate(a, 1):
+        cur = [i]
+        for j, y in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (x != y)))
+        prev = cur
+    return prev[-1]
+
+
+def _assert_ids_match(ids, n, logits_oracle, lens, tag):
+    """Greedy label ids against the oracle's, for EVERY utterance: identical when no frame of the utterance is a near
+    tie (oracle top-2 margin <= MARGIN); otherwise one flipped frame can change the collapsed sequence by at most two
+    edits (a b a -> a a a), so the Levenshtein distance is bounded by 2 x (near-tie frames of that utterance)."""
+    ref = ctc.greedy_decode(logits_oracle, lens)
+    margin = ctc.top2_margin(logits_oracle, lens)
+    ties = (margin <= MARGIN).sum(0)
+    exact = 0
+    for b in range(len(ref)):
+        got = [int(v) for v in ids[b, :int(n[b])]]
+        d = _lev(got, [int(v) for v in ref[b]])
+        assert d <= 2 * int(ties[b]), "%s: utterance %d differs by %d edits with %d near-tie frames" % (tag, b, d, ties[b])
+        exact += d == 0
+    print("%s: %d of %d utterances decode to exactly the oracle's ids (%d near-tie frames of %d, all within the bound)"
+          % (tag, exact, len(ref), int(ties.sum()), int(np.sum(lens))))
+    return exact
+
+
 def test_cfg1_golden_forward_backward(pkg, cuda):
     g = golden("model_cfg1.npz")
     L, H, F, C, T, B = [int(v) for v in g["dims"]]
@@ -63,9 +92,8 @@ def test_cfg1_golden_forward_backward(pkg, cuda):
     ids, n = m.greedy_decode(logits, lens)
     want = ctc.greedy_decode(g["logits"], g["lens"])
     ties = _assert_labels_match(logits.cpu().numpy(), g["logits"], g["lens"])
-    if ties == 0:
-        for b in range(B):
-            np.testing.assert_array_equal(ids[b, :int(n[b])].cpu().numpy(), want[b])
+    print("cfg-1 golden: %d near-tie frames of %d" % (ties, int(np.sum(g["lens"]))))
+    _assert_ids_match(ids.cpu().numpy(), n.cpu().numpy(), g["logits"], g["lens"], "cfg-1 golden")
 
 
 @pytest.mark.parametrize("L,H,F,C,B,T,ki,ko", [
@@ -155,6 +183,16 @@ def test_cfg2_shape_forward_against_oracle(pkg, cuda):
           % (err, rel.max(), ties, int(lens.sum())))
     assert err < 1e-3
     assert rel.max() < 1e-3
+    # near ties (oracle top-2 margin <= MARGIN) are counted and bounded, not waved through: Xavier weights give flat
+    # posteriors, a tenth of the frames at most may be that close; and every utterance WITHOUT a near-tie frame must
+    # decode to exactly the oracle's label ids
+    assert ties <= 0.1 * int(lens.sum())
+    ids, n = m.greedy_decode(logits, _dev(lens, cuda, np.int32))
+    _assert_ids_match(ids.cpu().numpy(), n.cpu().numpy(), want, lens, "cfg-2 forward")
+    # the decode kernel itself is exact: the host decoder on the GPU's own logits gives the same ids
+    own = ctc.greedy_decode(logits.cpu().numpy(), lens)
+    for b in range(B):
+        np.testing.assert_array_equal(ids[b, :int(n[b])].cpu().numpy(), own[b])
 
 
 def cfg2_backward_parity(pkg, cuda, keep_in, keep_out, tag):
@@ -389,3 +427,32 @@ def test_batch_normalization_against_oracle(pkg, cuda, L, H, F, C, B, T, ki):
     # the input-dense gradients are the ones that pass through the normalisation
     n_in = F * H + H
     assert np.abs(got[:n_in] - gw[:n_in]).max() < 2e-3 * np.abs(gw[:n_in]).max()
+
+
+def test_infer_signals_matches_oracle_pipeline(pkg, cuda):
+    """The batched inference path of bench.py --config cfg5 / stt.py --evaluate (AcousticModel.infer_signals: host PCM
+    -> one staged copy -> feature kernels -> forward per batch tile -> greedy decode -> ids on the host), 70 clips =
+    tiles of 64 + 6, against the oracle's features + forward + greedy decode."""
+    from oracle import features
+    L, H, F, C, B, sr = 2, 128, 120, 80, 70, 16000
+    rng = np.random.default_rng(70)
+    p = model.init_params(L, H, F, C, seed=11, dtype=np.float64)
+    flat = model.flatten(p, L, H, F, C)
+    sigs = [(0.1 * rng.standard_normal(int(sr * s))).astype(np.float32) for s in rng.uniform(0.4, 1.0, size=B)]
+    Tmax = 100
+    ap = pkg.AudioProcessor(Tmax, "fbank", device=cuda)
+    m = _build(pkg, cuda, L, H, F, C, B, Tmax, flat, training=False)
+    assert m.uses_tensor_cores and len(m._tiles) == 2
+    ids, n = m.infer_signals(ap, sigs, sr)
+    feats = [features.fbank(s, sr, Tmax) for s in sigs]
+    lens = np.array([min(k, Tmax) for _, k in feats])
+    T = int(max(ap.num_frames(len(s), sr) for s in sigs))
+    assert ids.shape == (B, min(T, Tmax)) and n.shape == (B,)
+    x = np.zeros((ids.shape[1], B, F))
+    for b, (f, _) in enumerate(feats):
+        x[:len(f), b] = f
+    want, _, _ = model.forward(p, x, lens, L, H, keep_cache=False)
+    for b in range(B):
+        assert np.all(ids[b, n[b]:] == -1)
+    exact = _assert_ids_match(ids, n, want, lens, "infer_signals")
+    assert exact >= B // 4
