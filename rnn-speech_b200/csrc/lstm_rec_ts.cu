@@ -37,6 +37,7 @@
 #include "tc_common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace rs {
 namespace {
@@ -731,6 +732,372 @@ rec_ts_fwd2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------
+// Forward, two chains, VALIDATED exchange: no release, no bulk-group wait, no second pass over the data.
+//
+// The exchange of rec_ts_fwd2_kernel costs four dependent hops per step: TMA store + bulk-group wait, proxy fence +
+// red.release (a MEMBAR behind every other store of the SM: ~0.6 us), the consumers' poll of the counter, their TMA load.
+// Here the writer side is two instructions: a 16-byte `st.relaxed.gpu` per (row, plane, half) of the CTA's 16 units and a
+// RELAXED `red` on the chain's counter.  Nothing orders the two, so the counter is only a hint that the tile is probably
+// there; the proof is in the data.  Before a forward pass the host fills slots 1..T of the h planes with the bit pattern
+// 0xFFFF -- a bf16 NaN that cvt.rn.bf16 never produces (NaN converts to 0x7FFF).  A consumer polls the counter and fetches
+// the chain's 48 KB tile with ONE TMA box as before.  A tile row that still holds fill pattern anywhere -- a store overtaken
+// by its producer's `red`, or not yet visible to the async proxy -- makes that batch column of the accumulator NaN in every
+// gate row (NaN x w = NaN, also for w = 0): THE TENSOR CORE VALIDATES THE TILE, the epilogue only tests the eight
+// pre-activations it computes anyway and votes in the barrier it needs anyway before publishing.  A NaN vote takes the slow
+// path: the four epilogue warps scan the landed tile for the fill pattern; if it is there, the producer warp fetches the
+// tile again and the MMA warp multiplies again (accumulate = 0 overwrites), nothing of the attempt having been kept or
+// published; if not, the NaN is the model's own (diverged training) and the step goes on.
+// (tests/test_gpu_model.py::test_exchange_fault_injection delays half of every publish behind its `red` and checks that the
+// retries happen and that nothing changes bit for bit.)
+//
+// The chains take turns: see the producer warps.
+// Requires Bpad == 32 and all of K in one tile (as rec_ts_fwd2_kernel).
+// ------------------------------------------------------------------------------------
+constexpr uint32_t kFill = 0xffffffffu;
+
+__device__ __forceinline__ void st_relaxed_v4(void* p, const uint4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+// barrier over `nthreads` threads (named barrier `id`) + vote: true for every thread iff the predicate holds for at least one
+__device__ __forceinline__ bool bar_any(int id, int nthreads, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %1, 0;\n\t"
+      "barrier.cta.red.or.aligned.pred q, %2, %3, p;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(r) : "r"((uint32_t)pred), "r"(id), "r"(nthreads) : "memory");
+  return r != 0;
+}
+// does the landed tile [bytes] at saddr hold the fill pattern in a row < rows?  Called by nthr threads (tid = index among
+// them); the tile is [K-blocks][2 planes][tile_rows x 128 B], so 16-byte chunk c lies in row (c >> 3) % tile_rows.
+__device__ __forceinline__ bool tile_has_fill(uint32_t saddr, uint32_t bytes, int tile_rows, int rows, int tid, int nthr) {
+  uint32_t low = 1u;                                       // min of ~word: 0 iff a word is the fill pattern
+  for (uint32_t c = (uint32_t)tid; c < bytes / 16; c += (uint32_t)nthr) {
+    if ((int)((c >> 3) % (uint32_t)tile_rows) < rows) {
+      const uint4 x = ld_shared_v4(saddr + c * 16u);
+      low = min(min(low, min(~x.x, ~x.y)), min(~x.z, ~x.w));
+    }
+  }
+  return low == 0u;
+}
+
+struct KFwd3 {
+  RecTcFwdArgs a;
+  int H, B, nslice, nkb, nkb_t;
+  int turns;                      // 1: the chains take turns at the TMA port and the tensor pipe (see the producer warps)
+  int fault;                      // STAMP instantiation only: delay half of every publish behind its hint (test of the retry path)
+  int endbar;                     // 1: the chain's four epilogue warps meet once more at the end of a step
+};
+
+// chain X stamps (STAMP instantiation, tests/gpu_diag.py xchg): event 8X + 0 counter seen, 1 fetch issued, 2 tile landed, 3 MMAs done,
+// 4 cell math done, 5 published, 6 end of step, 7 attempts so far
+#define RS_STAMP3(step, ev, val) do { if constexpr (STAMP) if (a.dbg && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) \
+    a.dbg[((size_t)(blockIdx.x ? a.T : 0) + (size_t)(step)) * 16 + 8 * X + (ev)] = (val); } while (0)
+template <int HH, bool STAMP>
+__global__ void __launch_bounds__(NTHREADS2, 1)
+rec_ts_fwd3_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmD0,
+                   const __grid_constant__ CUtensorMap tmD1, KFwd3 p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[2], tfull_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t retry_req[2];                                 // fetches of the current step asked for again, per chain (running count)
+  __shared__ uint32_t quit[2];                                      // the chain's last step is done
+  __shared__ uint32_t steps_done[2];                                // steps of the launch whose MMAs have completed, per chain
+  __shared__ uint32_t tiles_landed[2];                              // fetches of the launch that have landed, per chain
+  __shared__ __align__(128) __nv_bfloat16 sH[2][CHB][2][TSU];       // staged h_t per chain [b][plane][unit]
+  __shared__ __align__(128) __nv_bfloat16 sD[2][CHB][2][TSU];       // staged dropout(out_t) per chain
+  const RecTcFwdArgs& a = p.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x;
+  const int H = HH > 0 ? HH : p.H, B = p.B, T = a.T;
+  const int nkb = HH > 0 ? HH / 64 : p.nkb, nkb_t = HH > 0 ? HH / 64 : p.nkb_t, nslice = HH > 0 ? HH / TSU : p.nslice;
+  const int nkb_s = nkb - nkb_t;
+  constexpr uint32_t kb_bytes = 2u * CHB * 128u;                     // one K-block of a chain: hi rows, lo rows
+  const uint32_t slot_bytes = (uint32_t)nkb * kb_bytes;
+  unsigned char* sA = smem;                                          // [nkb_s][128 rows x 128 B] weight blocks outside TMEM
+  unsigned char* sRing = smem + (size_t)nkb_s * 16384;               // [2 chains][nkb][2 planes][16 rows x 128 B]
+  const uint32_t colD = (uint32_t)nkb_t * 32;
+
+  if (threadIdx.x == 0) {
+    for (int x = 0; x < 2; ++x) { tc::mbar_init(&full_bar[x], 1); tc::mbar_init(&tfull_bar[x], 1); retry_req[x] = 0; quit[x] = 0; steps_done[x] = 0; tiles_landed[x] = 0; }
+    tc::fence_mbar_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    // resident weights, as in rec_ts_fwd_kernel: TMEM lane = threadIdx.x; gate row 16q + (lane & 15), hi plane for lane < 16
+    const int row = j * 64 + 16 * warp + (lane & 15);
+    const __nv_bfloat16* src = ((lane < 16) ? a.wrec_hi : a.wrec_lo) + (size_t)row * H;
+    for (int c0 = 0; c0 < nkb_t * 32; c0 += 8) {
+      const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0));
+      const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0 + 8));
+      const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      tc::tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+    }
+    for (int kb = nkb_t; kb < nkb; ++kb) {
+      unsigned char* tile = sA + (size_t)(kb - nkb_t) * 16384 + (size_t)threadIdx.x * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(tile + ((c ^ (threadIdx.x & 7)) << 4)) = __ldg(reinterpret_cast<const uint4*>(src + kb * 64 + c * 8));
+    }
+    tc::tmem_st_wait();
+    tc::fence_proxy_async_smem();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+
+  if (warp == 8 || warp == 10) {
+    // ------------------------------------------------------------------ TMA producer of chain X
+    const int X = (warp - 8) >> 1;
+    if (lane == 0) tc::tma_prefetch_desc(&tmH);
+    __syncwarp();
+    const unsigned per_step = gridDim.x * 2u;                        // every CTA adds 2 per chain and step
+    const unsigned* ctr = a.barrier + 32 * X;
+    uint32_t served = 0;                                             // retry requests answered
+    // one box = nkb stacked tiles [kb][plane][16 rows][64]; row t*B + 16X = h_{t-1} of the chain's first utterance
+    auto fetch = [&](int t) {
+      tc::mbar_arrive_expect_tx_warp(&full_bar[X], slot_bytes);
+      tc::tma_load_4d_warp(sRing + (size_t)X * slot_bytes, &tmH, 0, t * B + CHB * X, 0, 0, &full_bar[X]);
+    };
+    // the epilogue found fill pattern in the tile of step t (after that attempt's MMAs had completed): fetch it again
+    auto serve = [&](int t) {
+      if (*reinterpret_cast<volatile uint32_t*>(&retry_req[X]) != served) { ++served; __syncwarp(); fetch(t); }
+    };
+    for (int ti = 0; ti < T; ++ti) {
+      const int t = a.t0 + ti;
+      if (ti > 0) {
+        uint32_t spins = 0;
+        while (ld_relaxed_u32(ctr) < per_step * (unsigned)ti) { serve(t - 1); if (++spins > (1u << 26)) __trap(); }
+        __syncwarp();
+      }
+      if (lane == 0) RS_STAMP3(ti, 0, gtime());
+      __syncwarp();
+      if (p.turns) {
+        // Two chains that start together stay together (measured: 6 ns apart after 900 steps, and they fall back into
+        // lockstep from either side of half a period): both tiles cross the SM's port at the same time and 2 x 48 MMAs
+        // queue on one tensor pipe, so that a step of either takes as long as the step of a 32-row batch.  So they take
+        // turns at the port: chain 1 fetches the tile of step ti when chain 0's tile of step ti has landed (turns == 1) or
+        // its MMAs are complete (turns == 2), chain 0 the tile of step ti + 1 when chain 1's of step ti has -- one chain
+        // computes while the other one exchanges.  (Retries only make the counts run ahead: a weaker constraint.)
+        const uint32_t need = (uint32_t)(ti + X);
+        const volatile uint32_t* other = p.turns == 2 ? &steps_done[X ^ 1] : &tiles_landed[X ^ 1];
+        while (*other < need) {}
+        __syncwarp();
+      }
+      fetch(t);
+      if (lane == 0) RS_STAMP3(ti, 1, gtime());
+      __syncwarp();
+    }
+    while (*reinterpret_cast<volatile uint32_t*>(&quit[X]) == 0) serve(a.t0 + T - 1);
+  } else if (warp == 9 || warp == 11) {
+    // ------------------------------------------------------------------ MMA issuer of chain X (converged warp): one batch per fetch
+    const int X = (warp - 9) >> 1;
+    const uint32_t idesc = tc::instr_desc_bf16(128, 2 * CHB);
+    const uint64_t dA0 = tc::smem_desc_sw128(tc::smem_u32(sA));
+    const uint64_t dB0 = tc::smem_desc_sw128(tc::smem_u32(sRing + (size_t)X * slot_bytes));
+    constexpr uint64_t kb_u = kb_bytes >> 4;
+    const uint32_t tmemD = tmem + colD + (uint32_t)(2 * CHB * X);
+    for (uint32_t n = 0;; ++n) {
+      tc::mbar_wait(&full_bar[X], n & 1);
+      if (*reinterpret_cast<volatile uint32_t*>(&quit[X]) != 0) break;
+      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&tiles_landed[X]) = n + 1;
+      tc::tc_fence_after();
+      if constexpr (STAMP) { if (lane == 0 && n < (uint32_t)T) RS_STAMP3(n, 2, gtime()); __syncwarp(); }   // tile landed (batch n = step n without retries)
+      issue_ts_blocks<12>(nkb_t, tmemD, tmem, dB0, kb_u, idesc, 0u);                                       // 12: H = 768
+      for (int kb = nkb_t; kb < nkb; ++kb)
+        tc::mma4_bf16_ss_warp(tmemD, dA0 + (uint64_t)(kb - nkb_t) * (16384 >> 4), dB0 + (uint64_t)kb * kb_u, idesc, (uint32_t)(kb != 0));
+      tc::mma_commit_warp(&tfull_bar[X]);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps of chain X = warp >> 2
+    const int q = warp & 3, X = warp >> 2, l16 = lane & 15, up = lane >> 4;
+    const int m = q * 16 + l16;                 // gate row (hi copy in lanes 0..15, lo copy in 16..31)
+    const int g = lane & 3;                     // gate of this row: 0 i, 1 j, 2 f, 3 o
+    const int ul = m >> 2;                      // unit inside the slice
+    const int unit = j * TSU + ul;
+    const int ctid = (int)threadIdx.x & 127;    // thread inside the chain
+    const int rowsX = min(max(B - CHB * X, 0), CHB);
+    const uint32_t tmemD = tmem + colD + (uint32_t)(2 * CHB * X) + ((uint32_t)(q * 32) << 16);
+    const bool leader = ctid == 0;
+    const CUtensorMap* tmD = X ? &tmD1 : &tmD0;
+    unsigned* ctr = a.barrier + 32 * X;
+    unsigned char* hbase = reinterpret_cast<unsigned char*>(a.h_hi);
+    const size_t row_bytes = (size_t)4 * H;                          // [hi H | lo H] bf16
+    // publish side: thread ctid < 64 stores the 16-byte half `phalf` of (row pbl, plane ppl) of the staged tile
+    const int pbl = ctid >> 2, ppl = (ctid >> 1) & 1, phalf = ctid & 1;
+    const bool publisher = ctid < 64 && pbl < rowsX;
+    const int ncol = min(max(rowsX - 8 * up, 0), 8);                 // batch columns of this lane that exist
+    float c[2], hl[2];
+    int lenr[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int b = X * CHB + 8 * up + 2 * g + k;
+      const bool ok = b < B;
+      c[k] = ok ? a.c0[(size_t)b * H + unit] : 0.f;
+      hl[k] = ok ? a.h0[(size_t)b * H + unit] : 0.f;
+      lenr[k] = ok ? a.len[b] : 0;
+    }
+    const float fbias = (g == 2) ? 1.0f : 0.0f;          // forget_bias
+    const float pre = (g == 1) ? 2.0f : 1.0f;            // tanh(x) = 2*sigmoid(2x) - 1
+    const float post_m = (g == 1) ? 2.0f : 1.0f, post_a = (g == 1) ? -1.0f : 0.0f;
+    float2* blob = reinterpret_cast<float2*>(a.gates);
+    uint32_t n = 0;                                      // MMA batches consumed
+
+    for (int ti = 0; ti < T; ++ti) {
+      const int t = a.t0 + ti;
+      // hoisted input projection for this step (independent of the recurrence: issue early); Bpad = 32, group X
+      const float4* gp = reinterpret_cast<const float4*>(a.gx + (((size_t)t * nslice + j) * 64 + m) * 32 + X * 16 + 8 * up);
+      const float4 gx0 = __ldg(gp), gx1 = __ldg(gp + 1);
+      float ig[2], jg[2], fg[2], og[2], c_new[2], h_new[2], hout[2];
+      for (;;) {
+        tc::mbar_wait(&tfull_bar[X], n & 1);
+        ++n;
+        tc::tc_fence_after();
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&steps_done[X]) = (uint32_t)(ti + 1);     // (every warp: whichever wakes first)
+        if (leader) RS_STAMP3(ti, 3, gtime());
+        float v[16], w[16];
+        tc::tmem_ld16(tmemD, v);                               // hi rows: W_hi h_hi ; lo rows: W_lo h_hi
+        tc::tmem_ld16(tmemD + (uint32_t)CHB, w);               // hi rows: W_hi h_lo
+        tc::tmem_ld_wait();
+        float act[8];
+        const float xs[8] = {gx0.x, gx0.y, gx0.z, gx0.w, gx1.x, gx1.y, gx1.z, gx1.w};
+        bool nan = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float s_a = v[i] + w[i], s_b = v[8 + i] + w[8 + i];
+          const float got = __shfl_xor_sync(0xffffffffu, up ? v[i] : s_b, 16);
+          const float z = ((up ? (got + v[8 + i]) : (s_a + got)) + xs[i] + fbias) * pre;
+          nan = nan || (i < ncol && z != z);                   // fill pattern anywhere in tile row 8 up + i (either plane)
+          act[i] = fmaf(fast_sigmoid(z), post_m, post_a);
+        }
+        float own[2], rcv[3][2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) own[k] = pick4(g, act[k], act[2 + k], act[4 + k], act[6 + k]);
+#pragma unroll
+        for (int d = 1; d < 4; ++d)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const float snd = pick4(g ^ d, act[k], act[2 + k], act[4 + k], act[6 + k]);
+            rcv[d - 1][k] = __shfl_xor_sync(0xffffffffu, snd, d);
+          }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          ig[k] = pick4(g ^ 0, own[k], rcv[0][k], rcv[1][k], rcv[2][k]);
+          jg[k] = pick4(g ^ 1, own[k], rcv[0][k], rcv[1][k], rcv[2][k]);
+          fg[k] = pick4(g ^ 2, own[k], rcv[0][k], rcv[1][k], rcv[2][k]);
+          og[k] = pick4(g ^ 3, own[k], rcv[0][k], rcv[1][k], rcv[2][k]);
+          c_new[k] = c[k] * fg[k] + ig[k] * jg[k];
+          h_new[k] = fast_tanh(c_new[k]) * og[k];
+          const int bl = 8 * up + 2 * g + k;                   // row inside the chain
+          hout[k] = (t < lenr[k]) ? h_new[k] : 0.f;
+          __nv_bfloat16 hh, hlo;
+          tc::split_bf16(hout[k], hh, hlo);
+          sH[X][bl][0][ul] = hh;                               // staged, not yet published
+          sH[X][bl][1][ul] = hlo;
+        }
+        tc::tc_fence_before();
+        if (leader) RS_STAMP3(ti, 4, gtime());
+        // the barrier before the publish doubles as the vote on the tile (NaN = fill pattern, or the model's own NaN)
+        if (!bar_any(1 + X, 128, nan)) break;
+        const bool stale = bar_any(1 + X, 128, ti > 0 && tile_has_fill(tc::smem_u32(sRing + (size_t)X * slot_bytes), slot_bytes, CHB, rowsX, ctid, 128));
+        if (!stale) break;
+        if (leader) *reinterpret_cast<volatile uint32_t*>(&retry_req[X]) = *reinterpret_cast<volatile uint32_t*>(&retry_req[X]) + 1u;
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (t < lenr[k]) { c[k] = c_new[k]; hl[k] = h_new[k]; }
+      // publish h_t: slot t + 1, this CTA's 16 units of every row of the chain -- one 32-byte sector per (row, plane) --
+      // and the hint
+      if (q < 2) {
+        void* dst = hbase + (size_t)((t + 1) * B + CHB * X + pbl) * row_bytes + (size_t)ppl * (2 * H) + (size_t)(j * TSU + phalf * 8) * 2;
+        const uint4 hv = *reinterpret_cast<const uint4*>(&sH[X][pbl][ppl][phalf * 8]);
+        bool faulty = false;
+        if constexpr (STAMP) faulty = p.fault != 0;
+        if (!faulty) {
+          if (publisher) st_relaxed_v4(dst, hv);
+          __syncwarp();
+          if (lane == 0 && ti + 1 < T) red_relaxed_add(ctr, 1u);
+        } else {
+          // test of the retry path: the hint overtakes half of the data by 3 us
+          if (publisher && !phalf) st_relaxed_v4(dst, hv);
+          __syncwarp();
+          if (lane == 0 && ti + 1 < T) red_relaxed_add(ctr, 1u);
+          const unsigned long long until = gtime() + 3000ull;
+          while (gtime() < until) {}
+          __syncwarp();
+          if (publisher && phalf) st_relaxed_v4(dst, hv);
+        }
+      }
+      if (leader) { RS_STAMP3(ti, 5, gtime()); RS_STAMP3(ti, 7, (unsigned long long)n); }
+      // reserve for backward (not on the critical path of the recurrence)
+      if (blob) {
+        blob[blob_idx(t, nslice, j, 1, 0, 0, warp, lane)] = make_float2(ig[0], ig[1]);
+        blob[blob_idx(t, nslice, j, 1, 0, 1, warp, lane)] = make_float2(jg[0], jg[1]);
+        blob[blob_idx(t, nslice, j, 1, 0, 2, warp, lane)] = make_float2(fg[0], fg[1]);
+        blob[blob_idx(t, nslice, j, 1, 0, 3, warp, lane)] = make_float2(og[0], og[1]);
+        blob[blob_idx(t, nslice, j, 1, 0, 4, warp, lane)] = make_float2(c_new[0], c_new[1]);
+      }
+      // fused hop: dropout(out_t) planes for the next layer / the output dense
+      if (a.drop_hi) {
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the previous hop store has read sD
+        chain_bar_sync(X);                                     // (also: every publisher has read sH)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int bl = 8 * up + 2 * g + k;
+          float dv = hout[k];
+          const unsigned long long idx = ((unsigned long long)t * B + (X * CHB + bl)) * H + unit;
+          if (a.drop_thr_a != 0xffffffffu) dv = dropout_keep(a.drop_key, a.drop_sa, idx, a.drop_thr_a) ? dv * a.drop_inv_a : 0.f;
+          if (a.drop_thr_b != 0xffffffffu) dv = dropout_keep(a.drop_key, a.drop_sb, idx, a.drop_thr_b) ? dv * a.drop_inv_b : 0.f;
+          __nv_bfloat16 dh_, dl_;
+          tc::split_bf16(dv, dh_, dl_);
+          sD[X][bl][0][ul] = dh_;
+          sD[X][bl][1][ul] = dl_;
+        }
+        tc::fence_proxy_async_smem();
+        chain_bar_sync(X);
+        if (leader) {
+          tc::tma_store_3d(tmD, &sD[X][0][0][0], j * TSU, 0, t * B + CHB * X);
+          tc::bulk_commit();
+        }
+      }
+      // (sH is staged again only after the next fetch, i.e. after the grid-wide count that includes this CTA's two adds,
+      //  each of which follows its warp's reads of sH -- except with the injected fault, where the add comes first)
+      if (p.endbar) chain_bar_sync(X);
+      if (leader) RS_STAMP3(ti, 6, gtime());
+    }
+    if (leader) {
+      // release the chain's producer and MMA warps
+      *reinterpret_cast<volatile uint32_t*>(&quit[X]) = 1u;
+      tc::mbar_arrive(&full_bar[X]);
+      if (a.drop_hi) tc::bulk_wait_all();
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int b = X * CHB + 8 * up + 2 * g + k;
+      if (b < B) {
+        if (a.cT) a.cT[(size_t)b * H + unit] = c[k];
+        if (a.hT) a.hT[(size_t)b * H + unit] = hl[k];
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------
 struct KBwd {
@@ -740,6 +1107,7 @@ struct KBwd {
   int nlo_t;                               // K-blocks of Wh_lo resident in tensor memory (the other nkbs - nlo_t in smem)
   int variant;
   uint32_t tmem_cols;
+  int fault;                               // STAMP instantiation of rec_ts_bwd3_kernel: delay half of every publish behind its hint
 };
 
 // 128 registers (no spills; 168 unconstrained) x 320 threads and ~50 KB of shared memory: with RS_TC_CORES=1 a 256-thread
@@ -1060,6 +1428,353 @@ rec_ts_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   if (warp == 8) tc::tmem_dealloc(tmem, p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------
+// Backward with the validated exchange of rec_ts_fwd3_kernel (bf16x3 only).  The dgates planes of the launch's steps
+// carry the fill pattern until their producers overwrite it; a CTA publishes its 4 x 16 columns of dgates_t with 16-byte
+// st.relaxed.gpu stores and a relaxed `red` per warp (the hint), the producer warp fetches the K segment with one TMA box
+// when the counter says so.  A tile row (one utterance's dgates) that still holds fill pattern makes that batch column of
+// the partial dh NaN in all 128 unit rows; unlike forward the result of the MMAs leaves the CTA before the cell math (the
+// reduce-scatter through distributed shared memory), so the epilogue warps vote on their accumulator columns in a barrier of
+// their own before they push; a NaN vote takes the slow path of rec_ts_fwd3_kernel (scan for the fill pattern, fetch and
+// multiply again if it is there).
+// ------------------------------------------------------------------------------------
+#define RS_STAMPB(step, ev, val) do { if constexpr (STAMP) if (a.dbg && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) \
+    a.dbg[((size_t)(blockIdx.x ? a.T : 0) + (size_t)((step) - a.t0)) * 16 + (ev)] = (val); } while (0)
+template <bool STAMP, int BPAD, int HH>
+__global__ void __maxnreg__(128)
+rec_ts_bwd3_kernel(const __grid_constant__ CUtensorMap tmG, KBwd p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar, tfull_bar, recv_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t retry_req, quit;                   // fetches asked for again (running count); the last step is done
+  const RecTcBwdArgs& a = p.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = HH > 0 ? HH : p.H, B = p.B, Bpad = BPAD > 0 ? BPAD : p.Bpad, T = a.T, nkbs = HH > 0 ? HH / 128 : p.nkbs, G = 4 * H;
+  const int nslice = HH > 0 ? HH / TSU : p.nslice;
+  const uint32_t rank = cluster_ctarank();            // K segment / owned unit slice inside the 128-unit block
+  const int blk = blockIdx.x / CL;
+  const int j = blk * CL + (int)rank;                   // 16-unit slice (same numbering as forward)
+  const int kseg0 = (int)rank * (H / 2);                // first dgates column of this CTA's K segment
+  const int nlo_t = HH > 0 ? HH / 128 : p.nlo_t;
+  const int nlo_s = nkbs - nlo_t;
+  const uint32_t kb_bytes = (uint32_t)Bpad * 128 * 2u;                       // one streamed K-block: hi rows ; lo rows
+  unsigned char* sG = smem;                                                  // [nkbs][2 planes][Bpad x 128 B] dgates_t K segment
+  unsigned char* sAlo = smem + (size_t)nkbs * kb_bytes;                      // [nlo_s][128 rows x 128 B] Wh_lo blocks outside TMEM
+  float* sR = reinterpret_cast<float*>(sAlo + (size_t)nlo_s * 16384);        // [CL src][16 units][Bpad] partial dh
+  __nv_bfloat16* sDG = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(sR) + (size_t)CL * TSU * Bpad * 4);
+                                                                             // [2 planes][Bpad][4 gates][16 units]
+  const uint32_t colLo = (uint32_t)(H / 4);              // Wh_hi: columns [0, H/4); Wh_lo: nlo_t blocks of 32 columns behind
+  const uint32_t colD = colLo + (uint32_t)nlo_t * 32;
+  const int t1 = a.t0 + T;                                // this launch: steps t1 - 1 down to t0
+  const bool primed = t1 < a.Ttot;                        // dh_{t1-1} comes from dgates_{t1} of the previous launch
+  const int ts_first = primed ? t1 : t1 - 1;              // first dgates step streamed through the tensor core
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&full_bar, 1);
+    tc::mbar_init(&tfull_bar, 1);
+    tc::mbar_init(&recv_bar, 1);
+    retry_req = 0; quit = 0;
+    tc::fence_mbar_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&tmem_slot, p.tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp < 4) {
+    // resident Wh[128 rows of the block][K segment]: TMEM lane = threadIdx.x = hidden unit k
+    const __nv_bfloat16* src = a.wh_hi + (size_t)(blk * 128 + (int)threadIdx.x) * G + kseg0;
+    for (int c0 = 0; c0 < H / 4; c0 += 8) {
+      const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0));
+      const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0 + 8));
+      const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      tc::tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+    }
+    const __nv_bfloat16* srcl = a.wh_lo + (size_t)(blk * 128 + (int)threadIdx.x) * G + kseg0;
+    for (int c0 = 0; c0 < nlo_t * 32; c0 += 8) {
+      const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(srcl + 2 * c0));
+      const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(srcl + 2 * c0 + 8));
+      const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      tc::tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + colLo + (uint32_t)c0, r);
+    }
+    for (int kb = nlo_t; kb < nkbs; ++kb) {
+      unsigned char* tile = sAlo + (size_t)(kb - nlo_t) * 16384 + (size_t)threadIdx.x * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(tile + ((c ^ (threadIdx.x & 7)) << 4)) = __ldg(reinterpret_cast<const uint4*>(srcl + kb * 64 + c * 8));
+    }
+    if (nlo_s > 0) tc::fence_proxy_async_smem();
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  cluster_sync_all();                                   // peers' mbarriers are initialised before any st.async
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) tc::tma_prefetch_desc(&tmG);
+    __syncwarp();
+    const unsigned per_step = gridDim.x * 8u;
+    const uint32_t tile_bytes = (uint32_t)nkbs * kb_bytes;
+    unsigned epoch = 0;
+    uint32_t served = 0;                                 // retry requests answered
+    auto fetch = [&](int t) {
+      tc::mbar_arrive_expect_tx_warp(&full_bar, tile_bytes);
+      tc::tma_load_4d_warp(sG, &tmG, 0, t * B, 0, kseg0 / 64, &full_bar);         // one box: [kb][plane][Bpad][64]
+    };
+    auto serve = [&](int t) {
+      if (*reinterpret_cast<volatile uint32_t*>(&retry_req) != served) { ++served; __syncwarp(); fetch(t); }
+    };
+    for (int t = ts_first; t >= a.t0 + 1; --t) {        // dh_{t-1} from dgates_t
+      if (t < t1) {                                       // dgates_t comes from this launch: wait for the hint
+        ++epoch;
+        uint32_t spins = 0;
+        while (ld_relaxed_u32(a.barrier) < per_step * epoch) { serve(t + 1); if (++spins > (1u << 26)) __trap(); }
+        __syncwarp();
+      }
+      if (lane == 0) RS_STAMPB(t, 0, gtime());
+      __syncwarp();
+      fetch(t);
+      if (lane == 0) RS_STAMPB(t, 1, gtime());
+      __syncwarp();
+    }
+    while (*reinterpret_cast<volatile uint32_t*>(&quit) == 0) serve(a.t0 + 1);
+  } else if (warp == 9) {
+    const uint32_t idesc = tc::instr_desc_bf16(128, Bpad);               // N = one plane
+    const uint32_t idesc2 = tc::instr_desc_bf16(128, 2 * Bpad);          // N = both planes stacked
+    const uint64_t dg0 = tc::smem_desc_sw128(tc::smem_u32(sG));
+    const uint64_t dAlo0 = tc::smem_desc_sw128(tc::smem_u32(sAlo));
+    const uint32_t tmemD = tmem + colD;
+    for (uint32_t n = 0;; ++n) {                       // one batch of MMAs per fetch
+      tc::mbar_wait(&full_bar, n & 1);
+      if (*reinterpret_cast<volatile uint32_t*>(&quit) != 0) break;
+      tc::tc_fence_after();
+      // D[:, 0:2Bpad) = Wh_hi [dg_hi | dg_lo] ; D[:, 0:Bpad) += Wh_lo dg_hi
+      issue_ts_blocks<6>(nkbs, tmemD, tmem, dg0, (uint64_t)(kb_bytes >> 4), idesc2, 0u);                             // 6: H = 768
+      issue_ts_blocks<6>(nlo_t, tmemD, tmem + colLo, dg0, (uint64_t)(kb_bytes >> 4), idesc, 1u);
+      for (int i = nlo_t; i < nkbs; ++i)
+        tc::mma4_bf16_ss_warp(tmemD, dAlo0 + (uint64_t)(i - nlo_t) * (16384 >> 4), dg0 + (uint64_t)i * (kb_bytes >> 4), idesc, 1u);
+      tc::mma_commit_warp(&tfull_bar);
+    }
+  } else {
+    const int q = warp & 3, hf = warp >> 2, l16 = lane & 15, up = lane >> 4;
+    const int g = lane & 3;
+    const int ul = q * 4 + (l16 >> 2);                   // owned unit inside the slice (cell math)
+    const int unit = j * TSU + ul;
+    const int ng = Bpad / 16;
+    const uint32_t tmemD = tmem + colD + ((uint32_t)(q * 32) << 16);
+    // push side: TMEM lane 32q + lane = unit 32q + lane of the block -> owner rank, unit inside its slice
+    const uint32_t owner = (uint32_t)(2 * q + up);
+    const uint32_t sR_local = tc::smem_u32(sR);
+    const uint32_t push_base = mapa_u32(sR_local + (uint32_t)(((int)rank * TSU + l16) * Bpad) * 4u, owner);
+    const uint32_t push_bar = mapa_u32(tc::smem_u32(&recv_bar), owner);
+    const float2* blob = reinterpret_cast<const float2*>(a.gates);
+    int lenr[MAXG][2];
+    float dc[MAXG][2];
+#pragma unroll
+    for (int gl = 0; gl < MAXG; ++gl)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int b = (hf + 2 * gl) * 16 + 8 * up + 2 * g + k;
+        lenr[gl][k] = ((hf + 2 * gl) < ng && b < B) ? a.len[b] : 0;
+        dc[gl][k] = 0.f;
+      }
+    float2* carry = reinterpret_cast<float2*>(a.dc_carry);
+    if (primed && carry) {
+#pragma unroll
+      for (int gl = 0; gl < MAXG; ++gl) {
+        const float2 x = carry[(((size_t)j * MAXG + gl) * 8 + warp) * 32 + lane];
+        dc[gl][0] = x.x; dc[gl][1] = x.y;
+      }
+    }
+    const unsigned nchunk = (unsigned)(2 * Bpad * 4 * 2);     // 16-byte chunks of the staged dgates tile
+    uint32_t n = primed ? 1u : 0u;                            // n - 1 = index of the MMA batch this step consumes
+    uint32_t na = 0;                                          // MMA batches consumed
+    for (int t = t1 - 1; t >= a.t0; --t, ++n) {
+      // operands of the cell backward (independent of the recurrence: issue before waiting)
+      float2 it2[MAXG][BLOB_ITEMS], cp2[MAXG];
+      float dy[MAXG][2];
+#pragma unroll
+      for (int gl = 0; gl < MAXG; ++gl) {
+        const int gi = hf + 2 * gl;
+        if (gi < ng) {
+#pragma unroll
+          for (int it = 0; it < BLOB_ITEMS; ++it) it2[gl][it] = __ldg(blob + blob_idx(t, nslice, j, p.ngl, gl, it, warp, lane));
+          if (t > 0) cp2[gl] = __ldg(blob + blob_idx(t - 1, nslice, j, p.ngl, gl, 4, warp, lane));
+          float cpv[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int b = gi * 16 + 8 * up + 2 * g + k;
+            float d = (b < B) ? __ldg(a.dout + ((size_t)t * B + b) * H + unit) : 0.f;
+            // backward of the hop's dropout(s): the same masks, applied as the gradient is read
+            const unsigned long long idx = ((unsigned long long)t * B + b) * H + unit;
+            if (a.drop_thr_a != 0xffffffffu) d = dropout_keep(a.drop_key, a.drop_sa, idx, a.drop_thr_a) ? d * a.drop_inv_a : 0.f;
+            if (a.drop_thr_b != 0xffffffffu) d = dropout_keep(a.drop_key, a.drop_sb, idx, a.drop_thr_b) ? d * a.drop_inv_b : 0.f;
+            dy[gl][k] = d;
+            cpv[k] = (t == 0 && b < B) ? __ldg(a.c0 + (size_t)b * H + unit) : 0.f;
+          }
+          if (t == 0) cp2[gl] = make_float2(cpv[0], cpv[1]);
+        }
+      }
+      float dh[MAXG][2];
+#pragma unroll
+      for (int gl = 0; gl < MAXG; ++gl) dh[gl][0] = dh[gl][1] = 0.f;
+      if (n > 0) {
+        // partial dh_t^T of this CTA's K segment -> reduce-scatter over the cluster
+        if (threadIdx.x == 0) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                       ::"r"(tc::smem_u32(&recv_bar)), "r"((uint32_t)(CL * TSU * Bpad * 4)) : "memory");
+        }
+        float v[MAXG][16];
+        const bool fresh = t + 1 < t1;                          // the tile (dgates_{t+1}) was produced by this launch
+        for (;;) {
+          tc::mbar_wait(&tfull_bar, na & 1);
+          ++na;
+          tc::tc_fence_after();
+          if (threadIdx.x == 0) RS_STAMPB(t, 3, gtime());
+          bool nan = false;
+#pragma unroll
+          for (int gl = 0; gl < MAXG; ++gl) {
+            const int gi = hf + 2 * gl;
+            if (gi < ng) {
+              float w[16];
+              tc::tmem_ld16(tmemD + (uint32_t)(gi * 16), v[gl]);
+              tc::tmem_ld16(tmemD + (uint32_t)(Bpad + gi * 16), w);      // Wh_hi dg_lo
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                v[gl][i] += w[i];
+                nan = nan || (gi * 16 + i < B && v[gl][i] != v[gl][i]);   // fill pattern in tile row gi*16 + i (either plane)
+              }
+            }
+          }
+          tc::tc_fence_before();
+          // the accumulator may leave the CTA only when its tile is known to have been complete: vote
+          if (!bar_any(1, 256, nan)) break;
+          const bool stale = bar_any(1, 256, fresh && tile_has_fill(tc::smem_u32(sG), (uint32_t)nkbs * kb_bytes, Bpad, B, (int)threadIdx.x, 256));
+          if (!stale) break;                                      // the model's own NaN
+          if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(&retry_req) = *reinterpret_cast<volatile uint32_t*>(&retry_req) + 1u;
+        }
+#pragma unroll
+        for (int gl = 0; gl < MAXG; ++gl) {
+          const int gi = hf + 2 * gl;
+          if (gi < ng) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              st_async_v4(push_base + (uint32_t)(gi * 16 + 4 * i) * 4u, make_float4(v[gl][4 * i], v[gl][4 * i + 1], v[gl][4 * i + 2], v[gl][4 * i + 3]),
+                          push_bar);
+          }
+        }
+        tc::tc_fence_before();
+        if (threadIdx.x == 0) RS_STAMPB(t, 4, gtime());
+        tc::mbar_wait(&recv_bar, (n - 1) & 1);
+        if (threadIdx.x == 0) RS_STAMPB(t, 5, gtime());
+#pragma unroll
+        for (int gl = 0; gl < MAXG; ++gl) {
+          const int gi = hf + 2 * gl;
+          if (gi < ng) {
+#pragma unroll
+            for (int s = 0; s < CL; ++s) {
+              const float2 x = *reinterpret_cast<const float2*>(sR + ((size_t)s * TSU + ul) * Bpad + gi * 16 + 8 * up + 2 * g);
+              dh[gl][0] += x.x; dh[gl][1] += x.y;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int gl = 0; gl < MAXG; ++gl) {
+        const int gi = hf + 2 * gl;
+        if (gi < ng) {
+          const float* pi = reinterpret_cast<const float*>(&it2[gl][0]);
+          const float* pj = reinterpret_cast<const float*>(&it2[gl][1]);
+          const float* pf = reinterpret_cast<const float*>(&it2[gl][2]);
+          const float* po = reinterpret_cast<const float*>(&it2[gl][3]);
+          const float* pct = reinterpret_cast<const float*>(&it2[gl][4]);
+          const float* pcp = reinterpret_cast<const float*>(&cp2[gl]);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int b = gi * 16 + 8 * up + 2 * g + k;
+            float di = 0.f, dj = 0.f, df = 0.f, dob = 0.f;
+            if (t < lenr[gl][k]) {
+              const float ig = pi[k], jg = pj[k], fg = pf[k], og = po[k];
+              const float dh_tot = dh[gl][k] + dy[gl][k];
+              const float tch = fast_tanh(pct[k]);
+              dob = dh_tot * tch * og * (1.f - og);
+              const float dc_tot = dc[gl][k] + dh_tot * og * (1.f - tch * tch);
+              di = dc_tot * jg * ig * (1.f - ig);
+              dj = dc_tot * ig * (1.f - jg * jg);
+              df = dc_tot * pcp[k] * fg * (1.f - fg);
+              dc[gl][k] = dc_tot * fg;
+            }
+            const float d4[4] = {di, dj, df, dob};
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) {
+              __nv_bfloat16 h0, l0;
+              tc::split_bf16(d4[gg], h0, l0);
+              sDG[(((size_t)0 * Bpad + b) * 4 + gg) * TSU + ul] = h0;
+              sDG[(((size_t)1 * Bpad + b) * 4 + gg) * TSU + ul] = l0;
+            }
+          }
+        }
+      }
+      if (threadIdx.x == 0) RS_STAMPB(t, 6, gtime());
+      epi_bar_sync();
+      // publish dgates_t: 16-byte stores of the staged tile (one 32-byte sector per (row, gate, plane)), then the hint
+      bool faulty = false;
+      if constexpr (STAMP) faulty = p.fault != 0;
+      if (!faulty) {
+        for (unsigned ch = threadIdx.x; ch < nchunk; ch += 256) {
+          const int half = ch & 1, gg = (ch >> 1) & 3, b = (ch >> 3) % Bpad, pl = (ch >> 3) / Bpad;
+          if (b < B) {
+            const uint4 x = *reinterpret_cast<const uint4*>(sDG + (((size_t)pl * Bpad + b) * 4 + gg) * TSU + half * 8);
+            st_relaxed_v4((pl ? a.dg_lo : a.dg_hi) + ((size_t)t * B + b) * G + (size_t)gg * H + j * TSU + half * 8, x);
+          }
+        }
+        __syncwarp();
+        if (lane == 0 && t > a.t0) red_relaxed_add(a.barrier, 1u);
+      } else {
+        // test of the retry path: the hint overtakes the odd chunks by 3 us (Bpad <= 32: at most two chunks per thread)
+        uint4 x[2];
+        __nv_bfloat16* dst[2];
+        int nx = 0;
+        for (unsigned ch = threadIdx.x; ch < nchunk && nx < 2; ch += 256) {
+          const int half = ch & 1, gg = (ch >> 1) & 3, b = (ch >> 3) % Bpad, pl = (ch >> 3) / Bpad;
+          x[nx] = *reinterpret_cast<const uint4*>(sDG + (((size_t)pl * Bpad + b) * 4 + gg) * TSU + half * 8);
+          dst[nx] = b < B ? (pl ? a.dg_lo : a.dg_hi) + ((size_t)t * B + b) * G + (size_t)gg * H + j * TSU + half * 8 : nullptr;
+          ++nx;
+        }
+        const bool late = threadIdx.x & 1;
+        if (!late) for (int i = 0; i < nx; ++i) if (dst[i]) st_relaxed_v4(dst[i], x[i]);
+        __syncwarp();
+        if (lane == 0 && t > a.t0) red_relaxed_add(a.barrier, 1u);
+        const unsigned long long until = gtime() + 3000ull;
+        while (gtime() < until) {}
+        __syncwarp();
+        if (late) for (int i = 0; i < nx; ++i) if (dst[i]) st_relaxed_v4(dst[i], x[i]);
+      }
+      if (threadIdx.x == 0) { RS_STAMPB(t, 7, gtime()); RS_STAMPB(t, 8, (unsigned long long)na); }
+      // (the staged tile is rewritten only after the next tfull wait, i.e. after a fetch that follows the grid-wide
+      //  count, which needs all eight adds above, each of which follows its warp's reads of the tile)
+    }
+    if (threadIdx.x == 0) {
+      // release the producer and MMA warps
+      *reinterpret_cast<volatile uint32_t*>(&quit) = 1u;
+      tc::mbar_arrive(&full_bar);
+    }
+    if (carry) {
+#pragma unroll
+      for (int gl = 0; gl < MAXG; ++gl)
+        carry[(((size_t)j * MAXG + gl) * 8 + warp) * 32 + lane] = make_float2(dc[gl][0], dc[gl][1]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) tc::tmem_dealloc(tmem, p.tmem_cols);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------
@@ -1138,7 +1853,51 @@ int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a_in, cudaStream
   const int hrows = (a.Ttot + 1) * g.B;
   // two independent 16-row chains per CTA (rec_ts_fwd2_kernel) when the batch allows it; RS_TS_CHAINS=0: one chain
   static const bool chains_env = [] { const char* v = getenv("RS_TS_CHAINS"); return !(v && v[0] == '0'); }();
-  if (chains_env && !a.dbg && ts_variant() == kDefaultVariant && g.Bpad == 32 && g.B > CHB && g.gkb == g.H / 64 && g.stages == 1) {
+  const bool shape2 = chains_env && ts_variant() == kDefaultVariant && g.Bpad == 32 && g.B > CHB && g.gkb == g.H / 64 && g.stages == 1;
+  const bool two_chains = shape2 && !a.dbg;
+  // self-validating exchange (rec_ts_fwd3_kernel; RS_TS_XCHG=0: the counter + TMA exchange of rec_ts_fwd2_kernel)
+  static const bool xchg_env = [] { const char* v = getenv("RS_TS_XCHG"); return !(v && v[0] == '0'); }();
+  if (shape2 && xchg_env) {
+    CUtensorMap td0, td1;
+    if ((rc = tmap_stacked_bf16(&th, a.h_hi, hrows, g.H, CHB, g.gkb)) != RS_OK) return rc;
+    td0 = th; td1 = th;
+    if (a.drop_hi) {
+      RS_REQUIRE(a.drop_lo > a.drop_hi, RS_ERR_INVALID, "lstm_rec_ts_forward: the low hop plane must follow the high one");
+      const size_t pstride = (size_t)((const char*)a.drop_lo - (const char*)a.drop_hi);
+      if ((rc = tmap_store3_bf16(&td0, a.drop_hi, g.H, 2, a.Ttot * g.B, pstride, (size_t)g.H * 2, TSU, 2, CHB)) != RS_OK) return rc;
+      if ((rc = tmap_store3_bf16(&td1, a.drop_hi, g.H, 2, a.Ttot * g.B, pstride, (size_t)g.H * 2, TSU, 2, g.B - CHB)) != RS_OK) return rc;
+    }
+    // slots 1..Ttot of the planes carry the fill pattern until their producers overwrite it (first launch of a pass)
+    if (a.t0 == 0)
+      RS_CHECK_CUDA(cudaMemsetAsync(a.h_hi + (size_t)g.B * a.h_ld, 0xff, (size_t)a.Ttot * g.B * a.h_ld * sizeof(__nv_bfloat16), st));
+    KFwd3 p3;
+    p3.a = a;
+    p3.H = g.H; p3.B = g.B; p3.nslice = g.nslice; p3.nkb = g.H / 64; p3.nkb_t = g.nkb_t;
+    static const int turns_env = [] { const char* v = getenv("RS_TS_TURNS"); return v ? atoi(v) : 1; }();
+    p3.turns = turns_env;
+    { const char* v = getenv("RS_TS_FAULT"); p3.fault = (a.dbg && v && v[0] == '1') ? 1 : 0; }
+    static const int endbar_env = [] { const char* v = getenv("RS_TS_ENDBAR"); return v ? atoi(v) : 0; }();
+    p3.endbar = (endbar_env || p3.fault) ? 1 : 0;
+    RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
+    const bool fast3 = g.H == 768 && g.nkb_t == 12;
+    auto kern3 = a.dbg ? (fast3 ? rec_ts_fwd3_kernel<768, true> : rec_ts_fwd3_kernel<0, true>) : fast3 ? rec_ts_fwd3_kernel<768, false> : rec_ts_fwd3_kernel<0, false>;
+    static size_t checked3_smem[kMaxDevices * 4] = {};
+    static int checked3_cap[kMaxDevices * 4] = {};
+    const int s3 = device_slot() * 4 + (a.dbg ? (fast3 ? 3 : 2) : fast3 ? 1 : 0);
+    if (checked3_smem[s3] != g.smem_bytes) {
+      int per_sm = 0;
+      RS_CHECK_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+      RS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern3, NTHREADS2, g.smem_bytes));
+      checked3_cap[s3] = per_sm * sm_count();
+      checked3_smem[s3] = g.smem_bytes;
+    }
+    RS_REQUIRE(checked3_cap[s3] >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_ts_forward: %d CTAs cannot be co-resident", g.nslice);
+    kern3<<<dim3(g.nslice), dim3(NTHREADS2), g.smem_bytes, st>>>(th, td0, td1, p3);
+    RS_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return RS_OK;
+  }
+  if (two_chains) {
     CUtensorMap ts0, ts1, td0, td1;
     if ((rc = tmap_stacked_bf16(&th, a.h_hi, hrows, g.H, CHB, g.gkb)) != RS_OK) return rc;
     if ((rc = tmap_store3_bf16(&ts0, a.h_hi, g.H, 2, hrows, (size_t)g.H * 2, (size_t)2 * g.H * 2, TSU, 2, CHB)) != RS_OK) return rc;
@@ -1243,6 +2002,7 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
   while ((int)cols < g.H / 4 + nlo_t * 32 + dcols) cols <<= 1;
   p.tmem_cols = cols;
   p.variant = ts_variant();
+  p.fault = 0;
   CUtensorMap tg;
   int rc;
   if (x3) {
@@ -1261,6 +2021,41 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
   // tensor-memory columns); sharing measured slower at cfg-2, see lstm_tc.cu
   if ((!share || cols > 256) && smem < 120 * 1024) smem = 120 * 1024;
   RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
+  // validated exchange (rec_ts_bwd3_kernel): RS_TS_XCHG_BWD=1.  Measured slower than TMA stores + release + counter so far
+  // (5.7 vs 5.3 us per step at cfg-2: the vote before the push is one more barrier in the longest phase), so off by default.
+  static const bool xchg_env = [] { const char* v = getenv("RS_TS_XCHG_BWD"); return v && v[0] == '1'; }();
+  const char* fault_env = getenv("RS_TS_FAULT");
+  if (x3 && (xchg_env || (a.dbg && fault_env && fault_env[0] == '1')) && p.variant == kDefaultVariant) {
+    // the launch's own rows of the dgates planes carry the fill pattern until their producers overwrite it
+    RS_CHECK_CUDA(cudaMemsetAsync(a.dg_hi + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
+    RS_CHECK_CUDA(cudaMemsetAsync(a.dg_lo + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
+    { const char* v = getenv("RS_TS_FAULT"); p.fault = (a.dbg && v && v[0] == '1' && g.Bpad <= 32) ? 1 : 0; }
+    const bool fast3 = g.Bpad == 32 && g.H == 768 && nlo_t == p.nkbs;
+    const int s3 = device_slot() * 3 + (a.dbg ? 2 : fast3 ? 1 : 0);
+    auto kern3 = a.dbg ? rec_ts_bwd3_kernel<true, 0, 0> : fast3 ? rec_ts_bwd3_kernel<false, 32, 768> : rec_ts_bwd3_kernel<false, 0, 0>;
+    static size_t attr3_smem[kMaxDevices * 3] = {};
+    static int nclusters3[kMaxDevices * 3] = {};
+    cudaLaunchConfig_t cfg3 = {};
+    cfg3.gridDim = dim3(g.nslice);
+    cfg3.blockDim = dim3(NTHREADS);
+    cfg3.dynamicSmemBytes = smem;
+    cfg3.stream = st;
+    cudaLaunchAttribute attr3[1];
+    attr3[0].id = cudaLaunchAttributeClusterDimension;
+    attr3[0].val.clusterDim.x = CL; attr3[0].val.clusterDim.y = 1; attr3[0].val.clusterDim.z = 1;
+    cfg3.attrs = attr3;
+    cfg3.numAttrs = 1;
+    if (attr3_smem[s3] != smem) {
+      RS_CHECK_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      RS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nclusters3[s3], kern3, &cfg3));
+      attr3_smem[s3] = smem;
+    }
+    RS_REQUIRE(nclusters3[s3] * CL >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_ts_backward: %d CTAs cannot be co-resident (%d clusters)",
+               g.nslice, nclusters3[s3]);
+    RS_CHECK_CUDA(cudaLaunchKernelEx(&cfg3, kern3, tg, p));
+    count_launch();
+    return RS_OK;
+  }
   const bool fast = !a.dbg && p.variant == kDefaultVariant && g.Bpad == 32 && g.H == 768 && (!x3 || nlo_t == p.nkbs);
   const int si = device_slot() * 4 + (a.dbg ? 1 : (fast ? (x3 ? 2 : 3) : 0));
   auto kern = a.dbg ? rec_ts_bwd_kernel<true, -1, 0, 0, -1>

@@ -303,6 +303,65 @@ def rec_diag():
                     (int(d[900, 15]) - int(d[100, 15])) / max(1, int(d[900, 7]) - int(d[100, 7])) * 1e3))
 
 
+def xchg_diag():
+    """cfg-2 forward recurrent kernel with the validated exchange (rec_ts_fwd3_kernel): mean time between the stamped
+    events of a step, per chain, for CTA 0 and the last CTA (steps 100..900 of a single launch over all T steps)."""
+    L, H, F, C, B, T = 3, 768, 120, 80, 32, 998
+    rng = np.random.default_rng(0)
+    flat = model.flatten(model.init_params(L, H, F, C, seed=0), L, H, F, C)
+    x = rng.standard_normal((T, B, F)).astype(np.float32)
+    lens = np.full(B, T, np.int32)
+    os.environ["RS_TC_CHUNK"] = "0"
+    m = rs.AcousticModel(L, H, B, 1000, 600, F, False, C, device=dev)
+    m.create_training_rnn(0.8, 0.5, 1, 3e-4, 0.33)
+    m.load_flat_params(flat)
+    m.enable_timing()
+    dbg_f = torch.zeros((2 * T, 16), dtype=torch.int64, device=dev)
+    dbg_b = torch.zeros((2 * T, 16), dtype=torch.int64, device=dev)
+    rs._lib.call("rs_am_set_debug_timeline", m._handle, dbg_f.data_ptr(), dbg_b.data_ptr())
+    xd, ld = torch.from_numpy(x).to(dev), torch.from_numpy(lens).to(dev)
+    dl = torch.from_numpy((rng.standard_normal((T, B, C)) * 0.01).astype(np.float32)).to(dev)
+    for it in range(2):
+        m.rnn_state.zero_()
+        dbg_f.zero_(); dbg_b.zero_()
+        m.forward(xd, ld, training=True, keep_state=False)
+        m.grads.zero_()
+        m.backward(xd, ld, dl)
+        torch.cuda.synchronize()
+    print("rec ms fwd/bwd", m.recurrent_ms())
+    db = dbg_b.cpu().numpy().astype(np.int64)
+    bnames = ["counter seen", "fetch issued", "-", "MMAs done", "partials pushed", "partials received",
+              "cell math done", "published"]
+    for cta, base in (("cta0", 0), ("ctaN", T)):
+        e = db[base + 100:base + 900, :8][::-1]          # backward runs t downwards: row = t - t0; the fetch for step t-1 is stamped at row t
+        if not e[:, 0].all():
+            print("  bwd %s: no stamps (the validated backward kernel did not run)" % cta)
+            continue
+        print("  bwd %s: step period %.0f ns" % (cta, np.diff(e[:, 0]).mean()))
+        for k in range(1, 2):
+            dt = e[:, k] - e[:, 0]
+            print("      %-26s %5.0f ns after 'counter seen' (p95 %5.0f)" % (bnames[k], dt.mean(), np.percentile(dt, 95)))
+        for k in range(3, 8):
+            dt = e[1:, k] - e[:-1, 0]                     # events 3..7 of row t-1 belong to the fetch stamped at row t
+            print("      %-26s %5.0f ns after 'counter seen' (p95 %5.0f)" % (bnames[k], dt.mean(), np.percentile(dt, 95)))
+        nxt = e[2:, 0] - e[2:, 7]                     # row t: 'published' of step t, then the counter for the fetch of tile t
+        print("      next counter seen +%5.0f ns after 'published' (p95 %5.0f)" % (nxt.mean(), np.percentile(nxt, 95)))
+    d = dbg_f.cpu().numpy().astype(np.int64)
+    names = ["counter seen", "fetch issued", "tile landed", "MMAs done", "cell math done", "published", "end of step"]
+    for cta, base in (("cta0", 0), ("ctaN", T)):
+        for X in range(2):
+            e = d[base + 100:base + 900, 8 * X:8 * X + 8]
+            period = np.diff(e[:, 0]).mean()
+            print("  %s chain %d: step period %.0f ns; attempts per step %.4f" % (cta, X, period, (e[-1, 7] - e[0, 7]) / (len(e) - 1)))
+            for k in range(1, 7):
+                dt = e[:, k] - e[:, 0]
+                print("      %-26s %5.0f ns after 'counter seen' (p95 %5.0f)" % (names[k], dt.mean(), np.percentile(dt, 95)))
+            nxt = e[1:, 0] - e[:-1, 5]
+            print("      next counter seen +%5.0f ns after 'published' (p95 %5.0f)" % (nxt.mean(), np.percentile(nxt, 95)))
+        print("  %s: chain 1 'counter seen' - chain 0 'counter seen': mean %.0f ns" % (cta, (d[base + 100:base + 900, 8] - d[base + 100:base + 900, 0]).mean()))
+    print("  ctaN - cta0 'published' (chain 0): mean %.0f ns, std %.0f" % ((d[T + 100:T + 900, 5] - d[100:900, 5]).mean(), (d[T + 100:T + 900, 5] - d[100:900, 5]).std()))
+
+
 def trace_diag():
     """cfg-2 training step: where the recurrent launches of the pipelined schedule sit in time (CUDA events on the
     launching streams, ms after the top of the forward / backward call) and how long each phase of the step takes."""
@@ -478,6 +537,8 @@ if __name__ == "__main__":
         stress_diag()
     if "e2e" in which:
         e2e_diag()
+    if "xchg" in which:
+        xchg_diag()
     if "trace" in which:
         trace_diag()
     if "mma" in which:

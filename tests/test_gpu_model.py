@@ -100,6 +100,8 @@ def test_cfg1_golden_forward_backward(pkg, cuda):
     (2, 50, 20, 50, 3, 17, 1.0, 1.0),       # odd sizes (reference's own test model: L2 H50 C50)
     (2, 64, 120, 80, 5, 33, 0.8, 0.5),      # dropout on both sides of every cell
     (3, 128, 120, 80, 40, 12, 1.0, 1.0),    # batch > 32 (two batch chunks)
+    (2, 256, 120, 80, 21, 45, 0.8, 0.5),    # two chains per CTA, the second with 5 of 16 rows; self-validating exchange
+    (1, 512, 40, 30, 32, 40, 1.0, 0.7),     # the same kernel at another hidden size
 ])
 def test_random_models_with_state_and_dropout(pkg, cuda, L, H, F, C, B, T, ki, ko):
     rng = np.random.default_rng(L * 1000 + H)
@@ -392,6 +394,55 @@ def test_stale_tile_stress(pkg, cuda):
             continue
         for a, b, what in zip(got, refs[k], ("logits", "state", "gradients")):
             assert torch.equal(a, b), "repetition %d: %s differ from the first run of the same input" % (it, what)
+
+
+def test_exchange_fault_injection(pkg, cuda, monkeypatch):
+    """The recurrent kernels publish h_t / dgates_t with plain stores and an unordered hint (a relaxed add on a counter);
+    a consumer whose TMA fetch overtakes a store sees the fill pattern (a bf16 NaN) in its tile, the tensor core turns it
+    into NaN accumulator columns, the epilogue votes, scans, and has the tile fetched and multiplied again.  Here the debug
+    instantiation of both kernels sends the hint 3 us BEFORE half of every publish (RS_TS_FAULT=1): retries must happen
+    (more MMA batches than steps) and logits, carried state and gradients must not change by a bit."""
+    L, H, F, C, B, T = 1, 256, 40, 30, 27, 60
+    rng = np.random.default_rng(3)
+    flat = model.flatten(model.init_params(L, H, F, C, seed=4), L, H, F, C)
+    x = _dev(rng.standard_normal((T, B, F)), cuda, np.float32)
+    lens_np = rng.integers(T // 2, T + 1, size=B).astype(np.int32)
+    lens_np[0] = T
+    lens = _dev(lens_np, cuda, np.int32)
+    dl = _dev(rng.standard_normal((T, B, C)) * (np.arange(T)[:, None, None] < lens_np[None, :, None]), cuda, np.float32)
+    monkeypatch.setenv("RS_TC_CHUNK", "0")              # one launch per layer: the debug instantiations are single-launch
+    m = _build(pkg, cuda, L, H, F, C, B, T, flat, training=True, ki=0.8, ko=0.5)
+    assert m.uses_tensor_cores
+
+    def run():
+        m.rnn_state.zero_()
+        m._dropout_calls = 0
+        logits = m.forward(x, lens, training=True)
+        m.grads.zero_()
+        m.backward(x, lens, dl)
+        torch.cuda.synchronize()
+        return logits.clone(), m.rnn_state.clone(), m.grads.clone()
+
+    ref = run()
+    dbg_f = torch.zeros((2 * T, 16), dtype=torch.int64, device=cuda)
+    dbg_b = torch.zeros((2 * T, 16), dtype=torch.int64, device=cuda)
+    pkg._lib.call("rs_am_set_debug_timeline", m._handle, dbg_f.data_ptr(), dbg_b.data_ptr())
+    try:
+        clean = run()
+        for a, b, what in zip(clean, ref, ("logits", "state", "gradients")):
+            assert torch.equal(a, b), "debug instantiation: %s differ" % what
+        batches_f, batches_b = int(dbg_f[T - 1, 7]), int(dbg_b[0, 8])
+        assert batches_f == T and batches_b == T - 1, "no retries expected without the fault: %d, %d" % (batches_f, batches_b)
+        monkeypatch.setenv("RS_TS_FAULT", "1")
+        dbg_f.zero_(); dbg_b.zero_()
+        got = run()
+        batches_f, batches_b = int(dbg_f[T - 1, 7]), int(dbg_b[0, 8])
+        print("fault injection: %d forward MMA batches for %d steps (chain 0 of CTA 0), %d backward for %d" % (batches_f, T, batches_b, T - 1))
+        assert batches_f > T and batches_b > T - 1, "the injected fault caused no retries: the test tests nothing"
+        for a, b, what in zip(got, ref, ("logits", "state", "gradients")):
+            assert torch.equal(a, b), "with the injected fault: %s differ" % what
+    finally:
+        pkg._lib.call("rs_am_set_debug_timeline", m._handle, 0, 0)
 
 
 @pytest.mark.parametrize("L,H,F,C,B,T,ki", [
