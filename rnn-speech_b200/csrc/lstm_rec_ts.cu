@@ -117,6 +117,24 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint
                : "memory");
 }
 
+// plain 16-byte store into a peer CTA's shared memory (ordered by a later release at cluster scope)
+__device__ __forceinline__ void st_cluster_v4(uint32_t remote_addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t remote_mbar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(tc::smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+
 // n TMEM-resident K-blocks (64 elements each = four K16 MMAs) issued back to back: A block i at a0 + 32 i columns,
 // B block i at b0 + i * bstep.  Fully unrolled for the usual counts so that no per-block address arithmetic sits
 // between two tcgen05.mma.
@@ -1107,7 +1125,8 @@ struct KBwd {
   int nlo_t;                               // K-blocks of Wh_lo resident in tensor memory (the other nkbs - nlo_t in smem)
   int variant;
   uint32_t tmem_cols;
-  int fault;                               // STAMP instantiation of rec_ts_bwd3_kernel: delay half of every publish behind its hint
+  int fault;                               // STAMP instantiations of rec_ts_bwd3/4_kernel: delay half of every publish behind its hint
+  int turns;                               // rec_ts_bwd4_kernel: the chains take turns at the TMA port
 };
 
 // 128 registers (no spills; 168 unconstrained) x 320 threads and ~50 KB of shared memory: with RS_TC_CORES=1 a 256-thread
@@ -1473,7 +1492,7 @@ rec_ts_bwd3_kernel(const __grid_constant__ CUtensorMap tmG, KBwd p) {
   if (threadIdx.x == 0) {
     tc::mbar_init(&full_bar, 1);
     tc::mbar_init(&tfull_bar, 1);
-    tc::mbar_init(&recv_bar, 1);
+    tc::mbar_init(&recv_bar, 2 * CL);                    // two epilogue warps (column halves) of each of the CL sources
     retry_req = 0; quit = 0;
     tc::fence_mbar_init();
   }
@@ -1623,10 +1642,6 @@ rec_ts_bwd3_kernel(const __grid_constant__ CUtensorMap tmG, KBwd p) {
       for (int gl = 0; gl < MAXG; ++gl) dh[gl][0] = dh[gl][1] = 0.f;
       if (n > 0) {
         // partial dh_t^T of this CTA's K segment -> reduce-scatter over the cluster
-        if (threadIdx.x == 0) {
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                       ::"r"(tc::smem_u32(&recv_bar)), "r"((uint32_t)(CL * TSU * Bpad * 4)) : "memory");
-        }
         float v[MAXG][16];
         const bool fresh = t + 1 < t1;                          // the tile (dgates_{t+1}) was produced by this launch
         for (;;) {
@@ -1651,25 +1666,29 @@ rec_ts_bwd3_kernel(const __grid_constant__ CUtensorMap tmG, KBwd p) {
             }
           }
           tc::tc_fence_before();
+          if (threadIdx.x == 0) RS_STAMPB(t, 9, gtime());
           // the accumulator may leave the CTA only when its tile is known to have been complete: vote
           if (!bar_any(1, 256, nan)) break;
           const bool stale = bar_any(1, 256, fresh && tile_has_fill(tc::smem_u32(sG), (uint32_t)nkbs * kb_bytes, Bpad, B, (int)threadIdx.x, 256));
           if (!stale) break;                                      // the model's own NaN
           if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(&retry_req) = *reinterpret_cast<volatile uint32_t*>(&retry_req) + 1u;
         }
+        if (threadIdx.x == 0) RS_STAMPB(t, 10, gtime());
 #pragma unroll
         for (int gl = 0; gl < MAXG; ++gl) {
           const int gi = hf + 2 * gl;
           if (gi < ng) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              st_async_v4(push_base + (uint32_t)(gi * 16 + 4 * i) * 4u, make_float4(v[gl][4 * i], v[gl][4 * i + 1], v[gl][4 * i + 2], v[gl][4 * i + 3]),
-                          push_bar);
+              st_cluster_v4(push_base + (uint32_t)(gi * 16 + 4 * i) * 4u, make_float4(v[gl][4 * i], v[gl][4 * i + 1], v[gl][4 * i + 2], v[gl][4 * i + 3]));
           }
         }
-        tc::tc_fence_before();
+        // one arrival per warp and owner instead of a transaction count per 16 bytes (1024 updates of one mbarrier per step:
+        // measured 0.69 us from the vote to the last st.async, 0.36 more until the barrier completed)
+        __syncwarp();
+        if (l16 == 0) mbar_arrive_remote_release(push_bar);
         if (threadIdx.x == 0) RS_STAMPB(t, 4, gtime());
-        tc::mbar_wait(&recv_bar, (n - 1) & 1);
+        mbar_wait_cluster(&recv_bar, (n - 1) & 1);
         if (threadIdx.x == 0) RS_STAMPB(t, 5, gtime());
 #pragma unroll
         for (int gl = 0; gl < MAXG; ++gl) {
@@ -1683,6 +1702,7 @@ rec_ts_bwd3_kernel(const __grid_constant__ CUtensorMap tmG, KBwd p) {
           }
         }
       }
+      if (threadIdx.x == 0) RS_STAMPB(t, 11, gtime());
 #pragma unroll
       for (int gl = 0; gl < MAXG; ++gl) {
         const int gi = hf + 2 * gl;
@@ -1721,6 +1741,7 @@ rec_ts_bwd3_kernel(const __grid_constant__ CUtensorMap tmG, KBwd p) {
       }
       if (threadIdx.x == 0) RS_STAMPB(t, 6, gtime());
       epi_bar_sync();
+      if (threadIdx.x == 0) RS_STAMPB(t, 12, gtime());
       // publish dgates_t: 16-byte stores of the staged tile (one 32-byte sector per (row, gate, plane)), then the hint
       bool faulty = false;
       if constexpr (STAMP) faulty = p.fault != 0;
@@ -1754,7 +1775,7 @@ rec_ts_bwd3_kernel(const __grid_constant__ CUtensorMap tmG, KBwd p) {
         __syncwarp();
         if (late) for (int i = 0; i < nx; ++i) if (dst[i]) st_relaxed_v4(dst[i], x[i]);
       }
-      if (threadIdx.x == 0) { RS_STAMPB(t, 7, gtime()); RS_STAMPB(t, 8, (unsigned long long)na); }
+      if (threadIdx.x == 0) { RS_STAMPB(t, 7, gtime()); RS_STAMPB(t, 2, (unsigned long long)na); }
       // (the staged tile is rewritten only after the next tfull wait, i.e. after a fetch that follows the grid-wide
       //  count, which needs all eight adds above, each of which follows its warp's reads of the tile)
     }
@@ -1768,6 +1789,324 @@ rec_ts_bwd3_kernel(const __grid_constant__ CUtensorMap tmG, KBwd p) {
       for (int gl = 0; gl < MAXG; ++gl)
         carry[(((size_t)j * MAXG + gl) * 8 + warp) * 32 + lane] = make_float2(dc[gl][0], dc[gl][1]);
     }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) tc::tmem_dealloc(tmem, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------
+// Backward, two chains, validated exchange.  The reduce-scatter of the partial dh over the cluster moves 16 KB out of and
+// into every CTA per step through distributed shared memory (~20 B/clk per SM: measured 0.7 us from the first st.async to
+// the last, 0.35 more until the transaction count is complete), the cell backward and the publish of dgates_t take another
+// 1.4 us, and during all of it the TMA port and the tensor pipe of the SM are idle.  As in forward (rec_ts_fwd3_kernel) the
+// mini-batch therefore runs as two independent 16-row recurrences per CTA -- own producer / MMA / four epilogue warps, own
+// tile, accumulator columns, receive buffer, mbarriers, named barrier and grid counter -- that take turns at the TMA port,
+// so that one chain fetches and multiplies while the other one reduces, computes its cells and publishes.
+// Exchange and validation as in rec_ts_bwd3_kernel (fill pattern -> NaN accumulator columns -> vote before the push).
+// Requires Bpad == 32, B > 16, bf16x3.
+// ------------------------------------------------------------------------------------
+template <bool STAMP, int HH>
+__global__ void __maxnreg__(128)
+rec_ts_bwd4_kernel(const __grid_constant__ CUtensorMap tmG, KBwd p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[2], tfull_bar[2], recv_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t retry_req[2], quit[2], tiles_landed[2];
+  const RecTcBwdArgs& a = p.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = HH > 0 ? HH : p.H, B = p.B, T = a.T, nkbs = HH > 0 ? HH / 128 : p.nkbs, G = 4 * H;
+  const int nslice = HH > 0 ? HH / TSU : p.nslice;
+  const uint32_t rank = cluster_ctarank();            // K segment / owned unit slice inside the 128-unit block
+  const int blk = blockIdx.x / CL;
+  const int j = blk * CL + (int)rank;                   // 16-unit slice (same numbering as forward)
+  const int kseg0 = (int)rank * (H / 2);                // first dgates column of this CTA's K segment
+  const int nlo_t = HH > 0 ? HH / 128 : p.nlo_t;
+  const int nlo_s = nkbs - nlo_t;
+  constexpr uint32_t kb_bytes = 2u * CHB * 128u;                             // one streamed K-block of a chain: hi rows ; lo rows
+  const uint32_t tile_bytes = (uint32_t)nkbs * kb_bytes;
+  unsigned char* sG = smem;                                                  // [2 chains][nkbs][2 planes][16 x 128 B] dgates_t K segment
+  unsigned char* sAlo = smem + (size_t)2 * tile_bytes;                       // [nlo_s][128 rows x 128 B] Wh_lo blocks outside TMEM
+  float* sR = reinterpret_cast<float*>(sAlo + (size_t)nlo_s * 16384);        // [2 chains][CL src][16 units][16] partial dh
+  __nv_bfloat16* sDG = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(sR) + (size_t)2 * CL * TSU * CHB * 4);
+                                                                             // [2 chains][2 planes][16][4 gates][16 units]
+  const uint32_t colLo = (uint32_t)(H / 4);              // Wh_hi: columns [0, H/4); Wh_lo: nlo_t blocks of 32 columns behind
+  const uint32_t colD = colLo + (uint32_t)nlo_t * 32;    // accumulator of chain X: 32 columns at colD + 32 X
+  const int t1 = a.t0 + T;                                // this launch: steps t1 - 1 down to t0
+  const bool primed = t1 < a.Ttot;                        // dh_{t1-1} comes from dgates_{t1} of the previous launch
+  const int ts_first = primed ? t1 : t1 - 1;              // first dgates step streamed through the tensor core
+
+  if (threadIdx.x == 0) {
+    for (int x = 0; x < 2; ++x) {
+      tc::mbar_init(&full_bar[x], 1); tc::mbar_init(&tfull_bar[x], 1); tc::mbar_init(&recv_bar[x], 1);
+      retry_req[x] = 0; quit[x] = 0; tiles_landed[x] = 0;
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&tmem_slot, p.tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp < 4) {
+    // resident Wh[128 rows of the block][K segment]: TMEM lane = threadIdx.x = hidden unit k
+    const __nv_bfloat16* src = a.wh_hi + (size_t)(blk * 128 + (int)threadIdx.x) * G + kseg0;
+    for (int c0 = 0; c0 < H / 4; c0 += 8) {
+      const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0));
+      const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0 + 8));
+      const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      tc::tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+    }
+    const __nv_bfloat16* srcl = a.wh_lo + (size_t)(blk * 128 + (int)threadIdx.x) * G + kseg0;
+    for (int c0 = 0; c0 < nlo_t * 32; c0 += 8) {
+      const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(srcl + 2 * c0));
+      const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(srcl + 2 * c0 + 8));
+      const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      tc::tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + colLo + (uint32_t)c0, r);
+    }
+    for (int kb = nlo_t; kb < nkbs; ++kb) {
+      unsigned char* tile = sAlo + (size_t)(kb - nlo_t) * 16384 + (size_t)threadIdx.x * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(tile + ((c ^ (threadIdx.x & 7)) << 4)) = __ldg(reinterpret_cast<const uint4*>(srcl + kb * 64 + c * 8));
+    }
+    if (nlo_s > 0) tc::fence_proxy_async_smem();
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  cluster_sync_all();                                   // peers' mbarriers are initialised before any st.async
+
+  if (warp == 8 || warp == 10) {
+    // ------------------------------------------------------------------ TMA producer of chain X
+    const int X = (warp - 8) >> 1;
+    if (lane == 0) tc::tma_prefetch_desc(&tmG);
+    __syncwarp();
+    const unsigned per_step = gridDim.x * 4u;           // every CTA adds 4 per chain and step
+    const unsigned* ctr = a.barrier + 32 * X;
+    unsigned epoch = 0;
+    uint32_t served = 0, nf = 0;                         // retry requests answered; fetches of the schedule issued
+    auto fetch = [&](int t) {
+      tc::mbar_arrive_expect_tx_warp(&full_bar[X], tile_bytes);
+      tc::tma_load_4d_warp(sG + (size_t)X * tile_bytes, &tmG, 0, t * B + CHB * X, 0, kseg0 / 64, &full_bar[X]);   // [kb][plane][16][64]
+    };
+    auto serve = [&](int t) {
+      if (*reinterpret_cast<volatile uint32_t*>(&retry_req[X]) != served) { ++served; __syncwarp(); fetch(t); }
+    };
+    for (int t = ts_first; t >= a.t0 + 1; --t, ++nf) {  // dh_{t-1} from dgates_t
+      if (t < t1) {                                       // dgates_t comes from this launch: wait for the hint
+        ++epoch;
+        uint32_t spins = 0;
+        while (ld_relaxed_u32(ctr) < per_step * epoch) { serve(t + 1); if (++spins > (1u << 26)) __trap(); }
+        __syncwarp();
+      }
+      if (lane == 0) RS_STAMPB(t, 8 * X + 0, gtime());
+      __syncwarp();
+      if (p.turns) {
+        // the chains take turns at the TMA port (see rec_ts_fwd3_kernel): chain 1's fetch i follows the landing of chain 0's
+        // fetch i, chain 0's fetch i + 1 that of chain 1's fetch i
+        const uint32_t need = nf + (uint32_t)X;
+        while (*reinterpret_cast<volatile uint32_t*>(&tiles_landed[X ^ 1]) < need) {}
+        __syncwarp();
+      }
+      fetch(t);
+      if (lane == 0) RS_STAMPB(t, 8 * X + 1, gtime());
+      __syncwarp();
+    }
+    while (*reinterpret_cast<volatile uint32_t*>(&quit[X]) == 0) serve(a.t0 + 1);
+  } else if (warp == 9 || warp == 11) {
+    // ------------------------------------------------------------------ MMA issuer of chain X: one batch per fetch
+    const int X = (warp - 9) >> 1;
+    const uint32_t idesc = tc::instr_desc_bf16(128, CHB);                // N = one plane
+    const uint32_t idesc2 = tc::instr_desc_bf16(128, 2 * CHB);           // N = both planes stacked
+    const uint64_t dg0 = tc::smem_desc_sw128(tc::smem_u32(sG + (size_t)X * tile_bytes));
+    const uint64_t dAlo0 = tc::smem_desc_sw128(tc::smem_u32(sAlo));
+    const uint32_t tmemD = tmem + colD + (uint32_t)(2 * CHB * X);
+    for (uint32_t n = 0;; ++n) {
+      tc::mbar_wait(&full_bar[X], n & 1);
+      if (*reinterpret_cast<volatile uint32_t*>(&quit[X]) != 0) break;
+      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&tiles_landed[X]) = n + 1;
+      tc::tc_fence_after();
+      // D[:, 0:32) = Wh_hi [dg_hi | dg_lo] ; D[:, 0:16) += Wh_lo dg_hi
+      issue_ts_blocks<6>(nkbs, tmemD, tmem, dg0, (uint64_t)(kb_bytes >> 4), idesc2, 0u);                             // 6: H = 768
+      issue_ts_blocks<6>(nlo_t, tmemD, tmem + colLo, dg0, (uint64_t)(kb_bytes >> 4), idesc, 1u);
+      for (int i = nlo_t; i < nkbs; ++i)
+        tc::mma4_bf16_ss_warp(tmemD, dAlo0 + (uint64_t)(i - nlo_t) * (16384 >> 4), dg0 + (uint64_t)i * (kb_bytes >> 4), idesc, 1u);
+      tc::mma_commit_warp(&tfull_bar[X]);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps of chain X = warp >> 2
+    const int q = warp & 3, X = warp >> 2, l16 = lane & 15, up = lane >> 4;
+    const int g = lane & 3;
+    const int ul = q * 4 + (l16 >> 2);                   // owned unit inside the slice (cell math)
+    const int unit = j * TSU + ul;
+    const int ctid = (int)threadIdx.x & 127;
+    const int rowsX = min(max(B - CHB * X, 0), CHB);
+    const uint32_t tmemD = tmem + colD + (uint32_t)(2 * CHB * X) + ((uint32_t)(q * 32) << 16);
+    // push side: TMEM lane 32q + lane = unit 32q + lane of the block -> owner rank, unit inside its slice
+    const uint32_t owner = (uint32_t)(2 * q + up);
+    float* sRX = sR + (size_t)X * CL * TSU * CHB;
+    __nv_bfloat16* sDGX = sDG + (size_t)X * 2 * CHB * 4 * TSU;
+    const uint32_t push_base = mapa_u32(tc::smem_u32(sRX) + (uint32_t)(((int)rank * TSU + l16) * CHB) * 4u, owner);
+    const uint32_t push_bar = mapa_u32(tc::smem_u32(&recv_bar[X]), owner);
+    unsigned* ctr = a.barrier + 32 * X;
+    const float2* blob = reinterpret_cast<const float2*>(a.gates);
+    int lenr[2];
+    float dc[2] = {0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int b = X * CHB + 8 * up + 2 * g + k;
+      lenr[k] = b < B ? a.len[b] : 0;
+    }
+    float2* carry = reinterpret_cast<float2*>(a.dc_carry);
+    if (primed && carry) {
+      const float2 x = carry[(((size_t)j * MAXG + 0) * 8 + warp) * 32 + lane];
+      dc[0] = x.x; dc[1] = x.y;
+    }
+    uint32_t n = primed ? 1u : 0u;                            // n - 1 = index of the receive this step consumes
+    uint32_t na = 0;                                          // MMA batches consumed
+    for (int t = t1 - 1; t >= a.t0; --t, ++n) {
+      // operands of the cell backward (independent of the recurrence: issue before waiting)
+      float2 it2[BLOB_ITEMS], cp2;
+      float dy[2];
+#pragma unroll
+      for (int it = 0; it < BLOB_ITEMS; ++it) it2[it] = __ldg(blob + blob_idx(t, nslice, j, 1, 0, it, warp, lane));
+      if (t > 0) cp2 = __ldg(blob + blob_idx(t - 1, nslice, j, 1, 0, 4, warp, lane));
+      {
+        float cpv[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int b = X * CHB + 8 * up + 2 * g + k;
+          float d = (b < B) ? __ldg(a.dout + ((size_t)t * B + b) * H + unit) : 0.f;
+          // backward of the hop's dropout(s): the same masks, applied as the gradient is read
+          const unsigned long long idx = ((unsigned long long)t * B + b) * H + unit;
+          if (a.drop_thr_a != 0xffffffffu) d = dropout_keep(a.drop_key, a.drop_sa, idx, a.drop_thr_a) ? d * a.drop_inv_a : 0.f;
+          if (a.drop_thr_b != 0xffffffffu) d = dropout_keep(a.drop_key, a.drop_sb, idx, a.drop_thr_b) ? d * a.drop_inv_b : 0.f;
+          dy[k] = d;
+          cpv[k] = (t == 0 && b < B) ? __ldg(a.c0 + (size_t)b * H + unit) : 0.f;
+        }
+        if (t == 0) cp2 = make_float2(cpv[0], cpv[1]);
+      }
+      float dh[2] = {0.f, 0.f};
+      if (n > 0) {
+        // partial dh_t^T of this CTA's K segment -> reduce-scatter over the cluster
+        if (ctid == 0) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                       ::"r"(tc::smem_u32(&recv_bar[X])), "r"((uint32_t)(CL * TSU * CHB * 4)) : "memory");
+        }
+        float v[16];
+        const bool fresh = t + 1 < t1;                          // the tile (dgates_{t+1}) was produced by this launch
+        for (;;) {
+          tc::mbar_wait(&tfull_bar[X], na & 1);
+          ++na;
+          tc::tc_fence_after();
+          if (ctid == 0) RS_STAMPB(t, 8 * X + 3, gtime());
+          float w[16];
+          tc::tmem_ld16(tmemD, v);
+          tc::tmem_ld16(tmemD + (uint32_t)CHB, w);                // Wh_hi dg_lo
+          tc::tmem_ld_wait();
+          bool nan = false;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] += w[i];
+            nan = nan || (i < rowsX && v[i] != v[i]);               // fill pattern in tile row i (either plane)
+          }
+          tc::tc_fence_before();
+          // the accumulator may leave the CTA only when its tile is known to have been complete: vote
+          if (!bar_any(1 + X, 128, nan)) break;
+          const bool stale = bar_any(1 + X, 128, fresh && tile_has_fill(tc::smem_u32(sG + (size_t)X * tile_bytes), tile_bytes, CHB, rowsX, ctid, 128));
+          if (!stale) break;                                      // the model's own NaN
+          if (ctid == 0) *reinterpret_cast<volatile uint32_t*>(&retry_req[X]) = *reinterpret_cast<volatile uint32_t*>(&retry_req[X]) + 1u;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          st_async_v4(push_base + (uint32_t)(4 * i) * 4u, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), push_bar);
+        if (ctid == 0) RS_STAMPB(t, 8 * X + 4, gtime());
+        tc::mbar_wait(&recv_bar[X], (n - 1) & 1);
+        if (ctid == 0) RS_STAMPB(t, 8 * X + 5, gtime());
+#pragma unroll
+        for (int s = 0; s < CL; ++s) {
+          const float2 x = *reinterpret_cast<const float2*>(sRX + ((size_t)s * TSU + ul) * CHB + 8 * up + 2 * g);
+          dh[0] += x.x; dh[1] += x.y;
+        }
+      }
+      {
+        const float* pi = reinterpret_cast<const float*>(&it2[0]);
+        const float* pj = reinterpret_cast<const float*>(&it2[1]);
+        const float* pf = reinterpret_cast<const float*>(&it2[2]);
+        const float* po = reinterpret_cast<const float*>(&it2[3]);
+        const float* pct = reinterpret_cast<const float*>(&it2[4]);
+        const float* pcp = reinterpret_cast<const float*>(&cp2);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int bl = 8 * up + 2 * g + k;
+          float di = 0.f, dj = 0.f, df = 0.f, dob = 0.f;
+          if (t < lenr[k]) {
+            const float ig = pi[k], jg = pj[k], fg = pf[k], og = po[k];
+            const float dh_tot = dh[k] + dy[k];
+            const float tch = fast_tanh(pct[k]);
+            dob = dh_tot * tch * og * (1.f - og);
+            const float dc_tot = dc[k] + dh_tot * og * (1.f - tch * tch);
+            di = dc_tot * jg * ig * (1.f - ig);
+            dj = dc_tot * ig * (1.f - jg * jg);
+            df = dc_tot * pcp[k] * fg * (1.f - fg);
+            dc[k] = dc_tot * fg;
+          }
+          const float d4[4] = {di, dj, df, dob};
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            __nv_bfloat16 h0, l0;
+            tc::split_bf16(d4[gg], h0, l0);
+            sDGX[(((size_t)0 * CHB + bl) * 4 + gg) * TSU + ul] = h0;
+            sDGX[(((size_t)1 * CHB + bl) * 4 + gg) * TSU + ul] = l0;
+          }
+        }
+      }
+      if (ctid == 0) RS_STAMPB(t, 8 * X + 6, gtime());
+      chain_bar_sync(X);
+      // publish dgates_t: 16-byte stores of the staged tile (one 32-byte sector per (row, gate, plane)), then the hint
+      bool faulty = false;
+      if constexpr (STAMP) faulty = p.fault != 0;
+      {
+        uint4 x[2];
+        __nv_bfloat16* dst[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int ch = ctid + 128 * i;                          // 256 chunks: [plane][row][gate][half]
+          const int half = ch & 1, gg = (ch >> 1) & 3, bl = (ch >> 3) & 15, pl = ch >> 7;
+          x[i] = *reinterpret_cast<const uint4*>(sDGX + (((size_t)pl * CHB + bl) * 4 + gg) * TSU + half * 8);
+          dst[i] = bl < rowsX ? (pl ? a.dg_lo : a.dg_hi) + ((size_t)t * B + CHB * X + bl) * G + (size_t)gg * H + j * TSU + half * 8 : nullptr;
+        }
+        if (!faulty) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) if (dst[i]) st_relaxed_v4(dst[i], x[i]);
+          __syncwarp();
+          if (lane == 0 && t > a.t0) red_relaxed_add(ctr, 1u);
+        } else {
+          // test of the retry path: the hint overtakes the odd chunks by 3 us
+          const bool late = ctid & 1;
+          if (!late) for (int i = 0; i < 2; ++i) if (dst[i]) st_relaxed_v4(dst[i], x[i]);
+          __syncwarp();
+          if (lane == 0 && t > a.t0) red_relaxed_add(ctr, 1u);
+          const unsigned long long until = gtime() + 3000ull;
+          while (gtime() < until) {}
+          __syncwarp();
+          if (late) for (int i = 0; i < 2; ++i) if (dst[i]) st_relaxed_v4(dst[i], x[i]);
+        }
+      }
+      if (ctid == 0) { RS_STAMPB(t, 8 * X + 7, gtime()); if (X == 0) RS_STAMPB(t, 2, (unsigned long long)na); }
+      // (the staged tile is rewritten only after the next tfull wait, i.e. after a fetch that follows the grid-wide
+      //  count, which needs all four adds above, each of which follows its warp's reads of the tile)
+    }
+    if (ctid == 0) {
+      // release the chain's producer and MMA warps
+      *reinterpret_cast<volatile uint32_t*>(&quit[X]) = 1u;
+      tc::mbar_arrive(&full_bar[X]);
+    }
+    if (carry) carry[(((size_t)j * MAXG + 0) * 8 + warp) * 32 + lane] = make_float2(dc[0], dc[1]);
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -2003,6 +2342,7 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
   p.tmem_cols = cols;
   p.variant = ts_variant();
   p.fault = 0;
+  p.turns = 0;
   CUtensorMap tg;
   int rc;
   if (x3) {
@@ -2023,6 +2363,49 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
   RS_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, 256 * sizeof(unsigned), st));
   // validated exchange (rec_ts_bwd3_kernel): RS_TS_XCHG_BWD=1.  Measured slower than TMA stores + release + counter so far
   // (5.7 vs 5.3 us per step at cfg-2: the vote before the push is one more barrier in the longest phase), so off by default.
+  // two chains per CTA (rec_ts_bwd4_kernel) when the batch allows it; RS_TS_CHAINS_BWD=0: one chain
+  static const bool chains_bwd_env = [] { const char* v = getenv("RS_TS_CHAINS_BWD"); return !(v && v[0] == '0'); }();
+  if (x3 && chains_bwd_env && p.variant == kDefaultVariant && g.Bpad == 32 && g.B > CHB) {
+    CUtensorMap tg2;
+    if ((rc = tmap_stacked2_bf16(&tg2, a.dg_hi, (size_t)((const char*)a.dg_lo - (const char*)a.dg_hi), a.Ttot * g.B, 4 * g.H,
+                                 4 * g.H, CHB, p.nkbs)) != RS_OK) return rc;
+    // the launch's own rows of the dgates planes carry the fill pattern until their producers overwrite it
+    RS_CHECK_CUDA(cudaMemsetAsync(a.dg_hi + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
+    RS_CHECK_CUDA(cudaMemsetAsync(a.dg_lo + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
+    { const char* v = getenv("RS_TS_FAULT"); p.fault = (a.dbg && v && v[0] == '1') ? 1 : 0; }
+    static const int turns_env = [] { const char* v = getenv("RS_TS_TURNS_BWD"); return v ? atoi(v) : 1; }();
+    p.turns = turns_env;
+    // shared memory: two tiles, the Wh_lo blocks outside tensor memory, two receive buffers, two staged dgates tiles
+    size_t smem4 = (size_t)2 * p.nkbs * 2 * CHB * 128 + (size_t)nlo_s * 16384 + (size_t)2 * CL * TSU * CHB * 4 +
+                   (size_t)2 * 2 * CHB * 4 * TSU * 2 + 1024;
+    if (smem4 < 120 * 1024) smem4 = 120 * 1024;          // one CTA per SM
+    const bool fast4 = g.H == 768 && nlo_t == p.nkbs;
+    const int s4 = device_slot() * 4 + (a.dbg ? (fast4 ? 3 : 2) : fast4 ? 1 : 0);
+    auto kern4 = a.dbg ? (fast4 ? rec_ts_bwd4_kernel<true, 768> : rec_ts_bwd4_kernel<true, 0>)
+                       : fast4 ? rec_ts_bwd4_kernel<false, 768> : rec_ts_bwd4_kernel<false, 0>;
+    static size_t attr4_smem[kMaxDevices * 4] = {};
+    static int nclusters4[kMaxDevices * 4] = {};
+    cudaLaunchConfig_t cfg4 = {};
+    cfg4.gridDim = dim3(g.nslice);
+    cfg4.blockDim = dim3(NTHREADS2);
+    cfg4.dynamicSmemBytes = smem4;
+    cfg4.stream = st;
+    cudaLaunchAttribute attr4[1];
+    attr4[0].id = cudaLaunchAttributeClusterDimension;
+    attr4[0].val.clusterDim.x = CL; attr4[0].val.clusterDim.y = 1; attr4[0].val.clusterDim.z = 1;
+    cfg4.attrs = attr4;
+    cfg4.numAttrs = 1;
+    if (attr4_smem[s4] != smem4) {
+      RS_CHECK_CUDA(cudaFuncSetAttribute(kern4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+      RS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nclusters4[s4], kern4, &cfg4));
+      attr4_smem[s4] = smem4;
+    }
+    RS_REQUIRE(nclusters4[s4] * CL >= g.nslice, RS_ERR_UNSUPPORTED, "lstm_rec_ts_backward: %d CTAs cannot be co-resident (%d clusters)",
+               g.nslice, nclusters4[s4]);
+    RS_CHECK_CUDA(cudaLaunchKernelEx(&cfg4, kern4, tg2, p));
+    count_launch();
+    return RS_OK;
+  }
   static const bool xchg_env = [] { const char* v = getenv("RS_TS_XCHG_BWD"); return v && v[0] == '1'; }();
   const char* fault_env = getenv("RS_TS_FAULT");
   if (x3 && (xchg_env || (a.dbg && fault_env && fault_env[0] == '1')) && p.variant == kDefaultVariant) {
@@ -2031,10 +2414,11 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
     RS_CHECK_CUDA(cudaMemsetAsync(a.dg_lo + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
     { const char* v = getenv("RS_TS_FAULT"); p.fault = (a.dbg && v && v[0] == '1' && g.Bpad <= 32) ? 1 : 0; }
     const bool fast3 = g.Bpad == 32 && g.H == 768 && nlo_t == p.nkbs;
-    const int s3 = device_slot() * 3 + (a.dbg ? 2 : fast3 ? 1 : 0);
-    auto kern3 = a.dbg ? rec_ts_bwd3_kernel<true, 0, 0> : fast3 ? rec_ts_bwd3_kernel<false, 32, 768> : rec_ts_bwd3_kernel<false, 0, 0>;
-    static size_t attr3_smem[kMaxDevices * 3] = {};
-    static int nclusters3[kMaxDevices * 3] = {};
+    const int s3 = device_slot() * 4 + (a.dbg ? (fast3 ? 3 : 2) : fast3 ? 1 : 0);
+    auto kern3 = a.dbg ? (fast3 ? rec_ts_bwd3_kernel<true, 32, 768> : rec_ts_bwd3_kernel<true, 0, 0>)
+                       : fast3 ? rec_ts_bwd3_kernel<false, 32, 768> : rec_ts_bwd3_kernel<false, 0, 0>;
+    static size_t attr3_smem[kMaxDevices * 4] = {};
+    static int nclusters3[kMaxDevices * 4] = {};
     cudaLaunchConfig_t cfg3 = {};
     cfg3.gridDim = dim3(g.nslice);
     cfg3.blockDim = dim3(NTHREADS);

@@ -332,19 +332,33 @@ def xchg_diag():
     db = dbg_b.cpu().numpy().astype(np.int64)
     bnames = ["counter seen", "fetch issued", "-", "MMAs done", "partials pushed", "partials received",
               "cell math done", "published"]
+    two = bool(db[100, 8] > 10 ** 12)                  # rec_ts_bwd4_kernel stamps chain 1 in events 8..15
     for cta, base in (("cta0", 0), ("ctaN", T)):
-        e = db[base + 100:base + 900, :8][::-1]          # backward runs t downwards: row = t - t0; the fetch for step t-1 is stamped at row t
-        if not e[:, 0].all():
-            print("  bwd %s: no stamps (the validated backward kernel did not run)" % cta)
+        eb = db[base + 100:base + 900, :][::-1]          # backward runs t downwards: row = t - t0; the fetch for step t-1 is stamped at row t
+        if not eb[:, 0].all():
+            print("  bwd %s: no stamps (a stamped backward kernel did not run)" % cta)
             continue
-        print("  bwd %s: step period %.0f ns" % (cta, np.diff(e[:, 0]).mean()))
-        for k in range(1, 2):
-            dt = e[:, k] - e[:, 0]
-            print("      %-26s %5.0f ns after 'counter seen' (p95 %5.0f)" % (bnames[k], dt.mean(), np.percentile(dt, 95)))
-        for k in range(3, 8):
-            dt = e[1:, k] - e[:-1, 0]                     # events 3..7 of row t-1 belong to the fetch stamped at row t
-            print("      %-26s %5.0f ns after 'counter seen' (p95 %5.0f)" % (bnames[k], dt.mean(), np.percentile(dt, 95)))
-        nxt = e[2:, 0] - e[2:, 7]                     # row t: 'published' of step t, then the counter for the fetch of tile t
+        if two:
+            for X in range(2):
+                o = 8 * X
+                print("  bwd %s chain %d: step period %.0f ns" % (cta, X, np.diff(eb[:, o]).mean()))
+                dt = eb[:, o + 1] - eb[:, o]
+                print("      %-26s %5.0f ns after 'counter seen' (p95 %5.0f)" % ("fetch issued", dt.mean(), np.percentile(dt, 95)))
+                for k, nm in ((3, "MMAs done"), (4, "voted + partials pushed"), (5, "partials received"), (6, "cell math done"), (7, "published")):
+                    dt = eb[1:, o + k] - eb[:-1, o]
+                    print("      %-26s %5.0f ns after 'counter seen' (p95 %5.0f)" % (nm, dt.mean(), np.percentile(dt, 95)))
+                nxt = eb[2:, o] - eb[2:, o + 7]
+                print("      next counter seen +%5.0f ns after 'published' (p95 %5.0f)" % (nxt.mean(), np.percentile(nxt, 95)))
+            print("  bwd %s: chain 1 'counter seen' - chain 0 'counter seen': mean %.0f ns" % (cta, (eb[:, 8] - eb[:, 0]).mean()))
+            continue
+        print("  bwd %s: step period %.0f ns" % (cta, np.diff(eb[:, 0]).mean()))
+        dt = eb[:, 1] - eb[:, 0]
+        print("      %-26s %5.0f ns after 'counter seen' (p95 %5.0f)" % ("fetch issued", dt.mean(), np.percentile(dt, 95)))
+        for k, nm in ((3, "MMAs done"), (9, "accumulator read"), (10, "voted"), (4, "partials pushed"), (5, "partials received"),
+                      (11, "partials summed"), (6, "cell math done"), (12, "barrier passed"), (7, "published")):
+            dt = eb[1:, k] - eb[:-1, 0]                   # events of row t-1 belong to the fetch stamped at row t
+            print("      %-26s %5.0f ns after 'counter seen' (p95 %5.0f)" % (nm, dt.mean(), np.percentile(dt, 95)))
+        nxt = eb[2:, 0] - eb[2:, 7]                      # row t: 'published' of step t, then the counter for the fetch of tile t
         print("      next counter seen +%5.0f ns after 'published' (p95 %5.0f)" % (nxt.mean(), np.percentile(nxt, 95)))
     d = dbg_f.cpu().numpy().astype(np.int64)
     names = ["counter seen", "fetch issued", "tile landed", "MMAs done", "cell math done", "published", "end of step"]

@@ -431,12 +431,12 @@ def test_exchange_fault_injection(pkg, cuda, monkeypatch):
         clean = run()
         for a, b, what in zip(clean, ref, ("logits", "state", "gradients")):
             assert torch.equal(a, b), "debug instantiation: %s differ" % what
-        batches_f, batches_b = int(dbg_f[T - 1, 7]), int(dbg_b[0, 8])
+        batches_f, batches_b = int(dbg_f[T - 1, 7]), int(dbg_b[0, 2])
         assert batches_f == T and batches_b == T - 1, "no retries expected without the fault: %d, %d" % (batches_f, batches_b)
         monkeypatch.setenv("RS_TS_FAULT", "1")
         dbg_f.zero_(); dbg_b.zero_()
         got = run()
-        batches_f, batches_b = int(dbg_f[T - 1, 7]), int(dbg_b[0, 8])
+        batches_f, batches_b = int(dbg_f[T - 1, 7]), int(dbg_b[0, 2])
         print("fault injection: %d forward MMA batches for %d steps (chain 0 of CTA 0), %d backward for %d" % (batches_f, T, batches_b, T - 1))
         assert batches_f > T and batches_b > T - 1, "the injected fault caused no retries: the test tests nothing"
         for a, b, what in zip(got, ref, ("logits", "state", "gradients")):
