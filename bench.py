@@ -341,9 +341,15 @@ def recurrent_roofline(h, m, c, T, step_ms, directions, traffic):
     n_launch = [len(x) for d in directions for x in trace[d]]
     rec_busy = sum(busy([iv for l in trace[d] for iv in l]) for d in directions)
     tc = bool(m.uses_tensor_cores)
-    names = " / ".join(["rec_ts_fwd_kernel", "rec_ts_bwd_kernel"][d] for d in directions)
-    return {"kernel": ("%s (persistent tcgen05 recurrent kernels, weights resident in tensor memory; %d launches per layer per "
-                       "direction, <= %d steps each, layers overlapped as a wavefront)" % (names, max(n_launch), chunk))
+    # batches of 17..32 run as two 16-row chains per CTA with the validated exchange (lstm_rec_ts.cu dispatch)
+    two = 16 < B <= 32 and os.environ.get("RS_TS_XCHG", "1") != "0"
+    names = " / ".join([("rec_ts_fwd3_kernel" if two else "rec_ts_fwd_kernel"),
+                        ("rec_ts_bwd4_kernel" if two and os.environ.get("RS_TS_CHAINS_BWD", "1") != "0" else "rec_ts_bwd_kernel")][d]
+                       for d in directions)
+    return {"kernel": ("%s (persistent tcgen05 recurrent kernels, weights resident in tensor memory%s; %d launches per layer per "
+                       "direction, <= %d steps each, layers overlapped as a wavefront)"
+                       % (names, ", two 16-row chains per CTA, h_t / dgates_t exchanged through L2 with plain stores + a relaxed "
+                                 "hint and validated by the tensor core (NaN fill pattern)" if two else "", max(n_launch), chunk))
             if tc else "lstm_rec_fwd_kernel / lstm_rec_bwd_kernel (fp32 FFMA)",
             "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
             "traffic": traffic if tc else None, "peak_source": peak_src, "avg_launch_ms": rec_ms,
@@ -542,8 +548,9 @@ def run_train(args, name):
         "vs_baseline": None, "dtype": "bf16x3" if tc else "f32", "data": "synthetic",
         "config": {"workload": c["workload"], "global_batch": c["B"] * world, "parallelism": "dp%d" % world,
                    "arithmetic": arithmetic_note(tc),
-                   "schedule": "time chunks of %s steps, layers as a wavefront (2 recurrent launches in flight), chunk GEMMs "
-                               "and weight-gradient GEMMs on the remaining SMs" % os.environ.get("RS_TC_CHUNK", "128"),
+                   "schedule": "time chunks (forward 96 steps: the layers of a wave side by side, chunk GEMMs as bursts between "
+                               "waves; backward %s steps: 2 recurrent launches in flight, chunk and weight-gradient GEMMs on the "
+                               "remaining SMs)" % os.environ.get("RS_TC_CHUNK", "128"),
                    "l2": "per-step working set (activations > 2 GB, parameters x4) exceeds the 126 MB L2; no flush needed",
                    "train_tflop_per_step": 3.0 * fwd_fl * world / 1e12,
                    "audio_seconds_per_step": audio_seconds * world},
