@@ -477,7 +477,7 @@ def run_train(args, name):
         sampler.start()
     ms, launches = h.timed(step_resident, args.steps, launch_count)
     T_last = res[(state["i"] - 1) % NB]["T"]
-    # dram__bytes_read + write per recurrent launch from profiles/r02_ncu_recurrent_kernels.txt: backward 110.4 MB per
+    # dram__bytes_read + write per recurrent launch from profiles/r02b_ncu_recurrent_and_beam.txt: backward 110.5 MB per
     # 128-step launch, forward 25.8 MB per 38-step launch = 65 MB per 96 steps; weighted by 24 / 33 launches per step
     roofline = recurrent_roofline(h, m, c, T_last, ms / args.steps, (0, 1), 84.0e6 if name == "cfg2" else None) \
         if rank == 0 else None
