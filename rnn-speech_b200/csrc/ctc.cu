@@ -240,6 +240,190 @@ ctc_lattice_kernel(const float* __restrict__ logits, const float* __restrict__ l
   }
 }
 
+// ------------------------------------------------------------------------------------
+// ctc_lattice1_kernel: the same lattice with ONE state per thread (2 N + 1 <= blockDim) and a short dependent chain
+// per time step.  The lattice is a chain of T dependent steps per item, so the kernel's time is T x (latency of one
+// step); what the general kernel above has on that chain besides the three-way log-sum-exp -- the block-wide maximum of
+// the row just written (5 shuffles, a shared-memory hop, 8 loads), libm's expf / logf, the reloads of the label
+// tables -- is taken off it here:
+//   * the shift of row t is derived from the maximum of row t-2, not t-1: O[t] = O[t-2] + max(row t-2), i.e.
+//     M[t] = max(row t-2) - M[t-1].  Still exact bookkeeping (the offsets are summed in double and the gradient
+//     kernel adds them back), the stored values stay within two steps' emissions of zero, and the warp / block
+//     reduction of row t-1 runs BESIDE step t's log-sum-exp instead of before it;
+//   * exp / log through the special-function unit (ex2.approx / lg2.approx: absolute error ~2e-7 per step on values
+//     of order one, against 1e-7 for libm; tests/test_gpu_ctc.py holds the gradient to 1e-4 / 1e-3);
+//   * label, skip flag and window of the thread's state live in registers; emissions are gathered 8 steps ahead.
+// dynamic smem: float row[2][Upad + 2]; float wmax[2][32]
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float lse3_fast(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  const float ms = (m == kNegInf) ? 0.f : m;            // all three -inf: exp(-inf - 0) = 0, log(0) = -inf
+  return ms + __logf(__expf(a - ms) + __expf(b - ms) + __expf(c - ms));
+}
+// warp maximum in one REDUX instruction: floats through their order-preserving unsigned image
+__device__ __forceinline__ float warp_max_redux(float v) {
+  const uint32_t bits = __float_as_uint(v);
+  const uint32_t key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+  const uint32_t k = __reduce_max_sync(0xffffffffu, key);
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
+ctc_lattice1_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
+                    const int* __restrict__ labels, const int* __restrict__ label_offsets,
+                    const int* __restrict__ len, int T, int B, int C, int Upad, int blank,
+                    int beta_skip_dest, float* __restrict__ alpha, float* __restrict__ beta,
+                    double* __restrict__ offs_a, double* __restrict__ offs_b, double* __restrict__ logp_out,
+                    float* __restrict__ loss) {
+  extern __shared__ unsigned char smem_raw[];
+  float* rowbuf = reinterpret_cast<float*>(smem_raw);
+  const int stride = Upad + 2;
+  float* wmax = rowbuf + 2 * stride;
+  const int b = blockIdx.x;
+  const bool is_beta = blockIdx.y == 1;
+  const CtcItem it = ctc_item(len, label_offsets, b);
+  if (it.skip) {
+    if (is_beta && threadIdx.x == 0) { loss[b] = 0.f; logp_out[b] = 0.0; }
+    return;
+  }
+  const int U = it.U, L = it.L;
+  const int u = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW4 = MAXT / 128;                        // float4 loads that cover one per-warp maximum per warp
+  const int* lab = labels + label_offsets[b];
+  auto lab_at = [&](int v) -> int { return (v >= 0 && v < U) ? ((v & 1) ? lab[v >> 1] : blank) : -1; };
+  const int l_u = (u < U) ? lab_at(u) : blank;
+  // row r of the lattice lives at rowbuf[(r & 1) * stride + 2 + v] (alpha: two -inf guards in front)
+  //                               rowbuf[(r & 1) * stride + v]     (beta: two -inf guards behind)
+  for (int i = threadIdx.x; i < 2 * stride; i += blockDim.x) rowbuf[i] = kNegInf;
+  if (threadIdx.x < 64) wmax[threadIdx.x] = kNegInf;
+  __syncthreads();
+  const int dir = is_beta ? -1 : 1;                      // direction of time
+  const int tfirst = is_beta ? L - 1 : 0;                // the row that is written directly
+  double O = 0.0;                                        // thread 0: offset of the current row
+  float Mprev = 0.f, vlast;
+  constexpr int D = MAXT <= 256 ? 8 : 2;                 // emissions in flight (the register budget of 1024 threads allows 4)
+  float2 em[D];
+  // running pointers (the chain of T dependent steps has no room for address arithmetic): emission of the next step to
+  // be gathered, lattice row / offset of the next step to be written
+  const ptrdiff_t BC = (ptrdiff_t)B * C;
+  const float* pe = logits + ((size_t)(tfirst + dir) * B + b) * C + l_u;
+  const float* pl = lse + (ptrdiff_t)(tfirst + dir) * B + b;
+  int te = tfirst + dir;                                 // the step pe / pl point at
+  auto emission = [&]() -> float2 {
+    const bool ok = is_beta ? te >= 0 : te < L;
+    const float2 e = ok ? make_float2(__ldg(pe), __ldg(pl)) : make_float2(0.f, 0.f);
+    pe += dir * BC; pl += dir * B; te += dir;
+    return e;
+  };
+  float* po = (is_beta ? beta : alpha) + ((size_t)b * T + tfirst) * Upad + u;
+  double* poffs = (is_beta ? offs_b : offs_a) + (size_t)b * T + tfirst;
+  // the shift of this step: max(row two steps back) - previous shift (uniform over the block)
+  auto shift = [&](int slot, bool have) -> float {
+    float M = 0.f;
+    if (have) {
+      float m = kNegInf;
+      const float4* w4 = reinterpret_cast<const float4*>(wmax + slot * 32);
+#pragma unroll
+      for (int i = 0; i < NW4; ++i) { const float4 w = w4[i]; m = fmaxf(fmaxf(m, fmaxf(w.x, w.y)), fmaxf(w.z, w.w)); }
+      M = ((m == kNegInf) ? 0.f : m) - Mprev;
+    }
+    Mprev = M;
+    return M;
+  };
+
+  if (!is_beta) {
+    const bool skip = (u > 1) && (u < U) && (l_u != blank) && (l_u != lab_at(u - 2));
+    {
+      const float* lg = logits + (size_t)b * C;
+      float v = kNegInf;
+      if (u == 0) v = lg[blank] - lse[b];
+      else if (u == 1 && U > 1) v = lg[l_u] - lse[b];
+      rowbuf[2 + u] = v;
+      if (u < U) *po = v;
+      vlast = v;
+      if (threadIdx.x == 0) *poffs = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) em[i] = emission();
+    __syncthreads();
+    auto step = [&](int t, float2 e) {
+      const float* prev = rowbuf + ((t - 1) & 1) * stride + 2;
+      float* cur = rowbuf + (t & 1) * stride + 2;
+      const float a0 = prev[u], a1 = prev[u - 1], a2 = skip ? prev[u - 2] : kNegInf;
+      const float M = shift((t - 1) & 1, t >= 2);
+      po += Upad; poffs += 1;
+      if (threadIdx.x == 0) { O += (double)M; *poffs = O; }
+      const bool inwin = (u >= U - 2 * (L - t)) && (u < U) && (u < 2 * (t + 1));
+      const float v = inwin ? lse3_fast(a0, a1, a2) + ((e.x - e.y) - M) : kNegInf;
+      cur[u] = v;
+      if (u < U) *po = v;
+      const float wm = warp_max_redux(vlast);            // maxima of row t-1: read by step t+1
+      if (lane == 0) wmax[(t & 1) * 32 + warp] = wm;
+      vlast = v;
+      __syncthreads();
+    };
+    int t = 1;
+    for (; t + D <= L; t += D) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) { const float2 e = em[i]; em[i] = emission(); step(t + i, e); }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) if (t + i < L) step(t + i, em[i]);
+  } else {
+    bool skip = false;
+    if (u + 2 < U) {
+      const int l2 = lab_at(u + 2);
+      skip = beta_skip_dest ? (l2 != blank && l2 != l_u) : (l_u != blank && l_u != l2);
+    }
+    {
+      const float* lgt = logits + ((size_t)(L - 1) * B + b) * C;
+      const float v = (u < U && u >= U - 2) ? 0.f : kNegInf;
+      if (u < U) *po = v;
+      const float nx = (u < U) ? v + (lgt[l_u] - lse[(L - 1) * B + b]) : kNegInf;
+      rowbuf[((L - 1) & 1) * stride + u] = nx;          // beta~[t] + logp[t]: what row t-1 sums over
+      vlast = nx;
+      if (threadIdx.x == 0) *poffs = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) em[i] = emission();
+    __syncthreads();
+    auto step = [&](int t, float2 e) {
+      const float* prev = rowbuf + ((t + 1) & 1) * stride;
+      float* cur = rowbuf + (t & 1) * stride;
+      const float b0 = prev[u], b1 = prev[u + 1], b2 = skip ? prev[u + 2] : kNegInf;
+      const float M = shift((t + 1) & 1, t <= L - 3);
+      po -= Upad; poffs -= 1;
+      if (threadIdx.x == 0) { O += (double)M; *poffs = O; }
+      const bool inwin = (u >= U - 2 * (L - t)) && (u < U) && (u < 2 * (t + 1));
+      const float v = inwin ? lse3_fast(b0, b1, b2) - M : kNegInf;
+      if (u < U) *po = v;
+      const float nx = v + (e.x - e.y);                  // becomes the summand of row t-1
+      cur[u] = nx;
+      const float wm = warp_max_redux(vlast);            // maxima of row t+1: read by step t-1
+      if (lane == 0) wmax[(t & 1) * 32 + warp] = wm;
+      vlast = nx;
+      __syncthreads();
+    };
+    int t = L - 2;
+    for (; t - D + 1 >= 0; t -= D) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) { const float2 e = em[i]; em[i] = emission(); step(t - i, e); }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) if (t - i >= 0) step(t - i, em[i]);
+    // log p(z|x) = LSE_u(alpha[0,u] + beta[0,u]); alpha[0,u] = logp[0,l'u] for u in {0,1}; row 0 of this pass holds
+    // beta~[0,u] + logp[0,l'u] with offset O = Ob[0]
+    if (threadIdx.x == 0) {
+      const float* r0 = rowbuf;
+      const float lpz = (U > 1) ? lse2(r0[0], r0[1]) : r0[0];
+      const double logp = (lpz == kNegInf) ? -INFINITY : (double)lpz + O;
+      logp_out[b] = logp;
+      loss[b] = (float)(-logp);   // +inf when no valid path
+    }
+  }
+}
+
 // one warp per (t,b) row.  dynamic smem: float acc[warps][C]
 __global__ void ctc_grad_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
                                 const int* __restrict__ labels, const int* __restrict__ label_offsets,
@@ -394,11 +578,20 @@ extern "C" int rs_ctc_loss_grad(const float* logits_d, const int32_t* labels_d,
   if (threads > 1024) threads = 1024;
   size_t smem = (size_t)upad * sizeof(int) + 2 * (size_t)(upad + 2) * sizeof(float) + 64 * sizeof(float);
   RS_REQUIRE(smem <= 200 * 1024, RS_ERR_UNSUPPORTED, "rs_ctc_loss_grad: label length %d too large", max_label_len);
-  if (smem > 48 * 1024)
-    RS_CHECK_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ctc_lattice_kernel<<<dim3(B, 2), threads, smem, st>>>(logits_d, lse, labels_d, label_offsets_d, len_d, T, B, C,
-                                                        upad, blank, beta_skip == RS_CTC_BETA_DEST ? 1 : 0,
-                                                        alpha, beta, offs_a, offs_b, logp, loss_d);
+  // one state per thread when every lattice row fits a block (RS_CTC_LATTICE=0: the general kernel)
+  static const bool one_env = [] { const char* v = getenv("RS_CTC_LATTICE"); return !(v && v[0] == '0'); }();
+  if (one_env && (int)align_up((size_t)U, 32) <= 1024) {
+    const size_t smem1 = 2 * (size_t)(upad + 2) * sizeof(float) + 64 * sizeof(float) + 16;
+    auto k = threads <= 256 ? ctc_lattice1_kernel<256> : ctc_lattice1_kernel<1024>;
+    k<<<dim3(B, 2), threads, smem1, st>>>(logits_d, lse, labels_d, label_offsets_d, len_d, T, B, C, upad, blank,
+                                         beta_skip == RS_CTC_BETA_DEST ? 1 : 0, alpha, beta, offs_a, offs_b, logp, loss_d);
+  } else {
+    if (smem > 48 * 1024)
+      RS_CHECK_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctc_lattice_kernel<<<dim3(B, 2), threads, smem, st>>>(logits_d, lse, labels_d, label_offsets_d, len_d, T, B, C,
+                                                          upad, blank, beta_skip == RS_CTC_BETA_DEST ? 1 : 0,
+                                                          alpha, beta, offs_a, offs_b, logp, loss_d);
+  }
   RS_CHECK_LAUNCH();
   if (grad_d) {
     const int warps = 8;

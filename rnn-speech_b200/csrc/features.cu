@@ -251,6 +251,216 @@ fbank_logmel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ o
   }
 }
 
+// ------------------------------------------------------------------------------------
+// fbank_logmel2_kernel: the same stage with the 512-point FFT in REGISTERS.
+//
+// The radix-2 kernel above makes nine passes over a warp's 8 KB of complex fp64 data in shared memory (plus a
+// bit-reversed scatter that lands 32 lanes on one bank): ~1150 shared-memory wavefronts per FFT before conflicts, ~3000
+// with them, and the SM's one shared-memory pipe is what the kernel waits for (ncu round 1: sm throughput 17 %, no
+// other pipe above 10 %).  Here 512 = 16 x 16 x 2:
+//   1. lane b loads x[b + 32 j], j = 0..15 (consecutive lanes read consecutive samples) and runs a 16-point FFT over j
+//      in its own registers: Y[b][k1];
+//   2. twiddle: Z[b][k1] = Y[b][k1] W512^(b k1), the powers of W512^b by repeated multiplication;
+//   3. ONE transpose through shared memory (rows padded to 33): lane (k1, b0) collects Z[2 b1 + b0][k1], b1 = 0..15,
+//      and runs the second 16-point FFT over b1: G[b0][k1][c1];
+//   4. the last radix-2 step X[k1 + 16 c1 + 256 c0] = G[0] +- W32^c1 G[1] is folded into the read of the unpack stage
+//      (the lane that unpacks bin k also unpacks bin 256 - k: the four values it reads are exactly the ones the two
+//      bins need, so the power spectra overwrite them in place).
+// Shared-memory traffic per FFT: 64 + 64 wavefronts for the transpose, 64 for G, ~40 for the unpack.
+// dynamic smem: double fft[8 warps][2][528]; double col[8][40]; double window[512]; float pcm[span + 1]
+// ------------------------------------------------------------------------------------
+static constexpr int kFftLd = 528;      // 16 rows of 33 (the transpose), >= 512 + 1 (G and the power spectra)
+
+__host__ __device__ constexpr double cos_pi16(int c) {   // cos(c pi / 16), c = 0..16
+  return c == 0 ? 1.0 : c == 1 ? 0.98078528040323044913 : c == 2 ? 0.92387953251128675613 : c == 3 ? 0.83146961230254523708
+       : c == 4 ? 0.70710678118654752440 : c == 5 ? 0.55557023301960222474 : c == 6 ? 0.38268343236508977173
+       : c == 7 ? 0.19509032201612826785 : c == 8 ? 0.0 : -cos_pi16(16 - c);
+}
+__host__ __device__ constexpr double sin_pi16(int c) { return c <= 8 ? cos_pi16(8 - c) : cos_pi16(c - 8); }
+__host__ __device__ constexpr int bitrev4(int i) { return ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3); }
+
+// 16-point DFT (forward, e^{-2 pi i jk/16}) of a lane's registers, decimation in frequency; the result is left in
+// bit-reversed order: X[k] = v[bitrev4(k)].  Everything is unrolled: indices and twiddles are compile-time constants.
+__device__ __forceinline__ void fft16_dif(double (&re)[16], double (&im)[16]) {
+#pragma unroll
+  for (int span = 8; span >= 1; span >>= 1) {
+#pragma unroll
+    for (int g = 0; g < 16; g += 2 * span) {
+#pragma unroll
+      for (int k = 0; k < span; ++k) {
+        const int i = g + k, j = i + span;
+        const int m = k * (8 / span);                      // W16^m = cos(m pi/8) - i sin(m pi/8)
+        const double tr = re[i] - re[j], ti = im[i] - im[j];
+        re[i] += re[j]; im[i] += im[j];
+        if (m == 0) { re[j] = tr; im[j] = ti; }
+        else if (m == 4) { re[j] = ti; im[j] = -tr; }      // times -i
+        else {
+          const double c = cos_pi16(2 * m), sn = sin_pi16(2 * m);
+          re[j] = tr * c + ti * sn;                        // (tr + i ti)(c - i sn)
+          im[j] = ti * c - tr * sn;
+        }
+      }
+    }
+  }
+}
+
+template <int MINB>      // CTAs per SM the register budget is cut for (2: 128 registers and a few spilled doubles; 1: 255)
+__global__ void __launch_bounds__(kFbankWarps * 32, MINB)
+fbank_logmel2_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ offsets,
+                     const FbankTables* __restrict__ tab, int frame_length, int frame_step,
+                     int Tstride, int nblk, double* __restrict__ logmel, double* __restrict__ partial,
+                     int* __restrict__ nframes_out) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int b = blockIdx.y;
+  const int64_t off = offsets[b];
+  const int64_t n = offsets[b + 1] - off;
+  int64_t d = n - frame_length; if (d < 0) d = -d;
+  const int T = (int)((d + frame_step - 1) / frame_step);
+  if (blockIdx.x == 0 && threadIdx.x == 0) nframes_out[b] = T;
+  const int t0 = blockIdx.x * kFramesPerCta;
+  double* part = partial + ((size_t)b * nblk + blockIdx.x) * kNfilt;
+  if (t0 >= T) {
+    if (threadIdx.x < kNfilt) part[threadIdx.x] = 0.0;
+    return;
+  }
+  const int nfr = min(kFramesPerCta, T - t0);
+  const int nuse = min(frame_length, kNfft);       // rfft(frames, 512) crops or zero-pads
+  const int span = (kFramesPerCta - 1) * frame_step + nuse;
+  double* sfft = reinterpret_cast<double*>(sm_raw);              // [8][2][528]
+  double* scol = sfft + kFbankWarps * 2 * kFftLd;                // [8][40] per-warp column sums
+  double* swin = scol + kFbankWarps * kNfilt;                    // [512]
+  float* spcm = reinterpret_cast<float*>(swin + kNfft);          // [span + 1], spcm[i] = x[s0 - 1 + i]
+  const int64_t s0 = (int64_t)t0 * frame_step;
+  const float* x = pcm + off;
+  for (int i = threadIdx.x; i < span + 1; i += blockDim.x) {
+    int64_t s = s0 - 1 + i;
+    spcm[i] = (s >= 0 && s < n) ? x[s] : 0.f;
+  }
+  for (int i = threadIdx.x; i < kNfft; i += blockDim.x) swin[i] = tab->window[i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = lane; i < kNfilt; i += 32) scol[warp * kNfilt + i] = 0.0;
+  __syncthreads();
+
+  double* re = sfft + warp * 2 * kFftLd;
+  double* im = re + kFftLd;
+  const double w1r = tab->tw_re[lane], w1i = tab->tw_im[lane];
+  const int k1 = lane & 15, b0 = lane >> 4;
+
+  for (int pair = warp; pair * 2 < nfr; pair += kFbankWarps) {
+    const int fa = pair * 2, fb = fa + 1;
+    const bool has_b = fb < nfr;
+    double vr[16], vi[16];
+    // load (float32 pre-emphasis, float64 window): frame A -> real parts, frame B -> imaginary parts
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i = lane + 32 * j;
+      double va = 0.0, vb = 0.0;
+      if (i < nuse) {
+        {
+          const int p = fa * frame_step + i + 1;         // index into spcm (shifted by one)
+          const int64_t s = s0 + fa * frame_step + i;    // absolute sample
+          // y[0] = x[0]; y[s] = x[s] - 0.97 x[s-1] in float32 with separately rounded product
+          // (numpy: sig[1:] - 0.97 * sig[:-1] on a float32 array); zero beyond the signal
+          const float prev = (s > 0) ? spcm[p - 1] : 0.f;
+          const float y = (s < n) ? __fsub_rn(spcm[p], __fmul_rn(0.97f, prev)) : 0.f;
+          va = (double)y * swin[i];
+        }
+        if (has_b) {
+          const int p = fb * frame_step + i + 1;
+          const int64_t s = s0 + fb * frame_step + i;
+          const float prev = (s > 0) ? spcm[p - 1] : 0.f;
+          const float y = (s < n) ? __fsub_rn(spcm[p], __fmul_rn(0.97f, prev)) : 0.f;
+          vb = (double)y * swin[i];
+        }
+      }
+      vr[j] = va; vi[j] = vb;
+    }
+    fft16_dif(vr, vi);                                  // Y[lane][k] = v[bitrev4(k)]
+    // twiddle by W512^(lane k) and transpose: row k of the buffer holds Z[.][k]
+    {
+      double pr = 1.0, pi = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const double yr = vr[bitrev4(k)], yi = vi[bitrev4(k)];
+        re[k * 33 + lane] = yr * pr - yi * pi;
+        im[k * 33 + lane] = yr * pi + yi * pr;
+        const double qr = pr * w1r - pi * w1i, qi = pr * w1i + pi * w1r;
+        pr = qr; pi = qi;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int b1 = 0; b1 < 16; ++b1) { vr[b1] = re[k1 * 33 + 2 * b1 + b0]; vi[b1] = im[k1 * 33 + 2 * b1 + b0]; }
+    __syncwarp();
+    fft16_dif(vr, vi);                                  // G[b0][k1][c] = v[bitrev4(c)]
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      // lanes with b0 = 1 carry the odd half: times W32^c = cos(c pi/16) - i sin(c pi/16)
+      const double wr = b0 ? cos_pi16(c) : 1.0, wi = b0 ? -sin_pi16(c) : 0.0;
+      const double gr = vr[bitrev4(c)], gi = vi[bitrev4(c)];
+      re[b0 * 256 + c * 16 + k1] = gr * wr - gi * wi;
+      im[b0 * 256 + c * 16 + k1] = gr * wi + gi * wr;
+    }
+    __syncwarp();
+    // X[k] = G0[k & 255] +- G1[k & 255] (minus for k >= 256).  Unpack the two real spectra, power = |X|^2 / 512: bins k
+    // and 256 - k together (their inputs are G0 / G1 at k and at 256 - k), in place -- frame A's spectrum in re[0..256],
+    // frame B's in im[0..256]
+    for (int k = lane; k <= 128; k += 32) {
+      const int k2 = 256 - k, k2i = k2 & 255;
+      const double ar = re[k], ai = im[k], br = re[256 + k], bi = im[256 + k];
+      const double cr = re[k2i], ci = im[k2i], dr = re[256 + k2i], di = im[256 + k2i];
+      // bin k: Z = X[k], Y = X[512 - k];  bin 256 - k: Z' = X[256 - k], Y' = X[256 + k]
+      const double zr = ar + br, zi = ai + bi, y2r = ar - br, y2i = ai - bi;
+      double yr, yi, z2r, z2i;
+      if (k == 0) { yr = zr; yi = zi; z2r = y2r; z2i = y2i; }         // X[0] and X[256] pair with themselves
+      else { yr = cr - dr; yi = ci - di; z2r = cr + dr; z2i = ci + di; }
+      {
+        const double fr = 0.5 * (zr + yr), fi = 0.5 * (zi - yi), gr = 0.5 * (zi + yi), gi = -0.5 * (zr - yr);
+        re[k] = (fr * fr + fi * fi) * (1.0 / kNfft);
+        im[k] = (gr * gr + gi * gi) * (1.0 / kNfft);
+      }
+      {
+        const double fr = 0.5 * (z2r + y2r), fi = 0.5 * (z2i - y2i), gr = 0.5 * (z2i + y2i), gi = -0.5 * (z2r - y2r);
+        re[k2] = (fr * fr + fi * fi) * (1.0 / kNfft);
+        im[k2] = (gr * gr + gi * gi) * (1.0 / kNfft);
+      }
+    }
+    __syncwarp();
+    const double* pw = re;
+    const double* pwb = im;
+    // 40 triangular filters; one lane owns filter m for BOTH frames of the pair so the
+    // per-warp column sums are accumulated in a fixed order (deterministic).
+    for (int m = lane; m < kNfilt; m += 32) {
+      const double* w = tab->melw + m * kBins;
+      double acc_a = 0.0, acc_b = 0.0;
+      const int kend = tab->mend[m];
+      for (int k = tab->mstart[m]; k < kend; ++k) {
+        const double wk = w[k];
+        acc_a = fma(pw[k], wk, acc_a);
+        acc_b = fma(pwb[k], wk, acc_b);
+      }
+      if (acc_a == 0.0) acc_a = 2.220446049250313e-16;   // util/audioprocessor.py:135
+      if (acc_b == 0.0) acc_b = 2.220446049250313e-16;
+      const double va = 10.0 * log10(acc_a);
+      double colsum = va;
+      logmel[((size_t)b * Tstride + (t0 + fa)) * kNfilt + m] = va;
+      if (has_b) {
+        const double vb = 10.0 * log10(acc_b);
+        logmel[((size_t)b * Tstride + (t0 + fb)) * kNfilt + m] = vb;
+        colsum += vb;
+      }
+      scol[warp * kNfilt + m] += colsum;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < kNfilt) {
+    double s = 0.0;
+    for (int w = 0; w < kFbankWarps; ++w) s += scol[w * kNfilt + threadIdx.x];
+    part[threadIdx.x] = s;
+  }
+}
+
 // grid (ceil(Tmax / 32), B), 256 threads
 __global__ void __launch_bounds__(256)
 fbank_delta_kernel(const double* __restrict__ logmel, const double* __restrict__ partial,
@@ -386,16 +596,18 @@ extern "C" int rs_fbank_forward(const float* pcm_d, const int64_t* offsets_d, in
 
   const int nuse = fp.frame_length < kNfft ? fp.frame_length : kNfft;
   const int span = (kFramesPerCta - 1) * fp.frame_step + nuse;
-  size_t smem = (size_t)(kFbankWarps * 2 * kNfft + kFbankWarps * kNfilt) * sizeof(double) +
+  // register FFT (fbank_logmel2_kernel); RS_FBANK_FFT=0: the shared-memory radix-2 kernel
+  static const bool reg_fft = [] { const char* v = getenv("RS_FBANK_FFT"); return !(v && v[0] == '0'); }();
+  const int fft_ld = reg_fft ? kFftLd : kNfft;
+  size_t smem = (size_t)(kFbankWarps * 2 * fft_ld + kFbankWarps * kNfilt + (reg_fft ? kNfft : 0)) * sizeof(double) +
                 (size_t)(span + 1 + 3) * sizeof(float);
   RS_REQUIRE(smem <= 220 * 1024, RS_ERR_UNSUPPORTED, "rs_fbank_forward: sr %d needs %zu B smem", sr, smem);
-  RS_CHECK_CUDA(cudaFuncSetAttribute(fbank_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // (two 89 KB CTAs per SM; measured: occupancy does not move this kernel -- 0.39 ms either way -- its radix-2 stages
-  //  are bound by 64-bit shared-memory traffic, see DESIGN.md "what comes next")
-  RS_CHECK_CUDA(cudaFuncSetAttribute(fbank_logmel_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  fbank_logmel_kernel<<<dim3(nblk, B), kFbankWarps * 32, smem, st>>>(pcm_d, offsets_d, tab_d, fp.frame_length,
-                                                                     fp.frame_step, Tfull, nblk, logmel, partial,
-                                                                     nframes_d);
+  static const int occ = [] { const char* v = getenv("RS_FBANK_OCC"); return v ? atoi(v) : 2; }();
+  auto kern = reg_fft ? (occ == 1 ? fbank_logmel2_kernel<1> : fbank_logmel2_kernel<2>) : fbank_logmel_kernel;
+  RS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  kern<<<dim3(nblk, B), kFbankWarps * 32, smem, st>>>(pcm_d, offsets_d, tab_d, fp.frame_length, fp.frame_step, Tfull, nblk,
+                                                      logmel, partial, nframes_d);
   RS_CHECK_LAUNCH();
   fbank_delta_kernel<<<dim3(cdiv(Tmax, 32), B), 256, 0, st>>>(logmel, partial, nframes_d, Tfull, nblk, Tmax, B,
                                                               delta_mode, time_major, out_d);

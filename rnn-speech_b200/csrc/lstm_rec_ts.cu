@@ -769,7 +769,7 @@ rec_ts_fwd2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
 // retries happen and that nothing changes bit for bit.)
 //
 // The chains take turns: see the producer warps.
-// Requires Bpad == 32 and all of K in one tile (as rec_ts_fwd2_kernel).
+// Requires Bpad <= 32 and all of K in one tile.  A batch of at most 16 rows runs as one chain (the second chain's warps idle).
 // ------------------------------------------------------------------------------------
 constexpr uint32_t kFill = 0xffffffffu;
 
@@ -807,7 +807,7 @@ __device__ __forceinline__ bool tile_has_fill(uint32_t saddr, uint32_t bytes, in
 
 struct KFwd3 {
   RecTcFwdArgs a;
-  int H, B, nslice, nkb, nkb_t;
+  int H, B, Bpad, nslice, nkb, nkb_t;
   int turns;                      // 1: the chains take turns at the TMA port and the tensor pipe (see the producer warps)
   int fault;                      // STAMP instantiation only: delay half of every publish behind its hint (test of the retry path)
   int endbar;                     // 1: the chain's four epilogue warps meet once more at the end of a step
@@ -876,7 +876,12 @@ rec_ts_fwd3_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
   __syncthreads();
   tc::tc_fence_after();
 
-  if (warp == 8 || warp == 10) {
+  // a batch of at most 16 rows is ONE chain: the roles of chain 1 have nothing to do (and nobody to take turns with)
+  const bool two = B > CHB;
+  const int my_chain = warp < 8 ? (warp >> 2) : ((warp - 8) >> 1);
+  if (my_chain == 1 && !two) {
+    // (falls through to the common exit)
+  } else if (warp == 8 || warp == 10) {
     // ------------------------------------------------------------------ TMA producer of chain X
     const int X = (warp - 8) >> 1;
     if (lane == 0) tc::tma_prefetch_desc(&tmH);
@@ -902,7 +907,7 @@ rec_ts_fwd3_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
       }
       if (lane == 0) RS_STAMP3(ti, 0, gtime());
       __syncwarp();
-      if (p.turns) {
+      if (p.turns && two) {
         // Two chains that start together stay together (measured: 6 ns apart after 900 steps, and they fall back into
         // lockstep from either side of half a period): both tiles cross the SM's port at the same time and 2 x 48 MMAs
         // queue on one tensor pipe, so that a step of either takes as long as the step of a 32-row batch.  So they take
@@ -975,8 +980,8 @@ rec_ts_fwd3_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
 
     for (int ti = 0; ti < T; ++ti) {
       const int t = a.t0 + ti;
-      // hoisted input projection for this step (independent of the recurrence: issue early); Bpad = 32, group X
-      const float4* gp = reinterpret_cast<const float4*>(a.gx + (((size_t)t * nslice + j) * 64 + m) * 32 + X * 16 + 8 * up);
+      // hoisted input projection for this step (independent of the recurrence: issue early); column group X of Bpad = 16 or 32
+      const float4* gp = reinterpret_cast<const float4*>(a.gx + (((size_t)t * nslice + j) * 64 + m) * p.Bpad + X * 16 + 8 * up);
       const float4 gx0 = __ldg(gp), gx1 = __ldg(gp + 1);
       float ig[2], jg[2], fg[2], og[2], c_new[2], h_new[2], hout[2];
       for (;;) {
@@ -2193,25 +2198,29 @@ int lstm_rec_ts_forward(const RecTcGeom& g, const RecTcFwdArgs& a_in, cudaStream
   // two independent 16-row chains per CTA (rec_ts_fwd2_kernel) when the batch allows it; RS_TS_CHAINS=0: one chain
   static const bool chains_env = [] { const char* v = getenv("RS_TS_CHAINS"); return !(v && v[0] == '0'); }();
   const bool shape2 = chains_env && ts_variant() == kDefaultVariant && g.Bpad == 32 && g.B > CHB && g.gkb == g.H / 64 && g.stages == 1;
+  // (rec_ts_fwd3_kernel also takes batches of at most 16 rows, as one chain; RS_TS_XCHG16=0: the round-1 kernel for those)
+  static const bool xchg16_env = [] { const char* v = getenv("RS_TS_XCHG16"); return !(v && v[0] == '0'); }();
+  const bool shape1 = xchg16_env && chains_env && ts_variant() == kDefaultVariant && g.Bpad == 16 && g.gkb == g.H / 64 && g.stages == 1;
   const bool two_chains = shape2 && !a.dbg;
   // self-validating exchange (rec_ts_fwd3_kernel; RS_TS_XCHG=0: the counter + TMA exchange of rec_ts_fwd2_kernel)
   static const bool xchg_env = [] { const char* v = getenv("RS_TS_XCHG"); return !(v && v[0] == '0'); }();
-  if (shape2 && xchg_env) {
+  if ((shape2 || shape1) && xchg_env) {
     CUtensorMap td0, td1;
     if ((rc = tmap_stacked_bf16(&th, a.h_hi, hrows, g.H, CHB, g.gkb)) != RS_OK) return rc;
     td0 = th; td1 = th;
     if (a.drop_hi) {
       RS_REQUIRE(a.drop_lo > a.drop_hi, RS_ERR_INVALID, "lstm_rec_ts_forward: the low hop plane must follow the high one");
       const size_t pstride = (size_t)((const char*)a.drop_lo - (const char*)a.drop_hi);
-      if ((rc = tmap_store3_bf16(&td0, a.drop_hi, g.H, 2, a.Ttot * g.B, pstride, (size_t)g.H * 2, TSU, 2, CHB)) != RS_OK) return rc;
-      if ((rc = tmap_store3_bf16(&td1, a.drop_hi, g.H, 2, a.Ttot * g.B, pstride, (size_t)g.H * 2, TSU, 2, g.B - CHB)) != RS_OK) return rc;
+      if ((rc = tmap_store3_bf16(&td0, a.drop_hi, g.H, 2, a.Ttot * g.B, pstride, (size_t)g.H * 2, TSU, 2, g.B < CHB ? g.B : CHB)) != RS_OK) return rc;
+      td1 = td0;
+      if (g.B > CHB && (rc = tmap_store3_bf16(&td1, a.drop_hi, g.H, 2, a.Ttot * g.B, pstride, (size_t)g.H * 2, TSU, 2, g.B - CHB)) != RS_OK) return rc;
     }
     // slots 1..Ttot of the planes carry the fill pattern until their producers overwrite it (first launch of a pass)
     if (a.t0 == 0)
       RS_CHECK_CUDA(cudaMemsetAsync(a.h_hi + (size_t)g.B * a.h_ld, 0xff, (size_t)a.Ttot * g.B * a.h_ld * sizeof(__nv_bfloat16), st));
     KFwd3 p3;
     p3.a = a;
-    p3.H = g.H; p3.B = g.B; p3.nslice = g.nslice; p3.nkb = g.H / 64; p3.nkb_t = g.nkb_t;
+    p3.H = g.H; p3.B = g.B; p3.Bpad = g.Bpad; p3.nslice = g.nslice; p3.nkb = g.H / 64; p3.nkb_t = g.nkb_t;
     static const int turns_env = [] { const char* v = getenv("RS_TS_TURNS"); return v ? atoi(v) : 1; }();
     p3.turns = turns_env;
     { const char* v = getenv("RS_TS_FAULT"); p3.fault = (a.dbg && v && v[0] == '1') ? 1 : 0; }

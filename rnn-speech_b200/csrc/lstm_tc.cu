@@ -482,7 +482,8 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
   std::vector<cudaEvent_t> e_gx((size_t)L * NC), e_out((size_t)L * NC), done;
 
   // hoisted input half of chunk c: gx = xin @ K[:H] + b, written in the recurrent kernel's layout
-  auto issue_gemm = [&](int l, int c) -> int {
+  // cap > 0: at most that many (persistent) CTAs -- a GEMM that runs beside the recurrent launches of a wave
+  auto issue_gemm = [&](int l, int c, int cap = 0) -> int {
     const int t0 = sc.start[c], n = sc.start[c + 1] - sc.start[c];
     if (l > 0) RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_out[(size_t)(l - 1) * NC + c], 0));
     SplitMat A{bf.wx_hi[l], bf.wx_lo[l], 4 * H, H, H};
@@ -490,7 +491,7 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     GemmTcOut o{};
     o.mode = GEMM_OUT_REC; o.C = bf.gx[l] + (size_t)t0 * 4 * H * am->tc.Bpad; o.bias = params_d + am->off_bias[l];
     o.recB = B; o.recBpad = am->tc.Bpad; o.recH = H; o.recU = am->tc.U;
-    o.max_ctas = sc.phases ? 0 : sc.fwd_gemm_ctas; o.tiles_per_cta = sc.gx_tpc;
+    o.max_ctas = cap > 0 ? cap : (sc.phases ? 0 : sc.fwd_gemm_ctas); o.tiles_per_cta = cap > 0 ? 0 : sc.gx_tpc;
     RC(gemm_tc_nt(A, Bm, 4 * H, n * B, H, 3, o, am->gemm_st));
     return ev_record(am, &e_gx[(size_t)l * NC + c], am->gemm_st);
   };
@@ -547,6 +548,14 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
     // the chunk GEMMs the next wave needs run as one burst on the whole machine -- the gate pre-activations of layer 0's
     // next chunk and of the chunks the layers above have just been handed.  The recurrent launches of a wave wait for the
     // burst to end, so that all their CTAs find free SMs at once.
+    //
+    // While the wavefront fills (waves 0 .. L-2) the layers that have not started leave nslice SMs each idle, and layer
+    // 0's input does not depend on the recurrences: the gate pre-activations of some of its LATER chunks are computed
+    // there, beside the wave, on a grid capped to the idle SMs -- those GEMMs then drop out of the bursts of the
+    // steady state.  RS_TC_HOIST = idle SMs per hoisted chunk GEMM (0: off).  Measured at cfg-2 (profiles/r02c_sweep1/2.log):
+    // forward 5.35 ms without, 5.21 / 5.13 / 5.05 / 5.05 / 5.07 / 5.15 ms with 40 / 26 / 20 / 16 / 12 / 8.
+    static const int hoist_env = [] { const char* v = getenv("RS_TC_HOIST"); return v ? atoi(v) : 16; }();
+    int next_g0 = 1;                                              // layer 0: first chunk whose GEMM has not been issued
     RC(issue_gemm(0, 0));
     RC(ev_record(am, &e_phase, am->gemm_st));
     for (int d = 0; d < NC + L - 1; ++d) {
@@ -554,12 +563,17 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
         const int c = d - l;
         if (c >= 0 && c < NC) RC(issue_rec(l, c));
       }
+      if (hoist_env > 0 && d + 1 < L) {
+        const int idle = sm_count() - (d + 1) * am->tc.nslice;
+        // the chunk the next wave needs stays in the burst unless this wave has room for it
+        for (int i = 0; i < idle / hoist_env && next_g0 < NC; ++i) RC(issue_gemm(0, next_g0++, idle));
+      }
       // the burst starts when the slowest launch of the wave has finished: GEMM CTAs must not take SMs from it
       for (int l = 0; l < L; ++l) {
         const int c = d - l;
         if (c >= 0 && c < NC) RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_out[(size_t)l * NC + c], 0));
       }
-      if (d + 1 < NC) RC(issue_gemm(0, d + 1));
+      if (d + 1 < NC && next_g0 <= d + 1) { RC(issue_gemm(0, d + 1)); next_g0 = d + 2; }
       for (int l = 1; l < L; ++l) {
         const int c = d - (l - 1);
         if (c >= 0 && c < NC) RC(issue_gemm(l, c));               // input = layer l - 1's chunk c of this wave
@@ -643,7 +657,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   RS_CHECK_CUDA(cudaMemsetAsync(bf.elastic, 0, 4096 * sizeof(int), st));
   for (int i = 0; i < 2; ++i) RS_CHECK_CUDA(cudaMemsetAsync(bf.colsum_ws[i], 0, colsum_scratch_bytes(4 * H > C ? 4 * H : C), st));
   int elastic_next = 0;
-  const bool use_elastic = NC > 1 && !sc.cores && !sc.phases && sc.side_tpc == 0 && 2 * L * NC + NC + 8 < 4096;
+  const bool use_elastic = NC > 1 && !sc.cores && !sc.phases && sc.side_tpc == 0 && 2 * L * NC + 2 * NC + 8 < 4096;
   cudaEvent_t e_fork;
   RC(ev_record(am, &e_fork, st));
   for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(am->lane[l], e_fork, 0));
@@ -713,17 +727,28 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
     return RS_OK;
   };
   // critical path between layers: din[l] = dg @ K[:H]^T for the steps of chunk c
+  // Layer 0's product is NOT on that path -- it only feeds the input dense's weight gradient -- so it goes to the side
+  // stream with the weight-gradient GEMMs (RS_TC_DX0_SIDE=0: in line with the others, where every third GEMM of the
+  // in-order critical stream made the layers above wait: profiles/r02b_trace.txt).
+  static const bool dx0_side_env = [] { const char* v = getenv("RS_TC_DX0_SIDE"); return !(v && v[0] == '0'); }();
+  const bool dx0_side = dx0_side_env && NC > 1 && !sc.phases && !sc.cores;
   auto issue_dx = [&](int l, int c) -> int {
     const int t0 = sc.start[c], n = sc.start[c + 1] - sc.start[c];
-    RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_rec[(size_t)l * NC + c], 0));
+    const bool off_path = l == 0 && dx0_side;
+    cudaStream_t gs = off_path ? side : am->gemm_st;
+    RS_CHECK_CUDA(cudaStreamWaitEvent(gs, e_rec[(size_t)l * NC + c], 0));
     SplitMat A{bf.dg_hi[l] + (size_t)t0 * B * 4 * H, bf.dg_lo[l] + (size_t)t0 * B * 4 * H, n * B, 4 * H, 4 * H};
     SplitMat Bm{bf.wxs_hi[l], bf.wxs_lo[l], H, 4 * H, 4 * H};
     GemmTcOut o{};
     o.mode = GEMM_OUT_F32; o.C = bf.din[l] + (size_t)t0 * B * H; o.ldc = H; o.max_ctas = (sc.cores || sc.phases) ? 0 : sc.gemm_ctas; o.tiles_per_cta = sc.dx_tpc; o.coresident = sc.cores;
-    RC(tev_record(am, 3, l, am->gemm_st));
-    RC(gemm_tc_nt(A, Bm, n * B, H, 4 * H, 3, o, am->gemm_st));
-    RC(tev_record(am, 3, l, am->gemm_st));
-    return ev_record(am, &e_dx[(size_t)l * NC + c], am->gemm_st);
+    if (off_path) {
+      o.max_ctas = sc.side_ctas; o.tiles_per_cta = side_tpc;
+      if (use_elastic) { o.elastic = bf.elastic; o.elastic_id = elastic_next++; }
+    }
+    RC(tev_record(am, 3, l, gs));
+    RC(gemm_tc_nt(A, Bm, n * B, H, 4 * H, 3, o, gs));
+    RC(tev_record(am, 3, l, gs));
+    return ev_record(am, &e_dx[(size_t)l * NC + c], gs);
   };
   // side stream: dK[:H] += xin^T dg ; dK[H:] += hprev^T dg ; db += colsum(dg) over the steps of chunk c, as soon as
   // that chunk's dgates exist (fp32 accumulation into the gradient buffer, chunk after chunk)
