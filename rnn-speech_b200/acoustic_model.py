@@ -58,7 +58,11 @@ def levenshtein(a, b):
     return int(prev[-1])
 
 
-TC_MAX_BATCH = 64      # utterances per launch of the tensor-core recurrent kernels (csrc/lstm_rec_ts.cu)
+# Utterances per launch of the tensor-core recurrent kernels: a larger mini-batch runs as batch tiles of this size.
+# csrc/lstm_rec_ts.cu takes up to 64 rows, but its fastest kernels (two 16-row chains per CTA, validated exchange) take
+# 32: measured at BASELINE config 5 (256 clips x 5 s), tiles of 32 give 11 588 clips/s against 10 546 with tiles of 64
+# (profiles/r02c_sweep5.log).  RS_TC_MAX_BATCH overrides.
+TC_MAX_BATCH = int(os.environ.get("RS_TC_MAX_BATCH", "32"))
 
 
 class AcousticModel(object):

@@ -243,30 +243,35 @@ ctc_lattice_kernel(const float* __restrict__ logits, const float* __restrict__ l
 // ------------------------------------------------------------------------------------
 // ctc_lattice1_kernel: the same lattice with ONE state per thread (2 N + 1 <= blockDim) and a short dependent chain
 // per time step.  The lattice is a chain of T dependent steps per item, so the kernel's time is T x (latency of one
-// step); what the general kernel above has on that chain besides the three-way log-sum-exp -- the block-wide maximum of
-// the row just written (5 shuffles, a shared-memory hop, 8 loads), libm's expf / logf, the reloads of the label
-// tables -- is taken off it here:
-//   * the shift of row t is derived from the maximum of row t-2, not t-1: O[t] = O[t-2] + max(row t-2), i.e.
-//     M[t] = max(row t-2) - M[t-1].  Still exact bookkeeping (the offsets are summed in double and the gradient
-//     kernel adds them back), the stored values stay within two steps' emissions of zero, and the warp / block
-//     reduction of row t-1 runs BESIDE step t's log-sum-exp instead of before it;
-//   * exp / log through the special-function unit (ex2.approx / lg2.approx: absolute error ~2e-7 per step on values
-//     of order one, against 1e-7 for libm; tests/test_gpu_ctc.py holds the gradient to 1e-4 / 1e-3);
-//   * label, skip flag and window of the thread's state live in registers; emissions are gathered 8 steps ahead.
-// dynamic smem: float row[2][Upad + 2]; float wmax[2][32]
+// step); ncu of the general kernel above and of this kernel's first version shows no memory or pipe limit, only
+// instructions that wait for each other (~6 cycles each).  What is on the chain here: three shared-memory loads, two
+// maxima, three ex2, two adds, one lg2, two adds, one store, the barrier.  Everything else is kept off it:
+//   * base-2 logarithms throughout (ex2.approx / lg2.approx are single SFU instructions; absolute error ~2e-7 per
+//     step on values of order one, against 1e-7 for libm; tests/test_gpu_ctc.py holds the gradient to 1e-4 / 1e-3).
+//     The rows in the workspace and the offsets are in base-2 units, log p(z|x) is converted at the end, and the
+//     gradient kernel is told (log2_domain);
+//   * the shift of row t is derived from the maximum of row t-3, not t-1: O[t] = O[t-3] + max(row t-3), i.e.
+//     M[t] = max(row t-3) - M[t-1] - M[t-2].  Still exact bookkeeping (the offsets are summed in double and the
+//     gradient kernel adds them back), the stored values stay within three steps' emissions of zero, and the per-warp
+//     maxima of row t-1 (one REDUX over order-preserving integer keys) are produced beside step t's log-sum-exp,
+//     fetched before its barrier and combined in the shadow of step t+1's loads;
+//   * label, skip flag and window of the thread's state live in registers, pointers advance by constants, emissions
+//     are gathered 8 steps ahead, the window is a -inf added to the emission instead of a branch.
+// dynamic smem: float row[2][Upad + 2]; uint32 wkey[2][32]
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ float lse3_fast(float a, float b, float c) {
-  const float m = fmaxf(a, fmaxf(b, c));
-  const float ms = (m == kNegInf) ? 0.f : m;            // all three -inf: exp(-inf - 0) = 0, log(0) = -inf
-  return ms + __logf(__expf(a - ms) + __expf(b - ms) + __expf(c - ms));
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// log2(2^a + 2^b + 2^c); all three -inf: the maximum is clamped to a finite value, 2^(-inf) = 0, lg2(0) = -inf
+__device__ __forceinline__ float l2se3(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(a, b), fmaxf(c, -3.0e38f));
+  return m + lg2_approx(ex2_approx(a - m) + ex2_approx(b - m) + ex2_approx(c - m));
 }
-// warp maximum in one REDUX instruction: floats through their order-preserving unsigned image
-__device__ __forceinline__ float warp_max_redux(float v) {
+// order-preserving image of a float in the unsigned integers, and back
+__device__ __forceinline__ uint32_t fkey(float v) {
   const uint32_t bits = __float_as_uint(v);
-  const uint32_t key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
-  const uint32_t k = __reduce_max_sync(0xffffffffu, key);
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+  return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
 }
+__device__ __forceinline__ float fkey_inv(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT)
@@ -279,7 +284,7 @@ ctc_lattice1_kernel(const float* __restrict__ logits, const float* __restrict__ 
   extern __shared__ unsigned char smem_raw[];
   float* rowbuf = reinterpret_cast<float*>(smem_raw);
   const int stride = Upad + 2;
-  float* wmax = rowbuf + 2 * stride;
+  uint32_t* wkey = reinterpret_cast<uint32_t*>(rowbuf + 2 * stride);
   const int b = blockIdx.x;
   const bool is_beta = blockIdx.y == 1;
   const CtcItem it = ctc_item(len, label_offsets, b);
@@ -287,27 +292,29 @@ ctc_lattice1_kernel(const float* __restrict__ logits, const float* __restrict__ 
     if (is_beta && threadIdx.x == 0) { loss[b] = 0.f; logp_out[b] = 0.0; }
     return;
   }
+  constexpr float kLog2e = 1.4426950408889634f;
+  constexpr double kLn2 = 0.6931471805599453;
   const int U = it.U, L = it.L;
   const int u = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int NW4 = MAXT / 128;                        // float4 loads that cover one per-warp maximum per warp
+  constexpr int NW4 = MAXT / 128;                        // uint4 loads that cover one per-warp maximum per warp
   const int* lab = labels + label_offsets[b];
   auto lab_at = [&](int v) -> int { return (v >= 0 && v < U) ? ((v & 1) ? lab[v >> 1] : blank) : -1; };
   const int l_u = (u < U) ? lab_at(u) : blank;
   // row r of the lattice lives at rowbuf[(r & 1) * stride + 2 + v] (alpha: two -inf guards in front)
   //                               rowbuf[(r & 1) * stride + v]     (beta: two -inf guards behind)
   for (int i = threadIdx.x; i < 2 * stride; i += blockDim.x) rowbuf[i] = kNegInf;
-  if (threadIdx.x < 64) wmax[threadIdx.x] = kNegInf;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) wkey[i] = fkey(kNegInf);      // (a block may be a single warp)
   __syncthreads();
   const int dir = is_beta ? -1 : 1;                      // direction of time
   const int tfirst = is_beta ? L - 1 : 0;                // the row that is written directly
-  double O = 0.0;                                        // thread 0: offset of the current row
-  float Mprev = 0.f, vlast;
-  constexpr int D = MAXT <= 256 ? 8 : 2;                 // emissions in flight (the register budget of 1024 threads allows 4)
+  double O = 0.0;                                        // thread 0: offset of the current row (base-2 units)
+  float M1 = 0.f, M2 = 0.f, vlast;                       // the shifts of the two previous steps
+  constexpr int D = MAXT <= 256 ? 8 : 2;                 // emissions in flight (what the register budget of 1024 threads allows)
   float2 em[D];
   // running pointers (the chain of T dependent steps has no room for address arithmetic): emission of the next step to
   // be gathered, lattice row / offset of the next step to be written
   const ptrdiff_t BC = (ptrdiff_t)B * C;
-  const float* pe = logits + ((size_t)(tfirst + dir) * B + b) * C + l_u;
+  const float* pe = logits + ((ptrdiff_t)(tfirst + dir) * B + b) * C + l_u;
   const float* pl = lse + (ptrdiff_t)(tfirst + dir) * B + b;
   int te = tfirst + dir;                                 // the step pe / pl point at
   auto emission = [&]() -> float2 {
@@ -318,18 +325,30 @@ ctc_lattice1_kernel(const float* __restrict__ logits, const float* __restrict__ 
   };
   float* po = (is_beta ? beta : alpha) + ((size_t)b * T + tfirst) * Upad + u;
   double* poffs = (is_beta ? offs_b : offs_a) + (size_t)b * T + tfirst;
-  // the shift of this step: max(row two steps back) - previous shift (uniform over the block)
-  auto shift = [&](int slot, bool have) -> float {
+  uint4 wk[NW4];                                         // per-warp maxima (keys) of the row three steps back, fetched before the barrier
+#pragma unroll
+  for (int i = 0; i < NW4; ++i) wk[i] = make_uint4(0u, 0u, 0u, 0u);
+  // the shift of this step from the keys fetched during the previous one (uniform over the block)
+  auto shift = [&](bool have) -> float {
     float M = 0.f;
     if (have) {
-      float m = kNegInf;
-      const float4* w4 = reinterpret_cast<const float4*>(wmax + slot * 32);
+      uint32_t k = 0u;
 #pragma unroll
-      for (int i = 0; i < NW4; ++i) { const float4 w = w4[i]; m = fmaxf(fmaxf(m, fmaxf(w.x, w.y)), fmaxf(w.z, w.w)); }
-      M = ((m == kNegInf) ? 0.f : m) - Mprev;
+      for (int i = 0; i < NW4; ++i) k = max(max(k, max(wk[i].x, wk[i].y)), max(wk[i].z, wk[i].w));
+      const float m = fkey_inv(k);
+      M = ((m == kNegInf) ? 0.f : m) - M1 - M2;
     }
-    Mprev = M;
+    M2 = M1; M1 = M;
     return M;
+  };
+  // end of a step: the maxima of the row before the one just written go to slot `wslot`, the maxima written during the
+  // previous step (slot `rslot`) are fetched for the next step's shift
+  auto row_end = [&](int wslot, int rslot) {
+    const uint32_t k = __reduce_max_sync(0xffffffffu, fkey(vlast));
+    if (lane == 0) wkey[wslot * 32 + warp] = k;
+    const uint4* w4 = reinterpret_cast<const uint4*>(wkey + rslot * 32);
+#pragma unroll
+    for (int i = 0; i < NW4; ++i) wk[i] = w4[i];
   };
 
   if (!is_beta) {
@@ -337,8 +356,8 @@ ctc_lattice1_kernel(const float* __restrict__ logits, const float* __restrict__ 
     {
       const float* lg = logits + (size_t)b * C;
       float v = kNegInf;
-      if (u == 0) v = lg[blank] - lse[b];
-      else if (u == 1 && U > 1) v = lg[l_u] - lse[b];
+      if (u == 0) v = (lg[blank] - lse[b]) * kLog2e;
+      else if (u == 1 && U > 1) v = (lg[l_u] - lse[b]) * kLog2e;
       rowbuf[2 + u] = v;
       if (u < U) *po = v;
       vlast = v;
@@ -347,19 +366,20 @@ ctc_lattice1_kernel(const float* __restrict__ logits, const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < D; ++i) em[i] = emission();
     __syncthreads();
+    // step t writes row t from row t-1; its shift comes from row t-3 (t >= 3)
     auto step = [&](int t, float2 e) {
       const float* prev = rowbuf + ((t - 1) & 1) * stride + 2;
       float* cur = rowbuf + (t & 1) * stride + 2;
       const float a0 = prev[u], a1 = prev[u - 1], a2 = skip ? prev[u - 2] : kNegInf;
-      const float M = shift((t - 1) & 1, t >= 2);
+      const float M = shift(t >= 3);
       po += Upad; poffs += 1;
       if (threadIdx.x == 0) { O += (double)M; *poffs = O; }
       const bool inwin = (u >= U - 2 * (L - t)) && (u < U) && (u < 2 * (t + 1));
-      const float v = inwin ? lse3_fast(a0, a1, a2) + ((e.x - e.y) - M) : kNegInf;
+      const float add = fmaf(e.x - e.y, kLog2e, -M) + (inwin ? 0.f : kNegInf);
+      const float v = l2se3(a0, a1, a2) + add;
       cur[u] = v;
       if (u < U) *po = v;
-      const float wm = warp_max_redux(vlast);            // maxima of row t-1: read by step t+1
-      if (lane == 0) wmax[(t & 1) * 32 + warp] = wm;
+      row_end(t & 1, (t - 1) & 1);                       // keys of row t-1 out, keys of row t-2 in (for step t+1)
       vlast = v;
       __syncthreads();
     };
@@ -380,7 +400,7 @@ ctc_lattice1_kernel(const float* __restrict__ logits, const float* __restrict__ 
       const float* lgt = logits + ((size_t)(L - 1) * B + b) * C;
       const float v = (u < U && u >= U - 2) ? 0.f : kNegInf;
       if (u < U) *po = v;
-      const float nx = (u < U) ? v + (lgt[l_u] - lse[(L - 1) * B + b]) : kNegInf;
+      const float nx = (u < U) ? v + (lgt[l_u] - lse[(L - 1) * B + b]) * kLog2e : kNegInf;
       rowbuf[((L - 1) & 1) * stride + u] = nx;          // beta~[t] + logp[t]: what row t-1 sums over
       vlast = nx;
       if (threadIdx.x == 0) *poffs = 0.0;
@@ -388,20 +408,21 @@ ctc_lattice1_kernel(const float* __restrict__ logits, const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < D; ++i) em[i] = emission();
     __syncthreads();
+    // step t writes row t from row t+1; its shift comes from row t+3 (t <= L-4)
     auto step = [&](int t, float2 e) {
       const float* prev = rowbuf + ((t + 1) & 1) * stride;
       float* cur = rowbuf + (t & 1) * stride;
       const float b0 = prev[u], b1 = prev[u + 1], b2 = skip ? prev[u + 2] : kNegInf;
-      const float M = shift((t + 1) & 1, t <= L - 3);
+      const float M = shift(t <= L - 4);
       po -= Upad; poffs -= 1;
       if (threadIdx.x == 0) { O += (double)M; *poffs = O; }
       const bool inwin = (u >= U - 2 * (L - t)) && (u < U) && (u < 2 * (t + 1));
-      const float v = inwin ? lse3_fast(b0, b1, b2) - M : kNegInf;
-      if (u < U) *po = v;
-      const float nx = v + (e.x - e.y);                  // becomes the summand of row t-1
+      const float win = inwin ? 0.f : kNegInf;
+      const float s = l2se3(b0, b1, b2);
+      const float nx = s + (fmaf(e.x - e.y, kLog2e, -M) + win);      // becomes the summand of row t-1
       cur[u] = nx;
-      const float wm = warp_max_redux(vlast);            // maxima of row t+1: read by step t-1
-      if (lane == 0) wmax[(t & 1) * 32 + warp] = wm;
+      if (u < U) *po = s + (win - M);                                // beta~[t]
+      row_end(t & 1, (t + 1) & 1);                       // keys of row t+1 out, keys of row t+2 in (for step t-1)
       vlast = nx;
       __syncthreads();
     };
@@ -413,11 +434,15 @@ ctc_lattice1_kernel(const float* __restrict__ logits, const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < D; ++i) if (t - i >= 0) step(t - i, em[i]);
     // log p(z|x) = LSE_u(alpha[0,u] + beta[0,u]); alpha[0,u] = logp[0,l'u] for u in {0,1}; row 0 of this pass holds
-    // beta~[0,u] + logp[0,l'u] with offset O = Ob[0]
+    // beta~[0,u] + logp[0,l'u] with offset O = Ob[0], all in base-2 units
     if (threadIdx.x == 0) {
       const float* r0 = rowbuf;
-      const float lpz = (U > 1) ? lse2(r0[0], r0[1]) : r0[0];
-      const double logp = (lpz == kNegInf) ? -INFINITY : (double)lpz + O;
+      const float m = (U > 1) ? fmaxf(r0[0], r0[1]) : r0[0];
+      double logp = -INFINITY;
+      if (m != kNegInf) {
+        const float lpz = (U > 1) ? m + log2f(exp2f(r0[0] - m) + exp2f(r0[1] - m)) : m;
+        logp = ((double)lpz + O) * kLn2;
+      }
       logp_out[b] = logp;
       loss[b] = (float)(-logp);   // +inf when no valid path
     }
@@ -430,7 +455,7 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logits, const float* _
                                 const int* __restrict__ len, int T, int B, int C, int Upad, int blank,
                                 const float* __restrict__ alpha, const float* __restrict__ beta,
                                 const double* __restrict__ offs_a, const double* __restrict__ offs_b,
-                                const double* __restrict__ logp_in, float* __restrict__ grad) {
+                                const double* __restrict__ logp_in, int log2_domain, float* __restrict__ grad) {
   extern __shared__ float acc_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -450,7 +475,8 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logits, const float* _
     return;
   }
   // alpha + beta - log p = alpha~ + beta~ + shift, the scalar part evaluated in double
-  const float shift = (float)(offs_a[(size_t)b * T + t] + offs_b[(size_t)b * T + t] - logp);
+  // (rows and offsets written by ctc_lattice1_kernel are in base-2 units, log p is always natural)
+  const float shift = (float)(offs_a[(size_t)b * T + t] + offs_b[(size_t)b * T + t] - (log2_domain ? logp * 1.4426950408889634 : logp));
   float* acc = acc_all + warp * C;
   for (int k = lane; k < C; k += 32) acc[k] = 0.f;
   __syncwarp();
@@ -461,7 +487,7 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logits, const float* _
   float blank_sum = 0.f;
   for (int u = lane; u < U; u += 32) {
     const float ab = a[u] + be[u];
-    const float w = (ab == kNegInf) ? 0.f : expf(ab + shift);
+    const float w = (ab == kNegInf) ? 0.f : (log2_domain ? exp2f(ab + shift) : expf(ab + shift));
     if (u & 1) {
       const int l = lab[u >> 1];
       atomicAdd(&acc[l], w);
@@ -580,7 +606,8 @@ extern "C" int rs_ctc_loss_grad(const float* logits_d, const int32_t* labels_d,
   RS_REQUIRE(smem <= 200 * 1024, RS_ERR_UNSUPPORTED, "rs_ctc_loss_grad: label length %d too large", max_label_len);
   // one state per thread when every lattice row fits a block (RS_CTC_LATTICE=0: the general kernel)
   static const bool one_env = [] { const char* v = getenv("RS_CTC_LATTICE"); return !(v && v[0] == '0'); }();
-  if (one_env && (int)align_up((size_t)U, 32) <= 1024) {
+  const bool one = one_env && (int)align_up((size_t)U, 32) <= 1024;
+  if (one) {
     const size_t smem1 = 2 * (size_t)(upad + 2) * sizeof(float) + 64 * sizeof(float) + 16;
     auto k = threads <= 256 ? ctc_lattice1_kernel<256> : ctc_lattice1_kernel<1024>;
     k<<<dim3(B, 2), threads, smem1, st>>>(logits_d, lse, labels_d, label_offsets_d, len_d, T, B, C, upad, blank,
@@ -598,7 +625,7 @@ extern "C" int rs_ctc_loss_grad(const float* logits_d, const int32_t* labels_d,
     size_t gsmem = (size_t)warps * C * sizeof(float);
     RS_REQUIRE(gsmem <= 48 * 1024, RS_ERR_UNSUPPORTED, "rs_ctc_loss_grad: C=%d too large", C);
     ctc_grad_kernel<<<cdiv(rows, warps), warps * 32, gsmem, st>>>(logits_d, lse, labels_d, label_offsets_d, len_d,
-                                                                  T, B, C, upad, blank, alpha, beta, offs_a, offs_b, logp, grad_d);
+                                                                  T, B, C, upad, blank, alpha, beta, offs_a, offs_b, logp, one ? 1 : 0, grad_d);
     RS_CHECK_LAUNCH();
   }
   return RS_OK;

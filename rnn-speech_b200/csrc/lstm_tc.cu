@@ -368,6 +368,12 @@ Sched make_sched(const rs_am* am, int T, bool forward) {
     static const int side_env = [] { const char* v = getenv("RS_TC_SIDE_CTAS"); return v ? atoi(v) : 0; }();
     const int sp = spare > 24 ? spare : 24;
     s.gemm_ctas = dx_env > 0 ? dx_env : (sp * 5 / 16 > 8 ? sp * 5 / 16 : 8);
+    // With layer 0's product off the critical stream (RS_TC_DX0_SIDE, the default) the dx GEMMs that remain on it are
+    // all on the path between two recurrent launches: they may take every SM one recurrent launch leaves, ahead of
+    // the weight-gradient CTAs (their stream has the higher priority).  Measured at cfg-2 (profiles/r02c_sweep3/4.log):
+    // 14.62 / 14.56 / 14.49 / 14.44 / 14.27 / 14.29 / 14.11 ms per step with 16 / 24 / 32 / 44 / 52 / 72 / 100 CTAs.
+    static const bool dx0_side = [] { const char* v = getenv("RS_TC_DX0_SIDE"); return !(v && v[0] == '0'); }();
+    if (!forward && dx_env <= 0 && dx0_side && !s.phases && sm_count() - am->tc.nslice > s.gemm_ctas) s.gemm_ctas = sm_count() - am->tc.nslice;
     s.side_ctas = side_env > 0 ? side_env : (sp - 4 > 8 ? sp - 4 : 8);
     s.fwd_gemm_ctas = sp;
     static const int side_tpc = [] { const char* v = getenv("RS_TC_SIDE_TPC"); return v ? atoi(v) : 0; }();

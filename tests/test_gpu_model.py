@@ -99,11 +99,14 @@ def test_cfg1_golden_forward_backward(pkg, cuda):
 @pytest.mark.parametrize("L,H,F,C,B,T,ki,ko", [
     (2, 50, 20, 50, 3, 17, 1.0, 1.0),       # odd sizes (reference's own test model: L2 H50 C50)
     (2, 64, 120, 80, 5, 33, 0.8, 0.5),      # dropout on both sides of every cell
-    (3, 128, 120, 80, 40, 12, 1.0, 1.0),    # batch > 32 (two batch chunks)
+    (3, 128, 120, 80, 40, 12, 1.0, 1.0),    # batch > 32 in one launch (two batch chunks; tile size 64)
     (2, 256, 120, 80, 21, 45, 0.8, 0.5),    # two chains per CTA, the second with 5 of 16 rows; self-validating exchange
     (1, 512, 40, 30, 32, 40, 1.0, 0.7),     # the same kernel at another hidden size
 ])
-def test_random_models_with_state_and_dropout(pkg, cuda, L, H, F, C, B, T, ki, ko):
+def test_random_models_with_state_and_dropout(pkg, cuda, monkeypatch, L, H, F, C, B, T, ki, ko):
+    import sys
+    # (batches of 33..64 rows are one launch of the recurrent kernels when the batch-tile size allows it)
+    monkeypatch.setattr(sys.modules[pkg.__name__ + ".acoustic_model"], "TC_MAX_BATCH", 64)
     rng = np.random.default_rng(L * 1000 + H)
     p = model.init_params(L, H, F, C, seed=1, dtype=np.float64)
     for k in p:
@@ -309,7 +312,7 @@ def test_cfg4_shape_wavefront_against_oracle(pkg, cuda, monkeypatch):
 
 
 def test_batch_tiles_training_against_oracle(pkg, cuda):
-    """A mini-batch above the tensor-core kernels' 64 utterances runs as batch tiles (64 + 36 here) that share
+    """A mini-batch above the batch-tile size (32 utterances: 32 + 32 + 32 + 4 here) runs as batch tiles that share
     parameters, gradients and workspace: logits, carried state and the accumulated gradient against the oracle."""
     L, H, F, C, B, T = 2, 128, 40, 30, 100, 19
     rng = np.random.default_rng(9)
@@ -320,7 +323,7 @@ def test_batch_tiles_training_against_oracle(pkg, cuda):
     lens[0] = T
     state = [(rng.standard_normal((B, H)) * .3, rng.standard_normal((B, H)) * .3) for _ in range(L)]
     m = _build(pkg, cuda, L, H, F, C, B, T, flat, training=True)
-    assert m.uses_tensor_cores and m._tiles is not None and len(m._tiles) == 2
+    assert m.uses_tensor_cores and m._tiles is not None and len(m._tiles) == 4
     m.rnn_state.copy_(_dev(np.stack([np.stack([c, h]) for c, h in state]), cuda, np.float32))
     xd, ld = _dev(x, cuda, np.float32), _dev(lens, cuda, np.int32)
     logits = m.forward(xd, ld, training=True)
@@ -338,7 +341,7 @@ def test_batch_tiles_training_against_oracle(pkg, cuda):
 
 def test_cfg5_shape_inference_greedy_labels(pkg, cuda):
     """BASELINE config 5 (forward only, batch 256, 3x768) at a frame count the float64 oracle finishes in seconds:
-    four batch tiles through the tensor-core path; logits and greedy label ids (process_input) against the oracle."""
+    eight batch tiles through the tensor-core path; logits and greedy label ids (process_input) against the oracle."""
     L, H, F, C, B, T = 3, 768, 120, 80, 256, 20
     rng = np.random.default_rng(55)
     p = model.init_params(L, H, F, C, seed=8, dtype=np.float64)
@@ -346,7 +349,7 @@ def test_cfg5_shape_inference_greedy_labels(pkg, cuda):
     x = rng.standard_normal((T, B, F)).astype(np.float32)
     lens = rng.integers(T // 2, T + 1, size=B).astype(np.int32)
     m = _build(pkg, cuda, L, H, F, C, B, T, flat, training=False)
-    assert m.uses_tensor_cores and len(m._tiles) == 4
+    assert m.uses_tensor_cores and len(m._tiles) == 8
     logits = m.forward(_dev(x, cuda, np.float32), _dev(lens, cuda, np.int32), training=False, keep_state=False)
     want, _, _ = model.forward(p, x.astype(np.float64), lens, L, H, keep_cache=False)
     got = logits.cpu().numpy()
@@ -483,7 +486,7 @@ def test_batch_normalization_against_oracle(pkg, cuda, L, H, F, C, B, T, ki):
 def test_infer_signals_matches_oracle_pipeline(pkg, cuda):
     """The batched inference path of bench.py --config cfg5 / stt.py --evaluate (AcousticModel.infer_signals: host PCM
     -> one staged copy -> feature kernels -> forward per batch tile -> greedy decode -> ids on the host), 70 clips =
-    tiles of 64 + 6, against the oracle's features + forward + greedy decode."""
+    tiles of 32 + 32 + 6, against the oracle's features + forward + greedy decode."""
     from oracle import features
     L, H, F, C, B, sr = 2, 128, 120, 80, 70, 16000
     rng = np.random.default_rng(70)
@@ -493,7 +496,7 @@ def test_infer_signals_matches_oracle_pipeline(pkg, cuda):
     Tmax = 100
     ap = pkg.AudioProcessor(Tmax, "fbank", device=cuda)
     m = _build(pkg, cuda, L, H, F, C, B, Tmax, flat, training=False)
-    assert m.uses_tensor_cores and len(m._tiles) == 2
+    assert m.uses_tensor_cores and len(m._tiles) == 3
     ids, n = m.infer_signals(ap, sigs, sr)
     feats = [features.fbank(s, sr, Tmax) for s in sigs]
     lens = np.array([min(k, Tmax) for _, k in feats])
