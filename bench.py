@@ -533,8 +533,8 @@ def run_train(args, name):
         return d
     fwd_fl = fwd_flops_per_frame(c) * Tm * c["B"]           # padded frames are computed too (dynamic_rnn semantics)
     roofline["families"] = {
-        "fbank (fbank_logmel_kernel + fbank_delta_kernel)": fam(fb_ms, 4.0 * n_samples + 4.0 * frames * c["F"]),
-        "ctc (ctc_lse/lattice/grad kernels)": fam(fam_ms.get("ctc", float("nan")), 2.0 * Tm * c["B"] * c["C"] * 4),
+        "fbank (fbank_logmel2_kernel + fbank_delta_kernel)": fam(fb_ms, 4.0 * n_samples + 4.0 * frames * c["F"]),
+        "ctc (ctc_lse / ctc_lattice1 / ctc_grad kernels)": fam(fam_ms.get("ctc", float("nan")), 2.0 * Tm * c["B"] * c["C"] * 4),
         "clip_adam (sumsq_kernel + clip_adam_kernel)": fam(fam_ms.get("clip_adam", float("nan")), 32.0 * P),
         "lstm_stack_forward (gemm_tc + rec_ts_fwd)": fam(fam_ms.get("forward", float("nan")), flops=fwd_fl),
         "lstm_stack_backward (gemm_tc + rec_ts_bwd)": fam(fam_ms.get("backward", float("nan")), flops=2.0 * fwd_fl),
@@ -549,8 +549,9 @@ def run_train(args, name):
         "config": {"workload": c["workload"], "global_batch": c["B"] * world, "parallelism": "dp%d" % world,
                    "arithmetic": arithmetic_note(tc),
                    "schedule": "time chunks (forward 96 steps: the layers of a wave side by side, chunk GEMMs as bursts between "
-                               "waves; backward %s steps: 2 recurrent launches in flight, chunk and weight-gradient GEMMs on the "
-                               "remaining SMs)" % os.environ.get("RS_TC_CHUNK", "128"),
+                               "waves, layer 0's input GEMMs of later chunks beside the first waves; backward %s steps: 2 "
+                               "recurrent launches in flight, the dx GEMMs between layers ahead of the weight-gradient GEMMs "
+                               "on the remaining SMs)" % os.environ.get("RS_TC_CHUNK", "128"),
                    "l2": "per-step working set (activations > 2 GB, parameters x4) exceeds the 126 MB L2; no flush needed",
                    "train_tflop_per_step": 3.0 * fwd_fl * world / 1e12,
                    "audio_seconds_per_step": audio_seconds * world},

@@ -327,6 +327,12 @@ Sched make_sched(const rs_am* am, int T, bool forward) {
   int chunk = am->chunk;
   if (forward && chunk > 0 && chunk_fwd_env > 0) chunk = chunk_fwd_env;
   else if (forward && want_phase && am->chunk_is_default) chunk = 96;
+  // backward with ONE launch in flight (see the window rule below): no wavefront to fill, so longer chunks -- fewer
+  // launches, larger GEMMs (cfg-4: 45.3 / 44.2 / 44.3 ms per batch with 128 / 256 / 512 steps, profiles/r02c_sweep8.log)
+  static const int wb_env0 = [] { const char* v = getenv("RS_TC_WINDOW_BWD"); return v ? atoi(v) : 0; }();
+  const bool bwd_single = !forward && am->tc.ts && am->tc.nslice > 0 &&
+                          (wb_env0 > 0 ? wb_env0 == 1 : (am->window > 1 && sm_count() - am->window * am->tc.nslice < 32));
+  if (bwd_single && chunk > 0 && am->chunk_is_default) chunk = 256;
   int Tc = (chunk + 7) / 8 * 8;                        // chunk starts stay 16-byte aligned in the transposed planes
   s.Tc = (am->tc.ts && chunk > 0 && Tc < T) ? Tc : T;
   // Chunk boundaries: uniform.  (While the wavefront fills and drains fewer launches are runnable than lanes, for as
@@ -356,6 +362,17 @@ Sched make_sched(const rs_am* am, int T, bool forward) {
   s.NC = (int)s.start.size() - 1;
   s.phases = (want_phase && s.NC > 1) ? 1 : 0;
   s.window = am->window;
+  if (!forward) {
+    // Two BACKWARD launches that share the machine slow each other down -- they are the launches with clusters and a
+    // reduce-scatter through distributed shared memory, and their clusters end up side by side in the GPCs: at cfg-2
+    // (48 CTAs each) a step takes 4.9 us instead of 3.1, which two launches in flight still win; at cfg-4 (64 CTAs
+    // each) 9.4 us instead of 4.8, which wins nothing and leaves the GEMMs 20 SMs (tests/gpu_diag.py trace with
+    // RS_TRACE_CFG=4, profiles/r02c_trace_cfg4_run7.txt).  Forward launches (no clusters) do not show this.  So
+    // backward keeps one launch in flight when two would leave fewer than 32 SMs; RS_TC_WINDOW_BWD overrides.
+    static const int wb_env = [] { const char* v = getenv("RS_TC_WINDOW_BWD"); return v ? atoi(v) : 0; }();
+    if (wb_env > 0) s.window = wb_env;
+    else if (s.window > 1 && am->tc.nslice > 0 && sm_count() - s.window * am->tc.nslice < 32) s.window = 1;
+  }
   if (am->tc.nslice > 0 && s.window > sm_count() / am->tc.nslice) s.window = sm_count() / am->tc.nslice;
   if (s.window < 1) s.window = 1;
   const int spare = sm_count() - (s.NC > 1 ? s.window : 1) * am->tc.nslice;

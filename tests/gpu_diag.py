@@ -380,11 +380,13 @@ def trace_diag():
     """cfg-2 training step: where the recurrent launches of the pipelined schedule sit in time (CUDA events on the
     launching streams, ms after the top of the forward / backward call) and how long each phase of the step takes."""
     L, H, F, C, B, T = 3, 768, 120, 80, 32, 998
+    if os.environ.get("RS_TRACE_CFG") == "4":            # BASELINE config 4's model and batch, an 11 s batch
+        L, H, B, T = 5, 1024, 16, 1096
     rng = np.random.default_rng(0)
     x = torch.from_numpy(rng.standard_normal((T, B, F)).astype(np.float32)).to(dev)
     lens = torch.full((B,), T, dtype=torch.int32, device=dev)
     labs = [np.append(rng.integers(1, 79, size=rng.integers(60, 121)), 79).astype(np.int32) for _ in range(B)]
-    m = rs.AcousticModel(L, H, B, 1000, 600, F, False, C, device=dev)
+    m = rs.AcousticModel(L, H, B, max(T, 1000), 600, F, False, C, device=dev)
     m.create_training_rnn(0.8, 0.5, 1, 3e-4, 0.33)
     m.initialize(None)
     m.enable_timing()
