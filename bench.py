@@ -331,7 +331,8 @@ def recurrent_roofline(h, m, c, T, step_ms, directions, traffic):
     trace = m.recurrent_trace()
     chunk = int(os.environ.get("RS_TC_CHUNK", "128"))
     tensor_peak, peak_src = h.tensor_peak()
-    B = min(c["B"], 64)
+    import rnn_speech_b200.acoustic_model as _am
+    B = c["B"] if c["B"] <= _am.TC_MAX_BATCH else _am.TC_MAX_BATCH          # rows per recurrent launch (batch tiles above that)
     durs = [b - a for d in directions for l in trace[d] for (a, b) in l]
     n_launches = max(1, len(durs))
     steps_per_launch = T * float(len(directions)) * c["L"] / n_launches
@@ -342,8 +343,10 @@ def recurrent_roofline(h, m, c, T, step_ms, directions, traffic):
     rec_busy = sum(busy([iv for l in trace[d] for iv in l]) for d in directions)
     tc = bool(m.uses_tensor_cores)
     # batches of 17..32 run as two 16-row chains per CTA with the validated exchange (lstm_rec_ts.cu dispatch)
+    # (forward also takes batches of at most 16 rows, as one chain)
     two = 16 < B <= 32 and os.environ.get("RS_TS_XCHG", "1") != "0"
-    names = " / ".join([("rec_ts_fwd3_kernel" if two else "rec_ts_fwd_kernel"),
+    fwd3 = two or (B <= 16 and os.environ.get("RS_TS_XCHG", "1") != "0" and os.environ.get("RS_TS_XCHG16", "1") != "0")
+    names = " / ".join([("rec_ts_fwd3_kernel" if fwd3 else "rec_ts_fwd_kernel"),
                         ("rec_ts_bwd4_kernel" if two and os.environ.get("RS_TS_CHAINS_BWD", "1") != "0" else "rec_ts_bwd_kernel")][d]
                        for d in directions)
     return {"kernel": ("%s (persistent tcgen05 recurrent kernels, weights resident in tensor memory%s; %d launches per layer per "
@@ -655,7 +658,7 @@ def run_infer(args, name):
                 "h2d_bytes_per_step": int(4 * n * c["B"] + 8 * (c["B"] + 1)),
                 "d2h_bytes_per_step": int(ids.nbytes + lens.nbytes),
                 "note": "AcousticModel.infer_signals: host PCM -> pinned staging -> ONE H2D copy -> feature kernels -> forward "
-                        "(batch tiles of 64) -> greedy decode -> decoded ids and lengths copied to the host; latency is "
+                        "(batch tiles of 32) -> greedy decode -> decoded ids and lengths copied to the host; latency is "
                         "wall clock per batch of 256 clips"},
         "gpu_launches": int(launches),
         "clocks": clocks,

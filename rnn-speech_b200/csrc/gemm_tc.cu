@@ -228,6 +228,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
         } else {
+          if (o.drop_thr != 0u && o.drop_thr != 0xffffffffu) {
+            const uint64_t e0 = (uint64_t)m * (uint64_t)p.N + (uint64_t)nb;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = dropout_keep(o.drop_key, o.drop_stream, e0 + i, o.drop_thr) ? v[i] * o.drop_inv : 0.f;
+          }
           __nv_bfloat16* hp = o.Chi + (size_t)m * o.ldc + nb;
           __nv_bfloat16* lp = o.Clo + (size_t)m * o.ldc + nb;
           if (nb + 15 < p.N && ((reinterpret_cast<uintptr_t>(hp) & 15) == 0)) {

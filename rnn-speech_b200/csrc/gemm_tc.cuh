@@ -40,6 +40,11 @@ struct GemmTcOut {
   int coresident;          // 1: the 129 KB / 256-TMEM-column variant that shares SMs with the backward recurrent CTAs
   int tiles_per_cta;       // > 0: grid = ceil(tiles / tiles_per_cta) short-lived CTAs instead of a persistent grid, so
                            // that the block scheduler can place them wherever (and whenever) SMs are free
+  // GEMM_OUT_SPLIT only: dropout of the result before the split (common.cuh dropout_keep; element index m*N + n).
+  // drop_thr = 0 (a zero-initialised struct) or 0xffffffff: no dropout
+  uint64_t drop_key;
+  uint32_t drop_stream, drop_thr;
+  float drop_inv;
 };
 
 // C[M,N] = A[M,K] * B[N,K]^T, both operands K-major (row-major with K contiguous).

@@ -472,9 +472,12 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
       RC(split_rows(bf.bn_xhat, TB, H, H, bf.xin_hi[0], bf.xin_lo[0], H, st));
     } else {
       o.mode = GEMM_OUT_SPLIT; o.Chi = bf.xin_hi[0]; o.Clo = bf.xin_lo[0]; o.ldc = H; o.bias = params_d + am->off_input_b;
+      // the input dropout of layer 0 (stream 0, element (t*B + b)*H + h) in the GEMM's epilogue
+      if (drop_in && fuse_dropout()) { o.drop_key = splitmix64(seed); o.drop_stream = 0; o.drop_thr = thr24(keep_in); o.drop_inv = 1.0f / keep_in; }
       RC(gemm_tc_nt(A, Bm, TB, H, K6, 1, o, st));
+      if (drop_in && !fuse_dropout()) RC(dropout_planes(bf.xin_hi[0], bf.xin_lo[0], H, H, bf.xin_hi[0], bf.xin_lo[0], nTBH, 0, seed, 0, keep_in, -1, 1.f, st));
     }
-    if (drop_in) RC(dropout_planes(bf.xin_hi[0], bf.xin_lo[0], H, H, bf.xin_hi[0], bf.xin_lo[0], nTBH, 0, seed, 0, keep_in, -1, 1.f, st));
+    if (drop_in && am->normalization) RC(dropout_planes(bf.xin_hi[0], bf.xin_lo[0], H, H, bf.xin_hi[0], bf.xin_lo[0], nTBH, 0, seed, 0, keep_in, -1, 1.f, st));
   }
   const int hld = am->tc.ts ? 2 * H : H;            // row stride of the h planes
   // carried-in h -> slot 0 of every layer's h planes
