@@ -341,6 +341,9 @@ def recurrent_roofline(h, m, c, T, step_ms, directions, traffic):
     achieved = rec_flops_launch / (rec_ms / 1e3) / 1e12
     n_launch = [len(x) for d in directions for x in trace[d]]
     rec_busy = sum(busy([iv for l in trace[d] for iv in l]) for d in directions)
+    # a mini-batch above the batch-tile size runs tile after tile: the trace is the last tile's
+    n_tiles = len(m._tiles) if getattr(m, "_tiles", None) else 1
+    rec_busy *= n_tiles
     tc = bool(m.uses_tensor_cores)
     # batches of 17..32 run as two 16-row chains per CTA with the validated exchange (lstm_rec_ts.cu dispatch)
     # (forward also takes batches of at most 16 rows, as one chain)
@@ -359,7 +362,7 @@ def recurrent_roofline(h, m, c, T, step_ms, directions, traffic):
             "steps_per_launch": steps_per_launch,
             "launch_ms": {"fwd": rec_f, "bwd": rec_b}, "launches_per_layer": max(n_launch),
             "sum_launch_ms": sum(rec_f) + (sum(rec_b) if 1 in directions else 0.0),
-            "share_of_step": rec_busy / step_ms,
+            "share_of_step": rec_busy / step_ms, "batch_tiles": n_tiles,
             "note": "algorithmic flops = 2*B*H*4H per recurrent step and layer (the bf16x3 products issue 3x that on the tensor "
                     "pipe).  The recurrence is a chain of T dependent steps with a grid-wide exchange of h per step: "
                     "latency-bound, not tensor-bound (DESIGN.md 'Recurrent step budget'); launch_ms sums a layer's chunk "
