@@ -442,9 +442,22 @@ def run_train(args, name):
         ev.record()
     issue_features(0, res[0])
 
+    diag_h2d = int(os.environ.get("RS_DIAG_H2D", "0"))       # diagnostic: a 20 MB pinned H2D copy per resident step
+    if diag_h2d:
+        dg_host = torch.empty(5 << 20, dtype=torch.float32).pin_memory()
+        dg_dev = torch.empty(5 << 20, dtype=torch.float32, device=dev)
+        dg_stream = torch.cuda.Stream(device=dev, priority=0)
+        dg_ev = torch.cuda.Event()
+
     def step_resident():
         slot, i = state["slot"], state["i"]
         r = res[i % NB]
+        if diag_h2d:
+            if diag_h2d == 2:                                  # placed: behind the previous step's optimizer
+                dg_ev.record()
+                dg_stream.wait_event(dg_ev)
+            with torch.cuda.stream(dg_stream):
+                dg_dev.copy_(dg_host, non_blocking=True)
         issue_features(1 - slot, res[(i + 1) % NB])       # next step's features, concurrent with this step
         torch.cuda.current_stream().wait_event(ready[slot])
         m.start_batch(None, True)
@@ -458,8 +471,10 @@ def run_train(args, name):
         state["slot"], state["i"] = 1 - slot, i + 1
 
     prefetch = rs.BatchPrefetcher(ap)
+    gate_features = os.environ.get("RS_PREFETCH_GATE", "1") != "0"
     pending = [prefetch.submit(res[0]["sigs"], c["sr"], time_major=True)]
     e2e_i = [0]
+    diag_e2e, diag_keep = os.environ.get("RS_DIAG_E2E", ""), []
 
     def step_e2e():
         # public API with HOST buffers.  Every step stages, copies (pinned, ONE H2D) and featurises ONE mini-batch --
@@ -467,10 +482,24 @@ def run_train(args, name):
         # the one submitted a step earlier, and reads the mean loss back.
         i = e2e_i[0]
         r = res[i % NB]
+        if diag_e2e:
+            # diagnostic: no input pipeline at all (the features of the first ticket again and again); "c": no read either
+            if not diag_keep:
+                diag_keep.extend(pending[0].result())
+            m.start_batch(None, True)
+            m.step_on_batch(diag_keep[0], diag_keep[1], r["labs"], compute_gradients=True, compute_error_rate=False)
+            if diag_e2e == "c":
+                m.apply_gradients()
+                return 0.0
+            return float(m.end_batch(None, True, rnn_state_reset_ratio=1.0 if diag_e2e != "d" else 1e-9)[0])
         f, nf = pending[0].result()
-        pending[0] = prefetch.submit(res[(i + 1) % NB]["sigs"], c["sr"], time_major=True)
+        # (the worker stages and copies at once; the feature kernels are enqueued in front of this step's forward pass,
+        #  beside its head: RS_PREFETCH_GATE=0 leaves them to the worker thread, i.e. to wherever the device happens to be)
+        nxt = pending[0] = prefetch.submit(res[(i + 1) % NB]["sigs"], c["sr"], time_major=True, defer_features=gate_features)
         m.start_batch(None, True)
         x = f if r["T"] == c["Tmax"] or NB == 1 else f[:r["T"]]
+        if gate_features:
+            nxt.launch_features()
         m.step_on_batch(x, nf, r["labs"], compute_gradients=True, compute_error_rate=False)
         mean_loss, _, _ = m.end_batch(None, True, rnn_state_reset_ratio=1.0)
         e2e_i[0] = i + 1
@@ -499,6 +528,23 @@ def run_train(args, name):
         step_e2e()
     ms_e2e, _ = h.timed(step_e2e, args.steps)
 
+    if os.environ.get("RS_BENCH_E2E_PHASES"):
+        # diagnostic: the phases of the END-TO-END step and the gap between two steps (stderr)
+        seq = []
+        for _ in range(6):
+            m._phase_events = []
+            step_e2e()
+            seq.append(m._phase_events)
+        torch.cuda.synchronize()
+        m._phase_events = None
+        ph = {}
+        for ev in seq[1:]:
+            for (na, ea), (_, eb) in zip(ev[:-1], ev[1:]):
+                ph.setdefault(na, []).append(ea.elapsed_time(eb))
+        gaps = [a[-1][1].elapsed_time(b[0][1]) for a, b in zip(seq[1:-1], seq[2:])]
+        sys.stderr.write("e2e phases (ms): %s; end -> next forward %.3f; step (forward mark to forward mark) %.3f\n" % (
+            ", ".join("%s %.3f" % (k, float(np.median(v))) for k, v in ph.items()), float(np.median(gaps)),
+            float(np.median([a[0][1].elapsed_time(b[0][1]) for a, b in zip(seq[1:-1], seq[2:])]))))
     # ---- per-family rooflines: phases of a step from CUDA events on the launching stream (every rank runs the steps:
     # the all-reduce is a collective), features alone on their stream
     fam_ms = {}

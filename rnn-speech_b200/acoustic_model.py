@@ -118,6 +118,8 @@ class AcousticModel(object):
         self._mini_batches = 0           # host copy of the mini-batch counter (models/AcousticModel.py:378-380)
         self._err_stream = None          # side stream of the prediction + edit-distance ops
         self._err_event = None
+        self._acc_event, self._acc_recorded = None, False         # end_batch's early read of the accumulators
+        self._read_stream = self._acc_host = self._read_done = None
         self._dataset_empty = False
 
     # ------------------------------------------------------------ construction
@@ -537,13 +539,19 @@ class AcousticModel(object):
             self._accumulate_error_rate_async(logits, len_d, label_rows)
         self._phase_mark("ctc")
         loss, grad = self.ctc_loss(logits, label_rows, len_d, want_grad=compute_gradients)
+        self._phase_mark("bookkeeping")
+        # display loss: mean(loss[b] / len[b]), and the mini-batch counter        (models/AcousticModel.py:361-383).
+        # In FRONT of the backward pass: the accumulators are final once the CTC kernel has run, and end_batch reads
+        # them from a side stream behind this event while the backward pass is still running.
+        _lib.call("rs_accumulate_mean", loss.data_ptr(), len_d.data_ptr(), int(loss.numel()), self._acc.data_ptr(),
+                  self._acc.data_ptr() + 8, _stream_ptr())
+        if self._acc_event is None:
+            self._acc_event = torch.cuda.Event()
+        self._acc_event.record(torch.cuda.current_stream(self.device))
+        self._acc_recorded = True
         self._phase_mark("backward")
         if compute_gradients:
             self.backward(x_d, len_d, grad)
-        self._phase_mark("bookkeeping")
-        # display loss: mean(loss[b] / len[b]), and the mini-batch counter        (models/AcousticModel.py:361-383)
-        _lib.call("rs_accumulate_mean", loss.data_ptr(), len_d.data_ptr(), int(loss.numel()), self._acc.data_ptr(),
-                  self._acc.data_ptr() + 8, _stream_ptr())
         self._mini_batches += 1
         return loss
 
@@ -616,6 +624,10 @@ class AcousticModel(object):
         start_time = time.time()
         x_d, len_d, dense_labels = self._next_batch()
         rows = self.sparse_labels_from_dense(dense_labels, fill_empty=True)
+        # the NEXT mini-batch's feature kernels go in front of this forward pass (see BatchPrefetcher._Ticket.launch_features)
+        launch = getattr(self._train_dataset if self.is_training else self._valid_dataset, "launch_pending_features", None)
+        if launch is not None:
+            launch()
         self.step_on_batch(x_d, len_d, rows, compute_gradients, compute_error_rate)
         logging.debug("Step duration : %.2f", time.time() - start_time)
         return float(self._mini_batches)
@@ -627,14 +639,60 @@ class AcousticModel(object):
         decision -- apply the (all-reduced) gradient iff any rank accumulated a mini-batch -- and the collectives
         of all ranks stay in lockstep whatever the shard sizes."""
         cur = torch.cuda.current_stream(self.device)
-        if self._err_event is not None:
-            cur.wait_event(self._err_event)
-            self._err_event = None
-        if self._dataset_empty:
-            _lib.call("rs_accumulate_mean", self._one.data_ptr(), None, 1, self._acc.data_ptr() + 12, None, _stream_ptr())
-        acc = allreduce_sum_(self._acc).cpu().numpy()
-        batchs_count = float(acc[2])
-        self._ranks_empty = int(round(float(acc[3])))
+        n_ranks = dist_world()[1]
+        early = None
+        if os.environ.get("RS_EARLY_READ", "1") != "0" and (n_ranks == 1 or os.environ.get("RS_EARLY_READ_DP", "1") != "0"):
+            # The accumulators are final right behind the last CTC kernel (step_on_batch records an event there), long
+            # before the backward pass has finished.  Their all-reduce (data parallel) and their device-to-host copy run
+            # on a side stream behind that event (and the decoder's, if it ran); the optimizer is enqueued behind the
+            # backward pass meanwhile, and the call returns as soon as the copy has landed -- the backward pass and the
+            # optimizer still running, the caller already enqueueing its next step -- instead of draining the device.
+            # One process: the decision below needs nothing from the device (the mini-batch count is known here).
+            if self._read_stream is None:
+                self._read_stream = torch.cuda.Stream(device=self.device, priority=-1)
+                self._acc_host = torch.empty(4, dtype=torch.float32).pin_memory()
+                self._read_done = torch.cuda.Event()
+            if self._acc_event is None:
+                self._acc_event = torch.cuda.Event()
+            rd = self._read_stream
+            if not self._acc_recorded:
+                self._acc_event.record(cur)               # no mini-batch here: behind start_batch's clear
+            if n_ranks > 1 or self._mini_batches > 0:
+                rd.wait_event(self._acc_event)
+                if self._err_event is not None:
+                    rd.wait_event(self._err_event)
+                with torch.cuda.stream(rd):
+                    if n_ranks > 1:
+                        if self._dataset_empty:
+                            _lib.call("rs_accumulate_mean", self._one.data_ptr(), None, 1, self._acc.data_ptr() + 12, None,
+                                      _stream_ptr())
+                        allreduce_sum_(self._acc)
+                    self._acc_host.copy_(self._acc, non_blocking=True)
+                    self._read_done.record(rd)
+                early = self._read_done
+            if n_ranks == 1:
+                batchs_count = float(self._mini_batches)
+                self._ranks_empty = 1 if self._dataset_empty else 0
+            else:
+                early.synchronize()
+                acc = self._acc_host.numpy().copy()
+                batchs_count = float(acc[2])
+                self._ranks_empty = int(round(float(acc[3])))
+            if self._err_event is not None:
+                cur.wait_event(self._err_event)       # (the next start_batch clears the accumulators on this stream)
+                self._err_event = None
+            if early is not None:
+                cur.wait_event(early)
+        else:
+            if self._err_event is not None:
+                cur.wait_event(self._err_event)
+                self._err_event = None
+            if self._dataset_empty:
+                _lib.call("rs_accumulate_mean", self._one.data_ptr(), None, 1, self._acc.data_ptr() + 12, None, _stream_ptr())
+            acc = allreduce_sum_(self._acc).cpu().numpy()
+            batchs_count = float(acc[2])
+            self._ranks_empty = int(round(float(acc[3])))
+        self._acc_recorded = False
         if is_training and batchs_count > 0:
             self.apply_gradients()
             # Reset the hidden state at the given random ratio (default to always)   (:681-682)
@@ -642,6 +700,9 @@ class AcousticModel(object):
                 _lib.call("rs_memset_zero", self.rnn_state.data_ptr(), 4 * self.rnn_state.numel(), _stream_ptr())
         if batchs_count <= 0:
             return 0.0, 0.0, self.global_step
+        if early is not None:
+            early.synchronize()
+            acc = self._acc_host.numpy().copy()
         mean_loss = acc[0] / batchs_count
         mean_error_rate = acc[1] / batchs_count
         return mean_loss, mean_error_rate, self.global_step

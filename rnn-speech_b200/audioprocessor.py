@@ -11,6 +11,8 @@ Added (not in the reference): ``process_batch`` -- a whole batch of utterances i
 one launch, result left on the device, optionally time-major, which is what the
 training path consumes.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -229,11 +231,42 @@ class BatchPrefetcher(object):
     """
 
     class _Ticket(object):
-        def __init__(self, future):
+        def __init__(self, future, owner=None, deferred=None):
             self._future = future
+            self._owner = owner
+            self._deferred = deferred            # (sr, time_major): the feature kernels have not been enqueued yet
+            self._out = None
+
+        def launch_features(self):
+            """Deferred ticket: enqueue the feature kernels NOW, on the prefetcher's low-priority stream, behind the
+            host-to-device copy and behind whatever the calling stream holds at this moment.  The caller runs ahead of
+            the device, so kernels enqueued by the worker thread as soon as its copy is issued land wherever the device
+            happens to be -- measured at cfg-2 (profiles/r02d_e2e_phases.txt): in the middle of the previous step's
+            backward pass, whose recurrent launches they hold up (8.55 -> 9.18 ms).  Called right in front of a step's
+            forward pass they run beside its head (input dense, first chunk GEMM: most SMs idle) and cost nothing."""
+            if self._deferred is None or self._out is not None:
+                return
+            pcm_d, off_d, lens, h2d_ev = self._future.result()
+            own = self._owner
+            sr, time_major = self._deferred
+            cur = torch.cuda.current_stream(own.device)
+            gate = torch.cuda.Event()
+            gate.record(cur)
+            own.stream.wait_event(h2d_ev)
+            own.stream.wait_event(gate)
+            with torch.cuda.stream(own.stream):
+                feats, nframes = own.audio_processor.features_device(pcm_d, off_d, len(lens), max(lens), sr,
+                                                                     time_major=time_major)
+                ev = torch.cuda.Event()
+                ev.record(own.stream)
+            self._out = (feats, nframes, ev)
 
         def result(self):
-            feats, nframes, ev = self._future.result()
+            if self._deferred is not None:
+                self.launch_features()
+                feats, nframes, ev = self._out
+            else:
+                feats, nframes, ev = self._future.result()
             cur = torch.cuda.current_stream(feats.device)
             cur.wait_event(ev)
             feats.record_stream(cur)
@@ -255,6 +288,14 @@ class BatchPrefetcher(object):
             ev.record(self.stream)
         return feats, nframes, ev
 
+    def _work_stage(self, signals, sr):
+        torch.cuda.set_device(self.device)
+        with torch.cuda.stream(self.stream):
+            pcm_d, off_d, lens = self.audio_processor.stage_batch(signals, sr)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return pcm_d, off_d, lens, ev
+
     def _work_files(self, file_names, time_major):
         torch.cuda.set_device(self.device)
         with torch.cuda.stream(self.stream):
@@ -263,7 +304,11 @@ class BatchPrefetcher(object):
             ev.record(self.stream)
         return feats, nframes, ev
 
-    def submit(self, signals, sr, time_major=True):
+    def submit(self, signals, sr, time_major=True, defer_features=False):
+        """defer_features: the worker only stages and copies; the feature kernels are enqueued by
+        ticket.launch_features() (or by ticket.result(), whichever comes first)."""
+        if defer_features:
+            return BatchPrefetcher._Ticket(self._pool.submit(self._work_stage, signals, sr), self, (sr, time_major))
         return BatchPrefetcher._Ticket(self._pool.submit(self._work, signals, sr, time_major))
 
     def submit_files(self, file_names, time_major=True):

@@ -117,6 +117,11 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint
                : "memory");
 }
 
+// bulk copy of this CTA's shared memory into a peer's, completing transaction bytes on the peer's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t remote_addr, uint32_t local_addr, uint32_t bytes, uint32_t remote_mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(remote_addr), "r"(local_addr), "r"(bytes), "r"(remote_mbar) : "memory");
+}
 // plain 16-byte store into a peer CTA's shared memory (ordered by a later release at cluster scope)
 __device__ __forceinline__ void st_cluster_v4(uint32_t remote_addr, float4 v) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -1132,6 +1137,8 @@ struct KBwd {
   uint32_t tmem_cols;
   int fault;                               // STAMP instantiations of rec_ts_bwd3/4_kernel: delay half of every publish behind its hint
   int turns;                               // rec_ts_bwd4_kernel: the chains take turns at the TMA port
+  int bulk;                                // rec_ts_bwd4_kernel: the reduce-scatter pushes 1 KB bulk copies (one per half-warp and owner)
+                                           // out of a staging buffer instead of 16-byte st.async (RS_TS_PUSH_BULK)
 };
 
 // 128 registers (no spills; 168 unconstrained) x 320 threads and ~50 KB of shared memory: with RS_TC_CORES=1 a 256-thread
@@ -1837,6 +1844,8 @@ rec_ts_bwd4_kernel(const __grid_constant__ CUtensorMap tmG, KBwd p) {
   float* sR = reinterpret_cast<float*>(sAlo + (size_t)nlo_s * 16384);        // [2 chains][CL src][16 units][16] partial dh
   __nv_bfloat16* sDG = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(sR) + (size_t)2 * CL * TSU * CHB * 4);
                                                                              // [2 chains][2 planes][16][4 gates][16 units]
+  float* sPush = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sDG) + (size_t)2 * 2 * CHB * 4 * TSU * 2);
+                                                                             // [2 chains][CL owners][16 units][16] staged pushes (p.bulk)
   const uint32_t colLo = (uint32_t)(H / 4);              // Wh_hi: columns [0, H/4); Wh_lo: nlo_t blocks of 32 columns behind
   const uint32_t colD = colLo + (uint32_t)nlo_t * 32;    // accumulator of chain X: 32 columns at colD + 32 X
   const int t1 = a.t0 + T;                                // this launch: steps t1 - 1 down to t0
@@ -2026,9 +2035,23 @@ rec_ts_bwd4_kernel(const __grid_constant__ CUtensorMap tmG, KBwd p) {
           if (!stale) break;                                      // the model's own NaN
           if (ctid == 0) *reinterpret_cast<volatile uint32_t*>(&retry_req[X]) = *reinterpret_cast<volatile uint32_t*>(&retry_req[X]) + 1u;
         }
+        if (p.bulk) {
+          // Stage the half-warp's 16 units x 16 rows (1 KB, the layout of the owner's receive block) and send it as ONE
+          // bulk copy: 8 transactions of 1 KB per chain and step instead of 512 of 16 bytes.  (The staging block is
+          // rewritten a step later, after a tile that every CTA's publish precedes, each of which follows the completion
+          // of its receive -- this CTA's copies included.)
+          float* stg = sPush + (((size_t)X * CL + owner) * TSU + l16) * CHB;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          st_async_v4(push_base + (uint32_t)(4 * i) * 4u, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), push_bar);
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(stg + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          tc::fence_proxy_async_smem();
+          __syncwarp();
+          if (l16 == 0) bulk_copy_to_peer(push_base, tc::smem_u32(stg), (uint32_t)(TSU * CHB * 4), push_bar);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            st_async_v4(push_base + (uint32_t)(4 * i) * 4u, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), push_bar);
+        }
         if (ctid == 0) RS_STAMPB(t, 8 * X + 4, gtime());
         tc::mbar_wait(&recv_bar[X], (n - 1) & 1);
         if (ctid == 0) RS_STAMPB(t, 8 * X + 5, gtime());
@@ -2385,8 +2408,10 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
     static const int turns_env = [] { const char* v = getenv("RS_TS_TURNS_BWD"); return v ? atoi(v) : 1; }();
     p.turns = turns_env;
     // shared memory: two tiles, the Wh_lo blocks outside tensor memory, two receive buffers, two staged dgates tiles
+    static const int bulk_env = [] { const char* v = getenv("RS_TS_PUSH_BULK"); return v ? atoi(v) : 0; }();
+    p.bulk = bulk_env;
     size_t smem4 = (size_t)2 * p.nkbs * 2 * CHB * 128 + (size_t)nlo_s * 16384 + (size_t)2 * CL * TSU * CHB * 4 +
-                   (size_t)2 * 2 * CHB * 4 * TSU * 2 + 1024;
+                   (size_t)2 * 2 * CHB * 4 * TSU * 2 + (size_t)2 * CL * TSU * CHB * 4 + 1024;
     if (smem4 < 120 * 1024) smem4 = 120 * 1024;          // one CTA per SM
     const bool fast4 = g.H == 768 && nlo_t == p.nkbs;
     const int s4 = device_slot() * 4 + (a.dbg ? (fast4 ? 3 : 2) : fast4 ? 1 : 0);

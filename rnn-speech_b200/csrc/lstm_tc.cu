@@ -444,16 +444,41 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
 
   // weight planes: re-packed when the parameters may have changed (every call unless the caller versions them:
   // rs_am_set_params_version; 57 MB read, 8 launches at cfg-2)
+  RC(ensure_streams(am));
+  am->ev_next = 0;
   if (!planes_cached(am, 0, params_d, ws_d)) {
     split3_T_kernel<<<ew_grid((int64_t)H * Fp), 256, 0, st>>>(params_d + am->off_input_w, F, H, Fp, bf.wi6);   // w_i^T [H][6 Fp]
     RS_CHECK_LAUNCH();
-    RC(split_planes_transposed(params_d + am->off_output_w, H, C, C, bf.wo_hi, bf.wo_lo, H, st));      // w_o^T [C][H]
+    // The planes of the recurrent stack and of the output dense (2 L + 1 launches, ~14 us each, in a training step
+    // after every optimizer step) are packed on the chunk-GEMM stream, beside the input dense: every consumer --
+    // the chunk GEMMs on that stream, the recurrent launches behind their events, the output dense behind the last
+    // launches -- is downstream of it.  RS_TC_PACK_SIDE=0: on the caller's stream, in front of the input dense.
+    static const bool pack_side = [] { const char* v = getenv("RS_TC_PACK_SIDE"); return !(v && v[0] == '0'); }();
+    cudaStream_t ps = st;
+    if (pack_side) {
+      cudaEvent_t e_pre;
+      RC(ev_record(am, &e_pre, st));
+      RS_CHECK_CUDA(cudaStreamWaitEvent(am->gemm_st, e_pre, 0));
+      ps = am->gemm_st;
+    }
     for (int l = 0; l < L; ++l) {
       const float* K = params_d + am->off_kernel[l];
-      RC(pack_wrec(K, H, am->tc.U, bf.wx_hi[l], bf.wx_lo[l], st));                                     // K[:H]^T, rows in rec order
-      RC(pack_wrec(K + (size_t)H * 4 * H, H, am->tc.U, bf.wrec_hi[l], bf.wrec_lo[l], st));
+      RC(pack_wrec(K, H, am->tc.U, bf.wx_hi[l], bf.wx_lo[l], ps));                                     // K[:H]^T, rows in rec order
+      RC(pack_wrec(K + (size_t)H * 4 * H, H, am->tc.U, bf.wrec_hi[l], bf.wrec_lo[l], ps));
     }
+    RC(split_planes_transposed(params_d + am->off_output_w, H, C, C, bf.wo_hi, bf.wo_lo, H, ps));      // w_o^T [C][H]
     planes_packed(am, 0, params_d, ws_d);
+    if (training && pack_side && !planes_cached(am, 1, params_d, ws_d)) {
+      // the backward pass's planes (weights as stored) too: off the head of the backward pass, which finds them cached
+      const int Cp = up8(C);
+      RC(split_rows(params_d + am->off_output_w, H, C, C, bf.wos_hi, bf.wos_lo, Cp, ps));
+      for (int l = 0; l < L; ++l) {
+        const float* K = params_d + am->off_kernel[l];
+        RC(split_planes(K, bf.wxs_hi[l], bf.wxs_lo[l], (int64_t)H * 4 * H, ps));
+        RC(split_planes(K + (size_t)H * 4 * H, bf.whs_hi[l], bf.whs_lo[l], (int64_t)H * 4 * H, ps));
+      }
+      planes_packed(am, 1, params_d, ws_d);
+    }
   }
   // input dense -> xin[0] planes                                 (models/AcousticModel.py:247-250)
   split3_rows_kernel<<<ew_grid((int64_t)TB * Fp), 256, 0, st>>>(x_d, TB, F, F, Fp, bf.x6);
@@ -499,8 +524,6 @@ int am_tc_forward(rs_am* am, const float* params_d, const float* x_d, const int3
   // ---- the recurrent stack as a wavefront over (layer, time chunk)
   const Sched sc = make_sched(am, T, true);
   const int NC = sc.NC;
-  RC(ensure_streams(am));
-  am->ev_next = 0;
   cudaEvent_t e_fork;
   RC(ev_record(am, &e_fork, st));
   for (int l = 0; l < L; ++l) RS_CHECK_CUDA(cudaStreamWaitEvent(am->lane[l], e_fork, 0));
@@ -742,6 +765,11 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
       a.drop_sb = (uint32_t)(2 * (l + 1)); a.drop_thr_b = (!last && drop_in) ? thr24(keep_in) : 0xffffffffu; a.drop_inv_b = 1.0f / keep_in;
     }
     a.dbg = (l == 0 && NC == 1) ? am->dbg_bwd : nullptr;
+    {
+      // RS_TC_DBG_LC="layer,chunk": the in-kernel timeline of ONE launch of the pipelined schedule (tests/gpu_diag.py xchg2)
+      static const int dbg_lc = [] { const char* v = getenv("RS_TC_DBG_LC"); int dl = -1, dc = -1; if (v && sscanf(v, "%d,%d", &dl, &dc) == 2) return dl * 4096 + dc; return -1; }();
+      if (NC > 1 && dbg_lc >= 0 && l == dbg_lc / 4096 && c == dbg_lc % 4096) a.dbg = am->dbg_bwd;
+    }
     RC(tev_record(am, 1, l, ls));
     if (am->tc.ts) RC(lstm_rec_ts_backward(am->tc, a, ls));
     else RC(lstm_rec_tc_backward(bg, a, ls));

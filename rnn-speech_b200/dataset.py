@@ -55,7 +55,17 @@ class AudioBatchDataset(object):
                         else list(label))
         if len(set(srs)) != 1:
             raise ValueError("all utterances of a mini-batch must share one sample rate, got %s" % sorted(set(srs)))
-        return prefetcher.submit(sigs, srs[0], time_major=True), labs, len(sigs)
+        # (staged and copied by the worker at once; the feature kernels are enqueued by launch_pending_features --
+        #  AcousticModel.run_step calls it in front of its forward pass -- or by the next iteration, whichever comes first)
+        return prefetcher.submit(sigs, srs[0], time_major=True, defer_features=True), labs, len(sigs)
+
+    def launch_pending_features(self):
+        """Enqueue the feature kernels of the mini-batch the iterator has in flight (no-op when there is none, when
+        they are already enqueued, or when the batch comes from files: those are featurised by the worker)."""
+        ticket = getattr(self, "_pending_ticket", None)
+        launch = getattr(ticket, "launch_features", None)
+        if launch is not None:
+            launch()
 
     def __iter__(self):
         """The next mini-batch's features are computed on a side stream while the caller trains on the current one
@@ -68,6 +78,7 @@ class AudioBatchDataset(object):
         for i in range(len(starts)):
             ticket, labs, n_real = pending
             pending = self._submit(prefetcher, starts[i + 1]) if i + 1 < len(starts) else None
+            self._pending_ticket = pending[0] if pending is not None else None
             feats, nframes = ticket.result()
             if n_real < B:      # pad the batch (features 0, length 0)
                 full = torch.zeros((feats.shape[0], B, feats.shape[2]), dtype=feats.dtype, device=feats.device)

@@ -376,6 +376,51 @@ def xchg_diag():
     print("  ctaN - cta0 'published' (chain 0): mean %.0f ns, std %.0f" % ((d[T + 100:T + 900, 5] - d[100:900, 5]).mean(), (d[T + 100:T + 900, 5] - d[100:900, 5]).std()))
 
 
+def xchg2_diag():
+    """The backward two-chain kernel's in-kernel timeline INSIDE the pipelined schedule (cfg-2): one launch -- layer and chunk
+    from RS_TC_DBG_LC, default "1,3" -- records its stamps while the other layer's launch and the GEMMs run beside it."""
+    L, H, F, C, B, T = 3, 768, 120, 80, 32, 998
+    os.environ.setdefault("RS_TC_DBG_LC", "1,3")
+    rng = np.random.default_rng(0)
+    flat = model.flatten(model.init_params(L, H, F, C, seed=0), L, H, F, C)
+    x = rng.standard_normal((T, B, F)).astype(np.float32)
+    lens = np.full(B, T, np.int32)
+    m = rs.AcousticModel(L, H, B, 1000, 600, F, False, C, device=dev)
+    m.create_training_rnn(0.8, 0.5, 1, 3e-4, 0.33)
+    m.load_flat_params(flat)
+    m.enable_timing()
+    n = 128
+    dbg_f = torch.zeros((2 * T, 16), dtype=torch.int64, device=dev)
+    dbg_b = torch.zeros((2 * T, 16), dtype=torch.int64, device=dev)
+    rs._lib.call("rs_am_set_debug_timeline", m._handle, dbg_f.data_ptr(), dbg_b.data_ptr())
+    xd, ld = torch.from_numpy(x).to(dev), torch.from_numpy(lens).to(dev)
+    dl = torch.from_numpy((rng.standard_normal((T, B, C)) * 0.01).astype(np.float32)).to(dev)
+    for it in range(2):
+        m.rnn_state.zero_()
+        dbg_b.zero_()
+        m.forward(xd, ld, training=True, keep_state=False)
+        m.grads.zero_()
+        m.backward(xd, ld, dl)
+        torch.cuda.synchronize()
+    print("RS_TC_DBG_LC=%s RS_TC_WINDOW_BWD=%s: rec ms fwd/bwd %s" % (os.environ["RS_TC_DBG_LC"], os.environ.get("RS_TC_WINDOW_BWD", "default"), m.recurrent_ms()))
+    db = dbg_b.cpu().numpy().astype(np.int64)
+    for cta, base in (("cta0", 0), ("ctaN", n)):
+        eb = db[base + 8:base + n - 8, :][::-1]
+        if not eb[:, 0].all():
+            print("  bwd %s: no stamps" % cta)
+            continue
+        for X in range(2):
+            o = 8 * X
+            print("  bwd %s chain %d: step period %.0f ns" % (cta, X, np.diff(eb[:, o]).mean()))
+            dt = eb[:, o + 1] - eb[:, o]
+            print("      %-26s %5.0f ns after 'counter seen' (p95 %5.0f)" % ("fetch issued", dt.mean(), np.percentile(dt, 95)))
+            for k, nm in ((3, "MMAs done"), (4, "voted + partials pushed"), (5, "partials received"), (6, "cell math done"), (7, "published")):
+                dt = eb[1:, o + k] - eb[:-1, o]
+                print("      %-26s %5.0f ns after 'counter seen' (p95 %5.0f)" % (nm, dt.mean(), np.percentile(dt, 95)))
+            nxt = eb[2:, o] - eb[2:, o + 7]
+            print("      next counter seen +%5.0f ns after 'published' (p95 %5.0f)" % (nxt.mean(), np.percentile(nxt, 95)))
+
+
 def trace_diag():
     """cfg-2 training step: where the recurrent launches of the pipelined schedule sit in time (CUDA events on the
     launching streams, ms after the top of the forward / backward call) and how long each phase of the step takes."""
@@ -537,6 +582,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["ctc", "fbank"]
     if "ctc" in which:
         ctc_diag()
+    if "xchg2" in which:
+        xchg2_diag()
     if "fbank" in which:
         fbank_diag()
     if "tc" in which:
