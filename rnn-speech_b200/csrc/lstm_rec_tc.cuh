@@ -93,6 +93,10 @@ struct RecTcBwdArgs {
   unsigned long long drop_key;
   unsigned drop_sa, drop_thr_a, drop_sb, drop_thr_b;
   float drop_inv_a, drop_inv_b;
+  // 1: the caller has already filled this launch's rows of the dgates planes with the 0xFFFF pattern of the validated
+  // exchange (the pipelined schedule fills every launch's rows on a side stream at the head of the pass, so that the
+  // two 25 MB memsets do not stand between a launch and the event it waited for)
+  int prefilled;
 };
 int lstm_rec_tc_backward(const RecTcBwdGeom& g, const RecTcBwdArgs& a, cudaStream_t st);
 

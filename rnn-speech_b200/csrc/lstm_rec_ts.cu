@@ -2402,8 +2402,10 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
     if ((rc = tmap_stacked2_bf16(&tg2, a.dg_hi, (size_t)((const char*)a.dg_lo - (const char*)a.dg_hi), a.Ttot * g.B, 4 * g.H,
                                  4 * g.H, CHB, p.nkbs)) != RS_OK) return rc;
     // the launch's own rows of the dgates planes carry the fill pattern until their producers overwrite it
-    RS_CHECK_CUDA(cudaMemsetAsync(a.dg_hi + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
-    RS_CHECK_CUDA(cudaMemsetAsync(a.dg_lo + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
+    if (!a.prefilled) {
+      RS_CHECK_CUDA(cudaMemsetAsync(a.dg_hi + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
+      RS_CHECK_CUDA(cudaMemsetAsync(a.dg_lo + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
+    }
     { const char* v = getenv("RS_TS_FAULT"); p.fault = (a.dbg && v && v[0] == '1') ? 1 : 0; }
     static const int turns_env = [] { const char* v = getenv("RS_TS_TURNS_BWD"); return v ? atoi(v) : 1; }();
     p.turns = turns_env;
@@ -2444,8 +2446,10 @@ int lstm_rec_ts_backward(const RecTcGeom& g, const RecTcBwdArgs& a_in, cudaStrea
   const char* fault_env = getenv("RS_TS_FAULT");
   if (x3 && (xchg_env || (a.dbg && fault_env && fault_env[0] == '1')) && p.variant == kDefaultVariant) {
     // the launch's own rows of the dgates planes carry the fill pattern until their producers overwrite it
-    RS_CHECK_CUDA(cudaMemsetAsync(a.dg_hi + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
-    RS_CHECK_CUDA(cudaMemsetAsync(a.dg_lo + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
+    if (!a.prefilled) {
+      RS_CHECK_CUDA(cudaMemsetAsync(a.dg_hi + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
+      RS_CHECK_CUDA(cudaMemsetAsync(a.dg_lo + (size_t)a.t0 * g.B * 4 * g.H, 0xff, (size_t)a.T * g.B * 4 * g.H * sizeof(__nv_bfloat16), st));
+    }
     { const char* v = getenv("RS_TS_FAULT"); p.fault = (a.dbg && v && v[0] == '1' && g.Bpad <= 32) ? 1 : 0; }
     const bool fast3 = g.Bpad == 32 && g.H == 768 && nlo_t == p.nkbs;
     const int s3 = device_slot() * 4 + (a.dbg ? (fast3 ? 3 : 2) : fast3 ? 1 : 0);

@@ -732,6 +732,24 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
   }
 
   std::vector<cudaEvent_t> e_rec((size_t)L * NC), e_dx((size_t)L * NC), done;
+  // The validated exchange of the two-chain backward kernel (batches of 17 .. 32 rows, both weight planes) wants a launch's
+  // rows of the dgates planes filled with its 0xFFFF pattern: two 25 MB memsets per launch at cfg-2, which used to sit on
+  // the launch's stream between the event it waited for and the kernel.  They all go to the low-priority stream at the
+  // head of the pass instead, in the order the launches need them.  RS_TC_PREFILL=0: the launches fill for themselves.
+  static const bool prefill_env = [] { const char* v = getenv("RS_TC_PREFILL"); return !(v && v[0] == '0'); }();
+  const bool prefill = prefill_env && am->tc.ts && NC > 1 && am->tc.Bpad == 32 && B > 16;
+  std::vector<cudaEvent_t> e_fill(prefill ? (size_t)L * NC : 0);
+  if (prefill) {
+    for (int d = 0; d < NC + L - 1; ++d)
+      for (int l = L - 1; l >= 0; --l) {
+        const int c = NC - 1 - (d - (L - 1 - l));
+        if (c < 0 || c >= NC) continue;
+        const size_t off = (size_t)sc.start[c] * B * 4 * H, n = (size_t)(sc.start[c + 1] - sc.start[c]) * B * 4 * H;
+        RS_CHECK_CUDA(cudaMemsetAsync(bf.dg_hi[l] + off, 0xff, n * sizeof(bf16), am->tr_st));
+        RS_CHECK_CUDA(cudaMemsetAsync(bf.dg_lo[l] + off, 0xff, n * sizeof(bf16), am->tr_st));
+        RC(ev_record(am, &e_fill[(size_t)l * NC + c], am->tr_st));
+      }
+  }
   cudaEvent_t e_phase = nullptr;           // phase schedule: the dx burst before the current wave has finished
   // phase schedule: weight-gradient GEMMs as short-lived CTAs (one tile each) on the lowest-priority stream -- they fill
   // whatever SMs the waves leave idle (fill and drain of the wavefront, the 4 SMs beside three launches) and give
@@ -764,6 +782,7 @@ int am_tc_backward(rs_am* am, const float* params_d, const float* x_d, const int
       a.drop_sa = (uint32_t)(2 * l + 1); a.drop_thr_a = drop_out ? thr24(keep_out) : 0xffffffffu; a.drop_inv_a = 1.0f / keep_out;
       a.drop_sb = (uint32_t)(2 * (l + 1)); a.drop_thr_b = (!last && drop_in) ? thr24(keep_in) : 0xffffffffu; a.drop_inv_b = 1.0f / keep_in;
     }
+    if (prefill) { RS_CHECK_CUDA(cudaStreamWaitEvent(ls, e_fill[(size_t)l * NC + c], 0)); a.prefilled = 1; }
     a.dbg = (l == 0 && NC == 1) ? am->dbg_bwd : nullptr;
     {
       // RS_TC_DBG_LC="layer,chunk": the in-kernel timeline of ONE launch of the pipelined schedule (tests/gpu_diag.py xchg2)
