@@ -495,7 +495,8 @@ def run_train(args, name):
         f, nf = pending[0].result()
         # (the worker stages and copies at once; the feature kernels are enqueued in front of this step's forward pass,
         #  beside its head: RS_PREFETCH_GATE=0 leaves them to the worker thread, i.e. to wherever the device happens to be)
-        nxt = pending[0] = prefetch.submit(res[(i + 1) % NB]["sigs"], c["sr"], time_major=True, defer_features=gate_features)
+        nxt = pending[0] = prefetch.submit(res[(i + 1) % NB]["sigs"], c["sr"], time_major=True, defer_features=gate_features,
+                                            copy_after_current=gate_features and os.environ.get("RS_PREFETCH_COPY_GATE", "0") != "0")
         m.start_batch(None, True)
         x = f if r["T"] == c["Tmax"] or NB == 1 else f[:r["T"]]
         if gate_features:

@@ -288,8 +288,10 @@ class BatchPrefetcher(object):
             ev.record(self.stream)
         return feats, nframes, ev
 
-    def _work_stage(self, signals, sr):
+    def _work_stage(self, signals, sr, after=None):
         torch.cuda.set_device(self.device)
+        if after is not None:
+            self.stream.wait_event(after)          # the copy itself waits for this point of the caller's stream
         with torch.cuda.stream(self.stream):
             pcm_d, off_d, lens = self.audio_processor.stage_batch(signals, sr)
             ev = torch.cuda.Event()
@@ -304,11 +306,19 @@ class BatchPrefetcher(object):
             ev.record(self.stream)
         return feats, nframes, ev
 
-    def submit(self, signals, sr, time_major=True, defer_features=False):
+    def submit(self, signals, sr, time_major=True, defer_features=False, copy_after_current=False):
         """defer_features: the worker only stages and copies; the feature kernels are enqueued by
-        ticket.launch_features() (or by ticket.result(), whichever comes first)."""
+        ticket.launch_features() (or by ticket.result(), whichever comes first).
+        copy_after_current (with defer_features): the host-to-device copy waits for everything the calling stream holds
+        at this moment (a caller that runs ahead of the device submits while the previous step's backward pass is still
+        running).  Measured at cfg-2 (profiles/r02d_sweep11.log): the 20 MB copy costs the pass it lands in ~0.4 ms
+        either way -- backward 8.5 -> 8.9 ms without the gate, forward 5.0 -> 5.4 ms with it -- so it is off by default."""
         if defer_features:
-            return BatchPrefetcher._Ticket(self._pool.submit(self._work_stage, signals, sr), self, (sr, time_major))
+            after = None
+            if copy_after_current:
+                after = torch.cuda.Event()
+                after.record(torch.cuda.current_stream(self.device))
+            return BatchPrefetcher._Ticket(self._pool.submit(self._work_stage, signals, sr, after), self, (sr, time_major))
         return BatchPrefetcher._Ticket(self._pool.submit(self._work, signals, sr, time_major))
 
     def submit_files(self, file_names, time_major=True):
