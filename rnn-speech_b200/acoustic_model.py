@@ -810,6 +810,13 @@ class AcousticModel(object):
         ids, out_len = self.infer_pcm_device(audio_processor, pcm_d, off_d, len(signals), max(lens), sr, decoder=decoder)
         return ids.cpu().numpy(), out_len.cpu().numpy()
 
+    def infer_ticket(self, audio_processor, ticket, sr, decoder="greedy"):
+        """infer_signals for a batch that BatchPrefetcher.submit(signals, sr, defer_features=True) has already staged and
+        copied on its own thread and stream: the staging and the copy of the next batch overlap this batch's kernels."""
+        pcm_d, off_d, lens = ticket.staged()
+        ids, out_len = self.infer_pcm_device(audio_processor, pcm_d, off_d, len(lens), max(lens), sr, decoder=decoder)
+        return ids.cpu().numpy(), out_len.cpu().numpy()
+
     # ------------------------------------------------------------- datasets
     @staticmethod
     def build_dataset(input_set, batch_size, max_input_seq_length, max_target_seq_length,

@@ -261,6 +261,16 @@ class BatchPrefetcher(object):
                 ev.record(own.stream)
             self._out = (feats, nframes, ev)
 
+        def staged(self):
+            """Deferred ticket: the staged PCM itself -- (pcm_d float32 [sum n], offsets_d int64 [B + 1], lengths) --
+            with the calling stream ordered behind the host-to-device copy (AcousticModel.infer_ticket)."""
+            pcm_d, off_d, lens, h2d_ev = self._future.result()
+            cur = torch.cuda.current_stream(pcm_d.device)
+            cur.wait_event(h2d_ev)
+            pcm_d.record_stream(cur)
+            off_d.record_stream(cur)
+            return pcm_d, off_d, lens
+
         def result(self):
             if self._deferred is not None:
                 self.launch_features()

@@ -510,3 +510,15 @@ def test_infer_signals_matches_oracle_pipeline(pkg, cuda):
         assert np.all(ids[b, n[b]:] == -1)
     exact = _assert_ids_match(ids, n, want, lens, "infer_signals")
     assert exact >= B // 4
+    # the pipelined form (bench.py --config cfg5's throughput figure): the batch staged and copied by the prefetcher's
+    # thread and stream, the rest as above -- the same ids, bit for bit
+    pre = pkg.BatchPrefetcher(ap)
+    t1 = pre.submit(sigs, sr, defer_features=True)
+    t2 = pre.submit(sigs[::-1], sr, defer_features=True)
+    ids1, n1 = m.infer_ticket(ap, t1, sr)
+    ids2, n2 = m.infer_ticket(ap, t2, sr)
+    pre.close()
+    assert np.array_equal(ids1, ids) and np.array_equal(n1, n)
+    assert np.array_equal(n2, n[::-1])
+    for b in range(B):
+        assert np.array_equal(ids2[b, :n2[b]], ids[B - 1 - b, :n[B - 1 - b]])

@@ -114,6 +114,35 @@ def test_step_protocol_accumulates_minibatches_and_epoch_end(pkg, cuda):
     assert abs(m.get_learning_rate() - lr * 0.33) < 1e-12
 
 
+def test_end_batch_early_read_equals_the_draining_read(pkg, cuda, monkeypatch):
+    """end_batch copies the accumulators from a side stream behind the CTC kernel and returns while the backward pass is
+    still running (RS_EARLY_READ, default) -- the losses, error rates, step counts and parameters of three accumulated
+    train steps must be those of the path that drains the device first (RS_EARLY_READ=0), bit for bit; the dataset
+    iterator's deferred feature kernels (launched by run_step in front of its forward pass) are part of both runs."""
+    import torch
+    L, H, F, C, B, Tmax = 2, 64, 120, 80, 4, 100
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RS_EARLY_READ", mode)
+        rng = np.random.default_rng(5)
+        items = _synthetic_set(rng, 16)
+        m = pkg.AcousticModel(L, H, B, Tmax, 600, F, False, C, device=cuda, seed=5)
+        m.create_training_rnn(0.8, 0.5, 1, 1e-3, 0.33, use_iterator=True)
+        m.initialize(None)
+        ds = pkg.AcousticModel.build_dataset(items, B, Tmax, 600, "fbank", pkg.ENGLISH_CHAR_MAP, device=cuda)
+        m.add_datasets_input(ds, ds)
+        res = [m.run_train_step(None, 2, 1.0, compute_error_rate=(k == 1)) for k in range(2)]
+        torch.cuda.synchronize()
+        out[mode] = (res, m.params.clone(), m.global_step)
+    (r1, p1, g1), (r0, p0, g0) = out["1"], out["0"]
+    assert g1 == g0 == 2
+    for a, b in zip(r1, r0):
+        assert a[2] == b[2] and a[3] == b[3]
+        assert np.array_equal(np.float32([a[0], a[1]]), np.float32([b[0], b[1]]), equal_nan=True), (a, b)
+        assert np.isfinite(a[0])
+    assert torch.equal(p1, p0)
+
+
 def test_loss_decreases_on_a_fixed_batch(pkg, cuda):
     L, H, F, C, B, Tmax = 2, 64, 120, 80, 4, 100
     rng = np.random.default_rng(3)
