@@ -532,9 +532,12 @@ def run_train(args, name):
     if os.environ.get("RS_BENCH_E2E_PHASES"):
         # diagnostic: the phases of the END-TO-END step and the gap between two steps (stderr)
         seq = []
-        for _ in range(6):
+        host_t = []
+        for _ in range(16):
             m._phase_events = []
+            t_h = time.perf_counter()
             step_e2e()
+            host_t.append((time.perf_counter() - t_h) * 1e3)
             seq.append(m._phase_events)
         torch.cuda.synchronize()
         m._phase_events = None
@@ -546,6 +549,11 @@ def run_train(args, name):
         sys.stderr.write("e2e phases (ms): %s; end -> next forward %.3f; step (forward mark to forward mark) %.3f\n" % (
             ", ".join("%s %.3f" % (k, float(np.median(v))) for k, v in ph.items()), float(np.median(gaps)),
             float(np.median([a[0][1].elapsed_time(b[0][1]) for a, b in zip(seq[1:-1], seq[2:])]))))
+        sys.stderr.write("e2e per step (ms, forward mark to forward mark): %s\n" % " ".join(
+            "%.2f" % a[0][1].elapsed_time(b[0][1]) for a, b in zip(seq[:-1], seq[1:])))
+        sys.stderr.write("e2e backward per step (ms): %s\n" % " ".join(
+            "%.2f" % dict((na, ea.elapsed_time(eb)) for (na, ea), (_, eb) in zip(ev[:-1], ev[1:]))["backward"] for ev in seq))
+        sys.stderr.write("e2e host time of the call chain per step (ms): %s\n" % " ".join("%.2f" % t for t in host_t))
     # ---- per-family rooflines: phases of a step from CUDA events on the launching stream (every rank runs the steps:
     # the all-reduce is a collective), features alone on their stream
     fam_ms = {}
