@@ -610,9 +610,13 @@ def run_train(args, name):
         "config": {"workload": c["workload"], "global_batch": c["B"] * world, "parallelism": "dp%d" % world,
                    "arithmetic": arithmetic_note(tc),
                    "schedule": "time chunks (forward 96 steps: the layers of a wave side by side, chunk GEMMs as bursts between "
-                               "waves, layer 0's input GEMMs of later chunks beside the first waves; backward %s steps: 2 "
-                               "recurrent launches in flight, the dx GEMMs between layers ahead of the weight-gradient GEMMs "
-                               "on the remaining SMs)" % os.environ.get("RS_TC_CHUNK", "128"),
+                               "waves, layer 0's input GEMMs of later chunks beside the first waves; backward %s, the dx "
+                               "GEMMs between layers ahead of the weight-gradient GEMMs on the remaining SMs, the fill "
+                               "patterns of the exchanged planes written at the head of the pass); weight planes packed once "
+                               "per optimizer step, beside the input dense"
+                               % ("%s steps: 2 recurrent launches in flight" % os.environ.get("RS_TC_CHUNK", "128")
+                                  if 2 * (c["H"] // 16) + 32 <= 148 else "256 steps: 1 recurrent launch in flight (two of "
+                                  "%d CTAs would leave the GEMMs fewer than 32 SMs)" % (c["H"] // 16)),
                    "l2": "per-step working set (activations > 2 GB, parameters x4) exceeds the 126 MB L2; no flush needed",
                    "train_tflop_per_step": 3.0 * fwd_fl * world / 1e12,
                    "audio_seconds_per_step": audio_seconds * world},

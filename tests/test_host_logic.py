@@ -144,6 +144,61 @@ def test_dataset_iteration_over_file_names_host_logic(pkg, monkeypatch):
     assert d1.shape[0] == 1 and list(d1[0]) == pkg.get_str_labels(pkg.ENGLISH_CHAR_MAP, "we")
 
 
+def test_dataset_defers_the_feature_kernels_of_in_memory_batches(pkg, monkeypatch):
+    """In-memory items: the iterator submits the NEXT mini-batch with defer_features=True (the worker stages and copies,
+    the feature kernels wait for launch_pending_features -- AcousticModel.run_step calls it in front of its forward pass --
+    or for the next iteration's result()), and launch_pending_features is a no-op for tickets without that method (file
+    batches) and when nothing is in flight.  Device work replaced by stand-ins."""
+    import torch
+    from rnn_speech_b200 import audioprocessor, dataset
+
+    log = []
+
+    class FakeTicket(object):
+        def __init__(self, k, n):
+            self.k, self.n, self.launched = k, n, 0
+
+        def launch_features(self):
+            self.launched += 1
+            log.append(("launch", self.k))
+
+        def result(self):
+            log.append(("result", self.k))
+            return torch.zeros((20, self.n, 120)), torch.full((self.n,), 12, dtype=torch.int32)
+
+    class FakePrefetcher(object):
+        def __init__(self, audio_processor):
+            self.count = 0
+
+        def submit(self, signals, sr, time_major=True, defer_features=False):
+            assert defer_features and time_major and sr == 16000
+            self.count += 1
+            log.append(("submit", self.count))
+            return FakeTicket(self.count, len(signals))
+
+        def close(self):
+            log.append("closed")
+
+    monkeypatch.setattr(audioprocessor, "BatchPrefetcher", FakePrefetcher)
+    sig = np.zeros(1600, np.float32)
+    items = [[(sig, 16000), [1, 2, 3]] for _ in range(5)]
+    ds = dataset.AudioBatchDataset(items, 2, 20, 600, "fbank", pkg.ENGLISH_CHAR_MAP)
+    ds.launch_pending_features()                              # nothing in flight yet
+    it = iter(ds)
+    next(it)
+    assert log == [("submit", 1), ("submit", 2), ("result", 1)]
+    ds.launch_pending_features()                              # run_step, in front of the forward pass of batch 1
+    assert log[-1] == ("launch", 2)
+    next(it)
+    assert log[-2:] == [("submit", 3), ("result", 2)]
+    f, l, d = next(it)                                        # last batch: one real item, padded; nothing left in flight
+    assert list(l) == [12, 0] and d.shape == (1, 3)
+    n = len(log)
+    ds.launch_pending_features()
+    assert len(log) == n
+    assert list(it) == [] and log[-1] == "closed"
+
+
 def test_evaluate_full_host_logic_with_file_batches(pkg, monkeypatch):
     """evaluate_full (models/AcousticModel.py:723-777): files are featurised batch_size at a time, too-long samples
     are skipped, the last batch is padded with empty items, WER / CER are averaged in percent.  Device work is
