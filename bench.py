@@ -41,6 +41,9 @@ if _is_reference_arm(sys.argv):
     for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
         os.environ[_k] = str(_host_threads())
 
+# (the package sets this at import too; here it is certain to precede the CUDA context: see rnn-speech_b200/__init__.py)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import argparse          # noqa: E402
 import json              # noqa: E402
 import subprocess        # noqa: E402
