@@ -698,7 +698,9 @@ def run_infer(args, name):
     m = rs.AcousticModel(c["L"], c["H"], c["B"], c["Tmax"], 600, c["F"], False, c["C"], device=dev, seed=0)
     m.create_forward_rnn()
     m.initialize(None)
-    m.enable_timing()
+    events_everywhere = bool(os.environ.get("RS_BENCH_TIMED_EVENTS"))    # (see run_train: the roofline's events get their
+    if events_everywhere:                                                 #  own timed region)
+        m.enable_timing()
     launch_count = rs._lib.raw("rs_launch_count")
     T = min(c["Tmax"], ap.num_frames(n, c["sr"]))
     pcm_d = torch.from_numpy(np.concatenate(sigs)).to(dev)
@@ -721,7 +723,6 @@ def run_infer(args, name):
     if rank == 0:
         sampler.start()
     ms, launches = h.timed(step_resident, args.steps, launch_count)
-    roofline = recurrent_roofline(h, m, c, T, ms / args.steps, (0,), None) if rank == 0 else None
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(max(3, args.warmup)):
         step_e2e()
@@ -743,6 +744,17 @@ def run_infer(args, name):
     ms_e2e, _ = h.timed(step_pipelined, args.steps)
     pend[0].staged()
     prefetch.close()
+    # ---- the roofline's region: the same K resident steps with CUDA events around every recurrent launch
+    m.enable_timing()
+    for _ in range(2):
+        step_resident()
+    ms_instr, _ = h.timed(step_resident, args.steps)
+    roofline = recurrent_roofline(h, m, c, T, ms_instr / args.steps, (0,), None) if rank == 0 else None
+    if roofline is not None:
+        roofline["instrumented_ms_per_step"] = ms_instr / args.steps
+        roofline["measured_over"] = ("a second timed region of the same %d resident steps with CUDA events on the launching "
+                                     "streams around every recurrent launch; `value` is the region without them"
+                                     % args.steps) if not events_everywhere else "the timed region of `value` (RS_BENCH_TIMED_EVENTS=1)"
     clips = c["B"] * world * args.steps
     if rank != 0:
         return
