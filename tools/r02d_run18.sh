@@ -1,5 +1,8 @@
 #!/bin/bash
 # round 2 (fourth session), GPU call 18: what the CUDA events around every recurrent launch (the roofline's measurement) cost
+# (run against the bench.py of that commit, where RS_BENCH_NO_TIMING=1 left the events out; since the next commit the
+#  events have a timed region of their own and RS_BENCH_TIMED_EVENTS=1 puts them back into every region: the same A/B is
+#  `RS_BENCH_TIMED_EVENTS=1 python bench.py` against `python bench.py`)
 mkdir -p gpurun_out
 bench() { timeout 400 python bench.py --no-cpu-baseline --steps 20 --warmup 5 "$@" 2>gpurun_out/last.err | tail -1 > gpurun_out/last.json; python - <<'PY'
 import json
